@@ -1,0 +1,157 @@
+/* mpnn_b200.h -- C ABI of libmpnn_b200.so: hochshi/mpnn's message-passing hot path on B200 (sm_100a).
+ *
+ * The reference has no native code and no FFI: its hot path is a set of PyTorch nn.Modules
+ * (mpnn_functions/..., models/mask_batch_norm.py) that call aten ops.  This ABI is the boundary a
+ * maintainer binds those modules' forward/backward to (INTEGRATION.md shows the ctypes stubs); each entry
+ * point below cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to contiguous row-major fp32 (float) or int32 (int) data, except the
+ *    `float* const*` weight-pointer arrays, which are HOST arrays of device pointers;
+ *  - the caller owns all memory (inputs, outputs, saved-for-backward buffers, workspaces); the library never
+ *    allocates device memory and keeps no global mutable state beyond a thread-local error string;
+ *  - every call only enqueues work on `stream` and returns; it never synchronises;
+ *  - return value 0 = success, < 0 = error (text via mpnn_last_error()); nothing aborts or exits;
+ *  - gradients are WRITTEN (not accumulated) unless stated otherwise;
+ *  - all reductions have a fixed order: results are bit-reproducible run to run.
+ *  - `*_workspace_bytes` give the scratch size for BOTH the _fwd and _bwd call of an op.
+ */
+#ifndef MPNN_B200_H
+#define MPNN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mpnn_stream_t; /* == cudaStream_t */
+
+#define MPNN_OK 0
+#define MPNN_ERR_ARG -1
+#define MPNN_ERR_UNSUPPORTED -2
+#define MPNN_ERR_CUDA -3
+#define MPNN_ERR_WORKSPACE -4
+
+int mpnn_version(void);            /* major*10000 + minor*100 + patch */
+const char* mpnn_last_error(void); /* thread-local, valid until the next failing call on this thread */
+
+/* ---- generic building blocks ------------------------------------------------------------------------ */
+/* out[r,:] (+)= scale * sum_{k in ptr[r]:ptr[r+1]} src[idx ? idx[k] : k, :]   (CSR/CSC gather-sum) */
+int mpnn_segment_sum(const float* src, const int* ptr, const int* idx, int rows, int width, long long lds, float* out,
+                     long long ldo, int accumulate, float scale, mpnn_stream_t stream);
+size_t mpnn_colsum_workspace_bytes(long long rows, int width);
+/* out[c] (+)= sum_r X[r,c] * (Y ? Y[r,c] : 1) */
+int mpnn_colsum(const float* X, const float* Y, long long rows, int width, long long ldx, long long ldy, float* out,
+                int accumulate, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+size_t mpnn_gemm_workspace_bytes(int M, int N, int K);
+/* C[m,n] = sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]); flags: 1 = ReLU, 2 = accumulate into C.
+ * Replaces the small aten::mm/addmm calls of the path (gru_update.py:27-28, graph_level_output.py:36,
+ * set2vec.py:69-72,128, the growth layers of edge_network.py:15-19). */
+int mpnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, long long sam, long long sak,
+              long long sbk, long long sbn, long long ldc, const float* bias, int flags, void* workspace,
+              size_t workspace_bytes, mpnn_stream_t stream);
+
+/* ---- a0: padded batch -> edge list (layout produced by pre_process/data_loader.py:50-70) -------------- */
+size_t mpnn_compact_workspace_bytes(int B, int N);
+/* Pass 1: edge predicate (adj != 0 or any bfm != 0; adj may be NULL), per-row / per-column counts and their
+ * exclusive scans.  row_ptr[B*N] (device) = number of edges E.  Order = torch.nonzero order (bit-exact). */
+int mpnn_compact_count(const float* bfm, const float* adj, int B, int N, int ef, int* row_ptr, int* col_ptr,
+                       void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* Pass 2: edge_src/edge_dst (flat node ids), edge_w (adj value), edge_x [capacity(+1), ef] bond rows,
+ * csc_eid (edge ids grouped by sender).  `workspace` must be the buffer pass 1 filled. */
+int mpnn_compact_fill(const float* bfm, const float* adj, int B, int N, int ef, const int* row_ptr, const int* col_ptr,
+                      int capacity, int* edge_src, int* edge_dst, float* edge_w, float* edge_x, int* csc_eid,
+                      const void* workspace, mpnn_stream_t stream);
+/* backward of the bond-row gather: dense[b,i,j,:] = d_edge_x[e,:] (dense is pre-zeroed by the caller) */
+int mpnn_scatter_edge_rows(const float* d_edge_x, const int* edge_dst, const int* edge_src, int E, int N, int ef,
+                           float* dense, mpnn_stream_t stream);
+
+/* ---- a1/a2: edge-network trunk = edge_map[:-1] (edge_network.py:14-21,36-37) on compacted rows -------- */
+long long mpnn_edge_trunk_saved_floats(int R, int ef, int n_growth, int P, int n_tied, long long* x_offset, int* ldx);
+size_t mpnn_edge_trunk_workspace_bytes(int R, int ef, int n_growth, int P);
+/* growth_w[g] [in^2, in], growth_b[g] [in^2] (nn.Linear layout), w_tied [P, P]; x = saved + *x_offset, [R, *ldx] */
+int mpnn_edge_trunk_fwd(const float* rows_in, int R, int ef, int n_growth, const float* const* growth_w,
+                        const float* const* growth_b, const float* w_tied, int P, int n_tied, float* saved,
+                        void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_edge_trunk_bwd(const float* rows_in, int R, int ef, int n_growth, const float* const* growth_w,
+                        const float* w_tied, int P, int n_tied, const float* saved, const float* dx, int lddx,
+                        float* const* d_growth_w, float* const* d_growth_b, float* d_w_tied, float* d_rows_in,
+                        void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
+/* ---- a3/a3'/a5-a7: message function fused with the neighbour aggregation ---------------------------------
+ * (edge_network.py:42-52 + adjacent_message_agg.py:18 / weighted_adjacent_message_agg.py:20 /
+ *  attention_message_agg.py:24).  See mpnn_b200/csrc/message.cu for the algebra. */
+long long mpnn_message_wt_floats(int nf, int mf, int P);
+/* Wt <- transposed + bias-augmented copy of edge_map[-1] (W_last [mf*nf, P], B_last [mf*nf]) */
+int mpnn_message_prepare(const float* W_last, const float* B_last, int nf, int mf, int P, float* Wt,
+                         mpnn_stream_t stream);
+int mpnn_message_fwd(const int* row_ptr, const int* edge_dst, const int* gidx, const int* xid, const float* alpha,
+                     const float* X, int ldx, int x0_row, const float* Gsrc, int ldg, const float* Q, const float* Wt,
+                     const float* beta, int nrows, int nf, int mf, int P, float* M, mpnn_stream_t stream);
+size_t mpnn_message_bwd_workspace_bytes(int nrows, int nf, int mf, int P);
+int mpnn_message_bwd(const int* row_ptr, const int* edge_dst, const int* gidx, const int* xid, const float* alpha,
+                     const float* X, int ldx, int x0_row, const float* Gsrc, int ldg, const float* Q, const float* Wt,
+                     const float* beta, int nrows, int n_edges, int nf, int mf, int P, const float* dM, float* T,
+                     int ldt, float* dG, float* dQ, float* dalpha, float* dW_last, float* dB_last, float* dbeta,
+                     void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
+/* ---- a4: attention gate of AttEdgeNetwork (att_edge_network.py:18-26) / row softmax -------------------- */
+int mpnn_softmax_mul_fwd(const float* logits, const float* V, long long rows, int n, float* gate, float* out,
+                         mpnn_stream_t stream);
+int mpnn_softmax_mul_bwd(const float* gate, const float* V, const float* dout, long long rows, int n, float* dlogits,
+                         float* dV, mpnn_stream_t stream);
+
+/* ---- a5-a7 on dense [B,N,N,mf] messages (the aggregators' stand-alone contract) ------------------------ */
+int mpnn_dense_agg_fwd(const float* messages, const float* weights, long long R, int N, int mf, float* out,
+                       mpnn_stream_t stream);
+int mpnn_dense_agg_bwd(const float* messages, const float* weights, const float* dout, long long R, int N, int mf,
+                       float* dmessages, float* dweights, mpnn_stream_t stream);
+
+/* ---- a8/a9: masked GRU update (gru_update.py:26-35,66-68); gates [rows, 4d] saved for backward --------- */
+size_t mpnn_gru_workspace_bytes(long long rows, int d);
+int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                 const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
+                 void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                 const float* gates, const float* dh_out, long long rows, int d, float* dm, float* dh, float* dW_ih,
+                 float* dW_hh, float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes,
+                 mpnn_stream_t stream);
+
+/* ---- a10/a11: masked batch norms (models/mask_batch_norm.py:9-15, 20-38); stats [2C+1] saved ------------ */
+size_t mpnn_bn_workspace_bytes(long long rows, int C);
+int mpnn_mask_bn_fwd(const float* x, const float* mask, long long rows, int C, float eps, float* y, float* stats,
+                     void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_mask_bn_bwd(const float* x, const float* mask, const float* dy, const float* stats, long long rows, int C,
+                     float* dx, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_mask_bn1d_fwd(const float* x, const float* mask, const float* weight, const float* bias, float* running_mean,
+                       float* running_var, long long rows, int C, int training, float momentum, float eps, float* y,
+                       float* stats, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_mask_bn1d_bwd(const float* x, const float* mask, const float* dy, const float* weight, const float* stats,
+                       const float* running_mean, const float* running_var, long long rows, int C, int training,
+                       float eps, float* dx, float* dweight, float* dbias, void* workspace, size_t workspace_bytes,
+                       mpnn_stream_t stream);
+
+/* ---- a12: GraphLevelOutput (readout/graph_level_output.py:30-47); mask NULL = the unmasked branch (:39) - */
+size_t mpnn_glo_workspace_bytes(int B, int N, int F2, int O);
+int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float* bi, const float* Wj, const float* bj,
+                 int B, int N, int F2, int O, float* out, float* u, float* v, float* UV, mpnn_stream_t stream);
+int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float* Wj, const float* u, const float* v,
+                 const float* UV, const float* dout, int B, int N, int F2, int O, float* dx, float* dWi, float* dbi,
+                 float* dWj, float* dbj, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
+/* ---- a13/a14: Set2Vec with its input-less LSTM (readout/set2vec.py:68-75, 93-151) ----------------------- */
+long long mpnn_set2vec_saved_floats(int B, int N, int F, int steps);
+size_t mpnn_set2vec_workspace_bytes(int B, int N, int F);
+int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
+                     const float* we, int B, int N, int F, int steps, float* out, float* saved, void* workspace,
+                     size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const float* Wq, const float* we,
+                     const float* saved, const float* dout, int B, int N, int F, int steps, float* dX, float* dWcat,
+                     float* dbcat, float* dWq, float* dwe, void* workspace, size_t workspace_bytes,
+                     mpnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPNN_B200_H */

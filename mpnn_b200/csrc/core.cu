@@ -1,0 +1,133 @@
+// Library-wide state: thread-local error string, version, device properties, small utility kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mpnn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int mpnn_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;  // B200
+  }
+  return sms;
+}
+
+namespace {
+
+// out[r, :] = sum over k in [ptr[r], ptr[r+1]) of scale * src[idx[k] (or k), :]   (deterministic order)
+__global__ void k_segment_sum(const float* __restrict__ src, const int* __restrict__ ptr, const int* __restrict__ idx,
+                              int rows, int width, long long lds, float* __restrict__ out, long long ldo,
+                              int accumulate, float scale) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)rows * width) return;
+  int r = (int)(t / width), c = (int)(t - (long long)r * width);
+  float acc = 0.f;
+  int kb = ptr[r], ke = ptr[r + 1];
+  for (int k = kb; k < ke; ++k) {
+    int s = idx ? idx[k] : k;
+    acc += src[(long long)s * lds + c];
+  }
+  acc *= scale;
+  float* o = out + (long long)r * ldo + c;
+  *o = accumulate ? *o + acc : acc;
+}
+
+// two-stage deterministic column sums of X[rows, width] (optionally of X*Y elementwise)
+constexpr int CS_T = 256;
+__global__ void k_colsum_partial(const float* __restrict__ X, const float* __restrict__ Y, long long rows, int width,
+                                 long long ldx, long long ldy, int rows_per_block, float* __restrict__ partial) {
+  // thread -> column (tid % width), row lane (tid / width); blockDim is a multiple of width (or width > CS_T)
+  extern __shared__ float sm[];
+  int lanes = blockDim.x / width;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  int c = threadIdx.x % width, rl = threadIdx.x / width;
+  float acc = 0.f;
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      float v = X[r * ldx + c];
+      if (Y) v *= Y[r * ldy + c];
+      acc += v;
+    }
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sm[l * width + c];
+    partial[(size_t)blockIdx.x * width + c] = s;
+  }
+}
+__global__ void k_colsum_final(const float* __restrict__ partial, int nblk, int width, float* __restrict__ out,
+                               int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * width + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+}  // namespace
+
+static int colsum_blocks(long long rows, int* rows_per_block) {
+  int target = 2 * mpnn_num_sms();
+  long long rpb = (rows + target - 1) / target;
+  if (rpb < 64) rpb = 64;
+  *rows_per_block = (int)rpb;
+  return (int)((rows + rpb - 1) / rpb);
+}
+
+extern "C" {
+
+int mpnn_version(void) { return 100; }  // 0.1.0
+
+const char* mpnn_last_error(void) { return g_err; }
+
+int mpnn_segment_sum(const float* src, const int* ptr, const int* idx, int rows, int width, long long lds, float* out,
+                     long long ldo, int accumulate, float scale, cudaStream_t stream) {
+  MPNN_REQUIRE(rows >= 0 && width > 0, MPNN_ERR_ARG, "segment_sum: bad dims");
+  if (rows == 0) return MPNN_OK;
+  k_segment_sum<<<ceil_div((long long)rows * width, 256), 256, 0, stream>>>(src, ptr, idx, rows, width, lds, out, ldo,
+                                                                           accumulate, scale);
+  MPNN_CHECK_LAUNCH("k_segment_sum");
+  return MPNN_OK;
+}
+
+size_t mpnn_colsum_workspace_bytes(long long rows, int width) {
+  int rpb;
+  int nblk = colsum_blocks(rows, &rpb);
+  return (size_t)nblk * width * sizeof(float);
+}
+
+// out[c] (+)= sum_r X[r,c] * (Y ? Y[r,c] : 1)
+int mpnn_colsum(const float* X, const float* Y, long long rows, int width, long long ldx, long long ldy, float* out,
+                int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(rows >= 0 && width > 0, MPNN_ERR_ARG, "colsum: bad dims");
+  MPNN_REQUIRE(width <= 1024, MPNN_ERR_UNSUPPORTED, "colsum: width %d > 1024", width);
+  int rpb;
+  int nblk = colsum_blocks(rows, &rpb);
+  if (rows == 0) nblk = 0;
+  MPNN_REQUIRE(workspace_bytes >= (size_t)nblk * width * sizeof(float), MPNN_ERR_WORKSPACE, "colsum: workspace");
+  int threads = width >= CS_T ? width : (CS_T / width) * width;
+  if (nblk > 0) {
+    k_colsum_partial<<<nblk, threads, threads * sizeof(float), stream>>>(X, Y, rows, width, ldx, ldy, rpb,
+                                                                        (float*)workspace);
+    MPNN_CHECK_LAUNCH("k_colsum_partial");
+  }
+  k_colsum_final<<<ceil_div(width, 128), 128, 0, stream>>>((const float*)workspace, nblk, width, out, accumulate);
+  MPNN_CHECK_LAUNCH("k_colsum_final");
+  return MPNN_OK;
+}
+
+}  // extern "C"

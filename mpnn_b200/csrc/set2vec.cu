@@ -1,0 +1,310 @@
+// Set2Vec readout (reference mpnn_functions/readout/set2vec.py:93-151, inner_prod="default") with its
+// input-less LSTM cell (LSTMCellHidden, set2vec.py:68-75).  `steps` (default 100) strictly sequential
+// iterations; each one: LSTM gates from the previous [m | read] vector, a query, additive attention
+// energies over ALL B*N rows, a softmax across the whole batch (set2vec.py:139, dim=0), and the per-graph
+// read-out.  The whole loop (forward or backward-through-time) is ONE C call that enqueues every launch;
+// the host never synchronises.  Reductions have a fixed order (bit-reproducible).
+//
+// Wcat = [w_hi | w_hf | w_hg | w_ho] ([2F, 4F]), bcat likewise ([4F]); gate order i, f, g, o.
+// saved, per step: m [B,2F] | c [B,F] | gates [B,4F] (activated) | tanh(c) [B,F] | q [B,F] | att [B*N]
+#include "common.cuh"
+
+extern "C" int mpnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, long long sam, long long sak,
+                         long long sbk, long long sbn, long long ldc, const float* bias, int flags, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
+extern "C" size_t mpnn_gemm_workspace_bytes(int M, int N, int K);
+extern "C" int mpnn_colsum(const float* X, const float* Y, long long rows, int width, long long ldx, long long ldy,
+                           float* out, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
+
+namespace {
+
+constexpr float BIG_NEGATIVE = -1e8f;  // set2vec.py:10
+
+struct StepPtrs {
+  float *m, *c, *gates, *tc, *q, *att;
+};
+
+__host__ __device__ inline size_t step_stride(int B, int N, int F) { return (size_t)B * 9 * F + (size_t)B * N; }
+
+inline StepPtrs step_ptrs(float* saved, int s, int B, int N, int F) {
+  float* p = saved + (size_t)s * step_stride(B, N, F);
+  StepPtrs r;
+  r.m = p;
+  r.c = r.m + (size_t)B * 2 * F;
+  r.gates = r.c + (size_t)B * F;
+  r.tc = r.gates + (size_t)B * 4 * F;
+  r.q = r.tc + (size_t)B * F;
+  r.att = r.q + (size_t)B * F;
+  return r;
+}
+
+// pre [B,4F] -> activated gates, c', h' (written to m[:, :F])
+__global__ void k_lstm_fwd(const float* __restrict__ pre, const float* __restrict__ cprev, int B, int F,
+                           float* __restrict__ gates, float* __restrict__ c, float* __restrict__ tc,
+                           float* __restrict__ m) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * F) return;
+  int b = t / F, f = t - b * F;
+  const float* p = pre + (size_t)b * 4 * F;
+  float i = 1.f / (1.f + expf(-p[f]));
+  float fg = 1.f / (1.f + expf(-p[F + f]));
+  float g = tanhf(p[2 * F + f]);
+  float o = 1.f / (1.f + expf(-p[3 * F + f]));
+  float cp = cprev ? cprev[t] : 0.f;
+  float cn = fg * cp + i * g;
+  float th = tanhf(cn);
+  float* gs = gates + (size_t)b * 4 * F;
+  gs[f] = i;
+  gs[F + f] = fg;
+  gs[2 * F + f] = g;
+  gs[3 * F + f] = o;
+  c[t] = cn;
+  tc[t] = th;
+  m[(size_t)b * 2 * F + f] = o * th;
+}
+
+// e[r] = sum_f we[f] * tanh(q[b,f] + X[r,f]) + (1-mask[r]) * BIG_NEGATIVE.   One warp per row.
+__global__ void k_energy(const float* __restrict__ X, const float* __restrict__ q, const float* __restrict__ we,
+                         const float* __restrict__ mask, int rows, int N, int F, float* __restrict__ e) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int b = row / N;
+  float s = 0.f;
+  for (int f = lane; f < F; f += 32) s = fmaf(we[f], tanhf(q[(size_t)b * F + f] + X[(size_t)row * F + f]), s);
+  s = warp_sum(s);
+  if (lane == 0) e[row] = mask ? s + (1.f - mask[row]) * BIG_NEGATIVE : s;
+}
+
+__device__ float block_reduce_1024(float v, float* red, bool is_max) {
+  // fixed-order tree over 1024 threads
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      float a = red[threadIdx.x], b = red[threadIdx.x + o];
+      red[threadIdx.x] = is_max ? fmaxf(a, b) : a + b;
+    }
+    __syncthreads();
+  }
+  float r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// att = softmax(e) over all rows (single block of 1024 threads)
+__global__ void __launch_bounds__(1024) k_global_softmax(const float* __restrict__ e, int rows,
+                                                         float* __restrict__ att) {
+  __shared__ float red[1024];
+  float mx = -INFINITY;
+  for (int r = threadIdx.x; r < rows; r += 1024) mx = fmaxf(mx, e[r]);
+  mx = block_reduce_1024(mx, red, true);
+  float s = 0.f;
+  for (int r = threadIdx.x; r < rows; r += 1024) s += expf(e[r] - mx);
+  s = block_reduce_1024(s, red, false);
+  float inv = 1.f / s;
+  for (int r = threadIdx.x; r < rows; r += 1024) att[r] = expf(e[r] - mx) * inv;
+}
+
+// read[b,f] = sum_i att[b,i] X[b,i,f]  -> m[b, F+f]
+__global__ void k_read(const float* __restrict__ X, const float* __restrict__ att, int B, int N, int F,
+                       float* __restrict__ m) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * F) return;
+  int b = t / F, f = t - b * F;
+  float s = 0.f;
+  for (int i = 0; i < N; ++i) s = fmaf(att[(size_t)b * N + i], X[((size_t)b * N + i) * F + f], s);
+  m[(size_t)b * 2 * F + F + f] = s;
+}
+
+// ---- backward pieces ----
+// datt[r] = sum_f dm[b, F+f] * X[r,f]
+__global__ void k_datt(const float* __restrict__ X, const float* __restrict__ dm, int rows, int N, int F,
+                       float* __restrict__ datt) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  int b = row / N;
+  float s = 0.f;
+  for (int f = lane; f < F; f += 32) s = fmaf(dm[(size_t)b * 2 * F + F + f], X[(size_t)row * F + f], s);
+  s = warp_sum(s);
+  if (lane == 0) datt[row] = s;
+}
+// de[r] = att[r] * (datt[r] - sum att*datt)   (single block)
+__global__ void __launch_bounds__(1024) k_global_softmax_bwd(const float* __restrict__ att,
+                                                             const float* __restrict__ datt, int rows,
+                                                             float* __restrict__ de) {
+  __shared__ float red[1024];
+  float s = 0.f;
+  for (int r = threadIdx.x; r < rows; r += 1024) s = fmaf(att[r], datt[r], s);
+  s = block_reduce_1024(s, red, false);
+  for (int r = threadIdx.x; r < rows; r += 1024) de[r] = att[r] * (datt[r] - s);
+}
+// one block per graph, thread per feature (looped): dq[b,f], pw[b,f] (partial d we), dX += att*dread + dpre
+__global__ void k_energy_bwd(const float* __restrict__ X, const float* __restrict__ q, const float* __restrict__ we,
+                             const float* __restrict__ att, const float* __restrict__ de,
+                             const float* __restrict__ dm, int N, int F, float* __restrict__ dq,
+                             float* __restrict__ pw, float* __restrict__ dX) {
+  int b = blockIdx.x;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float qv = q[(size_t)b * F + f], w = we[f], dread = dm[(size_t)b * 2 * F + F + f];
+    float sq = 0.f, sw = 0.f;
+    for (int i = 0; i < N; ++i) {
+      size_t r = (size_t)b * N + i;
+      float th = tanhf(qv + X[r * F + f]);
+      float d = de[r];
+      float dpre = d * w * (1.f - th * th);
+      sq += dpre;
+      sw = fmaf(d, th, sw);
+      dX[r * F + f] += att[r] * dread + dpre;
+    }
+    dq[(size_t)b * F + f] = sq;
+    pw[(size_t)b * F + f] = sw;
+  }
+}
+// dh [B,F] (already = dq Wq + dm[:, :F]) and dc_next -> dpre [B,4F], dc_prev
+__global__ void k_lstm_bwd(const float* __restrict__ gates, const float* __restrict__ tc,
+                           const float* __restrict__ cprev, const float* __restrict__ dh, float* __restrict__ dc,
+                           int B, int F, float* __restrict__ dpre) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * F) return;
+  int b = t / F, f = t - b * F;
+  const float* gs = gates + (size_t)b * 4 * F;
+  float i = gs[f], fg = gs[F + f], g = gs[2 * F + f], o = gs[3 * F + f];
+  float th = tc[t];
+  float dhv = dh[t];
+  float dcn = dhv * o * (1.f - th * th) + dc[t];
+  float cp = cprev ? cprev[t] : 0.f;
+  float* dp = dpre + (size_t)b * 4 * F;
+  dp[f] = dcn * g * i * (1.f - i);
+  dp[F + f] = dcn * cp * fg * (1.f - fg);
+  dp[2 * F + f] = dcn * i * (1.f - g * g);
+  dp[3 * F + f] = dhv * th * o * (1.f - o);
+  dc[t] = dcn * fg;
+}
+__global__ void k_add_cols(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int rows,
+                           int cols) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * cols) return;
+  int r = t / cols, c = t - r * cols;
+  dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
+}
+
+}  // namespace
+
+extern "C" {
+
+long long mpnn_set2vec_saved_floats(int B, int N, int F, int steps) {
+  return (long long)steps * (long long)step_stride(B, N, F);
+}
+
+size_t mpnn_set2vec_workspace_bytes(int B, int N, int F) {
+  size_t rows = (size_t)B * N;
+  size_t fl = (size_t)B * 4 * F      // pre / dpre
+              + 3 * rows             // e / datt / de
+              + (size_t)B * 2 * F * 2  // dm ping-pong
+              + (size_t)B * F * 4;   // dc, dq, pw, dh
+  size_t g = mpnn_gemm_workspace_bytes(2 * F, 4 * F, B);
+  size_t c = mpnn_colsum_workspace_bytes(B, 4 * F);
+  return align_up(fl * sizeof(float), 256) + align_up(g > c ? g : c, 256) + 256;
+}
+
+int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
+                     const float* we, int B, int N, int F, int steps, float* out, float* saved, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && N > 0 && F > 0 && steps > 0, MPNN_ERR_ARG, "set2vec_fwd: bad dims");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_workspace_bytes(B, N, F), MPNN_ERR_WORKSPACE, "set2vec_fwd: workspace");
+  const int rows = B * N;
+  float* pre = (float*)workspace;
+  float* e = pre + (size_t)B * 4 * F;
+  for (int s = 0; s < steps; ++s) {
+    StepPtrs cur = step_ptrs(saved, s, B, N, F);
+    int rc;
+    if (s == 0) {
+      // m_prev = 0: pre-activations are just the biases
+      rc = mpnn_gemm(nullptr, nullptr, pre, B, 4 * F, 0, 0, 0, 0, 0, 4 * F, bcat, 0, nullptr, 0, stream);
+    } else {
+      StepPtrs prev = step_ptrs(saved, s - 1, B, N, F);
+      rc = mpnn_gemm(prev.m, Wcat, pre, B, 4 * F, 2 * F, 2 * F, 1, 4 * F, 1, 4 * F, bcat, 0, nullptr, 0, stream);
+    }
+    if (rc) return rc;
+    const float* cprev = s == 0 ? nullptr : step_ptrs(saved, s - 1, B, N, F).c;
+    k_lstm_fwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(pre, cprev, B, F, cur.gates, cur.c, cur.tc, cur.m);
+    // q = h Wq^T  (h = m[:, :F], row stride 2F; Wq is nn.Linear weight [F_out, F_in])
+    if ((rc = mpnn_gemm(cur.m, Wq, cur.q, B, F, F, 2 * F, 1, 1, F, F, nullptr, 0, nullptr, 0, stream))) return rc;
+    k_energy<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(X, cur.q, we, mask, rows, N, F, e);
+    k_global_softmax<<<1, 1024, 0, stream>>>(e, rows, cur.att);
+    k_read<<<ceil_div(B * F, 256), 256, 0, stream>>>(X, cur.att, B, N, F, cur.m);
+    MPNN_CHECK_LAUNCH("set2vec_fwd step");
+  }
+  StepPtrs last = step_ptrs(saved, steps - 1, B, N, F);
+  MPNN_CUDA(cudaMemcpyAsync(out, last.m, (size_t)B * 2 * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  return MPNN_OK;
+}
+
+// dWcat [2F,4F], dbcat [4F], dWq [F,F], dwe [F], dX [B,N,F] are written (zero-initialised here).
+int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const float* Wq, const float* we,
+                     const float* saved_c, const float* dout, int B, int N, int F, int steps, float* dX, float* dWcat,
+                     float* dbcat, float* dWq, float* dwe, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && N > 0 && F > 0 && steps > 0, MPNN_ERR_ARG, "set2vec_bwd: bad dims");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_workspace_bytes(B, N, F), MPNN_ERR_WORKSPACE, "set2vec_bwd: workspace");
+  (void)mask;
+  float* saved = const_cast<float*>(saved_c);
+  const int rows = B * N;
+  float* dpre = (float*)workspace;
+  float* datt = dpre + (size_t)B * 4 * F;
+  float* de = datt + rows;
+  float* spare = de + rows;
+  float* dmA = spare + rows;
+  float* dmB = dmA + (size_t)B * 2 * F;
+  float* dc = dmB + (size_t)B * 2 * F;
+  float* dq = dc + (size_t)B * F;
+  float* pw = dq + (size_t)B * F;
+  float* dh = pw + (size_t)B * F;
+  char* sub = (char*)workspace + align_up(((size_t)B * 4 * F + 3 * (size_t)rows + (size_t)B * 2 * F * 2 +
+                                           (size_t)B * F * 4) * sizeof(float), 256);
+  size_t sub_bytes = workspace_bytes - (size_t)(sub - (char*)workspace);
+  MPNN_CUDA(cudaMemsetAsync(dX, 0, (size_t)rows * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(dWcat, 0, (size_t)2 * F * 4 * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(dbcat, 0, (size_t)4 * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(dWq, 0, (size_t)F * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(dwe, 0, (size_t)F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemcpyAsync(dmA, dout, (size_t)B * 2 * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  float* dm = dmA;
+  float* dm_prev = dmB;
+  for (int s = steps - 1; s >= 0; --s) {
+    StepPtrs cur = step_ptrs(saved, s, B, N, F);
+    int rc;
+    k_datt<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(X, dm, rows, N, F, datt);
+    k_global_softmax_bwd<<<1, 1024, 0, stream>>>(cur.att, datt, rows, de);
+    k_energy_bwd<<<B, 128, 0, stream>>>(X, cur.q, we, cur.att, de, dm, N, F, dq, pw, dX);
+    MPNN_CHECK_LAUNCH("set2vec_bwd energy");
+    if ((rc = mpnn_colsum(pw, nullptr, B, F, F, 0, dwe, 1, sub, sub_bytes, stream))) return rc;
+    // dh = dq Wq + dm[:, :F]
+    if ((rc = mpnn_gemm(dq, Wq, dh, B, F, F, F, 1, F, 1, F, nullptr, 0, nullptr, 0, stream))) return rc;
+    k_add_cols<<<ceil_div(B * F, 256), 256, 0, stream>>>(dh, F, dm, 2 * F, B, F);
+    // dWq += dq^T h
+    if ((rc = mpnn_gemm(dq, cur.m, dWq, F, F, B, 1, F, 2 * F, 1, F, nullptr, 2, sub, sub_bytes, stream))) return rc;
+    const float* cprev = s == 0 ? nullptr : step_ptrs(saved, s - 1, B, N, F).c;
+    k_lstm_bwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(cur.gates, cur.tc, cprev, dh, dc, B, F, dpre);
+    MPNN_CHECK_LAUNCH("set2vec_bwd lstm");
+    if ((rc = mpnn_colsum(dpre, nullptr, B, 4 * F, 4 * F, 0, dbcat, 1, sub, sub_bytes, stream))) return rc;
+    if (s > 0) {
+      StepPtrs prev = step_ptrs(saved, s - 1, B, N, F);
+      // dWcat += m_prev^T dpre ; dm_prev = dpre Wcat^T
+      if ((rc = mpnn_gemm(prev.m, dpre, dWcat, 2 * F, 4 * F, B, 1, 2 * F, 4 * F, 1, 4 * F, nullptr, 2, sub, sub_bytes,
+                          stream)))
+        return rc;
+      if ((rc = mpnn_gemm(dpre, Wcat, dm_prev, B, 2 * F, 4 * F, 4 * F, 1, 1, 4 * F, 2 * F, nullptr, 0, nullptr, 0,
+                          stream)))
+        return rc;
+      float* t = dm;
+      dm = dm_prev;
+      dm_prev = t;
+    }
+  }
+  return MPNN_OK;
+}
+
+}  // extern "C"

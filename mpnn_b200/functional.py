@@ -1,0 +1,517 @@
+"""torch.autograd glue over the C-ABI kernels.  PyTorch is used for device memory, streams and the autograd
+tape only; every forward and backward below is a call into libmpnn_b200.so.  No CPU path exists."""
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import check, f32c, ptr, ptr_array, stream, workspace
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mpnn_b200: CUDA tensors required (no CPU fallback); got %s" % t.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge-network trunk  (reference edge_network.py:14-21 minus the last Linear)
+# ------------------------------------------------------------------------------------------------
+class EdgeTrunkFn(torch.autograd.Function):
+    """x = trunk(rows): rows [R, ef] -> x [R, PP] (PP = P rounded up to 4, pad columns are zero)."""
+
+    @staticmethod
+    def forward(ctx, rows, w_tied, n_tied, *growth):
+        lib = _lib.load()
+        _need_cuda(rows, w_tied)
+        rows = f32c(rows)
+        w_tied = f32c(w_tied)
+        G = len(growth) // 2
+        gw = [f32c(t) for t in growth[:G]]
+        gb = [f32c(t) for t in growth[G:]]
+        R, ef = rows.shape
+        P = w_tied.shape[0]
+        x_off = ctypes.c_longlong(0)
+        ldx = ctypes.c_int(0)
+        total = lib.mpnn_edge_trunk_saved_floats(R, ef, G, P, n_tied, ctypes.byref(x_off), ctypes.byref(ldx))
+        if total < 0:
+            raise RuntimeError("mpnn_b200: inconsistent edge_map layer plan (ef=%d, growth=%d, P=%d)" % (ef, G, P))
+        saved = torch.empty(total, dtype=torch.float32, device=rows.device)
+        ws = workspace(lib.mpnn_edge_trunk_workspace_bytes(R, ef, G, P), rows.device)
+        check(lib.mpnn_edge_trunk_fwd(ptr(rows), R, ef, G, ptr_array(gw), ptr_array(gb), ptr(w_tied), P, n_tied,
+                                      ptr(saved), ptr(ws), ws.numel(), stream()), "edge_trunk_fwd")
+        PP = ldx.value
+        x = saved[x_off.value:x_off.value + R * PP].view(R, PP)
+        ctx.save_for_backward(rows, w_tied, saved, *gw)
+        ctx.dims = (R, ef, G, P, n_tied, PP)
+        return x
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dx):
+        lib = _lib.load()
+        rows, w_tied, saved = ctx.saved_tensors[:3]
+        gw = list(ctx.saved_tensors[3:])
+        R, ef, G, P, n_tied, PP = ctx.dims
+        if not (dx.dim() == 2 and dx.stride(1) == 1 and dx.stride(0) >= P and dx.dtype == torch.float32):
+            dx = dx.contiguous().float()
+        lddx = dx.stride(0)
+        dev = rows.device
+        d_w_tied = torch.empty_like(w_tied)
+        d_gw = [torch.empty_like(w) for w in gw]
+        d_gb = [torch.empty(w.shape[0], dtype=torch.float32, device=dev) for w in gw]
+        d_rows = torch.empty_like(rows) if ctx.needs_input_grad[0] else None
+        ws = workspace(lib.mpnn_edge_trunk_workspace_bytes(R, ef, G, P), dev)
+        check(lib.mpnn_edge_trunk_bwd(ptr(rows), R, ef, G, ptr_array(gw), ptr(w_tied), P, n_tied, ptr(saved),
+                                      ctypes.c_void_p(dx.data_ptr()), lddx, ptr_array(d_gw), ptr_array(d_gb),
+                                      ptr(d_w_tied), ptr(d_rows), ptr(ws), ws.numel(), stream()), "edge_trunk_bwd")
+        return (d_rows, d_w_tied, None) + tuple(d_gw) + tuple(d_gb)
+
+
+# ------------------------------------------------------------------------------------------------
+# gather-sum over an index list (CSR one way, CSC the other) -- deterministic, scatter-free both ways
+# ------------------------------------------------------------------------------------------------
+class GatherSumFn(torch.autograd.Function):
+    """out[r,:] = sum_{k in ptr[r]:ptr[r+1]} src[idx[k],:]  (idx None -> k);  backward uses the transposed lists."""
+
+    @staticmethod
+    def forward(ctx, src, ptr_t, idx, n_out, t_ptr, t_idx):
+        lib = _lib.load()
+        _need_cuda(src)
+        src = f32c(src)
+        width = src.shape[1]
+        out = torch.empty(n_out, width, dtype=torch.float32, device=src.device)
+        check(lib.mpnn_segment_sum(ptr(src), ptr(ptr_t), ptr(idx), n_out, width, width, ptr(out), width, 0, 1.0,
+                                   stream()), "segment_sum")
+        ctx.t = (t_ptr, t_idx, src.shape[0], width)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        t_ptr, t_idx, n_src, width = ctx.t
+        dout = f32c(dout)
+        dsrc = torch.empty(n_src, width, dtype=torch.float32, device=dout.device)
+        check(lib.mpnn_segment_sum(ptr(dout), ptr(t_ptr), ptr(t_idx), n_src, width, width, ptr(dsrc), width, 0, 1.0,
+                                   stream()), "segment_sum")
+        return dsrc, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# fused message + aggregation
+# ------------------------------------------------------------------------------------------------
+class EdgeMessageFn(torch.autograd.Function):
+    """M[i] = W~ . ( sum_{e in E(i)} alpha_e x~_e (x) g_e + x~_0 (x) Q_i ) (+ beta)   -- see csrc/message.cu.
+
+    X [E+1, ldx] trunk output (last row = x_0); G either node states H [n_rows, nf] (gather=True: g_e = H[src_e])
+    or explicit per-edge vectors [E, nf]; alpha [E] or None; Q [n_rows, nf] or None; W_last [mf*nf, P],
+    B_last [mf*nf] (reference edge_map[-1]), beta [mf] or None.
+    """
+
+    @staticmethod
+    def forward(ctx, X, G, alpha, Q, W_last, B_last, beta, el, gather, nf, mf, P):
+        lib = _lib.load()
+        _need_cuda(X, G, W_last)
+        assert X.stride(1) == 1
+        ldx = X.stride(0)
+        G = f32c(G)
+        alpha_c = f32c(alpha) if alpha is not None else None
+        Q_c = f32c(Q) if Q is not None else None
+        W_last, B_last = f32c(W_last), f32c(B_last)
+        beta_c = f32c(beta) if beta is not None else None
+        dev = X.device
+        n_wt = lib.mpnn_message_wt_floats(nf, mf, P)
+        if n_wt < 0:
+            raise RuntimeError("mpnn_b200: node/message feature width > 128 is not supported yet")
+        Wt = torch.empty(n_wt, dtype=torch.float32, device=dev)
+        check(lib.mpnn_message_prepare(ptr(W_last), ptr(B_last), nf, mf, P, ptr(Wt), stream()), "message_prepare")
+        M = torch.empty(el.n_rows, mf, dtype=torch.float32, device=dev)
+        gidx = el.edge_src if gather else None
+        check(lib.mpnn_message_fwd(ptr(el.row_ptr), ptr(el.edge_dst), ptr(gidx), None, ptr(alpha_c),
+                                   ctypes.c_void_p(X.data_ptr()), ldx, el.E, ptr(G), G.stride(0), ptr(Q_c), ptr(Wt),
+                                   ptr(beta_c), el.n_rows, nf, mf, P, ptr(M), stream()), "message_fwd")
+        ctx.save_for_backward(X, G, alpha_c, Q_c, Wt, beta_c)
+        ctx.meta = (el, gather, nf, mf, P, ldx)
+        return M
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dM):
+        lib = _lib.load()
+        X, G, alpha, Q, Wt, beta = ctx.saved_tensors
+        el, gather, nf, mf, P, ldx = ctx.meta
+        dev = X.device
+        dM = f32c(dM)
+        E = el.E
+        ldt = (P + 1 + 3) // 4 * 4
+        T = torch.zeros(E + 1, ldt, dtype=torch.float32, device=dev)
+        dG = torch.zeros(max(E, 1), nf, dtype=torch.float32, device=dev)
+        dQ = torch.empty_like(Q) if Q is not None else None
+        dalpha = torch.empty(max(E, 1), dtype=torch.float32, device=dev) if alpha is not None else None
+        dW = torch.empty(mf * nf, P, dtype=torch.float32, device=dev)
+        dB = torch.empty(mf * nf, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(mf, dtype=torch.float32, device=dev) if beta is not None else None
+        ws = workspace(lib.mpnn_message_bwd_workspace_bytes(el.n_rows, nf, mf, P), dev)
+        gidx = el.edge_src if gather else None
+        check(lib.mpnn_message_bwd(ptr(el.row_ptr), ptr(el.edge_dst), ptr(gidx), None, ptr(alpha),
+                                   ctypes.c_void_p(X.data_ptr()), ldx, E, ptr(G), G.stride(0), ptr(Q), ptr(Wt),
+                                   ptr(beta), el.n_rows, E, nf, mf, P, ptr(dM), ptr(T), ldt, ptr(dG), ptr(dQ),
+                                   ptr(dalpha), ptr(dW), ptr(dB), ptr(dbeta), ptr(ws), ws.numel(), stream()),
+              "message_bwd")
+        dX = T[:, :X.shape[1]]
+        if gather:
+            dGsrc = torch.empty(el.n_rows, nf, dtype=torch.float32, device=dev)
+            check(lib.mpnn_segment_sum(ptr(dG), ptr(el.col_ptr), ptr(el.csc_eid), el.n_rows, nf, nf, ptr(dGsrc), nf, 0,
+                                       1.0, stream()), "segment_sum")
+        else:
+            dGsrc = dG[:E]
+        return (dX, dGsrc, dalpha[:E] if dalpha is not None else None, dQ, dW, dB, dbeta,
+                None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# GRU update
+# ------------------------------------------------------------------------------------------------
+class GRUFn(torch.autograd.Function):
+    """reference gru_update.py:26-35,66-68 on flat [rows, d] tensors; mask [rows]."""
+
+    @staticmethod
+    def forward(ctx, m, h, mask, W_ih, W_hh, b_ih, b_hh):
+        lib = _lib.load()
+        _need_cuda(m, h, mask, W_ih)
+        m, h, mask = f32c(m), f32c(h), f32c(mask)
+        W_ih, W_hh, b_ih, b_hh = f32c(W_ih), f32c(W_hh), f32c(b_ih), f32c(b_hh)
+        rows, d = h.shape
+        out = torch.empty_like(h)
+        gates = torch.empty(rows, 4 * d, dtype=torch.float32, device=h.device)
+        ws = workspace(lib.mpnn_gru_workspace_bytes(rows, d), h.device)
+        check(lib.mpnn_gru_fwd(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), rows, d, ptr(out),
+                               ptr(gates), ptr(ws), ws.numel(), stream()), "gru_fwd")
+        ctx.save_for_backward(m, h, mask, W_ih, W_hh, gates)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        m, h, mask, W_ih, W_hh, gates = ctx.saved_tensors
+        rows, d = h.shape
+        dout = f32c(dout)
+        dev = h.device
+        dm, dh = torch.empty_like(m), torch.empty_like(h)
+        dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
+        db_ih = torch.empty(3 * d, dtype=torch.float32, device=dev)
+        db_hh = torch.empty(3 * d, dtype=torch.float32, device=dev)
+        ws = workspace(lib.mpnn_gru_workspace_bytes(rows, d), dev)
+        check(lib.mpnn_gru_bwd(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(gates), ptr(dout), rows, d, ptr(dm),
+                               ptr(dh), ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh), ptr(ws), ws.numel(), stream()),
+              "gru_bwd")
+        return dm, dh, None, dW_ih, dW_hh, db_ih, db_hh
+
+
+# ------------------------------------------------------------------------------------------------
+# masked batch norms
+# ------------------------------------------------------------------------------------------------
+class MaskBNFn(torch.autograd.Function):
+    """reference mask_batch_norm.py:9-15 on x [rows, C], mask [rows]."""
+
+    @staticmethod
+    def forward(ctx, x, mask, eps):
+        lib = _lib.load()
+        _need_cuda(x, mask)
+        x, mask = f32c(x), f32c(mask)
+        rows, C = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
+        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
+        check(lib.mpnn_mask_bn_fwd(ptr(x), ptr(mask), rows, C, float(eps), ptr(y), ptr(stats), ptr(ws), ws.numel(),
+                                   stream()), "mask_bn_fwd")
+        ctx.save_for_backward(x, mask, stats)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, mask, stats = ctx.saved_tensors
+        rows, C = x.shape
+        dy = f32c(dy)
+        dx = torch.empty_like(x)
+        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
+        check(lib.mpnn_mask_bn_bwd(ptr(x), ptr(mask), ptr(dy), ptr(stats), rows, C, ptr(dx), ptr(ws), ws.numel(),
+                                   stream()), "mask_bn_bwd")
+        return dx, None, None
+
+
+class MaskBN1dFn(torch.autograd.Function):
+    """reference mask_batch_norm.py:20-38; running buffers are updated in place when training."""
+
+    @staticmethod
+    def forward(ctx, x, mask, weight, bias, running_mean, running_var, training, momentum, eps):
+        lib = _lib.load()
+        _need_cuda(x, mask)
+        x, mask = f32c(x), f32c(mask)
+        weight_c = f32c(weight) if weight is not None else None
+        bias_c = f32c(bias) if bias is not None else None
+        rows, C = x.shape
+        y = torch.empty_like(x)
+        stats = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
+        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
+        check(lib.mpnn_mask_bn1d_fwd(ptr(x), ptr(mask), ptr(weight_c), ptr(bias_c), ptr(running_mean), ptr(running_var),
+                                     rows, C, int(training), float(momentum), float(eps), ptr(y), ptr(stats), ptr(ws),
+                                     ws.numel(), stream()), "mask_bn1d_fwd")
+        if training:
+            ctx.save_for_backward(x, mask, weight_c, stats)
+        else:  # eval normalises with the running statistics as they are now
+            ctx.save_for_backward(x, mask, weight_c, running_mean.clone(), running_var.clone())
+        ctx.cfg = (bool(training), float(eps))
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        training, eps = ctx.cfg
+        if training:
+            x, mask, weight, stats = ctx.saved_tensors
+            rm = rv = None
+        else:
+            x, mask, weight, rm, rv = ctx.saved_tensors
+            stats = None
+        rows, C = x.shape
+        dy = f32c(dy)
+        dev = x.device
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, dtype=torch.float32, device=dev)
+        db = torch.empty(C, dtype=torch.float32, device=dev)
+        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), dev)
+        check(lib.mpnn_mask_bn1d_bwd(ptr(x), ptr(mask), ptr(dy), ptr(weight), ptr(stats), ptr(rm), ptr(rv), rows, C,
+                                     int(training), eps, ptr(dx), ptr(dw), ptr(db), ptr(ws), ws.numel(), stream()),
+              "mask_bn1d_bwd")
+        return dx, None, (dw if weight is not None else None), (db if weight is not None else None), None, None, \
+            None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# graph-level readout
+# ------------------------------------------------------------------------------------------------
+class GraphLevelOutputFn(torch.autograd.Function):
+    """reference graph_level_output.py:30-47; x [B,N,F2], mask [B,N,1] or None."""
+
+    @staticmethod
+    def forward(ctx, x, mask, Wi, bi, Wj, bj):
+        lib = _lib.load()
+        _need_cuda(x, Wi)
+        x = f32c(x)
+        mask_c = f32c(mask) if mask is not None else None
+        Wi, bi, Wj, bj = f32c(Wi), f32c(bi), f32c(Wj), f32c(bj)
+        B, N, F2 = x.shape
+        O = Wi.shape[0]
+        dev = x.device
+        out = torch.empty(B, O, dtype=torch.float32, device=dev)
+        u = torch.empty(B * N, O, dtype=torch.float32, device=dev)
+        v = torch.empty(B * N, O, dtype=torch.float32, device=dev)
+        UV = torch.empty(B, 2, O, dtype=torch.float32, device=dev) if mask is None else None
+        check(lib.mpnn_glo_fwd(ptr(x), ptr(mask_c), ptr(Wi), ptr(bi), ptr(Wj), ptr(bj), B, N, F2, O, ptr(out), ptr(u),
+                               ptr(v), ptr(UV), stream()), "glo_fwd")
+        ctx.save_for_backward(x, mask_c, Wi, Wj, u, v, UV)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, mask, Wi, Wj, u, v, UV = ctx.saved_tensors
+        B, N, F2 = x.shape
+        O = Wi.shape[0]
+        dev = x.device
+        dout = f32c(dout)
+        dx = torch.empty_like(x)
+        dWi, dWj = torch.empty_like(Wi), torch.empty_like(Wj)
+        dbi = torch.empty(O, dtype=torch.float32, device=dev)
+        dbj = torch.empty(O, dtype=torch.float32, device=dev)
+        ws = workspace(lib.mpnn_glo_workspace_bytes(B, N, F2, O), dev)
+        check(lib.mpnn_glo_bwd(ptr(x), ptr(mask), ptr(Wi), ptr(Wj), ptr(u), ptr(v), ptr(UV), ptr(dout), B, N, F2, O,
+                               ptr(dx), ptr(dWi), ptr(dbi), ptr(dWj), ptr(dbj), ptr(ws), ws.numel(), stream()),
+              "glo_bwd")
+        return dx, None, dWi, dbi, dWj, dbj
+
+
+# ------------------------------------------------------------------------------------------------
+# row gather with a scatter-free backward (transposed index lists)
+# ------------------------------------------------------------------------------------------------
+class GatherRowsFn(torch.autograd.Function):
+    """out[t,:] = src[idx[t],:];  backward: dsrc[s,:] = sum_{k in t_ptr[s]:t_ptr[s+1]} dout[t_idx[k] (or k),:]."""
+
+    @staticmethod
+    def forward(ctx, src, idx, t_ptr, t_idx):
+        lib = _lib.load()
+        _need_cuda(src)
+        src = f32c(src)
+        T, width = idx.shape[0], src.shape[1]
+        out = torch.empty(T, width, dtype=torch.float32, device=src.device)
+        if T:
+            unit = torch.arange(T + 1, dtype=torch.int32, device=src.device)
+            check(lib.mpnn_segment_sum(ptr(src), ptr(unit), ptr(idx), T, width, width, ptr(out), width, 0, 1.0,
+                                       stream()), "segment_sum")
+        ctx.t = (t_ptr, t_idx, src.shape[0], width)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        t_ptr, t_idx, n_src, width = ctx.t
+        dout = f32c(dout)
+        dsrc = torch.empty(n_src, width, dtype=torch.float32, device=dout.device)
+        check(lib.mpnn_segment_sum(ptr(dout), ptr(t_ptr), ptr(t_idx), n_src, width, width, ptr(dsrc), width, 0, 1.0,
+                                   stream()), "segment_sum")
+        return dsrc, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# linear layer on flat rows (plumbing GEMM of the library; y = x W^T + b, W is an nn.Linear weight)
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        lib = _lib.load()
+        _need_cuda(x, W)
+        x, W = f32c(x), f32c(W)
+        b_c = f32c(b) if b is not None else None
+        R, K = x.shape
+        O = W.shape[0]
+        y = torch.empty(R, O, dtype=torch.float32, device=x.device)
+        check(lib.mpnn_gemm(ptr(x), ptr(W), ptr(y), R, O, K, K, 1, 1, K, O, ptr(b_c), 0, None, 0, stream()), "gemm")
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, W = ctx.saved_tensors
+        dy = f32c(dy)
+        R, K = x.shape
+        O = W.shape[0]
+        dev = x.device
+        dx = torch.empty_like(x)
+        dW = torch.empty_like(W)
+        check(lib.mpnn_gemm(ptr(dy), ptr(W), ptr(dx), R, K, O, O, 1, K, 1, K, None, 0, None, 0, stream()), "gemm")
+        ws = workspace(lib.mpnn_gemm_workspace_bytes(O, K, R) + lib.mpnn_colsum_workspace_bytes(R, O), dev)
+        check(lib.mpnn_gemm(ptr(dy), ptr(x), ptr(dW), O, K, R, 1, O, K, 1, K, None, 0, ptr(ws), ws.numel(), stream()),
+              "gemm")
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(O, dtype=torch.float32, device=dev)
+            check(lib.mpnn_colsum(ptr(dy), None, R, O, O, 0, ptr(db), 0, ptr(ws), ws.numel(), stream()), "colsum")
+        return dx, dW, db
+
+
+# ------------------------------------------------------------------------------------------------
+# softmax(logits) * V   (attention gate of AttEdgeNetwork; row softmax of WAdjMsgAgg with V=None)
+# ------------------------------------------------------------------------------------------------
+class SoftmaxMulFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, V):
+        lib = _lib.load()
+        _need_cuda(logits)
+        logits = f32c(logits)
+        V_c = f32c(V) if V is not None else None
+        rows, n = logits.shape
+        gate = torch.empty_like(logits)
+        out = torch.empty_like(logits)
+        check(lib.mpnn_softmax_mul_fwd(ptr(logits), ptr(V_c), rows, n, ptr(gate), ptr(out), stream()), "softmax_mul_fwd")
+        ctx.save_for_backward(gate, V_c)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        gate, V = ctx.saved_tensors
+        dout = f32c(dout)
+        rows, n = gate.shape
+        dlogits = torch.empty_like(gate)
+        dV = torch.empty_like(gate) if V is not None else None
+        check(lib.mpnn_softmax_mul_bwd(ptr(gate), ptr(V), ptr(dout), rows, n, ptr(dlogits), ptr(dV), stream()),
+              "softmax_mul_bwd")
+        return dlogits, dV
+
+
+# ------------------------------------------------------------------------------------------------
+# dense weighted aggregation over senders (stand-alone aggregator contract on [B,N,N,mf] messages)
+# ------------------------------------------------------------------------------------------------
+class DenseAggFn(torch.autograd.Function):
+    """out[b,i,:] = sum_j w[b,i,j] * messages[b,i,j,:]"""
+
+    @staticmethod
+    def forward(ctx, messages, w):
+        lib = _lib.load()
+        _need_cuda(messages, w)
+        messages, w = f32c(messages), f32c(w)
+        B, N, N2, mf = messages.shape
+        out = torch.empty(B, N, mf, dtype=torch.float32, device=messages.device)
+        check(lib.mpnn_dense_agg_fwd(ptr(messages), ptr(w), B * N, N2, mf, ptr(out), stream()), "dense_agg_fwd")
+        ctx.save_for_backward(messages, w)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        messages, w = ctx.saved_tensors
+        B, N, N2, mf = messages.shape
+        dout = f32c(dout)
+        dm = torch.empty_like(messages) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        check(lib.mpnn_dense_agg_bwd(ptr(messages), ptr(w), ptr(dout), B * N, N2, mf, ptr(dm), ptr(dw), stream()),
+              "dense_agg_bwd")
+        return dm, dw
+
+
+# ------------------------------------------------------------------------------------------------
+# Set2Vec readout
+# ------------------------------------------------------------------------------------------------
+class Set2VecFn(torch.autograd.Function):
+    """reference set2vec.py:93-151 ("default" inner product).  Wcat [2F,4F] = [w_hi|w_hf|w_hg|w_ho], bcat [4F]."""
+
+    @staticmethod
+    def forward(ctx, X, mask, Wcat, bcat, Wq, we, steps):
+        lib = _lib.load()
+        _need_cuda(X, Wcat)
+        X = f32c(X)
+        mask_c = f32c(mask) if mask is not None else None
+        Wcat, bcat, Wq, we = f32c(Wcat), f32c(bcat), f32c(Wq), f32c(we)
+        B, N, F = X.shape
+        dev = X.device
+        out = torch.empty(B, 2 * F, dtype=torch.float32, device=dev)
+        saved = torch.empty(lib.mpnn_set2vec_saved_floats(B, N, F, steps), dtype=torch.float32, device=dev)
+        ws = workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)
+        check(lib.mpnn_set2vec_fwd(ptr(X), ptr(mask_c), ptr(Wcat), ptr(bcat), ptr(Wq), ptr(we), B, N, F, steps, ptr(out),
+                                   ptr(saved), ptr(ws), ws.numel(), stream()), "set2vec_fwd")
+        ctx.save_for_backward(X, mask_c, Wcat, Wq, we, saved)
+        ctx.steps = steps
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        X, mask, Wcat, Wq, we, saved = ctx.saved_tensors
+        B, N, F = X.shape
+        dev = X.device
+        dout = f32c(dout)
+        dX = torch.empty_like(X)
+        dWcat = torch.empty_like(Wcat)
+        dbcat = torch.empty(4 * F, dtype=torch.float32, device=dev)
+        dWq = torch.empty_like(Wq)
+        dwe = torch.empty_like(we)
+        ws = workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)
+        check(lib.mpnn_set2vec_bwd(ptr(X), ptr(mask), ptr(Wcat), ptr(Wq), ptr(we), ptr(saved), ptr(dout), B, N, F,
+                                   ctx.steps, ptr(dX), ptr(dWcat), ptr(dbcat), ptr(dWq), ptr(dwe), ptr(ws), ws.numel(),
+                                   stream()), "set2vec_bwd")
+        return dX, None, dWcat, dbcat, dWq, dwe, None

@@ -1,0 +1,113 @@
+"""On-device edge list of a padded batch (CSR by receiver + CSC by sender), built once per batch.
+
+Layout contract: the reference's padded tensors (collate_2d_graphs, pre_process/data_loader.py:50-70):
+bfm [B,N,N,ef], adj [B,N,N].  The compacted form is what every message kernel consumes.
+"""
+import collections
+
+import torch
+
+from . import _lib
+
+
+class EdgeList(object):
+    """Device arrays describing the non-zero atom pairs of one padded batch.
+
+    row_ptr [B*N+1] int32, edge_dst/edge_src [E] int32 (flat node ids b*N+i / b*N+j), edge_w [E] (adj value),
+    rows [E+1, ef] (bond rows; the LAST row is the all-zero row x_0), col_ptr [B*N+1], csc_eid [E].
+    Edge order is row-major (b,i,j) == torch.nonzero order (bit-exact contract).
+    """
+
+    def __init__(self, B, N, ef, E, row_ptr, col_ptr, edge_src, edge_dst, edge_w, rows, csc_eid):
+        self.B, self.N, self.ef, self.E = B, N, ef, E
+        self.n_rows = B * N
+        self.row_ptr, self.col_ptr = row_ptr, col_ptr
+        self.edge_src, self.edge_dst, self.edge_w = edge_src, edge_dst, edge_w
+        self.rows, self.csc_eid = rows, csc_eid
+        self._csc_dst = None
+
+    @property
+    def csc_dst(self):
+        """receiver row of every CSC entry (for scatter-free transposed reductions)"""
+        if self._csc_dst is None:
+            self._csc_dst = self.edge_dst[self.csc_eid.long()].contiguous() if self.E else self.edge_dst
+        return self._csc_dst
+
+
+def compact_edges(bfm, adj=None):
+    """Compacts (bfm, adj) -> EdgeList.  One 4-byte device->host read (the edge count) sizes the arrays."""
+    lib = _lib.load()
+    if not bfm.is_cuda:
+        raise RuntimeError("mpnn_b200.compact_edges needs CUDA tensors (no CPU fallback)")
+    bfm_c = _lib.f32c(bfm.detach())
+    adj_c = _lib.f32c(adj.detach()) if adj is not None else None
+    B, N, N2, ef = bfm_c.shape
+    assert N == N2, "bfm must be [B,N,N,ef]"
+    if adj_c is not None:
+        assert tuple(adj_c.shape) == (B, N, N), "adj must be [B,N,N]"
+    dev = bfm_c.device
+    n_rows = B * N
+    row_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    col_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    ws = _lib.workspace(lib.mpnn_compact_workspace_bytes(B, N), dev)
+    _lib.check(lib.mpnn_compact_count(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, _lib.ptr(row_ptr), _lib.ptr(col_ptr),
+                                      _lib.ptr(ws), ws.numel(), _lib.stream()), "compact_count")
+    E = int(row_ptr[-1].item())
+    edge_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    edge_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    csc_eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    edge_w = torch.empty(max(E, 1), dtype=torch.float32, device=dev)
+    rows = torch.zeros(E + 1, ef, dtype=torch.float32, device=dev)
+    _lib.check(lib.mpnn_compact_fill(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, _lib.ptr(row_ptr), _lib.ptr(col_ptr), E,
+                                     _lib.ptr(edge_src), _lib.ptr(edge_dst), _lib.ptr(edge_w), _lib.ptr(rows),
+                                     _lib.ptr(csc_eid), _lib.ptr(ws), _lib.stream()), "compact_fill")
+    return EdgeList(B, N, ef, E, row_ptr, col_ptr, edge_src[:E], edge_dst[:E], edge_w[:E], rows, csc_eid[:E])
+
+
+# ---- small identity cache: the same (bfm, adj) pair is compacted once per batch, whatever number of
+# ---- EdgeNetworks / steps consume it (reference models call mf(afm, bfm) T times per forward).
+_CACHE = collections.OrderedDict()
+_CACHE_SIZE = 8
+
+
+def _key(t):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.device.index)
+
+
+def edge_list_for(bfm, adj=None):
+    k = (_key(bfm), _key(adj))
+    hit = _CACHE.get(k)
+    if hit is not None:
+        _CACHE.move_to_end(k)
+        return hit[0]
+    el = compact_edges(bfm, adj)
+    _CACHE[k] = (el, bfm, adj)  # keep the tensors alive so data_ptr cannot be recycled under the key
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return el
+
+
+def clear_cache():
+    _CACHE.clear()
+
+
+class GatherEdgeRows(torch.autograd.Function):
+    """rows[E+1, ef] as a differentiable function of the dense bfm (needed when bfm comes out of a trainable
+    bond encoder, normed_encoded_basic_model.py:68): backward scatters d rows back to [B,N,N,ef]."""
+
+    @staticmethod
+    def forward(ctx, bfm, el):
+        ctx.el = el
+        ctx.shape = tuple(bfm.shape)
+        return el.rows
+
+    @staticmethod
+    def backward(ctx, d_rows):
+        el = ctx.el
+        lib = _lib.load()
+        dense = torch.zeros(ctx.shape, dtype=torch.float32, device=d_rows.device)
+        d_rows = _lib.f32c(d_rows)
+        if el.E:
+            _lib.check(lib.mpnn_scatter_edge_rows(_lib.ptr(d_rows), _lib.ptr(el.edge_dst), _lib.ptr(el.edge_src), el.E,
+                                                  el.N, el.ef, _lib.ptr(dense), _lib.stream()), "scatter_edge_rows")
+        return dense, None

@@ -1,0 +1,475 @@
+"""Drop-in nn.Modules for the reference's message-passing plug-in API.
+
+Same class names, constructor signatures, forward signatures, parameter names/shapes and state_dict keys
+as hochshi/mpnn's `mpnn_functions` package and `models/mask_batch_norm.py`, so the reference's model files
+(constructor injection, models/basic_model.py:7-32, or `from mpnn_functions import *`, :3) run against
+them unchanged.  Every forward/backward is a call into the sm_100a CUDA library through the C-ABI
+(`mpnn_b200._lib`); there is no PyTorch or CPU fallback -- CPU tensors raise.
+"""
+import torch
+from torch import nn
+
+from . import graph
+from .functional import (DenseAggFn, EdgeMessageFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn, GraphLevelOutputFn, GRUFn,
+                         LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn)
+
+_N_TIED = 50  # edge_network.py:20
+
+
+def _key(t):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+
+
+# =================================================================================================
+# message functions
+# =================================================================================================
+class LazyMessages(object):
+    """What EdgeNetwork.forward returns: the messages of one (afm, bfm) pair, not yet evaluated.
+
+    The reference HEAD is internally inconsistent: EdgeNetwork.forward returns already-summed
+    messages [B,N,mf] (edge_network.py:50-51) while the aggregators expect per-pair messages [B,N,N,mf]
+    (adjacent_message_agg.py:13-18; the commented lines edge_network.py:40,52).  One object serves both:
+      * an mpnn_b200 aggregator recognises it and calls `.aggregate(...)`: the documented per-pair form,
+        fused with the aggregation, never materialising [B,N,N,mf];
+      * any other consumer (e.g. lipo_basic_model.py:85 feeds it straight to a batch norm) gets the HEAD
+        tensor [B,N,mf]: attribute access, operators and torch functions all materialise it first.
+    """
+
+    def __init__(self, net, afm, bfm, reuse):
+        self._net, self._afm, self._bfm, self._reuse = net, afm, bfm, reuse
+        self._value = None
+
+    # ---- HEAD form ----
+    def materialize(self):
+        if self._value is None:
+            self._value = self._net._head_messages(self._afm, self._bfm, self._reuse)
+        return self._value
+
+    # ---- documented per-pair form, fused with the aggregation ----
+    def aggregate(self, adj, alpha_fn=None, gamma_fn=None):
+        return self._net._aggregated_messages(self._afm, self._bfm, adj, self._reuse, alpha_fn, gamma_fn)
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def unwrap(a):
+            if isinstance(a, LazyMessages):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(unwrap(x) for x in a)
+            return a
+        kwargs = {k: unwrap(v) for k, v in (kwargs or {}).items()}
+        return func(*[unwrap(a) for a in args], **kwargs)
+
+    def __len__(self):
+        return self._afm.shape[0]
+
+    def __repr__(self):
+        return "LazyMessages(%s, afm=%s)" % (type(self._net).__name__, tuple(self._afm.shape))
+
+
+def _binop(name):
+    def f(self, other):
+        return getattr(self.materialize(), name)(other)
+    return f
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
+           "__matmul__", "__getitem__", "__pow__", "__eq__", "__ne__", "__lt__", "__gt__", "__le__", "__ge__"):
+    setattr(LazyMessages, _n, _binop(_n))
+LazyMessages.__neg__ = lambda self: -self.materialize()
+LazyMessages.__hash__ = object.__hash__
+
+
+class EdgeNetwork(nn.Module):
+    """Gilmer edge network (reference mpnn_functions/message/edge_network.py).
+
+    Parameters are held by real nn.Linear children laid out exactly like the reference's `edge_map`
+    (growth layers, the SAME Sequential(Linear(P,P,bias=False), act) object repeated 50 times, last Linear)
+    so state_dict keys, `model.apply(init_weights)` and optimisers behave identically; the kernels read the
+    weights in place.
+    """
+
+    def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
+        super(EdgeNetwork, self).__init__()
+        self.nf = node_features
+        self.ef = edge_features
+        self.mf = message_features
+        self.act_fn = activation_fn if activation_fn is not None else nn.ReLU()
+        if not isinstance(self.act_fn, nn.ReLU):
+            raise NotImplementedError("mpnn_b200.EdgeNetwork: only ReLU is implemented natively (no fallback); got %r"
+                                      % (self.act_fn,))
+        edge_map = []
+        in_layer = self.ef
+        self._growth_idx = []
+        while in_layer ** 2 < self.nf * self.mf:
+            self._growth_idx.append(len(edge_map))
+            edge_map.append(nn.Linear(in_layer, in_layer ** 2))
+            edge_map.append(self.act_fn)
+            in_layer = in_layer ** 2
+        self.P = in_layer
+        self._tied_idx = len(edge_map)
+        edge_map += [nn.Sequential(nn.Linear(in_layer, in_layer, bias=False), self.act_fn)] * _N_TIED
+        self._last_idx = len(edge_map)
+        edge_map.append(nn.Linear(in_layer, self.nf * self.mf))
+        self.edge_map = nn.Sequential(*edge_map)
+        self.message_bias = nn.Parameter(torch.zeros(self.mf))
+        self._trunk_cache = None   # (edge-list, bfm key, X)         <- the reference's self.edge_embed
+        self._msg_cache = {}       # message tensors of the current edge embedding
+
+    # ---- pieces -----------------------------------------------------------------------------------
+    def _trunk(self, bfm, el, reuse):
+        """x = edge_map[:-1](bond rows) on the compacted rows (+ zero row), cached like self.edge_embed."""
+        c = self._trunk_cache
+        if reuse and c is not None and c[0] is el:
+            return c[2]
+        rows = graph.GatherEdgeRows.apply(bfm, el) if bfm.requires_grad else el.rows
+        gw = [self.edge_map[i].weight for i in self._growth_idx]
+        gb = [self.edge_map[i].bias for i in self._growth_idx]
+        X = EdgeTrunkFn.apply(rows, self.edge_map[self._tied_idx][0].weight, _N_TIED, *(gw + gb))
+        self._trunk_cache = (el, None, X)
+        self._msg_cache = {}
+        return X
+
+    def _last(self):
+        last = self.edge_map[self._last_idx]
+        return last.weight, last.bias
+
+    def _sender_vectors(self, afm, bfm, el):
+        """(G, gather): what multiplies the edge matrix -- the sender state itself for the plain edge network."""
+        return afm.reshape(-1, self.nf), True
+
+    def _nonedge_vectors(self, afm, el, H):
+        """per-row vector that multiplies A(x_0): sum of sender states over the NON-edge pairs of the row."""
+        B, N, nf = afm.shape
+        S = afm.sum(dim=1, keepdim=True).expand(B, N, nf).reshape(-1, nf)
+        return S - GatherSumFn.apply(H, el.row_ptr, el.edge_src, el.n_rows, el.col_ptr, el.csc_dst)
+
+    def _head_messages(self, afm, bfm, reuse):
+        """edge_network.py:42-51: out[b,i] = sum over ALL j of A(bfm[b,i,j]) afm[b,j] + message_bias."""
+        B, N, nf = afm.shape
+        el = graph.edge_list_for(bfm, None)
+        X = self._trunk(bfm, el, reuse)
+        k = ("head", _key(afm))
+        if reuse and k in self._msg_cache:
+            return self._msg_cache[k]
+        if bfm.requires_grad:
+            raise NotImplementedError("mpnn_b200.EdgeNetwork: HEAD-form messages with a differentiable bfm are not "
+                                      "implemented (the non-bonded rows' gradient); use an aggregator")
+        G, gather = self._sender_vectors(afm, bfm, el)
+        Q = self._nonedge_vectors(afm, el, afm.reshape(-1, nf))
+        W, Bv = self._last()
+        M = EdgeMessageFn.apply(X, G, None, Q, W, Bv, self.message_bias, el, gather, self.nf, self.mf, self.P)
+        M = M.view(B, N, self.mf)
+        self._msg_cache[k] = M
+        return M
+
+    def _aggregated_messages(self, afm, bfm, adj, reuse, alpha_fn, gamma_fn):
+        """sum_j weight[b,i,j] * (A(bfm[b,i,j]) g[b,i,j])  (edge_network.py:52 + the aggregator), no bias."""
+        B, N, nf = afm.shape
+        el = graph.edge_list_for(bfm, adj)
+        X = self._trunk(bfm, el, reuse)
+        k = ("agg", _key(afm), _key(adj), id(alpha_fn), id(gamma_fn))
+        if reuse and alpha_fn is None and k in self._msg_cache:
+            return self._msg_cache[k]
+        G, gather = self._sender_vectors(afm, bfm, el)
+        alpha = el.edge_w if alpha_fn is None else alpha_fn(el)
+        Q = None
+        if gamma_fn is not None:  # aggregators that also weight the non-bonded pairs
+            Q = gamma_fn(el) * self._nonedge_vectors(afm, el, afm.reshape(-1, nf))
+        W, Bv = self._last()
+        M = EdgeMessageFn.apply(X, G, alpha, Q, W, Bv, None, el, gather, self.nf, self.mf, self.P)
+        M = M.view(B, N, self.mf)
+        if alpha_fn is None:
+            self._msg_cache[k] = M
+        return M
+
+    def forward(self, afm, bfm, reuse_graph_tensors=False):
+        if not afm.is_cuda:
+            raise RuntimeError("mpnn_b200.EdgeNetwork: CUDA tensors required (there is no CPU fallback)")
+        return LazyMessages(self, afm, bfm, bool(reuse_graph_tensors))
+
+
+class AttEdgeNetwork(EdgeNetwork):
+    """reference att_edge_network.py: the sender state is gated, per pair, by softmax_features(attn(cat(h_i, bond)))."""
+
+    def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
+        super(AttEdgeNetwork, self).__init__(node_features, edge_features, message_features, activation_fn)
+        self.attn = nn.Linear(self.nf + self.ef, self.nf)
+        self.attn_act = attn_act if attn_act is not None else nn.Softmax(dim=-1)
+        if not (isinstance(self.attn_act, nn.Softmax) and self.attn_act.dim in (-1, 3)):
+            raise NotImplementedError("mpnn_b200.AttEdgeNetwork: only the default Softmax(dim=-1) gate is implemented")
+
+    def _gate_logits(self, Hr, Xe):
+        Wa, ba = self.attn.weight, self.attn.bias
+        logits = LinearFn.apply(Hr, Wa[:, :self.nf].contiguous(), ba)
+        if Xe is not None:
+            logits = logits + LinearFn.apply(Xe, Wa[:, self.nf:].contiguous(), None)
+        return logits
+
+    def _sender_vectors(self, afm, bfm, el):
+        H = afm.reshape(-1, self.nf)
+        Hr = GatherRowsFn.apply(H, el.edge_dst, el.row_ptr, None)          # receiver state per edge
+        Hs = GatherRowsFn.apply(H, el.edge_src, el.col_ptr, el.csc_eid)    # sender state per edge
+        rows = graph.GatherEdgeRows.apply(bfm, el) if bfm.requires_grad else el.rows
+        return SoftmaxMulFn.apply(self._gate_logits(Hr, rows[:el.E]), Hs), False
+
+    def _nonedge_vectors(self, afm, el, H):
+        base = super(AttEdgeNetwork, self)._nonedge_vectors(afm, el, H)
+        return SoftmaxMulFn.apply(self._gate_logits(H, None), base)       # gate of a zero bond row
+
+    def _head_messages(self, afm, bfm, reuse):
+        raise NotImplementedError("mpnn_b200.AttEdgeNetwork: per-pair messages must be consumed by an mpnn_b200 "
+                                  "aggregator (AdjMsgAgg / WAdjMsgAgg / AttMsgAgg); the reference's own HEAD forward "
+                                  "fails for this class (SURVEY.md 2.3)")
+
+
+class BiLiniearEdgeNetwork(nn.Module):
+    """reference bilinear_edge_network.py (parameter-free h_j^T E_ij h_i).  Scheduled after the hot path
+    (SURVEY.md 8f rank 3); constructing it works so `from mpnn_functions import *` resolves, forward raises."""
+
+    def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
+        super(BiLiniearEdgeNetwork, self).__init__()
+        self.nf, self.ef, self.mf = node_features, edge_features, message_features
+
+    def forward(self, afm, bfm, reuse_graph_tensors=False):
+        raise NotImplementedError("mpnn_b200.BiLiniearEdgeNetwork has no CUDA implementation yet (no fallback)")
+
+
+class GGNNMsgPass(nn.Module):
+    """reference ggnn_msg_pass.py: integer bond type -> [mf, nf] matrix lookup.  Same contraction kernel with
+    x_e = one-hot(bond type) (P = #types), W~ = adj_w; type 0 (no bond) maps to the zero matrix."""
+
+    def __init__(self, node_features, edge_features, message_features):
+        super(GGNNMsgPass, self).__init__()
+        self.nf, self.ef, self.mf = node_features, edge_features, message_features
+        self.register_parameter('adj_w', nn.Parameter(torch.Tensor(self.ef, self.mf, self.nf)))
+        self.register_parameter('message_bias', nn.Parameter(torch.zeros(self.mf).float()))
+        self.register_parameter('zeros', nn.Parameter(torch.zeros(1, self.mf, self.nf).float(), requires_grad=False))
+
+    def init_weights(self):
+        torch.nn.init.kaiming_uniform_(self.adj_w, nonlinearity='relu')
+
+    def forward(self, afm, bfm, reuse_graph_tensors=False):
+        if not afm.is_cuda:
+            raise RuntimeError("mpnn_b200.GGNNMsgPass: CUDA tensors required (there is no CPU fallback)")
+        B, N, nf = afm.shape
+        onehot = torch.zeros(B, N, N, self.ef, dtype=torch.float32, device=afm.device)
+        onehot.scatter_(-1, (bfm.long().clamp(min=1) - 1).unsqueeze(-1), (bfm > 0).float().unsqueeze(-1))
+        el = graph.edge_list_for(onehot, None)
+        W = self.adj_w.permute(1, 2, 0).reshape(self.mf * self.nf, self.ef)   # [(k*nf+l), p]
+        Bv = torch.zeros(self.mf * self.nf, dtype=torch.float32, device=afm.device)
+        M = EdgeMessageFn.apply(el.rows, afm.reshape(-1, nf), None, None, W, Bv, self.message_bias, el, True,
+                                self.nf, self.mf, self.ef)
+        return M.view(B, N, self.mf)
+
+
+# =================================================================================================
+# aggregators
+# =================================================================================================
+def _as_dense(messages):
+    return messages.materialize() if isinstance(messages, LazyMessages) else messages
+
+
+class AdjMsgAgg(nn.Module):
+    """reference adjacent_message_agg.py: out[b,i] = sum_j adj[b,i,j] * messages[b,i,j]."""
+
+    def __init__(self, adj_dim, attn_act=None):
+        super(AdjMsgAgg, self).__init__()
+
+    def forward(self, messages, adj):
+        if isinstance(messages, LazyMessages):
+            return messages.aggregate(adj)
+        return DenseAggFn.apply(messages, adj)
+
+
+class WAdjMsgAgg(nn.Module):
+    """reference weighted_adjacent_message_agg.py: weights softmax_j(adj[b,i,:]) -- non-neighbours and padded
+    atoms get e^0/Z too."""
+
+    def __init__(self, adj_dim, attn_act=None):
+        super(WAdjMsgAgg, self).__init__()
+
+    def forward(self, messages, adj):
+        if isinstance(messages, LazyMessages):
+            def parts(el):
+                ew = torch.exp(el.edge_w)
+                deg = (el.row_ptr[1:] - el.row_ptr[:-1]).float()
+                Z = GatherSumFn.apply(ew.unsqueeze(1), el.row_ptr, None, el.n_rows, None, None).squeeze(1) \
+                    + (el.N - deg)
+                return ew, Z
+            return messages.aggregate(
+                adj,
+                alpha_fn=lambda el: (lambda ew, Z: ew / Z[el.edge_dst.long()])(*parts(el)),
+                gamma_fn=lambda el: (1.0 / parts(el)[1]).unsqueeze(1))
+        B, N, _ = adj.shape
+        w = SoftmaxMulFn.apply(adj.reshape(B * N, N), None).view(B, N, N)
+        return DenseAggFn.apply(messages, w)
+
+
+class AttMsgAgg(nn.Module):
+    """reference attention_message_agg.py: weights act(Linear(adj[..., None])); with the default
+    Softmax(dim=-1) over the size-1 axis every weight is exactly 1 (an unmasked sum)."""
+
+    def __init__(self, adj_dim, attn_act=None):
+        super(AttMsgAgg, self).__init__()
+        self.adj_dim = adj_dim
+        self.att = nn.Sequential(
+            nn.Linear(adj_dim, 1),
+            attn_act if attn_act is not None else nn.Softmax(dim=-1)
+        )
+
+    def forward(self, messages, adj):
+        if isinstance(messages, LazyMessages):
+            dev = adj.device
+            return messages.aggregate(
+                adj,
+                alpha_fn=lambda el: self.att(el.edge_w.unsqueeze(-1)).squeeze(-1),
+                gamma_fn=lambda el: self.att(torch.zeros(1, 1, device=dev)).reshape(1, 1))
+        return DenseAggFn.apply(messages, self.att(adj.unsqueeze(-1)).squeeze(-1))
+
+
+# =================================================================================================
+# update
+# =================================================================================================
+class GRUCell(nn.Module):
+    """Parameter holder with the reference's names/shapes/init (gru_update.py:5-24); weights are [in, 3d]."""
+
+    def __init__(self, node_features, message_features):
+        super(GRUCell, self).__init__()
+        self.nf = node_features
+        self.mf = message_features
+        self.register_parameter('weight_ih', nn.Parameter(torch.Tensor(self.mf, 3 * self.nf)))
+        self.register_parameter('weight_hh', nn.Parameter(torch.Tensor(self.nf, 3 * self.nf)))
+        self.register_parameter('bias_ih', nn.Parameter(torch.Tensor(3 * self.mf)))
+        self.register_parameter('bias_hh', nn.Parameter(torch.Tensor(3 * self.nf)))
+        self.init_params()
+
+    def init_params(self):
+        torch.nn.init.xavier_uniform_(self.weight_ih, gain=torch.nn.init.calculate_gain('sigmoid'))
+        torch.nn.init.xavier_uniform_(self.weight_hh, gain=torch.nn.init.calculate_gain('sigmoid'))
+        nn.init.constant_(self.bias_ih, 0.0)
+        nn.init.constant_(self.bias_hh, 0.0)
+
+    def forward(self, messages, node_states, mask):
+        return GRUFn.apply(messages, node_states, mask.reshape(-1), self.weight_ih, self.weight_hh, self.bias_ih,
+                           self.bias_hh)
+
+
+class GRUUpdate(nn.Module):
+    """reference gru_update.py:39-68 (including the swapped GRUCell(mf, nf) construction, :53, which makes the
+    module usable only with node_features == message_features)."""
+
+    def __init__(self, node_features, message_features):
+        super(GRUUpdate, self).__init__()
+        self.nf = node_features
+        self.mf = message_features
+        self.gru_cell = GRUCell(self.mf, self.nf)
+
+    def forward(self, messages, node_states, mask):
+        messages = _as_dense(messages)
+        if self.nf != self.mf:
+            raise RuntimeError("GRUUpdate requires node_features == message_features (reference gru_update.py:53)")
+        h = self.gru_cell(messages.reshape(-1, self.mf), node_states.reshape(-1, self.nf), mask)
+        return h.view(node_states.shape)
+
+
+# =================================================================================================
+# masked batch norms  (reference models/mask_batch_norm.py)
+# =================================================================================================
+class MaskBatchNorm(nn.Module):
+    def __init__(self):
+        super(MaskBatchNorm, self).__init__()
+
+    def forward(self, tensor, mask, eps=1e-6):
+        tensor = _as_dense(tensor)
+        y = MaskBNFn.apply(tensor.reshape(-1, tensor.shape[-1]), mask.reshape(-1), eps)
+        return y.view(tensor.shape)
+
+
+class MaskBatchNorm1d(nn.BatchNorm1d):
+    def forward(self, tensor, mask):
+        tensor = _as_dense(tensor)
+        training = self.training or not self.track_running_stats
+        rm = self.running_mean if self.track_running_stats else None
+        rv = self.running_var if self.track_running_stats else None
+        y = MaskBN1dFn.apply(tensor.reshape(-1, tensor.shape[-1]), mask.reshape(-1),
+                             self.weight if self.affine else None, self.bias if self.affine else None,
+                             rm, rv, training, self.momentum, self.eps)
+        return y.view(tensor.shape)
+
+
+# =================================================================================================
+# readouts
+# =================================================================================================
+class GraphLevelOutput(nn.Module):
+    """reference readout/graph_level_output.py."""
+
+    def __init__(self, node_features, output_dim, time_steps=100, inner_prod="default", activation_fn=None,
+                 attn_act=None, dropout=0):
+        super(GraphLevelOutput, self).__init__()
+        self.in_dim = node_features
+        self.out_dim = output_dim
+        self.act_fn = activation_fn() if activation_fn is not None else nn.ReLU()
+        self.attn_act = attn_act() if attn_act is not None else nn.Softmax(dim=1)
+        self.dropout = dropout
+        self.i = nn.Sequential(nn.Linear(2 * self.in_dim, self.out_dim))
+        self.j = nn.Sequential(nn.Linear(2 * self.in_dim, self.out_dim))
+
+    def forward(self, input_set, mask=None, mprev=None, cprev=None):
+        input_set = _as_dense(input_set)
+        return GraphLevelOutputFn.apply(input_set, mask, self.i[0].weight, self.i[0].bias, self.j[0].weight,
+                                        self.j[0].bias)
+
+
+class LSTMCellHidden(nn.Module):
+    """Parameter holder of the input-less LSTM (reference set2vec.py:13-66): w_h{i,f,g,o} [hd, cd], b_h* [1, cd]."""
+
+    def __init__(self, hidden_dim, cell_dim, bias=True):
+        super(LSTMCellHidden, self).__init__()
+        self.hd = hidden_dim
+        self.cd = cell_dim
+        self.bias = bias
+        stdv = 1.0 / (self.hd ** 0.5)
+        for g in ("i", "f", "g", "o"):
+            self.register_parameter("w_h" + g, nn.Parameter(torch.zeros([self.hd, self.cd]).uniform_(-stdv, stdv)))
+        for g in ("i", "f", "g", "o"):
+            self.register_parameter("b_h" + g, nn.Parameter(torch.zeros([1, self.cd])))
+
+    def cat_params(self):
+        W = torch.cat([self.w_hi, self.w_hf, self.w_hg, self.w_ho], dim=1)
+        b = torch.cat([self.b_hi, self.b_hf, self.b_hg, self.b_ho], dim=1).reshape(-1)
+        return W, b
+
+    def forward(self, hprev, cprev):
+        raise NotImplementedError("mpnn_b200.LSTMCellHidden is evaluated inside the fused Set2Vec kernels")
+
+
+class Set2Vec(nn.Module):
+    """reference readout/set2vec.py ("default" inner product; the "dot" variant is broken at HEAD)."""
+
+    def __init__(self, node_features, output_dim, time_steps=100, inner_prod="default", activation_fn=None,
+                 attn_act=None, dropout=0):
+        super(Set2Vec, self).__init__()
+        self.nf = 2 * node_features
+        self.steps = time_steps
+        self.q_attn = nn.Linear(self.nf, self.nf, bias=False)
+        if "default" == inner_prod:
+            self.ip = True
+            self.e_attn = nn.Linear(self.nf, 1, bias=False)
+        elif "dot" == inner_prod:
+            raise NotImplementedError('mpnn_b200.Set2Vec: inner_prod="dot" fails in the reference itself; not built')
+        else:
+            raise ValueError("Invalid inner_prod type: {}".format(inner_prod))
+        self.add_module('lstmcell', LSTMCellHidden(self.nf * 2, self.nf))
+
+    def forward(self, input_set, mask=None, mprev=None, cprev=None):
+        input_set = _as_dense(input_set)
+        if mprev is not None or cprev is not None:
+            raise NotImplementedError("mpnn_b200.Set2Vec: explicit mprev/cprev are not supported (no fallback)")
+        W, b = self.lstmcell.cat_params()
+        return Set2VecFn.apply(input_set, mask, W, b, self.q_attn.weight, self.e_attn.weight.reshape(-1), self.steps)

@@ -1,0 +1,3 @@
+from ...modules import GraphLevelOutput, LSTMCellHidden, Set2Vec  # noqa: F401
+
+__all__ = ["GraphLevelOutput", "LSTMCellHidden", "Set2Vec"]

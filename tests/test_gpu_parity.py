@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the drop-in modules -> C-ABI) against
+  (1) the golden vectors frozen from the UNMODIFIED reference (tests/golden, oracle/make_golden.py),
+  (2) the CPU oracle on seeded config-shaped inputs,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances (stated per SURVEY.md 8c): integer/index work bit-exact; fp32 forward <= 1e-4 * max|ref|,
+gradients <= 1e-3 * max|ref| (the oracle's own fp32-vs-fp64 gap on the 50-layer trunk is ~2e-6)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from golden_util import Case, all_cases, leaf_sd, oracle_forward, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_OUT = 1e-4
+TOL_GRAD = 1e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mpnn_b200 import _lib
+    _lib.load()  # must exist: there is no fallback
+    return torch.device("cuda:0")
+
+
+def _cuda_inputs(case, dev, grad_keys):
+    ins = {}
+    for k, v in case.inputs.items():
+        t = v.clone().to(dev)
+        if k in grad_keys and t.dtype.is_floating_point:
+            t.requires_grad_(True)
+        ins[k] = t
+    return ins
+
+
+def _check_grads(module, case, ins, grad_keys, skip_params=()):
+    for k in grad_keys:
+        assert rel_err(ins[k].grad.cpu(), case.gin[k]) <= TOL_GRAD, "grad of input %s" % k
+    params = dict(module.named_parameters())
+    for k, g in case.gsd.items():
+        if k in skip_params:
+            continue
+        p = params[k]
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g)
+        assert rel_err(got, g) <= TOL_GRAD, "grad of parameter %s" % k
+
+
+# ------------------------------------------------------------------------------------------------
+# compaction: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 1, 6, 4), (5, 2, 40, 7), (4, 30, 70, 3)])
+def test_compaction_bit_exact(dev, shape):
+    from mpnn_b200 import graph, synthetic
+    from oracle import mpnn_oracle as O
+    B, lo, hi, ef = shape
+    b = synthetic.small_batch(B=B, n_lo=lo, n_hi=hi, afm_width=3, ef=ef, seed=B, weighted_adj=True)
+    bfm, adj = torch.from_numpy(b["bfm"]).clone(), torch.from_numpy(b["adj"]).clone()
+    if bfm.shape[1] > 1:
+        bfm[0, 0, 1] = 0       # adj-only edge
+        adj[-1, 0, 1] = 0      # bfm-only edge
+    want = O.compact_edges(bfm, adj)
+    el = graph.compact_edges(bfm.to(dev), adj.to(dev))
+    assert torch.equal(el.row_ptr.cpu(), want["row_ptr"])
+    assert torch.equal(el.edge_dst.cpu(), want["dst"])
+    assert torch.equal(el.edge_src.cpu(), want["src"])
+    assert torch.equal(el.edge_w.cpu(), want["w"])
+    assert torch.equal(el.rows[:el.E].cpu(), want["x"])
+    assert torch.equal(el.rows[el.E].cpu(), torch.zeros(ef))
+    # CSC: the same edges ordered by (sender, receiver)
+    order = torch.argsort(want["src"].long() * (1 << 32) + want["dst"].long())
+    assert torch.equal(el.csc_eid.cpu().long(), order)
+    cnt = torch.bincount(want["src"].long(), minlength=el.n_rows)
+    assert torch.equal((el.col_ptr[1:] - el.col_ptr[:-1]).cpu().long(), cnt)
+    # bfm-only compaction (adj = None)
+    el2 = graph.compact_edges(bfm.to(dev), None)
+    want2 = O.compact_edges(bfm, torch.zeros_like(adj))
+    assert torch.equal(el2.edge_src.cpu(), want2["src"]) and torch.equal(el2.row_ptr.cpu(), want2["row_ptr"])
+
+
+def test_compaction_empty_batch(dev):
+    from mpnn_b200 import graph
+    bfm = torch.zeros(2, 5, 5, 3, device=dev)
+    adj = torch.zeros(2, 5, 5, device=dev)
+    el = graph.compact_edges(bfm, adj)
+    assert el.E == 0 and int(el.row_ptr.abs().sum()) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone modules against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+def _build(case, dev):
+    from mpnn_b200 import modules as M
+    m = case.meta
+    cls = m["cls"]
+    if cls in ("EdgeNetwork", "EdgeNetworkD"):
+        mod = M.EdgeNetwork(m["nf"], m["ef"], m["mf"])
+    elif cls == "AttEdgeNetworkD":
+        mod = M.AttEdgeNetwork(m["nf"], m["ef"], m["mf"])
+    elif cls == "GGNNMsgPass":
+        mod = M.GGNNMsgPass(m["nf"], m["ef"], m["mf"])
+    elif cls in ("AdjMsgAgg", "WAdjMsgAgg", "AttMsgAgg"):
+        mod = getattr(M, cls)(1)
+    elif cls == "GRUUpdate":
+        mod = M.GRUUpdate(m["d"], m["d"])
+    elif cls == "MaskBatchNorm":
+        mod = M.MaskBatchNorm()
+    elif cls == "MaskBatchNorm1d":
+        mod = M.MaskBatchNorm1d(case.inputs["tensor"].shape[-1])
+    elif cls == "GraphLevelOutput":
+        mod = M.GraphLevelOutput(m["nf"], m["out"])
+    elif cls == "Set2Vec":
+        mod = M.Set2Vec(m["nf"], 99, time_steps=m["steps"])
+    else:
+        raise KeyError(cls)
+    mod.load_state_dict(case.sd, strict=True)
+    return mod.to(dev)
+
+
+DIRECT = [n for n in all_cases() if n.split("_")[0] in ("agg", "gru", "bn", "readout")] + \
+    [n for n in all_cases("msg_EdgeNetwork_")] + ["msg_GGNNMsgPass"]
+
+
+@pytest.mark.parametrize("name", DIRECT)
+def test_module_matches_reference_golden(dev, name):
+    case = Case(name)
+    mod = _build(case, dev)
+    cls = case.meta["cls"]
+    grad_keys = [k for k in case.gin if not (cls == "EdgeNetwork" and k == "bfm")]
+    ins = _cuda_inputs(case, dev, grad_keys)
+    if cls == "MaskBatchNorm1d":
+        mod.train(case.meta["mode"] == "train")
+    if cls in ("EdgeNetwork", "GGNNMsgPass"):
+        out = mod(ins["afm"], ins["bfm"])
+        out = out.materialize() if hasattr(out, "materialize") else out
+    elif cls in ("AdjMsgAgg", "WAdjMsgAgg", "AttMsgAgg"):
+        out = mod(ins["messages"], ins["adj"])
+    elif cls == "GRUUpdate":
+        out = mod(ins["messages"], ins["node_states"], ins["mask"])
+    elif cls in ("MaskBatchNorm", "MaskBatchNorm1d"):
+        out = mod(ins["tensor"], ins["mask"])
+    elif cls == "GraphLevelOutput":
+        out = mod(ins["input_set"], mask=ins.get("mask"))
+    elif cls == "Set2Vec":
+        out = mod(ins["input_set"], mask=ins["mask"])
+    assert out.shape == case.out["y"].shape
+    assert rel_err(out.detach().cpu(), case.out["y"]) <= TOL_OUT
+    (out * case.cot.to(dev)).sum().backward()
+    if cls == "AttMsgAgg":
+        grad_keys = ["messages"]  # d/d adj goes through the (constant) softmax over a size-1 axis: zero either way
+    _check_grads(mod, case, ins, grad_keys)
+    for k, v in case.out.items():
+        if k in ("running_mean", "running_var"):
+            assert rel_err(getattr(mod, k).cpu(), v) <= TOL_OUT, k
+
+
+# ------------------------------------------------------------------------------------------------
+# per-pair message functions fused with each aggregator: oracle (pinned by the golden vectors) on CPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", all_cases("msg_EdgeNetworkD_") + all_cases("msg_AttEdgeNetworkD_"))
+@pytest.mark.parametrize("agg", ["AdjMsgAgg", "WAdjMsgAgg", "AttMsgAgg"])
+def test_fused_message_aggregation(dev, name, agg):
+    from mpnn_b200 import modules as M, synthetic
+    from oracle import mpnn_oracle as O
+    case = Case(name)
+    m = case.meta
+    seed = 11 if m["cls"] == "EdgeNetworkD" else 12
+    batch = synthetic.small_batch(B=3, n_lo=1, n_hi=6, afm_width=m["nf"], ef=m["ef"], seed=seed, weighted_adj=True)
+    assert np.array_equal(batch["bfm"], case.inputs["bfm"].numpy())
+    adj = torch.from_numpy(batch["adj"])
+    # golden forward: contract the reference's dense per-pair output with the aggregation weights
+    if agg == "AdjMsgAgg":
+        w = adj
+    elif agg == "WAdjMsgAgg":
+        w = torch.softmax(adj, dim=-1)
+    else:
+        w = torch.ones_like(adj)
+    want_fwd = (case.out["y"] * w.unsqueeze(-1)).sum(-2)
+
+    net = _build(case, dev)
+    aggm = getattr(M, agg)(1).to(dev)
+    afm = case.inputs["afm"].clone().to(dev).requires_grad_(True)
+    bfm = case.inputs["bfm"].clone().to(dev).requires_grad_(True)
+    out = aggm(net(afm, bfm), adj.to(dev))
+    assert rel_err(out.detach().cpu(), want_fwd) <= TOL_OUT
+    cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(5))
+    (out * cot.to(dev)).sum().backward()
+
+    # gradients: oracle on CPU
+    sd = leaf_sd(case.sd)
+    a = case.inputs["afm"].clone().requires_grad_(True)
+    b = case.inputs["bfm"].clone().requires_grad_(True)
+    fn = O.edge_network_pairs if m["cls"] == "EdgeNetworkD" else O.att_edge_network_pairs
+    ref = (fn(a, b, sd, "", m["mf"]) * w.unsqueeze(-1)).sum(-2)
+    (ref * cot).sum().backward()
+    assert rel_err(afm.grad.cpu(), a.grad) <= TOL_GRAD
+    edge = ((case.inputs["bfm"] != 0).any(-1) | (adj != 0)).unsqueeze(-1).float()
+    if agg == "AdjMsgAgg":   # non-edge rows carry weight 0 -> the dense bfm gradient is exact everywhere
+        assert rel_err(bfm.grad.cpu(), b.grad) <= TOL_GRAD
+    else:                    # others: compared on the compacted rows (non-bonded rows: documented limitation)
+        assert rel_err(bfm.grad.cpu() * edge, b.grad * edge) <= TOL_GRAD
+    params = dict(net.named_parameters())
+    for k in case.gsd:
+        if k == "message_bias":
+            continue
+        g = sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])
+        got = params[k].grad.cpu() if params[k].grad is not None else torch.zeros_like(g)
+        assert rel_err(got, g) <= TOL_GRAD, k
+
+
+# ------------------------------------------------------------------------------------------------
+# compositions (caller loops) against the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+def _model_for(case, dev):
+    from mpnn_b200 import modules as M
+    from mpnn_b200.callers import MessagePassingModel
+    m = case.meta
+    cls = m["cls"]
+    if cls == "lipo_basic_model.BasicModel":
+        mod = MessagePassingModel("lipo", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=m["steps"])
+    elif cls == "model_basic":
+        mod = MessagePassingModel("basic", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=3)
+    elif cls == "model_normed_basic":
+        mod = MessagePassingModel("normed", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=2)
+    elif cls == "model_autoencoder_encode":
+        mod = MessagePassingModel("autoencoder", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=2)
+    elif cls == "att_model.BasicModel":
+        mod = MessagePassingModel("att", m["d"], m["ef"], m["d"], 1, 9, message_func=M.AttEdgeNetwork,
+                                  message_agg_func=getattr(M, m["agg"]), message_steps=m["steps"],
+                                  readout_func=M.Set2Vec, readout_opts={"time_steps": m["s2v_steps"]})
+    elif cls == "normed_encoded_basic_model.BasicModel":
+        ae = nn.Sequential(nn.Linear(30, 15, bias=False), nn.Tanh(), nn.Linear(15, 8))
+        be = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
+        mod = MessagePassingModel("normed_encoded", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=m["steps"],
+                                  atom_encoder=ae, bond_encoder=be)
+    else:
+        raise KeyError(cls)
+    missing = mod.load_state_dict(case.sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return mod.to(dev)
+
+
+@pytest.mark.parametrize("name", all_cases("model_"))
+def test_model_matches_reference_golden(dev, name):
+    case = Case(name)
+    mod = _model_for(case, dev)
+    mod.train()
+    ins = _cuda_inputs(case, dev, ["afm"])
+    out = mod(ins["afm"], ins["bfm"], ins["adj"], ins["mask"])
+    assert out.shape == case.out["y"].shape
+    assert rel_err(out.detach().cpu(), case.out["y"]) <= TOL_OUT
+    (out * case.cot.to(dev)).sum().backward()
+    _check_grads(mod, case, ins, ["afm"])
+    sd_now = mod.state_dict()
+    for k, v in case.out.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel_err(sd_now[k].cpu(), v) <= TOL_OUT, k
+
+
+# ------------------------------------------------------------------------------------------------
+# config-shaped inputs against the oracle + properties at full size
+# ------------------------------------------------------------------------------------------------
+def _oracle_sd(mod):
+    sd = {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+    return leaf_sd(sd)
+
+
+@pytest.mark.parametrize("cfg", ["lipo", "qm9"])
+def test_config_shaped_against_oracle(dev, cfg):
+    from mpnn_b200 import synthetic
+    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from oracle import mpnn_oracle as O
+    torch.manual_seed(317)
+    if cfg == "lipo":
+        batch = synthetic.make_batch("lipo", B=8)
+        d, ef = 19, 7
+        mod = MessagePassingModel("lipo", d, ef, d, 1, 38, message_steps=6)
+    else:
+        batch = synthetic.make_batch("qm9", B=32)
+        d, ef = 16, 7
+        mod = MessagePassingModel("normed", d, ef, d, 1, 64, message_steps=3)
+    mod.apply(kaiming_init)
+    sd = _oracle_sd(mod)
+    mod = mod.to(dev).train()
+    t = {k: torch.from_numpy(batch[k]) for k in ("afm", "bfm", "adj", "mask")}
+    afm = t["afm"].clone().to(dev).requires_grad_(True)
+    out = mod(afm, t["bfm"].to(dev), t["adj"].to(dev), t["mask"].to(dev))
+    a = t["afm"].clone().requires_grad_(True)
+    if cfg == "lipo":
+        ref = O.lipo_model(a, t["bfm"], t["adj"], t["mask"], sd, steps=6, buffers={})
+    else:
+        ref = O.normed_basic_model(a, t["bfm"], t["adj"], t["mask"], sd, steps=3)
+    assert rel_err(out.detach().cpu(), ref.detach()) <= TOL_OUT
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9))
+    (out * cot.to(dev)).sum().backward()
+    (ref * cot).sum().backward()
+    assert rel_err(afm.grad.cpu(), a.grad) <= TOL_GRAD
+    for k, p in mod.named_parameters():
+        if p.grad is None or sd[k].grad is None:
+            continue
+        assert rel_err(p.grad.cpu(), sd[k].grad) <= TOL_GRAD, k
+
+
+def test_full_size_properties(dev):
+    """BASELINE config 2 at full size (B=256): run-to-run bit-identical, masked rows exactly zero, graphs
+    independent (BN-free variant): permuting the batch permutes the outputs."""
+    from mpnn_b200 import synthetic, graph
+    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    torch.manual_seed(317)
+    batch = synthetic.make_batch("qm9")
+    t = {k: torch.from_numpy(batch[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+    mod = MessagePassingModel("basic", 16, 7, 16, 1, 64, message_steps=3)
+    mod.apply(kaiming_init)
+    mod = mod.to(dev)
+
+    def run(tt):
+        graph.clear_cache()
+        a = tt["afm"].clone().requires_grad_(True)
+        o = mod(a, tt["bfm"], tt["adj"], tt["mask"])
+        mod.zero_grad()
+        o.pow(2).sum().backward()
+        return o.detach(), a.grad.detach(), [p.grad.clone() for p in mod.parameters() if p.grad is not None]
+
+    o1, g1, p1 = run(t)
+    o2, g2, p2 = run(t)
+    assert torch.equal(o1, o2) and torch.equal(g1, g2)
+    for x, y in zip(p1, p2):
+        assert torch.equal(x, y)
+    perm = torch.randperm(t["afm"].shape[0], generator=torch.Generator().manual_seed(3)).to(dev)
+    tp = {k: v[perm].contiguous() for k, v in t.items()}
+    o3, _, _ = run(tp)
+    assert rel_err(o3.cpu(), o1[perm].cpu()) <= 1e-5
+    # the GRU writes exact zeros on padded rows
+    from mpnn_b200 import modules as M
+    uf = M.GRUUpdate(16, 16).to(dev)
+    h = uf(torch.randn_like(t["afm"]), torch.randn_like(t["afm"]), t["mask"])
+    assert float((h * (1 - t["mask"])).abs().max()) == 0.0
