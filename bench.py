@@ -1,0 +1,359 @@
+"""bench.py -- graphs/sec of one fwd+bwd training step of the message-passing path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config qm9|lipo|autoenc] [--impl ours|reference]
+
+Workload (N=1 default): BASELINE.json configs[1] -- normed_basic_model (one EdgeNetwork per step, AdjMsgAgg,
+masked GRU, MaskBatchNorm, GraphLevelOutput) on QM9-shaped synthetic graphs, batch 256 per GPU, d=16, ef=7,
+P=49, T=3, 12 regression targets, MSE + Adam.  A "step" = forward + loss + backward + optimizer step
+(+ gradient all-reduce when N>1; weak scaling: 256 graphs per GPU).
+
+JSON keys beyond the base contract:
+  roofline     the dominant kernel of the step (the fused edge-network trunk), algorithmic FLOPs / its
+               CUDA-event time measured live, against the MEASURED peaks (MEASURED_PEAKS.json)
+  cpu_baseline the oracle port of the reference's CPU path (oracle/mpnn_oracle.py), timed on this box's host
+               cores on a bounded sample of the same workload
+  e2e          the same metric through the public module API with HOST (pinned) inputs: H2D of the step's
+               padded batch and a D2H read of the loss inside the timed region
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "graphs/sec (fwd+bwd train step)"
+
+WORKLOADS = {
+    # name: (synthetic config, caller variant, d, ef, T, readout width, targets)
+    "qm9": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256,
+                desc="normed_basic_model + MaskBatchNorm, QM9-shaped (n<=29), B=256/GPU, d=16, ef=7, P=49, T=3"),
+    "lipo": dict(variant="lipo", d=19, ef=7, T=6, out=38, targets=1, B=32,
+                 desc="lipo_basic_model (HEAD form), Lipophilicity-shaped, B=32, d=19, ef=7, P=49, T=6"),
+    "autoenc": dict(variant="autoencoder", d=64, ef=8, T=3, out=128, targets=128, B=512,
+                    desc="basic_graph_autoencoder.encode, ZINC-shaped, B=512/GPU, d=64, ef=8, P=64, T=3"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+FP32_FFMA_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.5: CUDA-core fp32 peak of a B200 at max clock (nominal)
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, gpu_index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def build_model(w, dev):
+    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    torch.manual_seed(317)
+    body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"])
+    body.apply(kaiming_init)
+    head = torch.nn.Linear(w["out"], w["targets"])
+    return body.to(dev), head.to(dev)
+
+
+def algorithmic_step_work(w, n, e):
+    """forward FLOPs of the trunk (rows actually evaluated = e+1) and of one message-passing step."""
+    d, P = w["d"], 49 if w["ef"] == 7 else 64
+    ef = w["ef"]
+    trunk = 2.0 * (e + 1) * (ef * P + 50 * P * P)
+    step = 2.0 * e * P * d + 2.0 * n * P * d * d + 14.0 * n * d * d + 30.0 * n * d
+    q_step = 4.0 * e * P + 8.0 * e + 4.0 * n + 12.0 * n * d + 4.0 * (P * d * d + 6 * d * d + 8 * d)
+    return trunk, step, q_step
+
+
+def run_ours(args):
+    from mpnn_b200 import _lib, dist as D, graph, synthetic
+    from mpnn_b200.functional import EdgeTrunkFn
+    _lib.load()  # fail loudly if the CUDA library is missing
+    rank, world = D.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = WORKLOADS[args.config]
+    B = w["B"]
+    batch = synthetic.make_batch("qm9" if args.config == "qm9" else args.config, B=B, seed_offset=rank)
+    if args.config != "qm9":
+        batch["labels"] = np.random.RandomState(rank).normal(size=(B, w["targets"])).astype(np.float32)
+    n, e = batch["n_atoms"], batch["n_edges"]
+    keys = ("afm", "bfm", "adj", "mask", "labels")
+    host = {k: torch.from_numpy(batch[k]).pin_memory() for k in keys}
+    devb = {k: v.to(dev) for k, v in host.items()}
+    body, head = build_model(w, dev)
+    params = list(body.parameters()) + list(head.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    allreduce = D.FlatGradAllReduce(params)
+    # L2 (126 MB) is flushed between timed iterations by writing a 256 MB buffer
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(b):
+        graph.clear_cache()
+        opt.zero_grad(set_to_none=True)
+        out = head(body(b["afm"], b["bfm"], b["adj"], b["mask"]))
+        loss = torch.nn.functional.mse_loss(out, b["labels"])
+        loss.backward()
+        allreduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(devb)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 1)
+        ev[i][0].record()
+        step(devb)
+        ev[i][1].record()
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- e2e: host buffers, H2D + loss D2H inside the timed region ----------------------------
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(i & 1)
+        ev2[i][0].record()
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        loss = step(b)
+        _ = float(loss.item())
+        ev2[i][1].record()
+    barrier()
+    ms2 = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms2 = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel (edge-network trunk forward), timed alone with CUDA events ------
+    roof = None
+    launches = None
+    if rank == 0:
+        el = graph.compact_edges(devb["bfm"], devb["adj"])
+        net = body.mfs[0] if hasattr(body, "mfs") else body.mf
+        gw = [net.edge_map[i].weight for i in net._growth_idx]
+        gb = [net.edge_map[i].bias for i in net._growth_idx]
+        wt = net.edge_map[net._tied_idx][0].weight
+        with torch.no_grad():
+            for _ in range(3):
+                EdgeTrunkFn.apply(el.rows, wt, 50, *(gw + gb))
+            torch.cuda.synchronize()
+            reps = 10
+            tt = []
+            for _ in range(reps):
+                flush.fill_(0)
+                a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                EdgeTrunkFn.apply(el.rows, wt, 50, *(gw + gb))
+                b2.record()
+                torch.cuda.synchronize()
+                tt.append(a.elapsed_time(b2))
+        trunk_ms = float(np.median(tt))
+        trunk_flops, step_flops, q_step = algorithmic_step_work(w, n, el.E)
+        peaks = load_peaks()
+        achieved = trunk_flops / (trunk_ms * 1e-3) / 1e12
+        roof = {"kernel": "k_tied_fwd (edge-network trunk, fp32 FFMA)", "bound": "tensor", "achieved": achieved,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "traffic": None, "peak_source": peaks["source"] + " (cuBLAS bf16, sustained)",
+                "fp32_ffma_peak_tflops": FP32_FFMA_TFLOPS, "frac_of_fp32_ffma": achieved / FP32_FFMA_TFLOPS,
+                "ms_per_launch": trunk_ms, "algorithmic_flops_per_launch": trunk_flops,
+                "rows_evaluated": el.E + 1, "mp_step_fwd_flops": step_flops, "mp_step_fwd_bytes": q_step}
+        launches = count_launches(lambda: step(devb))
+
+    if rank != 0:
+        return
+    gb_in = sum(v.numel() * v.element_size() for v in host.values())
+    line = {
+        "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "graphs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "graphs_per_gpu": B, "atoms_per_gpu": n, "directed_edges_per_gpu": e,
+                   "optimizer": "Adam", "loss": "MSE", "l2_flush": "256 MB write between timed iterations",
+                   "parallelism": "dp%d" % world},
+        "e2e": {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": gb_in,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.config, budget_s=20.0)
+    print(json.dumps(line))
+
+
+def count_launches(fn):
+    """number of kernels launched by one step (torch profiler, CUDA activity)"""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        return int(sum(ev.count for ev in prof.key_averages()
+                       if ev.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in ev.key.lower()
+                       and "memset" not in ev.key.lower()))
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port): same model, same synthetic batch, torch CPU fp32, all host cores
+# ---------------------------------------------------------------------------------------------------
+def _oracle_step_fn(config, B):
+    from mpnn_b200 import synthetic
+    from mpnn_b200.callers import kaiming_init, MessagePassingModel
+    from oracle import mpnn_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import leaf_sd
+    w = WORKLOADS[config]
+    batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=B)
+    torch.manual_seed(317)
+    body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"])
+    body.apply(kaiming_init)
+    sd = leaf_sd({k: v.detach().clone() for k, v in body.state_dict().items()})
+    head = torch.nn.Linear(w["out"], w["targets"])
+    leaves, seen = [], set()
+    for v in list(sd.values()) + list(head.parameters()):
+        if v.dtype.is_floating_point and v.requires_grad and id(v) not in seen:
+            seen.add(id(v))
+            leaves.append(v)
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    t = {k: torch.from_numpy(batch[k]) for k in ("afm", "bfm", "adj", "mask")}
+    labels = torch.from_numpy(batch["labels"]) if config == "qm9" else torch.zeros(B, w["targets"])
+    buffers = {}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        a = (t["afm"], t["bfm"], t["adj"], t["mask"])
+        if w["variant"] == "normed":
+            y = O.normed_basic_model(*a, sd=sd, steps=w["T"])
+        elif w["variant"] == "lipo":
+            y = O.lipo_model(*a, sd=sd, steps=w["T"], buffers=buffers)
+        else:
+            y = O.basic_model(*a, sd=sd, steps=w["T"], chain_state=False)
+        loss = torch.nn.functional.mse_loss(head(y), labels)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    return step, B
+
+
+def cpu_baseline(config, budget_s=20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = 32 if config != "lipo" else 32
+    step, B = _oracle_step_fn(config, B)
+    step()  # warm-up
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        step()
+        k += 1
+        if time.perf_counter() - t0 > budget_s or k >= 50:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": B * k / dt, "unit": "graphs/s", "cores": cores, "kind": "port",
+            "sample": "%d fwd+bwd+Adam steps of the oracle port (dense B*N*N edge embedding, as the reference) on a "
+                      "B=%d slice of the workload, torch CPU fp32, %d threads" % (k, B, cores),
+            "ms_per_step": dt / k * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = WORKLOADS[args.config]
+    B = 32
+    step, B = _oracle_step_fn(args.config, B)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = B * steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "graphs/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": "B=%d graphs per step (bounded CPU sample of the same workload)" % B},
+        "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps at B=%d, oracle port of the reference's PyTorch CPU path" % (steps, B)},
+        "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="qm9", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,12 +40,16 @@ def _check_grads(module, case, ins, grad_keys, skip_params=()):
     for k in grad_keys:
         assert rel_err(ins[k].grad.cpu(), case.gin[k]) <= TOL_GRAD, "grad of input %s" % k
     params = dict(module.named_parameters())
+    # gradients that are mathematically zero (e.g. a bias feeding a batch norm) are pure rounding noise on both
+    # sides: allow an absolute floor of 1e-6 x the largest parameter gradient of the case
+    gscale = max([float(g.abs().max()) for g in case.gsd.values()] + [0.0])
     for k, g in case.gsd.items():
         if k in skip_params:
             continue
         p = params[k]
         got = p.grad.cpu() if p.grad is not None else torch.zeros_like(g)
-        assert rel_err(got, g) <= TOL_GRAD, "grad of parameter %s" % k
+        diff = float((got.double() - g.double()).abs().max())
+        assert diff <= TOL_GRAD * float(g.abs().max()) + 1e-6 * gscale, "grad of parameter %s" % k
 
 
 # ------------------------------------------------------------------------------------------------
@@ -297,10 +301,12 @@ def test_config_shaped_against_oracle(dev, cfg):
     (out * cot.to(dev)).sum().backward()
     (ref * cot).sum().backward()
     assert rel_err(afm.grad.cpu(), a.grad) <= TOL_GRAD
+    gscale = max(float(v.grad.abs().max()) for v in sd.values() if getattr(v, "grad", None) is not None)
     for k, p in mod.named_parameters():
         if p.grad is None or sd[k].grad is None:
             continue
-        assert rel_err(p.grad.cpu(), sd[k].grad) <= TOL_GRAD, k
+        diff = float((p.grad.cpu().double() - sd[k].grad.double()).abs().max())
+        assert diff <= TOL_GRAD * float(sd[k].grad.abs().max()) + 1e-6 * gscale, k
 
 
 def test_full_size_properties(dev):
