@@ -67,6 +67,51 @@ int mpnn_compact_fill(const float* bfm, const float* adj, int B, int N, int ef, 
 int mpnn_scatter_edge_rows(const float* d_edge_x, const int* edge_dst, const int* edge_src, int E, int N, int ef,
                            float* dense, mpnn_stream_t stream);
 
+/* ---- a0 (cont.): exact de-duplication of the compacted bond rows + stable grouping of edges by distinct row.
+ * Bond features are categorical (reference mol_graph/mol_graph.py:74-90), and edge_map is a pure function of the
+ * row (edge_network.py:14-21,36-37), so evaluating it once per distinct row is exact.  Rows are compared by bit
+ * pattern; distinct rows are numbered by first occurrence.  Nothing is read back to the host. */
+size_t mpnn_dedup_workspace_bytes(int edge_capacity, int unique_capacity);
+/* n_edges_ptr: DEVICE pointer to the edge count (row_ptr + B*N).  urows [unique_capacity+1, ef] must be pre-zeroed
+ * (rows >= U stay zero; row unique_capacity is the zero bond row x_0).  counts [4] = {E, U, overflow, 0}. */
+int mpnn_dedup_rows(const float* rows, const int* n_edges_ptr, int edge_capacity, int ef, int unique_capacity,
+                    int* uid, float* urows, int* counts, int sort, int* type_ptr, int* type_eid, int* type_pos,
+                    void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+size_t mpnn_type_sort_workspace_bytes(int edge_capacity, int unique_capacity);
+int mpnn_type_sort(const int* uid, const int* counts, int edge_capacity, int unique_capacity, int* type_ptr,
+                   int* type_eid, int* type_pos, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
+/* ---- a1-a3, a5 on the distinct rows ("typed" path, mpnn_b200/csrc/typed.cu) -----------------------------------
+ * table T[u][l][k] = edge_map(distinct row u).view(mf, nf)[k][l]  (edge_network.py:21,37), padded to DP x DP;
+ * tableT is its transpose.  DP = mpnn_typed_dp(nf, mf) (power of two >= 8; -1: widths > 32, not served here). */
+int mpnn_typed_dp(int nf, int mf);
+int mpnn_graph_sum(const float* X, int B, int N, int width, float* out, mpnn_stream_t stream);
+int mpnn_table_from_flat(const float* flat, int R, int nf, int mf, float* table, float* tableT, mpnn_stream_t stream);
+int mpnn_table_to_flat(const float* dT, int R, int nf, int mf, float* dflat, mpnn_stream_t stream);
+/* fused growth layers + n_tied tied layers + last Linear on R distinct rows (trunk width P <= 64) */
+int mpnn_enet_supported(int ef, int n_growth, int P);
+long long mpnn_enet_saved_floats(int R, int n_growth, int n_tied);
+size_t mpnn_enet_workspace_bytes(int R, int ef, int n_growth, int P);
+int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
+                  const float* const* growth_b, const float* w_tied, int P, int n_tied, const float* w_last,
+                  const float* b_last, int nf, int mf, float* saved, float* table, float* tableT,
+                  mpnn_stream_t stream);
+int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* const* growth_w, const float* w_tied,
+                  int P, int n_tied, const float* w_last, int nf, int mf, const float* saved, const float* dT,
+                  float* const* d_growth_w, float* const* d_growth_b, float* d_w_tied, float* d_w_last,
+                  float* d_b_last, float* d_rows, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* message function + aggregation as a gather over the CSR (edge_network.py:42-52 + adjacent_message_agg.py:18).
+ * S != NULL ([B, nf] per-graph sums of H) selects the HEAD form (edge_network.py:50-51: all pairs + beta). */
+size_t mpnn_tmsg_bwd_workspace_bytes(int edge_capacity, int unique_capacity, int nf, int mf, int B);
+int mpnn_tmsg_fwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, const float* H,
+                  const float* table, const float* S, const float* beta, int n_rows, int N, int nf, int mf,
+                  int zero_type, float* M, mpnn_stream_t stream);
+int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, const int* edge_src, const int* edge_dst,
+                  const int* uid, const int* type_ptr, const int* type_eid, const int* counts, const float* alpha,
+                  const float* H, const float* table, const float* tableT, const float* S, int n_rows, int B, int N,
+                  int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dH, float* dT,
+                  void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
 /* ---- a1/a2: edge-network trunk = edge_map[:-1] (edge_network.py:14-21,36-37) on compacted rows -------- */
 long long mpnn_edge_trunk_saved_floats(int R, int ef, int n_growth, int P, int n_tied, long long* x_offset, int* ldx);
 size_t mpnn_edge_trunk_workspace_bytes(int R, int ef, int n_growth, int P);

@@ -28,6 +28,24 @@ SIGNATURES = {
     "mpnn_compact_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_compact_count": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mpnn_compact_fill": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "mpnn_dedup_workspace_bytes": (_Z, [_I, _I]),
+    "mpnn_dedup_rows": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_type_sort_workspace_bytes": (_Z, [_I, _I]),
+    "mpnn_type_sort": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_typed_dp": (_I, [_I, _I]),
+    "mpnn_graph_sum": (_I, [_P, _I, _I, _I, _P, _P]),
+    "mpnn_table_from_flat": (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    "mpnn_table_to_flat": (_I, [_P, _I, _I, _I, _P, _P]),
+    "mpnn_enet_supported": (_I, [_I, _I, _I]),
+    "mpnn_enet_saved_floats": (_L, [_I, _I, _I]),
+    "mpnn_enet_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "mpnn_enet_fwd": (_I, [_P, _I, _I, _I, _PP, _PP, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "mpnn_enet_bwd": (_I, [_P, _I, _I, _I, _PP, _P, _I, _I, _P, _I, _I, _P, _P, _PP, _PP, _P, _P, _P, _P, _P, _Z,
+                           _P]),
+    "mpnn_tmsg_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "mpnn_tmsg_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "mpnn_tmsg_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P,
+                           _P, _P, _P, _Z, _P]),
     "mpnn_scatter_edge_rows": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "mpnn_edge_trunk_saved_floats": (_L, [_I, _I, _I, _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_I)]),
     "mpnn_edge_trunk_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -1,0 +1,745 @@
+// "Typed" message path: the edge network evaluated once per DISTINCT bond row (csrc/dedup.cu), its last Linear
+// (edge_network.py:21) folded into a table of U+1 small matrices, and the message function + neighbour
+// aggregation (edge_network.py:42-52 + adjacent_message_agg.py:18) as one gather kernel over the CSR:
+//
+//     T[u][l][k] = B_last[k*nf+l] + sum_p W_last[k*nf+l, p] * x_u[p]          (x_u = trunk output of distinct row u)
+//     M[i, k]    = sum_{e in E(i)} alpha_e * sum_l T[uid_e][l][k] * H[src_e, l]
+//                  (+ sum_l T[zero][l][k] * (S_b[l] - sum_{e in E(i)} H[src_e, l]) + beta[k]      HEAD form)
+//
+// This is the same contraction as csrc/message.cu (edge-embedding (x) neighbour-state against the shared weight),
+// with the contraction over p hoisted out of the per-edge work: exact, because x depends on the bond row only.
+// Per-edge d x d matrices are never formed; the table has one matrix per distinct bond row (a few dozen).
+// Feature widths up to 32 run here on CUDA cores (HBM/L1-bound gather); wider states use csrc/typed_mma.cu.
+//
+// All reductions have a fixed order (CSC lists, type-sorted chunks): results are bit-reproducible.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// per-graph column sums: out[b, c] = sum_i X[b, i, c]
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_graph_sum(const float* __restrict__ X, int B, int N, int w, float* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * w) return;
+  int b = t / w, c = t - b * w;
+  const float* p = X + (size_t)b * N * w + c;
+  float s = 0.f;
+  for (int i = 0; i < N; ++i) s += p[(size_t)i * w];
+  out[t] = s;
+}
+
+struct TMsg {
+  const int* row_ptr;   // CSR by receiver [n_rows+1]
+  const int* edge_src;  // [E]
+  const int* edge_dst;  // [E]
+  const int* uid;       // [E]
+  const float* alpha;   // [E] or null (1)
+  const float* H;       // [n_rows, nf] sender states
+  const float* table;   // [(ucap+1)][DP][DP]  T[u][l][k]
+  const float* tableT;  // [(ucap+1)][DP][DP]  T[u][k][l]
+  const float* S;       // [B, nf] per-graph sums of H (HEAD form) or null
+  const float* beta;    // [mf] or null
+  int n_rows, N, nf, mf, zero_type;
+};
+
+template <int DP>
+__device__ __forceinline__ uint32_t group_mask(int lane) {
+  if constexpr (DP == 32) {
+    return 0xffffffffu;
+  } else {
+    return ((1u << DP) - 1u) << ((lane / DP) * DP);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward: one group of DP lanes per receiver row, lane k owns M[i, k]
+// ---------------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) k_tmsg_fwd(TMsg a, float* __restrict__ M) {
+  const int lane = threadIdx.x & 31;
+  const int k = lane % DP;
+  const uint32_t gm = group_mask<DP>(lane);
+  const int groups_per_block = 256 / DP;
+  for (int i = blockIdx.x * groups_per_block + threadIdx.x / DP; i < a.n_rows; i += gridDim.x * groups_per_block) {
+    const int eb = a.row_ptr[i], ee = a.row_ptr[i + 1];
+    float acc = 0.f, hs = 0.f;
+    for (int e = eb; e < ee; ++e) {
+      const int j = __ldg(a.edge_src + e);
+      const int u = __ldg(a.uid + e);
+      const float al = a.alpha ? __ldg(a.alpha + e) : 1.f;
+      const float hj = k < a.nf ? __ldg(a.H + (size_t)j * a.nf + k) : 0.f;
+      hs += hj;
+      const float* T = a.table + (size_t)u * DP * DP + k;
+      float s = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < a.nf; ++l) s = fmaf(__ldg(T + l * DP), __shfl_sync(gm, hj, l, DP), s);
+      acc = fmaf(al, s, acc);
+    }
+    if (a.S) {  // all non-bonded pairs of the row share the zero bond row (HEAD form, edge_network.py:50)
+      const int b = i / a.N;
+      const float q = (k < a.nf ? __ldg(a.S + (size_t)b * a.nf + k) : 0.f) - hs;
+      const float* T = a.table + (size_t)a.zero_type * DP * DP + k;
+      float s = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < a.nf; ++l) s = fmaf(__ldg(T + l * DP), __shfl_sync(gm, q, l, DP), s);
+      acc += s;
+    }
+    if (k < a.mf) M[(size_t)i * a.mf + k] = acc + (a.beta ? a.beta[k] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward w.r.t. the sender states: one group per sender row j (CSC), lane l owns dH[j, l]
+//   dH[j,l] = sum_{e: src_e = j} alpha_e sum_k (T[u_e] - [HEAD] T[zero])[l][k] dM[dst_e, k]  (+ [HEAD] dS_b[l])
+// ---------------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256) k_tmsg_bwd_src(TMsg a, const int* __restrict__ col_ptr,
+                                                      const int* __restrict__ csc_eid, const float* __restrict__ dM,
+                                                      const float* __restrict__ Dsum /*[B, mf] or null*/,
+                                                      float* __restrict__ dH) {
+  const int lane = threadIdx.x & 31;
+  const int l = lane % DP;
+  const uint32_t gm = group_mask<DP>(lane);
+  const int groups_per_block = 256 / DP;
+  const bool head = a.S != nullptr;
+  const float* T0 = a.tableT + (size_t)a.zero_type * DP * DP + l;
+  for (int j = blockIdx.x * groups_per_block + threadIdx.x / DP; j < a.n_rows; j += gridDim.x * groups_per_block) {
+    const int cb = col_ptr[j], ce = col_ptr[j + 1];
+    float acc = 0.f;
+    for (int c = cb; c < ce; ++c) {
+      const int e = __ldg(csc_eid + c);
+      const int i = __ldg(a.edge_dst + e);
+      const int u = __ldg(a.uid + e);
+      const float al = a.alpha ? __ldg(a.alpha + e) : 1.f;
+      const float dm = l < a.mf ? __ldg(dM + (size_t)i * a.mf + l) : 0.f;
+      const float* T = a.tableT + (size_t)u * DP * DP + l;
+      float s = 0.f;
+      if (head) {
+#pragma unroll 8
+        for (int k = 0; k < a.mf; ++k)
+          s = fmaf(__ldg(T + k * DP) - __ldg(T0 + k * DP), __shfl_sync(gm, dm, k, DP), s);
+      } else {
+#pragma unroll 8
+        for (int k = 0; k < a.mf; ++k) s = fmaf(__ldg(T + k * DP), __shfl_sync(gm, dm, k, DP), s);
+      }
+      acc = fmaf(al, s, acc);
+    }
+    if (head) {
+      const int b = j / a.N;
+      const float ds = l < a.mf ? __ldg(Dsum + (size_t)b * a.mf + l) : 0.f;
+      float s = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < a.mf; ++k) s = fmaf(__ldg(T0 + k * DP), __shfl_sync(gm, ds, k, DP), s);
+      acc += s;
+    }
+    if (l < a.nf) dH[(size_t)j * a.nf + l] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward w.r.t. the table, level 1: chunks of CH edges in type-sorted order; partial of the (chunk c,
+// type u) pair goes to slot c + u (pairs are strictly increasing in c + u along the sorted list).
+//   dT[u][l][k] = sum_{e in type u} alpha_e H[src_e, l] dM[dst_e, k]
+// ---------------------------------------------------------------------------------------------------
+constexpr int CH = 256;  // edges per chunk
+constexpr int SB = 32;   // edges staged per round
+
+template <int DP>
+__global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __restrict__ counts, int cap,
+                                                        const int* __restrict__ type_eid, const float* __restrict__ dM,
+                                                        float* __restrict__ part) {
+  constexpr int OPT = (DP * DP + 255) / 256;  // outputs per thread (DP=32: 4, else 1)
+  __shared__ float g[SB][DP + 1];
+  __shared__ float m[SB][DP + 1];
+  __shared__ int ty[SB];
+  const int E = min(counts[0], cap);
+  const int p0 = blockIdx.x * CH;
+  if (p0 >= E) return;
+  const int p1 = min(p0 + CH, E);
+  const int tid = threadIdx.x;
+  // thread -> (l, k0..k0+OPT): consecutive threads walk k first
+  const int o0 = tid * OPT;
+  const int l = o0 / DP, k0 = o0 % DP;
+  const bool active = o0 < DP * DP;
+  float acc[OPT];
+#pragma unroll
+  for (int q = 0; q < OPT; ++q) acc[q] = 0.f;
+  int cur = -1;
+  for (int base = p0; base < p1; base += SB) {
+    const int nb = min(SB, p1 - base);
+    __syncthreads();
+    for (int idx = tid; idx < nb * DP; idx += 256) {
+      const int s = idx / DP, c = idx - s * DP;
+      const int e = type_eid[base + s];
+      const float al = a.alpha ? a.alpha[e] : 1.f;
+      g[s][c] = c < a.nf ? al * a.H[(size_t)a.edge_src[e] * a.nf + c] : 0.f;
+      m[s][c] = c < a.mf ? dM[(size_t)a.edge_dst[e] * a.mf + c] : 0.f;
+      if (c == 0) ty[s] = a.uid[e];
+    }
+    __syncthreads();
+    if (active) {
+      for (int s = 0; s < nb; ++s) {
+        const int u = ty[s];
+        if (u != cur) {
+          if (cur >= 0) {
+            float* o = part + (size_t)(blockIdx.x + cur) * DP * DP + o0;
+#pragma unroll
+            for (int q = 0; q < OPT; ++q) {
+              o[q] = acc[q];
+              acc[q] = 0.f;
+            }
+          }
+          cur = u;
+        }
+        const float gv = g[s][l];
+#pragma unroll
+        for (int q = 0; q < OPT; ++q) acc[q] = fmaf(gv, m[s][k0 + q], acc[q]);
+      }
+    }
+  }
+  if (active && cur >= 0) {
+    float* o = part + (size_t)(blockIdx.x + cur) * DP * DP + o0;
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) o[q] = acc[q];
+  }
+}
+
+// level 2: one block per type; sums the type's chunk partials in chunk order.  dT [(ucap+1)][DP][DP].
+template <int DP>
+__global__ void __launch_bounds__(256) k_tmsg_bwd_table_reduce(const int* __restrict__ type_ptr,
+                                                               const float* __restrict__ part, int zero_type,
+                                                               float* __restrict__ dT) {
+  const int u = blockIdx.x;
+  float* out = dT + (size_t)u * DP * DP;
+  int b = 0, e = 0;
+  if (u < zero_type) {
+    b = type_ptr[u];
+    e = type_ptr[u + 1];
+  }
+  for (int o = threadIdx.x; o < DP * DP; o += 256) {
+    float s = 0.f;
+    if (e > b) {
+      const int c0 = b / CH, c1 = (e - 1) / CH;
+      const float* p = part + (size_t)(c0 + u) * DP * DP + o;
+#pragma unroll 4
+      for (int c = c0; c <= c1; ++c, p += DP * DP) s += *p;
+    }
+    out[o] = s;
+  }
+}
+
+// HEAD form: dT[zero][l][k] = sum_b S[b,l] Dsum[b,k] - sum_{u < zero} dT[u][l][k]     (one block)
+template <int DP>
+__global__ void __launch_bounds__(256) k_tmsg_bwd_table_zero(const float* __restrict__ S, const float* __restrict__ Dsum,
+                                                             int B, int nf, int mf, int zero_type,
+                                                             float* __restrict__ dT) {
+  for (int o = threadIdx.x; o < DP * DP; o += 256) {
+    const int l = o / DP, k = o % DP;
+    float s = 0.f;
+    if (l < nf && k < mf)
+      for (int b = 0; b < B; ++b) s = fmaf(S[(size_t)b * nf + l], Dsum[(size_t)b * mf + k], s);
+    float t = 0.f;
+    for (int u = 0; u < zero_type; ++u) t += dT[(size_t)u * DP * DP + o];
+    dT[(size_t)zero_type * DP * DP + o] = s - t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// table <-> flat last-layer output.  flat[u, k*nf + l] (what Linear(P, nf*mf) returns, edge_network.py:21,37)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_table_from_flat(const float* __restrict__ flat, int R, int nf, int mf, int DP,
+                                  float* __restrict__ table, float* __restrict__ tableT) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * DP * DP) return;
+  int k = (int)(t % DP), l = (int)((t / DP) % DP);
+  int u = (int)(t / ((long long)DP * DP));
+  float v = (k < mf && l < nf) ? flat[(size_t)u * mf * nf + (size_t)k * nf + l] : 0.f;
+  table[t] = v;
+  tableT[((size_t)u * DP + k) * DP + l] = v;
+}
+
+__global__ void k_table_to_flat(const float* __restrict__ dT, int R, int nf, int mf, int DP,
+                                float* __restrict__ dflat) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * mf * nf) return;
+  int l = (int)(t % nf), k = (int)((t / nf) % mf);
+  int u = (int)(t / ((long long)mf * nf));
+  dflat[t] = dT[((size_t)u * DP + l) * DP + k];
+}
+
+// ===================================================================================================
+// Fused edge network on the distinct rows, P <= 64:  growth layers -> 50 tied layers -> table.
+// One CTA per RT rows; thread (r, o) = (tid / 64, tid % 64).  W_tied^T resident in shared memory.
+// ===================================================================================================
+constexpr int RT = 4;     // rows per CTA
+constexpr int PW = 64;    // max padded trunk width handled here
+constexpr int MAXG = 4;
+
+struct ENet {
+  const float* rows;    // [R, ef]
+  const float* gw[MAXG];
+  const float* gb[MAXG];
+  const float* w_tied;  // [P, P]
+  const float* w_last;  // [mf*nf, P]
+  const float* b_last;  // [mf*nf]
+  int R, ef, G, P, L, nf, mf, DP;
+  int gin[MAXG], gout[MAXG];
+};
+
+// saved layout (floats): acts[(G + L + 1)][R][PW] : slot 0 = input rows (zero padded), 1..G growth outputs,
+// G+1..G+L tied outputs (slot G+L = x)
+__global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ acts, float* __restrict__ table,
+                                                  float* __restrict__ tableT) {
+  __shared__ __align__(16) float Wt[PW * PW];      // Wt[i][o] = W[o][i]
+  __shared__ __align__(16) float A[2][RT][PW];
+  const int tid = threadIdx.x;
+  const int r = tid >> 6, o = tid & 63;
+  const int row0 = blockIdx.x * RT;
+  const int row = row0 + r;
+  const bool live = row < n.R;
+  const int P = n.P;
+  for (int idx = tid; idx < PW * PW; idx += 256) {
+    int oo = idx / PW, ii = idx - oo * PW;
+    Wt[ii * PW + oo] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
+  }
+  float v = (live && o < n.ef) ? n.rows[(size_t)row * n.ef + o] : 0.f;
+  A[0][r][o] = v;
+  if (live) acts[((size_t)0 * n.R + row) * PW + o] = v;
+  __syncthreads();
+  int cur = 0;
+  int slot = 1;
+  for (int g = 0; g < n.G; ++g, ++slot) {
+    float acc = 0.f;
+    if (o < n.gout[g]) {
+      const float* w = n.gw[g] + (size_t)o * n.gin[g];
+      acc = n.gb[g][o];
+      for (int i = 0; i < n.gin[g]; ++i) acc = fmaf(__ldg(w + i), A[cur][r][i], acc);
+      acc = fmaxf(acc, 0.f);
+    }
+    A[cur ^ 1][r][o] = acc;
+    if (live) acts[((size_t)slot * n.R + row) * PW + o] = acc;
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int l = 0; l < n.L; ++l, ++slot) {
+    float acc = 0.f;
+    const float4* ap = reinterpret_cast<const float4*>(&A[cur][r][0]);
+    const float* wp = Wt + o;
+#pragma unroll 4
+    for (int i4 = 0; i4 < PW / 4; ++i4) {
+      float4 a4 = ap[i4];
+      acc = fmaf(a4.x, wp[(i4 * 4 + 0) * PW], acc);
+      acc = fmaf(a4.y, wp[(i4 * 4 + 1) * PW], acc);
+      acc = fmaf(a4.z, wp[(i4 * 4 + 2) * PW], acc);
+      acc = fmaf(a4.w, wp[(i4 * 4 + 3) * PW], acc);
+    }
+    acc = fmaxf(acc, 0.f);
+    A[cur ^ 1][r][o] = acc;
+    if (live) acts[((size_t)slot * n.R + row) * PW + o] = acc;
+    __syncthreads();
+    cur ^= 1;
+  }
+  // table rows of this CTA's distinct rows: T[u][l][k] = B[k*nf+l] + W_last[k*nf+l, :] . x_u
+  const int DP = n.DP;
+  const int nout = n.mf * n.nf;
+  for (int q = tid; q < RT * DP * DP; q += 256) {
+    const int rr = q / (DP * DP);
+    const int lk = q - rr * DP * DP;
+    const int l = lk / DP, k = lk - l * DP;
+    const int u = row0 + rr;
+    if (u >= n.R) continue;
+    float acc = 0.f;
+    if (l < n.nf && k < n.mf) {
+      const int f = k * n.nf + l;
+      const float* w = n.w_last + (size_t)f * P;
+      acc = n.b_last[f];
+      for (int p = 0; p < P; ++p) acc = fmaf(__ldg(w + p), A[cur][rr][p], acc);
+    }
+    table[((size_t)u * DP + l) * DP + k] = acc;
+    tableT[((size_t)u * DP + k) * DP + l] = acc;
+  }
+  (void)nout;
+}
+
+// backward of the fused edge network.  Per CTA (RT rows): dx = dT . W_last, tied layers (dW_tied partial in
+// registers: thread owns a 4 x 4 micro-tile of the 64 x 64 gradient), growth layers; partials per CTA.
+// partial layout per CTA (floats): [PW*PW tied] then for each growth layer g: [gout*gin weights][gout bias]
+__global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restrict__ acts, const float* __restrict__ dT,
+                                                  float* __restrict__ partial, int partial_stride,
+                                                  float* __restrict__ d_rows /*[R, ef] or null*/) {
+  __shared__ __align__(16) float Ws[PW * (PW + 4)];  // natural W[o][i], row stride PW+4
+  __shared__ __align__(16) float D[RT][PW];          // delta (masked gradient of the layer output)
+  __shared__ __align__(16) float Ap[RT][PW];         // a_{l-1}
+  __shared__ __align__(16) float dA[RT][PW];
+  const int WS = PW + 4;
+  const int tid = threadIdx.x;
+  const int r = tid >> 6, o = tid & 63;
+  const int row0 = blockIdx.x * RT;
+  const int row = row0 + r;
+  const bool live = row < n.R;
+  const int P = n.P, DP = n.DP;
+  for (int idx = tid; idx < PW * PW; idx += 256) {
+    int oo = idx / PW, ii = idx - oo * PW;
+    Ws[oo * WS + ii] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
+  }
+  // dx[r][p] = sum_{k,l} dT[u][l][k] W_last[k*nf+l, p]
+  {
+    float acc = 0.f;
+    if (live && o < P) {
+      const float* dt = dT + (size_t)row * DP * DP;
+      for (int k = 0; k < n.mf; ++k)
+        for (int l = 0; l < n.nf; ++l)
+          acc = fmaf(__ldg(dt + l * DP + k), __ldg(n.w_last + (size_t)(k * n.nf + l) * P + o), acc);
+    }
+    dA[r][o] = acc;
+  }
+  const int nslots = n.G + n.L + 1;
+  auto act = [&](int slot, int rr, int c) -> float {
+    int rw = row0 + rr;
+    return rw < n.R ? acts[((size_t)slot * n.R + rw) * PW + c] : 0.f;
+  };
+  Ap[r][o] = act(nslots - 1, r, o);
+  __syncthreads();
+  // dW_tied micro-tile owned by this thread: rows og*4.., cols ig*4..
+  const int og = tid >> 4, ig = tid & 15;
+  float accW[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) accW[a][b] = 0.f;
+  for (int l = n.L; l >= 1; --l) {
+    const int slot = n.G + l;  // output slot of tied layer l; its input is slot-1
+    const float aout = Ap[r][o];
+    const float dl = aout > 0.f ? dA[r][o] : 0.f;
+    const float aprev = act(slot - 1, r, o);
+    __syncthreads();
+    D[r][o] = dl;
+    Ap[r][o] = aprev;
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < RT; ++rr) {
+      float4 d4 = *reinterpret_cast<const float4*>(&D[rr][og * 4]);
+      float4 a4 = *reinterpret_cast<const float4*>(&Ap[rr][ig * 4]);
+      float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) accW[a][b] = fmaf(dv[a], av[b], accW[a][b]);
+    }
+    // dA_prev[r][i=o] = sum_oo delta[r][oo] W[oo][o]
+    float acc = 0.f;
+    const float4* dp = reinterpret_cast<const float4*>(&D[r][0]);
+#pragma unroll 4
+    for (int q = 0; q < PW / 4; ++q) {
+      float4 d4 = dp[q];
+      acc = fmaf(d4.x, Ws[(q * 4 + 0) * WS + o], acc);
+      acc = fmaf(d4.y, Ws[(q * 4 + 1) * WS + o], acc);
+      acc = fmaf(d4.z, Ws[(q * 4 + 2) * WS + o], acc);
+      acc = fmaf(d4.w, Ws[(q * 4 + 3) * WS + o], acc);
+    }
+    dA[r][o] = acc;  // own element only: no hazard with other threads' reads of D/Ap
+  }
+  float* part = partial + (size_t)blockIdx.x * partial_stride;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    *reinterpret_cast<float4*>(part + (og * 4 + a) * PW + ig * 4) =
+        make_float4(accW[a][0], accW[a][1], accW[a][2], accW[a][3]);
+  size_t poff = (size_t)PW * PW;
+  // growth layers, last to first.  Ap holds the output of growth layer g (= tied input) at loop entry.
+  for (int g = n.G - 1; g >= 0; --g) {
+    const int slot = g + 1;
+    const float aout = Ap[r][o];
+    const float dl = (o < n.gout[g] && aout > 0.f) ? dA[r][o] : 0.f;
+    const float aprev = act(slot - 1, r, o);
+    __syncthreads();
+    D[r][o] = dl;
+    Ap[r][o] = aprev;
+    __syncthreads();
+    const int gin = n.gin[g], gout = n.gout[g];
+    for (int q = tid; q < gout * gin; q += 256) {
+      int oo = q / gin, ii = q - oo * gin;
+      float s = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < RT; ++rr) s = fmaf(D[rr][oo], Ap[rr][ii], s);
+      part[poff + q] = s;
+    }
+    for (int q = tid; q < gout; q += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < RT; ++rr) s += D[rr][q];
+      part[poff + (size_t)gout * gin + q] = s;
+    }
+    poff += (size_t)gout * gin + gout;
+    float acc = 0.f;
+    if (o < gin) {
+      const float* w = n.gw[g] + o;
+      for (int oo = 0; oo < gout; ++oo) acc = fmaf(D[r][oo], __ldg(w + (size_t)oo * gin), acc);
+    }
+    dA[r][o] = acc;
+  }
+  if (d_rows && live && o < n.ef) d_rows[(size_t)row * n.ef + o] = dA[r][o];
+}
+
+// fixed-order reduction of the per-CTA partials: out[idx] = sum_c partial[c][idx]
+__global__ void k_enet_reduce(const float* __restrict__ partial, int nparts, int partial_stride, int count,
+                              float* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  float s = 0.f;
+  for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * partial_stride + idx];
+  out[idx] = s;
+}
+
+// unpack the reduced tied gradient [PW][PW] -> [P][P]
+__global__ void k_enet_unpack_tied(const float* __restrict__ red, int P, float* __restrict__ dW) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * P) return;
+  int o = idx / P, i = idx - o * P;
+  dW[idx] = red[o * PW + i];
+}
+
+// dW_last[k*nf+l, p] = sum_u dT[u][l][k] x_u[p];  dB_last[k*nf+l] = sum_u dT[u][l][k]
+__global__ void k_enet_last_bwd(const float* __restrict__ acts_x /*[R][PW]*/, const float* __restrict__ dT, int R,
+                                int nf, int mf, int P, int DP, float* __restrict__ dW, float* __restrict__ dB) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (f, p), p fastest, p in [0, P]
+  int total = mf * nf * (P + 1);
+  if (idx >= total) return;
+  int p = idx % (P + 1), f = idx / (P + 1);
+  int l = f % nf, k = f / nf;
+  float s = 0.f;
+  for (int u = 0; u < R; ++u) {
+    float d = dT[((size_t)u * DP + l) * DP + k];
+    s = fmaf(d, p < P ? acts_x[(size_t)u * PW + p] : 1.f, s);
+  }
+  if (p < P)
+    dW[(size_t)f * P + p] = s;
+  else
+    dB[f] = s;
+}
+
+int pick_dp(int nf, int mf) {
+  int d = nf > mf ? nf : mf;
+  return pow2_at_least(d, 8);
+}
+
+int msg_grid(int n_rows, int DP) {
+  int per = 256 / DP;
+  int want = ceil_div(n_rows, per);
+  int cap = mpnn_num_sms() * 8;
+  return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+bool fill_enet(ENet* n, const float* rows, int R, int ef, int G, const float* const* gw, const float* const* gb,
+               const float* w_tied, int P, int L, const float* w_last, const float* b_last, int nf, int mf) {
+  if (G > MAXG || G < 0 || P > PW) return false;
+  n->rows = rows;
+  n->w_tied = w_tied;
+  n->w_last = w_last;
+  n->b_last = b_last;
+  n->R = R;
+  n->ef = ef;
+  n->G = G;
+  n->P = P;
+  n->L = L;
+  n->nf = nf;
+  n->mf = mf;
+  n->DP = pick_dp(nf, mf);
+  int w = ef;
+  for (int g = 0; g < MAXG; ++g) {
+    n->gw[g] = nullptr;
+    n->gb[g] = nullptr;
+    n->gin[g] = n->gout[g] = 0;
+  }
+  for (int g = 0; g < G; ++g) {
+    n->gw[g] = gw[g];
+    n->gb[g] = gb ? gb[g] : nullptr;
+    n->gin[g] = w;
+    n->gout[g] = w * w;
+    w = w * w;
+  }
+  return w == P && ef <= PW;
+}
+
+int enet_partial_stride(const ENet& n) {
+  size_t s = (size_t)PW * PW;
+  for (int g = 0; g < n.G; ++g) s += (size_t)n.gout[g] * n.gin[g] + n.gout[g];
+  return (int)((s + 3) & ~(size_t)3);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- table geometry -----------------------------------------------------------------------------------
+// padded feature width of the table (power of two >= max(nf, mf), >= 8); -1 if this file cannot serve it
+int mpnn_typed_dp(int nf, int mf) {
+  int DP = pick_dp(nf, mf);
+  return DP <= 32 ? DP : -1;
+}
+
+int mpnn_graph_sum(const float* X, int B, int N, int width, float* out, cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && N > 0 && width > 0, MPNN_ERR_ARG, "graph_sum: bad dims");
+  k_graph_sum<<<ceil_div((long long)B * width, 256), 256, 0, stream>>>(X, B, N, width, out);
+  MPNN_CHECK_LAUNCH("k_graph_sum");
+  return MPNN_OK;
+}
+
+// flat [R, mf*nf] (output of the last Linear on the distinct rows) -> table / tableT [R][DP][DP]
+int mpnn_table_from_flat(const float* flat, int R, int nf, int mf, float* table, float* tableT, cudaStream_t stream) {
+  int DP = pick_dp(nf, mf);
+  MPNN_REQUIRE(R > 0 && nf > 0 && mf > 0, MPNN_ERR_ARG, "table_from_flat: bad dims");
+  k_table_from_flat<<<ceil_div((long long)R * DP * DP, 256), 256, 0, stream>>>(flat, R, nf, mf, DP, table, tableT);
+  MPNN_CHECK_LAUNCH("k_table_from_flat");
+  return MPNN_OK;
+}
+
+int mpnn_table_to_flat(const float* dT, int R, int nf, int mf, float* dflat, cudaStream_t stream) {
+  int DP = pick_dp(nf, mf);
+  MPNN_REQUIRE(R > 0 && nf > 0 && mf > 0, MPNN_ERR_ARG, "table_to_flat: bad dims");
+  k_table_to_flat<<<ceil_div((long long)R * mf * nf, 256), 256, 0, stream>>>(dT, R, nf, mf, DP, dflat);
+  MPNN_CHECK_LAUNCH("k_table_to_flat");
+  return MPNN_OK;
+}
+
+// ---- fused edge network on the distinct rows (P <= 64) -------------------------------------------------
+int mpnn_enet_supported(int ef, int n_growth, int P) { return (P <= PW && ef <= PW && n_growth <= MAXG) ? 1 : 0; }
+
+long long mpnn_enet_saved_floats(int R, int n_growth, int n_tied) {
+  return (long long)(n_growth + n_tied + 1) * R * PW;
+}
+
+size_t mpnn_enet_workspace_bytes(int R, int ef, int n_growth, int P) {
+  ENet n;
+  const float* dummy[MAXG] = {nullptr, nullptr, nullptr, nullptr};
+  if (!fill_enet(&n, nullptr, R, ef, n_growth, dummy, dummy, nullptr, P, 1, nullptr, nullptr, 1, 1)) return 0;
+  size_t stride = (size_t)enet_partial_stride(n);
+  return ((size_t)ceil_div(R, RT) + 1) * stride * sizeof(float);
+}
+
+int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
+                  const float* const* growth_b, const float* w_tied, int P, int n_tied, const float* w_last,
+                  const float* b_last, int nf, int mf, float* saved, float* table, float* tableT,
+                  cudaStream_t stream) {
+  ENet n;
+  MPNN_REQUIRE(R > 0 && n_tied >= 1 && nf > 0 && mf > 0, MPNN_ERR_ARG, "enet_fwd: bad dims");
+  MPNN_REQUIRE(fill_enet(&n, rows, R, ef, n_growth, growth_w, growth_b, w_tied, P, n_tied, w_last, b_last, nf, mf),
+               MPNN_ERR_UNSUPPORTED, "enet_fwd: layer plan ef=%d growth=%d P=%d not supported by the fused kernel", ef,
+               n_growth, P);
+  MPNN_REQUIRE(n.DP <= 32, MPNN_ERR_UNSUPPORTED, "enet_fwd: feature width > 32");
+  k_enet_fwd<<<ceil_div(R, RT), 256, 0, stream>>>(n, saved, table, tableT);
+  MPNN_CHECK_LAUNCH("k_enet_fwd");
+  return MPNN_OK;
+}
+
+// dT [R][DP][DP] -> d_growth_w/b, d_w_tied, d_w_last, d_b_last (all written), optional d_rows [R, ef]
+int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* const* growth_w, const float* w_tied,
+                  int P, int n_tied, const float* w_last, int nf, int mf, const float* saved, const float* dT,
+                  float* const* d_growth_w, float* const* d_growth_b, float* d_w_tied, float* d_w_last,
+                  float* d_b_last, float* d_rows, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ENet n;
+  MPNN_REQUIRE(R > 0 && n_tied >= 1 && nf > 0 && mf > 0, MPNN_ERR_ARG, "enet_bwd: bad dims");
+  MPNN_REQUIRE(fill_enet(&n, rows, R, ef, n_growth, growth_w, nullptr, w_tied, P, n_tied, w_last, nullptr, nf, mf),
+               MPNN_ERR_UNSUPPORTED, "enet_bwd: layer plan not supported by the fused kernel");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_enet_workspace_bytes(R, ef, n_growth, P), MPNN_ERR_WORKSPACE,
+               "enet_bwd: workspace too small");
+  const int stride = enet_partial_stride(n);
+  const int nparts = ceil_div(R, RT);
+  float* partial = (float*)workspace;
+  float* red = partial + (size_t)nparts * stride;
+  k_enet_bwd<<<nparts, 256, 0, stream>>>(n, saved, dT, partial, stride, d_rows);
+  MPNN_CHECK_LAUNCH("k_enet_bwd");
+  k_enet_reduce<<<ceil_div(stride, 256), 256, 0, stream>>>(partial, nparts, stride, stride, red);
+  MPNN_CHECK_LAUNCH("k_enet_reduce");
+  k_enet_unpack_tied<<<ceil_div(P * P, 256), 256, 0, stream>>>(red, P, d_w_tied);
+  MPNN_CHECK_LAUNCH("k_enet_unpack_tied");
+  size_t off = (size_t)PW * PW;
+  for (int g = n_growth - 1; g >= 0; --g) {
+    size_t wn = (size_t)n.gout[g] * n.gin[g];
+    MPNN_CUDA(cudaMemcpyAsync(d_growth_w[g], red + off, wn * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    MPNN_CUDA(cudaMemcpyAsync(d_growth_b[g], red + off + wn, (size_t)n.gout[g] * sizeof(float),
+                              cudaMemcpyDeviceToDevice, stream));
+    off += wn + n.gout[g];
+  }
+  const float* x = saved + (size_t)(n_growth + n_tied) * R * PW;
+  k_enet_last_bwd<<<ceil_div((long long)mf * nf * (P + 1), 256), 256, 0, stream>>>(x, dT, R, nf, mf, P, n.DP, d_w_last,
+                                                                                  d_b_last);
+  MPNN_CHECK_LAUNCH("k_enet_last_bwd");
+  return MPNN_OK;
+}
+
+// ---- typed message + aggregation ------------------------------------------------------------------------
+size_t mpnn_tmsg_bwd_workspace_bytes(int edge_capacity, int unique_capacity, int nf, int mf, int B) {
+  int DP = pick_dp(nf, mf);
+  size_t chunks = (size_t)ceil_div(edge_capacity > 0 ? edge_capacity : 1, CH);
+  return (chunks + unique_capacity + 2) * DP * DP * sizeof(float) + align_up((size_t)B * mf * sizeof(float), 256);
+}
+
+// M[n_rows, mf].  S = per-graph sums of H ([B, nf], mpnn_graph_sum) selects the HEAD form (all pairs, zero-row
+// type = zero_type); S == NULL is the documented per-pair form fused with AdjMsgAgg (alpha = adj value).
+int mpnn_tmsg_fwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, const float* H,
+                  const float* table, const float* S, const float* beta, int n_rows, int N, int nf, int mf,
+                  int zero_type, float* M, cudaStream_t stream) {
+  MPNN_REQUIRE(n_rows > 0 && N > 0 && nf > 0 && mf > 0, MPNN_ERR_ARG, "tmsg_fwd: bad dims");
+  int DP = pick_dp(nf, mf);
+  MPNN_REQUIRE(DP <= 32, MPNN_ERR_UNSUPPORTED, "tmsg_fwd: feature width > 32 is served by the tensor-core path");
+  TMsg a = {row_ptr, edge_src, nullptr, uid, alpha, H, table, nullptr, S, beta, n_rows, N, nf, mf, zero_type};
+  int grid = msg_grid(n_rows, DP);
+  switch (DP) {
+    case 8: k_tmsg_fwd<8><<<grid, 256, 0, stream>>>(a, M); break;
+    case 16: k_tmsg_fwd<16><<<grid, 256, 0, stream>>>(a, M); break;
+    default: k_tmsg_fwd<32><<<grid, 256, 0, stream>>>(a, M); break;
+  }
+  MPNN_CHECK_LAUNCH("k_tmsg_fwd");
+  return MPNN_OK;
+}
+
+// dH [n_rows, nf], dT [(unique_capacity+1)][DP][DP] (both written).  counts = device {E, U, ..} of the edge list.
+int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, const int* edge_src, const int* edge_dst,
+                  const int* uid, const int* type_ptr, const int* type_eid, const int* counts, const float* alpha,
+                  const float* H, const float* table, const float* tableT, const float* S, int n_rows, int B, int N,
+                  int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dH, float* dT,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(n_rows > 0 && N > 0 && nf > 0 && mf > 0 && B > 0, MPNN_ERR_ARG, "tmsg_bwd: bad dims");
+  int DP = pick_dp(nf, mf);
+  MPNN_REQUIRE(DP <= 32, MPNN_ERR_UNSUPPORTED, "tmsg_bwd: feature width > 32 is served by the tensor-core path");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tmsg_bwd_workspace_bytes(edge_capacity, unique_capacity, nf, mf, B),
+               MPNN_ERR_WORKSPACE, "tmsg_bwd: workspace too small");
+  const int zero_type = unique_capacity;
+  TMsg a = {row_ptr, edge_src, edge_dst, uid, alpha, H, table, tableT, S, nullptr, n_rows, N, nf, mf, zero_type};
+  char* wp = (char*)workspace;
+  float* Dsum = (float*)wp;
+  wp += align_up((size_t)B * mf * sizeof(float), 256);
+  float* part = (float*)wp;
+  if (S) {
+    int rc = mpnn_graph_sum(dM, B, N, mf, Dsum, stream);
+    if (rc) return rc;
+  }
+  const int grid = msg_grid(n_rows, DP);
+  const int chunks = ceil_div(edge_capacity > 0 ? edge_capacity : 1, CH);
+  switch (DP) {
+    case 8:
+      k_tmsg_bwd_src<8><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
+      k_tmsg_bwd_table<8><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, type_eid, dM, part);
+      k_tmsg_bwd_table_reduce<8><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, dT);
+      if (S) k_tmsg_bwd_table_zero<8><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
+      break;
+    case 16:
+      k_tmsg_bwd_src<16><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
+      k_tmsg_bwd_table<16><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, type_eid, dM, part);
+      k_tmsg_bwd_table_reduce<16><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, dT);
+      if (S) k_tmsg_bwd_table_zero<16><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
+      break;
+    default:
+      k_tmsg_bwd_src<32><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
+      k_tmsg_bwd_table<32><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, type_eid, dM, part);
+      k_tmsg_bwd_table_reduce<32><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, dT);
+      if (S) k_tmsg_bwd_table_zero<32><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
+      break;
+  }
+  MPNN_CHECK_LAUNCH("k_tmsg_bwd");
+  return MPNN_OK;
+}
+
+}  // extern "C"

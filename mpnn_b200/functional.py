@@ -515,3 +515,137 @@ class Set2VecFn(torch.autograd.Function):
                                    ctx.steps, ptr(dX), ptr(dWcat), ptr(dbcat), ptr(dWq), ptr(dwe), ptr(ws), ws.numel(),
                                    stream()), "set2vec_bwd")
         return dX, None, dWcat, dbcat, dWq, dwe, None
+
+
+# ------------------------------------------------------------------------------------------------
+# typed path: edge network on the DISTINCT bond rows -> table of matrices; gather message kernel
+# (csrc/dedup.cu, csrc/typed.cu)
+# ------------------------------------------------------------------------------------------------
+def typed_dp(nf, mf):
+    return _lib.load().mpnn_typed_dp(nf, mf)
+
+
+class EdgeNetTableFn(torch.autograd.Function):
+    """Fused growth layers + 50 tied layers + last Linear on the distinct rows (P <= 64):
+    urows [R, ef] -> table T[u][l][k], tableT T[u][k][l]  ([R, DP, DP] each; reference edge_network.py:14-21,37)."""
+
+    @staticmethod
+    def forward(ctx, urows, w_tied, n_tied, W_last, B_last, nf, mf, *growth):
+        lib = _lib.load()
+        _need_cuda(urows, w_tied, W_last)
+        urows, w_tied, W_last, B_last = f32c(urows), f32c(w_tied), f32c(W_last), f32c(B_last)
+        G = len(growth) // 2
+        gw = [f32c(t) for t in growth[:G]]
+        gb = [f32c(t) for t in growth[G:]]
+        R, ef = urows.shape
+        P = w_tied.shape[0]
+        DP = lib.mpnn_typed_dp(nf, mf)
+        dev = urows.device
+        saved = torch.empty(lib.mpnn_enet_saved_floats(R, G, n_tied), dtype=torch.float32, device=dev)
+        table = torch.empty(R, DP, DP, dtype=torch.float32, device=dev)
+        tableT = torch.empty(R, DP, DP, dtype=torch.float32, device=dev)
+        check(lib.mpnn_enet_fwd(ptr(urows), R, ef, G, ptr_array(gw), ptr_array(gb), ptr(w_tied), P, n_tied, ptr(W_last),
+                                ptr(B_last), nf, mf, ptr(saved), ptr(table), ptr(tableT), stream()), "enet_fwd")
+        ctx.save_for_backward(urows, w_tied, W_last, saved, *gw)
+        ctx.dims = (R, ef, G, P, n_tied, nf, mf)
+        ctx.mark_non_differentiable(tableT)
+        return table, tableT
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dT, _dTt):
+        lib = _lib.load()
+        urows, w_tied, W_last, saved = ctx.saved_tensors[:4]
+        gw = list(ctx.saved_tensors[4:])
+        R, ef, G, P, n_tied, nf, mf = ctx.dims
+        dT = f32c(dT)
+        dev = urows.device
+        d_w_tied = torch.empty_like(w_tied)
+        d_W_last = torch.empty_like(W_last)
+        d_B_last = torch.empty(W_last.shape[0], dtype=torch.float32, device=dev)
+        d_gw = [torch.empty_like(w) for w in gw]
+        d_gb = [torch.empty(w.shape[0], dtype=torch.float32, device=dev) for w in gw]
+        d_rows = torch.empty_like(urows) if ctx.needs_input_grad[0] else None
+        ws = workspace(lib.mpnn_enet_workspace_bytes(R, ef, G, P), dev)
+        check(lib.mpnn_enet_bwd(ptr(urows), R, ef, G, ptr_array(gw), ptr(w_tied), P, n_tied, ptr(W_last), nf, mf,
+                                ptr(saved), ptr(dT), ptr_array(d_gw), ptr_array(d_gb), ptr(d_w_tied), ptr(d_W_last),
+                                ptr(d_B_last), ptr(d_rows), ptr(ws), ws.numel(), stream()), "enet_bwd")
+        return (d_rows, d_w_tied, None, d_W_last, d_B_last, None, None) + tuple(d_gw) + tuple(d_gb)
+
+
+class TableLayoutFn(torch.autograd.Function):
+    """flat [R, mf*nf] (last Linear's output on the distinct rows) -> table, tableT [R, DP, DP] (any trunk width)."""
+
+    @staticmethod
+    def forward(ctx, flat, nf, mf):
+        lib = _lib.load()
+        _need_cuda(flat)
+        flat = f32c(flat)
+        R = flat.shape[0]
+        DP = lib.mpnn_typed_dp(nf, mf)
+        table = torch.empty(R, DP, DP, dtype=torch.float32, device=flat.device)
+        tableT = torch.empty(R, DP, DP, dtype=torch.float32, device=flat.device)
+        check(lib.mpnn_table_from_flat(ptr(flat), R, nf, mf, ptr(table), ptr(tableT), stream()), "table_from_flat")
+        ctx.dims = (R, nf, mf)
+        ctx.mark_non_differentiable(tableT)
+        return table, tableT
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dT, _dTt):
+        lib = _lib.load()
+        R, nf, mf = ctx.dims
+        dT = f32c(dT)
+        dflat = torch.empty(R, mf * nf, dtype=torch.float32, device=dT.device)
+        check(lib.mpnn_table_to_flat(ptr(dT), R, nf, mf, ptr(dflat), stream()), "table_to_flat")
+        return dflat, None, None
+
+
+class TypedMessageFn(torch.autograd.Function):
+    """M[i] = sum_{e in E(i)} alpha_e T[uid_e]^T H[src_e]  (+ HEAD terms: zero-row matrix on all non-bonded pairs,
+    + beta).  H [n_rows, nf]; table/tableT from EdgeNetTableFn / TableLayoutFn; alpha [E] or None (not
+    differentiated: the adjacency value); head selects edge_network.py:50-51 over edge_network.py:52."""
+
+    @staticmethod
+    def forward(ctx, H, table, tableT, beta, el, alpha, head, nf, mf):
+        lib = _lib.load()
+        _need_cuda(H, table)
+        H, table, tableT = f32c(H), f32c(table), f32c(tableT)
+        beta_c = f32c(beta) if beta is not None else None
+        alpha_c = f32c(alpha) if alpha is not None else None
+        ti = el.typed()
+        dev = H.device
+        S = None
+        if head:
+            S = torch.empty(el.B, nf, dtype=torch.float32, device=dev)
+            check(lib.mpnn_graph_sum(ptr(H), el.B, el.N, nf, ptr(S), stream()), "graph_sum")
+        M = torch.empty(el.n_rows, mf, dtype=torch.float32, device=dev)
+        check(lib.mpnn_tmsg_fwd(ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha_c), ptr(H), ptr(table), ptr(S),
+                                ptr(beta_c), el.n_rows, el.N, nf, mf, ti.zero_type, ptr(M), stream()), "tmsg_fwd")
+        ctx.save_for_backward(H, table, tableT, S, alpha_c)
+        ctx.meta = (el, nf, mf, beta is not None)
+        return M
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dM):
+        lib = _lib.load()
+        H, table, tableT, S, alpha = ctx.saved_tensors
+        el, nf, mf, has_beta = ctx.meta
+        ti = el.typed()
+        dev = H.device
+        dM = f32c(dM)
+        dH = torch.empty_like(H)
+        dT = torch.empty_like(table)
+        ws = workspace(lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, nf, mf, el.B), dev)
+        check(lib.mpnn_tmsg_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src), ptr(el.edge_dst),
+                                ptr(ti.uid), ptr(ti.type_ptr), ptr(ti.type_eid), ptr(ti.counts), ptr(alpha), ptr(H),
+                                ptr(table), ptr(tableT), ptr(S), el.n_rows, el.B, el.N, nf, mf, el.Ecap, ti.Ucap,
+                                ptr(dM), ptr(dH), ptr(dT), ptr(ws), ws.numel(), stream()), "tmsg_bwd")
+        dbeta = None
+        if has_beta:
+            dbeta = torch.empty(mf, dtype=torch.float32, device=dev)
+            ws2 = workspace(lib.mpnn_colsum_workspace_bytes(el.n_rows, mf), dev)
+            check(lib.mpnn_colsum(ptr(dM), None, el.n_rows, mf, mf, 0, ptr(dbeta), 0, ptr(ws2), ws2.numel(), stream()),
+                  "colsum")
+        return dH, dT, None, dbeta, None, None, None, None, None

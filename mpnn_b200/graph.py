@@ -25,6 +25,14 @@ class EdgeList(object):
         self.edge_src, self.edge_dst, self.edge_w = edge_src, edge_dst, edge_w
         self.rows, self.csc_eid = rows, csc_eid
         self._csc_dst = None
+        self._typed = None
+        self.Ecap = E           # allocated edge slots (== E unless built with explicit capacities)
+
+    def typed(self):
+        """Distinct bond rows of the batch + edges grouped by distinct row (csrc/dedup.cu), built once."""
+        if self._typed is None:
+            self._typed = dedup_rows(self)
+        return self._typed
 
     @property
     def csc_dst(self):
@@ -62,6 +70,61 @@ def compact_edges(bfm, adj=None):
                                      _lib.ptr(edge_src), _lib.ptr(edge_dst), _lib.ptr(edge_w), _lib.ptr(rows),
                                      _lib.ptr(csc_eid), _lib.ptr(ws), _lib.stream()), "compact_fill")
     return EdgeList(B, N, ef, E, row_ptr, col_ptr, edge_src[:E], edge_dst[:E], edge_w[:E], rows, csc_eid[:E])
+
+
+class TypedInfo(object):
+    """uid [E] (distinct-row id per edge), urows [Ucap+1, ef] (distinct rows; row Ucap is the all-zero row x_0),
+    counts [4] device {E, U, overflow, 0}, type_ptr [Ucap+1] / type_eid [E] / type_pos [E] (edges grouped by uid,
+    stable).  U == Ucap unless explicit capacities were given (CUDA-graph capture)."""
+
+    def __init__(self, uid, urows, counts, type_ptr, type_eid, type_pos, U, Ucap):
+        self.uid, self.urows, self.counts = uid, urows, counts
+        self.type_ptr, self.type_eid, self.type_pos = type_ptr, type_eid, type_pos
+        self.U, self.Ucap = U, Ucap
+        self.zero_type = Ucap
+
+
+TYPED_MAX_UNIQUE = 1024   # beyond this many distinct bond rows the per-edge contraction (csrc/message.cu) is used
+
+
+def dedup_rows(el, unique_capacity=None):
+    """Exact de-duplication of el.rows by bit pattern.  Eager mode (unique_capacity None) reads U back (one 16-byte
+    D2H) to size the distinct-row arrays exactly; with an explicit capacity nothing is read back (graph capture)
+    and counts[2] flags an overflow."""
+    lib = _lib.load()
+    dev = el.rows.device
+    Ecap, ef = el.Ecap, el.ef
+    n_edges_ptr = el.row_ptr[el.n_rows:]
+    uid = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    type_eid = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    type_pos = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    if unique_capacity is None:
+        ucap0 = max(Ecap, 1)
+        urows = torch.zeros(ucap0 + 1, ef, dtype=torch.float32, device=dev)
+        ws = _lib.workspace(lib.mpnn_dedup_workspace_bytes(Ecap, 1), dev)
+        _lib.check(lib.mpnn_dedup_rows(_lib.ptr(el.rows), _lib.ptr(n_edges_ptr), Ecap, ef, ucap0, _lib.ptr(uid),
+                                       _lib.ptr(urows), _lib.ptr(counts), 0, None, None, None, _lib.ptr(ws),
+                                       ws.numel(), _lib.stream()), "dedup_rows")
+        U = int(counts[1].item())
+        Ucap = max(U, 1)
+        urows = urows[:Ucap + 1].contiguous()   # rows >= U are zero: row Ucap is x_0
+        type_ptr = None
+        if Ucap <= TYPED_MAX_UNIQUE:
+            type_ptr = torch.empty(Ucap + 1, dtype=torch.int32, device=dev)
+            ws = _lib.workspace(lib.mpnn_type_sort_workspace_bytes(Ecap, Ucap), dev)
+            _lib.check(lib.mpnn_type_sort(_lib.ptr(uid), _lib.ptr(counts), Ecap, Ucap, _lib.ptr(type_ptr),
+                                          _lib.ptr(type_eid), _lib.ptr(type_pos), _lib.ptr(ws), ws.numel(),
+                                          _lib.stream()), "type_sort")
+        return TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], U, Ucap)
+    Ucap = int(unique_capacity)
+    urows = torch.zeros(Ucap + 1, ef, dtype=torch.float32, device=dev)
+    type_ptr = torch.empty(Ucap + 1, dtype=torch.int32, device=dev)
+    ws = _lib.workspace(lib.mpnn_dedup_workspace_bytes(Ecap, Ucap), dev)
+    _lib.check(lib.mpnn_dedup_rows(_lib.ptr(el.rows), _lib.ptr(n_edges_ptr), Ecap, ef, Ucap, _lib.ptr(uid),
+                                   _lib.ptr(urows), _lib.ptr(counts), 1, _lib.ptr(type_ptr), _lib.ptr(type_eid),
+                                   _lib.ptr(type_pos), _lib.ptr(ws), ws.numel(), _lib.stream()), "dedup_rows")
+    return TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], None, Ucap)
 
 
 # ---- small identity cache: the same (bfm, adj) pair is compacted once per batch, whatever number of

@@ -10,8 +10,10 @@ import torch
 from torch import nn
 
 from . import graph
-from .functional import (DenseAggFn, EdgeMessageFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn, GraphLevelOutputFn, GRUFn,
-                         LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn)
+from .functional import (DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
+                         GraphLevelOutputFn, GRUFn, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
+                         TableLayoutFn, TypedMessageFn, typed_dp)
+from . import _lib
 
 _N_TIED = 50  # edge_network.py:20
 
@@ -119,6 +121,7 @@ class EdgeNetwork(nn.Module):
         self.edge_map = nn.Sequential(*edge_map)
         self.message_bias = nn.Parameter(torch.zeros(self.mf))
         self._trunk_cache = None   # (edge-list, bfm key, X)         <- the reference's self.edge_embed
+        self._table_cache = None   # (edge-list, table, tableT)      <- same role on the typed path
         self._msg_cache = {}       # message tensors of the current edge embedding
 
     # ---- pieces -----------------------------------------------------------------------------------
@@ -139,6 +142,36 @@ class EdgeNetwork(nn.Module):
         last = self.edge_map[self._last_idx]
         return last.weight, last.bias
 
+    # ---- typed path: edge network once per DISTINCT bond row -> table of matrices (csrc/typed.cu) ----------
+    _typed_capable = True      # subclasses that gate the sender state per pair turn this off
+
+    def _typed_ok(self, bfm, el):
+        """The typed path serves the plain edge network on data bond features (the reference's datasets):
+        bfm is not differentiated, feature widths <= 32, and the batch holds few distinct bond rows."""
+        if not self._typed_capable or bfm.requires_grad or typed_dp(self.nf, self.mf) < 0:
+            return False
+        ti = el.typed()
+        return ti.type_ptr is not None
+
+    def _table(self, el, reuse):
+        c = self._table_cache
+        if reuse and c is not None and c[0] is el:
+            return c[1], c[2]
+        ti = el.typed()
+        gw = [self.edge_map[i].weight for i in self._growth_idx]
+        gb = [self.edge_map[i].bias for i in self._growth_idx]
+        w_tied = self.edge_map[self._tied_idx][0].weight
+        W, Bv = self._last()
+        if _lib.load().mpnn_enet_supported(self.ef, len(gw), self.P):
+            table, tableT = EdgeNetTableFn.apply(ti.urows, w_tied, _N_TIED, W, Bv, self.nf, self.mf, *(gw + gb))
+        else:   # wide trunks (P = 256, 625, 4096): generic trunk + last Linear on the distinct rows
+            X = EdgeTrunkFn.apply(ti.urows, w_tied, _N_TIED, *(gw + gb))
+            flat = LinearFn.apply(X[:, :self.P].contiguous(), W, Bv)
+            table, tableT = TableLayoutFn.apply(flat, self.nf, self.mf)
+        self._table_cache = (el, table, tableT)
+        self._msg_cache = {}
+        return table, tableT
+
     def _sender_vectors(self, afm, bfm, el):
         """(G, gather): what multiplies the edge matrix -- the sender state itself for the plain edge network."""
         return afm.reshape(-1, self.nf), True
@@ -153,8 +186,16 @@ class EdgeNetwork(nn.Module):
         """edge_network.py:42-51: out[b,i] = sum over ALL j of A(bfm[b,i,j]) afm[b,j] + message_bias."""
         B, N, nf = afm.shape
         el = graph.edge_list_for(bfm, None)
-        X = self._trunk(bfm, el, reuse)
         k = ("head", _key(afm))
+        if self._typed_ok(bfm, el):
+            table, tableT = self._table(el, reuse)
+            if reuse and k in self._msg_cache:
+                return self._msg_cache[k]
+            M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, self.message_bias, el, None, True,
+                                     self.nf, self.mf).view(B, N, self.mf)
+            self._msg_cache[k] = M
+            return M
+        X = self._trunk(bfm, el, reuse)
         if reuse and k in self._msg_cache:
             return self._msg_cache[k]
         if bfm.requires_grad:
@@ -172,8 +213,16 @@ class EdgeNetwork(nn.Module):
         """sum_j weight[b,i,j] * (A(bfm[b,i,j]) g[b,i,j])  (edge_network.py:52 + the aggregator), no bias."""
         B, N, nf = afm.shape
         el = graph.edge_list_for(bfm, adj)
-        X = self._trunk(bfm, el, reuse)
         k = ("agg", _key(afm), _key(adj), id(alpha_fn), id(gamma_fn))
+        if alpha_fn is None and gamma_fn is None and self._typed_ok(bfm, el):
+            table, tableT = self._table(el, reuse)
+            if reuse and k in self._msg_cache:
+                return self._msg_cache[k]
+            M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, None, el, el.edge_w, False,
+                                     self.nf, self.mf).view(B, N, self.mf)
+            self._msg_cache[k] = M
+            return M
+        X = self._trunk(bfm, el, reuse)
         if reuse and alpha_fn is None and k in self._msg_cache:
             return self._msg_cache[k]
         G, gather = self._sender_vectors(afm, bfm, el)
@@ -196,6 +245,7 @@ class EdgeNetwork(nn.Module):
 
 class AttEdgeNetwork(EdgeNetwork):
     """reference att_edge_network.py: the sender state is gated, per pair, by softmax_features(attn(cat(h_i, bond)))."""
+    _typed_capable = False
 
     def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
         super(AttEdgeNetwork, self).__init__(node_features, edge_features, message_features, activation_fn)

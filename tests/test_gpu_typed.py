@@ -1,0 +1,181 @@
+"""GPU tests of the typed path (csrc/dedup.cu, csrc/typed.cu): exact de-duplication of the bond rows, the stable
+grouping of edges by distinct row, and the table-form message kernels against (1) the per-edge contraction
+kernels of csrc/message.cu, which the golden-vector tests pin to the reference, and (2) the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mpnn_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def _first_occurrence_ids(rows):
+    """reference numbering: distinct rows (by bit pattern) numbered by first occurrence"""
+    keys = [r.tobytes() for r in rows]
+    ids, uid = {}, []
+    for k in keys:
+        if k not in ids:
+            ids[k] = len(ids)
+        uid.append(ids[k])
+    return np.asarray(uid, dtype=np.int64), len(ids)
+
+
+@pytest.mark.parametrize("cfg", [("qm9", 64), ("lipo", 16), ("autoenc", 32)])
+def test_dedup_bit_exact(dev, cfg):
+    from mpnn_b200 import graph, synthetic
+    name, B = cfg
+    b = synthetic.make_batch(name, B=B)
+    el = graph.compact_edges(torch.from_numpy(b["bfm"]).to(dev), torch.from_numpy(b["adj"]).to(dev))
+    ti = el.typed()
+    rows = el.rows[:el.E].cpu().numpy()
+    uid, U = _first_occurrence_ids(rows)
+    assert ti.U == U and ti.Ucap == max(U, 1)
+    assert np.array_equal(ti.uid.cpu().numpy().astype(np.int64), uid)
+    counts = ti.counts.cpu().numpy()
+    assert counts[0] == el.E and counts[1] == U and counts[2] == 0
+    # distinct rows in first-occurrence order, then the zero row
+    first = np.asarray([np.nonzero(uid == u)[0][0] for u in range(U)], dtype=np.int64)
+    assert np.array_equal(ti.urows[:U].cpu().numpy().view(np.uint32), rows[first].view(np.uint32))
+    assert float(ti.urows[ti.zero_type].abs().sum()) == 0.0
+    # stable grouping by type
+    order = np.argsort(uid, kind="stable")
+    assert np.array_equal(ti.type_eid.cpu().numpy().astype(np.int64), order)
+    inv = np.empty_like(order)
+    inv[order] = np.arange(len(order))
+    assert np.array_equal(ti.type_pos.cpu().numpy().astype(np.int64), inv)
+    cnt = np.bincount(uid, minlength=U)
+    tp = ti.type_ptr.cpu().numpy().astype(np.int64)
+    assert np.array_equal(tp[1:U + 1] - tp[:U], cnt) and tp[0] == 0
+
+
+def test_dedup_continuous_rows_and_capacity_mode(dev):
+    """all-distinct rows (continuous bond features) and the explicit-capacity (graph-capture) entry"""
+    from mpnn_b200 import graph, synthetic
+    b = synthetic.small_batch(B=4, n_lo=3, n_hi=9, afm_width=4, ef=3, seed=3)
+    bfm = torch.from_numpy(b["bfm"])
+    bfm = bfm * (1.0 + torch.rand(bfm.shape[:3], generator=torch.Generator().manual_seed(1)).unsqueeze(-1))
+    el = graph.compact_edges(bfm.to(dev), torch.from_numpy(b["adj"]).to(dev))
+    ti = el.typed()
+    uid, U = _first_occurrence_ids(el.rows[:el.E].cpu().numpy())
+    assert ti.U == U and np.array_equal(ti.uid.cpu().numpy().astype(np.int64), uid)
+    ti2 = graph.dedup_rows(el, unique_capacity=U + 5)
+    assert np.array_equal(ti2.uid.cpu().numpy().astype(np.int64), uid)
+    assert ti2.counts.cpu().tolist()[:3] == [el.E, U, 0]
+    assert float(ti2.urows[U:].abs().sum()) == 0.0
+    ti3 = graph.dedup_rows(el, unique_capacity=max(U - 2, 1))
+    assert ti3.counts.cpu().tolist()[2] == 1      # overflow is flagged, not silently truncated
+
+
+def _net(nf, ef, mf, dev, seed):
+    from mpnn_b200 import modules as M
+    from mpnn_b200.callers import kaiming_init
+    torch.manual_seed(seed)
+    net = M.EdgeNetwork(nf, ef, mf)
+    net.apply(kaiming_init)
+    with torch.no_grad():
+        net.message_bias.normal_()
+        net.edge_map[net._last_idx].bias.normal_(std=0.1)
+    return net.to(dev)
+
+
+def _run(net, afm, bfm, adj, form, typed, cot):
+    from mpnn_b200 import modules as M, graph
+    graph.clear_cache()
+    net.zero_grad()
+    type(net)._typed_capable = typed
+    try:
+        a = afm.clone().requires_grad_(True)
+        msgs = net(a, bfm)
+        out = M.AdjMsgAgg(1)(msgs, adj) if form == "agg" else msgs.materialize()
+        (out * cot).sum().backward()
+    finally:
+        type(net)._typed_capable = True
+    grads = {k: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for k, p in net.named_parameters()}
+    return out.detach(), a.grad.clone(), grads
+
+
+SHAPES = [
+    # nf, ef, mf, B, n_lo, n_hi
+    (16, 7, 16, 6, 3, 12),     # config-2 widths: P = 49, one growth layer, fused edge network
+    (22, 7, 22, 4, 2, 20),     # config-1 widths (DP = 32)
+    (8, 2, 8, 5, 2, 9),        # config-4 widths: P = 16, two growth layers
+    (5, 3, 9, 3, 1, 6),        # rectangular nf != mf
+    (32, 8, 32, 4, 3, 15),     # config-3 widths: P = 64, no padding anywhere
+    (16, 3, 16, 3, 2, 8),      # P = 81 > 64: generic trunk + last Linear + table layout
+    (6, 9, 6, 3, 2, 7),        # ef^2 >= nf*mf: no growth layer, P = ef = 9
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("form", ["agg", "head"])
+def test_typed_path_matches_contraction_path(dev, shape, form):
+    from mpnn_b200 import synthetic
+    nf, ef, mf, B, lo, hi = shape
+    b = synthetic.small_batch(B=B, n_lo=lo, n_hi=hi, afm_width=nf, ef=ef, seed=nf + ef, weighted_adj=True)
+    afm = torch.from_numpy(b["afm"]).to(dev)
+    bfm = torch.from_numpy(b["bfm"]).to(dev)
+    adj = torch.from_numpy(b["adj"]).to(dev)
+    net = _net(nf, ef, mf, dev, seed=ef)
+    cot = torch.randn(B, afm.shape[1], mf, generator=torch.Generator().manual_seed(9)).to(dev)
+    o1, ga1, gp1 = _run(net, afm, bfm, adj, form, True, cot)
+    o0, ga0, gp0 = _run(net, afm, bfm, adj, form, False, cot)
+    assert rel_err(o1.cpu(), o0.cpu()) <= 2e-5
+    assert rel_err(ga1.cpu(), ga0.cpu()) <= 2e-5
+    for k in gp0:
+        scale = max(float(g.abs().max()) for g in gp0.values())
+        diff = float((gp1[k] - gp0[k]).abs().max())
+        assert diff <= 1e-4 * float(gp0[k].abs().max()) + 1e-6 * scale, k
+
+
+def test_typed_path_against_oracle_config2(dev):
+    """config-2 shaped batch (categorical bond rows), AdjMsgAgg form, against the CPU oracle"""
+    from mpnn_b200 import graph, modules as M, synthetic
+    from oracle import mpnn_oracle as O
+    from golden_util import leaf_sd
+    b = synthetic.make_batch("qm9", B=24)
+    afm, bfm, adj = (torch.from_numpy(b[k]) for k in ("afm", "bfm", "adj"))
+    nf = afm.shape[-1]
+    net = _net(nf, bfm.shape[-1], nf, dev, seed=1)
+    graph.clear_cache()
+    a = afm.clone().to(dev).requires_grad_(True)
+    out = M.AdjMsgAgg(1)(net(a, bfm.to(dev)), adj.to(dev))
+    assert graph.edge_list_for(bfm.to(dev), adj.to(dev)) is not None
+    cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(2))
+    (out * cot.to(dev)).sum().backward()
+    sd = leaf_sd({k: v.detach().cpu().clone() for k, v in net.state_dict().items()})
+    a0 = afm.clone().requires_grad_(True)
+    ref = (O.edge_network_pairs(a0, bfm, sd, "", nf) * adj.unsqueeze(-1)).sum(-2)
+    (ref * cot).sum().backward()
+    assert rel_err(out.detach().cpu(), ref.detach()) <= 1e-4
+    assert rel_err(a.grad.cpu(), a0.grad) <= 1e-3
+    params = dict(net.named_parameters())
+    gscale = max(float(v.grad.abs().max()) for v in sd.values() if v.grad is not None)
+    for k, v in sd.items():
+        if v.grad is None or k == "message_bias" or k not in params:
+            continue
+        diff = float((params[k].grad.cpu() - v.grad).abs().max())
+        assert diff <= 1e-3 * float(v.grad.abs().max()) + 1e-6 * gscale, k
+
+
+def test_typed_path_bit_reproducible(dev):
+    from mpnn_b200 import synthetic
+    b = synthetic.make_batch("qm9", B=32)
+    afm, bfm, adj = (torch.from_numpy(b[k]).to(dev) for k in ("afm", "bfm", "adj"))
+    nf = afm.shape[-1]
+    net = _net(nf, bfm.shape[-1], nf, dev, seed=4)
+    cot = torch.randn(afm.shape[0], afm.shape[1], nf, generator=torch.Generator().manual_seed(3)).to(dev)
+    r1 = _run(net, afm, bfm, adj, "agg", True, cot)
+    r2 = _run(net, afm, bfm, adj, "agg", True, cot)
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
+    for k in r1[2]:
+        assert torch.equal(r1[2][k], r2[2][k]), k
