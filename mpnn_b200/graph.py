@@ -37,13 +37,42 @@ class EdgeList(object):
     @property
     def csc_dst(self):
         """receiver row of every CSC entry (for scatter-free transposed reductions)"""
+        if self.E is None:
+            raise RuntimeError("mpnn_b200: only the typed message path is available in capacity (graph-capture) mode")
         if self._csc_dst is None:
             self._csc_dst = self.edge_dst[self.csc_eid.long()].contiguous() if self.E else self.edge_dst
         return self._csc_dst
 
 
+# ---- capacity mode (CUDA-graph capture): array sizes come from the caller, nothing is read back ----------
+_CAPACITY = None          # (edge_capacity, unique_capacity) or None
+_CAPTURED_COUNTS = []     # counts tensors of the edge lists built in capacity mode (overflow flags)
+STATS = {"E": 0, "U": 0}  # largest edge / distinct-row counts seen by the eager path (sizes the capacities)
+
+
+class capacities(object):
+    """`with capacities(ecap, ucap):` edge lists are built with fixed array sizes and NO device->host read, so
+    the whole step can be captured into a CUDA graph and replayed on other batches of the same padded shape.
+    Only the typed message path is available in this mode; an overflow is flagged in counts[2]."""
+
+    def __init__(self, edge_capacity, unique_capacity):
+        self.cap = (int(edge_capacity), int(unique_capacity))
+
+    def __enter__(self):
+        global _CAPACITY
+        self.prev = _CAPACITY
+        _CAPACITY = self.cap
+        return self
+
+    def __exit__(self, *exc):
+        global _CAPACITY
+        _CAPACITY = self.prev
+        return False
+
+
 def compact_edges(bfm, adj=None):
-    """Compacts (bfm, adj) -> EdgeList.  One 4-byte device->host read (the edge count) sizes the arrays."""
+    """Compacts (bfm, adj) -> EdgeList.  One 4-byte device->host read (the edge count) sizes the arrays
+    (none in capacity mode)."""
     lib = _lib.load()
     if not bfm.is_cuda:
         raise RuntimeError("mpnn_b200.compact_edges needs CUDA tensors (no CPU fallback)")
@@ -60,7 +89,24 @@ def compact_edges(bfm, adj=None):
     ws = _lib.workspace(lib.mpnn_compact_workspace_bytes(B, N), dev)
     _lib.check(lib.mpnn_compact_count(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, _lib.ptr(row_ptr), _lib.ptr(col_ptr),
                                       _lib.ptr(ws), ws.numel(), _lib.stream()), "compact_count")
+    if _CAPACITY is not None:
+        Ecap = _CAPACITY[0]
+        edge_src = torch.empty(Ecap, dtype=torch.int32, device=dev)
+        edge_dst = torch.empty(Ecap, dtype=torch.int32, device=dev)
+        csc_eid = torch.empty(Ecap, dtype=torch.int32, device=dev)
+        edge_w = torch.empty(Ecap, dtype=torch.float32, device=dev)
+        rows = torch.zeros(Ecap + 1, ef, dtype=torch.float32, device=dev)
+        _lib.check(lib.mpnn_compact_fill(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, _lib.ptr(row_ptr),
+                                         _lib.ptr(col_ptr), Ecap, _lib.ptr(edge_src), _lib.ptr(edge_dst),
+                                         _lib.ptr(edge_w), _lib.ptr(rows), _lib.ptr(csc_eid), _lib.ptr(ws),
+                                         _lib.stream()), "compact_fill")
+        el = EdgeList(B, N, ef, None, row_ptr, col_ptr, edge_src, edge_dst, edge_w, rows, csc_eid)
+        el.Ecap = Ecap
+        el._typed = dedup_rows(el, unique_capacity=_CAPACITY[1])
+        _CAPTURED_COUNTS.append(el._typed.counts)
+        return el
     E = int(row_ptr[-1].item())
+    STATS["E"] = max(STATS["E"], E)
     edge_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
     edge_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
     csc_eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
@@ -107,6 +153,7 @@ def dedup_rows(el, unique_capacity=None):
                                        _lib.ptr(urows), _lib.ptr(counts), 0, None, None, None, _lib.ptr(ws),
                                        ws.numel(), _lib.stream()), "dedup_rows")
         U = int(counts[1].item())
+        STATS["U"] = max(STATS["U"], U)
         Ucap = max(U, 1)
         urows = urows[:Ucap + 1].contiguous()   # rows >= U are zero: row Ucap is x_0
         type_ptr = None

@@ -127,6 +127,9 @@ class EdgeNetwork(nn.Module):
     # ---- pieces -----------------------------------------------------------------------------------
     def _trunk(self, bfm, el, reuse):
         """x = edge_map[:-1](bond rows) on the compacted rows (+ zero row), cached like self.edge_embed."""
+        if el.E is None:
+            raise RuntimeError("mpnn_b200.EdgeNetwork: this configuration (differentiable bond features, attention "
+                               "gate, or > 32 features) is not available in capacity (graph-capture) mode")
         c = self._trunk_cache
         if reuse and c is not None and c[0] is el:
             return c[2]
