@@ -15,6 +15,7 @@ namespace {
 constexpr int MAXQ = 5;
 
 enum Mode { STATS1 = 0, STATS2 = 1, BWD_PLAIN = 2, BWD_1D_TRAIN = 3, BWD_1D_EVAL = 4 };
+enum Fin { FIN_NONE = 0, FIN_MEAN_PLAIN = 1, FIN_MEAN_1D = 2, FIN_SD_PLAIN = 3, FIN_SD_1D = 4 };
 
 struct RedArgs {
   const float* x;
@@ -28,11 +29,20 @@ struct RedArgs {
   int rows_per_block;
   int mode;
   int nq;
+  // finalisation, done by the LAST block to finish (fixed summation order over the per-block partials)
+  int fin;
+  float eps, momentum;
+  float* red;           // [nq*C] reduced sums
+  float* stats;         // [2C+1] mean | sd | M
+  float* running_mean;  // optional (1d, training)
+  float* running_var;
+  unsigned int* counter;  // zeroed by the caller
 };
 
 // thread -> (column tid % C, row lane tid / C); partial[block][q][C]
-__global__ void k_bn_reduce(RedArgs a, float* __restrict__ partial) {
+__global__ void k_bn_stage(RedArgs a, float* __restrict__ partial) {
   extern __shared__ float sm[];
+  __shared__ int is_last;
   const int C = a.C;
   const int lanes = blockDim.x / C;
   const int c = threadIdx.x % C, rl = threadIdx.x / C;
@@ -42,8 +52,10 @@ __global__ void k_bn_reduce(RedArgs a, float* __restrict__ partial) {
   float q[MAXQ] = {0.f, 0.f, 0.f, 0.f, 0.f};
   if (rl < lanes) {
     const float m0 = a.p0 ? a.p0[c] : 0.f;
-    const float m1 = a.p1 ? a.p1[c] : 0.f;
+    float m1 = a.p1 ? a.p1[c] : 0.f;
     const float m2 = a.p2 ? a.p2[c] : 1.f;  // weight (affine off -> 1)
+    if (a.mode == BWD_1D_TRAIN) m1 = 1.f / (m1 + a.eps);           // p1 = sd
+    if (a.mode == BWD_1D_EVAL) m1 = 1.f / (sqrtf(m1) + a.eps);     // p1 = running_var
     for (long long r = r0 + rl; r < r1; r += lanes) {
       const float xv = a.x[r * C + c];
       const float mu = a.mask[r];
@@ -51,11 +63,11 @@ __global__ void k_bn_reduce(RedArgs a, float* __restrict__ partial) {
         case STATS1:
           q[0] += xv;
           q[1] += xv * mu;
+          q[2] += mu;   // M = sum(mask): sums of 0/1 values are exact, any order
           break;
         case STATS2: {  // p0 = mean
           float cc = (xv - m0) * mu;
           q[0] += cc * cc;
-          q[1] += cc * mu;
           break;
         }
         case BWD_PLAIN: {  // p0 = mean
@@ -66,7 +78,7 @@ __global__ void k_bn_reduce(RedArgs a, float* __restrict__ partial) {
           q[2] += cc * mu;
           break;
         }
-        case BWD_1D_TRAIN: {  // p0 = mean, p1 = 1/(s+eps), p2 = weight
+        case BWD_1D_TRAIN: {  // p0 = mean, m1 = 1/(s+eps), p2 = weight
           float d = a.dy[r * C + c] * mu;
           float xc = xv - m0;
           float dyh = d * m2;
@@ -77,7 +89,7 @@ __global__ void k_bn_reduce(RedArgs a, float* __restrict__ partial) {
           q[4] += d;
           break;
         }
-        default: {  // BWD_1D_EVAL: p0 = running_mean, p1 = 1/(sqrt(rv)+eps)
+        default: {  // BWD_1D_EVAL: p0 = running_mean, m1 = 1/(sqrt(rv)+eps)
           float d = a.dy[r * C + c] * mu;
           q[0] += d * (xv - m0) * m1;
           q[1] += d;
@@ -96,42 +108,58 @@ __global__ void k_bn_reduce(RedArgs a, float* __restrict__ partial) {
       partial[((size_t)blockIdx.x * a.nq + k) * C + c] = s;
     }
   }
-}
-
-__global__ void k_bn_final(const float* __restrict__ partial, int nblk, int nq, int C, float* __restrict__ out) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nq * C) return;
-  int k = t / C, c = t - k * C;
-  float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * nq + k) * C + c];
-  out[t] = s;
-}
-
-__global__ void k_mask_sum(const float* __restrict__ mask, long long rows, float* __restrict__ out) {
-  // single block, fixed order
-  __shared__ float sm[256];
-  float s = 0.f;
-  for (long long r = threadIdx.x; r < rows; r += 256) s += mask[r];
-  sm[threadIdx.x] = s;
+  // ---- last block: reduce the partials (fixed order) and derive the statistics ----
+  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < 256; ++i) t += sm[i];
-    *out = t;
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nqC = a.nq * C;
+  const int nblk = gridDim.x;
+  const int nsl = blockDim.x >= nqC ? blockDim.x / nqC : 1;
+  for (int e0 = 0; e0 < nqC; e0 += blockDim.x) {
+    const int e = e0 + (int)threadIdx.x % (nsl > 1 ? nqC : blockDim.x);
+    const int sl = nsl > 1 ? threadIdx.x / nqC : 0;
+    float s = 0.f;
+    if (e < nqC && sl < nsl)
+      for (int b = sl; b < nblk; b += nsl) s += __ldcg(partial + (size_t)b * nqC + e);
+    __syncthreads();
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (sl == 0 && e < nqC) {
+      float t = 0.f;
+      for (int j = 0; j < nsl; ++j) t += sm[j * nqC + (e - e0)];
+      a.red[e] = t;
+    }
   }
+  __syncthreads();
+  if (a.fin == FIN_NONE) {
+    if (threadIdx.x == 0) *a.counter = 0u;
+    return;
+  }
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    if (a.fin == FIN_MEAN_PLAIN || a.fin == FIN_MEAN_1D) {
+      const float M = a.red[2 * C];
+      a.stats[cc] = a.red[(a.fin == FIN_MEAN_1D ? C : 0) + cc] / M;
+      if (cc == 0) a.stats[2 * C] = M;
+    } else {
+      const float var = a.red[cc] / a.stats[2 * C];
+      if (a.fin == FIN_SD_PLAIN) {
+        a.stats[C + cc] = sqrtf(var + a.eps);
+      } else {
+        a.stats[C + cc] = sqrtf(var);
+        if (a.running_mean) {
+          a.running_mean[cc] = (1.f - a.momentum) * a.running_mean[cc] + a.momentum * a.stats[cc];
+          a.running_var[cc] = (1.f - a.momentum) * a.running_var[cc] + a.momentum * var;
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) *a.counter = 0u;
 }
 
 // stats layout written by the forward and consumed by the backward: [mean | scale | M (1 float, at 2C)]
-__global__ void k_plain_derive1(const float* __restrict__ sums, const float* __restrict__ M, int C,
-                                float* __restrict__ stats) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) stats[c] = sums[c] / *M;  // unmasked sum / M
-  if (c == 0) stats[2 * C] = *M;
-}
-__global__ void k_plain_derive2(const float* __restrict__ sums, int C, float eps, float* __restrict__ stats) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) stats[C + c] = sqrtf(sums[c] / stats[2 * C] + eps);  // s = sqrt(var + eps)
-}
 __global__ void k_plain_apply(const float* __restrict__ x, const float* __restrict__ mask,
                               const float* __restrict__ stats, long long rows, int C, float* __restrict__ y) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,23 +187,6 @@ __global__ void k_plain_bwd_apply(const float* __restrict__ x, const float* __re
 }
 
 // --- MaskBatchNorm1d ---
-__global__ void k_1d_derive1(const float* __restrict__ sums, const float* __restrict__ M, int C,
-                             float* __restrict__ stats) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) stats[c] = sums[C + c] / *M;  // masked sum / M
-  if (c == 0) stats[2 * C] = *M;
-}
-__global__ void k_1d_derive2(const float* __restrict__ sums, int C, float momentum, float* __restrict__ stats,
-                             float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float var = sums[c] / stats[2 * C];
-  stats[C + c] = sqrtf(var);
-  if (running_mean) {
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * stats[c];
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var;
-  }
-}
 __global__ void k_1d_apply(const float* __restrict__ x, const float* __restrict__ mask, const float* __restrict__ mean,
                            const float* __restrict__ sd, int sd_is_var, const float* __restrict__ w,
                            const float* __restrict__ b, float eps, long long rows, int C, float* __restrict__ y) {
@@ -188,20 +199,22 @@ __global__ void k_1d_apply(const float* __restrict__ x, const float* __restrict_
   if (w) v = w[c] * v + b[c];
   y[t] = v * mask[r];
 }
-__global__ void k_1d_inv(const float* __restrict__ sd, int sd_is_var, float eps, int C, float* __restrict__ inv) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) inv[c] = 1.f / ((sd_is_var ? sqrtf(sd[c]) : sd[c]) + eps);
-}
 // train: red = [A1 | A2 | A3 | dgamma | dbeta]
 __global__ void k_1d_bwd_apply_train(const float* __restrict__ x, const float* __restrict__ mask,
                                      const float* __restrict__ dy, const float* __restrict__ w,
-                                     const float* __restrict__ stats, const float* __restrict__ inv,
-                                     const float* __restrict__ red, long long rows, int C, float* __restrict__ dx) {
+                                     const float* __restrict__ stats, float eps, const float* __restrict__ red,
+                                     long long rows, int C, float* __restrict__ dx, float* __restrict__ dweight,
+                                     float* __restrict__ dbias) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < C) {
+    if (dweight) dweight[t] = red[3 * C + t];
+    if (dbias) dbias[t] = red[4 * C + t];
+  }
   if (t >= rows * C) return;
   long long r = t / C;
   int c = (int)(t - r * C);
-  const float M = stats[2 * C], mean = stats[c], s = stats[C + c], iv = inv[c];
+  const float M = stats[2 * C], mean = stats[c], s = stats[C + c];
+  const float iv = 1.f / (s + eps);
   const float A1 = red[c], A2 = red[C + c], A3 = red[2 * C + c];
   const float mu = mask[r];
   const float gam = w ? w[c] : 1.f;
@@ -214,13 +227,18 @@ __global__ void k_1d_bwd_apply_train(const float* __restrict__ x, const float* _
   dx[t] = dyh * iv + dvar * 2.f * cc / M * mu + dmean * mu / M;
 }
 __global__ void k_1d_bwd_apply_eval(const float* __restrict__ mask, const float* __restrict__ dy,
-                                    const float* __restrict__ w, const float* __restrict__ inv, long long rows, int C,
-                                    float* __restrict__ dx) {
+                                    const float* __restrict__ w, const float* __restrict__ running_var, float eps,
+                                    const float* __restrict__ red, long long rows, int C, float* __restrict__ dx,
+                                    float* __restrict__ dweight, float* __restrict__ dbias) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < C) {
+    if (dweight) dweight[t] = red[t];
+    if (dbias) dbias[t] = red[C + t];
+  }
   if (t >= rows * C) return;
   long long r = t / C;
   int c = (int)(t - r * C);
-  dx[t] = dy[t] * mask[r] * (w ? w[c] : 1.f) * inv[c];
+  dx[t] = dy[t] * mask[r] * (w ? w[c] : 1.f) / (sqrtf(running_var[c]) + eps);
 }
 
 int red_blocks(long long rows, int* rpb) {
@@ -231,15 +249,13 @@ int red_blocks(long long rows, int* rpb) {
   return (int)((rows + per - 1) / per);
 }
 
-int run_reduce(RedArgs a, float* partial, float* out, cudaStream_t stream) {
+int run_stage(RedArgs a, float* partial, cudaStream_t stream) {
   int rpb;
   int nblk = red_blocks(a.rows, &rpb);
   a.rows_per_block = rpb;
   int threads = a.C >= 256 ? a.C : (256 / a.C) * a.C;
-  k_bn_reduce<<<nblk, threads, threads * sizeof(float), stream>>>(a, partial);
-  MPNN_CHECK_LAUNCH("k_bn_reduce");
-  k_bn_final<<<ceil_div(a.nq * a.C, 128), 128, 0, stream>>>(partial, nblk, a.nq, a.C, out);
-  MPNN_CHECK_LAUNCH("k_bn_final");
+  k_bn_stage<<<nblk, threads, threads * sizeof(float), stream>>>(a, partial);
+  MPNN_CHECK_LAUNCH("k_bn_stage");
   return MPNN_OK;
 }
 
@@ -247,7 +263,7 @@ int run_reduce(RedArgs a, float* partial, float* out, cudaStream_t stream) {
 
 extern "C" {
 
-// workspace: partial sums + reduced vectors
+// workspace: partial sums + reduced vectors + the completion counter
 size_t mpnn_bn_workspace_bytes(long long rows, int C) {
   int rpb;
   int nblk = red_blocks(rows, &rpb);
@@ -255,7 +271,7 @@ size_t mpnn_bn_workspace_bytes(long long rows, int C) {
          256;
 }
 
-static void carve(void* workspace, long long rows, int C, float** partial, float** red, float** scal) {
+static void carve(void* workspace, long long rows, int C, float** partial, float** red, unsigned int** counter) {
   int rpb;
   int nblk = red_blocks(rows, &rpb);
   char* wp = (char*)workspace;
@@ -263,7 +279,7 @@ static void carve(void* workspace, long long rows, int C, float** partial, float
   wp += align_up((size_t)nblk * MAXQ * C * sizeof(float), 256);
   *red = (float*)wp;
   wp += align_up((size_t)(MAXQ + 2) * C * sizeof(float), 256);
-  *scal = (float*)wp;
+  *counter = (unsigned int*)wp;
 }
 
 // stats: [2*C + 1] floats (mean, sqrt(var+eps), M) saved for backward
@@ -271,16 +287,17 @@ int mpnn_mask_bn_fwd(const float* x, const float* mask, long long rows, int C, f
                      void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(rows > 0 && C > 0 && C <= 1024, MPNN_ERR_ARG, "mask_bn_fwd: bad dims rows=%lld C=%d", rows, C);
   MPNN_REQUIRE(workspace_bytes >= mpnn_bn_workspace_bytes(rows, C), MPNN_ERR_WORKSPACE, "mask_bn_fwd: workspace");
-  float *partial, *red, *scal;
-  carve(workspace, rows, C, &partial, &red, &scal);
-  k_mask_sum<<<1, 256, 0, stream>>>(mask, rows, scal);
-  RedArgs a = {x, mask, nullptr, nullptr, nullptr, nullptr, rows, C, 0, STATS1, 2};
-  int rc = run_reduce(a, partial, red, stream);
+  float *partial, *red;
+  unsigned int* counter;
+  carve(workspace, rows, C, &partial, &red, &counter);
+  MPNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  RedArgs a = {x, mask, nullptr, nullptr, nullptr, nullptr, rows, C, 0, STATS1, 3,
+               FIN_MEAN_PLAIN, eps, 0.f, red, stats, nullptr, nullptr, counter};
+  int rc = run_stage(a, partial, stream);
   if (rc) return rc;
-  k_plain_derive1<<<ceil_div(C, 128), 128, 0, stream>>>(red, scal, C, stats);
-  RedArgs b = {x, mask, nullptr, stats, nullptr, nullptr, rows, C, 0, STATS2, 2};
-  if ((rc = run_reduce(b, partial, red, stream))) return rc;
-  k_plain_derive2<<<ceil_div(C, 128), 128, 0, stream>>>(red, C, eps, stats);
+  RedArgs b = {x, mask, nullptr, stats, nullptr, nullptr, rows, C, 0, STATS2, 1,
+               FIN_SD_PLAIN, eps, 0.f, red, stats, nullptr, nullptr, counter};
+  if ((rc = run_stage(b, partial, stream))) return rc;
   k_plain_apply<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, stats, rows, C, y);
   MPNN_CHECK_LAUNCH("mask_bn_fwd");
   return MPNN_OK;
@@ -290,10 +307,13 @@ int mpnn_mask_bn_bwd(const float* x, const float* mask, const float* dy, const f
                      float* dx, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(rows > 0 && C > 0 && C <= 1024, MPNN_ERR_ARG, "mask_bn_bwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_bn_workspace_bytes(rows, C), MPNN_ERR_WORKSPACE, "mask_bn_bwd: workspace");
-  float *partial, *red, *scal;
-  carve(workspace, rows, C, &partial, &red, &scal);
-  RedArgs a = {x, mask, dy, stats, nullptr, nullptr, rows, C, 0, BWD_PLAIN, 3};
-  int rc = run_reduce(a, partial, red, stream);
+  float *partial, *red;
+  unsigned int* counter;
+  carve(workspace, rows, C, &partial, &red, &counter);
+  MPNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  RedArgs a = {x, mask, dy, stats, nullptr, nullptr, rows, C, 0, BWD_PLAIN, 3,
+               FIN_NONE, 0.f, 0.f, red, nullptr, nullptr, nullptr, counter};
+  int rc = run_stage(a, partial, stream);
   if (rc) return rc;
   k_plain_bwd_apply<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, dy, stats, red, rows, C, dx);
   MPNN_CHECK_LAUNCH("mask_bn_bwd");
@@ -314,16 +334,17 @@ int mpnn_mask_bn1d_fwd(const float* x, const float* mask, const float* weight, c
     MPNN_CHECK_LAUNCH("k_1d_apply");
     return MPNN_OK;
   }
-  float *partial, *red, *scal;
-  carve(workspace, rows, C, &partial, &red, &scal);
-  k_mask_sum<<<1, 256, 0, stream>>>(mask, rows, scal);
-  RedArgs a = {x, mask, nullptr, nullptr, nullptr, nullptr, rows, C, 0, STATS1, 2};
-  int rc = run_reduce(a, partial, red, stream);
+  float *partial, *red;
+  unsigned int* counter;
+  carve(workspace, rows, C, &partial, &red, &counter);
+  MPNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  RedArgs a = {x, mask, nullptr, nullptr, nullptr, nullptr, rows, C, 0, STATS1, 3,
+               FIN_MEAN_1D, eps, momentum, red, stats, nullptr, nullptr, counter};
+  int rc = run_stage(a, partial, stream);
   if (rc) return rc;
-  k_1d_derive1<<<ceil_div(C, 128), 128, 0, stream>>>(red, scal, C, stats);
-  RedArgs b = {x, mask, nullptr, stats, nullptr, nullptr, rows, C, 0, STATS2, 2};
-  if ((rc = run_reduce(b, partial, red, stream))) return rc;
-  k_1d_derive2<<<ceil_div(C, 128), 128, 0, stream>>>(red, C, momentum, stats, running_mean, running_var);
+  RedArgs b = {x, mask, nullptr, stats, nullptr, nullptr, rows, C, 0, STATS2, 1,
+               FIN_SD_1D, eps, momentum, red, stats, running_mean, running_var, counter};
+  if ((rc = run_stage(b, partial, stream))) return rc;
   k_1d_apply<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, stats, stats + C, 0, weight, bias, eps, rows, C, y);
   MPNN_CHECK_LAUNCH("mask_bn1d_fwd");
   return MPNN_OK;
@@ -335,25 +356,23 @@ int mpnn_mask_bn1d_bwd(const float* x, const float* mask, const float* dy, const
                        cudaStream_t stream) {
   MPNN_REQUIRE(rows > 0 && C > 0 && C <= 1024, MPNN_ERR_ARG, "mask_bn1d_bwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_bn_workspace_bytes(rows, C), MPNN_ERR_WORKSPACE, "mask_bn1d_bwd: workspace");
-  float *partial, *red, *scal;
-  carve(workspace, rows, C, &partial, &red, &scal);
-  float* inv = red + (size_t)MAXQ * C;
+  float *partial, *red;
+  unsigned int* counter;
+  carve(workspace, rows, C, &partial, &red, &counter);
+  MPNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   int rc;
   if (training) {
-    k_1d_inv<<<ceil_div(C, 128), 128, 0, stream>>>(stats + C, 0, eps, C, inv);
-    RedArgs a = {x, mask, dy, stats, inv, weight, rows, C, 0, BWD_1D_TRAIN, 5};
-    if ((rc = run_reduce(a, partial, red, stream))) return rc;
-    k_1d_bwd_apply_train<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, dy, weight, stats, inv, red, rows, C,
-                                                                      dx);
-    if (dweight) MPNN_CUDA(cudaMemcpyAsync(dweight, red + 3 * C, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    if (dbias) MPNN_CUDA(cudaMemcpyAsync(dbias, red + 4 * C, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    RedArgs a = {x, mask, dy, stats, stats + C, weight, rows, C, 0, BWD_1D_TRAIN, 5,
+                 FIN_NONE, eps, 0.f, red, nullptr, nullptr, nullptr, counter};
+    if ((rc = run_stage(a, partial, stream))) return rc;
+    k_1d_bwd_apply_train<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, dy, weight, stats, eps, red, rows, C, dx,
+                                                                      dweight, dbias);
   } else {
-    k_1d_inv<<<ceil_div(C, 128), 128, 0, stream>>>(running_var, 1, eps, C, inv);
-    RedArgs a = {x, mask, dy, running_mean, inv, nullptr, rows, C, 0, BWD_1D_EVAL, 2};
-    if ((rc = run_reduce(a, partial, red, stream))) return rc;
-    k_1d_bwd_apply_eval<<<ceil_div(rows * C, 256), 256, 0, stream>>>(mask, dy, weight, inv, rows, C, dx);
-    if (dweight) MPNN_CUDA(cudaMemcpyAsync(dweight, red, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    if (dbias) MPNN_CUDA(cudaMemcpyAsync(dbias, red + C, C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    RedArgs a = {x, mask, dy, running_mean, running_var, nullptr, rows, C, 0, BWD_1D_EVAL, 2,
+                 FIN_NONE, eps, 0.f, red, nullptr, nullptr, nullptr, counter};
+    if ((rc = run_stage(a, partial, stream))) return rc;
+    k_1d_bwd_apply_eval<<<ceil_div(rows * C, 256), 256, 0, stream>>>(mask, dy, weight, running_var, eps, red, rows, C,
+                                                                     dx, dweight, dbias);
   }
   MPNN_CHECK_LAUNCH("mask_bn1d_bwd");
   return MPNN_OK;

@@ -70,6 +70,222 @@ __global__ void k_gru_point_bwd(const float* __restrict__ gates, const float* __
   dh[t] = go * z;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused GRU for feature widths <= 32: one kernel forward, one kernel (+ a fixed-order reduction of the
+// per-CTA weight-gradient partials) backward.  A group of DP lanes owns a row; lane c owns column c of
+// every gate.  Both gate weight matrices live in shared memory for the whole kernel; nothing but the
+// saved gates [rows, 4d] is written besides the outputs (no [rows, 3d] pre-activation round trip).
+// ---------------------------------------------------------------------------------------------------
+template <int DP>
+__device__ __forceinline__ uint32_t grp_mask(int lane) {
+  if constexpr (DP == 32) {
+    return 0xffffffffu;
+  } else {
+    return ((1u << DP) - 1u) << ((lane / DP) * DP);
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(256) k_gru_fwd_fused(const float* __restrict__ m, const float* __restrict__ h,
+                                                       const float* __restrict__ mask, const float* __restrict__ W_ih,
+                                                       const float* __restrict__ W_hh, const float* __restrict__ b_ih,
+                                                       const float* __restrict__ b_hh, long long rows, int d,
+                                                       float* __restrict__ hout, float* __restrict__ gates) {
+  extern __shared__ __align__(16) float sm[];
+  float* Wi = sm;               // [d][3d]
+  float* Wh = sm + d * 3 * d;   // [d][3d]
+  for (int i = threadIdx.x; i < d * 3 * d; i += 256) {
+    Wi[i] = W_ih[i];
+    Wh[i] = W_hh[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c = lane % DP;
+  const uint32_t gm = grp_mask<DP>(lane);
+  const int gpb = 256 / DP;
+  const bool on = c < d;
+  const int cc = on ? c : 0;
+  const float bir = b_ih[cc], biz = b_ih[d + cc], bin = b_ih[2 * d + cc];
+  const float bhr = b_hh[cc], bhz = b_hh[d + cc], bhn = b_hh[2 * d + cc];
+  for (long long row = (long long)blockIdx.x * gpb + threadIdx.x / DP; row < rows; row += (long long)gridDim.x * gpb) {
+    const float mv = on ? m[row * d + c] : 0.f;
+    const float hv = on ? h[row * d + c] : 0.f;
+    float ir = bir, iz = biz, in_ = bin, hr = bhr, hz = bhz, hn = bhn;
+#pragma unroll 4
+    for (int l = 0; l < d; ++l) {
+      const float ml = __shfl_sync(gm, mv, l, DP);
+      const float hl = __shfl_sync(gm, hv, l, DP);
+      const float* wi = Wi + l * 3 * d + cc;
+      const float* wh = Wh + l * 3 * d + cc;
+      ir = fmaf(ml, wi[0], ir);
+      iz = fmaf(ml, wi[d], iz);
+      in_ = fmaf(ml, wi[2 * d], in_);
+      hr = fmaf(hl, wh[0], hr);
+      hz = fmaf(hl, wh[d], hz);
+      hn = fmaf(hl, wh[2 * d], hn);
+    }
+    if (on) {
+      const float mu = mask[row];
+      const float sr = 1.f / (1.f + expf(-(ir + hr)));
+      const float sz = 1.f / (1.f + expf(-(iz + hz)));
+      const float r = sr * mu, z = sz * mu;
+      const float tn = tanhf(in_ + r * hn);
+      const float n = tn * mu;
+      hout[row * d + c] = ((1.f - z) * n + z * hv) * mu;
+      float* g = gates + row * 4 * d;
+      g[c] = sr;
+      g[d + c] = sz;
+      g[2 * d + c] = tn;
+      g[3 * d + c] = hn;
+    }
+  }
+}
+
+// partial layout per CTA: [dW_ih d*3d | dW_hh d*3d | db_ih 3d | db_hh 3d]
+template <int DP>
+__global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__ m, const float* __restrict__ h,
+                                                       const float* __restrict__ mask, const float* __restrict__ W_ih,
+                                                       const float* __restrict__ W_hh, const float* __restrict__ gates,
+                                                       const float* __restrict__ dhout, long long rows, int d,
+                                                       float* __restrict__ dm, float* __restrict__ dh,
+                                                       float* __restrict__ partial) {
+  constexpr int TR = 256 / DP;                      // rows per tile (one per group)
+  constexpr int NACC = (6 * DP * DP + 255) / 256;   // weight-gradient elements per thread
+  extern __shared__ __align__(16) float sm[];
+  const int d3 = 3 * d;
+  const int ldt = d + 1;
+  float* WiT = sm;                    // [3d][d+1]  WiT[g][l] = W_ih[l][g]
+  float* WhT = WiT + d3 * ldt;        // [3d][d+1]
+  float* Ms = WhT + d3 * ldt;         // [TR][d]
+  float* Hs = Ms + TR * d;            // [TR][d]
+  float* Gi = Hs + TR * d;            // [TR][3d]
+  float* Gh = Gi + TR * d3;           // [TR][3d]
+  for (int i = threadIdx.x; i < d * d3; i += 256) {
+    int l = i / d3, g = i - l * d3;
+    WiT[g * ldt + l] = W_ih[i];
+    WhT[g * ldt + l] = W_hh[i];
+  }
+  const int lane = threadIdx.x & 31;
+  const int c = lane % DP;
+  const int grp = threadIdx.x / DP;
+  const bool on = c < d;
+  const int nW = d * d3;
+  float acc[NACC];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+  float accb = 0.f;  // threads [0, 6d): bias gradients
+  const long long ntiles = (rows + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * TR + grp;
+    const bool live = row < rows;
+    __syncthreads();  // previous tile's accumulation is done with the staging buffers (and W*T are loaded)
+    float dar = 0.f, daz = 0.f, dan = 0.f, dnh = 0.f, dhd = 0.f, mv = 0.f, hv = 0.f;
+    if (live && on) {
+      const float mu = mask[row];
+      const float* g = gates + row * 4 * d;
+      const float sr = g[c], sz = g[d + c], tn = g[2 * d + c], nh = g[3 * d + c];
+      const float r = sr * mu, z = sz * mu, n = tn * mu;
+      hv = h[row * d + c];
+      mv = m[row * d + c];
+      const float go = dhout[row * d + c] * mu;
+      const float dn = go * (1.f - z);
+      const float dz = go * (hv - n);
+      dan = dn * mu * (1.f - tn * tn);
+      const float dr = dan * nh;
+      dnh = dan * r;
+      dar = dr * mu * sr * (1.f - sr);
+      daz = dz * mu * sz * (1.f - sz);
+      dhd = go * z;
+    }
+    if (on) {
+      Ms[grp * d + c] = mv;
+      Hs[grp * d + c] = hv;
+      Gi[grp * d3 + c] = dar;
+      Gi[grp * d3 + d + c] = daz;
+      Gi[grp * d3 + 2 * d + c] = dan;
+      Gh[grp * d3 + c] = dar;
+      Gh[grp * d3 + d + c] = daz;
+      Gh[grp * d3 + 2 * d + c] = dnh;
+    }
+    __syncthreads();
+    if (live && on) {
+      float am = 0.f, ah = dhd;
+      const float* gi = Gi + grp * d3;
+      const float* gh = Gh + grp * d3;
+#pragma unroll 4
+      for (int g = 0; g < d3; ++g) {
+        am = fmaf(gi[g], WiT[g * ldt + c], am);
+        ah = fmaf(gh[g], WhT[g * ldt + c], ah);
+      }
+      dm[row * d + c] = am;
+      dh[row * d + c] = ah;
+    }
+    // weight gradients: element q -> (which, l, g); rows of the tile that are out of range staged zeros
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) {
+      const int e = threadIdx.x + q * 256;
+      if (e < 2 * nW) {
+        const int which = e >= nW;
+        const int ee = e - which * nW;
+        const int l = ee / d3, g = ee - l * d3;
+        const float* xs = which ? Hs : Ms;
+        const float* gs = which ? Gh : Gi;
+        float a = acc[q];
+#pragma unroll 4
+        for (int r = 0; r < TR; ++r) a = fmaf(xs[r * d + l], gs[r * d3 + g], a);
+        acc[q] = a;
+      }
+    }
+    if (threadIdx.x < 2 * d3) {
+      const int which = threadIdx.x >= d3;
+      const int g = threadIdx.x - which * d3;
+      const float* gs = which ? Gh : Gi;
+      float a = accb;
+      for (int r = 0; r < TR; ++r) a += gs[r * d3 + g];
+      accb = a;
+    }
+  }
+  float* part = partial + (size_t)blockIdx.x * (2 * nW + 2 * d3);
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    const int e = threadIdx.x + q * 256;
+    if (e < 2 * nW) part[e] = acc[q];
+  }
+  if (threadIdx.x < 2 * d3) part[2 * nW + threadIdx.x] = accb;
+}
+
+__global__ void k_gru_bwd_reduce(const float* __restrict__ partial, int nparts, int d, float* __restrict__ dW_ih,
+                                 float* __restrict__ dW_hh, float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  const int nW = d * 3 * d, d3 = 3 * d;
+  const int total = 2 * nW + 2 * d3;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * total + e];
+  if (e < nW)
+    dW_ih[e] = s;
+  else if (e < 2 * nW)
+    dW_hh[e - nW] = s;
+  else if (e < 2 * nW + d3)
+    db_ih[e - 2 * nW] = s;
+  else
+    db_hh[e - 2 * nW - d3] = s;
+}
+
+int fused_dp(int d) { return d <= 8 ? 8 : (d <= 16 ? 16 : 32); }
+
+int gru_bwd_grid(long long rows, int DP) {
+  long long tiles = (rows + (256 / DP) - 1) / (256 / DP);
+  int cap = mpnn_num_sms();
+  return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
+size_t gru_bwd_smem(int d, int DP) {
+  int TR = 256 / DP;
+  return (size_t)(2 * 3 * d * (d + 1) + 2 * TR * d + 2 * TR * 3 * d) * sizeof(float);
+}
+
 }  // namespace
 
 extern "C" {
@@ -78,7 +294,9 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
   size_t pre = 2 * align_up((size_t)rows * 3 * d * sizeof(float), 256);
   size_t g = mpnn_gemm_workspace_bytes(d, 3 * d, (int)rows);
   size_t c = mpnn_colsum_workspace_bytes(rows, 3 * d);
-  return pre + align_up(g > c ? g : c, 256);
+  size_t fused = (size_t)mpnn_num_sms() * (6 * (size_t)d * d + 6 * d) * sizeof(float);
+  size_t need = pre + align_up(g > c ? g : c, 256);
+  return need > fused ? need : fused;
 }
 
 int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
@@ -86,6 +304,20 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(rows > 0 && d > 0 && rows < (1ll << 31), MPNN_ERR_ARG, "gru_fwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_gru_workspace_bytes(rows, d), MPNN_ERR_WORKSPACE, "gru_fwd: workspace");
+  if (d <= 32) {
+    const int DP = fused_dp(d);
+    const int gpb = 256 / DP;
+    long long want = (rows + gpb - 1) / gpb;
+    int grid = (int)(want < 4LL * mpnn_num_sms() ? want : 4LL * mpnn_num_sms());
+    size_t smem = (size_t)2 * d * 3 * d * sizeof(float);
+    switch (DP) {
+      case 8: k_gru_fwd_fused<8><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, b_ih, b_hh, rows, d, h_out, gates); break;
+      case 16: k_gru_fwd_fused<16><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, b_ih, b_hh, rows, d, h_out, gates); break;
+      default: k_gru_fwd_fused<32><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, b_ih, b_hh, rows, d, h_out, gates); break;
+    }
+    MPNN_CHECK_LAUNCH("k_gru_fwd_fused");
+    return MPNN_OK;
+  }
   char* wp = (char*)workspace;
   float* gi = (float*)wp;
   wp += align_up((size_t)rows * 3 * d * sizeof(float), 256);
@@ -107,6 +339,21 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
                  cudaStream_t stream) {
   MPNN_REQUIRE(rows > 0 && d > 0 && rows < (1ll << 31), MPNN_ERR_ARG, "gru_bwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_gru_workspace_bytes(rows, d), MPNN_ERR_WORKSPACE, "gru_bwd: workspace");
+  if (d <= 32) {
+    const int DP = fused_dp(d);
+    const int grid = gru_bwd_grid(rows, DP);
+    const size_t smem = gru_bwd_smem(d, DP);
+    float* partial = (float*)workspace;
+    switch (DP) {
+      case 8: k_gru_bwd_fused<8><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
+      case 16: k_gru_bwd_fused<16><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
+      default: k_gru_bwd_fused<32><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
+    }
+    MPNN_CHECK_LAUNCH("k_gru_bwd_fused");
+    k_gru_bwd_reduce<<<ceil_div(6 * d * d + 6 * d, 128), 128, 0, stream>>>(partial, grid, d, dW_ih, dW_hh, db_ih, db_hh);
+    MPNN_CHECK_LAUNCH("k_gru_bwd_reduce");
+    return MPNN_OK;
+  }
   char* wp = (char*)workspace;
   float* dgi = (float*)wp;
   wp += align_up((size_t)rows * 3 * d * sizeof(float), 256);

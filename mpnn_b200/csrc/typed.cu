@@ -142,11 +142,10 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_src(TMsg a, const int* __restr
 // type u) pair goes to slot c + u (pairs are strictly increasing in c + u along the sorted list).
 //   dT[u][l][k] = sum_{e in type u} alpha_e H[src_e, l] dM[dst_e, k]
 // ---------------------------------------------------------------------------------------------------
-constexpr int CH = 256;  // edges per chunk
-constexpr int SB = 32;   // edges staged per round
+constexpr int SB = 64;   // edges staged per round (chunk sizes are multiples of SB)
 
 template <int DP>
-__global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __restrict__ counts, int cap,
+__global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __restrict__ counts, int cap, int ch,
                                                         const int* __restrict__ type_eid, const float* __restrict__ dM,
                                                         float* __restrict__ part) {
   constexpr int OPT = (DP * DP + 255) / 256;  // outputs per thread (DP=32: 4, else 1)
@@ -154,9 +153,9 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __res
   __shared__ float m[SB][DP + 1];
   __shared__ int ty[SB];
   const int E = min(counts[0], cap);
-  const int p0 = blockIdx.x * CH;
+  const int p0 = blockIdx.x * ch;
   if (p0 >= E) return;
-  const int p1 = min(p0 + CH, E);
+  const int p1 = min(p0 + ch, E);
   const int tid = threadIdx.x;
   // thread -> (l, k0..k0+OPT): consecutive threads walk k first
   const int o0 = tid * OPT;
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __res
 // level 2: one block per type; sums the type's chunk partials in chunk order.  dT [(ucap+1)][DP][DP].
 template <int DP>
 __global__ void __launch_bounds__(256) k_tmsg_bwd_table_reduce(const int* __restrict__ type_ptr,
-                                                               const float* __restrict__ part, int zero_type,
+                                                               const float* __restrict__ part, int zero_type, int ch,
                                                                float* __restrict__ dT) {
   const int u = blockIdx.x;
   float* out = dT + (size_t)u * DP * DP;
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_table_reduce(const int* __rest
   for (int o = threadIdx.x; o < DP * DP; o += 256) {
     float s = 0.f;
     if (e > b) {
-      const int c0 = b / CH, c1 = (e - 1) / CH;
+      const int c0 = b / ch, c1 = (e - 1) / ch;
       const float* p = part + (size_t)(c0 + u) * DP * DP + o;
 #pragma unroll 4
       for (int c = c0; c <= c1; ++c, p += DP * DP) s += *p;
@@ -270,10 +269,12 @@ __global__ void k_table_to_flat(const float* __restrict__ dT, int R, int nf, int
 
 // ===================================================================================================
 // Fused edge network on the distinct rows, P <= 64:  growth layers -> 50 tied layers -> table.
-// One CTA per RT rows; thread (r, o) = (tid / 64, tid % 64).  W_tied^T resident in shared memory.
+// One distinct row per CTA at a time (the rows are few and the 50 layers are a serial chain, so the kernel is
+// latency-bound: every dot product is split over 4 lanes and finished with two shuffles, one barrier per
+// layer).  The tied weight stays in shared memory for all layers.
 // ===================================================================================================
-constexpr int RT = 4;     // rows per CTA
 constexpr int PW = 64;    // max padded trunk width handled here
+constexpr int WS_ = 68;   // shared-memory row stride of the tied weight (== 4 mod 32: conflict-free 4-lane split)
 constexpr int MAXG = 4;
 
 struct ENet {
@@ -287,199 +288,218 @@ struct ENet {
   int gin[MAXG], gout[MAXG];
 };
 
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
 // saved layout (floats): acts[(G + L + 1)][R][PW] : slot 0 = input rows (zero padded), 1..G growth outputs,
 // G+1..G+L tied outputs (slot G+L = x)
 __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ acts, float* __restrict__ table,
                                                   float* __restrict__ tableT) {
-  __shared__ __align__(16) float Wt[PW * PW];      // Wt[i][o] = W[o][i]
-  __shared__ __align__(16) float A[2][RT][PW];
+  __shared__ __align__(16) float Wn[PW * WS_];   // Wn[o][i] = W[o][i]
+  __shared__ __align__(16) float A[2][PW];
   const int tid = threadIdx.x;
-  const int r = tid >> 6, o = tid & 63;
-  const int row0 = blockIdx.x * RT;
-  const int row = row0 + r;
-  const bool live = row < n.R;
+  const int o = tid >> 2, q = tid & 3;
   const int P = n.P;
   for (int idx = tid; idx < PW * PW; idx += 256) {
     int oo = idx / PW, ii = idx - oo * PW;
-    Wt[ii * PW + oo] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
+    Wn[oo * WS_ + ii] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
   }
-  float v = (live && o < n.ef) ? n.rows[(size_t)row * n.ef + o] : 0.f;
-  A[0][r][o] = v;
-  if (live) acts[((size_t)0 * n.R + row) * PW + o] = v;
-  __syncthreads();
-  int cur = 0;
-  int slot = 1;
-  for (int g = 0; g < n.G; ++g, ++slot) {
-    float acc = 0.f;
-    if (o < n.gout[g]) {
-      const float* w = n.gw[g] + (size_t)o * n.gin[g];
-      acc = n.gb[g][o];
-      for (int i = 0; i < n.gin[g]; ++i) acc = fmaf(__ldg(w + i), A[cur][r][i], acc);
-      acc = fmaxf(acc, 0.f);
+  for (int row = blockIdx.x; row < n.R; row += gridDim.x) {
+    __syncthreads();  // Wn loaded / previous row done with A
+    if (tid < PW) {
+      float v = tid < n.ef ? n.rows[(size_t)row * n.ef + tid] : 0.f;
+      A[0][tid] = v;
+      acts[((size_t)0 * n.R + row) * PW + tid] = v;
     }
-    A[cur ^ 1][r][o] = acc;
-    if (live) acts[((size_t)slot * n.R + row) * PW + o] = acc;
     __syncthreads();
-    cur ^= 1;
-  }
-  for (int l = 0; l < n.L; ++l, ++slot) {
-    float acc = 0.f;
-    const float4* ap = reinterpret_cast<const float4*>(&A[cur][r][0]);
-    const float* wp = Wt + o;
-#pragma unroll 4
-    for (int i4 = 0; i4 < PW / 4; ++i4) {
-      float4 a4 = ap[i4];
-      acc = fmaf(a4.x, wp[(i4 * 4 + 0) * PW], acc);
-      acc = fmaf(a4.y, wp[(i4 * 4 + 1) * PW], acc);
-      acc = fmaf(a4.z, wp[(i4 * 4 + 2) * PW], acc);
-      acc = fmaf(a4.w, wp[(i4 * 4 + 3) * PW], acc);
+    int cur = 0, slot = 1;
+    for (int g = 0; g < n.G; ++g, ++slot) {
+      float acc = 0.f;
+      if (o < n.gout[g]) {
+        const float* w = n.gw[g] + (size_t)o * n.gin[g];
+        for (int i = q; i < n.gin[g]; i += 4) acc = fmaf(__ldg(w + i), A[cur][i], acc);
+      }
+      acc = quad_sum(acc);
+      if (q == 0) {
+        acc = o < n.gout[g] ? fmaxf(acc + n.gb[g][o], 0.f) : 0.f;
+        A[cur ^ 1][o] = acc;
+        acts[((size_t)slot * n.R + row) * PW + o] = acc;
+      }
+      __syncthreads();
+      cur ^= 1;
     }
-    acc = fmaxf(acc, 0.f);
-    A[cur ^ 1][r][o] = acc;
-    if (live) acts[((size_t)slot * n.R + row) * PW + o] = acc;
-    __syncthreads();
-    cur ^= 1;
-  }
-  // table rows of this CTA's distinct rows: T[u][l][k] = B[k*nf+l] + W_last[k*nf+l, :] . x_u
-  const int DP = n.DP;
-  const int nout = n.mf * n.nf;
-  for (int q = tid; q < RT * DP * DP; q += 256) {
-    const int rr = q / (DP * DP);
-    const int lk = q - rr * DP * DP;
-    const int l = lk / DP, k = lk - l * DP;
-    const int u = row0 + rr;
-    if (u >= n.R) continue;
-    float acc = 0.f;
-    if (l < n.nf && k < n.mf) {
-      const int f = k * n.nf + l;
+    const float* wrow = Wn + o * WS_ + q;
+    for (int l = 0; l < n.L; ++l, ++slot) {
+      const float* ap = &A[cur][q];
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int ii = 0; ii < PW / 4; ii += 2) {
+        a0 = fmaf(wrow[ii * 4], ap[ii * 4], a0);
+        a1 = fmaf(wrow[ii * 4 + 4], ap[ii * 4 + 4], a1);
+      }
+      float acc = quad_sum(a0 + a1);
+      if (q == 0) {
+        acc = fmaxf(acc, 0.f);
+        A[cur ^ 1][o] = acc;
+        acts[((size_t)slot * n.R + row) * PW + o] = acc;
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+    // table of this distinct row: T[u][l][k] = B[k*nf+l] + W_last[k*nf+l, :] . x_u   (one warp per output, lanes over p)
+    const int DP = n.DP;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nout = n.mf * n.nf;
+    const float x0 = lane < P ? A[cur][lane] : 0.f;
+    const float x1 = lane + 32 < P ? A[cur][lane + 32] : 0.f;
+    for (int f = warp; f < nout; f += 8) {
       const float* w = n.w_last + (size_t)f * P;
-      acc = n.b_last[f];
-      for (int p = 0; p < P; ++p) acc = fmaf(__ldg(w + p), A[cur][rr][p], acc);
+      float acc = lane < P ? __ldg(w + lane) * x0 : 0.f;
+      if (lane + 32 < P) acc = fmaf(__ldg(w + lane + 32), x1, acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        acc += n.b_last[f];
+        const int k = f / n.nf, l = f - k * n.nf;
+        table[((size_t)row * DP + l) * DP + k] = acc;
+        tableT[((size_t)row * DP + k) * DP + l] = acc;
+      }
     }
-    table[((size_t)u * DP + l) * DP + k] = acc;
-    tableT[((size_t)u * DP + k) * DP + l] = acc;
+    // zero the padding of the table (feature widths that are not a power of two)
+    if (n.nf < DP || n.mf < DP) {
+      for (int e = tid; e < DP * DP; e += 256) {
+        const int l = e / DP, k = e - l * DP;
+        if (l >= n.nf || k >= n.mf) {
+          table[((size_t)row * DP + l) * DP + k] = 0.f;
+          tableT[((size_t)row * DP + k) * DP + l] = 0.f;
+        }
+      }
+    }
   }
-  (void)nout;
 }
 
-// backward of the fused edge network.  Per CTA (RT rows): dx = dT . W_last, tied layers (dW_tied partial in
-// registers: thread owns a 4 x 4 micro-tile of the 64 x 64 gradient), growth layers; partials per CTA.
-// partial layout per CTA (floats): [PW*PW tied] then for each growth layer g: [gout*gin weights][gout bias]
+// backward of the fused edge network.  Per distinct row: dx = dT . W_last, the tied layers (dW_tied partial in
+// registers: thread owns a 4 x 4 micro-tile of the 64 x 64 gradient, accumulated over the CTA's rows), the growth
+// layers; partials per CTA.
+// partial layout per CTA (floats): [PW*PW tied] then for g = G-1 .. 0: [gout*gin weights][gout bias]
 __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restrict__ acts, const float* __restrict__ dT,
                                                   float* __restrict__ partial, int partial_stride,
                                                   float* __restrict__ d_rows /*[R, ef] or null*/) {
-  __shared__ __align__(16) float Ws[PW * (PW + 4)];  // natural W[o][i], row stride PW+4
-  __shared__ __align__(16) float D[RT][PW];          // delta (masked gradient of the layer output)
-  __shared__ __align__(16) float Ap[RT][PW];         // a_{l-1}
-  __shared__ __align__(16) float dA[RT][PW];
-  const int WS = PW + 4;
+  __shared__ __align__(16) float Wt[PW * WS_];   // Wt[i][o] = W[o][i]
+  __shared__ __align__(16) float D[2][PW];       // delta of the current layer
+  __shared__ __align__(16) float Ap[2][PW];      // input activation of the current layer
+  __shared__ __align__(16) float dAs[PW];        // un-masked gradient w.r.t. the tied input
+  __shared__ float red4[4][PW];
   const int tid = threadIdx.x;
-  const int r = tid >> 6, o = tid & 63;
-  const int row0 = blockIdx.x * RT;
-  const int row = row0 + r;
-  const bool live = row < n.R;
+  const int i_ = tid >> 2, q = tid & 3;          // (output index, split lane) of the dA dot products
+  const int og = tid >> 4, ig = tid & 15;        // dW micro-tile
   const int P = n.P, DP = n.DP;
   for (int idx = tid; idx < PW * PW; idx += 256) {
     int oo = idx / PW, ii = idx - oo * PW;
-    Ws[oo * WS + ii] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
+    Wt[ii * WS_ + oo] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
   }
-  // dx[r][p] = sum_{k,l} dT[u][l][k] W_last[k*nf+l, p]
-  {
-    float acc = 0.f;
-    if (live && o < P) {
-      const float* dt = dT + (size_t)row * DP * DP;
-      for (int k = 0; k < n.mf; ++k)
-        for (int l = 0; l < n.nf; ++l)
-          acc = fmaf(__ldg(dt + l * DP + k), __ldg(n.w_last + (size_t)(k * n.nf + l) * P + o), acc);
-    }
-    dA[r][o] = acc;
-  }
-  const int nslots = n.G + n.L + 1;
-  auto act = [&](int slot, int rr, int c) -> float {
-    int rw = row0 + rr;
-    return rw < n.R ? acts[((size_t)slot * n.R + rw) * PW + c] : 0.f;
-  };
-  Ap[r][o] = act(nslots - 1, r, o);
-  __syncthreads();
-  // dW_tied micro-tile owned by this thread: rows og*4.., cols ig*4..
-  const int og = tid >> 4, ig = tid & 15;
   float accW[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) accW[a][b] = 0.f;
-  for (int l = n.L; l >= 1; --l) {
-    const int slot = n.G + l;  // output slot of tied layer l; its input is slot-1
-    const float aout = Ap[r][o];
-    const float dl = aout > 0.f ? dA[r][o] : 0.f;
-    const float aprev = act(slot - 1, r, o);
-    __syncthreads();
-    D[r][o] = dl;
-    Ap[r][o] = aprev;
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < RT; ++rr) {
-      float4 d4 = *reinterpret_cast<const float4*>(&D[rr][og * 4]);
-      float4 a4 = *reinterpret_cast<const float4*>(&Ap[rr][ig * 4]);
-      float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-      float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) accW[a][b] = fmaf(dv[a], av[b], accW[a][b]);
-    }
-    // dA_prev[r][i=o] = sum_oo delta[r][oo] W[oo][o]
-    float acc = 0.f;
-    const float4* dp = reinterpret_cast<const float4*>(&D[r][0]);
-#pragma unroll 4
-    for (int q = 0; q < PW / 4; ++q) {
-      float4 d4 = dp[q];
-      acc = fmaf(d4.x, Ws[(q * 4 + 0) * WS + o], acc);
-      acc = fmaf(d4.y, Ws[(q * 4 + 1) * WS + o], acc);
-      acc = fmaf(d4.z, Ws[(q * 4 + 2) * WS + o], acc);
-      acc = fmaf(d4.w, Ws[(q * 4 + 3) * WS + o], acc);
-    }
-    dA[r][o] = acc;  // own element only: no hazard with other threads' reads of D/Ap
-  }
   float* part = partial + (size_t)blockIdx.x * partial_stride;
+  // growth partials accumulate over the CTA's rows in global memory (own slice): zero them first
+  for (int e = PW * PW + tid; e < partial_stride; e += 256) part[e] = 0.f;
+  const int nslots = n.G + n.L + 1;
+  for (int row = blockIdx.x; row < n.R; row += gridDim.x) {
+    __syncthreads();
+    // dx[p] = sum_f dT[row][l][k] W_last[f, p]   (f = k*nf + l), f split over the 4 warp pairs
+    {
+      const int p = tid & 63, part_f = tid >> 6;
+      float acc = 0.f;
+      if (p < P) {
+        const float* dt = dT + (size_t)row * DP * DP;
+        const int nout = n.mf * n.nf;
+        for (int f = part_f; f < nout; f += 4) {
+          const int k = f / n.nf, l = f - k * n.nf;
+          acc = fmaf(__ldg(dt + l * DP + k), __ldg(n.w_last + (size_t)f * P + p), acc);
+        }
+      }
+      red4[part_f][p] = acc;
+    }
+    __syncthreads();
+    if (tid < PW) {
+      const float g = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
+      const float aout = acts[((size_t)(nslots - 1) * n.R + row) * PW + tid];
+      D[0][tid] = aout > 0.f ? g : 0.f;
+      Ap[0][tid] = acts[((size_t)(nslots - 2) * n.R + row) * PW + tid];
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int l = n.L; l >= 1; --l) {
+      // slot of this layer's input: G + l - 1; prefetch the input of the NEXT (lower) layer: slot G + l - 2
+      float pre = 0.f;
+      if (q == 0 && l >= 2) pre = acts[((size_t)(n.G + l - 2) * n.R + row) * PW + i_];
+      {
+        float4 d4 = *reinterpret_cast<const float4*>(&D[cur][og * 4]);
+        float4 a4 = *reinterpret_cast<const float4*>(&Ap[cur][ig * 4]);
+        float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) accW[a][b] = fmaf(dv[a], av[b], accW[a][b]);
+      }
+      const float* wt = Wt + i_ * WS_ + q;
+      const float* dp = &D[cur][q];
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int oo = 0; oo < PW / 4; oo += 2) {
+        a0 = fmaf(dp[oo * 4], wt[oo * 4], a0);
+        a1 = fmaf(dp[oo * 4 + 4], wt[oo * 4 + 4], a1);
+      }
+      const float g = quad_sum(a0 + a1);   // gradient w.r.t. this layer's input a_{l-1}[i_]
+      if (q == 0) {
+        if (l >= 2) {
+          D[cur ^ 1][i_] = Ap[cur][i_] > 0.f ? g : 0.f;
+          Ap[cur ^ 1][i_] = pre;
+        } else {
+          dAs[i_] = g;
+        }
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+    // growth layers, last to first; dAs = gradient w.r.t. the output of growth layer G-1 (or the input rows)
+    size_t poff = (size_t)PW * PW;
+    for (int g = n.G - 1; g >= 0; --g) {
+      const int gin = n.gin[g], gout = n.gout[g];
+      // delta and input activation of this layer
+      if (tid < PW) {
+        const float aout = acts[((size_t)(g + 1) * n.R + row) * PW + tid];
+        D[0][tid] = (tid < gout && aout > 0.f) ? dAs[tid] : 0.f;
+        Ap[0][tid] = acts[((size_t)g * n.R + row) * PW + tid];
+      }
+      __syncthreads();
+      for (int e = tid; e < gout * gin; e += 256) {
+        const int oo = e / gin, ii = e - oo * gin;
+        part[poff + e] += D[0][oo] * Ap[0][ii];
+      }
+      for (int e = tid; e < gout; e += 256) part[poff + (size_t)gout * gin + e] += D[0][e];
+      poff += (size_t)gout * gin + gout;
+      float acc = 0.f;
+      if (tid < gin) {
+        const float* w = n.gw[g] + tid;
+        for (int oo = 0; oo < gout; ++oo) acc = fmaf(D[0][oo], __ldg(w + (size_t)oo * gin), acc);
+      }
+      __syncthreads();
+      if (tid < PW) dAs[tid] = tid < gin ? acc : 0.f;
+      __syncthreads();
+    }
+    if (d_rows && tid < n.ef) d_rows[(size_t)row * n.ef + tid] = dAs[tid];
+  }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
     *reinterpret_cast<float4*>(part + (og * 4 + a) * PW + ig * 4) =
         make_float4(accW[a][0], accW[a][1], accW[a][2], accW[a][3]);
-  size_t poff = (size_t)PW * PW;
-  // growth layers, last to first.  Ap holds the output of growth layer g (= tied input) at loop entry.
-  for (int g = n.G - 1; g >= 0; --g) {
-    const int slot = g + 1;
-    const float aout = Ap[r][o];
-    const float dl = (o < n.gout[g] && aout > 0.f) ? dA[r][o] : 0.f;
-    const float aprev = act(slot - 1, r, o);
-    __syncthreads();
-    D[r][o] = dl;
-    Ap[r][o] = aprev;
-    __syncthreads();
-    const int gin = n.gin[g], gout = n.gout[g];
-    for (int q = tid; q < gout * gin; q += 256) {
-      int oo = q / gin, ii = q - oo * gin;
-      float s = 0.f;
-#pragma unroll
-      for (int rr = 0; rr < RT; ++rr) s = fmaf(D[rr][oo], Ap[rr][ii], s);
-      part[poff + q] = s;
-    }
-    for (int q = tid; q < gout; q += 256) {
-      float s = 0.f;
-#pragma unroll
-      for (int rr = 0; rr < RT; ++rr) s += D[rr][q];
-      part[poff + (size_t)gout * gin + q] = s;
-    }
-    poff += (size_t)gout * gin + gout;
-    float acc = 0.f;
-    if (o < gin) {
-      const float* w = n.gw[g] + o;
-      for (int oo = 0; oo < gout; ++oo) acc = fmaf(D[r][oo], __ldg(w + (size_t)oo * gin), acc);
-    }
-    dA[r][o] = acc;
-  }
-  if (d_rows && live && o < n.ef) d_rows[(size_t)row * n.ef + o] = dA[r][o];
 }
 
 // fixed-order reduction of the per-CTA partials: out[idx] = sum_c partial[c][idx]
@@ -524,6 +544,13 @@ int pick_dp(int nf, int mf) {
   return pow2_at_least(d, 8);
 }
 
+// edges per chunk of the table-gradient pass: enough chunks to fill the machine, few enough partials to reduce
+int table_chunk(int edge_capacity) {
+  int ch = SB;
+  while (ch < 1024 && (long long)ch * 4 * mpnn_num_sms() < edge_capacity) ch <<= 1;
+  return ch;
+}
+
 int msg_grid(int n_rows, int DP) {
   int per = 256 / DP;
   int want = ceil_div(n_rows, per);
@@ -560,6 +587,11 @@ bool fill_enet(ENet* n, const float* rows, int R, int ef, int G, const float* co
     w = w * w;
   }
   return w == P && ef <= PW;
+}
+
+int enet_grid(int R) {
+  int cap = 2 * mpnn_num_sms();
+  return R < cap ? (R > 0 ? R : 1) : cap;
 }
 
 int enet_partial_stride(const ENet& n) {
@@ -615,7 +647,7 @@ size_t mpnn_enet_workspace_bytes(int R, int ef, int n_growth, int P) {
   const float* dummy[MAXG] = {nullptr, nullptr, nullptr, nullptr};
   if (!fill_enet(&n, nullptr, R, ef, n_growth, dummy, dummy, nullptr, P, 1, nullptr, nullptr, 1, 1)) return 0;
   size_t stride = (size_t)enet_partial_stride(n);
-  return ((size_t)ceil_div(R, RT) + 1) * stride * sizeof(float);
+  return ((size_t)enet_grid(R) + 1) * stride * sizeof(float);
 }
 
 int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
@@ -628,7 +660,7 @@ int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* c
                MPNN_ERR_UNSUPPORTED, "enet_fwd: layer plan ef=%d growth=%d P=%d not supported by the fused kernel", ef,
                n_growth, P);
   MPNN_REQUIRE(n.DP <= 32, MPNN_ERR_UNSUPPORTED, "enet_fwd: feature width > 32");
-  k_enet_fwd<<<ceil_div(R, RT), 256, 0, stream>>>(n, saved, table, tableT);
+  k_enet_fwd<<<enet_grid(R), 256, 0, stream>>>(n, saved, table, tableT);
   MPNN_CHECK_LAUNCH("k_enet_fwd");
   return MPNN_OK;
 }
@@ -645,7 +677,7 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   MPNN_REQUIRE(workspace_bytes >= mpnn_enet_workspace_bytes(R, ef, n_growth, P), MPNN_ERR_WORKSPACE,
                "enet_bwd: workspace too small");
   const int stride = enet_partial_stride(n);
-  const int nparts = ceil_div(R, RT);
+  const int nparts = enet_grid(R);
   float* partial = (float*)workspace;
   float* red = partial + (size_t)nparts * stride;
   k_enet_bwd<<<nparts, 256, 0, stream>>>(n, saved, dT, partial, stride, d_rows);
@@ -672,7 +704,7 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
 // ---- typed message + aggregation ------------------------------------------------------------------------
 size_t mpnn_tmsg_bwd_workspace_bytes(int edge_capacity, int unique_capacity, int nf, int mf, int B) {
   int DP = pick_dp(nf, mf);
-  size_t chunks = (size_t)ceil_div(edge_capacity > 0 ? edge_capacity : 1, CH);
+  size_t chunks = (size_t)ceil_div(edge_capacity > 0 ? edge_capacity : 1, table_chunk(edge_capacity));
   return (chunks + unique_capacity + 2) * DP * DP * sizeof(float) + align_up((size_t)B * mf * sizeof(float), 256);
 }
 
@@ -717,24 +749,25 @@ int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, co
     if (rc) return rc;
   }
   const int grid = msg_grid(n_rows, DP);
-  const int chunks = ceil_div(edge_capacity > 0 ? edge_capacity : 1, CH);
+  const int ch = table_chunk(edge_capacity);
+  const int chunks = ceil_div(edge_capacity > 0 ? edge_capacity : 1, ch);
   switch (DP) {
     case 8:
       k_tmsg_bwd_src<8><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
-      k_tmsg_bwd_table<8><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, type_eid, dM, part);
-      k_tmsg_bwd_table_reduce<8><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, dT);
+      k_tmsg_bwd_table<8><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);
+      k_tmsg_bwd_table_reduce<8><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);
       if (S) k_tmsg_bwd_table_zero<8><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
       break;
     case 16:
       k_tmsg_bwd_src<16><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
-      k_tmsg_bwd_table<16><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, type_eid, dM, part);
-      k_tmsg_bwd_table_reduce<16><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, dT);
+      k_tmsg_bwd_table<16><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);
+      k_tmsg_bwd_table_reduce<16><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);
       if (S) k_tmsg_bwd_table_zero<16><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
       break;
     default:
       k_tmsg_bwd_src<32><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
-      k_tmsg_bwd_table<32><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, type_eid, dM, part);
-      k_tmsg_bwd_table_reduce<32><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, dT);
+      k_tmsg_bwd_table<32><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);
+      k_tmsg_bwd_table_reduce<32><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);
       if (S) k_tmsg_bwd_table_zero<32><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
       break;
   }
