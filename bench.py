@@ -89,6 +89,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def make_workload_batch(config, w, rank):
+    from mpnn_b200 import synthetic
+    batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=w["B"], seed_offset=rank)
+    if config != "qm9":
+        batch["labels"] = np.random.RandomState(rank).normal(size=(w["B"], w["targets"])).astype(np.float32)
+    return batch
+
+
 def build_model(w, dev):
     from mpnn_b200.callers import MessagePassingModel, kaiming_init
     torch.manual_seed(317)
@@ -118,9 +126,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     w = WORKLOADS[args.config]
     B = w["B"]
-    batch = synthetic.make_batch("qm9" if args.config == "qm9" else args.config, B=B, seed_offset=rank)
-    if args.config != "qm9":
-        batch["labels"] = np.random.RandomState(rank).normal(size=(B, w["targets"])).astype(np.float32)
+    batch = make_workload_batch(args.config, w, rank)
     n, e = batch["n_atoms"], batch["n_edges"]
     keys = ("afm", "bfm", "adj", "mask", "labels")
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in keys}

@@ -40,6 +40,7 @@ struct RedArgs {
 };
 
 // thread -> (column tid % C, row lane tid / C); partial[block][q][C]
+template <int MODE>
 __global__ void k_bn_stage(RedArgs a, float* __restrict__ partial) {
   extern __shared__ float sm[];
   __shared__ int is_last;
@@ -54,12 +55,13 @@ __global__ void k_bn_stage(RedArgs a, float* __restrict__ partial) {
     const float m0 = a.p0 ? a.p0[c] : 0.f;
     float m1 = a.p1 ? a.p1[c] : 0.f;
     const float m2 = a.p2 ? a.p2[c] : 1.f;  // weight (affine off -> 1)
-    if (a.mode == BWD_1D_TRAIN) m1 = 1.f / (m1 + a.eps);           // p1 = sd
-    if (a.mode == BWD_1D_EVAL) m1 = 1.f / (sqrtf(m1) + a.eps);     // p1 = running_var
+    if (MODE == BWD_1D_TRAIN) m1 = 1.f / (m1 + a.eps);           // p1 = sd
+    if (MODE == BWD_1D_EVAL) m1 = 1.f / (sqrtf(m1) + a.eps);     // p1 = running_var
+#pragma unroll 4
     for (long long r = r0 + rl; r < r1; r += lanes) {
       const float xv = a.x[r * C + c];
       const float mu = a.mask[r];
-      switch (a.mode) {
+      switch (MODE) {
         case STATS1:
           q[0] += xv;
           q[1] += xv * mu;
@@ -122,8 +124,10 @@ __global__ void k_bn_stage(RedArgs a, float* __restrict__ partial) {
     const int e = e0 + (int)threadIdx.x % (nsl > 1 ? nqC : blockDim.x);
     const int sl = nsl > 1 ? threadIdx.x / nqC : 0;
     float s = 0.f;
-    if (e < nqC && sl < nsl)
+    if (e < nqC && sl < nsl) {
+#pragma unroll 8
       for (int b = sl; b < nblk; b += nsl) s += __ldcg(partial + (size_t)b * nqC + e);
+    }
     __syncthreads();
     sm[threadIdx.x] = s;
     __syncthreads();
@@ -244,7 +248,7 @@ __global__ void k_1d_bwd_apply_eval(const float* __restrict__ mask, const float*
 int red_blocks(long long rows, int* rpb) {
   int target = 2 * mpnn_num_sms();
   long long per = (rows + target - 1) / target;
-  if (per < 32) per = 32;
+  if (per < 128) per = 128;   // small inputs: fewer partials for the last block to sum
   *rpb = (int)per;
   return (int)((rows + per - 1) / per);
 }
@@ -254,7 +258,13 @@ int run_stage(RedArgs a, float* partial, cudaStream_t stream) {
   int nblk = red_blocks(a.rows, &rpb);
   a.rows_per_block = rpb;
   int threads = a.C >= 256 ? a.C : (256 / a.C) * a.C;
-  k_bn_stage<<<nblk, threads, threads * sizeof(float), stream>>>(a, partial);
+  switch (a.mode) {
+    case STATS1: k_bn_stage<STATS1><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
+    case STATS2: k_bn_stage<STATS2><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
+    case BWD_PLAIN: k_bn_stage<BWD_PLAIN><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
+    case BWD_1D_TRAIN: k_bn_stage<BWD_1D_TRAIN><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
+    default: k_bn_stage<BWD_1D_EVAL><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
+  }
   MPNN_CHECK_LAUNCH("k_bn_stage");
   return MPNN_OK;
 }

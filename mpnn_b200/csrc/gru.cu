@@ -95,9 +95,24 @@ __global__ void __launch_bounds__(256) k_gru_fwd_fused(const float* __restrict__
   extern __shared__ __align__(16) float sm[];
   float* Wi = sm;               // [d][3d]
   float* Wh = sm + d * 3 * d;   // [d][3d]
-  for (int i = threadIdx.x; i < d * 3 * d; i += 256) {
-    Wi[i] = W_ih[i];
-    Wh[i] = W_hh[i];
+  {
+    constexpr int NW = (3 * DP * DP + 255) / 256;
+    const int nw = d * 3 * d;
+    float wi[NW], wh[NW];
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {  // unconditional clamped loads: all in flight together
+      const int i = min((int)threadIdx.x + t * 256, nw - 1);
+      wi[t] = __ldg(W_ih + i);
+      wh[t] = __ldg(W_hh + i);
+    }
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = threadIdx.x + t * 256;
+      if (i < nw) {
+        Wi[i] = wi[t];
+        Wh[i] = wh[t];
+      }
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -109,8 +124,10 @@ __global__ void __launch_bounds__(256) k_gru_fwd_fused(const float* __restrict__
   const float bir = b_ih[cc], biz = b_ih[d + cc], bin = b_ih[2 * d + cc];
   const float bhr = b_hh[cc], bhz = b_hh[d + cc], bhn = b_hh[2 * d + cc];
   for (long long row = (long long)blockIdx.x * gpb + threadIdx.x / DP; row < rows; row += (long long)gridDim.x * gpb) {
-    const float mv = on ? m[row * d + c] : 0.f;
-    const float hv = on ? h[row * d + c] : 0.f;
+    float mv = __ldg(m + row * d + cc);
+    float hv = __ldg(h + row * d + cc);
+    const float mu = __ldg(mask + row);
+    if (!on) mv = hv = 0.f;
     float ir = bir, iz = biz, in_ = bin, hr = bhr, hz = bhz, hn = bhn;
 #pragma unroll 4
     for (int l = 0; l < d; ++l) {
@@ -126,7 +143,6 @@ __global__ void __launch_bounds__(256) k_gru_fwd_fused(const float* __restrict__
       hn = fmaf(hl, wh[2 * d], hn);
     }
     if (on) {
-      const float mu = mask[row];
       const float sr = 1.f / (1.f + expf(-(ir + hr)));
       const float sz = 1.f / (1.f + expf(-(iz + hz)));
       const float r = sr * mu, z = sz * mu;
@@ -161,10 +177,25 @@ __global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__
   float* Hs = Ms + TR * d;            // [TR][d]
   float* Gi = Hs + TR * d;            // [TR][3d]
   float* Gh = Gi + TR * d3;           // [TR][3d]
-  for (int i = threadIdx.x; i < d * d3; i += 256) {
-    int l = i / d3, g = i - l * d3;
-    WiT[g * ldt + l] = W_ih[i];
-    WhT[g * ldt + l] = W_hh[i];
+  {
+    constexpr int NW = (3 * DP * DP + 255) / 256;
+    const int nw = d * d3;
+    float wi[NW], wh[NW];
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = min((int)threadIdx.x + t * 256, nw - 1);
+      wi[t] = __ldg(W_ih + i);
+      wh[t] = __ldg(W_hh + i);
+    }
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = threadIdx.x + t * 256;
+      if (i < nw) {
+        const int l = i / d3, g = i - l * d3;
+        WiT[g * ldt + l] = wi[t];
+        WhT[g * ldt + l] = wh[t];
+      }
+    }
   }
   const int lane = threadIdx.x & 31;
   const int c = lane % DP;
@@ -181,14 +212,19 @@ __global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__
     const bool live = row < rows;
     __syncthreads();  // previous tile's accumulation is done with the staging buffers (and W*T are loaded)
     float dar = 0.f, daz = 0.f, dan = 0.f, dnh = 0.f, dhd = 0.f, mv = 0.f, hv = 0.f;
-    if (live && on) {
-      const float mu = mask[row];
-      const float* g = gates + row * 4 * d;
-      const float sr = g[c], sz = g[d + c], tn = g[2 * d + c], nh = g[3 * d + c];
+    {
+      // unconditional clamped loads (8 requests in flight), masked afterwards
+      const long long rr = live ? row : rows - 1;
+      const int cq = on ? c : 0;
+      const float* g = gates + rr * 4 * d;
+      const float mu = __ldg(mask + rr);
+      const float sr = __ldg(g + cq), sz = __ldg(g + d + cq), tn = __ldg(g + 2 * d + cq), nh = __ldg(g + 3 * d + cq);
+      const float hl = __ldg(h + rr * d + cq), ml = __ldg(m + rr * d + cq), dl = __ldg(dhout + rr * d + cq);
+      if (live && on) {
       const float r = sr * mu, z = sz * mu, n = tn * mu;
-      hv = h[row * d + c];
-      mv = m[row * d + c];
-      const float go = dhout[row * d + c] * mu;
+      hv = hl;
+      mv = ml;
+      const float go = dl * mu;
       const float dn = go * (1.f - z);
       const float dz = go * (hv - n);
       dan = dn * mu * (1.f - tn * tn);
@@ -197,6 +233,7 @@ __global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__
       dar = dr * mu * sr * (1.f - sr);
       daz = dz * mu * sz * (1.f - sz);
       dhd = go * z;
+      }
     }
     if (on) {
       Ms[grp * d + c] = mv;
@@ -255,14 +292,26 @@ __global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__
   if (threadIdx.x < 2 * d3) part[2 * nW + threadIdx.x] = accb;
 }
 
-__global__ void k_gru_bwd_reduce(const float* __restrict__ partial, int nparts, int d, float* __restrict__ dW_ih,
-                                 float* __restrict__ dW_hh, float* __restrict__ db_ih, float* __restrict__ db_hh) {
+// 32 elements x 8 partial slices per block; slices are combined in a fixed order
+__global__ void __launch_bounds__(256) k_gru_bwd_reduce(const float* __restrict__ partial, int nparts, int d,
+                                                        float* __restrict__ dW_ih, float* __restrict__ dW_hh,
+                                                        float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  __shared__ float sm[8][33];
   const int nW = d * 3 * d, d3 = 3 * d;
   const int total = 2 * nW + 2 * d3;
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
+  const int el = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + el;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * total + e];
+  if (e < total) {
+#pragma unroll 4
+    for (int p = sl; p < nparts; p += 8) s += partial[(size_t)p * total + e];
+  }
+  sm[sl][el] = s;
+  __syncthreads();
+  if (sl != 0 || e >= total) return;
+  s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += sm[j][el];
   if (e < nW)
     dW_ih[e] = s;
   else if (e < 2 * nW)
@@ -350,7 +399,7 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
       default: k_gru_bwd_fused<32><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
     }
     MPNN_CHECK_LAUNCH("k_gru_bwd_fused");
-    k_gru_bwd_reduce<<<ceil_div(6 * d * d + 6 * d, 128), 128, 0, stream>>>(partial, grid, d, dW_ih, dW_hh, db_ih, db_hh);
+    k_gru_bwd_reduce<<<ceil_div(6 * d * d + 6 * d, 32), 256, 0, stream>>>(partial, grid, d, dW_ih, dW_hh, db_ih, db_hh);
     MPNN_CHECK_LAUNCH("k_gru_bwd_reduce");
     return MPNN_OK;
   }

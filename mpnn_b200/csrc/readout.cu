@@ -255,6 +255,291 @@ __global__ void k_row_scale(float* __restrict__ a, float* __restrict__ b, const 
   b[t] *= mu;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused masked readout for O <= 64, F2 <= 64 (the reference's configurations): projections + feature softmax +
+// gate + per-graph sum in ONE kernel forward; backward = one kernel (du', dv', dx, per-CTA weight-gradient
+// partials) + a fixed-order reduction.  A warp owns a row; lane o (+32) owns output feature o.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FO = 64;   // max O and F2 of the fused kernels
+constexpr int FK = 2;    // 32-lane slices per row
+
+__global__ void __launch_bounds__(256) k_glo_fwd_fused(const float* __restrict__ x, const float* __restrict__ mask,
+                                                       const float* __restrict__ Wi, const float* __restrict__ bi,
+                                                       const float* __restrict__ Wj, const float* __restrict__ bj,
+                                                       int B, int N, int F2, int O, float* __restrict__ out,
+                                                       float* __restrict__ u, float* __restrict__ v) {
+  __shared__ float WiT[FO * FO];   // WiT[l][o]
+  __shared__ float WjT[FO * FO];
+  __shared__ float red[8][FO];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    constexpr int NW = FO * FO / 256;
+    const int nw = O * F2;
+    float a[NW], b[NW];
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = min(tid + t * 256, nw - 1);
+      a[t] = __ldg(Wi + i);
+      b[t] = __ldg(Wj + i);
+    }
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = tid + t * 256;
+      if (i < nw) {
+        const int o = i / F2, l = i - o * F2;
+        WiT[l * FO + o] = a[t];
+        WjT[l * FO + o] = b[t];
+      }
+    }
+  }
+  float bio[FK], bjo[FK];
+#pragma unroll
+  for (int k = 0; k < FK; ++k) {
+    const int o = min(lane + 32 * k, O - 1);
+    bio[k] = bi[o];
+    bjo[k] = bj[o];
+  }
+  __syncthreads();
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float acc[FK] = {0.f, 0.f};
+    for (int i = warp; i < N; i += 8) {
+      const size_t row = (size_t)b * N + i;
+      const float mu = __ldg(mask + row);
+      float xl[FK];
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        const int l = lane + 32 * k;
+        xl[k] = __ldg(x + row * F2 + min(l, F2 - 1)) * mu;
+        if (l >= F2) xl[k] = 0.f;
+      }
+      float ua[FK] = {0.f, 0.f}, va[FK] = {0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < FK; ++kk) {
+        const int lend = min(32, F2 - 32 * kk);
+        for (int ll = 0; ll < lend; ++ll) {
+          const int l = ll + 32 * kk;
+          const float xv = __shfl_sync(0xffffffffu, xl[kk], ll);
+#pragma unroll
+          for (int k = 0; k < FK; ++k) {
+            ua[k] = fmaf(xv, WiT[l * FO + lane + 32 * k], ua[k]);
+            va[k] = fmaf(xv, WjT[l * FO + lane + 32 * k], va[k]);
+          }
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        ua[k] += bio[k];
+        va[k] += bjo[k];
+        if (lane + 32 * k < O) mx = fmaxf(mx, ua[k]);
+      }
+      mx = warp_max(mx);
+      float ex[FK], den = 0.f;
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        ex[k] = lane + 32 * k < O ? expf(ua[k] - mx) : 0.f;
+        den += ex[k];
+      }
+      den = warp_sum(den);
+      const float inv = 1.f / den;
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        const int o = lane + 32 * k;
+        if (o < O) {
+          u[row * O + o] = ua[k];
+          v[row * O + o] = va[k];
+          acc[k] += ex[k] * inv * va[k] * mu;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < FK; ++k) red[warp][lane + 32 * k] = acc[k];
+    __syncthreads();
+    if (tid < O) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][tid];
+      out[(size_t)b * O + tid] = s;
+    }
+  }
+}
+
+// partial layout per CTA: [dWi O*F2 | dWj O*F2 | dbi O | dbj O]
+__global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__ x, const float* __restrict__ mask,
+                                                       const float* __restrict__ Wi, const float* __restrict__ Wj,
+                                                       const float* __restrict__ u, const float* __restrict__ v,
+                                                       const float* __restrict__ dout, int B, int N, int F2, int O,
+                                                       float* __restrict__ dx, float* __restrict__ partial) {
+  constexpr int LD = FO + 1;
+  __shared__ float Wis[FO * LD];      // Wis[o][l]
+  __shared__ float Wjs[FO * LD];
+  __shared__ float du_s[8][FO], dv_s[8][FO], dub_s[8][FO], dvb_s[8][FO], x_s[8][FO];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nw = O * F2;
+  {
+    constexpr int NW = FO * FO / 256;
+    float a[NW], b[NW];
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = min(tid + t * 256, nw - 1);
+      a[t] = __ldg(Wi + i);
+      b[t] = __ldg(Wj + i);
+    }
+#pragma unroll
+    for (int t = 0; t < NW; ++t) {
+      const int i = tid + t * 256;
+      if (i < nw) {
+        const int o = i / F2, l = i - o * F2;
+        Wis[o * LD + l] = a[t];
+        Wjs[o * LD + l] = b[t];
+      }
+    }
+  }
+  constexpr int NACC = 2 * FO * FO / 256;   // 32
+  float acc[NACC];
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+  float accb = 0.f;
+  const long long rows = (long long)B * N;
+  const long long ntiles = (rows + 7) / 8;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * 8 + warp;
+    const bool live = row < rows;
+    const long long rr = live ? row : rows - 1;
+    const long long b = rr / N;
+    __syncthreads();   // weights staged / previous tile's accumulation finished
+    {
+      const float mu = __ldg(mask + rr);
+      float s[FK], vv[FK], dr[FK];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        const int o = min(lane + 32 * k, O - 1);
+        s[k] = __ldg(u + rr * O + o);
+        vv[k] = __ldg(v + rr * O + o);
+        dr[k] = __ldg(dout + b * O + o);
+        if (lane + 32 * k < O) mx = fmaxf(mx, s[k]);
+      }
+      mx = warp_max(mx);
+      float den = 0.f;
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        s[k] = lane + 32 * k < O ? expf(s[k] - mx) : 0.f;
+        den += s[k];
+      }
+      den = warp_sum(den);
+      const float inv = 1.f / den;
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        s[k] *= inv;
+        dot += dr[k] * mu * vv[k] * s[k];
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int k = 0; k < FK; ++k) {
+        const int o = lane + 32 * k;
+        const float dg = dr[k] * mu;
+        float dvp = dg * s[k];
+        float dup = s[k] * (dg * vv[k] - dot);
+        if (!live || o >= O) dvp = dup = 0.f;
+        dub_s[warp][o] = dup;           // d u' (bias gradient)
+        dvb_s[warp][o] = dvp;
+        du_s[warp][o] = dup * mu;       // d u_raw (u' = mu * u_raw + b)
+        dv_s[warp][o] = dvp * mu;
+        const int l = lane + 32 * k;
+        float xv = __ldg(x + rr * F2 + min(l, F2 - 1));
+        if (!live || l >= F2) xv = 0.f;
+        x_s[warp][l] = xv;
+      }
+    }
+    __syncwarp();
+    if (live) {
+      // dx[row, l] = sum_o du_raw[o] Wi[o][l] + dv_raw[o] Wj[o][l]
+      float dxa[FK] = {0.f, 0.f};
+      for (int o = 0; o < O; ++o) {
+        const float a0 = du_s[warp][o], b0 = dv_s[warp][o];
+#pragma unroll
+        for (int k = 0; k < FK; ++k) {
+          dxa[k] = fmaf(a0, Wis[o * LD + lane + 32 * k], dxa[k]);
+          dxa[k] = fmaf(b0, Wjs[o * LD + lane + 32 * k], dxa[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < FK; ++k)
+        if (lane + 32 * k < F2) dx[row * F2 + lane + 32 * k] = dxa[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) {
+      const int e = tid + q * 256;
+      if (e < 2 * nw) {
+        const int which = e >= nw;
+        const int ee = e - which * nw;
+        const int o = ee / F2, l = ee - o * F2;
+        const float(*gs)[FO] = which ? dv_s : du_s;
+        float a = acc[q];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a = fmaf(gs[r][o], x_s[r][l], a);
+        acc[q] = a;
+      }
+    }
+    if (tid < 2 * O) {
+      const int which = tid >= O;
+      const int o = tid - which * O;
+      const float(*gs)[FO] = which ? dvb_s : dub_s;
+      float a = accb;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a += gs[r][o];
+      accb = a;
+    }
+  }
+  float* part = partial + (size_t)blockIdx.x * (2 * nw + 2 * O);
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    const int e = tid + q * 256;
+    if (e < 2 * nw) part[e] = acc[q];
+  }
+  if (tid < 2 * O) part[2 * nw + tid] = accb;
+}
+
+__global__ void __launch_bounds__(256) k_glo_bwd_reduce(const float* __restrict__ partial, int nparts, int F2, int O,
+                                                        float* __restrict__ dWi, float* __restrict__ dWj,
+                                                        float* __restrict__ dbi, float* __restrict__ dbj) {
+  __shared__ float sm[8][33];
+  const int nw = O * F2;
+  const int total = 2 * nw + 2 * O;
+  const int el = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + el;
+  float s = 0.f;
+  if (e < total) {
+#pragma unroll 4
+    for (int p = sl; p < nparts; p += 8) s += partial[(size_t)p * total + e];
+  }
+  sm[sl][el] = s;
+  __syncthreads();
+  if (sl != 0 || e >= total) return;
+  s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += sm[j][el];
+  if (e < nw)
+    dWi[e] = s;
+  else if (e < 2 * nw)
+    dWj[e - nw] = s;
+  else if (e < 2 * nw + O)
+    dbi[e - 2 * nw] = s;
+  else
+    dbj[e - 2 * nw - O] = s;
+}
+
+int glo_bwd_grid(long long rows) {
+  long long tiles = (rows + 7) / 8;
+  int cap = mpnn_num_sms();
+  return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,7 +548,9 @@ size_t mpnn_glo_workspace_bytes(int B, int N, int F2, int O) {
   long long rows = (long long)B * N;
   size_t g = mpnn_gemm_workspace_bytes(O, F2, (int)rows);
   size_t c = mpnn_colsum_workspace_bytes(rows, O);
-  return 2 * align_up((size_t)rows * O * sizeof(float), 256) + align_up(g > c ? g : c, 256);
+  size_t fusedb = (size_t)mpnn_num_sms() * (2 * (size_t)O * F2 + 2 * O) * sizeof(float);
+  size_t need = 2 * align_up((size_t)rows * O * sizeof(float), 256) + align_up(g > c ? g : c, 256);
+  return need > fusedb ? need : fusedb;
 }
 
 // u, v: [B*N, O] saved for backward; UV: [B, 2, O] (unmasked form only)
@@ -273,6 +560,12 @@ int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float
   MPNN_REQUIRE(O <= 32 * KMAX, MPNN_ERR_UNSUPPORTED, "glo_fwd: output_dim %d > %d", O, 32 * KMAX);
   int rows = B * N;
   int rc;
+  if (mask && O <= FO && F2 <= FO) {
+    int grid = B < 4 * mpnn_num_sms() ? B : 4 * mpnn_num_sms();
+    k_glo_fwd_fused<<<grid, 256, 0, stream>>>(x, mask, Wi, bi, Wj, bj, B, N, F2, O, out, u, v);
+    MPNN_CHECK_LAUNCH("k_glo_fwd_fused");
+    return MPNN_OK;
+  }
   if ((rc = mpnn_gemm(x, Wi, u, rows, O, F2, F2, 1, 1, F2, O, nullptr, 0, nullptr, 0, stream))) return rc;
   if ((rc = mpnn_gemm(x, Wj, v, rows, O, F2, F2, 1, 1, F2, O, nullptr, 0, nullptr, 0, stream))) return rc;
   if (mask) {
@@ -291,6 +584,15 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
   MPNN_REQUIRE(B > 0 && N > 0 && F2 > 0 && O > 0 && O <= 32 * KMAX, MPNN_ERR_ARG, "glo_bwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_glo_workspace_bytes(B, N, F2, O), MPNN_ERR_WORKSPACE, "glo_bwd: workspace");
   long long rows = (long long)B * N;
+  if (mask && O <= FO && F2 <= FO) {
+    const int grid = glo_bwd_grid(rows);
+    float* partial = (float*)workspace;
+    k_glo_bwd_fused<<<grid, 256, 0, stream>>>(x, mask, Wi, Wj, u, v, dout, B, N, F2, O, dx, partial);
+    MPNN_CHECK_LAUNCH("k_glo_bwd_fused");
+    k_glo_bwd_reduce<<<ceil_div(2 * O * F2 + 2 * O, 32), 256, 0, stream>>>(partial, grid, F2, O, dWi, dWj, dbi, dbj);
+    MPNN_CHECK_LAUNCH("k_glo_bwd_reduce");
+    return MPNN_OK;
+  }
   char* wp = (char*)workspace;
   float* du = (float*)wp;
   wp += align_up((size_t)rows * O * sizeof(float), 256);

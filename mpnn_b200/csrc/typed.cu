@@ -64,25 +64,50 @@ __global__ void __launch_bounds__(256) k_tmsg_fwd(TMsg a, float* __restrict__ M)
   for (int i = blockIdx.x * groups_per_block + threadIdx.x / DP; i < a.n_rows; i += gridDim.x * groups_per_block) {
     const int eb = a.row_ptr[i], ee = a.row_ptr[i + 1];
     float acc = 0.f, hs = 0.f;
-    for (int e = eb; e < ee; ++e) {
-      const int j = __ldg(a.edge_src + e);
-      const int u = __ldg(a.uid + e);
-      const float al = a.alpha ? __ldg(a.alpha + e) : 1.f;
-      const float hj = k < a.nf ? __ldg(a.H + (size_t)j * a.nf + k) : 0.f;
-      hs += hj;
-      const float* T = a.table + (size_t)u * DP * DP + k;
-      float s = 0.f;
-#pragma unroll 8
-      for (int l = 0; l < a.nf; ++l) s = fmaf(__ldg(T + l * DP), __shfl_sync(gm, hj, l, DP), s);
-      acc = fmaf(al, s, acc);
+    for (int e0 = eb; e0 < ee; e0 += DP) {
+      // lane t of the group fetches the metadata of edge e0 + t (coalesced), then the group walks the edges
+      const int cnt = min(DP, ee - e0);
+      int jm = 0, um = 0;
+      float am = 1.f;
+      if (k < cnt) {
+        jm = __ldg(a.edge_src + e0 + k);
+        um = __ldg(a.uid + e0 + k);
+        if (a.alpha) am = __ldg(a.alpha + e0 + k);
+      }
+      int j = __shfl_sync(gm, jm, 0, DP);
+      float hj = k < a.nf ? __ldg(a.H + (size_t)j * a.nf + k) : 0.f;
+      for (int t = 0; t < cnt; ++t) {
+        const int u = __shfl_sync(gm, um, t, DP);
+        const float al = __shfl_sync(gm, am, t, DP);
+        const float hcur = hj;
+        if (t + 1 < cnt) {  // prefetch the next sender state while this edge is contracted
+          j = __shfl_sync(gm, jm, t + 1, DP);
+          hj = k < a.nf ? __ldg(a.H + (size_t)j * a.nf + k) : 0.f;
+        }
+        hs += hcur;
+        const float* T = a.table + (size_t)u * DP * DP + k;
+        float tv[DP];
+#pragma unroll
+        for (int l = 0; l < DP; ++l) tv[l] = __ldg(T + l * DP);   // DP independent loads (padding rows are zero)
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int l = 0; l < DP; l += 2) {
+          s0 = fmaf(tv[l], __shfl_sync(gm, hcur, l, DP), s0);
+          s1 = fmaf(tv[l + 1], __shfl_sync(gm, hcur, l + 1, DP), s1);
+        }
+        acc = fmaf(al, s0 + s1, acc);
+      }
     }
     if (a.S) {  // all non-bonded pairs of the row share the zero bond row (HEAD form, edge_network.py:50)
       const int b = i / a.N;
       const float q = (k < a.nf ? __ldg(a.S + (size_t)b * a.nf + k) : 0.f) - hs;
       const float* T = a.table + (size_t)a.zero_type * DP * DP + k;
+      float tv[DP];
+#pragma unroll
+      for (int l = 0; l < DP; ++l) tv[l] = __ldg(T + l * DP);
       float s = 0.f;
-#pragma unroll 8
-      for (int l = 0; l < a.nf; ++l) s = fmaf(__ldg(T + l * DP), __shfl_sync(gm, q, l, DP), s);
+#pragma unroll
+      for (int l = 0; l < DP; ++l) s = fmaf(tv[l], __shfl_sync(gm, q, l, DP), s);
       acc += s;
     }
     if (k < a.mf) M[(size_t)i * a.mf + k] = acc + (a.beta ? a.beta[k] : 0.f);
@@ -107,30 +132,49 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_src(TMsg a, const int* __restr
   for (int j = blockIdx.x * groups_per_block + threadIdx.x / DP; j < a.n_rows; j += gridDim.x * groups_per_block) {
     const int cb = col_ptr[j], ce = col_ptr[j + 1];
     float acc = 0.f;
-    for (int c = cb; c < ce; ++c) {
-      const int e = __ldg(csc_eid + c);
-      const int i = __ldg(a.edge_dst + e);
-      const int u = __ldg(a.uid + e);
-      const float al = a.alpha ? __ldg(a.alpha + e) : 1.f;
-      const float dm = l < a.mf ? __ldg(dM + (size_t)i * a.mf + l) : 0.f;
-      const float* T = a.tableT + (size_t)u * DP * DP + l;
-      float s = 0.f;
-      if (head) {
-#pragma unroll 8
-        for (int k = 0; k < a.mf; ++k)
-          s = fmaf(__ldg(T + k * DP) - __ldg(T0 + k * DP), __shfl_sync(gm, dm, k, DP), s);
-      } else {
-#pragma unroll 8
-        for (int k = 0; k < a.mf; ++k) s = fmaf(__ldg(T + k * DP), __shfl_sync(gm, dm, k, DP), s);
+    for (int c0 = cb; c0 < ce; c0 += DP) {
+      const int cnt = min(DP, ce - c0);
+      int im = 0, um = 0;
+      float am = 1.f;
+      if (l < cnt) {
+        const int e = __ldg(csc_eid + c0 + l);
+        im = __ldg(a.edge_dst + e);
+        um = __ldg(a.uid + e);
+        if (a.alpha) am = __ldg(a.alpha + e);
       }
-      acc = fmaf(al, s, acc);
+      int i = __shfl_sync(gm, im, 0, DP);
+      float dmn = l < a.mf ? __ldg(dM + (size_t)i * a.mf + l) : 0.f;
+      for (int t = 0; t < cnt; ++t) {
+        const int u = __shfl_sync(gm, um, t, DP);
+        const float al = __shfl_sync(gm, am, t, DP);
+        const float dm = dmn;
+        if (t + 1 < cnt) {
+          i = __shfl_sync(gm, im, t + 1, DP);
+          dmn = l < a.mf ? __ldg(dM + (size_t)i * a.mf + l) : 0.f;
+        }
+        const float* T = a.tableT + (size_t)u * DP * DP + l;
+        float tv[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) tv[k] = __ldg(T + k * DP);
+        if (head) {
+#pragma unroll
+          for (int k = 0; k < DP; ++k) tv[k] -= __ldg(T0 + k * DP);
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < DP; k += 2) {
+          s0 = fmaf(tv[k], __shfl_sync(gm, dm, k, DP), s0);
+          s1 = fmaf(tv[k + 1], __shfl_sync(gm, dm, k + 1, DP), s1);
+        }
+        acc = fmaf(al, s0 + s1, acc);
+      }
     }
     if (head) {
       const int b = j / a.N;
       const float ds = l < a.mf ? __ldg(Dsum + (size_t)b * a.mf + l) : 0.f;
       float s = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < a.mf; ++k) s = fmaf(__ldg(T0 + k * DP), __shfl_sync(gm, ds, k, DP), s);
+#pragma unroll
+      for (int k = 0; k < DP; ++k) s = fmaf(__ldg(T0 + k * DP), __shfl_sync(gm, ds, k, DP), s);
       acc += s;
     }
     if (l < a.nf) dH[(size_t)j * a.nf + l] = acc;
@@ -303,9 +347,20 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ ac
   const int tid = threadIdx.x;
   const int o = tid >> 2, q = tid & 3;
   const int P = n.P;
-  for (int idx = tid; idx < PW * PW; idx += 256) {
-    int oo = idx / PW, ii = idx - oo * PW;
-    Wn[oo * WS_ + ii] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
+  {
+    float wv[PW * PW / 256];
+#pragma unroll
+    for (int t = 0; t < PW * PW / 256; ++t) {  // all loads in flight at once (clamped address, masked value)
+      const int idx = tid + t * 256;
+      const int oo = idx / PW, ii = idx - oo * PW;
+      wv[t] = __ldg(n.w_tied + min(oo, P - 1) * P + min(ii, P - 1));
+    }
+#pragma unroll
+    for (int t = 0; t < PW * PW / 256; ++t) {
+      const int idx = tid + t * 256;
+      const int oo = idx / PW, ii = idx - oo * PW;
+      Wn[oo * WS_ + ii] = (oo < P && ii < P) ? wv[t] : 0.f;
+    }
   }
   for (int row = blockIdx.x; row < n.R; row += gridDim.x) {
     __syncthreads();  // Wn loaded / previous row done with A
@@ -355,16 +410,30 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ ac
     const int nout = n.mf * n.nf;
     const float x0 = lane < P ? A[cur][lane] : 0.f;
     const float x1 = lane + 32 < P ? A[cur][lane + 32] : 0.f;
-    for (int f = warp; f < nout; f += 8) {
-      const float* w = n.w_last + (size_t)f * P;
-      float acc = lane < P ? __ldg(w + lane) * x0 : 0.f;
-      if (lane + 32 < P) acc = fmaf(__ldg(w + lane + 32), x1, acc);
-      acc = warp_sum(acc);
+    constexpr int FB = 8;  // outputs per batch: 2*FB independent loads in flight per lane
+    for (int fb = warp * FB; fb < nout; fb += 8 * FB) {
+      float acc[FB], w0[FB], w1[FB];
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {  // unconditional (clamped) loads: 2*FB requests in flight; x0/x1 are 0 off-range
+        const float* w = n.w_last + (size_t)min(fb + j, nout - 1) * P;
+        w0[j] = __ldg(w + min(lane, P - 1));
+        w1[j] = __ldg(w + min(lane + 32, P - 1));
+      }
+#pragma unroll
+      for (int j = 0; j < FB; ++j) acc[j] = fmaf(w1[j], x1, w0[j] * x0);
+#pragma unroll
+      for (int j = 0; j < FB; ++j) acc[j] = warp_sum(acc[j]);
       if (lane == 0) {
-        acc += n.b_last[f];
-        const int k = f / n.nf, l = f - k * n.nf;
-        table[((size_t)row * DP + l) * DP + k] = acc;
-        tableT[((size_t)row * DP + k) * DP + l] = acc;
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+          const int f = fb + j;
+          if (f < nout) {
+            const float v = acc[j] + n.b_last[f];
+            const int k = f / n.nf, l = f - k * n.nf;
+            table[((size_t)row * DP + l) * DP + k] = v;
+            tableT[((size_t)row * DP + k) * DP + l] = v;
+          }
+        }
       }
     }
     // zero the padding of the table (feature widths that are not a power of two)
@@ -396,9 +465,20 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
   const int i_ = tid >> 2, q = tid & 3;          // (output index, split lane) of the dA dot products
   const int og = tid >> 4, ig = tid & 15;        // dW micro-tile
   const int P = n.P, DP = n.DP;
-  for (int idx = tid; idx < PW * PW; idx += 256) {
-    int oo = idx / PW, ii = idx - oo * PW;
-    Wt[ii * WS_ + oo] = (oo < P && ii < P) ? n.w_tied[oo * P + ii] : 0.f;
+  {
+    float wv[PW * PW / 256];
+#pragma unroll
+    for (int t = 0; t < PW * PW / 256; ++t) {
+      const int idx = tid + t * 256;
+      const int oo = idx / PW, ii = idx - oo * PW;
+      wv[t] = __ldg(n.w_tied + min(oo, P - 1) * P + min(ii, P - 1));
+    }
+#pragma unroll
+    for (int t = 0; t < PW * PW / 256; ++t) {
+      const int idx = tid + t * 256;
+      const int oo = idx / PW, ii = idx - oo * PW;
+      Wt[ii * WS_ + oo] = (oo < P && ii < P) ? wv[t] : 0.f;
+    }
   }
   float accW[4][4];
 #pragma unroll
@@ -418,6 +498,7 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
       if (p < P) {
         const float* dt = dT + (size_t)row * DP * DP;
         const int nout = n.mf * n.nf;
+#pragma unroll 8
         for (int f = part_f; f < nout; f += 4) {
           const int k = f / n.nf, l = f - k * n.nf;
           acc = fmaf(__ldg(dt + l * DP + k), __ldg(n.w_last + (size_t)f * P + p), acc);
@@ -508,6 +589,7 @@ __global__ void k_enet_reduce(const float* __restrict__ partial, int nparts, int
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count) return;
   float s = 0.f;
+#pragma unroll 8
   for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * partial_stride + idx];
   out[idx] = s;
 }
@@ -529,6 +611,7 @@ __global__ void k_enet_last_bwd(const float* __restrict__ acts_x /*[R][PW]*/, co
   int p = idx % (P + 1), f = idx / (P + 1);
   int l = f % nf, k = f / nf;
   float s = 0.f;
+#pragma unroll 8
   for (int u = 0; u < R; ++u) {
     float d = dT[((size_t)u * DP + l) * DP + k];
     s = fmaf(d, p < P ? acts_x[(size_t)u * PW + p] : 1.f, s);
