@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int MAXQ = 5;
+constexpr int MAXQ = 7;
 
 enum Mode { STATS1 = 0, STATS2 = 1, BWD_PLAIN = 2, BWD_1D_TRAIN = 3, BWD_1D_EVAL = 4 };
 enum Fin { FIN_NONE = 0, FIN_MEAN_PLAIN = 1, FIN_MEAN_1D = 2, FIN_SD_PLAIN = 3, FIN_SD_1D = 4 };
@@ -163,6 +163,159 @@ __global__ void k_bn_stage(RedArgs a, float* __restrict__ partial) {
   if (threadIdx.x == 0) *a.counter = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Forward statistics in ONE launch.  The reference's two passes (mean, then the variance of the centred
+// values) become: every block centres its rows on its OWN mean (second look at rows that are still in L1),
+// and the last block to finish combines the per-block moments exactly:
+//   sum_r mu_r^2 (x_r - m)^2 = sum_b [ A_b + 2 (s_b - m) B_b + (s_b - m)^2 C_b ],
+//   A_b = sum mu^2 (x - s_b)^2, B_b = sum mu^2 (x - s_b), C_b = sum mu^2, s_b = the block's shift.
+// Valid for any mask values; no cancellation (the shift is within the data).  Fixed combination order.
+// partial[block][7][C] = {sum x, sum x mu, sum mu, shift, A, B, C}
+// ---------------------------------------------------------------------------------------------------
+struct StatArgs {
+  const float* x;
+  const float* mask;
+  long long rows;
+  int C;
+  int rows_per_block;
+  int one_d;            // 0: MaskBatchNorm (mean = unmasked sum / M, sd = sqrt(var + eps)); 1: MaskBatchNorm1d
+  float eps, momentum;
+  float* stats;         // [2C+1] mean | sd | M
+  float* running_mean;
+  float* running_var;
+  unsigned int* counter;
+};
+
+__global__ void k_bn_stats(StatArgs a, float* __restrict__ partial) {
+  extern __shared__ float sm[];      // [blockDim] reduction scratch, then [C] shifts
+  __shared__ int is_last;
+  const int C = a.C;
+  const int lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, rl = threadIdx.x / C;
+  float* shift = sm + blockDim.x;
+  long long r0 = (long long)blockIdx.x * a.rows_per_block;
+  long long r1 = r0 + a.rows_per_block;
+  if (r1 > a.rows) r1 = a.rows;
+  float q[3] = {0.f, 0.f, 0.f};
+  if (rl < lanes) {
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const float xv = a.x[r * C + c];
+      const float mu = a.mask[r];
+      q[0] += xv;
+      q[1] += xv * mu;
+      q[2] += mu;
+    }
+  }
+  float* prt = partial + (size_t)blockIdx.x * 7 * C;
+  for (int k = 0; k < 3; ++k) {
+    __syncthreads();
+    sm[threadIdx.x] = q[k];
+    __syncthreads();
+    if (rl == 0) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += sm[l * C + c];
+      q[k] = s;
+      prt[k * C + c] = s;
+    }
+  }
+  if (rl == 0) {
+    const float sh = q[2] > 0.f ? q[1] / q[2] : 0.f;
+    shift[c] = sh;
+    prt[3 * C + c] = sh;
+  }
+  __syncthreads();
+  float w[3] = {0.f, 0.f, 0.f};
+  if (rl < lanes) {
+    const float sh = shift[c];
+#pragma unroll 4
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const float xv = a.x[r * C + c];
+      const float mu = a.mask[r];
+      const float m2 = mu * mu, dv = xv - sh;
+      w[0] = fmaf(m2 * dv, dv, w[0]);
+      w[1] = fmaf(m2, dv, w[1]);
+      w[2] += m2;
+    }
+  }
+  for (int k = 0; k < 3; ++k) {
+    __syncthreads();
+    sm[threadIdx.x] = w[k];
+    __syncthreads();
+    if (rl == 0) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += sm[l * C + c];
+      prt[(4 + k) * C + c] = s;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last block: column c, slice rl takes blocks rl, rl + lanes, ...; slices are combined in a fixed order ----
+  const int nblk = gridDim.x;
+  float* s3 = sm + blockDim.x + C;   // [3][blockDim]
+  float S0 = 0.f, S1 = 0.f, M = 0.f;
+  if (rl < lanes) {
+#pragma unroll 4
+    for (int b = rl; b < nblk; b += lanes) {
+      const float* pb = partial + (size_t)b * 7 * C + c;
+      S0 += __ldcg(pb);
+      S1 += __ldcg(pb + C);
+      M += __ldcg(pb + 2 * C);
+    }
+  }
+  __syncthreads();
+  s3[threadIdx.x] = S0;
+  s3[blockDim.x + threadIdx.x] = S1;
+  s3[2 * blockDim.x + threadIdx.x] = M;
+  __syncthreads();
+  if (rl == 0) {
+    S0 = S1 = M = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      S0 += s3[l * C + c];
+      S1 += s3[blockDim.x + l * C + c];
+      M += s3[2 * blockDim.x + l * C + c];
+    }
+    shift[c] = (a.one_d ? S1 : S0) / M;   // the mean
+    if (c == 0) a.stats[2 * C] = M;
+    sm[c] = M;
+  }
+  __syncthreads();
+  const float mean = shift[c];
+  float V = 0.f;
+  if (rl < lanes) {
+#pragma unroll 4
+    for (int b = rl; b < nblk; b += lanes) {
+      const float* pb = partial + (size_t)b * 7 * C + c;
+      const float dlt = __ldcg(pb + 3 * C) - mean;
+      V += __ldcg(pb + 4 * C) + 2.f * dlt * __ldcg(pb + 5 * C) + dlt * dlt * __ldcg(pb + 6 * C);
+    }
+  }
+  const float Mtot = sm[c];
+  __syncthreads();
+  s3[threadIdx.x] = V;
+  __syncthreads();
+  if (rl == 0) {
+    V = 0.f;
+    for (int l = 0; l < lanes; ++l) V += s3[l * C + c];
+    const float var = fmaxf(V, 0.f) / Mtot;
+    a.stats[c] = mean;
+    if (!a.one_d) {
+      a.stats[C + c] = sqrtf(var + a.eps);
+    } else {
+      a.stats[C + c] = sqrtf(var);
+      if (a.running_mean) {
+        a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+        a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * var;
+      }
+    }
+  }
+  if (threadIdx.x == 0) *a.counter = 0u;
+}
+
 // stats layout written by the forward and consumed by the backward: [mean | scale | M (1 float, at 2C)]
 __global__ void k_plain_apply(const float* __restrict__ x, const float* __restrict__ mask,
                               const float* __restrict__ stats, long long rows, int C, float* __restrict__ y) {
@@ -269,6 +422,16 @@ int run_stage(RedArgs a, float* partial, cudaStream_t stream) {
   return MPNN_OK;
 }
 
+int run_stats(StatArgs a, float* partial, cudaStream_t stream) {
+  int rpb;
+  int nblk = red_blocks(a.rows, &rpb);
+  a.rows_per_block = rpb;
+  int threads = a.C >= 256 ? a.C : (256 / a.C) * a.C;
+  k_bn_stats<<<nblk, threads, (4 * threads + a.C) * sizeof(float), stream>>>(a, partial);
+  MPNN_CHECK_LAUNCH("k_bn_stats");
+  return MPNN_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -301,13 +464,9 @@ int mpnn_mask_bn_fwd(const float* x, const float* mask, long long rows, int C, f
   unsigned int* counter;
   carve(workspace, rows, C, &partial, &red, &counter);
   MPNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
-  RedArgs a = {x, mask, nullptr, nullptr, nullptr, nullptr, rows, C, 0, STATS1, 3,
-               FIN_MEAN_PLAIN, eps, 0.f, red, stats, nullptr, nullptr, counter};
-  int rc = run_stage(a, partial, stream);
+  StatArgs a = {x, mask, rows, C, 0, 0, eps, 0.f, stats, nullptr, nullptr, counter};
+  int rc = run_stats(a, partial, stream);
   if (rc) return rc;
-  RedArgs b = {x, mask, nullptr, stats, nullptr, nullptr, rows, C, 0, STATS2, 1,
-               FIN_SD_PLAIN, eps, 0.f, red, stats, nullptr, nullptr, counter};
-  if ((rc = run_stage(b, partial, stream))) return rc;
   k_plain_apply<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, stats, rows, C, y);
   MPNN_CHECK_LAUNCH("mask_bn_fwd");
   return MPNN_OK;
@@ -348,13 +507,9 @@ int mpnn_mask_bn1d_fwd(const float* x, const float* mask, const float* weight, c
   unsigned int* counter;
   carve(workspace, rows, C, &partial, &red, &counter);
   MPNN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
-  RedArgs a = {x, mask, nullptr, nullptr, nullptr, nullptr, rows, C, 0, STATS1, 3,
-               FIN_MEAN_1D, eps, momentum, red, stats, nullptr, nullptr, counter};
-  int rc = run_stage(a, partial, stream);
+  StatArgs a = {x, mask, rows, C, 0, 1, eps, momentum, stats, running_mean, running_var, counter};
+  int rc = run_stats(a, partial, stream);
   if (rc) return rc;
-  RedArgs b = {x, mask, nullptr, stats, nullptr, nullptr, rows, C, 0, STATS2, 1,
-               FIN_SD_1D, eps, momentum, red, stats, running_mean, running_var, counter};
-  if ((rc = run_stage(b, partial, stream))) return rc;
   k_1d_apply<<<ceil_div(rows * C, 256), 256, 0, stream>>>(x, mask, stats, stats + C, 0, weight, bias, eps, rows, C, y);
   MPNN_CHECK_LAUNCH("mask_bn1d_fwd");
   return MPNN_OK;

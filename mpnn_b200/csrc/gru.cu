@@ -203,8 +203,19 @@ __global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__
   const bool on = c < d;
   const int nW = d * d3;
   float acc[NACC];
+  int pk[NACC];      // per element: offset into [Ms|Hs] (low 16 bits) and into [Gi|Gh] (high bits); -1 = none
 #pragma unroll
-  for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+  for (int q = 0; q < NACC; ++q) {
+    acc[q] = 0.f;
+    const int e = threadIdx.x + q * 256;
+    pk[q] = -1;
+    if (e < 2 * nW) {
+      const int which = e >= nW;
+      const int ee = e - which * nW;
+      const int l = ee / d3, g = ee - l * d3;
+      pk[q] = (which * TR * d + l) | ((which * TR * d3 + g) << 16);
+    }
+  }
   float accb = 0.f;  // threads [0, 6d): bias gradients
   const long long ntiles = (rows + TR - 1) / TR;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -261,16 +272,12 @@ __global__ void __launch_bounds__(256) k_gru_bwd_fused(const float* __restrict__
     // weight gradients: element q -> (which, l, g); rows of the tile that are out of range staged zeros
 #pragma unroll
     for (int q = 0; q < NACC; ++q) {
-      const int e = threadIdx.x + q * 256;
-      if (e < 2 * nW) {
-        const int which = e >= nW;
-        const int ee = e - which * nW;
-        const int l = ee / d3, g = ee - l * d3;
-        const float* xs = which ? Hs : Ms;
-        const float* gs = which ? Gh : Gi;
+      if (pk[q] >= 0) {
+        const float* xs = Ms + (pk[q] & 0xffff);
+        const float* gs = Gi + (pk[q] >> 16);
         float a = acc[q];
-#pragma unroll 4
-        for (int r = 0; r < TR; ++r) a = fmaf(xs[r * d + l], gs[r * d3 + g], a);
+#pragma unroll 8
+        for (int r = 0; r < TR; ++r) a = fmaf(xs[r * d], gs[r * d3], a);
         acc[q] = a;
       }
     }

@@ -397,11 +397,16 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
       }
     }
   }
-  constexpr int NACC = 2 * FO * FO / 256;   // 32
-  float acc[NACC];
+  // weight-gradient elements of this thread: (which, o = warp + 8 j, l = lane + 32 kf) -- no index divisions
+  float acc[2][FK][8];
 #pragma unroll
-  for (int q = 0; q < NACC; ++q) acc[q] = 0.f;
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int k = 0; k < FK; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[a][k][j] = 0.f;
   float accb = 0.f;
+  const int nkf = (F2 + 31) / 32;
   const long long rows = (long long)B * N;
   const long long ntiles = (rows + 7) / 8;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -459,12 +464,15 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
     if (live) {
       // dx[row, l] = sum_o du_raw[o] Wi[o][l] + dv_raw[o] Wj[o][l]
       float dxa[FK] = {0.f, 0.f};
+#pragma unroll 4
       for (int o = 0; o < O; ++o) {
         const float a0 = du_s[warp][o], b0 = dv_s[warp][o];
 #pragma unroll
         for (int k = 0; k < FK; ++k) {
-          dxa[k] = fmaf(a0, Wis[o * LD + lane + 32 * k], dxa[k]);
-          dxa[k] = fmaf(b0, Wjs[o * LD + lane + 32 * k], dxa[k]);
+          if (k < nkf) {
+            dxa[k] = fmaf(a0, Wis[o * LD + lane + 32 * k], dxa[k]);
+            dxa[k] = fmaf(b0, Wjs[o * LD + lane + 32 * k], dxa[k]);
+          }
         }
       }
 #pragma unroll
@@ -473,17 +481,18 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < NACC; ++q) {
-      const int e = tid + q * 256;
-      if (e < 2 * nw) {
-        const int which = e >= nw;
-        const int ee = e - which * nw;
-        const int o = ee / F2, l = ee - o * F2;
-        const float(*gs)[FO] = which ? dv_s : du_s;
-        float a = acc[q];
+    for (int r = 0; r < 8; ++r) {
+      float xv[FK];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) a = fmaf(gs[r][o], x_s[r][l], a);
-        acc[q] = a;
+      for (int k = 0; k < FK; ++k) xv[k] = x_s[r][lane + 32 * k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gu = du_s[r][warp + 8 * j], gv = dv_s[r][warp + 8 * j];
+#pragma unroll
+        for (int k = 0; k < FK; ++k) {
+          acc[0][k][j] = fmaf(gu, xv[k], acc[0][k][j]);
+          acc[1][k][j] = fmaf(gv, xv[k], acc[1][k][j]);
+        }
       }
     }
     if (tid < 2 * O) {
@@ -498,10 +507,14 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
   }
   float* part = partial + (size_t)blockIdx.x * (2 * nw + 2 * O);
 #pragma unroll
-  for (int q = 0; q < NACC; ++q) {
-    const int e = tid + q * 256;
-    if (e < 2 * nw) part[e] = acc[q];
-  }
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int k = 0; k < FK; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int o = warp + 8 * j, l = lane + 32 * k;
+        if (o < O && l < F2) part[(size_t)a * nw + o * F2 + l] = acc[a][k][j];
+      }
   if (tid < 2 * O) part[2 * nw + tid] = accb;
 }
 

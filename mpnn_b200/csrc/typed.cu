@@ -340,30 +340,27 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // saved layout (floats): acts[(G + L + 1)][R][PW] : slot 0 = input rows (zero padded), 1..G growth outputs,
 // G+1..G+L tied outputs (slot G+L = x)
-__global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ acts, float* __restrict__ table,
-                                                  float* __restrict__ tableT) {
-  __shared__ __align__(16) float Wn[PW * WS_];   // Wn[o][i] = W[o][i]
+__global__ void __launch_bounds__(256) k_enet_fwd(ENet n, int fch, float* __restrict__ acts,
+                                                  float* __restrict__ table, float* __restrict__ tableT) {
+  extern __shared__ __align__(16) float Wl[];   // [fch][P | 1] staged rows of the last Linear
   __shared__ __align__(16) float A[2][PW];
+  int staged_f0 = -1;
   const int tid = threadIdx.x;
   const int o = tid >> 2, q = tid & 3;
   const int P = n.P;
-  {
-    float wv[PW * PW / 256];
+  // this thread's slice of row o of the tied weight, kept in REGISTERS for all layers and rows:
+  // wreg[4j + t] = W[o][16j + 4q + t]   (the 16-byte chunk q of every 64-byte group: conflict-free LDS.128)
+  float wreg[16];
 #pragma unroll
-    for (int t = 0; t < PW * PW / 256; ++t) {  // all loads in flight at once (clamped address, masked value)
-      const int idx = tid + t * 256;
-      const int oo = idx / PW, ii = idx - oo * PW;
-      wv[t] = __ldg(n.w_tied + min(oo, P - 1) * P + min(ii, P - 1));
-    }
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int t = 0; t < PW * PW / 256; ++t) {
-      const int idx = tid + t * 256;
-      const int oo = idx / PW, ii = idx - oo * PW;
-      Wn[oo * WS_ + ii] = (oo < P && ii < P) ? wv[t] : 0.f;
+    for (int t = 0; t < 4; ++t) {
+      const int i = 16 * j + 4 * q + t;
+      const float w = __ldg(n.w_tied + (size_t)min(o, P - 1) * P + min(i, P - 1));
+      wreg[4 * j + t] = (o < P && i < P) ? w : 0.f;
     }
-  }
   for (int row = blockIdx.x; row < n.R; row += gridDim.x) {
-    __syncthreads();  // Wn loaded / previous row done with A
+    __syncthreads();  // previous row done with A
     if (tid < PW) {
       float v = tid < n.ef ? n.rows[(size_t)row * n.ef + tid] : 0.f;
       A[0][tid] = v;
@@ -386,14 +383,16 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ ac
       __syncthreads();
       cur ^= 1;
     }
-    const float* wrow = Wn + o * WS_ + q;
     for (int l = 0; l < n.L; ++l, ++slot) {
-      const float* ap = &A[cur][q];
+      const float4* ap = reinterpret_cast<const float4*>(&A[cur][4 * q]);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int ii = 0; ii < PW / 4; ii += 2) {
-        a0 = fmaf(wrow[ii * 4], ap[ii * 4], a0);
-        a1 = fmaf(wrow[ii * 4 + 4], ap[ii * 4 + 4], a1);
+      for (int j = 0; j < 4; ++j) {
+        const float4 a4 = ap[4 * j];
+        a0 = fmaf(wreg[4 * j + 0], a4.x, a0);
+        a1 = fmaf(wreg[4 * j + 1], a4.y, a1);
+        a0 = fmaf(wreg[4 * j + 2], a4.z, a0);
+        a1 = fmaf(wreg[4 * j + 3], a4.w, a1);
       }
       float acc = quad_sum(a0 + a1);
       if (q == 0) {
@@ -404,36 +403,50 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ ac
       __syncthreads();
       cur ^= 1;
     }
-    // table of this distinct row: T[u][l][k] = B[k*nf+l] + W_last[k*nf+l, :] . x_u   (one warp per output, lanes over p)
+    // table of this distinct row: T[u][l][k] = B[k*nf+l] + W_last[k*nf+l, :] . x_u
+    // W_last is staged through shared memory in chunks of `fch` output rows (coalesced, all loads in flight),
+    // then one thread per output walks its row (odd row stride: conflict-free) against the broadcast x_u.
     const int DP = n.DP;
     const int warp = tid >> 5, lane = tid & 31;
     const int nout = n.mf * n.nf;
-    const float x0 = lane < P ? A[cur][lane] : 0.f;
-    const float x1 = lane + 32 < P ? A[cur][lane + 32] : 0.f;
-    constexpr int FB = 8;  // outputs per batch: 2*FB independent loads in flight per lane
-    for (int fb = warp * FB; fb < nout; fb += 8 * FB) {
-      float acc[FB], w0[FB], w1[FB];
+    const int LP = P | 1;
+    for (int f0 = 0; f0 < nout; f0 += fch) {
+      const int cnt = min(fch, nout - f0);
+      if (f0 != staged_f0) {     // single-chunk tables are staged once per CTA
+        __syncthreads();
+        for (int fb = warp * 8; fb < cnt; fb += 64) {
+          float w0[8], w1[8];
 #pragma unroll
-      for (int j = 0; j < FB; ++j) {  // unconditional (clamped) loads: 2*FB requests in flight; x0/x1 are 0 off-range
-        const float* w = n.w_last + (size_t)min(fb + j, nout - 1) * P;
-        w0[j] = __ldg(w + min(lane, P - 1));
-        w1[j] = __ldg(w + min(lane + 32, P - 1));
-      }
+          for (int j = 0; j < 8; ++j) {
+            const float* w = n.w_last + (size_t)(f0 + min(fb + j, cnt - 1)) * P;
+            w0[j] = __ldg(w + min(lane, P - 1));
+            w1[j] = __ldg(w + min(lane + 32, P - 1));
+          }
 #pragma unroll
-      for (int j = 0; j < FB; ++j) acc[j] = fmaf(w1[j], x1, w0[j] * x0);
-#pragma unroll
-      for (int j = 0; j < FB; ++j) acc[j] = warp_sum(acc[j]);
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const int f = fb + j;
-          if (f < nout) {
-            const float v = acc[j] + n.b_last[f];
-            const int k = f / n.nf, l = f - k * n.nf;
-            table[((size_t)row * DP + l) * DP + k] = v;
-            tableT[((size_t)row * DP + k) * DP + l] = v;
+          for (int j = 0; j < 8; ++j) {
+            if (fb + j < cnt) {
+              if (lane < P) Wl[(fb + j) * LP + lane] = w0[j];
+              if (lane + 32 < P) Wl[(fb + j) * LP + lane + 32] = w1[j];
+            }
           }
         }
+        staged_f0 = f0;
+        __syncthreads();
+      }
+      for (int t = tid; t < cnt; t += 256) {
+        const int f = f0 + t;
+        const float* wr = Wl + t * LP;
+        float a0 = n.b_last[f], a1 = 0.f;
+        int pp = 0;
+        for (; pp + 1 < P; pp += 2) {
+          a0 = fmaf(wr[pp], A[cur][pp], a0);
+          a1 = fmaf(wr[pp + 1], A[cur][pp + 1], a1);
+        }
+        if (pp < P) a0 = fmaf(wr[pp], A[cur][pp], a0);
+        const float v = a0 + a1;
+        const int k = f / n.nf, l = f - k * n.nf;
+        table[((size_t)row * DP + l) * DP + k] = v;
+        tableT[((size_t)row * DP + k) * DP + l] = v;
       }
     }
     // zero the padding of the table (feature widths that are not a power of two)
@@ -456,7 +469,6 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, float* __restrict__ ac
 __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restrict__ acts, const float* __restrict__ dT,
                                                   float* __restrict__ partial, int partial_stride,
                                                   float* __restrict__ d_rows /*[R, ef] or null*/) {
-  __shared__ __align__(16) float Wt[PW * WS_];   // Wt[i][o] = W[o][i]
   __shared__ __align__(16) float D[2][PW];       // delta of the current layer
   __shared__ __align__(16) float Ap[2][PW];      // input activation of the current layer
   __shared__ __align__(16) float dAs[PW];        // un-masked gradient w.r.t. the tied input
@@ -465,21 +477,16 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
   const int i_ = tid >> 2, q = tid & 3;          // (output index, split lane) of the dA dot products
   const int og = tid >> 4, ig = tid & 15;        // dW micro-tile
   const int P = n.P, DP = n.DP;
-  {
-    float wv[PW * PW / 256];
+  // wreg[4j + t] = W[16j + 4q + t][i_]: this thread's slice of COLUMN i_ of the tied weight, in registers
+  float wreg[16];
 #pragma unroll
-    for (int t = 0; t < PW * PW / 256; ++t) {
-      const int idx = tid + t * 256;
-      const int oo = idx / PW, ii = idx - oo * PW;
-      wv[t] = __ldg(n.w_tied + min(oo, P - 1) * P + min(ii, P - 1));
-    }
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int t = 0; t < PW * PW / 256; ++t) {
-      const int idx = tid + t * 256;
-      const int oo = idx / PW, ii = idx - oo * PW;
-      Wt[ii * WS_ + oo] = (oo < P && ii < P) ? wv[t] : 0.f;
+    for (int t = 0; t < 4; ++t) {
+      const int oo = 16 * j + 4 * q + t;
+      const float w = __ldg(n.w_tied + (size_t)min(oo, P - 1) * P + min(i_, P - 1));
+      wreg[4 * j + t] = (oo < P && i_ < P) ? w : 0.f;
     }
-  }
   float accW[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -498,10 +505,15 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
       if (p < P) {
         const float* dt = dT + (size_t)row * DP * DP;
         const int nout = n.mf * n.nf;
+        int k = part_f / n.nf, l = part_f - k * n.nf;   // f = k*nf + l, advanced without divisions
 #pragma unroll 8
         for (int f = part_f; f < nout; f += 4) {
-          const int k = f / n.nf, l = f - k * n.nf;
           acc = fmaf(__ldg(dt + l * DP + k), __ldg(n.w_last + (size_t)f * P + p), acc);
+          l += 4;
+          while (l >= n.nf) {
+            l -= n.nf;
+            ++k;
+          }
         }
       }
       red4[part_f][p] = acc;
@@ -529,13 +541,15 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
 #pragma unroll
           for (int b = 0; b < 4; ++b) accW[a][b] = fmaf(dv[a], av[b], accW[a][b]);
       }
-      const float* wt = Wt + i_ * WS_ + q;
-      const float* dp = &D[cur][q];
+      const float4* dp = reinterpret_cast<const float4*>(&D[cur][4 * q]);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int oo = 0; oo < PW / 4; oo += 2) {
-        a0 = fmaf(dp[oo * 4], wt[oo * 4], a0);
-        a1 = fmaf(dp[oo * 4 + 4], wt[oo * 4 + 4], a1);
+      for (int j = 0; j < 4; ++j) {
+        const float4 d4 = dp[4 * j];
+        a0 = fmaf(wreg[4 * j + 0], d4.x, a0);
+        a1 = fmaf(wreg[4 * j + 1], d4.y, a1);
+        a0 = fmaf(wreg[4 * j + 2], d4.z, a0);
+        a1 = fmaf(wreg[4 * j + 3], d4.w, a1);
       }
       const float g = quad_sum(a0 + a1);   // gradient w.r.t. this layer's input a_{l-1}[i_]
       if (q == 0) {
@@ -611,10 +625,19 @@ __global__ void k_enet_last_bwd(const float* __restrict__ acts_x /*[R][PW]*/, co
   int p = idx % (P + 1), f = idx / (P + 1);
   int l = f % nf, k = f / nf;
   float s = 0.f;
-#pragma unroll 8
-  for (int u = 0; u < R; ++u) {
-    float d = dT[((size_t)u * DP + l) * DP + k];
-    s = fmaf(d, p < P ? acts_x[(size_t)u * PW + p] : 1.f, s);
+  const float* dcol = dT + (size_t)l * DP + k;
+  const float* xcol = acts_x + min(p, P - 1);
+  for (int u0 = 0; u0 < R; u0 += 8) {
+    float dv[8], xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 16 independent clamped loads
+      const int u = min(u0 + j, R - 1);
+      dv[j] = __ldg(dcol + (size_t)u * DP * DP);
+      xv[j] = __ldg(xcol + (size_t)u * PW);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (u0 + j < R) s = fmaf(dv[j], p < P ? xv[j] : 1.f, s);
   }
   if (p < P)
     dW[(size_t)f * P + p] = s;
@@ -743,7 +766,10 @@ int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* c
                MPNN_ERR_UNSUPPORTED, "enet_fwd: layer plan ef=%d growth=%d P=%d not supported by the fused kernel", ef,
                n_growth, P);
   MPNN_REQUIRE(n.DP <= 32, MPNN_ERR_UNSUPPORTED, "enet_fwd: feature width > 32");
-  k_enet_fwd<<<enet_grid(R), 256, 0, stream>>>(n, saved, table, tableT);
+  int fch = nf * mf < 512 ? nf * mf : 512;
+  size_t smem = (size_t)fch * (P | 1) * sizeof(float);
+  MPNN_CUDA(cudaFuncSetAttribute(k_enet_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_enet_fwd<<<enet_grid(R), 256, smem, stream>>>(n, fch, saved, table, tableT);
   MPNN_CHECK_LAUNCH("k_enet_fwd");
   return MPNN_OK;
 }
