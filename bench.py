@@ -238,7 +238,8 @@ def run_ours(args):
                 "fp32_ffma_peak_tflops": FP32_FFMA_TFLOPS, "frac_of_fp32_ffma": achieved / FP32_FFMA_TFLOPS,
                 "ms_per_launch": trunk_ms, "algorithmic_flops_per_launch": trunk_flops,
                 "rows_evaluated": el.E + 1, "mp_step_fwd_flops": step_flops, "mp_step_fwd_bytes": q_step}
-        launches = count_launches(run_resident)
+    # every rank replays the step here (it contains the gradient all-reduce when N > 1); rank 0 keeps the count
+    launches = count_launches(run_resident)
     if gs is not None:
         gs.check()
 
