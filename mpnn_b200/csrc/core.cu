@@ -78,6 +78,28 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int nblk, int 
   out[c] = accumulate ? out[c] + s : s;
 }
 
+// wide matrices (width > 1024: the flat [rows, mf*nf] output of edge_map's last Linear on the distinct bond rows):
+// one thread per column, coalesced across the warp, rows walked in order
+__global__ void k_colsum_wide(const float* __restrict__ X, const float* __restrict__ Y, long long rows, int width,
+                              long long ldx, long long ldy, float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  float s0 = 0.f, s1 = 0.f;
+  long long r = 0;
+  for (; r + 1 < rows; r += 2) {
+    float a = X[r * ldx + c], b = X[(r + 1) * ldx + c];
+    if (Y) {
+      a *= Y[r * ldy + c];
+      b *= Y[(r + 1) * ldy + c];
+    }
+    s0 += a;
+    s1 += b;
+  }
+  if (r < rows) s0 += X[r * ldx + c] * (Y ? Y[r * ldy + c] : 1.f);
+  const float s = s0 + s1;
+  out[c] = accumulate ? out[c] + s : s;
+}
+
 }  // namespace
 
 static int colsum_blocks(long long rows, int* rows_per_block) {
@@ -114,7 +136,11 @@ size_t mpnn_colsum_workspace_bytes(long long rows, int width) {
 int mpnn_colsum(const float* X, const float* Y, long long rows, int width, long long ldx, long long ldy, float* out,
                 int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(rows >= 0 && width > 0, MPNN_ERR_ARG, "colsum: bad dims");
-  MPNN_REQUIRE(width <= 1024, MPNN_ERR_UNSUPPORTED, "colsum: width %d > 1024", width);
+  if (width > 1024) {
+    k_colsum_wide<<<ceil_div(width, 256), 256, 0, stream>>>(X, Y, rows, width, ldx, ldy, out, accumulate);
+    MPNN_CHECK_LAUNCH("k_colsum_wide");
+    return MPNN_OK;
+  }
   int rpb;
   int nblk = colsum_blocks(rows, &rpb);
   if (rows == 0) nblk = 0;

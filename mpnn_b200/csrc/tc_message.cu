@@ -1,0 +1,751 @@
+// Typed message path on the 5th-generation tensor cores (tcgen05 + TMEM), feature widths 33..256.
+//
+// Reference: edge_network.py:42-52 (message function) + adjacent_message_agg.py:18 (aggregation).  On the typed
+// path (exact de-duplication of bond rows, csrc/dedup.cu) the per-pair matrix A(bfm[b,i,j]) is one of U table
+// entries T[u] (U ~ tens), so with the edges grouped by u the message function is a GROUPED GEMM:
+//
+//     Y[e, :]  = alpha_e * T[u_e] h[src_e]                (forward;  A = gathered sender states,  B = T[u])
+//     dG[e, :] = alpha_e * T[u_e]^T dM[dst_e]             (backward; A = gathered message grads,  B = T[u]^T)
+//     dT[u]    = sum_{e of type u} alpha_e h[src_e] (x) dM[dst_e]      (backward, K = the edges of the type)
+//
+// followed by the fixed-order CSR / CSC segmented sums (mpnn_segment_sum) -> no float atomics, bit-reproducible.
+//
+// Kernel anatomy (one persistent CTA per SM, 288 threads):
+//   warps 0-3  producers: gather 128-byte row pieces (coalesced float4 loads, 8 lanes per row) and store them
+//              into shared memory in the canonical 128B-swizzled UMMA layout; generic->async proxy fence;
+//              mbarrier arrive (full[stage]).
+//   warp  4    one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=DP, K=8) with the accumulator in TMEM,
+//              tcgen05.commit releases the stage (empty[stage]) and publishes the accumulator (acc_full).
+//   warps 5-8  epilogue: tcgen05.ld the accumulator (one TMEM lane = one edge row per thread), scale by alpha_e,
+//              store.  The accumulator is double buffered in TMEM so the epilogue overlaps the next tile's MMAs.
+// Operands are fp32 in memory and are read by the tensor core as TF32 (10-bit mantissa); accumulation is fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;      // edges per tile = UMMA M
+constexpr int KB = 32;         // fp32 elements per 128-byte swizzle line
+constexpr int PRODUCERS = 128;
+constexpr int THREADS = 288;
+constexpr int MMA_WARP = 4;
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug must end in a trap (a CUDA error on the host), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], TF32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// mbarrier arrive once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA instruction descriptor, kind::tf32: D fp32 [4,6)=1, A/B format TF32 [7,10)=[10,13)=2, A/B major bits 15/16
+// (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// UMMA shared-memory descriptor, 128-byte swizzle: start>>4 [0,14), leading byte offset>>4 [16,30), stride byte
+// offset>>4 [32,46), version 1 [46,48), layout type SWIZZLE_128B = 2 [61,64).  Tile bases are 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t layout_type = 2u) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void sts4(uint8_t* base, uint32_t off, float4 v) {
+  *reinterpret_cast<float4*>(base + off) = v;
+}
+// byte offset of 16-byte chunk `chunk` of 128-byte line `line` inside a swizzled region (region base 1024-aligned)
+__device__ __forceinline__ uint32_t swz(int line, int chunk) {
+  return (uint32_t)line * 128u + (uint32_t)((chunk ^ (line & 7)) << 4);
+}
+// MN-major fp32/tf32 operands use the SWIZZLE_128B_BASE32B layout (UMMA layout type 1): atoms of 4 K-rows x 128
+// bytes (32 fp32 along M/N); inside an atom the 32-BYTE chunk index is XORed with the K-row index.  Returns the
+// byte offset of 16-byte chunk `chunk` (0..7) of K-row `row4` (0..3) inside a 512-byte atom.
+__device__ __forceinline__ uint32_t swz32(int row4, int chunk) {
+  return (uint32_t)row4 * 128u + (uint32_t)(((chunk >> 1) ^ row4) << 5) + (uint32_t)((chunk & 1) << 4);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tile plan: the type-sorted edge list cut into single-type tiles of <= 128 edges (device side, no host read)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_tc_plan_scan(const int* __restrict__ type_ptr, int ntypes, int max_tiles,
+                                                       int* __restrict__ tile_off /*[ntypes+1]*/,
+                                                       int* __restrict__ n_tiles) {
+  __shared__ int buf[1024];
+  __shared__ int carry;
+  const int tid = threadIdx.x;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int u0 = 0; u0 < ntypes; u0 += 1024) {
+    const int u = u0 + tid;
+    int nt = 0;
+    if (u < ntypes) {
+      const int cnt = type_ptr[u + 1] - type_ptr[u];
+      nt = cnt > 0 ? (cnt + TILE - 1) / TILE : 0;
+    }
+    buf[tid] = nt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = tid >= o ? buf[tid - o] : 0;
+      __syncthreads();
+      buf[tid] += t;
+      __syncthreads();
+    }
+    if (u < ntypes) tile_off[u] = carry + buf[tid] - nt;
+    __syncthreads();
+    if (tid == 0) carry += buf[1023];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    tile_off[ntypes] = carry;
+    *n_tiles = min(carry, max_tiles);
+  }
+}
+
+// tile t -> (type, first sorted position, edge count): binary search of t in tile_off
+__global__ void __launch_bounds__(256) k_tc_plan_fill(const int* __restrict__ type_ptr, int ntypes,
+                                                      const int* __restrict__ tile_off,
+                                                      const int* __restrict__ n_tiles, int* __restrict__ tile_type,
+                                                      int* __restrict__ tile_pos, int* __restrict__ tile_cnt) {
+  const int total = *n_tiles;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < total; t += gridDim.x * 256) {
+    int lo = 0, hi = ntypes - 1;   // last u with tile_off[u] <= t (types without tiles share their successor's offset)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int u = lo;
+    const int p0 = type_ptr[u], cnt = type_ptr[u + 1] - p0;
+    const int k = t - tile_off[u];
+    tile_type[t] = u;
+    tile_pos[t] = p0 + k * TILE;
+    tile_cnt[t] = min(TILE, cnt - k * TILE);
+  }
+}
+
+struct TcPlan {
+  const int* n_tiles;
+  const int* tile_off;
+  const int* tile_type;
+  const int* tile_pos;
+  const int* tile_cnt;
+};
+
+struct TcGemm {
+  TcPlan plan;
+  const int* type_eid;  // sorted position -> edge id
+  const int* gidx;      // edge id -> row of A
+  const float* A;       // [*, lda]
+  const float* Bm;      // [types][DP][DP]: row n, K contiguous
+  const float* alpha;   // [E] or null
+  float* Y;             // [E, ldy]
+  int lda, K, ldy, N;
+};
+
+template <int DP>
+struct GemmCfg {
+  static constexpr int A_BYTES = TILE * 128;
+  static constexpr int B_BYTES = DP * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = 4;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int TCOLS = 2 * DP;  // double-buffered accumulator
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Y[e, 0:N] = alpha_e * sum_k A[gidx[e], k] * Bm[type(e)][n][k]       (edges in type-sorted tiles)
+// ---------------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
+  using C = GemmCfg<DP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSTAGE + s); };
+  auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * C::NSTAGE + s); };
+  auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * C::NSTAGE + 2 + s); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) {
+      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(accfull_bar(s), 1);
+      mbar_init(accempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = *a.plan.n_tiles;
+  const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t0 = blockIdx.x * per;
+  const int t1 = min(t0 + per, n_tiles);
+  constexpr int NKB = DP / KB;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int sub = tid >> 3, chunk = tid & 7;
+    int stage = 0, phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int u = a.plan.tile_type[t], pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
+      const float* arow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 16 + sub;
+        int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
+        arow[i] = e >= 0 ? a.A + (size_t)__ldg(a.gidx + e) * a.lda : nullptr;
+      }
+      const float* brow = a.Bm + ((size_t)u * DP + sub) * DP;
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int kk = kb * KB + chunk * 4;
+        float4 va[8], vb[DP / 16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          va[i] = (arow[i] != nullptr && kk < a.K) ? ldg4(arow[i] + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < DP / 16; ++i) vb[i] = ldg4(brow + (size_t)i * 16 * DP + kk);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        uint8_t* As = smem + stage * C::STAGE;
+        uint8_t* Bs = As + C::A_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts4(As, swz(i * 16 + sub, chunk), va[i]);
+#pragma unroll
+        for (int i = 0; i < DP / 16; ++i) sts4(Bs, swz(i * 16 + sub, chunk), vb[i]);
+        fence_proxy_async();
+        mbar_arrive(full_bar(stage));
+        if (++stage == C::NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE, DP, 0, 0);
+      int stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int i = t - t0, acc = i & 1, use = i >> 1;
+        mbar_wait(accempty_bar(acc), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * DP);
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          const uint64_t ad = make_sdesc(sa, 16, 1024);
+          const uint64_t bd = make_sdesc(sa + C::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int j = 0; j < KB / 8; ++j)  // K = 8 per instruction: +32 bytes inside the swizzle line
+            umma_tf32(d, ad + 2u * j, bd + 2u * j, idesc, (kb | j) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == C::NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(accfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int r = q * 32 + lane;
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, acc = i & 1, use = i >> 1;
+      const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
+      const int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
+      const float al = (e >= 0 && a.alpha) ? __ldg(a.alpha + e) : 1.f;
+      mbar_wait(accfull_bar(acc), use & 1);
+      tc_fence_after();
+      float* yrow = a.Y + (size_t)(e >= 0 ? e : 0) * a.ldy;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        if (c0 >= a.N) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DP + c0), v);
+        if (e >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (c0 + 4 * j < a.N)
+              *reinterpret_cast<float4*>(yrow + c0 + 4 * j) =
+                  make_float4(al * v[4 * j], al * v[4 * j + 1], al * v[4 * j + 2], al * v[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(accempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dT[u][l][k] = sum_{e of type u} alpha_e H[src_e, l] dM[dst_e, k]: K = the edges.  Both operands are gathered
+// rows, i.e. MN-major: a stage holds 32 edges, every 128-byte row piece is one K-row of a [4 x 32] atom of the
+// SWIZZLE_128B_BASE32B layout (the only shared-memory layout tcgen05 accepts for MN-major 32-bit operands).
+// A CTA walks a contiguous range of tiles and keeps accumulating in TMEM while the type does not change; each
+// (CTA, type) segment is flushed to partial slot (cta + type) -- strictly increasing along the sorted list --
+// and k_tc_table_reduce sums the slots of a type in fixed order.
+// ---------------------------------------------------------------------------------------------------
+struct TcGrad {
+  TcPlan plan;
+  const int* type_eid;
+  const int* edge_src;
+  const int* edge_dst;
+  const float* alpha;
+  const float* H;    // [*, nf]
+  const float* dM;   // [*, mf]
+  float* partial;    // [slots][DP][DP]
+  int nf, mf;
+};
+
+template <int DP>
+struct GradCfg {
+  static constexpr int MP = DP < 128 ? 128 : DP;  // UMMA M is 128: narrower tables are zero padded
+  static constexpr int MB = MP / 128;
+  static constexpr int KST = 32;                  // edges per stage
+  static constexpr int A_BYTES = KST * MP * 4;
+  static constexpr int B_BYTES = KST * DP * 4;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = DP == 256 ? 3 : 4;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+  static constexpr int TCOLS = MB * DP < 32 ? 32 : MB * DP;
+  static constexpr uint32_t SBO = 512;               // between [4 x 32] atoms along K (groups of 4 edges)
+  static constexpr uint32_t LBO = (KST / 4) * 512;   // between atoms along M/N (32 columns)
+};
+
+template <int DP>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
+  using C = GradCfg<DP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 2);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSTAGE + s); };
+  const uint32_t accfull_bar = bar_base + 8u * (2 * C::NSTAGE);
+  const uint32_t accempty_bar = bar_base + 8u * (2 * C::NSTAGE + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) {
+      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accfull_bar, 1);
+    mbar_init(accempty_bar, 128);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = *a.plan.n_tiles;
+  const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t0 = blockIdx.x * per;
+  const int t1 = min(t0 + per, n_tiles);
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int sub = tid >> 3, chunk = tid & 7;   // sub: 0..15 -> edges sub and sub+16 of the stage
+    int stage = 0, phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
+      for (int s0 = 0; s0 < cnt; s0 += C::KST) {
+        const float* hrow[2];
+        const float* mrow[2];
+        float al[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = s0 + sub + 16 * h;
+          const int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
+          hrow[h] = e >= 0 ? a.H + (size_t)__ldg(a.edge_src + e) * a.nf : nullptr;
+          mrow[h] = e >= 0 ? a.dM + (size_t)__ldg(a.edge_dst + e) * a.mf : nullptr;
+          al[h] = (e >= 0 && a.alpha) ? __ldg(a.alpha + e) : 1.f;
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        uint8_t* As = smem + stage * C::STAGE;
+        uint8_t* Bs = As + C::A_BYTES;
+        // A: H rows (scaled by alpha), MP/32 column blocks x 2 edges per thread
+        {
+          float4 v[2 * C::MP / 32];
+#pragma unroll
+          for (int mb = 0; mb < C::MP / 32; ++mb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int col = mb * 32 + chunk * 4;
+              float4 x = (hrow[h] != nullptr && col < a.nf) ? ldg4(hrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[mb * 2 + h] = make_float4(al[h] * x.x, al[h] * x.y, al[h] * x.z, al[h] * x.w);
+            }
+#pragma unroll
+          for (int mb = 0; mb < C::MP / 32; ++mb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = sub + 16 * h;  // edge within the stage
+              sts4(As, (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[mb * 2 + h]);
+            }
+        }
+        // B: dM rows
+        {
+          float4 v[2 * DP / 32];
+#pragma unroll
+          for (int nb = 0; nb < DP / 32; ++nb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int col = nb * 32 + chunk * 4;
+              v[nb * 2 + h] = (mrow[h] != nullptr && col < a.mf) ? ldg4(mrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+          for (int nb = 0; nb < DP / 32; ++nb)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = sub + 16 * h;
+              sts4(Bs, (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[nb * 2 + h]);
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(full_bar(stage));
+        if (++stage == C::NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, DP, 1, 1);
+      int stage = 0, phase = 0, seg = 0, cur = -1;
+      bool fresh = true;
+      for (int t = t0; t < t1; ++t) {
+        const int u = a.plan.tile_type[t], cnt = a.plan.tile_cnt[t];
+        if (u != cur) {
+          if (cur >= 0) {
+            umma_commit(accfull_bar);
+            mbar_wait(accempty_bar, seg & 1);  // the epilogue has drained the accumulator of segment `seg`
+            tc_fence_after();
+            ++seg;
+          }
+          cur = u;
+          fresh = true;
+        }
+        for (int s0 = 0; s0 < cnt; s0 += C::KST) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE;
+#pragma unroll
+          for (int j = 0; j < C::KST / 8; ++j) {
+            // K = 8 per instruction = two 4-edge atoms (SBO apart); operands span M/N in atoms LBO apart
+            const uint64_t bd = make_sdesc(sa + C::A_BYTES + j * 1024, C::LBO, C::SBO, 1u);
+#pragma unroll
+            for (int m = 0; m < C::MB; ++m) {
+              const uint64_t ad = make_sdesc(sa + m * 4 * C::LBO + j * 1024, C::LBO, C::SBO, 1u);
+              umma_tf32(tmem_base + (uint32_t)(m * DP), ad, bd, idesc, fresh ? 0u : 1u);
+            }
+            fresh = false;
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == C::NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if (cur >= 0) umma_commit(accfull_bar);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    int seg = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int u = a.plan.tile_type[t];
+      const bool last = (t + 1 == t1) || (a.plan.tile_type[t + 1] != u);
+      if (!last) continue;
+      mbar_wait(accfull_bar, seg & 1);
+      tc_fence_after();
+      float* out = a.partial + (size_t)(blockIdx.x + u) * DP * DP;
+#pragma unroll 1
+      for (int m = 0; m < C::MB; ++m) {
+        const int l = m * 128 + q * 32 + lane;
+        if (m * 128 + q * 32 < DP) {  // warp-uniform: quadrants beyond a narrow table hold only padding
+#pragma unroll 1
+          for (int c0 = 0; c0 < DP; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * DP + c0), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(out + (size_t)l * DP + c0 + 4 * j) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(accempty_bar);
+      ++seg;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+// dT[u][idx] = sum over the CTAs whose tile range touches type u of partial[cta + u][idx]  (fixed order)
+__global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int grid_ctas, int ntypes, int elems,
+                                                         const float* __restrict__ partial, float* __restrict__ dT) {
+  const int u = blockIdx.y;
+  const int n_tiles = *plan.n_tiles;
+  const int per = (n_tiles + grid_ctas - 1) / grid_ctas;
+  const int f = plan.tile_off[u], l = (u < ntypes ? plan.tile_off[u + 1] : f);
+  int c0 = 0, c1 = -1;
+  if (l > f && per > 0 && f < n_tiles) {
+    c0 = f / per;
+    c1 = (min(l, n_tiles) - 1) / per;
+  }
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < elems; idx += gridDim.x * 256) {
+    float s = 0.f;
+    for (int c = c0; c <= c1; ++c) s += partial[(size_t)(c + u) * elems + idx];
+    dT[(size_t)u * elems + idx] = s;
+  }
+}
+
+int tc_dp(int nf, int mf) {
+  int d = nf > mf ? nf : mf;
+  if (d <= 32 || d > 256 || (nf & 3) || (mf & 3)) return -1;
+  return pow2_at_least(d, 64);
+}
+int tc_grid() { return mpnn_num_sms(); }
+int tc_max_tiles(int edge_capacity, int ntypes) { return edge_capacity / TILE + ntypes + 1; }
+
+struct PlanBuf {
+  int* n_tiles;
+  int* tile_off;
+  int* tile_type;
+  int* tile_pos;
+  int* tile_cnt;
+};
+size_t plan_bytes(int edge_capacity, int ntypes) {
+  const size_t mt = (size_t)tc_max_tiles(edge_capacity, ntypes);
+  return align_up(((size_t)ntypes + 2 + 3 * mt + 4) * sizeof(int), 256);
+}
+PlanBuf carve_plan(void* ws, int edge_capacity, int ntypes) {
+  const size_t mt = (size_t)tc_max_tiles(edge_capacity, ntypes);
+  int* p = (int*)ws;
+  PlanBuf b;
+  b.n_tiles = p;
+  b.tile_off = p + 4;
+  b.tile_type = b.tile_off + ntypes + 2;
+  b.tile_pos = b.tile_type + mt;
+  b.tile_cnt = b.tile_pos + mt;
+  return b;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+// padded feature width served by the tensor-core typed path (64, 128 or 256); -1 = not served
+int mpnn_tc_dp(int nf, int mf) { return tc_dp(nf, mf); }
+
+// plan buffer: the type-sorted edge list cut into single-type tiles; built once per edge list
+size_t mpnn_tc_plan_bytes(int edge_capacity, int unique_capacity) { return plan_bytes(edge_capacity, unique_capacity + 1); }
+
+int mpnn_tc_plan(const int* type_ptr, int edge_capacity, int unique_capacity, void* plan, size_t plan_bytes_,
+                 cudaStream_t stream) {
+  const int ntypes = unique_capacity + 1;   // type_ptr has unique_capacity+1 entries: the last "type" is empty
+  MPNN_REQUIRE(type_ptr && plan, MPNN_ERR_ARG, "tc_plan: null argument");
+  MPNN_REQUIRE(plan_bytes_ >= plan_bytes(edge_capacity, ntypes), MPNN_ERR_WORKSPACE, "tc_plan: plan buffer too small");
+  PlanBuf b = carve_plan(plan, edge_capacity, ntypes);
+  // types 0..unique_capacity-1 own [type_ptr[u], type_ptr[u+1]); entry `unique_capacity` closes the last one
+  const int max_tiles = tc_max_tiles(edge_capacity, ntypes);
+  k_tc_plan_scan<<<1, 1024, 0, stream>>>(type_ptr, unique_capacity, max_tiles, b.tile_off, b.n_tiles);
+  MPNN_CHECK_LAUNCH("k_tc_plan_scan");
+  int fgrid = ceil_div(max_tiles, 256);
+  if (fgrid > 4 * mpnn_num_sms()) fgrid = 4 * mpnn_num_sms();
+  k_tc_plan_fill<<<fgrid, 256, 0, stream>>>(type_ptr, unique_capacity, b.tile_off, b.n_tiles, b.tile_type, b.tile_pos,
+                                            b.tile_cnt);
+  MPNN_CHECK_LAUNCH("k_tc_plan_fill");
+  return MPNN_OK;
+}
+
+// Y[e, 0:N] = alpha_e * Bm[uid_e] (N x K, K contiguous, padded to DP x DP) . A[gidx[e], 0:K]
+// forward: A = H, gidx = edge_src, Bm = tableT, K = nf, N = mf;  backward: A = dM, gidx = edge_dst, Bm = table.
+int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid, const int* gidx,
+                      const float* A, int lda, int K, const float* Bm, int DP, const float* alpha, float* Y, int ldy,
+                      int N, cudaStream_t stream) {
+  MPNN_REQUIRE(plan && type_eid && gidx && A && Bm && Y, MPNN_ERR_ARG, "tc_edge_gemm: null argument");
+  MPNN_REQUIRE((K & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldy & 3) == 0 && K <= DP && N <= DP,
+               MPNN_ERR_UNSUPPORTED, "tc_edge_gemm: widths must be multiples of 4 and <= DP");
+  PlanBuf b = carve_plan(const_cast<void*>(plan), edge_capacity, unique_capacity + 1);
+  TcGemm a;
+  a.plan = TcPlan{b.n_tiles, b.tile_off, b.tile_type, b.tile_pos, b.tile_cnt};
+  a.type_eid = type_eid;
+  a.gidx = gidx;
+  a.A = A;
+  a.Bm = Bm;
+  a.alpha = alpha;
+  a.Y = Y;
+  a.lda = lda;
+  a.K = K;
+  a.ldy = ldy;
+  a.N = N;
+  const int grid = tc_grid();
+  switch (DP) {
+    case 64:
+      MPNN_REQUIRE(set_smem(k_tc_edge_gemm<64>, GemmCfg<64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_edge_gemm: smem attribute");
+      k_tc_edge_gemm<64><<<grid, THREADS, GemmCfg<64>::SMEM, stream>>>(a);
+      break;
+    case 128:
+      MPNN_REQUIRE(set_smem(k_tc_edge_gemm<128>, GemmCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_edge_gemm: smem attribute");
+      k_tc_edge_gemm<128><<<grid, THREADS, GemmCfg<128>::SMEM, stream>>>(a);
+      break;
+    case 256:
+      MPNN_REQUIRE(set_smem(k_tc_edge_gemm<256>, GemmCfg<256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_edge_gemm: smem attribute");
+      k_tc_edge_gemm<256><<<grid, THREADS, GemmCfg<256>::SMEM, stream>>>(a);
+      break;
+    default:
+      MPNN_REQUIRE(false, MPNN_ERR_UNSUPPORTED, "tc_edge_gemm: DP must be 64, 128 or 256 (got %d)", DP);
+  }
+  MPNN_CHECK_LAUNCH("k_tc_edge_gemm");
+  return MPNN_OK;
+}
+
+size_t mpnn_tc_table_grad_workspace_bytes(int unique_capacity, int DP) {
+  return (size_t)(tc_grid() + unique_capacity + 2) * DP * DP * sizeof(float);
+}
+
+// dT [(unique_capacity+1)][DP][DP]:  dT[u][l][k] = sum_{e of type u} alpha_e H[src_e, l] dM[dst_e, k]
+int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid,
+                       const int* edge_src, const int* edge_dst, const float* alpha, const float* H, int nf,
+                       const float* dM, int mf, int DP, float* dT, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  MPNN_REQUIRE(plan && type_eid && edge_src && edge_dst && H && dM && dT, MPNN_ERR_ARG, "tc_table_grad: null argument");
+  MPNN_REQUIRE((nf & 3) == 0 && (mf & 3) == 0 && nf <= DP && mf <= DP, MPNN_ERR_UNSUPPORTED,
+               "tc_table_grad: widths must be multiples of 4 and <= DP");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_table_grad_workspace_bytes(unique_capacity, DP), MPNN_ERR_WORKSPACE,
+               "tc_table_grad: workspace too small");
+  PlanBuf b = carve_plan(const_cast<void*>(plan), edge_capacity, unique_capacity + 1);
+  TcGrad a;
+  a.plan = TcPlan{b.n_tiles, b.tile_off, b.tile_type, b.tile_pos, b.tile_cnt};
+  a.type_eid = type_eid;
+  a.edge_src = edge_src;
+  a.edge_dst = edge_dst;
+  a.alpha = alpha;
+  a.H = H;
+  a.dM = dM;
+  a.partial = (float*)workspace;
+  a.nf = nf;
+  a.mf = mf;
+  const int grid = tc_grid();
+  switch (DP) {
+    case 64:
+      MPNN_REQUIRE(set_smem(k_tc_table_grad<64>, GradCfg<64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_table_grad: smem attribute");
+      k_tc_table_grad<64><<<grid, THREADS, GradCfg<64>::SMEM, stream>>>(a);
+      break;
+    case 128:
+      MPNN_REQUIRE(set_smem(k_tc_table_grad<128>, GradCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_table_grad: smem attribute");
+      k_tc_table_grad<128><<<grid, THREADS, GradCfg<128>::SMEM, stream>>>(a);
+      break;
+    case 256:
+      MPNN_REQUIRE(set_smem(k_tc_table_grad<256>, GradCfg<256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_table_grad: smem attribute");
+      k_tc_table_grad<256><<<grid, THREADS, GradCfg<256>::SMEM, stream>>>(a);
+      break;
+    default:
+      MPNN_REQUIRE(false, MPNN_ERR_UNSUPPORTED, "tc_table_grad: DP must be 64, 128 or 256 (got %d)", DP);
+  }
+  MPNN_CHECK_LAUNCH("k_tc_table_grad");
+  dim3 rgrid(ceil_div(DP * DP, 256 * 4), unique_capacity + 1);
+  k_tc_table_reduce<<<rgrid, 256, 0, stream>>>(a.plan, grid, unique_capacity, DP * DP, a.partial, dT);
+  MPNN_CHECK_LAUNCH("k_tc_table_reduce");
+  return MPNN_OK;
+}
+
+}  // extern "C"

@@ -525,6 +525,17 @@ def typed_dp(nf, mf):
     return _lib.load().mpnn_typed_dp(nf, mf)
 
 
+def tc_dp(nf, mf):
+    """padded width (64/128/256) when the tcgen05 typed path (csrc/tc_message.cu) serves the shape, else -1"""
+    return _lib.load().mpnn_tc_dp(int(nf), int(mf))
+
+
+def table_dp(nf, mf):
+    """padded width of the table of per-type matrices, whichever typed kernel family serves the shape (-1: none)"""
+    d = typed_dp(nf, mf)
+    return d if d >= 0 else tc_dp(nf, mf)
+
+
 class EdgeNetTableFn(torch.autograd.Function):
     """Fused growth layers + 50 tied layers + last Linear on the distinct rows (P <= 64):
     urows [R, ef] -> table T[u][l][k], tableT T[u][k][l]  ([R, DP, DP] each; reference edge_network.py:14-21,37)."""
@@ -582,7 +593,7 @@ class TableLayoutFn(torch.autograd.Function):
         _need_cuda(flat)
         flat = f32c(flat)
         R = flat.shape[0]
-        DP = lib.mpnn_typed_dp(nf, mf)
+        DP = table_dp(nf, mf)
         table = torch.empty(R, DP, DP, dtype=torch.float32, device=flat.device)
         tableT = torch.empty(R, DP, DP, dtype=torch.float32, device=flat.device)
         check(lib.mpnn_table_from_flat(ptr(flat), R, nf, mf, ptr(table), ptr(tableT), stream()), "table_from_flat")
@@ -649,3 +660,57 @@ class TypedMessageFn(torch.autograd.Function):
             check(lib.mpnn_colsum(ptr(dM), None, el.n_rows, mf, mf, 0, ptr(dbeta), 0, ptr(ws2), ws2.numel(), stream()),
                   "colsum")
         return dH, dT, None, dbeta, None, None, None, None, None
+
+
+class TypedMessageTCFn(torch.autograd.Function):
+    """Tensor-core form of the typed message path for feature widths 33..256 (csrc/tc_message.cu):
+    M[i] = sum_{e in E(i)} alpha_e T[uid_e]^T H[src_e] as a grouped TF32 GEMM over the type-sorted edge tiles
+    (tcgen05.mma, accumulator in TMEM) + the fixed-order CSR segmented sum.  Backward: the same GEMM kernel on the
+    gathered message gradients + CSC segmented sum, and dT[u] = sum_e alpha_e H[src_e] (x) dM[dst_e] with K = edges.
+    The HEAD-form extras (edge_network.py:50-51) are composed around this op in modules.EdgeNetwork."""
+
+    @staticmethod
+    def forward(ctx, H, table, tableT, el, alpha, nf, mf):
+        lib = _lib.load()
+        _need_cuda(H, table)
+        H, table, tableT = f32c(H), f32c(table), f32c(tableT)
+        alpha_c = f32c(alpha) if alpha is not None else None
+        ti = el.typed()
+        DP = table.shape[-1]
+        dev = H.device
+        plan = ti.tc_plan(el)
+        Y = torch.empty(max(el.Ecap, 1), mf, dtype=torch.float32, device=dev)
+        check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), ptr(el.edge_src), ptr(H), nf, nf,
+                                    ptr(tableT), DP, ptr(alpha_c), ptr(Y), mf, mf, stream()), "tc_edge_gemm")
+        M = torch.empty(el.n_rows, mf, dtype=torch.float32, device=dev)
+        check(lib.mpnn_segment_sum(ptr(Y), ptr(el.row_ptr), None, el.n_rows, mf, mf, ptr(M), mf, 0, 1.0, stream()),
+              "segment_sum")
+        ctx.save_for_backward(H, table, alpha_c)
+        ctx.meta = (el, nf, mf, DP)
+        return M
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dM):
+        lib = _lib.load()
+        H, table, alpha = ctx.saved_tensors
+        el, nf, mf, DP = ctx.meta
+        ti = el.typed()
+        dev = H.device
+        dM = f32c(dM)
+        plan = ti.tc_plan(el)
+        dH = dT = None
+        if ctx.needs_input_grad[0]:
+            dG = torch.empty(max(el.Ecap, 1), nf, dtype=torch.float32, device=dev)
+            check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), ptr(el.edge_dst), ptr(dM), mf, mf,
+                                        ptr(table), DP, ptr(alpha), ptr(dG), nf, nf, stream()), "tc_edge_gemm")
+            dH = torch.empty_like(H)
+            check(lib.mpnn_segment_sum(ptr(dG), ptr(el.col_ptr), ptr(el.csc_eid), el.n_rows, nf, nf, ptr(dH), nf, 0,
+                                       1.0, stream()), "segment_sum")
+        if ctx.needs_input_grad[1]:
+            dT = torch.empty_like(table)
+            ws = workspace(lib.mpnn_tc_table_grad_workspace_bytes(ti.Ucap, DP), dev)
+            check(lib.mpnn_tc_table_grad(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), ptr(el.edge_src),
+                                         ptr(el.edge_dst), ptr(alpha), ptr(H), nf, ptr(dM), mf, DP, ptr(dT), ptr(ws),
+                                         ws.numel(), stream()), "tc_table_grad")
+        return dH, dT, None, None, None, None, None

@@ -128,6 +128,19 @@ class TypedInfo(object):
         self.type_ptr, self.type_eid, self.type_pos = type_ptr, type_eid, type_pos
         self.U, self.Ucap = U, Ucap
         self.zero_type = Ucap
+        self._tc_plan = None
+
+    def tc_plan(self, el):
+        """single-type tiles of <= 128 type-sorted edges for the tcgen05 kernels (csrc/tc_message.cu), built once"""
+        if self._tc_plan is None:
+            lib = _lib.load()
+            if self.type_ptr is None:
+                raise RuntimeError("mpnn_b200: the tensor-core typed path needs the type-sorted edge list")
+            plan = _lib.workspace(lib.mpnn_tc_plan_bytes(el.Ecap, self.Ucap), self.uid.device)
+            _lib.check(lib.mpnn_tc_plan(_lib.ptr(self.type_ptr), el.Ecap, self.Ucap, _lib.ptr(plan), plan.numel(),
+                                        _lib.stream()), "tc_plan")
+            self._tc_plan = plan
+        return self._tc_plan
 
 
 TYPED_MAX_UNIQUE = 1024   # beyond this many distinct bond rows the per-edge contraction (csrc/message.cu) is used

@@ -12,7 +12,7 @@ from torch import nn
 from . import graph
 from .functional import (DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
                          GraphLevelOutputFn, GRUFn, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
-                         TableLayoutFn, TypedMessageFn, typed_dp)
+                         TableLayoutFn, TypedMessageFn, TypedMessageTCFn, table_dp, tc_dp, typed_dp)
 from . import _lib
 
 _N_TIED = 50  # edge_network.py:20
@@ -150,8 +150,10 @@ class EdgeNetwork(nn.Module):
 
     def _typed_ok(self, bfm, el):
         """The typed path serves the plain edge network on data bond features (the reference's datasets):
-        bfm is not differentiated, feature widths <= 32, and the batch holds few distinct bond rows."""
-        if not self._typed_capable or bfm.requires_grad or typed_dp(self.nf, self.mf) < 0:
+        bfm is not differentiated, the batch holds few distinct bond rows, and the feature widths are <= 32
+        (CUDA-core gather kernels, csrc/typed.cu) or 33..256 in multiples of 4 (tcgen05 grouped GEMM,
+        csrc/tc_message.cu)."""
+        if not self._typed_capable or bfm.requires_grad or table_dp(self.nf, self.mf) < 0:
             return False
         ti = el.typed()
         return ti.type_ptr is not None
@@ -165,7 +167,7 @@ class EdgeNetwork(nn.Module):
         gb = [self.edge_map[i].bias for i in self._growth_idx]
         w_tied = self.edge_map[self._tied_idx][0].weight
         W, Bv = self._last()
-        if _lib.load().mpnn_enet_supported(self.ef, len(gw), self.P):
+        if typed_dp(self.nf, self.mf) >= 0 and _lib.load().mpnn_enet_supported(self.ef, len(gw), self.P):
             table, tableT = EdgeNetTableFn.apply(ti.urows, w_tied, _N_TIED, W, Bv, self.nf, self.mf, *(gw + gb))
         else:   # wide trunks (P = 256, 625, 4096): generic trunk + last Linear on the distinct rows
             X = EdgeTrunkFn.apply(ti.urows, w_tied, _N_TIED, *(gw + gb))
@@ -174,6 +176,20 @@ class EdgeNetwork(nn.Module):
         self._table_cache = (el, table, tableT)
         self._msg_cache = {}
         return table, tableT
+
+    def _head_messages_tc(self, afm, table, el):
+        """HEAD form (edge_network.py:50-51) around the tensor-core grouped GEMM: every pair (i, j) of a graph
+        contributes A(bfm[b,i,j]) h_j and non-bonded pairs share the zero-row matrix T0, so
+        M[i] = sum_{e in E(i)} (T[u_e] - T0) h[src_e]  +  T0 S[b]  +  beta,   S[b] = sum_j h[b,j]."""
+        B, N, nf = afm.shape
+        z = el.typed().zero_type
+        T0 = table[z]                                            # [DP, DP], T0[l][k]
+        table_h = table - T0.unsqueeze(0)
+        tableT_h = table_h.detach().transpose(1, 2).contiguous()
+        M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table_h, tableT_h, el, None, self.nf, self.mf)
+        S = afm.sum(dim=1)                                       # [B, nf]
+        base = LinearFn.apply(S, T0[:self.nf, :self.mf].t().contiguous(), self.message_bias)   # [B, mf]
+        return M.view(B, N, self.mf) + base.unsqueeze(1)
 
     def _sender_vectors(self, afm, bfm, el):
         """(G, gather): what multiplies the edge matrix -- the sender state itself for the plain edge network."""
@@ -194,8 +210,11 @@ class EdgeNetwork(nn.Module):
             table, tableT = self._table(el, reuse)
             if reuse and k in self._msg_cache:
                 return self._msg_cache[k]
-            M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, self.message_bias, el, None, True,
-                                     self.nf, self.mf).view(B, N, self.mf)
+            if typed_dp(self.nf, self.mf) >= 0:
+                M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, self.message_bias, el, None, True,
+                                         self.nf, self.mf).view(B, N, self.mf)
+            else:
+                M = self._head_messages_tc(afm, table, el)
             self._msg_cache[k] = M
             return M
         X = self._trunk(bfm, el, reuse)
@@ -221,8 +240,12 @@ class EdgeNetwork(nn.Module):
             table, tableT = self._table(el, reuse)
             if reuse and k in self._msg_cache:
                 return self._msg_cache[k]
-            M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, None, el, el.edge_w, False,
-                                     self.nf, self.mf).view(B, N, self.mf)
+            if typed_dp(self.nf, self.mf) >= 0:
+                M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, None, el, el.edge_w, False,
+                                         self.nf, self.mf).view(B, N, self.mf)
+            else:
+                M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table, tableT, el, el.edge_w, self.nf,
+                                           self.mf).view(B, N, self.mf)
             self._msg_cache[k] = M
             return M
         X = self._trunk(bfm, el, reuse)
