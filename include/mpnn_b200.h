@@ -116,22 +116,26 @@ int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, co
  * The type-sorted edge list is cut into single-type tiles of <= 128 edges (the plan, device side, no host read);
  * the message function (edge_network.py:42-52) is then a grouped TF32 GEMM with the accumulator in TMEM:
  *   Y[e, 0:N] = alpha_e * Bm[uid_e] (N x K, K contiguous, zero padded to DP x DP) . A[gidx[e], 0:K]
- * forward: A = H, gidx = edge_src, Bm = tableT, K = nf, N = mf; backward (d sender states): A = dM, gidx = edge_dst,
+ * forward: A = H, rows = edge_src, Bm = tableT, K = nf, N = mf; backward (d sender states): A = dM, rows = edge_dst,
  * Bm = table, K = mf, N = nf.  The aggregation (adjacent_message_agg.py:18) is mpnn_segment_sum over row_ptr /
  * (col_ptr, csc_eid).  mpnn_tc_table_grad: dT[u][l][k] = sum_{e of type u} alpha_e H[src_e, l] dM[dst_e, k].
  * mpnn_tc_dp: 64 / 128 / 256, or -1 when the shape is not served (widths <= 32, > 256 or not multiples of 4). */
 int mpnn_tc_dp(int nf, int mf);
 size_t mpnn_tc_plan_bytes(int edge_capacity, int unique_capacity);
-int mpnn_tc_plan(const int* type_ptr, int edge_capacity, int unique_capacity, void* plan, size_t plan_bytes,
+/* plan = tiles + per-position gather rows (edge_src / edge_dst) and weights (edge_w, NULL = 1) of the sorted list */
+int mpnn_tc_plan(const int* type_ptr, const int* type_eid, const int* edge_src, const int* edge_dst,
+                 const float* edge_w, int edge_capacity, int unique_capacity, void* plan, size_t plan_bytes,
                  mpnn_stream_t stream);
-int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid, const int* gidx,
-                      const float* A, int lda, int K, const float* Bm, int DP, const float* alpha, float* Y, int ldy,
-                      int N, mpnn_stream_t stream);
+size_t mpnn_tc_edge_gemm_workspace_bytes(int unique_capacity, int DP);
+/* use_dst: 0 = rows of A are the senders (forward), 1 = the receivers (backward); use_alpha: scale by the plan's
+ * edge weights; workspace holds the pre-swizzled shared-memory image of Bm (one bulk copy per pipeline stage) */
+int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid, int use_dst,
+                      const float* A, int lda, int K, const float* Bm, int DP, int use_alpha, float* Y, int ldy,
+                      int N, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 size_t mpnn_tc_table_grad_workspace_bytes(int unique_capacity, int DP);
-int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid,
-                       const int* edge_src, const int* edge_dst, const float* alpha, const float* H, int nf,
-                       const float* dM, int mf, int DP, float* dT, void* workspace, size_t workspace_bytes,
-                       mpnn_stream_t stream);
+int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity, const float* H, int nf,
+                       const float* dM, int mf, int DP, int use_alpha, float* dT, void* workspace,
+                       size_t workspace_bytes, mpnn_stream_t stream);
 
 /* ---- a1/a2: edge-network trunk = edge_map[:-1] (edge_network.py:14-21,36-37) on compacted rows -------- */
 long long mpnn_edge_trunk_saved_floats(int R, int ef, int n_growth, int P, int n_tied, long long* x_offset, int* ldx);

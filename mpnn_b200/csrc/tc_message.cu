@@ -11,9 +11,11 @@
 // followed by the fixed-order CSR / CSC segmented sums (mpnn_segment_sum) -> no float atomics, bit-reproducible.
 //
 // Kernel anatomy (one persistent CTA per SM, 288 threads):
-//   warps 0-3  producers: gather 128-byte row pieces (coalesced float4 loads, 8 lanes per row) and store them
-//              into shared memory in the canonical 128B-swizzled UMMA layout; generic->async proxy fence;
-//              mbarrier arrive (full[stage]).
+//   warps 0-3  producers: gather 128-byte row pieces with 16-byte cp.async (8 lanes per row, fully coalesced) straight
+//              into the canonical 128B-swizzled UMMA layout in shared memory -- no register staging, so a 4-stage
+//              ring keeps ~64 KB of gathers in flight per SM; completion is tracked by the stage's mbarrier
+//              (cp.async.mbarrier.arrive.noinc).  The B operand (the type's matrix) comes from a pre-swizzled image
+//              of the table with ONE bulk async copy per stage (cp.async.bulk + complete_tx).
 //   warp  4    one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=DP, K=8) with the accumulator in TMEM,
 //              tcgen05.commit releases the stage (empty[stage]) and publishes the accumulator (acc_full).
 //   warps 5-8  epilogue: tcgen05.ld the accumulator (one TMEM lane = one edge row per thread), scale by alpha_e,
@@ -54,6 +56,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (ok) return;
   }
   __trap();
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// 16-byte asynchronous global->shared copy; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// contiguous global->shared bulk copy (TMA engine, no tensor map); bytes are credited to the mbarrier's tx count
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -126,11 +146,12 @@ __device__ __forceinline__ uint32_t swz32(int row4, int chunk) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// tile plan: the type-sorted edge list cut into single-type tiles of <= 128 edges (device side, no host read)
+// tile plan: the type-sorted edge list cut into single-type tiles of <= 128 edges (device side, no host read),
+// plus the per-position gather indices and weights (psrc/pdst/palpha) so the kernels need one index load per row.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_tc_plan_scan(const int* __restrict__ type_ptr, int ntypes, int max_tiles,
                                                        int* __restrict__ tile_off /*[ntypes+1]*/,
-                                                       int* __restrict__ n_tiles) {
+                                                       int* __restrict__ head /*{n_tiles, unit_alpha, 0, 0}*/) {
   __shared__ int buf[1024];
   __shared__ int carry;
   const int tid = threadIdx.x;
@@ -158,7 +179,8 @@ __global__ void __launch_bounds__(1024) k_tc_plan_scan(const int* __restrict__ t
   }
   if (tid == 0) {
     tile_off[ntypes] = carry;
-    *n_tiles = min(carry, max_tiles);
+    head[0] = min(carry, max_tiles);
+    head[1] = 1;  // cleared by k_tc_plan_gather if any edge weight differs from 1
   }
 }
 
@@ -183,21 +205,62 @@ __global__ void __launch_bounds__(256) k_tc_plan_fill(const int* __restrict__ ty
   }
 }
 
+// psrc[p] = edge_src[type_eid[p]], pdst likewise, palpha[p] = edge_w[type_eid[p]] (1 if edge_w is null)
+__global__ void __launch_bounds__(256) k_tc_plan_gather(const int* __restrict__ type_ptr, int ntypes, int cap,
+                                                        const int* __restrict__ type_eid,
+                                                        const int* __restrict__ edge_src,
+                                                        const int* __restrict__ edge_dst,
+                                                        const float* __restrict__ edge_w, int* __restrict__ psrc,
+                                                        int* __restrict__ pdst, float* __restrict__ palpha,
+                                                        int* __restrict__ head) {
+  const int E = min(type_ptr[ntypes], cap);
+  bool unit = true;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < E; p += gridDim.x * 256) {
+    const int e = type_eid[p];
+    psrc[p] = edge_src[e];
+    pdst[p] = edge_dst[e];
+    const float w = edge_w ? edge_w[e] : 1.f;
+    palpha[p] = w;
+    unit = unit && (w == 1.f);
+  }
+  if (!unit) head[1] = 0;
+}
+
 struct TcPlan {
-  const int* n_tiles;
+  const int* head;      // {n_tiles, unit_alpha}
   const int* tile_off;
   const int* tile_type;
   const int* tile_pos;
   const int* tile_cnt;
+  const int* psrc;
+  const int* pdst;
+  const float* palpha;
 };
+
+// Bimg[(u * NKB + kb)][n][chunk ^ (n & 7)][4] = Bm[u][n][kb*32 + chunk*4 + 0..3]: the exact shared-memory image of
+// one K-block of one type's matrix (K-major, 128-byte swizzle), so a stage's B operand is ONE contiguous bulk copy
+__global__ void __launch_bounds__(256) k_tc_swizzle_table(const float* __restrict__ Bm, int ntypes, int DP,
+                                                          float* __restrict__ Bimg) {
+  const int nkb = DP / KB;
+  const long long total = (long long)ntypes * DP * (DP / 4);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c4 = (int)(i % (DP / 4));
+    const int n = (int)((i / (DP / 4)) % DP);
+    const int u = (int)(i / ((long long)DP * (DP / 4)));
+    const int kb = c4 >> 3, chunk = c4 & 7;
+    const float4 v = *reinterpret_cast<const float4*>(Bm + ((size_t)u * DP + n) * DP + c4 * 4);
+    float* dst = Bimg + (((size_t)u * nkb + kb) * DP + n) * KB + ((chunk ^ (n & 7)) << 2);
+    *reinterpret_cast<float4*>(dst) = v;
+  }
+}
 
 struct TcGemm {
   TcPlan plan;
-  const int* type_eid;  // sorted position -> edge id
-  const int* gidx;      // edge id -> row of A
+  const int* type_eid;  // sorted position -> edge id (output row)
+  const int* prow;      // sorted position -> row of A (plan.psrc or plan.pdst)
   const float* A;       // [*, lda]
-  const float* Bm;      // [types][DP][DP]: row n, K contiguous
-  const float* alpha;   // [E] or null
+  const float* Bimg;    // pre-swizzled table image
+  int use_alpha;
   float* Y;             // [E, ldy]
   int lda, K, ldy, N;
 };
@@ -213,7 +276,7 @@ struct GemmCfg {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Y[e, 0:N] = alpha_e * sum_k A[gidx[e], k] * Bm[type(e)][n][k]       (edges in type-sorted tiles)
+// Y[e, 0:N] = alpha_e * sum_k A[row(e), k] * B[type(e)][n][k]       (edges in type-sorted tiles)
 // ---------------------------------------------------------------------------------------------------
 template <int DP>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
@@ -232,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::NSTAGE; ++s) {
-      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(full_bar(s), PRODUCERS + 1);  // 128 cp.async completions + the bulk copy's expect_tx arrival
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -247,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_tiles = *a.plan.n_tiles;
+  const int n_tiles = a.plan.head[0];
   const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
@@ -257,33 +320,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
     // ===================== producers =====================
     const int sub = tid >> 3, chunk = tid & 7;
     int stage = 0, phase = 0;
-    for (int t = t0; t < t1; ++t) {
-      const int u = a.plan.tile_type[t], pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
-      const float* arow[8];
+    int rows_next[8];   // A rows of the NEXT tile (prefetched one tile ahead)
+    auto load_rows = [&](int t, int* rows) {
+      if (t < t1) {
+        const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 16 + sub;
-        int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
-        arow[i] = e >= 0 ? a.A + (size_t)__ldg(a.gidx + e) * a.lda : nullptr;
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 16 + sub;
+          rows[i] = r < cnt ? __ldg(a.prow + pos + r) : -1;
+        }
       }
-      const float* brow = a.Bm + ((size_t)u * DP + sub) * DP;
+    };
+    load_rows(t0, rows_next);
+    for (int t = t0; t < t1; ++t) {
+      const int u = a.plan.tile_type[t];
+      int rows[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rows[i] = rows_next[i];
+      load_rows(t + 1, rows_next);
+      const float* bimg = a.Bimg + (size_t)u * NKB * (DP * KB);
       for (int kb = 0; kb < NKB; ++kb) {
         const int kk = kb * KB + chunk * 4;
-        float4 va[8], vb[DP / 16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          va[i] = (arow[i] != nullptr && kk < a.K) ? ldg4(arow[i] + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < DP / 16; ++i) vb[i] = ldg4(brow + (size_t)i * 16 * DP + kk);
         mbar_wait(empty_bar(stage), phase ^ 1);
-        uint8_t* As = smem + stage * C::STAGE;
-        uint8_t* Bs = As + C::A_BYTES;
+        const uint32_t As = smem_base + stage * C::STAGE;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);
+          bulk_copy(As + C::A_BYTES, bimg + (size_t)kb * (DP * KB), C::B_BYTES, full_bar(stage));
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sts4(As, swz(i * 16 + sub, chunk), va[i]);
-#pragma unroll
-        for (int i = 0; i < DP / 16; ++i) sts4(Bs, swz(i * 16 + sub, chunk), vb[i]);
-        fence_proxy_async();
-        mbar_arrive(full_bar(stage));
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = rows[i] >= 0 && kk < a.K;
+          const float* src = ok ? a.A + (size_t)rows[i] * a.lda + kk : a.A;
+          cp_async16(As + swz(i * 16 + sub, chunk), src, ok ? 16u : 0u);
+        }
+        cp_async_arrive_noinc(full_bar(stage));
         if (++stage == C::NSTAGE) {
           stage = 0;
           phase ^= 1;
@@ -302,6 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
         const uint32_t d = tmem_base + (uint32_t)(acc * DP);
         for (int kb = 0; kb < NKB; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          fence_proxy_async();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE;
           const uint64_t ad = make_sdesc(sa, 16, 1024);
@@ -326,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
       const int i = t - t0, acc = i & 1, use = i >> 1;
       const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
       const int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
-      const float al = (e >= 0 && a.alpha) ? __ldg(a.alpha + e) : 1.f;
+      const float al = (e >= 0 && a.use_alpha) ? __ldg(a.plan.palpha + pos + r) : 1.f;
       mbar_wait(accfull_bar(acc), use & 1);
       tc_fence_after();
       float* yrow = a.Y + (size_t)(e >= 0 ? e : 0) * a.ldy;
@@ -363,17 +434,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
 // A CTA walks a contiguous range of tiles and keeps accumulating in TMEM while the type does not change; each
 // (CTA, type) segment is flushed to partial slot (cta + type) -- strictly increasing along the sorted list --
 // and k_tc_table_reduce sums the slots of a type in fixed order.
+// Unit edge weights (0/1 adjacency, every reference dataset): 16-byte cp.async gathers as in the edge GEMM.
+// General weights: the H rows are scaled by alpha_e in registers on their way to shared memory.
 // ---------------------------------------------------------------------------------------------------
 struct TcGrad {
   TcPlan plan;
-  const int* type_eid;
-  const int* edge_src;
-  const int* edge_dst;
-  const float* alpha;
   const float* H;    // [*, nf]
   const float* dM;   // [*, mf]
   float* partial;    // [slots][DP][DP]
   int nf, mf;
+  int use_alpha;     // 0: all weights are 1 (HEAD form); 1: the plan's edge weights
 };
 
 template <int DP>
@@ -421,7 +491,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_tiles = *a.plan.n_tiles;
+  const int n_tiles = a.plan.head[0];
+  const bool unit_alpha = !a.use_alpha || a.plan.head[1] != 0;
   const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
@@ -439,53 +510,75 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int r = s0 + sub + 16 * h;
-          const int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
-          hrow[h] = e >= 0 ? a.H + (size_t)__ldg(a.edge_src + e) * a.nf : nullptr;
-          mrow[h] = e >= 0 ? a.dM + (size_t)__ldg(a.edge_dst + e) * a.mf : nullptr;
-          al[h] = (e >= 0 && a.alpha) ? __ldg(a.alpha + e) : 1.f;
+          const bool ok = r < cnt;
+          hrow[h] = ok ? a.H + (size_t)__ldg(a.plan.psrc + pos + r) * a.nf : nullptr;
+          mrow[h] = ok ? a.dM + (size_t)__ldg(a.plan.pdst + pos + r) * a.mf : nullptr;
+          al[h] = (ok && !unit_alpha) ? __ldg(a.plan.palpha + pos + r) : 1.f;
         }
         mbar_wait(empty_bar(stage), phase ^ 1);
-        uint8_t* As = smem + stage * C::STAGE;
-        uint8_t* Bs = As + C::A_BYTES;
-        // A: H rows (scaled by alpha), MP/32 column blocks x 2 edges per thread
-        {
-          float4 v[2 * C::MP / 32];
+        const uint32_t As = smem_base + stage * C::STAGE;
+        const uint32_t Bs = As + C::A_BYTES;
+        if (unit_alpha) {
 #pragma unroll
           for (int mb = 0; mb < C::MP / 32; ++mb)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int col = mb * 32 + chunk * 4;
-              float4 x = (hrow[h] != nullptr && col < a.nf) ? ldg4(hrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-              v[mb * 2 + h] = make_float4(al[h] * x.x, al[h] * x.y, al[h] * x.z, al[h] * x.w);
-            }
-#pragma unroll
-          for (int mb = 0; mb < C::MP / 32; ++mb)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = sub + 16 * h;  // edge within the stage
-              sts4(As, (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[mb * 2 + h]);
-            }
-        }
-        // B: dM rows
-        {
-          float4 v[2 * DP / 32];
-#pragma unroll
-          for (int nb = 0; nb < DP / 32; ++nb)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = nb * 32 + chunk * 4;
-              v[nb * 2 + h] = (mrow[h] != nullptr && col < a.mf) ? ldg4(mrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const int r = sub + 16 * h, col = mb * 32 + chunk * 4;
+              const bool ok = hrow[h] != nullptr && col < a.nf;
+              cp_async16(As + (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk),
+                         ok ? hrow[h] + col : a.H, ok ? 16u : 0u);
             }
 #pragma unroll
           for (int nb = 0; nb < DP / 32; ++nb)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              const int r = sub + 16 * h;
-              sts4(Bs, (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[nb * 2 + h]);
+              const int r = sub + 16 * h, col = nb * 32 + chunk * 4;
+              const bool ok = mrow[h] != nullptr && col < a.mf;
+              cp_async16(Bs + (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk),
+                         ok ? mrow[h] + col : a.dM, ok ? 16u : 0u);
             }
+          cp_async_arrive_noinc(full_bar(stage));
+        } else {
+          uint8_t* Ag = smem + stage * C::STAGE;
+          uint8_t* Bg = Ag + C::A_BYTES;
+          {
+            float4 v[2 * C::MP / 32];
+#pragma unroll
+            for (int mb = 0; mb < C::MP / 32; ++mb)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int col = mb * 32 + chunk * 4;
+                float4 x = (hrow[h] != nullptr && col < a.nf) ? ldg4(hrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[mb * 2 + h] = make_float4(al[h] * x.x, al[h] * x.y, al[h] * x.z, al[h] * x.w);
+              }
+#pragma unroll
+            for (int mb = 0; mb < C::MP / 32; ++mb)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int r = sub + 16 * h;
+                sts4(Ag, (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[mb * 2 + h]);
+              }
+          }
+          {
+            float4 v[2 * DP / 32];
+#pragma unroll
+            for (int nb = 0; nb < DP / 32; ++nb)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int col = nb * 32 + chunk * 4;
+                v[nb * 2 + h] = (mrow[h] != nullptr && col < a.mf) ? ldg4(mrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+            for (int nb = 0; nb < DP / 32; ++nb)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int r = sub + 16 * h;
+                sts4(Bg, (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[nb * 2 + h]);
+              }
+          }
+          fence_proxy_async();
+          mbar_arrive(full_bar(stage));
         }
-        fence_proxy_async();
-        mbar_arrive(full_bar(stage));
         if (++stage == C::NSTAGE) {
           stage = 0;
           phase ^= 1;
@@ -512,6 +605,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
         }
         for (int s0 = 0; s0 < cnt; s0 += C::KST) {
           mbar_wait(full_bar(stage), phase);
+          fence_proxy_async();
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE;
 #pragma unroll
@@ -577,7 +671,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
 __global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int grid_ctas, int ntypes, int elems,
                                                          const float* __restrict__ partial, float* __restrict__ dT) {
   const int u = blockIdx.y;
-  const int n_tiles = *plan.n_tiles;
+  const int n_tiles = plan.head[0];
   const int per = (n_tiles + grid_ctas - 1) / grid_ctas;
   const int f = plan.tile_off[u], l = (u < ntypes ? plan.tile_off[u + 1] : f);
   int c0 = 0, c1 = -1;
@@ -601,26 +695,37 @@ int tc_grid() { return mpnn_num_sms(); }
 int tc_max_tiles(int edge_capacity, int ntypes) { return edge_capacity / TILE + ntypes + 1; }
 
 struct PlanBuf {
-  int* n_tiles;
+  int* head;
   int* tile_off;
   int* tile_type;
   int* tile_pos;
   int* tile_cnt;
+  int* psrc;
+  int* pdst;
+  float* palpha;
 };
-size_t plan_bytes(int edge_capacity, int ntypes) {
+size_t plan_words(int edge_capacity, int ntypes) {
   const size_t mt = (size_t)tc_max_tiles(edge_capacity, ntypes);
-  return align_up(((size_t)ntypes + 2 + 3 * mt + 4) * sizeof(int), 256);
+  const size_t cap = (size_t)(edge_capacity > 0 ? edge_capacity : 1);
+  return 4 + ((size_t)ntypes + 2) + 3 * mt + 3 * cap;
 }
 PlanBuf carve_plan(void* ws, int edge_capacity, int ntypes) {
   const size_t mt = (size_t)tc_max_tiles(edge_capacity, ntypes);
+  const size_t cap = (size_t)(edge_capacity > 0 ? edge_capacity : 1);
   int* p = (int*)ws;
   PlanBuf b;
-  b.n_tiles = p;
+  b.head = p;
   b.tile_off = p + 4;
   b.tile_type = b.tile_off + ntypes + 2;
   b.tile_pos = b.tile_type + mt;
   b.tile_cnt = b.tile_pos + mt;
+  b.psrc = b.tile_cnt + mt;
+  b.pdst = b.psrc + cap;
+  b.palpha = reinterpret_cast<float*>(b.pdst + cap);
   return b;
+}
+TcPlan as_plan(const PlanBuf& b) {
+  return TcPlan{b.head, b.tile_off, b.tile_type, b.tile_pos, b.tile_cnt, b.psrc, b.pdst, b.palpha};
 }
 
 template <typename K>
@@ -636,42 +741,68 @@ extern "C" {
 int mpnn_tc_dp(int nf, int mf) { return tc_dp(nf, mf); }
 
 // plan buffer: the type-sorted edge list cut into single-type tiles; built once per edge list
-size_t mpnn_tc_plan_bytes(int edge_capacity, int unique_capacity) { return plan_bytes(edge_capacity, unique_capacity + 1); }
+size_t mpnn_tc_plan_bytes(int edge_capacity, int unique_capacity) {
+  return align_up(plan_words(edge_capacity, unique_capacity + 1) * sizeof(int), 256);
+}
 
-int mpnn_tc_plan(const int* type_ptr, int edge_capacity, int unique_capacity, void* plan, size_t plan_bytes_,
+int mpnn_tc_plan(const int* type_ptr, const int* type_eid, const int* edge_src, const int* edge_dst,
+                 const float* edge_w, int edge_capacity, int unique_capacity, void* plan, size_t plan_bytes_,
                  cudaStream_t stream) {
   const int ntypes = unique_capacity + 1;   // type_ptr has unique_capacity+1 entries: the last "type" is empty
-  MPNN_REQUIRE(type_ptr && plan, MPNN_ERR_ARG, "tc_plan: null argument");
-  MPNN_REQUIRE(plan_bytes_ >= plan_bytes(edge_capacity, ntypes), MPNN_ERR_WORKSPACE, "tc_plan: plan buffer too small");
+  MPNN_REQUIRE(type_ptr && type_eid && edge_src && edge_dst && plan, MPNN_ERR_ARG, "tc_plan: null argument");
+  MPNN_REQUIRE(plan_bytes_ >= mpnn_tc_plan_bytes(edge_capacity, unique_capacity), MPNN_ERR_WORKSPACE,
+               "tc_plan: plan buffer too small");
   PlanBuf b = carve_plan(plan, edge_capacity, ntypes);
   // types 0..unique_capacity-1 own [type_ptr[u], type_ptr[u+1]); entry `unique_capacity` closes the last one
   const int max_tiles = tc_max_tiles(edge_capacity, ntypes);
-  k_tc_plan_scan<<<1, 1024, 0, stream>>>(type_ptr, unique_capacity, max_tiles, b.tile_off, b.n_tiles);
+  k_tc_plan_scan<<<1, 1024, 0, stream>>>(type_ptr, unique_capacity, max_tiles, b.tile_off, b.head);
   MPNN_CHECK_LAUNCH("k_tc_plan_scan");
   int fgrid = ceil_div(max_tiles, 256);
   if (fgrid > 4 * mpnn_num_sms()) fgrid = 4 * mpnn_num_sms();
-  k_tc_plan_fill<<<fgrid, 256, 0, stream>>>(type_ptr, unique_capacity, b.tile_off, b.n_tiles, b.tile_type, b.tile_pos,
+  k_tc_plan_fill<<<fgrid, 256, 0, stream>>>(type_ptr, unique_capacity, b.tile_off, b.head, b.tile_type, b.tile_pos,
                                             b.tile_cnt);
   MPNN_CHECK_LAUNCH("k_tc_plan_fill");
+  int ggrid = ceil_div(edge_capacity > 0 ? edge_capacity : 1, 256);
+  if (ggrid > 8 * mpnn_num_sms()) ggrid = 8 * mpnn_num_sms();
+  k_tc_plan_gather<<<ggrid, 256, 0, stream>>>(type_ptr, unique_capacity, edge_capacity, type_eid, edge_src, edge_dst,
+                                              edge_w, b.psrc, b.pdst, b.palpha, b.head);
+  MPNN_CHECK_LAUNCH("k_tc_plan_gather");
   return MPNN_OK;
 }
 
-// Y[e, 0:N] = alpha_e * Bm[uid_e] (N x K, K contiguous, padded to DP x DP) . A[gidx[e], 0:K]
-// forward: A = H, gidx = edge_src, Bm = tableT, K = nf, N = mf;  backward: A = dM, gidx = edge_dst, Bm = table.
-int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid, const int* gidx,
-                      const float* A, int lda, int K, const float* Bm, int DP, const float* alpha, float* Y, int ldy,
-                      int N, cudaStream_t stream) {
-  MPNN_REQUIRE(plan && type_eid && gidx && A && Bm && Y, MPNN_ERR_ARG, "tc_edge_gemm: null argument");
+size_t mpnn_tc_edge_gemm_workspace_bytes(int unique_capacity, int DP) {
+  return (size_t)(unique_capacity + 1) * DP * DP * sizeof(float);
+}
+
+// Y[e, 0:N] = alpha_e * Bm[uid_e] (N x K, K contiguous, padded to DP x DP) . A[row_e, 0:K]
+// forward (use_dst = 0): A = H, row_e = src_e, Bm = tableT, K = nf, N = mf;
+// backward (use_dst = 1): A = dM, row_e = dst_e, Bm = table, K = mf, N = nf.
+int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid, int use_dst,
+                      const float* A, int lda, int K, const float* Bm, int DP, int use_alpha, float* Y, int ldy,
+                      int N, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(plan && type_eid && A && Bm && Y && workspace, MPNN_ERR_ARG, "tc_edge_gemm: null argument");
   MPNN_REQUIRE((K & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldy & 3) == 0 && K <= DP && N <= DP,
                MPNN_ERR_UNSUPPORTED, "tc_edge_gemm: widths must be multiples of 4 and <= DP");
+  MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED,
+               "tc_edge_gemm: DP must be 64, 128 or 256 (got %d)", DP);
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_edge_gemm_workspace_bytes(unique_capacity, DP), MPNN_ERR_WORKSPACE,
+               "tc_edge_gemm: workspace too small");
   PlanBuf b = carve_plan(const_cast<void*>(plan), edge_capacity, unique_capacity + 1);
+  float* img = (float*)workspace;
+  {
+    const long long total = (long long)(unique_capacity + 1) * DP * (DP / 4);
+    int g = ceil_div(total, 256);
+    if (g > 8 * mpnn_num_sms()) g = 8 * mpnn_num_sms();
+    k_tc_swizzle_table<<<g, 256, 0, stream>>>(Bm, unique_capacity + 1, DP, img);
+    MPNN_CHECK_LAUNCH("k_tc_swizzle_table");
+  }
   TcGemm a;
-  a.plan = TcPlan{b.n_tiles, b.tile_off, b.tile_type, b.tile_pos, b.tile_cnt};
+  a.plan = as_plan(b);
   a.type_eid = type_eid;
-  a.gidx = gidx;
+  a.prow = use_dst ? b.pdst : b.psrc;
   a.A = A;
-  a.Bm = Bm;
-  a.alpha = alpha;
+  a.Bimg = img;
+  a.use_alpha = use_alpha;
   a.Y = Y;
   a.lda = lda;
   a.K = K;
@@ -687,12 +818,10 @@ int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, 
       MPNN_REQUIRE(set_smem(k_tc_edge_gemm<128>, GemmCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_edge_gemm: smem attribute");
       k_tc_edge_gemm<128><<<grid, THREADS, GemmCfg<128>::SMEM, stream>>>(a);
       break;
-    case 256:
+    default:
       MPNN_REQUIRE(set_smem(k_tc_edge_gemm<256>, GemmCfg<256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_edge_gemm: smem attribute");
       k_tc_edge_gemm<256><<<grid, THREADS, GemmCfg<256>::SMEM, stream>>>(a);
       break;
-    default:
-      MPNN_REQUIRE(false, MPNN_ERR_UNSUPPORTED, "tc_edge_gemm: DP must be 64, 128 or 256 (got %d)", DP);
   }
   MPNN_CHECK_LAUNCH("k_tc_edge_gemm");
   return MPNN_OK;
@@ -703,27 +832,26 @@ size_t mpnn_tc_table_grad_workspace_bytes(int unique_capacity, int DP) {
 }
 
 // dT [(unique_capacity+1)][DP][DP]:  dT[u][l][k] = sum_{e of type u} alpha_e H[src_e, l] dM[dst_e, k]
-int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity, const int* type_eid,
-                       const int* edge_src, const int* edge_dst, const float* alpha, const float* H, int nf,
-                       const float* dM, int mf, int DP, float* dT, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream) {
-  MPNN_REQUIRE(plan && type_eid && edge_src && edge_dst && H && dM && dT, MPNN_ERR_ARG, "tc_table_grad: null argument");
+// (alpha = the edge weights the plan was built with if use_alpha, else 1)
+int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity, const float* H, int nf,
+                       const float* dM, int mf, int DP, int use_alpha, float* dT, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(plan && H && dM && dT && workspace, MPNN_ERR_ARG, "tc_table_grad: null argument");
   MPNN_REQUIRE((nf & 3) == 0 && (mf & 3) == 0 && nf <= DP && mf <= DP, MPNN_ERR_UNSUPPORTED,
                "tc_table_grad: widths must be multiples of 4 and <= DP");
+  MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED,
+               "tc_table_grad: DP must be 64, 128 or 256 (got %d)", DP);
   MPNN_REQUIRE(workspace_bytes >= mpnn_tc_table_grad_workspace_bytes(unique_capacity, DP), MPNN_ERR_WORKSPACE,
                "tc_table_grad: workspace too small");
   PlanBuf b = carve_plan(const_cast<void*>(plan), edge_capacity, unique_capacity + 1);
   TcGrad a;
-  a.plan = TcPlan{b.n_tiles, b.tile_off, b.tile_type, b.tile_pos, b.tile_cnt};
-  a.type_eid = type_eid;
-  a.edge_src = edge_src;
-  a.edge_dst = edge_dst;
-  a.alpha = alpha;
+  a.plan = as_plan(b);
   a.H = H;
   a.dM = dM;
   a.partial = (float*)workspace;
   a.nf = nf;
   a.mf = mf;
+  a.use_alpha = use_alpha;
   const int grid = tc_grid();
   switch (DP) {
     case 64:
@@ -734,12 +862,10 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
       MPNN_REQUIRE(set_smem(k_tc_table_grad<128>, GradCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_table_grad: smem attribute");
       k_tc_table_grad<128><<<grid, THREADS, GradCfg<128>::SMEM, stream>>>(a);
       break;
-    case 256:
+    default:
       MPNN_REQUIRE(set_smem(k_tc_table_grad<256>, GradCfg<256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_table_grad: smem attribute");
       k_tc_table_grad<256><<<grid, THREADS, GradCfg<256>::SMEM, stream>>>(a);
       break;
-    default:
-      MPNN_REQUIRE(false, MPNN_ERR_UNSUPPORTED, "tc_table_grad: DP must be 64, 128 or 256 (got %d)", DP);
   }
   MPNN_CHECK_LAUNCH("k_tc_table_grad");
   dim3 rgrid(ceil_div(DP * DP, 256 * 4), unique_capacity + 1);

@@ -667,34 +667,35 @@ class TypedMessageTCFn(torch.autograd.Function):
     M[i] = sum_{e in E(i)} alpha_e T[uid_e]^T H[src_e] as a grouped TF32 GEMM over the type-sorted edge tiles
     (tcgen05.mma, accumulator in TMEM) + the fixed-order CSR segmented sum.  Backward: the same GEMM kernel on the
     gathered message gradients + CSC segmented sum, and dT[u] = sum_e alpha_e H[src_e] (x) dM[dst_e] with K = edges.
+    alpha is the edge list's own weight (adj value) when weighted is True, else 1.
     The HEAD-form extras (edge_network.py:50-51) are composed around this op in modules.EdgeNetwork."""
 
     @staticmethod
-    def forward(ctx, H, table, tableT, el, alpha, nf, mf):
+    def forward(ctx, H, table, tableT, el, weighted, nf, mf):
         lib = _lib.load()
         _need_cuda(H, table)
         H, table, tableT = f32c(H), f32c(table), f32c(tableT)
-        alpha_c = f32c(alpha) if alpha is not None else None
         ti = el.typed()
         DP = table.shape[-1]
         dev = H.device
         plan = ti.tc_plan(el)
         Y = torch.empty(max(el.Ecap, 1), mf, dtype=torch.float32, device=dev)
-        check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), ptr(el.edge_src), ptr(H), nf, nf,
-                                    ptr(tableT), DP, ptr(alpha_c), ptr(Y), mf, mf, stream()), "tc_edge_gemm")
+        ws = workspace(lib.mpnn_tc_edge_gemm_workspace_bytes(ti.Ucap, DP), dev)
+        check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), 0, ptr(H), nf, nf, ptr(tableT), DP,
+                                    1 if weighted else 0, ptr(Y), mf, mf, ptr(ws), ws.numel(), stream()), "tc_edge_gemm")
         M = torch.empty(el.n_rows, mf, dtype=torch.float32, device=dev)
         check(lib.mpnn_segment_sum(ptr(Y), ptr(el.row_ptr), None, el.n_rows, mf, mf, ptr(M), mf, 0, 1.0, stream()),
               "segment_sum")
-        ctx.save_for_backward(H, table, alpha_c)
-        ctx.meta = (el, nf, mf, DP)
+        ctx.save_for_backward(H, table)
+        ctx.meta = (el, nf, mf, DP, bool(weighted))
         return M
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dM):
         lib = _lib.load()
-        H, table, alpha = ctx.saved_tensors
-        el, nf, mf, DP = ctx.meta
+        H, table = ctx.saved_tensors
+        el, nf, mf, DP, weighted = ctx.meta
         ti = el.typed()
         dev = H.device
         dM = f32c(dM)
@@ -702,15 +703,16 @@ class TypedMessageTCFn(torch.autograd.Function):
         dH = dT = None
         if ctx.needs_input_grad[0]:
             dG = torch.empty(max(el.Ecap, 1), nf, dtype=torch.float32, device=dev)
-            check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), ptr(el.edge_dst), ptr(dM), mf, mf,
-                                        ptr(table), DP, ptr(alpha), ptr(dG), nf, nf, stream()), "tc_edge_gemm")
+            ws = workspace(lib.mpnn_tc_edge_gemm_workspace_bytes(ti.Ucap, DP), dev)
+            check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), 1, ptr(dM), mf, mf, ptr(table), DP,
+                                        1 if weighted else 0, ptr(dG), nf, nf, ptr(ws), ws.numel(), stream()),
+                  "tc_edge_gemm")
             dH = torch.empty_like(H)
             check(lib.mpnn_segment_sum(ptr(dG), ptr(el.col_ptr), ptr(el.csc_eid), el.n_rows, nf, nf, ptr(dH), nf, 0,
                                        1.0, stream()), "segment_sum")
         if ctx.needs_input_grad[1]:
             dT = torch.empty_like(table)
             ws = workspace(lib.mpnn_tc_table_grad_workspace_bytes(ti.Ucap, DP), dev)
-            check(lib.mpnn_tc_table_grad(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), ptr(el.edge_src),
-                                         ptr(el.edge_dst), ptr(alpha), ptr(H), nf, ptr(dM), mf, DP, ptr(dT), ptr(ws),
-                                         ws.numel(), stream()), "tc_table_grad")
+            check(lib.mpnn_tc_table_grad(ptr(plan), el.Ecap, ti.Ucap, ptr(H), nf, ptr(dM), mf, DP, 1 if weighted else 0,
+                                         ptr(dT), ptr(ws), ws.numel(), stream()), "tc_table_grad")
         return dH, dT, None, None, None, None, None

@@ -137,8 +137,9 @@ class TypedInfo(object):
             if self.type_ptr is None:
                 raise RuntimeError("mpnn_b200: the tensor-core typed path needs the type-sorted edge list")
             plan = _lib.workspace(lib.mpnn_tc_plan_bytes(el.Ecap, self.Ucap), self.uid.device)
-            _lib.check(lib.mpnn_tc_plan(_lib.ptr(self.type_ptr), el.Ecap, self.Ucap, _lib.ptr(plan), plan.numel(),
-                                        _lib.stream()), "tc_plan")
+            _lib.check(lib.mpnn_tc_plan(_lib.ptr(self.type_ptr), _lib.ptr(self.type_eid), _lib.ptr(el.edge_src),
+                                        _lib.ptr(el.edge_dst), _lib.ptr(el.edge_w), el.Ecap, self.Ucap, _lib.ptr(plan),
+                                        plan.numel(), _lib.stream()), "tc_plan")
             self._tc_plan = plan
         return self._tc_plan
 

@@ -186,7 +186,7 @@ class EdgeNetwork(nn.Module):
         T0 = table[z]                                            # [DP, DP], T0[l][k]
         table_h = table - T0.unsqueeze(0)
         tableT_h = table_h.detach().transpose(1, 2).contiguous()
-        M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table_h, tableT_h, el, None, self.nf, self.mf)
+        M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table_h, tableT_h, el, False, self.nf, self.mf)
         S = afm.sum(dim=1)                                       # [B, nf]
         base = LinearFn.apply(S, T0[:self.nf, :self.mf].t().contiguous(), self.message_bias)   # [B, mf]
         return M.view(B, N, self.mf) + base.unsqueeze(1)
@@ -244,7 +244,7 @@ class EdgeNetwork(nn.Module):
                 M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, None, el, el.edge_w, False,
                                          self.nf, self.mf).view(B, N, self.mf)
             else:
-                M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table, tableT, el, el.edge_w, self.nf,
+                M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table, tableT, el, True, self.nf,
                                            self.mf).view(B, N, self.mf)
             self._msg_cache[k] = M
             return M

@@ -61,7 +61,7 @@ def test_tc_kernels_against_fp64(dev, dims, weighted):
     tableT = table.detach().transpose(1, 2).contiguous()
     H = torch.randn(el.n_rows, nf, generator=g).to(dev).requires_grad_(True)
     cot = torch.randn(el.n_rows, mf, generator=g).to(dev)
-    M = TypedMessageTCFn.apply(H, table, tableT, el, el.edge_w, nf, mf)
+    M = TypedMessageTCFn.apply(H, table, tableT, el, True, nf, mf)
     (M * cot).sum().backward()
 
     H64 = H.detach().double().requires_grad_(True)
