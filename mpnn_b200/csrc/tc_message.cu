@@ -271,7 +271,8 @@ struct GemmCfg {
   static constexpr int B_BYTES = DP * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = 4;
-  static constexpr int SMEM = NSTAGE * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;  // per epilogue warp: 32 rows x 32 columns, row stride 33
+  static constexpr int SMEM = NSTAGE * STAGE + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
   static constexpr int TCOLS = 2 * DP;  // double-buffered accumulator
 };
 
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
   using C = GemmCfg<DP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  float* epi = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE + C::EPI_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
@@ -391,29 +393,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
     }
   } else {
     // ===================== epilogue =====================
+    // One TMEM lane (= one edge row) per thread comes out of tcgen05.ld; storing it as is would touch 32 different
+    // 128-byte lines per warp instruction.  Each warp transposes its 32 x 32 block through shared memory so that
+    // 8 lanes write one row's 128 contiguous bytes (4 rows per instruction).
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     const int r = q * 32 + lane;
+    float* tb = epi + q * (32 * 33);
+    const int orow = lane >> 3, ocol = (lane & 7) * 4;
     for (int t = t0; t < t1; ++t) {
       const int i = t - t0, acc = i & 1, use = i >> 1;
       const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
       const int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
       const float al = (e >= 0 && a.use_alpha) ? __ldg(a.plan.palpha + pos + r) : 1.f;
+      int erow[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) erow[it] = __shfl_sync(0xffffffffu, e, it * 4 + orow);
       mbar_wait(accfull_bar(acc), use & 1);
       tc_fence_after();
-      float* yrow = a.Y + (size_t)(e >= 0 ? e : 0) * a.ldy;
 #pragma unroll 1
       for (int c0 = 0; c0 < DP; c0 += 32) {
         if (c0 >= a.N) break;
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DP + c0), v);
-        if (e >= 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (c0 + 4 * j < a.N)
-              *reinterpret_cast<float4*>(yrow + c0 + 4 * j) =
-                  make_float4(al * v[4 * j], al * v[4 * j + 1], al * v[4 * j + 2], al * v[4 * j + 3]);
+        for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = al * v[c];
+        __syncwarp();
+        if (c0 + ocol < a.N) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const float* p = tb + (it * 4 + orow) * 33 + ocol;
+            if (erow[it] >= 0)
+              *reinterpret_cast<float4*>(a.Y + (size_t)erow[it] * a.ldy + c0 + ocol) = make_float4(p[0], p[1], p[2], p[3]);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(accempty_bar(acc));
@@ -450,11 +463,12 @@ template <int DP>
 struct GradCfg {
   static constexpr int MP = DP < 128 ? 128 : DP;  // UMMA M is 128: narrower tables are zero padded
   static constexpr int MB = MP / 128;
-  static constexpr int KST = 32;                  // edges per stage
+  static constexpr int KST = DP == 256 ? 32 : 64;  // edges per stage
+  static constexpr int EPT = KST / 16;             // edges per producer thread and stage
   static constexpr int A_BYTES = KST * MP * 4;
   static constexpr int B_BYTES = KST * DP * 4;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = DP == 256 ? 3 : 4;
+  static constexpr int NSTAGE = DP == 64 ? 4 : 3;
   static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
   static constexpr int TCOLS = MB * DP < 32 ? 32 : MB * DP;
   static constexpr uint32_t SBO = 512;               // between [4 x 32] atoms along K (groups of 4 edges)
@@ -499,16 +513,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
 
   if (warp < 4) {
     // ===================== producers =====================
-    const int sub = tid >> 3, chunk = tid & 7;   // sub: 0..15 -> edges sub and sub+16 of the stage
+    const int sub = tid >> 3, chunk = tid & 7;   // sub: 0..15 -> edges sub, sub+16, ... of the stage
     int stage = 0, phase = 0;
     for (int t = t0; t < t1; ++t) {
       const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
       for (int s0 = 0; s0 < cnt; s0 += C::KST) {
-        const float* hrow[2];
-        const float* mrow[2];
-        float al[2];
+        const float* hrow[C::EPT];
+        const float* mrow[C::EPT];
+        float al[C::EPT];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < C::EPT; ++h) {
           const int r = s0 + sub + 16 * h;
           const bool ok = r < cnt;
           hrow[h] = ok ? a.H + (size_t)__ldg(a.plan.psrc + pos + r) * a.nf : nullptr;
@@ -522,7 +536,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
 #pragma unroll
           for (int mb = 0; mb < C::MP / 32; ++mb)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < C::EPT; ++h) {
               const int r = sub + 16 * h, col = mb * 32 + chunk * 4;
               const bool ok = hrow[h] != nullptr && col < a.nf;
               cp_async16(As + (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk),
@@ -531,7 +545,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
 #pragma unroll
           for (int nb = 0; nb < DP / 32; ++nb)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < C::EPT; ++h) {
               const int r = sub + 16 * h, col = nb * 32 + chunk * 4;
               const bool ok = mrow[h] != nullptr && col < a.mf;
               cp_async16(Bs + (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk),
@@ -542,38 +556,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
           uint8_t* Ag = smem + stage * C::STAGE;
           uint8_t* Bg = Ag + C::A_BYTES;
           {
-            float4 v[2 * C::MP / 32];
+            float4 v[C::EPT * C::MP / 32];
 #pragma unroll
             for (int mb = 0; mb < C::MP / 32; ++mb)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
+              for (int h = 0; h < C::EPT; ++h) {
                 const int col = mb * 32 + chunk * 4;
                 float4 x = (hrow[h] != nullptr && col < a.nf) ? ldg4(hrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[mb * 2 + h] = make_float4(al[h] * x.x, al[h] * x.y, al[h] * x.z, al[h] * x.w);
+                v[mb * C::EPT + h] = make_float4(al[h] * x.x, al[h] * x.y, al[h] * x.z, al[h] * x.w);
               }
 #pragma unroll
             for (int mb = 0; mb < C::MP / 32; ++mb)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
+              for (int h = 0; h < C::EPT; ++h) {
                 const int r = sub + 16 * h;
-                sts4(Ag, (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[mb * 2 + h]);
+                sts4(Ag, (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[mb * C::EPT + h]);
               }
           }
           {
-            float4 v[2 * DP / 32];
+            float4 v[C::EPT * DP / 32];
 #pragma unroll
             for (int nb = 0; nb < DP / 32; ++nb)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
+              for (int h = 0; h < C::EPT; ++h) {
                 const int col = nb * 32 + chunk * 4;
-                v[nb * 2 + h] = (mrow[h] != nullptr && col < a.mf) ? ldg4(mrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[nb * C::EPT + h] = (mrow[h] != nullptr && col < a.mf) ? ldg4(mrow[h] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
             for (int nb = 0; nb < DP / 32; ++nb)
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
+              for (int h = 0; h < C::EPT; ++h) {
                 const int r = sub + 16 * h;
-                sts4(Bg, (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[nb * 2 + h]);
+                sts4(Bg, (uint32_t)nb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk), v[nb * C::EPT + h]);
               }
           }
           fence_proxy_async();
