@@ -90,6 +90,7 @@ int mpnn_table_from_flat(const float* flat, int R, int nf, int mf, float* table,
 int mpnn_table_to_flat(const float* dT, int R, int nf, int mf, float* dflat, mpnn_stream_t stream);
 /* fused growth layers + n_tied tied layers + last Linear on R distinct rows (trunk width P <= 64) */
 int mpnn_enet_supported(int ef, int n_growth, int P);
+int mpnn_enet_max_dp(void); /* widest padded feature width (64) the fused kernel serves */
 long long mpnn_enet_saved_floats(int R, int n_growth, int n_tied);
 size_t mpnn_enet_workspace_bytes(int R, int ef, int n_growth, int P);
 int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* const* growth_w,

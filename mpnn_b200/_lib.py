@@ -37,6 +37,7 @@ SIGNATURES = {
     "mpnn_table_from_flat": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "mpnn_table_to_flat": (_I, [_P, _I, _I, _I, _P, _P]),
     "mpnn_enet_supported": (_I, [_I, _I, _I]),
+    "mpnn_enet_max_dp": (_I, []),
     "mpnn_enet_saved_floats": (_L, [_I, _I, _I]),
     "mpnn_enet_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "mpnn_enet_fwd": (_I, [_P, _I, _I, _I, _PP, _PP, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P]),

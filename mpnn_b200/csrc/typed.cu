@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
   __shared__ __align__(16) float Ap[2][PW];      // input activation of the current layer
   __shared__ __align__(16) float dAs[PW];        // un-masked gradient w.r.t. the tied input
   __shared__ float red4[4][PW];
+  extern __shared__ __align__(16) float As[];    // [G + L + 1][PW]: every saved activation of the current row
   const int tid = threadIdx.x;
   const int i_ = tid >> 2, q = tid & 3;          // (output index, split lane) of the dA dot products
   const int og = tid >> 4, ig = tid & 15;        // dW micro-tile
@@ -498,6 +499,15 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
   const int nslots = n.G + n.L + 1;
   for (int row = blockIdx.x; row < n.R; row += gridDim.x) {
     __syncthreads();
+    // all saved activations of the row -> shared memory with one wave of 16-byte async copies (the per-layer
+    // loads of the 52-layer chain would otherwise pay one L2/HBM latency each); overlapped with the dx pre-pass
+    for (int idx = tid; idx < nslots * (PW / 4); idx += 256) {
+      const int slot = idx / (PW / 4), c4 = idx - slot * (PW / 4);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(As + slot * PW + c4 * 4);
+      const float* src = acts + ((size_t)slot * n.R + row) * PW + c4 * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // dx[p] = sum_f dT[row][l][k] W_last[f, p]   (f = k*nf + l), f split over the 4 warp pairs
     {
       const int p = tid & 63, part_f = tid >> 6;
@@ -518,19 +528,20 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
       }
       red4[part_f][p] = acc;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (tid < PW) {
       const float g = (red4[0][tid] + red4[1][tid]) + (red4[2][tid] + red4[3][tid]);
-      const float aout = acts[((size_t)(nslots - 1) * n.R + row) * PW + tid];
+      const float aout = As[(nslots - 1) * PW + tid];
       D[0][tid] = aout > 0.f ? g : 0.f;
-      Ap[0][tid] = acts[((size_t)(nslots - 2) * n.R + row) * PW + tid];
+      Ap[0][tid] = As[(nslots - 2) * PW + tid];
     }
     __syncthreads();
     int cur = 0;
     for (int l = n.L; l >= 1; --l) {
       // slot of this layer's input: G + l - 1; prefetch the input of the NEXT (lower) layer: slot G + l - 2
       float pre = 0.f;
-      if (q == 0 && l >= 2) pre = acts[((size_t)(n.G + l - 2) * n.R + row) * PW + i_];
+      if (q == 0 && l >= 2) pre = As[(n.G + l - 2) * PW + i_];
       {
         float4 d4 = *reinterpret_cast<const float4*>(&D[cur][og * 4]);
         float4 a4 = *reinterpret_cast<const float4*>(&Ap[cur][ig * 4]);
@@ -569,9 +580,9 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
       const int gin = n.gin[g], gout = n.gout[g];
       // delta and input activation of this layer
       if (tid < PW) {
-        const float aout = acts[((size_t)(g + 1) * n.R + row) * PW + tid];
+        const float aout = As[(g + 1) * PW + tid];
         D[0][tid] = (tid < gout && aout > 0.f) ? dAs[tid] : 0.f;
-        Ap[0][tid] = acts[((size_t)g * n.R + row) * PW + tid];
+        Ap[0][tid] = As[g * PW + tid];
       }
       __syncthreads();
       for (int e = tid; e < gout * gin; e += 256) {
@@ -743,6 +754,8 @@ int mpnn_table_to_flat(const float* dT, int R, int nf, int mf, float* dflat, cud
 
 // ---- fused edge network on the distinct rows (P <= 64) -------------------------------------------------
 int mpnn_enet_supported(int ef, int n_growth, int P) { return (P <= PW && ef <= PW && n_growth <= MAXG) ? 1 : 0; }
+// widest padded table (DP) the fused kernel writes; wider tables go through the generic trunk + last Linear
+int mpnn_enet_max_dp(void) { return 64; }
 
 long long mpnn_enet_saved_floats(int R, int n_growth, int n_tied) {
   return (long long)(n_growth + n_tied + 1) * R * PW;
@@ -765,7 +778,7 @@ int mpnn_enet_fwd(const float* rows, int R, int ef, int n_growth, const float* c
   MPNN_REQUIRE(fill_enet(&n, rows, R, ef, n_growth, growth_w, growth_b, w_tied, P, n_tied, w_last, b_last, nf, mf),
                MPNN_ERR_UNSUPPORTED, "enet_fwd: layer plan ef=%d growth=%d P=%d not supported by the fused kernel", ef,
                n_growth, P);
-  MPNN_REQUIRE(n.DP <= 32, MPNN_ERR_UNSUPPORTED, "enet_fwd: feature width > 32");
+  MPNN_REQUIRE(n.DP <= 64, MPNN_ERR_UNSUPPORTED, "enet_fwd: feature width > 64");
   int fch = nf * mf < 512 ? nf * mf : 512;
   size_t smem = (size_t)fch * (P | 1) * sizeof(float);
   MPNN_CUDA(cudaFuncSetAttribute(k_enet_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -789,7 +802,10 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   const int nparts = enet_grid(R);
   float* partial = (float*)workspace;
   float* red = partial + (size_t)nparts * stride;
-  k_enet_bwd<<<nparts, 256, 0, stream>>>(n, saved, dT, partial, stride, d_rows);
+  const size_t act_smem = (size_t)(n_growth + n_tied + 1) * PW * sizeof(float);
+  MPNN_REQUIRE(act_smem <= 160 * 1024, MPNN_ERR_UNSUPPORTED, "enet_bwd: too many layers for the shared-memory stage");
+  MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
+  k_enet_bwd<<<nparts, 256, act_smem, stream>>>(n, saved, dT, partial, stride, d_rows);
   MPNN_CHECK_LAUNCH("k_enet_bwd");
   k_enet_reduce<<<ceil_div(stride, 256), 256, 0, stream>>>(partial, nparts, stride, stride, red);
   MPNN_CHECK_LAUNCH("k_enet_reduce");

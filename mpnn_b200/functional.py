@@ -1,12 +1,76 @@
 """torch.autograd glue over the C-ABI kernels.  PyTorch is used for device memory, streams and the autograd
 tape only; every forward and backward below is a call into libmpnn_b200.so.  No CPU path exists."""
 import ctypes
+import os
 
 import torch
 from torch.autograd.function import once_differentiable
 
 from . import _lib
 from ._lib import check, f32c, ptr, ptr_array, stream, workspace
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-gradient work off the critical path
+# ------------------------------------------------------------------------------------------------
+# The backward of the edge network on the distinct bond rows (50 dependent layers, latency-bound) produces only
+# PARAMETER gradients: nothing else in the backward pass waits for it.  It is therefore enqueued on a side stream
+# (forked from the current stream by an event, also under CUDA-graph capture, where it becomes a parallel branch
+# of the graph) and joined once, at the end of the backward pass, by an autograd-engine callback.
+_SIDE_STREAMS = {}
+_SIDE_PENDING = {}
+SIDE_STREAM_ENABLED = os.environ.get("MPNN_B200_SIDE_STREAM", "1") != "0"
+
+
+def _side_stream(device):
+    k = device.index if device.index is not None else torch.cuda.current_device()
+    if k not in _SIDE_STREAMS:
+        _SIDE_STREAMS[k] = torch.cuda.Stream(device=device)
+    return k, _SIDE_STREAMS[k]
+
+
+def _join_side_streams():
+    for k in list(_SIDE_PENDING):
+        ev = _SIDE_PENDING.pop(k)
+        torch.cuda.current_stream(k).wait_event(ev)
+
+
+class _on_side_stream(object):
+    """`with _on_side_stream(device, tensors_read): ...` runs the body's launches on the side stream, after
+    everything enqueued so far on the current stream; the join is deferred to the end of the backward pass."""
+
+    def __init__(self, device, tensors):
+        self.device, self.tensors = device, [t for t in tensors if t is not None]
+
+    def __enter__(self):
+        self.key, self.side = _side_stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        first = self.key not in _SIDE_PENDING
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        _SIDE_PENDING[self.key] = ev
+        self.ctx.__exit__(*exc)
+        for t in self.tensors:
+            t.record_stream(self.side)
+        if first:
+            torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
+        return False
+
+
+class _inline(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 def _need_cuda(*ts):
@@ -550,7 +614,7 @@ class EdgeNetTableFn(torch.autograd.Function):
         gb = [f32c(t) for t in growth[G:]]
         R, ef = urows.shape
         P = w_tied.shape[0]
-        DP = lib.mpnn_typed_dp(nf, mf)
+        DP = table_dp(nf, mf)
         dev = urows.device
         saved = torch.empty(lib.mpnn_enet_saved_floats(R, G, n_tied), dtype=torch.float32, device=dev)
         table = torch.empty(R, DP, DP, dtype=torch.float32, device=dev)
@@ -577,10 +641,17 @@ class EdgeNetTableFn(torch.autograd.Function):
         d_gw = [torch.empty_like(w) for w in gw]
         d_gb = [torch.empty(w.shape[0], dtype=torch.float32, device=dev) for w in gw]
         d_rows = torch.empty_like(urows) if ctx.needs_input_grad[0] else None
-        ws = workspace(lib.mpnn_enet_workspace_bytes(R, ef, G, P), dev)
-        check(lib.mpnn_enet_bwd(ptr(urows), R, ef, G, ptr_array(gw), ptr(w_tied), P, n_tied, ptr(W_last), nf, mf,
-                                ptr(saved), ptr(dT), ptr_array(d_gw), ptr_array(d_gb), ptr(d_w_tied), ptr(d_W_last),
-                                ptr(d_B_last), ptr(d_rows), ptr(ws), ws.numel(), stream()), "enet_bwd")
+        # only parameter gradients come out of this call (d_rows is needed upstream: stay on the main stream then)
+        # deferred join is only safe when autograd ASSIGNS these gradients (param.grad is None: no kernel touches
+        # them before the join); if it has to accumulate into an existing .grad the work stays on the main stream
+        side = (SIDE_STREAM_ENABLED and d_rows is None
+                and all(getattr(t, "grad", None) is None for t in [w_tied, W_last] + gw))
+        with (_on_side_stream(dev, [dT, urows, w_tied, W_last, saved] + gw) if side else _inline()):
+            ws = workspace(lib.mpnn_enet_workspace_bytes(R, ef, G, P), dev)
+            check(lib.mpnn_enet_bwd(ptr(urows), R, ef, G, ptr_array(gw), ptr(w_tied), P, n_tied, ptr(W_last), nf, mf,
+                                    ptr(saved), ptr(dT), ptr_array(d_gw), ptr_array(d_gb), ptr(d_w_tied),
+                                    ptr(d_W_last), ptr(d_B_last), ptr(d_rows), ptr(ws), ws.numel(), stream()),
+                  "enet_bwd")
         return (d_rows, d_w_tied, None, d_W_last, d_B_last, None, None) + tuple(d_gw) + tuple(d_gb)
 
 

@@ -167,7 +167,8 @@ class EdgeNetwork(nn.Module):
         gb = [self.edge_map[i].bias for i in self._growth_idx]
         w_tied = self.edge_map[self._tied_idx][0].weight
         W, Bv = self._last()
-        if typed_dp(self.nf, self.mf) >= 0 and _lib.load().mpnn_enet_supported(self.ef, len(gw), self.P):
+        lib = _lib.load()
+        if table_dp(self.nf, self.mf) <= lib.mpnn_enet_max_dp() and lib.mpnn_enet_supported(self.ef, len(gw), self.P):
             table, tableT = EdgeNetTableFn.apply(ti.urows, w_tied, _N_TIED, W, Bv, self.nf, self.mf, *(gw + gb))
         else:   # wide trunks (P = 256, 625, 4096): generic trunk + last Linear on the distinct rows
             X = EdgeTrunkFn.apply(ti.urows, w_tied, _N_TIED, *(gw + gb))
