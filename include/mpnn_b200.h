@@ -189,7 +189,9 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
                  float* dW_hh, float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes,
                  mpnn_stream_t stream);
 
-/* ---- a10/a11: masked batch norms (models/mask_batch_norm.py:9-15, 20-38); stats [2C+1] saved ------------ */
+/* ---- a10/a11: masked batch norms (models/mask_batch_norm.py:9-15, 20-38); stats [2C+1] saved ------------
+ * Workspace contract: zero-filled ONCE by the caller; every call leaves it reusable (its completion counter is
+ * reset by the last block), so consecutive calls on one stream need no memset. */
 size_t mpnn_bn_workspace_bytes(long long rows, int C);
 int mpnn_mask_bn_fwd(const float* x, const float* mask, long long rows, int C, float eps, float* y, float* stats,
                      void* workspace, size_t workspace_bytes, mpnn_stream_t stream);

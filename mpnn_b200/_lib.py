@@ -138,6 +138,20 @@ def workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+_CLEAN_WS = {}
+
+
+def clean_workspace(nbytes, device):
+    """Persistent zero-initialised workspace per (device, stream, size) for ops whose kernels leave their scratch
+    counters zero on exit (masked batch norms): no memset per call."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
+    ws = _CLEAN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _CLEAN_WS[key] = ws
+    return ws
+
+
 def f32c(t):
     """contiguous fp32 view/copy (the C-ABI contract)"""
     if t.dtype != torch.float32:

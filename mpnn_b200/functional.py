@@ -289,7 +289,7 @@ class MaskBNFn(torch.autograd.Function):
         rows, C = x.shape
         y = torch.empty_like(x)
         stats = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
-        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
+        ws = _lib.clean_workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
         check(lib.mpnn_mask_bn_fwd(ptr(x), ptr(mask), rows, C, float(eps), ptr(y), ptr(stats), ptr(ws), ws.numel(),
                                    stream()), "mask_bn_fwd")
         ctx.save_for_backward(x, mask, stats)
@@ -303,7 +303,7 @@ class MaskBNFn(torch.autograd.Function):
         rows, C = x.shape
         dy = f32c(dy)
         dx = torch.empty_like(x)
-        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
+        ws = _lib.clean_workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
         check(lib.mpnn_mask_bn_bwd(ptr(x), ptr(mask), ptr(dy), ptr(stats), rows, C, ptr(dx), ptr(ws), ws.numel(),
                                    stream()), "mask_bn_bwd")
         return dx, None, None
@@ -322,7 +322,7 @@ class MaskBN1dFn(torch.autograd.Function):
         rows, C = x.shape
         y = torch.empty_like(x)
         stats = torch.empty(2 * C + 1, dtype=torch.float32, device=x.device)
-        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
+        ws = _lib.clean_workspace(lib.mpnn_bn_workspace_bytes(rows, C), x.device)
         check(lib.mpnn_mask_bn1d_fwd(ptr(x), ptr(mask), ptr(weight_c), ptr(bias_c), ptr(running_mean), ptr(running_var),
                                      rows, C, int(training), float(momentum), float(eps), ptr(y), ptr(stats), ptr(ws),
                                      ws.numel(), stream()), "mask_bn1d_fwd")
@@ -350,7 +350,7 @@ class MaskBN1dFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dw = torch.empty(C, dtype=torch.float32, device=dev)
         db = torch.empty(C, dtype=torch.float32, device=dev)
-        ws = workspace(lib.mpnn_bn_workspace_bytes(rows, C), dev)
+        ws = _lib.clean_workspace(lib.mpnn_bn_workspace_bytes(rows, C), dev)
         check(lib.mpnn_mask_bn1d_bwd(ptr(x), ptr(mask), ptr(dy), ptr(weight), ptr(stats), ptr(rm), ptr(rv), rows, C,
                                      int(training), eps, ptr(dx), ptr(dw), ptr(db), ptr(ws), ws.numel(), stream()),
               "mask_bn1d_bwd")
