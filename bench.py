@@ -39,6 +39,13 @@ WORKLOADS = {
                  desc="lipo_basic_model (HEAD form), Lipophilicity-shaped, B=32, d=19, ef=7, P=49, T=6"),
     "autoenc": dict(variant="autoencoder", d=64, ef=8, T=3, out=128, targets=128, B=512,
                     desc="basic_graph_autoencoder.encode, ZINC-shaped, B=512/GPU, d=64, ef=8, P=64, T=3"),
+    # configs[2]: att_model (AttEdgeNetwork + AdjMsgAgg + MaskBatchNorm + Set2Vec, 100 steps), 128 graphs per GPU
+    "zinc": dict(variant="att", d=32, ef=8, T=3, out=128, targets=1, B=128, message_func="AttEdgeNetwork",
+                 readout_func="Set2Vec", graph=False,
+                 desc="att_model (AttEdgeNetwork, AdjMsgAgg, Set2Vec x100), ZINC-shaped, B=128/GPU, d=32, ef=8, P=64, T=3"),
+    # configs[3]: normed_encoded_basic_model (atom/bond encoders + masked BN1d everywhere), B=2048 global
+    "affinity": dict(variant="normed_encoded", d=8, ef=2, T=3, out=16, targets=1, B=2048, encoders=True, graph=False,
+                     desc="normed_encoded_basic_model (encoders 30->8 / 8->2, MaskBatchNorm1d), B=2048, d=8, ef=2, P=16, T=3"),
 }
 
 
@@ -91,7 +98,8 @@ class ClockSampler(threading.Thread):
 
 def make_workload_batch(config, w, rank):
     from mpnn_b200 import synthetic
-    batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=w["B"], seed_offset=rank)
+    batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=w["B"], seed_offset=rank,
+                                 d=w["d"] if config == "autoenc" else None)
     if config != "qm9":
         batch["labels"] = np.random.RandomState(rank).normal(size=(w["B"], w["targets"])).astype(np.float32)
     return batch
@@ -99,8 +107,17 @@ def make_workload_batch(config, w, rank):
 
 def build_model(w, dev):
     from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from mpnn_b200 import modules as M
     torch.manual_seed(317)
-    body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"])
+    kw = {}
+    if w.get("message_func"):
+        kw["message_func"] = getattr(M, w["message_func"])
+    if w.get("readout_func"):
+        kw["readout_func"] = getattr(M, w["readout_func"])
+    if w.get("encoders"):   # AtomAutoEncoder / BondAutoEncoder .encoder halves (encoders/*_autoencoder.py:7-11)
+        kw["atom_encoder"] = torch.nn.Sequential(torch.nn.Linear(30, 15, bias=False), torch.nn.Tanh(), torch.nn.Linear(15, 8))
+        kw["bond_encoder"] = torch.nn.Sequential(torch.nn.Linear(8, 4, bias=False), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+    body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"], **kw)
     body.apply(kaiming_init)
     head = torch.nn.Linear(w["out"], w["targets"])
     return body.to(dev), head.to(dev)
@@ -123,7 +140,14 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    w = WORKLOADS[args.config]
+    w = dict(WORKLOADS[args.config])
+    if args.batch:
+        w["B"] = args.batch
+        w["desc"] += " [batch overridden: %d]" % args.batch
+    if args.hidden:
+        w["d"] = args.hidden
+        w["out"] = w["targets"] = 2 * args.hidden
+        w["desc"] += " [hidden overridden: %d]" % args.hidden
     B = w["B"]
     batch = make_workload_batch(args.config, w, rank)
     n, e = batch["n_atoms"], batch["n_edges"]
@@ -132,7 +156,9 @@ def run_ours(args):
     devb = {k: v.to(dev) for k, v in host.items()}
     body, head = build_model(w, dev)
     params = list(body.parameters()) + list(head.parameters())
-    use_graph = not args.no_graph
+    # the attention gate (per-pair sender vectors) and differentiable bond features run on the per-edge contraction
+    # kernels, whose array sizes come from a host read of the edge count: eager launches for those workloads
+    use_graph = not args.no_graph and w.get("graph", True)
     opt = torch.optim.Adam(params, lr=1e-3, capturable=use_graph, fused=use_graph or None)
     allreduce = D.FlatGradAllReduce(params)
     # L2 (126 MB) is flushed between timed iterations by writing a 256 MB buffer
@@ -162,12 +188,33 @@ def run_ours(args):
         def run_resident():
             return gs.replay()
 
+        # e2e input pipeline: like a prefetching DataLoader (pin_memory + non_blocking), the NEXT step's host->device
+        # copy runs on a copy stream into a staging buffer while the current step computes; every timed step still
+        # contains one full H2D of a padded batch, a D2D into the graph's static inputs and a synchronous loss read.
+        copy_stream = torch.cuda.Stream()
+        staging = {k: torch.empty_like(v) for k, v in devb.items()}
+        ev_copy, ev_loaded = torch.cuda.Event(), torch.cuda.Event()
+
+        def prefetch():
+            with torch.cuda.stream(copy_stream):
+                for k in keys:
+                    staging[k].copy_(host[k], non_blocking=True)
+                ev_copy.record(copy_stream)
+
         def run_e2e():
-            gs.load(host, non_blocking=True)
+            main = torch.cuda.current_stream()
+            main.wait_event(ev_copy)           # this step's inputs have landed in the staging buffer
+            gs.load(staging, non_blocking=True)
+            ev_loaded.record(main)
+            copy_stream.wait_event(ev_loaded)  # the staging buffer may be overwritten from here on
+            prefetch()                         # next step's H2D overlaps this step's kernels
             return gs.replay()
     else:
         def run_resident():
             return step(devb)
+
+        def prefetch():
+            pass
 
         def run_e2e():
             return step({k: v.to(dev, non_blocking=True) for k, v in host.items()})
@@ -189,6 +236,7 @@ def run_ours(args):
     ms = sum(a.elapsed_time(b) for a, b in ev)
     # ---- e2e: host buffers, H2D + loss D2H inside the timed region ----------------------------
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    prefetch()   # the first step's inputs; every timed step issues the copy for its successor
     barrier()
     for i in range(args.steps):
         flush.fill_(i & 1)
@@ -225,7 +273,9 @@ def run_ours(args):
                    "optimizer": "Adam", "loss": "MSE", "cuda_graph": bool(use_graph), "l2_flush": "256 MB write between timed iterations",
                    "parallelism": "dp%d" % world},
         "e2e": {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": gb_in,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps,
+                "pipeline": "H2D of the next padded batch on a copy stream (pinned -> staging) overlapped with the current "
+                            "step; D2D staging -> graph inputs; loss.item() every step" if use_graph else "serial"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -330,11 +380,8 @@ def _oracle_step_fn(config, B):
     from golden_util import leaf_sd
     w = WORKLOADS[config]
     batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=B)
-    torch.manual_seed(317)
-    body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"])
-    body.apply(kaiming_init)
+    body, head = build_model(w, torch.device("cpu"))
     sd = leaf_sd({k: v.detach().clone() for k, v in body.state_dict().items()})
-    head = torch.nn.Linear(w["out"], w["targets"])
     leaves, seen = [], set()
     for v in list(sd.values()) + list(head.parameters()):
         if v.dtype.is_floating_point and v.requires_grad and id(v) not in seen:
@@ -352,6 +399,10 @@ def _oracle_step_fn(config, B):
             y = O.normed_basic_model(*a, sd=sd, steps=w["T"])
         elif w["variant"] == "lipo":
             y = O.lipo_model(*a, sd=sd, steps=w["T"], buffers=buffers)
+        elif w["variant"] == "att":
+            y = O.att_model(*a, sd=sd, steps=w["T"], s2v_steps=100, agg="adj")
+        elif w["variant"] == "normed_encoded":
+            y = O.normed_encoded_model(*a, sd=sd, steps=w["T"], buffers=buffers)
         else:
             y = O.basic_model(*a, sd=sd, steps=w["T"], chain_state=False)
         loss = torch.nn.functional.mse_loss(head(y), labels)
@@ -418,6 +469,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
+    ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")
+    ap.add_argument("--hidden", type=int, default=0, help="feature width d (autoenc sweep of BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

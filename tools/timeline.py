@@ -1,5 +1,5 @@
 """Warm per-kernel timeline of one graphed train step (CUPTI via torch.profiler): name, duration, gap to the
-previous kernel.  Usage: python tools/timeline.py [config] > gpurun_out/timeline.txt"""
+previous kernel.  Usage: python tools/timeline.py [config [batch [hidden]]] > gpurun_out/timeline.txt"""
 import os
 import sys
 
@@ -14,7 +14,12 @@ def main():
     from mpnn_b200 import graph, synthetic
     from mpnn_b200.graphs import GraphedStep
     dev = torch.device("cuda:0")
-    w = bench.WORKLOADS[cfg]
+    w = dict(bench.WORKLOADS[cfg])
+    if len(sys.argv) > 2:
+        w["B"] = int(sys.argv[2])
+    if len(sys.argv) > 3:
+        w["d"] = int(sys.argv[3])
+        w["out"] = w["targets"] = 2 * w["d"]
     batch = bench.make_workload_batch(cfg, w, 0)
     devb = {k: torch.from_numpy(batch[k]).to(dev) for k in ("afm", "bfm", "adj", "mask", "labels")}
     body, head = bench.build_model(w, dev)
