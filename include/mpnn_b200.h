@@ -138,6 +138,20 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
                        const float* dM, int mf, int DP, int use_alpha, float* dT, void* workspace,
                        size_t workspace_bytes, mpnn_stream_t stream);
 
+/* Dense GEMMs on the same tcgen05 kernels (identity plan): the GRU gate products (gru_update.py:27-28) and the
+ * readout projections (graph_level_output.py:36) at widths 33..256.  TF32 operands, fp32 accumulate.
+ *   Y[r, g*ycol + n] (+)= sum_{s<kseg} sum_{k<K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + (g*kseg+s)*w_sb] + bias[g*N + n]
+ *   out[g*o_sg + l*o_sl + k] = sum_r X[r, l] * D[r, g*dcol + k]                 (weight gradients X^T D) */
+size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP);
+int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                       long long w_sn, long long w_sk, long long w_sb, int G, int N, const float* bias, float* Y,
+                       int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
+                       mpnn_stream_t stream);
+size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
+int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol, int G,
+                          int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
+                          size_t workspace_bytes, mpnn_stream_t stream);
+
 /* ---- a1/a2: edge-network trunk = edge_map[:-1] (edge_network.py:14-21,36-37) on compacted rows -------- */
 long long mpnn_edge_trunk_saved_floats(int R, int ef, int n_growth, int P, int n_tied, long long* x_offset, int* ldx);
 size_t mpnn_edge_trunk_workspace_bytes(int R, int ef, int n_growth, int P);

@@ -54,6 +54,10 @@ SIGNATURES = {
     "mpnn_tc_edge_gemm": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _Z, _P]),
     "mpnn_tc_table_grad_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_tc_table_grad": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _Z, _P]),
+    "mpnn_tc_dense_workspace_bytes": (_Z, [_I, _I]),
+    "mpnn_tc_dense_gemm": (_I, [_P, _L, _I, _I, _I, _I, _P, _L, _L, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_dense_grad_workspace_bytes": (_Z, [_I, _I]),
+    "mpnn_tc_dense_gemm_tn": (_I, [_P, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _L, _L, _P, _Z, _P]),
     "mpnn_scatter_edge_rows": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "mpnn_edge_trunk_saved_floats": (_L, [_I, _I, _I, _I, _I, ctypes.POINTER(_L), ctypes.POINTER(_I)]),
     "mpnn_edge_trunk_workspace_bytes": (_Z, [_I, _I, _I, _I]),

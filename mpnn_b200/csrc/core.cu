@@ -55,11 +55,29 @@ __global__ void k_colsum_partial(const float* __restrict__ X, const float* __res
   int c = threadIdx.x % width, rl = threadIdx.x / width;
   float acc = 0.f;
   if (rl < lanes) {
-    for (long long r = r0 + rl; r < r1; r += lanes) {
+    // four independent loads in flight per thread (fixed combination order: bit-reproducible)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    long long r = r0 + rl;
+    const long long st = lanes;
+    for (; r + 3 * st < r1; r += 4 * st) {
+      float v0 = X[r * ldx + c], v1 = X[(r + st) * ldx + c], v2 = X[(r + 2 * st) * ldx + c], v3 = X[(r + 3 * st) * ldx + c];
+      if (Y) {
+        v0 *= Y[r * ldy + c];
+        v1 *= Y[(r + st) * ldy + c];
+        v2 *= Y[(r + 2 * st) * ldy + c];
+        v3 *= Y[(r + 3 * st) * ldy + c];
+      }
+      a0 += v0;
+      a1 += v1;
+      a2 += v2;
+      a3 += v3;
+    }
+    for (; r < r1; r += st) {
       float v = X[r * ldx + c];
       if (Y) v *= Y[r * ldy + c];
-      acc += v;
+      a0 += v;
     }
+    acc = (a0 + a1) + (a2 + a3);
   }
   sm[threadIdx.x] = acc;
   __syncthreads();
@@ -164,7 +182,7 @@ __global__ void k_colsum_wide(const float* __restrict__ X, const float* __restri
 }  // namespace
 
 static int colsum_blocks(long long rows, int* rows_per_block) {
-  int target = 2 * mpnn_num_sms();
+  int target = 8 * mpnn_num_sms();
   long long rpb = (rows + target - 1) / target;
   if (rpb < 64) rpb = 64;
   *rows_per_block = (int)rpb;

@@ -13,6 +13,17 @@ extern "C" int mpnn_colsum(const float* X, const float* Y, long long rows, int w
                            float* out, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
 
+extern "C" int mpnn_tc_dp(int nf, int mf);
+extern "C" size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP);
+extern "C" int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                                  long long w_sn, long long w_sk, long long w_sb, int G, int N, const float* bias,
+                                  float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream);
+extern "C" size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
+extern "C" int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol,
+                                     int G, int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream);
+
 namespace {
 
 __global__ void k_gru_point_fwd(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h,
@@ -351,7 +362,13 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
   size_t g = mpnn_gemm_workspace_bytes(d, 3 * d, (int)rows);
   size_t c = mpnn_colsum_workspace_bytes(rows, 3 * d);
   size_t fused = (size_t)mpnn_num_sms() * (6 * (size_t)d * d + 6 * d) * sizeof(float);
-  size_t need = pre + align_up(g > c ? g : c, 256);
+  size_t sub = g > c ? g : c;
+  const int DP = d > 32 ? mpnn_tc_dp(d, d) : -1;   // widths 33..256: gate GEMMs on the tensor cores (tc_message.cu)
+  if (DP > 0) {
+    size_t t = align_up(mpnn_tc_dense_workspace_bytes(3, DP), 256) + mpnn_tc_dense_grad_workspace_bytes(3, DP);
+    if (t > sub) sub = t;
+  }
+  size_t need = pre + align_up(sub, 256);
   return need > fused ? need : fused;
 }
 
@@ -380,10 +397,22 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
   float* gh = (float*)wp;
   wp += align_up((size_t)rows * 3 * d * sizeof(float), 256);
   int R = (int)rows;
-  int rc = mpnn_gemm(m, W_ih, gi, R, 3 * d, d, d, 1, 3 * d, 1, 3 * d, b_ih, 0, nullptr, 0, stream);
-  if (rc) return rc;
-  rc = mpnn_gemm(h, W_hh, gh, R, 3 * d, d, d, 1, 3 * d, 1, 3 * d, b_hh, 0, nullptr, 0, stream);
-  if (rc) return rc;
+  int rc;
+  const int DP = mpnn_tc_dp(d, d);
+  if (DP > 0) {
+    // [rows, d] x [d, 3d] as three d x d N-blocks on the tcgen05 grouped-GEMM kernel (TF32 operands, fp32 accumulate)
+    void* sub = wp;
+    size_t sub_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
+    rc = mpnn_tc_dense_gemm(m, rows, d, d, 1, 0, W_ih, 1, 3 * d, d, 3, d, b_ih, gi, 3 * d, d, 0, DP, sub, sub_bytes, stream);
+    if (rc) return rc;
+    rc = mpnn_tc_dense_gemm(h, rows, d, d, 1, 0, W_hh, 1, 3 * d, d, 3, d, b_hh, gh, 3 * d, d, 0, DP, sub, sub_bytes, stream);
+    if (rc) return rc;
+  } else {
+    rc = mpnn_gemm(m, W_ih, gi, R, 3 * d, d, d, 1, 3 * d, 1, 3 * d, b_ih, 0, nullptr, 0, stream);
+    if (rc) return rc;
+    rc = mpnn_gemm(h, W_hh, gh, R, 3 * d, d, d, 1, 3 * d, 1, 3 * d, b_hh, 0, nullptr, 0, stream);
+    if (rc) return rc;
+  }
   k_gru_point_fwd<<<ceil_div(rows * d, 256), 256, 0, stream>>>(gi, gh, h, mask, rows, d, h_out, gates);
   MPNN_CHECK_LAUNCH("k_gru_point_fwd");
   return MPNN_OK;
@@ -421,6 +450,25 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
   k_gru_point_bwd<<<ceil_div(rows * d, 256), 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dgi, dgh, dh);
   MPNN_CHECK_LAUNCH("k_gru_point_bwd");
   int rc;
+  const int DP = mpnn_tc_dp(d, d);
+  if (DP > 0) {
+    // tensor-core path: dm = sum_g dgi_g W_ih,g^T (three K segments), dW = X^T dG (K = rows, per-CTA partials)
+    char* ip = (char*)sub;
+    size_t img_bytes = align_up(mpnn_tc_dense_workspace_bytes(3, DP), 256);
+    void* gsub = ip + img_bytes;
+    size_t gsub_bytes = sub_bytes - img_bytes;
+    if ((rc = mpnn_tc_dense_gemm(dgi, rows, 3 * d, d, 3, d, W_ih, 3 * d, 1, d, 1, d, nullptr, dm, d, 0, 0, DP, sub, sub_bytes,
+                                 stream)))
+      return rc;
+    if ((rc = mpnn_tc_dense_gemm(dgh, rows, 3 * d, d, 3, d, W_hh, 3 * d, 1, d, 1, d, nullptr, dh, d, 0, 1, DP, sub, sub_bytes,
+                                 stream)))
+      return rc;
+    if ((rc = mpnn_tc_dense_gemm_tn(m, rows, d, d, dgi, 3 * d, d, 3, d, DP, dW_ih, d, 3 * d, gsub, gsub_bytes, stream))) return rc;
+    if ((rc = mpnn_tc_dense_gemm_tn(h, rows, d, d, dgh, 3 * d, d, 3, d, DP, dW_hh, d, 3 * d, gsub, gsub_bytes, stream))) return rc;
+    if ((rc = mpnn_colsum(dgi, nullptr, rows, 3 * d, 3 * d, 0, db_ih, 0, gsub, gsub_bytes, stream))) return rc;
+    if ((rc = mpnn_colsum(dgh, nullptr, rows, 3 * d, 3 * d, 0, db_hh, 0, gsub, gsub_bytes, stream))) return rc;
+    return MPNN_OK;
+  }
   // dm = dgi W_ih^T ; dh += dgh W_hh^T
   if ((rc = mpnn_gemm(dgi, W_ih, dm, R, d, 3 * d, 3 * d, 1, 1, 3 * d, d, nullptr, 0, nullptr, 0, stream))) return rc;
   if ((rc = mpnn_gemm(dgh, W_hh, dh, R, d, 3 * d, 3 * d, 1, 1, 3 * d, d, nullptr, 2, nullptr, 0, stream))) return rc;

@@ -259,11 +259,34 @@ struct TcGemm {
   const int* type_eid;  // sorted position -> edge id (output row)
   const int* prow;      // sorted position -> row of A (plan.psrc or plan.pdst)
   const float* A;       // [*, lda]
-  const float* Bimg;    // pre-swizzled table image
+  const float* Bimg;    // pre-swizzled image of the B matrices
   int use_alpha;
   float* Y;             // [E, ldy]
   int lda, K, ldy, N;
+  // dense mode (plain GEMM on contiguous rows, no plan): tile t -> row block t / G, N-block ("type") t % G
+  int dense, G;
+  long long rows;
+  int kseg;             // K segments accumulated per tile: segment s reads A columns s*acol.. and B matrix u*kseg+s
+  int acol;
+  int ycol;             // output column offset between N-blocks
+  int accumulate;       // Y += result
+  const float* bias;    // [G*N] or null
 };
+
+// tile t -> (type u, first row / sorted position, rows in the tile)
+__device__ __forceinline__ void gemm_tile(const TcGemm& a, int t, int& u, int& pos, int& cnt) {
+  if (a.dense) {
+    const int rt = t / a.G;
+    u = t - rt * a.G;
+    pos = rt * TILE;
+    const long long rem = a.rows - (long long)pos;
+    cnt = rem < TILE ? (int)rem : TILE;
+  } else {
+    u = a.plan.tile_type[t];
+    pos = a.plan.tile_pos[t];
+    cnt = a.plan.tile_cnt[t];
+  }
+}
 
 template <int DP>
 struct GemmCfg {
@@ -312,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_tiles = a.plan.head[0];
+  const int n_tiles = a.dense ? (int)((a.rows + TILE - 1) / TILE) * a.G : a.plan.head[0];
   const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
@@ -325,24 +348,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
     int rows_next[8];   // A rows of the NEXT tile (prefetched one tile ahead)
     auto load_rows = [&](int t, int* rows) {
       if (t < t1) {
-        const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
+        int u_, pos, cnt;
+        gemm_tile(a, t, u_, pos, cnt);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 16 + sub;
-          rows[i] = r < cnt ? __ldg(a.prow + pos + r) : -1;
+          rows[i] = r < cnt ? (a.dense ? pos + r : __ldg(a.prow + pos + r)) : -1;
         }
       }
     };
     load_rows(t0, rows_next);
     for (int t = t0; t < t1; ++t) {
-      const int u = a.plan.tile_type[t];
+      int u, pos_, cnt_;
+      gemm_tile(a, t, u, pos_, cnt_);
       int rows[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) rows[i] = rows_next[i];
       load_rows(t + 1, rows_next);
-      const float* bimg = a.Bimg + (size_t)u * NKB * (DP * KB);
-      for (int kb = 0; kb < NKB; ++kb) {
+      for (int sk = 0; sk < a.kseg * NKB; ++sk) {
+        const int seg = sk / NKB, kb = sk - seg * NKB;
+        const float* bimg = a.Bimg + (size_t)(u * a.kseg + seg) * NKB * (DP * KB);
         const int kk = kb * KB + chunk * 4;
+        const int acol = seg * a.acol + kk;
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t As = smem_base + stage * C::STAGE;
         if (tid == 0) {
@@ -352,7 +379,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const bool ok = rows[i] >= 0 && kk < a.K;
-          const float* src = ok ? a.A + (size_t)rows[i] * a.lda + kk : a.A;
+          const float* src = ok ? a.A + (size_t)rows[i] * a.lda + acol : a.A;
           cp_async16(As + swz(i * 16 + sub, chunk), src, ok ? 16u : 0u);
         }
         cp_async_arrive_noinc(full_bar(stage));
@@ -372,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
         mbar_wait(accempty_bar(acc), (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(acc * DP);
-        for (int kb = 0; kb < NKB; ++kb) {
+        for (int kb = 0; kb < a.kseg * NKB; ++kb) {
           mbar_wait(full_bar(stage), phase);
           fence_proxy_async();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
           tc_fence_after();
@@ -402,9 +429,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
     const int orow = lane >> 3, ocol = (lane & 7) * 4;
     for (int t = t0; t < t1; ++t) {
       const int i = t - t0, acc = i & 1, use = i >> 1;
-      const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
-      const int e = r < cnt ? __ldg(a.type_eid + pos + r) : -1;
+      int u, pos, cnt;
+      gemm_tile(a, t, u, pos, cnt);
+      const int e = r < cnt ? (a.dense ? pos + r : __ldg(a.type_eid + pos + r)) : -1;
       const float al = (e >= 0 && a.use_alpha) ? __ldg(a.plan.palpha + pos + r) : 1.f;
+      const int ybase = a.dense ? u * a.ycol : 0;
+      const float* bias = a.bias ? a.bias + (size_t)u * a.N : nullptr;
       int erow[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) erow[it] = __shfl_sync(0xffffffffu, e, it * 4 + orow);
@@ -419,11 +449,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
         for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = al * v[c];
         __syncwarp();
         if (c0 + ocol < a.N) {
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + ocol));
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const float* p = tb + (it * 4 + orow) * 33 + ocol;
-            if (erow[it] >= 0)
-              *reinterpret_cast<float4*>(a.Y + (size_t)erow[it] * a.ldy + c0 + ocol) = make_float4(p[0], p[1], p[2], p[3]);
+            if (erow[it] >= 0) {
+              float4* y = reinterpret_cast<float4*>(a.Y + (size_t)erow[it] * a.ldy + ybase + c0 + ocol);
+              float4 o = make_float4(p[0] + bv.x, p[1] + bv.y, p[2] + bv.z, p[3] + bv.w);
+              if (a.accumulate) {
+                const float4 old = *y;
+                o.x += old.x;
+                o.y += old.y;
+                o.z += old.z;
+                o.w += old.w;
+              }
+              *y = o;
+            }
           }
         }
         __syncwarp();
@@ -457,7 +499,24 @@ struct TcGrad {
   float* partial;    // [slots][DP][DP]
   int nf, mf;
   int use_alpha;     // 0: all weights are 1 (HEAD form); 1: the plan's edge weights
+  // dense mode (out[g] = H^T dM[:, g*bcol ...] on contiguous rows): tile t -> type t / RT, row block t % RT
+  int dense, G, RT;
+  long long rows;
+  int ldh, ldm, bcol;
 };
+
+__device__ __forceinline__ void grad_tile(const TcGrad& a, int t, int& u, int& pos, int& cnt) {
+  if (a.dense) {
+    u = t / a.RT;
+    pos = (t - u * a.RT) * TILE;
+    const long long rem = a.rows - (long long)pos;
+    cnt = rem < TILE ? (int)rem : TILE;
+  } else {
+    u = a.plan.tile_type[t];
+    pos = a.plan.tile_pos[t];
+    cnt = a.plan.tile_cnt[t];
+  }
+}
 
 template <int DP>
 struct GradCfg {
@@ -505,8 +564,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_tiles = a.plan.head[0];
-  const bool unit_alpha = !a.use_alpha || a.plan.head[1] != 0;
+  const int n_tiles = a.dense ? a.G * a.RT : a.plan.head[0];
+  const bool unit_alpha = a.dense || !a.use_alpha || a.plan.head[1] != 0;
   const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
@@ -516,7 +575,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
     const int sub = tid >> 3, chunk = tid & 7;   // sub: 0..15 -> edges sub, sub+16, ... of the stage
     int stage = 0, phase = 0;
     for (int t = t0; t < t1; ++t) {
-      const int pos = a.plan.tile_pos[t], cnt = a.plan.tile_cnt[t];
+      int u_, pos, cnt;
+      grad_tile(a, t, u_, pos, cnt);
       for (int s0 = 0; s0 < cnt; s0 += C::KST) {
         const float* hrow[C::EPT];
         const float* mrow[C::EPT];
@@ -525,8 +585,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
         for (int h = 0; h < C::EPT; ++h) {
           const int r = s0 + sub + 16 * h;
           const bool ok = r < cnt;
-          hrow[h] = ok ? a.H + (size_t)__ldg(a.plan.psrc + pos + r) * a.nf : nullptr;
-          mrow[h] = ok ? a.dM + (size_t)__ldg(a.plan.pdst + pos + r) * a.mf : nullptr;
+          if (a.dense) {
+            hrow[h] = ok ? a.H + (size_t)(pos + r) * a.ldh : nullptr;
+            mrow[h] = ok ? a.dM + (size_t)(pos + r) * a.ldm + (size_t)u_ * a.bcol : nullptr;
+          } else {
+            hrow[h] = ok ? a.H + (size_t)__ldg(a.plan.psrc + pos + r) * a.nf : nullptr;
+            mrow[h] = ok ? a.dM + (size_t)__ldg(a.plan.pdst + pos + r) * a.mf : nullptr;
+          }
           al[h] = (ok && !unit_alpha) ? __ldg(a.plan.palpha + pos + r) : 1.f;
         }
         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -606,7 +671,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
       int stage = 0, phase = 0, seg = 0, cur = -1;
       bool fresh = true;
       for (int t = t0; t < t1; ++t) {
-        const int u = a.plan.tile_type[t], cnt = a.plan.tile_cnt[t];
+        int u, pos_, cnt;
+        grad_tile(a, t, u, pos_, cnt);
         if (u != cur) {
           if (cur >= 0) {
             umma_commit(accfull_bar);
@@ -647,8 +713,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
     const int q = warp & 3;
     int seg = 0;
     for (int t = t0; t < t1; ++t) {
-      const int u = a.plan.tile_type[t];
-      const bool last = (t + 1 == t1) || (a.plan.tile_type[t + 1] != u);
+      int u, pos_, cnt_, un = -1;
+      grad_tile(a, t, u, pos_, cnt_);
+      if (t + 1 < t1) grad_tile(a, t + 1, un, pos_, cnt_);
+      const bool last = (t + 1 == t1) || (un != u);
       if (!last) continue;
       mbar_wait(accfull_bar, seg & 1);
       tc_fence_after();
@@ -681,22 +749,52 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
   }
 }
 
-// dT[u][idx] = sum over the CTAs whose tile range touches type u of partial[cta + u][idx]  (fixed order)
-__global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int grid_ctas, int ntypes, int elems,
-                                                         const float* __restrict__ partial, float* __restrict__ dT) {
+// out[u*su + l*sl + k] (l < M, k < N) = sum over the CTAs whose tile range touches type u of partial[cta + u][l][k]
+// (fixed order).  Plan mode: the tile range of a type comes from tile_off; dense mode: type u owns tiles [u*RT, (u+1)*RT).
+__global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int dense, int RT, int grid_ctas, int ntypes,
+                                                         int DP, int M, int N, long long su, long long sl,
+                                                         const float* __restrict__ partial, float* __restrict__ out) {
   const int u = blockIdx.y;
-  const int n_tiles = plan.head[0];
+  int n_tiles, f, l;
+  if (dense) {
+    n_tiles = ntypes * RT;
+    f = u * RT;
+    l = f + RT;
+  } else {
+    n_tiles = plan.head[0];
+    f = plan.tile_off[u];
+    l = (u < ntypes ? plan.tile_off[u + 1] : f);
+  }
   const int per = (n_tiles + grid_ctas - 1) / grid_ctas;
-  const int f = plan.tile_off[u], l = (u < ntypes ? plan.tile_off[u + 1] : f);
   int c0 = 0, c1 = -1;
   if (l > f && per > 0 && f < n_tiles) {
     c0 = f / per;
     c1 = (min(l, n_tiles) - 1) / per;
   }
+  const int elems = DP * DP;
   for (int idx = blockIdx.x * 256 + threadIdx.x; idx < elems; idx += gridDim.x * 256) {
+    const int li = idx / DP, ki = idx - li * DP;
+    if (li >= M || ki >= N) continue;
     float s = 0.f;
     for (int c = c0; c <= c1; ++c) s += partial[(size_t)(c + u) * elems + idx];
-    dT[(size_t)u * elems + idx] = s;
+    out[(size_t)u * su + (size_t)li * sl + ki] = s;
+  }
+}
+
+// image[(b*NKB + kb)][n][chunk ^ (n & 7)][j] = W[n*sn + k*sk + b*sb], k = kb*32 + chunk*4 + j  (zero outside N x K):
+// packs nb strided weight blocks straight into the shared-memory image the dense GEMM bulk-copies per stage
+__global__ void __launch_bounds__(256) k_tc_pack_image(const float* __restrict__ W, long long sn, long long sk,
+                                                       long long sb, int nb, int N, int K, int DP,
+                                                       float* __restrict__ img) {
+  const int nkb = DP / KB;
+  const long long total = (long long)nb * DP * DP;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int k = (int)(i % DP);
+    const int n = (int)((i / DP) % DP);
+    const int b = (int)(i / ((long long)DP * DP));
+    const float v = (n < N && k < K) ? __ldg(W + (size_t)n * sn + (size_t)k * sk + (size_t)b * sb) : 0.f;
+    const int kb = k >> 5, chunk = (k & 31) >> 2, j = k & 3;
+    img[(((size_t)b * nkb + kb) * DP + n) * KB + ((chunk ^ (n & 7)) << 2) + j] = v;
   }
 }
 
@@ -822,6 +920,14 @@ int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, 
   a.K = K;
   a.ldy = ldy;
   a.N = N;
+  a.dense = 0;
+  a.G = 1;
+  a.rows = 0;
+  a.kseg = 1;
+  a.acol = 0;
+  a.ycol = 0;
+  a.accumulate = 0;
+  a.bias = nullptr;
   const int grid = tc_grid();
   switch (DP) {
     case 64:
@@ -866,6 +972,10 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
   a.nf = nf;
   a.mf = mf;
   a.use_alpha = use_alpha;
+  a.dense = 0;
+  a.G = a.RT = 0;
+  a.rows = 0;
+  a.ldh = a.ldm = a.bcol = 0;
   const int grid = tc_grid();
   switch (DP) {
     case 64:
@@ -883,8 +993,125 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
   }
   MPNN_CHECK_LAUNCH("k_tc_table_grad");
   dim3 rgrid(ceil_div(DP * DP, 256 * 4), unique_capacity + 1);
-  k_tc_table_reduce<<<rgrid, 256, 0, stream>>>(a.plan, grid, unique_capacity, DP * DP, a.partial, dT);
+  k_tc_table_reduce<<<rgrid, 256, 0, stream>>>(a.plan, 0, 0, grid, unique_capacity, DP, DP, DP, (long long)DP * DP, DP,
+                                               a.partial, dT);
   MPNN_CHECK_LAUNCH("k_tc_table_reduce");
+  return MPNN_OK;
+}
+
+// ---- dense GEMMs on the same kernels (GRU gates, readout projections at widths 33..256) ----------------------
+// The GRU update (gru_update.py:27-28) and the readout projections (graph_level_output.py:36) are plain
+// [rows, K] x [K, N] products on contiguous rows: the grouped-GEMM kernel with an identity plan.
+size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP) { return (size_t)n_blocks * DP * DP * sizeof(float); }
+
+// Y[r, g*ycol + n] (+)= sum_{s < kseg} sum_{k < K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + (g*kseg + s)*w_sb] + bias[g*N + n]
+// for g < G, n < N.  K, N <= DP in {64, 128, 256}; widths, strides of A / Y multiples of 4 floats.
+int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                       long long w_sn, long long w_sk, long long w_sb, int G, int N, const float* bias, float* Y,
+                       int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  MPNN_REQUIRE(A && W && Y && workspace && rows > 0 && G > 0 && kseg > 0, MPNN_ERR_ARG, "tc_dense_gemm: bad argument");
+  MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm: DP must be 64, 128 or 256");
+  MPNN_REQUIRE((K & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldy & 3) == 0 && (acol & 3) == 0 && (ycol & 3) == 0 &&
+                   K <= DP && N <= DP,
+               MPNN_ERR_UNSUPPORTED, "tc_dense_gemm: widths must be multiples of 4 and <= DP");
+  MPNN_REQUIRE(rows < (1ll << 31) - TILE, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm: too many rows");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_dense_workspace_bytes(G * kseg, DP), MPNN_ERR_WORKSPACE,
+               "tc_dense_gemm: workspace too small");
+  float* img = (float*)workspace;
+  {
+    const long long total = (long long)G * kseg * DP * DP;
+    int g = ceil_div(total, 256);
+    if (g > 8 * mpnn_num_sms()) g = 8 * mpnn_num_sms();
+    k_tc_pack_image<<<g, 256, 0, stream>>>(W, w_sn, w_sk, w_sb, G * kseg, N, K, DP, img);
+    MPNN_CHECK_LAUNCH("k_tc_pack_image");
+  }
+  TcGemm a;
+  memset(&a, 0, sizeof(a));
+  a.A = A;
+  a.Bimg = img;
+  a.Y = Y;
+  a.lda = lda;
+  a.K = K;
+  a.ldy = ldy;
+  a.N = N;
+  a.dense = 1;
+  a.G = G;
+  a.rows = rows;
+  a.kseg = kseg;
+  a.acol = acol;
+  a.ycol = ycol;
+  a.accumulate = accumulate;
+  a.bias = bias;
+  const long long tiles = ((rows + TILE - 1) / TILE) * G;
+  const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
+  switch (DP) {
+    case 64:
+      MPNN_REQUIRE(set_smem(k_tc_edge_gemm<64>, GemmCfg<64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_dense_gemm: smem attribute");
+      k_tc_edge_gemm<64><<<grid, THREADS, GemmCfg<64>::SMEM, stream>>>(a);
+      break;
+    case 128:
+      MPNN_REQUIRE(set_smem(k_tc_edge_gemm<128>, GemmCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_dense_gemm: smem attribute");
+      k_tc_edge_gemm<128><<<grid, THREADS, GemmCfg<128>::SMEM, stream>>>(a);
+      break;
+    default:
+      MPNN_REQUIRE(set_smem(k_tc_edge_gemm<256>, GemmCfg<256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_dense_gemm: smem attribute");
+      k_tc_edge_gemm<256><<<grid, THREADS, GemmCfg<256>::SMEM, stream>>>(a);
+      break;
+  }
+  MPNN_CHECK_LAUNCH("k_tc_edge_gemm (dense)");
+  return MPNN_OK;
+}
+
+size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP) {
+  return (size_t)(tc_grid() + G + 2) * DP * DP * sizeof(float);
+}
+
+// out[g*o_sg + l*o_sl + k] = sum_r X[r, l] * D[r, g*dcol + k]   (l < M, k < N, g < G): the weight gradients X^T D
+int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol, int G,
+                          int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(X && D && out && workspace && rows > 0 && G > 0, MPNN_ERR_ARG, "tc_dense_gemm_tn: bad argument");
+  MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm_tn: DP must be 64, 128 or 256");
+  MPNN_REQUIRE((M & 3) == 0 && (N & 3) == 0 && (ldx & 3) == 0 && (ldd & 3) == 0 && (dcol & 3) == 0 && M <= DP && N <= DP,
+               MPNN_ERR_UNSUPPORTED, "tc_dense_gemm_tn: widths must be multiples of 4 and <= DP");
+  MPNN_REQUIRE(rows < (1ll << 31) - TILE, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm_tn: too many rows");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_dense_grad_workspace_bytes(G, DP), MPNN_ERR_WORKSPACE,
+               "tc_dense_gemm_tn: workspace too small");
+  TcGrad a;
+  memset(&a, 0, sizeof(a));
+  a.H = X;
+  a.dM = D;
+  a.partial = (float*)workspace;
+  a.nf = M;
+  a.mf = N;
+  a.use_alpha = 0;
+  a.dense = 1;
+  a.G = G;
+  a.RT = (int)((rows + TILE - 1) / TILE);
+  a.rows = rows;
+  a.ldh = ldx;
+  a.ldm = ldd;
+  a.bcol = dcol;
+  const int grid = tc_grid();
+  switch (DP) {
+    case 64:
+      MPNN_REQUIRE(set_smem(k_tc_table_grad<64>, GradCfg<64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_dense_gemm_tn: smem attribute");
+      k_tc_table_grad<64><<<grid, THREADS, GradCfg<64>::SMEM, stream>>>(a);
+      break;
+    case 128:
+      MPNN_REQUIRE(set_smem(k_tc_table_grad<128>, GradCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_dense_gemm_tn: smem attribute");
+      k_tc_table_grad<128><<<grid, THREADS, GradCfg<128>::SMEM, stream>>>(a);
+      break;
+    default:
+      MPNN_REQUIRE(set_smem(k_tc_table_grad<256>, GradCfg<256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_dense_gemm_tn: smem attribute");
+      k_tc_table_grad<256><<<grid, THREADS, GradCfg<256>::SMEM, stream>>>(a);
+      break;
+  }
+  MPNN_CHECK_LAUNCH("k_tc_table_grad (dense)");
+  dim3 rgrid(ceil_div(DP * DP, 256 * 4), G);
+  k_tc_table_reduce<<<rgrid, 256, 0, stream>>>(a.plan, 1, a.RT, grid, G, DP, M, N, o_sg, o_sl, a.partial, out);
+  MPNN_CHECK_LAUNCH("k_tc_table_reduce (dense)");
   return MPNN_OK;
 }
 

@@ -117,3 +117,36 @@ def test_tc_path_bit_reproducible(dev):
     assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
     for k in r1[2]:
         assert torch.equal(r1[2][k], r2[2][k]), k
+
+
+@pytest.mark.parametrize("d", [64, 100, 256])
+def test_gru_gate_gemms_on_tensor_cores(dev, d):
+    """GRUUpdate at widths 33..256: the gate products run on the tcgen05 dense-GEMM mode (TF32 operands); outputs and
+    every gradient against the fp32 CPU oracle (gru_update.py:26-35,66-68)."""
+    from mpnn_b200 import modules as M
+    from oracle import mpnn_oracle as O
+    B, N = 7, 45          # 315 rows: two full tiles and a ragged one
+    g = torch.Generator().manual_seed(d)
+    mask = (torch.rand(B, N, 1, generator=g) > 0.2).float()
+    m = torch.randn(B, N, d, generator=g)
+    h = torch.randn(B, N, d, generator=g) * mask
+    cot = torch.randn(B, N, d, generator=g)
+    torch.manual_seed(d)
+    mod = M.GRUUpdate(d, d)
+    with torch.no_grad():
+        mod.gru_cell.bias_ih.normal_(std=0.3)
+        mod.gru_cell.bias_hh.normal_(std=0.3)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    mod = mod.to(dev)
+    md, hd = m.clone().to(dev).requires_grad_(True), h.clone().to(dev).requires_grad_(True)
+    out = mod(md, hd, mask.to(dev))
+    (out * cot.to(dev)).sum().backward()
+    m0, h0 = m.clone().requires_grad_(True), h.clone().requires_grad_(True)
+    ref = O.gru_update(m0, h0, mask, sd, "")
+    (ref * cot).sum().backward()
+    assert rel_err(out.detach().cpu(), ref.detach()) <= TF32_TOL
+    assert rel_err(md.grad.cpu(), m0.grad) <= TF32_TOL
+    assert rel_err(hd.grad.cpu(), h0.grad) <= TF32_TOL
+    for k, p in mod.named_parameters():
+        assert rel_err(p.grad.cpu(), sd[k].grad) <= TF32_TOL, k
+    assert float((out.detach().cpu() * (1 - mask)).abs().max()) == 0.0
