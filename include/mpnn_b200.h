@@ -140,17 +140,28 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
 
 /* Dense GEMMs on the same tcgen05 kernels (identity plan): the GRU gate products (gru_update.py:27-28) and the
  * readout projections (graph_level_output.py:36) at widths 33..256.  TF32 operands, fp32 accumulate.
- *   Y[r, g*ycol + n] (+)= sum_{s<kseg} sum_{k<K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + (g*kseg+s)*w_sb] + bias[g*N + n]
+ *   Y[r, g*ycol + n] (+)= sum_{s<kseg} sum_{k<K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + g*w_sg + s*w_ss] + bias[g*N + n]
  *   out[g*o_sg + l*o_sl + k] = sum_r X[r, l] * D[r, g*dcol + k]                 (weight gradients X^T D) */
 size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP);
 int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
-                       long long w_sn, long long w_sk, long long w_sb, int G, int N, const float* bias, float* Y,
-                       int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
+                       long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
+                       float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
                        mpnn_stream_t stream);
 size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
 int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol, int G,
                           int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
                           size_t workspace_bytes, mpnn_stream_t stream);
+
+/* nn.Linear-shaped wrappers (W [N, K] row-major; K, N multiples of 4 up to 1024, cut into blocks of <= 256) */
+int mpnn_tc_linear_supported(int K, int N);
+size_t mpnn_tc_linear_workspace_bytes(int K, int N);
+int mpnn_tc_linear_fwd(const float* X, long long rows, int ldx, int K, const float* W, int N, const float* bias,
+                       float* Y, int ldy, int accumulate, void* workspace, size_t workspace_bytes,
+                       mpnn_stream_t stream);
+int mpnn_tc_linear_bwd_data(const float* dY, long long rows, int ldd, int N, const float* W, int K, float* dX, int ldx,
+                            int accumulate, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, const float* X, int ldx, int K,
+                              float* dW, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 
 /* ---- a1/a2: edge-network trunk = edge_map[:-1] (edge_network.py:14-21,36-37) on compacted rows -------- */
 long long mpnn_edge_trunk_saved_floats(int R, int ef, int n_growth, int P, int n_tied, long long* x_offset, int* ldx);
@@ -222,7 +233,8 @@ int mpnn_mask_bn1d_bwd(const float* x, const float* mask, const float* dy, const
 /* ---- a12: GraphLevelOutput (readout/graph_level_output.py:30-47); mask NULL = the unmasked branch (:39) - */
 size_t mpnn_glo_workspace_bytes(int B, int N, int F2, int O);
 int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float* bi, const float* Wj, const float* bj,
-                 int B, int N, int F2, int O, float* out, float* u, float* v, float* UV, mpnn_stream_t stream);
+                 int B, int N, int F2, int O, float* out, float* u, float* v, float* UV, void* workspace,
+                 size_t workspace_bytes, mpnn_stream_t stream);
 int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float* Wj, const float* u, const float* v,
                  const float* UV, const float* dout, int B, int N, int F2, int O, float* dx, float* dWi, float* dbi,
                  float* dWj, float* dbj, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);

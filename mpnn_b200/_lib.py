@@ -55,7 +55,12 @@ SIGNATURES = {
     "mpnn_tc_table_grad_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_tc_table_grad": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _Z, _P]),
     "mpnn_tc_dense_workspace_bytes": (_Z, [_I, _I]),
-    "mpnn_tc_dense_gemm": (_I, [_P, _L, _I, _I, _I, _I, _P, _L, _L, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_dense_gemm": (_I, [_P, _L, _I, _I, _I, _I, _P, _L, _L, _L, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_linear_supported": (_I, [_I, _I]),
+    "mpnn_tc_linear_workspace_bytes": (_Z, [_I, _I]),
+    "mpnn_tc_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_linear_bwd_data": (_I, [_P, _L, _I, _I, _P, _I, _P, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_linear_bwd_weight": (_I, [_P, _L, _I, _I, _P, _I, _I, _P, _P, _Z, _P]),
     "mpnn_tc_dense_grad_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_tc_dense_gemm_tn": (_I, [_P, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _L, _L, _P, _Z, _P]),
     "mpnn_scatter_edge_rows": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
@@ -78,7 +83,7 @@ SIGNATURES = {
     "mpnn_mask_bn1d_fwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _F, _P, _P, _P, _Z, _P]),
     "mpnn_mask_bn1d_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "mpnn_glo_workspace_bytes": (_Z, [_I, _I, _I, _I]),
-    "mpnn_glo_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "mpnn_glo_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_glo_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_softmax_mul_fwd": (_I, [_P, _P, _L, _I, _P, _P, _P]),
     "mpnn_softmax_mul_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P]),

@@ -16,9 +16,9 @@ extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
 extern "C" int mpnn_tc_dp(int nf, int mf);
 extern "C" size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP);
 extern "C" int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
-                                  long long w_sn, long long w_sk, long long w_sb, int G, int N, const float* bias,
-                                  float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream);
+                                  long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N,
+                                  const float* bias, float* Y, int ldy, int ycol, int accumulate, int DP,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
 extern "C" int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol,
                                      int G, int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
@@ -403,9 +403,9 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
     // [rows, d] x [d, 3d] as three d x d N-blocks on the tcgen05 grouped-GEMM kernel (TF32 operands, fp32 accumulate)
     void* sub = wp;
     size_t sub_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
-    rc = mpnn_tc_dense_gemm(m, rows, d, d, 1, 0, W_ih, 1, 3 * d, d, 3, d, b_ih, gi, 3 * d, d, 0, DP, sub, sub_bytes, stream);
+    rc = mpnn_tc_dense_gemm(m, rows, d, d, 1, 0, W_ih, 1, 3 * d, d, 0, 3, d, b_ih, gi, 3 * d, d, 0, DP, sub, sub_bytes, stream);
     if (rc) return rc;
-    rc = mpnn_tc_dense_gemm(h, rows, d, d, 1, 0, W_hh, 1, 3 * d, d, 3, d, b_hh, gh, 3 * d, d, 0, DP, sub, sub_bytes, stream);
+    rc = mpnn_tc_dense_gemm(h, rows, d, d, 1, 0, W_hh, 1, 3 * d, d, 0, 3, d, b_hh, gh, 3 * d, d, 0, DP, sub, sub_bytes, stream);
     if (rc) return rc;
   } else {
     rc = mpnn_gemm(m, W_ih, gi, R, 3 * d, d, d, 1, 3 * d, 1, 3 * d, b_ih, 0, nullptr, 0, stream);
@@ -457,10 +457,10 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
     size_t img_bytes = align_up(mpnn_tc_dense_workspace_bytes(3, DP), 256);
     void* gsub = ip + img_bytes;
     size_t gsub_bytes = sub_bytes - img_bytes;
-    if ((rc = mpnn_tc_dense_gemm(dgi, rows, 3 * d, d, 3, d, W_ih, 3 * d, 1, d, 1, d, nullptr, dm, d, 0, 0, DP, sub, sub_bytes,
+    if ((rc = mpnn_tc_dense_gemm(dgi, rows, 3 * d, d, 3, d, W_ih, 3 * d, 1, 0, d, 1, d, nullptr, dm, d, 0, 0, DP, sub, sub_bytes,
                                  stream)))
       return rc;
-    if ((rc = mpnn_tc_dense_gemm(dgh, rows, 3 * d, d, 3, d, W_hh, 3 * d, 1, d, 1, d, nullptr, dh, d, 0, 1, DP, sub, sub_bytes,
+    if ((rc = mpnn_tc_dense_gemm(dgh, rows, 3 * d, d, 3, d, W_hh, 3 * d, 1, 0, d, 1, d, nullptr, dh, d, 0, 1, DP, sub, sub_bytes,
                                  stream)))
       return rc;
     if ((rc = mpnn_tc_dense_gemm_tn(m, rows, d, d, dgi, 3 * d, d, 3, d, DP, dW_ih, d, 3 * d, gsub, gsub_bytes, stream))) return rc;

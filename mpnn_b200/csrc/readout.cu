@@ -14,11 +14,23 @@ extern "C" int mpnn_colsum(const float* X, const float* Y, long long rows, int w
                            float* out, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
 
+extern "C" int mpnn_tc_linear_supported(int K, int N);
+extern "C" size_t mpnn_tc_linear_workspace_bytes(int K, int N);
+extern "C" int mpnn_tc_linear_fwd(const float* X, long long rows, int ldx, int K, const float* W, int N, const float* bias,
+                                  float* Y, int ldy, int accumulate, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream);
+extern "C" int mpnn_tc_linear_bwd_data(const float* dY, long long rows, int ldd, int N, const float* W, int K, float* dX,
+                                       int ldx, int accumulate, void* workspace, size_t workspace_bytes,
+                                       cudaStream_t stream);
+extern "C" int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, const float* X, int ldx, int K,
+                                         float* dW, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 namespace {
 
 constexpr int KMAX = 32;  // O <= 32*KMAX = 1024
 
 // u' = mu*u + bi, v' = mu*v + bj in place; out[b] = sum_i softmax(u') * v' * mu.  One block per graph.
+template <int NK>  // NK = ceil(O / 32) rounded up to a power of two: register arrays sized to the real width
 __global__ void __launch_bounds__(256) k_glo_fwd_masked(float* __restrict__ u, float* __restrict__ v,
                                                         const float* __restrict__ mask, const float* __restrict__ bi,
                                                         const float* __restrict__ bj, int N, int O,
@@ -26,18 +38,18 @@ __global__ void __launch_bounds__(256) k_glo_fwd_masked(float* __restrict__ u, f
   extern __shared__ float sm[];  // [8][O]
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (O + 31) / 32;
-  float acc[KMAX];
+  float acc[NK];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int k = 0; k < NK; ++k) acc[k] = 0.f;
   for (int i = warp; i < N; i += 8) {
     const size_t row = (size_t)b * N + i;
     const float mu = mask[row];
     float* ur = u + row * O;
     float* vr = v + row * O;
-    float uv[KMAX];
+    float uv[NK];
     float mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
+    for (int k = 0; k < NK; ++k) {
       int o = lane + 32 * k;
       if (k < nk && o < O) {
         uv[k] = mu * ur[o] + bi[o];
@@ -48,7 +60,7 @@ __global__ void __launch_bounds__(256) k_glo_fwd_masked(float* __restrict__ u, f
     mx = warp_max(mx);
     float den = 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
+    for (int k = 0; k < NK; ++k) {
       int o = lane + 32 * k;
       if (k < nk && o < O) {
         uv[k] = expf(uv[k] - mx);
@@ -58,7 +70,7 @@ __global__ void __launch_bounds__(256) k_glo_fwd_masked(float* __restrict__ u, f
     den = warp_sum(den);
     const float inv = 1.f / den;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
+    for (int k = 0; k < NK; ++k) {
       int o = lane + 32 * k;
       if (k < nk && o < O) {
         float vv = mu * vr[o] + bj[o];
@@ -68,7 +80,7 @@ __global__ void __launch_bounds__(256) k_glo_fwd_masked(float* __restrict__ u, f
     }
   }
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < NK; ++k) {
     int o = lane + 32 * k;
     if (k < nk && o < O) sm[warp * O + o] = acc[k];
   }
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(256) k_glo_fwd_masked(float* __restrict__ u, f
 }
 
 // du', dv' from dout (masked form).  One warp per row.
+template <int NK>
 __global__ void __launch_bounds__(256) k_glo_bwd_masked(const float* __restrict__ u, const float* __restrict__ v,
                                                         const float* __restrict__ mask,
                                                         const float* __restrict__ dout, long long rows, int N, int O,
@@ -94,10 +107,10 @@ __global__ void __launch_bounds__(256) k_glo_bwd_masked(const float* __restrict_
   const float* ur = u + row * O;
   const float* vr = v + row * O;
   const float* dr = dout + b * O;
-  float s[KMAX];
+  float s[NK];
   float mx = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < NK; ++k) {
     int o = lane + 32 * k;
     if (k < nk && o < O) {
       s[k] = ur[o];
@@ -107,7 +120,7 @@ __global__ void __launch_bounds__(256) k_glo_bwd_masked(const float* __restrict_
   mx = warp_max(mx);
   float den = 0.f;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < NK; ++k) {
     int o = lane + 32 * k;
     if (k < nk && o < O) {
       s[k] = expf(s[k] - mx);
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(256) k_glo_bwd_masked(const float* __restrict_
   const float inv = 1.f / den;
   float dot = 0.f;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < NK; ++k) {
     int o = lane + 32 * k;
     if (k < nk && o < O) {
       s[k] *= inv;
@@ -127,7 +140,7 @@ __global__ void __launch_bounds__(256) k_glo_bwd_masked(const float* __restrict_
   }
   dot = warp_sum(dot);
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < NK; ++k) {
     int o = lane + 32 * k;
     if (k < nk && o < O) {
       float dg = dr[o] * mu;
@@ -562,13 +575,17 @@ size_t mpnn_glo_workspace_bytes(int B, int N, int F2, int O) {
   size_t g = mpnn_gemm_workspace_bytes(O, F2, (int)rows);
   size_t c = mpnn_colsum_workspace_bytes(rows, O);
   size_t fusedb = (size_t)mpnn_num_sms() * (2 * (size_t)O * F2 + 2 * O) * sizeof(float);
-  size_t need = 2 * align_up((size_t)rows * O * sizeof(float), 256) + align_up(g > c ? g : c, 256);
+  size_t sub = g > c ? g : c;
+  const size_t t = mpnn_tc_linear_workspace_bytes(F2, O);   // projections on the tensor cores when the widths allow
+  if (t > sub) sub = t;
+  size_t need = 2 * align_up((size_t)rows * O * sizeof(float), 256) + align_up(sub, 256);
   return need > fusedb ? need : fusedb;
 }
 
 // u, v: [B*N, O] saved for backward; UV: [B, 2, O] (unmasked form only)
 int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float* bi, const float* Wj, const float* bj,
-                 int B, int N, int F2, int O, float* out, float* u, float* v, float* UV, cudaStream_t stream) {
+                 int B, int N, int F2, int O, float* out, float* u, float* v, float* UV, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(B > 0 && N > 0 && F2 > 0 && O > 0, MPNN_ERR_ARG, "glo_fwd: bad dims");
   MPNN_REQUIRE(O <= 32 * KMAX, MPNN_ERR_UNSUPPORTED, "glo_fwd: output_dim %d > %d", O, 32 * KMAX);
   int rows = B * N;
@@ -579,10 +596,23 @@ int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float
     MPNN_CHECK_LAUNCH("k_glo_fwd_fused");
     return MPNN_OK;
   }
-  if ((rc = mpnn_gemm(x, Wi, u, rows, O, F2, F2, 1, 1, F2, O, nullptr, 0, nullptr, 0, stream))) return rc;
-  if ((rc = mpnn_gemm(x, Wj, v, rows, O, F2, F2, 1, 1, F2, O, nullptr, 0, nullptr, 0, stream))) return rc;
+  if (mpnn_tc_linear_supported(F2, O) && workspace && workspace_bytes >= mpnn_tc_linear_workspace_bytes(F2, O)) {
+    // u = x Wi^T, v = x Wj^T on the tcgen05 dense-GEMM mode (TF32 operands, fp32 accumulate)
+    if ((rc = mpnn_tc_linear_fwd(x, rows, F2, F2, Wi, O, nullptr, u, O, 0, workspace, workspace_bytes, stream))) return rc;
+    if ((rc = mpnn_tc_linear_fwd(x, rows, F2, F2, Wj, O, nullptr, v, O, 0, workspace, workspace_bytes, stream))) return rc;
+  } else {
+    if ((rc = mpnn_gemm(x, Wi, u, rows, O, F2, F2, 1, 1, F2, O, nullptr, 0, nullptr, 0, stream))) return rc;
+    if ((rc = mpnn_gemm(x, Wj, v, rows, O, F2, F2, 1, 1, F2, O, nullptr, 0, nullptr, 0, stream))) return rc;
+  }
   if (mask) {
-    k_glo_fwd_masked<<<B, 256, 8 * O * sizeof(float), stream>>>(u, v, mask, bi, bj, N, O, out);
+    const int nk = (O + 31) / 32;
+    const size_t sm = 8 * (size_t)O * sizeof(float);
+    if (nk <= 1) k_glo_fwd_masked<1><<<B, 256, sm, stream>>>(u, v, mask, bi, bj, N, O, out);
+    else if (nk <= 2) k_glo_fwd_masked<2><<<B, 256, sm, stream>>>(u, v, mask, bi, bj, N, O, out);
+    else if (nk <= 4) k_glo_fwd_masked<4><<<B, 256, sm, stream>>>(u, v, mask, bi, bj, N, O, out);
+    else if (nk <= 8) k_glo_fwd_masked<8><<<B, 256, sm, stream>>>(u, v, mask, bi, bj, N, O, out);
+    else if (nk <= 16) k_glo_fwd_masked<16><<<B, 256, sm, stream>>>(u, v, mask, bi, bj, N, O, out);
+    else k_glo_fwd_masked<KMAX><<<B, 256, sm, stream>>>(u, v, mask, bi, bj, N, O, out);
   } else {
     MPNN_REQUIRE(UV != nullptr, MPNN_ERR_ARG, "glo_fwd: UV buffer required without mask");
     k_glo_fwd_nomask<<<B, 256, (2 * O + 256) * sizeof(float), stream>>>(u, v, bi, bj, N, O, UV, out);
@@ -614,7 +644,14 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
   void* sub = wp;
   size_t sub_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
   if (mask) {
-    k_glo_bwd_masked<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
+    const int nk = (O + 31) / 32;
+    const int gb = ceil_div(rows * 32, 256);
+    if (nk <= 1) k_glo_bwd_masked<1><<<gb, 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
+    else if (nk <= 2) k_glo_bwd_masked<2><<<gb, 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
+    else if (nk <= 4) k_glo_bwd_masked<4><<<gb, 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
+    else if (nk <= 8) k_glo_bwd_masked<8><<<gb, 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
+    else if (nk <= 16) k_glo_bwd_masked<16><<<gb, 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
+    else k_glo_bwd_masked<KMAX><<<gb, 256, 0, stream>>>(u, v, mask, dout, rows, N, O, du, dv);
   } else {
     k_glo_bwd_nomask<<<B, 256, (O + 256) * sizeof(float), stream>>>(UV, dout, N, O, du, dv);
   }
@@ -627,6 +664,13 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
     MPNN_CHECK_LAUNCH("k_row_scale");
   }
   int R = (int)rows;
+  if (mpnn_tc_linear_supported(F2, O)) {
+    if ((rc = mpnn_tc_linear_bwd_data(du, rows, O, O, Wi, F2, dx, F2, 0, sub, sub_bytes, stream))) return rc;
+    if ((rc = mpnn_tc_linear_bwd_data(dv, rows, O, O, Wj, F2, dx, F2, 1, sub, sub_bytes, stream))) return rc;
+    if ((rc = mpnn_tc_linear_bwd_weight(du, rows, O, O, x, F2, F2, dWi, sub, sub_bytes, stream))) return rc;
+    if ((rc = mpnn_tc_linear_bwd_weight(dv, rows, O, O, x, F2, F2, dWj, sub, sub_bytes, stream))) return rc;
+    return MPNN_OK;
+  }
   // dx = du Wi + dv Wj  (W [O, F2] row-major)
   if ((rc = mpnn_gemm(du, Wi, dx, R, F2, O, O, 1, F2, 1, F2, nullptr, 0, nullptr, 0, stream))) return rc;
   if ((rc = mpnn_gemm(dv, Wj, dx, R, F2, O, O, 1, F2, 1, F2, nullptr, 2, nullptr, 0, stream))) return rc;

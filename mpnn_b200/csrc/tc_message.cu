@@ -781,18 +781,20 @@ __global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int dense,
   }
 }
 
-// image[(b*NKB + kb)][n][chunk ^ (n & 7)][j] = W[n*sn + k*sk + b*sb], k = kb*32 + chunk*4 + j  (zero outside N x K):
+// image[(b*NKB + kb)][n][chunk ^ (n & 7)][j] = W[n*sn + k*sk + g*sg + s*ss], b = g*kseg + s, k = kb*32 + chunk*4 + j
+// (zero outside N x K):
 // packs nb strided weight blocks straight into the shared-memory image the dense GEMM bulk-copies per stage
 __global__ void __launch_bounds__(256) k_tc_pack_image(const float* __restrict__ W, long long sn, long long sk,
-                                                       long long sb, int nb, int N, int K, int DP,
-                                                       float* __restrict__ img) {
+                                                       long long sg, long long ss, int kseg, int nb, int N, int K,
+                                                       int DP, float* __restrict__ img) {
   const int nkb = DP / KB;
   const long long total = (long long)nb * DP * DP;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int k = (int)(i % DP);
     const int n = (int)((i / DP) % DP);
     const int b = (int)(i / ((long long)DP * DP));
-    const float v = (n < N && k < K) ? __ldg(W + (size_t)n * sn + (size_t)k * sk + (size_t)b * sb) : 0.f;
+    const int g = b / kseg, sgm = b - g * kseg;
+    const float v = (n < N && k < K) ? __ldg(W + (size_t)n * sn + (size_t)k * sk + (size_t)g * sg + (size_t)sgm * ss) : 0.f;
     const int kb = k >> 5, chunk = (k & 31) >> 2, j = k & 3;
     img[(((size_t)b * nkb + kb) * DP + n) * KB + ((chunk ^ (n & 7)) << 2) + j] = v;
   }
@@ -1004,11 +1006,11 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
 // [rows, K] x [K, N] products on contiguous rows: the grouped-GEMM kernel with an identity plan.
 size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP) { return (size_t)n_blocks * DP * DP * sizeof(float); }
 
-// Y[r, g*ycol + n] (+)= sum_{s < kseg} sum_{k < K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + (g*kseg + s)*w_sb] + bias[g*N + n]
+// Y[r, g*ycol + n] (+)= sum_{s < kseg} sum_{k < K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + g*w_sg + s*w_ss] + bias[g*N + n]
 // for g < G, n < N.  K, N <= DP in {64, 128, 256}; widths, strides of A / Y multiples of 4 floats.
 int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
-                       long long w_sn, long long w_sk, long long w_sb, int G, int N, const float* bias, float* Y,
-                       int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
+                       long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
+                       float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
   MPNN_REQUIRE(A && W && Y && workspace && rows > 0 && G > 0 && kseg > 0, MPNN_ERR_ARG, "tc_dense_gemm: bad argument");
   MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm: DP must be 64, 128 or 256");
@@ -1023,7 +1025,7 @@ int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg,
     const long long total = (long long)G * kseg * DP * DP;
     int g = ceil_div(total, 256);
     if (g > 8 * mpnn_num_sms()) g = 8 * mpnn_num_sms();
-    k_tc_pack_image<<<g, 256, 0, stream>>>(W, w_sn, w_sk, w_sb, G * kseg, N, K, DP, img);
+    k_tc_pack_image<<<g, 256, 0, stream>>>(W, w_sn, w_sk, w_sg, w_ss, kseg, G * kseg, N, K, DP, img);
     MPNN_CHECK_LAUNCH("k_tc_pack_image");
   }
   TcGemm a;
@@ -1112,6 +1114,77 @@ int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const 
   dim3 rgrid(ceil_div(DP * DP, 256 * 4), G);
   k_tc_table_reduce<<<rgrid, 256, 0, stream>>>(a.plan, 1, a.RT, grid, G, DP, M, N, o_sg, o_sl, a.partial, out);
   MPNN_CHECK_LAUNCH("k_tc_table_reduce (dense)");
+  return MPNN_OK;
+}
+
+// ---- nn.Linear-shaped helpers on the dense mode: W [N, K] row-major (out-features major), K, N up to 1024 -------
+// The contraction and output widths are cut into equal blocks of <= 256 (multiples of 4).
+static bool tc_split(int W, int* parts, int* width) {
+  for (int p = 1; p <= 8; ++p) {
+    if (W % p) continue;
+    const int w = W / p;
+    if (w <= 256 && (w & 3) == 0) {
+      *parts = p;
+      *width = w;
+      return true;
+    }
+  }
+  return false;
+}
+static int tc_linear_plan(int K, int N, int* kseg, int* Ks, int* G, int* Nb) {
+  if ((K <= 32 && N <= 32) || !tc_split(K, kseg, Ks) || !tc_split(N, G, Nb)) return -1;
+  const int m = *Ks > *Nb ? *Ks : *Nb;
+  return pow2_at_least(m, 64);
+}
+
+// 1 if Y = X W^T (+ b) with these widths is served by the tensor-core dense mode
+int mpnn_tc_linear_supported(int K, int N) {
+  int a, b, c, d;
+  return tc_linear_plan(K, N, &a, &b, &c, &d) > 0 ? 1 : 0;
+}
+
+size_t mpnn_tc_linear_workspace_bytes(int K, int N) {
+  int kseg, Ks, G, Nb;
+  const int DP = tc_linear_plan(K, N, &kseg, &Ks, &G, &Nb);
+  if (DP < 0) return 0;
+  const size_t img = align_up(mpnn_tc_dense_workspace_bytes(G * kseg, DP), 256);
+  const int Gmax = G > kseg ? G : kseg;
+  return img + mpnn_tc_dense_grad_workspace_bytes(Gmax, DP);
+}
+
+// Y[rows, N] (+)= X[rows, K] W^T + bias          (graph_level_output.py:36: the i / j projections)
+int mpnn_tc_linear_fwd(const float* X, long long rows, int ldx, int K, const float* W, int N, const float* bias,
+                       float* Y, int ldy, int accumulate, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  int kseg, Ks, G, Nb;
+  const int DP = tc_linear_plan(K, N, &kseg, &Ks, &G, &Nb);
+  MPNN_REQUIRE(DP > 0, MPNN_ERR_UNSUPPORTED, "tc_linear_fwd: widths K=%d N=%d not served", K, N);
+  return mpnn_tc_dense_gemm(X, rows, ldx, Ks, kseg, Ks, W, K, 1, (long long)Nb * K, Ks, G, Nb, bias, Y, ldy, Nb, accumulate,
+                            DP, workspace, workspace_bytes, stream);
+}
+
+// dX[rows, K] (+)= dY[rows, N] W
+int mpnn_tc_linear_bwd_data(const float* dY, long long rows, int ldd, int N, const float* W, int K, float* dX, int ldx,
+                            int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  int kseg, Ks, G, Nb;
+  const int DP = tc_linear_plan(K, N, &kseg, &Ks, &G, &Nb);
+  MPNN_REQUIRE(DP > 0, MPNN_ERR_UNSUPPORTED, "tc_linear_bwd_data: widths K=%d N=%d not served", K, N);
+  // contraction over the N out-features (G segments of Nb), output over the K in-features (kseg blocks of Ks)
+  return mpnn_tc_dense_gemm(dY, rows, ldd, Nb, G, Nb, W, 1, K, Ks, (long long)Nb * K, kseg, Ks, nullptr, dX, ldx, Ks,
+                            accumulate, DP, workspace, workspace_bytes, stream);
+}
+
+// dW[N, K] = dY^T X
+int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, const float* X, int ldx, int K,
+                              float* dW, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  int kseg, Ks, G, Nb;
+  const int DP = tc_linear_plan(K, N, &kseg, &Ks, &G, &Nb);
+  MPNN_REQUIRE(DP > 0, MPNN_ERR_UNSUPPORTED, "tc_linear_bwd_weight: widths K=%d N=%d not served", K, N);
+  for (int mb = 0; mb < G; ++mb) {  // out-feature blocks: rows of dW
+    int rc = mpnn_tc_dense_gemm_tn(dY + (size_t)mb * Nb, rows, ldd, Nb, X, ldx, Ks, kseg, Ks, DP,
+                                   dW + (size_t)mb * Nb * K, Ks, K, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+  }
   return MPNN_OK;
 }
 

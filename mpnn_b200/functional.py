@@ -378,8 +378,9 @@ class GraphLevelOutputFn(torch.autograd.Function):
         u = torch.empty(B * N, O, dtype=torch.float32, device=dev)
         v = torch.empty(B * N, O, dtype=torch.float32, device=dev)
         UV = torch.empty(B, 2, O, dtype=torch.float32, device=dev) if mask is None else None
+        ws = workspace(lib.mpnn_glo_workspace_bytes(B, N, F2, O), dev)
         check(lib.mpnn_glo_fwd(ptr(x), ptr(mask_c), ptr(Wi), ptr(bi), ptr(Wj), ptr(bj), B, N, F2, O, ptr(out), ptr(u),
-                               ptr(v), ptr(UV), stream()), "glo_fwd")
+                               ptr(v), ptr(UV), ptr(ws), ws.numel(), stream()), "glo_fwd")
         ctx.save_for_backward(x, mask_c, Wi, Wj, u, v, UV)
         return out
 

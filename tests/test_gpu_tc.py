@@ -150,3 +150,32 @@ def test_gru_gate_gemms_on_tensor_cores(dev, d):
     for k, p in mod.named_parameters():
         assert rel_err(p.grad.cpu(), sd[k].grad) <= TF32_TOL, k
     assert float((out.detach().cpu() * (1 - mask)).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dims", [(64, 128), (100, 72), (256, 512)])
+@pytest.mark.parametrize("masked", [True, False])
+def test_readout_projections_on_tensor_cores(dev, dims, masked):
+    """GraphLevelOutput with 2*nf / output_dim in the tensor-core range (graph_level_output.py:30-47): the i / j
+    projections, their data and weight gradients run on the tcgen05 dense-GEMM mode (K and N cut into <= 256 blocks)."""
+    from mpnn_b200 import modules as M
+    from oracle import mpnn_oracle as O
+    nf, out_dim = dims
+    B, N = 5, 33
+    g = torch.Generator().manual_seed(nf)
+    mask = (torch.rand(B, N, 1, generator=g) > 0.25).float()
+    x = torch.randn(B, N, 2 * nf, generator=g) * 0.5
+    cot = torch.randn(B, out_dim, generator=g)
+    torch.manual_seed(nf)
+    mod = M.GraphLevelOutput(nf, out_dim)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    mod = mod.to(dev)
+    xd = x.clone().to(dev).requires_grad_(True)
+    out = mod(xd, mask=mask.to(dev) if masked else None)
+    (out * cot.to(dev)).sum().backward()
+    x0 = x.clone().requires_grad_(True)
+    ref = O.graph_level_output(x0, mask if masked else None, sd, "")
+    (ref * cot).sum().backward()
+    assert rel_err(out.detach().cpu(), ref.detach()) <= TF32_TOL
+    assert rel_err(xd.grad.cpu(), x0.grad) <= TF32_TOL
+    for k, p in mod.named_parameters():
+        assert rel_err(p.grad.cpu(), sd[k].grad) <= TF32_TOL, k
