@@ -152,6 +152,14 @@ int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const 
                           int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
                           size_t workspace_bytes, mpnn_stream_t stream);
 
+/* Fused masked GRU forward (gru_update.py:26-35,66-68) for widths 33..128: both gate products accumulate in TMEM and
+ * the gate arithmetic runs in the epilogue, so the [rows, 3d] pre-activations never reach HBM.  mpnn_gru_fwd uses it. */
+int mpnn_tc_gru_supported(int d);
+size_t mpnn_tc_gru_workspace_bytes(int d);
+int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                    const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
+                    void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
 /* nn.Linear-shaped wrappers (W [N, K] row-major; K, N multiples of 4 up to 1024, cut into blocks of <= 256) */
 int mpnn_tc_linear_supported(int K, int N);
 size_t mpnn_tc_linear_workspace_bytes(int K, int N);

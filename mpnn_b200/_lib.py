@@ -56,6 +56,9 @@ SIGNATURES = {
     "mpnn_tc_table_grad": (_I, [_P, _I, _I, _P, _I, _P, _I, _I, _I, _P, _P, _Z, _P]),
     "mpnn_tc_dense_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_tc_dense_gemm": (_I, [_P, _L, _I, _I, _I, _I, _P, _L, _L, _L, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_gru_supported": (_I, [_I]),
+    "mpnn_tc_gru_workspace_bytes": (_Z, [_I]),
+    "mpnn_tc_gru_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _Z, _P]),
     "mpnn_tc_linear_supported": (_I, [_I, _I]),
     "mpnn_tc_linear_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_tc_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _I, _I, _P, _Z, _P]),

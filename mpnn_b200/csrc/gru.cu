@@ -14,6 +14,11 @@ extern "C" int mpnn_colsum(const float* X, const float* Y, long long rows, int w
 extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
 
 extern "C" int mpnn_tc_dp(int nf, int mf);
+extern "C" int mpnn_tc_gru_supported(int d);
+extern "C" size_t mpnn_tc_gru_workspace_bytes(int d);
+extern "C" int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                               const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP);
 extern "C" int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
                                   long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N,
@@ -369,6 +374,8 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
     if (t > sub) sub = t;
   }
   size_t need = pre + align_up(sub, 256);
+  const size_t tg = mpnn_tc_gru_workspace_bytes(d);
+  if (tg > need) need = tg;
   return need > fused ? need : fused;
 }
 
@@ -391,6 +398,8 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
     MPNN_CHECK_LAUNCH("k_gru_fwd_fused");
     return MPNN_OK;
   }
+  if (mpnn_tc_gru_supported(d))  // widths 33..128: gate products + gate arithmetic fused on the tensor cores
+    return mpnn_tc_gru_fwd(m, h, mask, W_ih, W_hh, b_ih, b_hh, rows, d, h_out, gates, workspace, workspace_bytes, stream);
   char* wp = (char*)workspace;
   float* gi = (float*)wp;
   wp += align_up((size_t)rows * 3 * d * sizeof(float), 256);

@@ -749,6 +749,300 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused masked GRU forward (gru_update.py:26-35, 66-68) for widths 33..128: both gate products and the gate
+// arithmetic in ONE kernel, so the [rows, 3d] pre-activations never travel through HBM.
+//   K segment 0: A = messages m, B = W_ih  -> accumulators NI, R, Z      (TMEM columns [0,DP) [DP,2DP) [2DP,3DP))
+//   K segment 1: A = states   h, B = W_hh  -> accumulators     R, Z, NH  (R, Z accumulate on top of segment 0)
+//   epilogue   : r = sigmoid(R + b)mu, z = sigmoid(Z + b)mu, n = tanh(NI + b + r (NH + b))mu, h' = ((1-z)n + z h)mu;
+//                each 32 x 32 accumulator block is transposed through shared memory so that every global access of
+//                the epilogue (h in, h' and the four saved gate planes out) is a full 128-byte line per 8 lanes.
+// ---------------------------------------------------------------------------------------------------
+struct TcGru {
+  const float* m;      // [rows, d]
+  const float* h;      // [rows, d]
+  const float* mask;   // [rows]
+  const float* Bimg;   // [2 segments][NKB][3 blocks][DP][32] swizzled
+  const float* b_ih;   // [3d]
+  const float* b_hh;   // [3d]
+  float* hout;         // [rows, d]
+  float* gates;        // [rows, 4d]: sigmoid r | sigmoid z | tanh n | nh
+  long long rows;
+  int d;
+};
+
+// MUFU.TANH (max relative error 2^-11, the same order as the TF32 operands feeding it): the gate arithmetic of the
+// fused GRU epilogue is issue-bound on 8 warps, so the 1-instruction forms matter
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+
+template <int DP>
+struct GruCfg {
+  static constexpr int A_BYTES = TILE * 128;
+  static constexpr int B_BYTES = 3 * DP * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = DP == 64 ? 4 : 3;
+  static constexpr int EPW = 8;                          // epilogue warps: two per TMEM lane quadrant, split by column chunk
+  static constexpr int GRU_THREADS = PRODUCERS + 32 + 32 * EPW;
+  static constexpr int EPI_BYTES = EPW * 32 * 33 * 4;
+  static constexpr int SMEM = NSTAGE * STAGE + EPI_BYTES + 1024 + 256;
+  static constexpr int NACC = (8 * DP <= 512) ? 2 : 1;   // accumulator sets (4*DP columns each) that fit in TMEM
+  static constexpr int TCOLS = 512;
+};
+
+// image[((s*NKB + kb)*3 + j)][n][chunk ^ (n & 7)][4]: segment s, K-block kb, gate block j; W_* are [d, 3d] input-major
+__global__ void __launch_bounds__(256) k_tc_gru_pack(const float* __restrict__ W_ih, const float* __restrict__ W_hh,
+                                                     int d, int DP, float* __restrict__ img) {
+  const int nkb = DP / KB;
+  const long long total = 2LL * 3 * DP * DP;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int k = (int)(i % DP);
+    const int n = (int)((i / DP) % DP);
+    const int j = (int)((i / ((long long)DP * DP)) % 3);
+    const int sgm = (int)(i / (3LL * DP * DP));
+    // segment 0 blocks: NI, R, Z = gates 2, 0, 1 of W_ih; segment 1 blocks: R, Z, NH = gates 0, 1, 2 of W_hh
+    const int gate = sgm == 0 ? (j == 0 ? 2 : j - 1) : j;
+    const float* W = sgm == 0 ? W_ih : W_hh;
+    const float v = (n < d && k < d) ? __ldg(W + (size_t)k * 3 * d + (size_t)gate * d + n) : 0.f;
+    const int kb = k >> 5, chunk = (k & 31) >> 2, jj = k & 3;
+    img[((((size_t)sgm * nkb + kb) * 3 + j) * DP + n) * KB + ((chunk ^ (n & 7)) << 2) + jj] = v;
+  }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru a) {
+  using C = GruCfg<DP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE + C::EPI_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSTAGE + s); };
+  auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * C::NSTAGE + s); };
+  auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * C::NSTAGE + 2 + s); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) {
+      mbar_init(full_bar(s), PRODUCERS + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(accfull_bar(s), 1);
+      mbar_init(accempty_bar(s), 32 * C::EPW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = (int)((a.rows + TILE - 1) / TILE);
+  const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t0 = blockIdx.x * per;
+  const int t1 = min(t0 + per, n_tiles);
+  constexpr int NKB = DP / KB;
+  const int d = a.d;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int sub = tid >> 3, chunk = tid & 7;
+    int stage = 0, phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      const long long pos = (long long)t * TILE;
+      for (int sk = 0; sk < 2 * NKB; ++sk) {
+        const int seg = sk / NKB, kb = sk - seg * NKB;
+        const float* A = seg == 0 ? a.m : a.h;
+        const int kk = kb * KB + chunk * 4;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t As = smem_base + stage * C::STAGE;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);
+          bulk_copy(As + C::A_BYTES, a.Bimg + (size_t)(seg * NKB + kb) * 3 * (DP * KB), C::B_BYTES, full_bar(stage));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long row = pos + i * 16 + sub;
+          const bool ok = row < a.rows && kk < d;
+          cp_async16(As + swz(i * 16 + sub, chunk), ok ? A + (size_t)row * d + kk : A, ok ? 16u : 0u);
+        }
+        cp_async_arrive_noinc(full_bar(stage));
+        if (++stage == C::NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE, DP, 0, 0);
+      int stage = 0, phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int i = t - t0, acc = i % C::NACC, use = i / C::NACC;
+        mbar_wait(accempty_bar(acc), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dbase = tmem_base + (uint32_t)(acc * 4 * DP);
+        for (int sk = 0; sk < 2 * NKB; ++sk) {
+          const int seg = sk / NKB, kb = sk - seg * NKB;
+          mbar_wait(full_bar(stage), phase);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          const uint64_t ad = make_sdesc(sa, 16, 1024);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            // segment 0 blocks -> NI, R, Z (column blocks 0, 1, 2); segment 1 blocks -> R, Z, NH (1, 2, 3)
+            const uint32_t dcol = dbase + (uint32_t)((seg + j) * DP);
+            const uint64_t bd = make_sdesc(sa + C::A_BYTES + j * DP * 128, 16, 1024);
+            const bool carried = seg == 1 && j < 2;   // R and Z continue the sums started by segment 0
+#pragma unroll
+            for (int ks = 0; ks < KB / 8; ++ks)
+              umma_tf32(dcol, ad + 2u * ks, bd + 2u * ks, idesc, (carried || (kb | ks) != 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == C::NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(accfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quadrant of this warp
+    const int ew = warp - (MMA_WARP + 1);   // 0 .. EPW-1
+    const int half = ew >> 2;               // which 32-column chunks this warp takes
+    float* tb = epi + ew * (32 * 33);
+    const int orow = lane >> 3, ocol = (lane & 7) * 4;
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, acc = i % C::NACC, use = i / C::NACC;
+      const long long pos = (long long)t * TILE + q * 32;
+      mbar_wait(accfull_bar(acc), use & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 4 * DP);
+      float mu[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long row = pos + it * 4 + orow;
+        mu[it] = row < a.rows ? __ldg(a.mask + row) : 0.f;
+      }
+#pragma unroll 1
+      for (int c0 = 32 * half; c0 < DP; c0 += 32 * (C::EPW / 4)) {
+        if (c0 >= d) break;
+        const int col = c0 + ocol;
+        const bool cok = col < d;
+        float4 sr[8], sz[8], nh[8];
+        float v[32];
+        // ---- R ----
+        tmem_ld32(tacc + (uint32_t)(DP + c0), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = v[c];
+        __syncwarp();
+        {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok) {
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.b_ih + col));
+            const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.b_hh + col));
+            b = make_float4(b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const float* p = tb + (it * 4 + orow) * 33 + ocol;
+            sr[it] = make_float4(fast_sigmoid(p[0] + b.x), fast_sigmoid(p[1] + b.y), fast_sigmoid(p[2] + b.z), fast_sigmoid(p[3] + b.w));
+          }
+        }
+        __syncwarp();
+        // ---- Z ----
+        tmem_ld32(tacc + (uint32_t)(2 * DP + c0), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = v[c];
+        __syncwarp();
+        {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok) {
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.b_ih + d + col));
+            const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.b_hh + d + col));
+            b = make_float4(b1.x + b2.x, b1.y + b2.y, b1.z + b2.z, b1.w + b2.w);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const float* p = tb + (it * 4 + orow) * 33 + ocol;
+            sz[it] = make_float4(fast_sigmoid(p[0] + b.x), fast_sigmoid(p[1] + b.y), fast_sigmoid(p[2] + b.z), fast_sigmoid(p[3] + b.w));
+          }
+        }
+        __syncwarp();
+        // ---- NH ----
+        tmem_ld32(tacc + (uint32_t)(3 * DP + c0), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = v[c];
+        __syncwarp();
+        {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cok) b = __ldg(reinterpret_cast<const float4*>(a.b_hh + 2 * d + col));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const float* p = tb + (it * 4 + orow) * 33 + ocol;
+            nh[it] = make_float4(p[0] + b.x, p[1] + b.y, p[2] + b.z, p[3] + b.w);
+          }
+        }
+        __syncwarp();
+        // ---- NI, then the gate arithmetic and the coalesced stores ----
+        tmem_ld32(tacc + (uint32_t)c0, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = v[c];
+        __syncwarp();
+        if (cok) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.b_ih + 2 * d + col));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const long long row = pos + it * 4 + orow;
+            if (row < a.rows) {
+              const float* p = tb + (it * 4 + orow) * 33 + ocol;
+              const float m_ = mu[it];
+              const float4 hv = __ldg(reinterpret_cast<const float4*>(a.h + (size_t)row * d + col));
+              float4 tn, ho;
+              tn.x = fast_tanh(p[0] + b.x + sr[it].x * m_ * nh[it].x);
+              tn.y = fast_tanh(p[1] + b.y + sr[it].y * m_ * nh[it].y);
+              tn.z = fast_tanh(p[2] + b.z + sr[it].z * m_ * nh[it].z);
+              tn.w = fast_tanh(p[3] + b.w + sr[it].w * m_ * nh[it].w);
+              ho.x = ((1.f - sz[it].x * m_) * tn.x * m_ + sz[it].x * m_ * hv.x) * m_;
+              ho.y = ((1.f - sz[it].y * m_) * tn.y * m_ + sz[it].y * m_ * hv.y) * m_;
+              ho.z = ((1.f - sz[it].z * m_) * tn.z * m_ + sz[it].z * m_ * hv.z) * m_;
+              ho.w = ((1.f - sz[it].w * m_) * tn.w * m_ + sz[it].w * m_ * hv.w) * m_;
+              *reinterpret_cast<float4*>(a.hout + (size_t)row * d + col) = ho;
+              float* g = a.gates + (size_t)row * 4 * d + col;
+              *reinterpret_cast<float4*>(g) = sr[it];
+              *reinterpret_cast<float4*>(g + d) = sz[it];
+              *reinterpret_cast<float4*>(g + 2 * d) = tn;
+              *reinterpret_cast<float4*>(g + 3 * d) = nh[it];
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(accempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
 // out[u*su + l*sl + k] (l < M, k < N) = sum over the CTAs whose tile range touches type u of partial[cta + u][l][k]
 // (fixed order).  Plan mode: the tile range of a type comes from tile_off; dense mode: type u owns tiles [u*RT, (u+1)*RT).
 __global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int dense, int RT, int grid_ctas, int ntypes,
@@ -1185,6 +1479,40 @@ int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, c
                                    dW + (size_t)mb * Nb * K, Ks, K, workspace, workspace_bytes, stream);
     if (rc) return rc;
   }
+  return MPNN_OK;
+}
+
+// ---- fused masked GRU forward on the tensor cores (widths 33..128, multiples of 4) -------------------------------
+int mpnn_tc_gru_supported(int d) { return (d > 32 && d <= 128 && (d & 3) == 0) ? 1 : 0; }
+
+size_t mpnn_tc_gru_workspace_bytes(int d) {
+  if (!mpnn_tc_gru_supported(d)) return 0;
+  const int DP = pow2_at_least(d, 64);
+  return (size_t)2 * 3 * DP * DP * sizeof(float);
+}
+
+// h_out [rows, d], gates [rows, 4d] (sigmoid r | sigmoid z | tanh n | nh: what mpnn_gru_bwd reads)
+int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                    const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(mpnn_tc_gru_supported(d), MPNN_ERR_UNSUPPORTED, "tc_gru_fwd: width %d not served", d);
+  MPNN_REQUIRE(rows > 0 && rows < (1ll << 31) - TILE, MPNN_ERR_ARG, "tc_gru_fwd: bad row count");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_workspace_bytes(d), MPNN_ERR_WORKSPACE, "tc_gru_fwd: workspace too small");
+  const int DP = pow2_at_least(d, 64);
+  float* img = (float*)workspace;
+  k_tc_gru_pack<<<ceil_div(2LL * 3 * DP * DP, 256), 256, 0, stream>>>(W_ih, W_hh, d, DP, img);
+  MPNN_CHECK_LAUNCH("k_tc_gru_pack");
+  TcGru a = {m, h, mask, img, b_ih, b_hh, h_out, gates, rows, d};
+  const long long tiles = (rows + TILE - 1) / TILE;
+  const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
+  if (DP == 64) {
+    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<64>, GruCfg<64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
+    k_tc_gru_fwd<64><<<grid, GruCfg<64>::GRU_THREADS, GruCfg<64>::SMEM, stream>>>(a);
+  } else {
+    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<128>, GruCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
+    k_tc_gru_fwd<128><<<grid, GruCfg<128>::GRU_THREADS, GruCfg<128>::SMEM, stream>>>(a);
+  }
+  MPNN_CHECK_LAUNCH("k_tc_gru_fwd");
   return MPNN_OK;
 }
 

@@ -119,7 +119,7 @@ def test_tc_path_bit_reproducible(dev):
         assert torch.equal(r1[2][k], r2[2][k]), k
 
 
-@pytest.mark.parametrize("d", [64, 100, 256])
+@pytest.mark.parametrize("d", [64, 36, 100, 128, 256])
 def test_gru_gate_gemms_on_tensor_cores(dev, d):
     """GRUUpdate at widths 33..256: the gate products run on the tcgen05 dense-GEMM mode (TF32 operands); outputs and
     every gradient against the fp32 CPU oracle (gru_update.py:26-35,66-68)."""
