@@ -21,6 +21,11 @@ extern "C" int mpnn_colsum(const float* X, const float* Y, long long rows, int w
                            float* out, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
 
+extern "C" size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
+extern "C" int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol,
+                                     int G, int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream);
+
 namespace {
 
 constexpr int TR = 64;        // rows per tile
@@ -70,6 +75,18 @@ __global__ void k_pad_copy(const float* __restrict__ src, int R, int w, float* _
   if (t >= (long long)R * ld) return;
   int r = (int)(t / ld), c = (int)(t - (long long)r * ld);
   dst[t] = c < w ? src[(long long)r * w + c] : 0.f;
+}
+
+// out[c][r] = in[r][c] for a square [P, P] matrix (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) k_transpose_sq(const float* __restrict__ in, int P, float* __restrict__ out) {
+  __shared__ float t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8)
+    if (by + j < P && bx + tx < P) t[j][tx] = in[(size_t)(by + j) * P + bx + tx];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+    if (bx + j < P && by + tx < P) out[(size_t)(bx + j) * P + by + tx] = t[tx][j];
 }
 
 __global__ void k_relu_mask(float* __restrict__ d, const float* __restrict__ a, long long n) {
@@ -299,6 +316,11 @@ int tied_grid(int R, size_t smem_bytes) {
 size_t fwd_smem(int PP) { return ((size_t)PP * PP + 2 * (size_t)PP * TRP) * sizeof(float); }
 size_t bwd_smem(int PP) { return ((size_t)PP * PP + 3 * (size_t)TR * (PP + 4)) * sizeof(float); }
 constexpr int MAX_PP_SMEM = 128;
+constexpr int MAX_TIED = 64;   // tied layers the wide-trunk backward can stack (the reference uses 50)
+constexpr int WIDE_STACK_ROWS = 256;   // the delta stack is kept only for few rows (typed path: distinct bond rows)
+// widths whose tied-weight gradient runs as ONE stacked X^T D GEMM on the tensor cores (TF32 operands)
+inline int wide_block(int P) { return P % 256 == 0 ? 256 : (P % 128 == 0 ? 128 : 64); }
+inline bool wide_dw_on_tc(int P) { return P % 64 == 0 && P >= 256; }
 
 }  // namespace
 
@@ -317,9 +339,20 @@ size_t mpnn_edge_trunk_workspace_bytes(int R, int ef, int n_growth, int P) {
   int PP = pad4(P);
   size_t g = mpnn_gemm_workspace_bytes(P, P, R);  // largest split-K user (weight grads)
   size_t c = mpnn_colsum_workspace_bytes(R, PP);
-  size_t partial = (size_t)2 * mpnn_num_sms() * PP * PP * sizeof(float);
+  size_t partial = PP <= MAX_PP_SMEM ? (size_t)2 * mpnn_num_sms() * PP * PP * sizeof(float) : 0;
   size_t dA = 2 * (size_t)R * PP * sizeof(float);
-  return align_up(g > c ? g : c, 256) + align_up(partial, 256) + align_up(dA, 256) + 1024;
+  size_t wide = 0;
+  if (PP > MAX_PP_SMEM) {
+    // wide trunks: transposed weight + the stacked deltas of all tied layers (+ the tensor-core X^T D workspace)
+    size_t skinny = mpnn_gemm_workspace_bytes(R, P, P);
+    if (skinny > g) g = skinny;
+    wide = align_up((size_t)P * P * sizeof(float), 256) + 512;
+    if (R <= WIDE_STACK_ROWS) {
+      wide += align_up((size_t)MAX_TIED * R * PP * sizeof(float), 256);
+      if (wide_dw_on_tc(P)) wide += align_up(mpnn_tc_dense_grad_workspace_bytes(P / wide_block(P), wide_block(P)), 256);
+    }
+  }
+  return align_up(g > c ? g : c, 256) + align_up(partial, 256) + align_up(dA, 256) + wide + 1024;
 }
 
 int mpnn_edge_trunk_fwd(const float* rows_in, int R, int ef, int n_growth, const float* const* growth_w,
@@ -381,12 +414,16 @@ int mpnn_edge_trunk_bwd(const float* rows_in, int R, int ef, int n_growth, const
   const int PP = lo.PP;
   char* wp = (char*)workspace;
   size_t gbytes = mpnn_gemm_workspace_bytes(P, P, R);
+  if (PP > MAX_PP_SMEM) {
+    const size_t skinny = mpnn_gemm_workspace_bytes(R, P, P);
+    if (skinny > gbytes) gbytes = skinny;
+  }
   size_t cbytes = mpnn_colsum_workspace_bytes(R, PP);
   size_t sub_bytes = align_up(gbytes > cbytes ? gbytes : cbytes, 256);
   void* sub = wp;
   wp += sub_bytes;
   float* partial = (float*)wp;
-  wp += align_up((size_t)2 * mpnn_num_sms() * PP * PP * sizeof(float), 256);
+  wp += align_up(PP <= MAX_PP_SMEM ? (size_t)2 * mpnn_num_sms() * PP * PP * sizeof(float) : 0, 256);
   float* dA = (float*)wp;  // [R, PP] grad w.r.t. tied input (then reused down the growth layers)
   float* dB = dA + (size_t)R * PP;
 
@@ -410,27 +447,69 @@ int mpnn_edge_trunk_bwd(const float* rows_in, int R, int ef, int n_growth, const
     k_tied_dw_reduce<<<ceil_div(P * P, 256), 256, 0, stream>>>(partial, grid, P, PP, d_w_tied);
     MPNN_CHECK_LAUNCH("k_tied_dw_reduce");
   } else {
-    // layer-by-layer: delta = d * relu'(a_l); dW += delta^T a_{l-1}; d = delta W
-    MPNN_CUDA(cudaMemsetAsync(dA, 0, (size_t)R * PP * sizeof(float), stream));
-    MPNN_CUDA(cudaMemcpy2DAsync(dA, (size_t)PP * sizeof(float), dx, (size_t)lddx * sizeof(float), (size_t)P * sizeof(float),
-                                R, cudaMemcpyDeviceToDevice, stream));
-    MPNN_CUDA(cudaMemsetAsync(d_w_tied, 0, (size_t)P * P * sizeof(float), stream));
-    float* cur = dA;
-    float* nxt = dB;
-    for (int l = n_tied; l >= 1; --l) {
-      const float* al = tied_out + (size_t)(l - 1) * R * PP;
-      const float* ap = (l == 1) ? tied_in : tied_out + (size_t)(l - 2) * R * PP;
-      k_relu_mask<<<ceil_div((long long)R * PP, 256), 256, 0, stream>>>(cur, al, (long long)R * PP);
-      int rc = mpnn_gemm(cur, ap, d_w_tied, P, P, R, 1, PP, PP, 1, P, nullptr, 2, sub, sub_bytes, stream);
-      if (rc) return rc;
-      if (PP != P) MPNN_CUDA(cudaMemsetAsync(nxt, 0, (size_t)R * PP * sizeof(float), stream));
-      rc = mpnn_gemm(cur, w_tied, nxt, R, P, P, PP, 1, P, 1, PP, nullptr, 0, sub, sub_bytes, stream);
-      if (rc) return rc;
-      float* t = cur;
-      cur = nxt;
-      nxt = t;
+    // Wide trunk (P = 256, 625, 4096: hidden >= 128 in the reference's models), R = distinct bond rows (tens):
+    //   delta_l = d_l * relu'(a_l) is kept for every layer in one stack [L*R, PP];
+    //   d_{l-1} = delta_l W runs on the skinny GEMM against a TRANSPOSED copy of W (k-contiguous operand: 4x faster
+    //   than the strided form), and the tied-weight gradient sum_l delta_l^T a_{l-1} is ONE GEMM over the stacked
+    //   rows -- on the tensor cores when P is a multiple of 64, else layer by layer in fp32.
+    const bool stacked = R <= WIDE_STACK_ROWS && n_tied <= MAX_TIED;
+    char* xp = (char*)(dB + (size_t)R * PP);
+    xp = (char*)align_up((size_t)xp, 256);
+    float* Wt = (float*)xp;
+    xp += align_up((size_t)P * P * sizeof(float), 256);
+    float* stack = (float*)xp;
+    xp += align_up((size_t)MAX_TIED * R * PP * sizeof(float), 256);
+    void* tcws = xp;
+    const size_t tcws_bytes = wide_dw_on_tc(P) ? mpnn_tc_dense_grad_workspace_bytes(P / wide_block(P), wide_block(P)) : 0;
+    {
+      dim3 tg(ceil_div(P, 32), ceil_div(P, 32));
+      k_transpose_sq<<<tg, 256, 0, stream>>>(w_tied, P, Wt);
+      MPNN_CHECK_LAUNCH("k_transpose_sq");
     }
-    if (cur != dA) MPNN_CUDA(cudaMemcpyAsync(dA, cur, (size_t)R * PP * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    const size_t slab = (size_t)R * PP;
+    // layer l's delta lives in slot(l): its own slab of the stack, or (many rows: per-edge path) one of two buffers
+    auto slot = [&](int l) { return stacked ? stack + (size_t)(l - 1) * slab : (((n_tied - l) & 1) ? dB : dA); };
+    float* top = slot(n_tied);
+    if (PP != P) {
+      if (stacked) MPNN_CUDA(cudaMemsetAsync(stack, 0, (size_t)n_tied * slab * sizeof(float), stream));
+      MPNN_CUDA(cudaMemsetAsync(dA, 0, 2 * slab * sizeof(float), stream));
+    }
+    MPNN_CUDA(cudaMemcpy2DAsync(top, (size_t)PP * sizeof(float), dx, (size_t)lddx * sizeof(float), (size_t)P * sizeof(float),
+                                R, cudaMemcpyDeviceToDevice, stream));
+    const bool contiguous_acts = lo.tied_in_off + slab == lo.tied_off;
+    const bool tc_dw = stacked && wide_dw_on_tc(P) && contiguous_acts;
+    if (!tc_dw) MPNN_CUDA(cudaMemsetAsync(d_w_tied, 0, (size_t)P * P * sizeof(float), stream));
+    for (int l = n_tied; l >= 1; --l) {
+      float* cur = slot(l);
+      const float* al = tied_out + (size_t)(l - 1) * slab;
+      const float* ap = (l == 1) ? tied_in : tied_out + (size_t)(l - 2) * slab;
+      k_relu_mask<<<ceil_div((long long)slab, 256), 256, 0, stream>>>(cur, al, (long long)slab);
+      MPNN_CHECK_LAUNCH("k_relu_mask");
+      int rc;
+      if (!tc_dw) {
+        rc = mpnn_gemm(cur, ap, d_w_tied, P, P, R, 1, PP, PP, 1, P, nullptr, 2, sub, sub_bytes, stream);
+        if (rc) return rc;
+      }
+      float* nxt = (l == 1) ? (stacked ? dA : (cur == dA ? dB : dA)) : slot(l - 1);
+      // d_{l-1}[r, i] = sum_o delta[r, o] W[o, i] = sum_o delta[r, o] Wt[i, o]: operand Wt is k(=o)-contiguous
+      rc = mpnn_gemm(cur, Wt, nxt, R, P, P, PP, 1, 1, P, PP, nullptr, 0, sub, sub_bytes, stream);
+      if (rc) return rc;
+    }
+    if (!stacked) {  // the gradient w.r.t. the tied input must end up in dA
+      float* last = (slot(1) == dA) ? dB : dA;
+      if (last != dA) MPNN_CUDA(cudaMemcpyAsync(dA, last, slab * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+    if (tc_dw) {
+      // dW[o, i] = sum_{l, r} delta_l[r, o] a_{l-1}[r, i]: X = the delta stack, D = the saved activations (tied input
+      // followed by the outputs of layers 1..L-1 are contiguous in `saved`), K = L*R stacked rows
+      const int blk = wide_block(P);
+      const long long krows = (long long)n_tied * R;
+      for (int mb = 0; mb < P / blk; ++mb) {
+        int rc = mpnn_tc_dense_gemm_tn(stack + (size_t)mb * blk, krows, PP, blk, tied_in, PP, blk, P / blk, blk, blk,
+                                       d_w_tied + (size_t)mb * blk * P, blk, P, tcws, tcws_bytes, stream);
+        if (rc) return rc;
+      }
+    }
   }
 
   // growth layers, last to first: dA holds d(output of growth g) with row stride gld[g]

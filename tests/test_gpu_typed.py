@@ -179,3 +179,33 @@ def test_typed_path_bit_reproducible(dev):
     assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1])
     for k in r1[2]:
         assert torch.equal(r1[2][k], r2[2][k]), k
+
+
+@pytest.mark.parametrize("shape", [(33, 4096, 4096), (7, 300, 513), (64, 1024, 130), (1, 256, 128)])
+@pytest.mark.parametrize("form", ["nt", "nn"])
+def test_skinny_gemm_matches_torch(dev, shape, form):
+    """mpnn_gemm's skinny path (M <= 64 rows: the wide trunk on the distinct bond rows, edge_network.py:20, and its
+    last Linear) in both operand forms, with bias + ReLU and with accumulation, against torch in fp64."""
+    import ctypes
+    from mpnn_b200 import _lib
+    from mpnn_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) if form == "nt" else torch.randn(K, N, generator=g)).to(dev) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(dev)
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    ws = _lib.workspace(lib.mpnn_gemm_workspace_bytes(M, N, K), dev)
+    sbk, sbn = (1, K) if form == "nt" else (N, 1)
+    ref = A.double() @ (W.double().t() if form == "nt" else W.double())
+    # bias + ReLU
+    C = torch.empty(M, N, device=dev)
+    check(lib.mpnn_gemm(ptr(A), ptr(W), ptr(C), M, N, K, K, 1, sbk, sbn, N, ptr(bias), 1, ptr(ws), ws.numel(), stream()), "gemm")
+    want = torch.relu(ref + bias.double())
+    assert float((C.double() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
+    # accumulate into C
+    C = C0.clone()
+    check(lib.mpnn_gemm(ptr(A), ptr(W), ptr(C), M, N, K, K, 1, sbk, sbn, N, None, 2, ptr(ws), ws.numel(), stream()), "gemm")
+    want = ref + C0.double()
+    assert float((C.double() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
