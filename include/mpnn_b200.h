@@ -152,7 +152,7 @@ int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const 
                           int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
                           size_t workspace_bytes, mpnn_stream_t stream);
 
-/* Fused masked GRU forward (gru_update.py:26-35,66-68) for widths 33..128: both gate products accumulate in TMEM and
+/* Fused masked GRU forward (gru_update.py:26-35,66-68) for widths 33..256 (256: two 128-column blocks): both gate products accumulate in TMEM and
  * the gate arithmetic runs in the epilogue, so the [rows, 3d] pre-activations never reach HBM.  mpnn_gru_fwd uses it. */
 int mpnn_tc_gru_supported(int d);
 size_t mpnn_tc_gru_workspace_bytes(int d);

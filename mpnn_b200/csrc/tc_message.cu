@@ -762,13 +762,14 @@ struct TcGru {
   const float* m;      // [rows, d]
   const float* h;      // [rows, d]
   const float* mask;   // [rows]
-  const float* Bimg;   // [2 segments][NKB][3 blocks][DP][32] swizzled
+  const float* Bimg;   // [column blocks][2 segments][NKB][3 gate blocks][DP][32] swizzled
   const float* b_ih;   // [3d]
   const float* b_hh;   // [3d]
   float* hout;         // [rows, d]
   float* gates;        // [rows, 4d]: sigmoid r | sigmoid z | tanh n | nh
   long long rows;
   int d;
+  int ncb;             // output-column blocks of DP (d = 256: two blocks of 128, the A tiles are read once per block)
 };
 
 // MUFU.TANH (max relative error 2^-11, the same order as the TF32 operands feeding it): the gate arithmetic of the
@@ -780,7 +781,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 __device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 
-template <int DP>
+template <int DP, int KP>   // DP: output columns per tile (N of the MMAs), KP: padded contraction width
 struct GruCfg {
   static constexpr int A_BYTES = TILE * 128;
   static constexpr int B_BYTES = 3 * DP * 128;
@@ -794,28 +795,31 @@ struct GruCfg {
   static constexpr int TCOLS = 512;
 };
 
-// image[((s*NKB + kb)*3 + j)][n][chunk ^ (n & 7)][4]: segment s, K-block kb, gate block j; W_* are [d, 3d] input-major
+// image[(((cb*2 + s)*NKB + kb)*3 + j)][n][chunk ^ (n & 7)][4]: column block cb, segment s, K-block kb, gate block j;
+// W_* are [d, 3d] input-major
 __global__ void __launch_bounds__(256) k_tc_gru_pack(const float* __restrict__ W_ih, const float* __restrict__ W_hh,
-                                                     int d, int DP, float* __restrict__ img) {
-  const int nkb = DP / KB;
-  const long long total = 2LL * 3 * DP * DP;
+                                                     int d, int DP, int KP, int ncb, float* __restrict__ img) {
+  const int nkb = KP / KB;
+  const long long total = (long long)ncb * 2 * 3 * DP * KP;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int k = (int)(i % DP);
-    const int n = (int)((i / DP) % DP);
-    const int j = (int)((i / ((long long)DP * DP)) % 3);
-    const int sgm = (int)(i / (3LL * DP * DP));
+    const int k = (int)(i % KP);
+    const int nl = (int)((i / KP) % DP);
+    const int j = (int)((i / ((long long)DP * KP)) % 3);
+    const int sgm = (int)((i / (3LL * DP * KP)) % 2);
+    const int cb = (int)(i / (6LL * DP * KP));
+    const int n = cb * DP + nl;
     // segment 0 blocks: NI, R, Z = gates 2, 0, 1 of W_ih; segment 1 blocks: R, Z, NH = gates 0, 1, 2 of W_hh
     const int gate = sgm == 0 ? (j == 0 ? 2 : j - 1) : j;
     const float* W = sgm == 0 ? W_ih : W_hh;
     const float v = (n < d && k < d) ? __ldg(W + (size_t)k * 3 * d + (size_t)gate * d + n) : 0.f;
     const int kb = k >> 5, chunk = (k & 31) >> 2, jj = k & 3;
-    img[((((size_t)sgm * nkb + kb) * 3 + j) * DP + n) * KB + ((chunk ^ (n & 7)) << 2) + jj] = v;
+    img[(((((size_t)cb * 2 + sgm) * nkb + kb) * 3 + j) * DP + nl) * KB + ((chunk ^ (nl & 7)) << 2) + jj] = v;
   }
 }
 
-template <int DP>
-__global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru a) {
-  using C = GruCfg<DP>;
+template <int DP, int KP>
+__global__ void __launch_bounds__(GruCfg<DP, KP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru a) {
+  using C = GruCfg<DP, KP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* epi = reinterpret_cast<float*>(smem + C::NSTAGE * C::STAGE);
@@ -846,11 +850,12 @@ __global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_tiles = (int)((a.rows + TILE - 1) / TILE);
+  const int ncb = a.ncb;
+  const int n_tiles = (int)((a.rows + TILE - 1) / TILE) * ncb;   // tile t -> row block t / ncb, column block t % ncb
   const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
-  constexpr int NKB = DP / KB;
+  constexpr int NKB = KP / KB;
   const int d = a.d;
 
   if (warp < 4) {
@@ -858,7 +863,8 @@ __global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru
     const int sub = tid >> 3, chunk = tid & 7;
     int stage = 0, phase = 0;
     for (int t = t0; t < t1; ++t) {
-      const long long pos = (long long)t * TILE;
+      const long long pos = (long long)(t / ncb) * TILE;
+      const int cb = t % ncb;
       for (int sk = 0; sk < 2 * NKB; ++sk) {
         const int seg = sk / NKB, kb = sk - seg * NKB;
         const float* A = seg == 0 ? a.m : a.h;
@@ -867,7 +873,8 @@ __global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru
         const uint32_t As = smem_base + stage * C::STAGE;
         if (tid == 0) {
           mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);
-          bulk_copy(As + C::A_BYTES, a.Bimg + (size_t)(seg * NKB + kb) * 3 * (DP * KB), C::B_BYTES, full_bar(stage));
+          bulk_copy(As + C::A_BYTES, a.Bimg + (size_t)((cb * 2 + seg) * NKB + kb) * 3 * (DP * KB), C::B_BYTES,
+                    full_bar(stage));
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -927,7 +934,8 @@ __global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru
     const int orow = lane >> 3, ocol = (lane & 7) * 4;
     for (int t = t0; t < t1; ++t) {
       const int i = t - t0, acc = i % C::NACC, use = i / C::NACC;
-      const long long pos = (long long)t * TILE + q * 32;
+      const long long pos = (long long)(t / ncb) * TILE + q * 32;
+      const int cbase = (t % ncb) * DP;   // first output column of this tile
       mbar_wait(accfull_bar(acc), use & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 4 * DP);
@@ -939,8 +947,8 @@ __global__ void __launch_bounds__(GruCfg<DP>::GRU_THREADS, 1) k_tc_gru_fwd(TcGru
       }
 #pragma unroll 1
       for (int c0 = 32 * half; c0 < DP; c0 += 32 * (C::EPW / 4)) {
-        if (c0 >= d) break;
-        const int col = c0 + ocol;
+        if (cbase + c0 >= d) break;
+        const int col = cbase + c0 + ocol;
         const bool cok = col < d;
         float4 sr[8], sz[8], nh[8];
         float v[32];
@@ -1482,13 +1490,20 @@ int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, c
   return MPNN_OK;
 }
 
-// ---- fused masked GRU forward on the tensor cores (widths 33..128, multiples of 4) -------------------------------
-int mpnn_tc_gru_supported(int d) { return (d > 32 && d <= 128 && (d & 3) == 0) ? 1 : 0; }
+// ---- fused masked GRU forward on the tensor cores (widths 33..256, multiples of 4) -------------------------------
+int mpnn_tc_gru_supported(int d) { return (d > 32 && d <= 256 && (d & 3) == 0) ? 1 : 0; }
+
+static void tc_gru_dims(int d, int* DP, int* KP, int* ncb) {
+  *KP = pow2_at_least(d, 64);
+  *DP = *KP > 128 ? 128 : *KP;      // four accumulators of DP columns must fit in the 512 TMEM columns
+  *ncb = *KP / *DP;
+}
 
 size_t mpnn_tc_gru_workspace_bytes(int d) {
   if (!mpnn_tc_gru_supported(d)) return 0;
-  const int DP = pow2_at_least(d, 64);
-  return (size_t)2 * 3 * DP * DP * sizeof(float);
+  int DP, KP, ncb;
+  tc_gru_dims(d, &DP, &KP, &ncb);
+  return (size_t)ncb * 2 * 3 * DP * KP * sizeof(float);
 }
 
 // h_out [rows, d], gates [rows, 4d] (sigmoid r | sigmoid z | tanh n | nh: what mpnn_gru_bwd reads)
@@ -1496,21 +1511,25 @@ int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const flo
                     const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(mpnn_tc_gru_supported(d), MPNN_ERR_UNSUPPORTED, "tc_gru_fwd: width %d not served", d);
-  MPNN_REQUIRE(rows > 0 && rows < (1ll << 31) - TILE, MPNN_ERR_ARG, "tc_gru_fwd: bad row count");
+  MPNN_REQUIRE(rows > 0 && rows < (1ll << 30), MPNN_ERR_ARG, "tc_gru_fwd: bad row count");
   MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_workspace_bytes(d), MPNN_ERR_WORKSPACE, "tc_gru_fwd: workspace too small");
-  const int DP = pow2_at_least(d, 64);
+  int DP, KP, ncb;
+  tc_gru_dims(d, &DP, &KP, &ncb);
   float* img = (float*)workspace;
-  k_tc_gru_pack<<<ceil_div(2LL * 3 * DP * DP, 256), 256, 0, stream>>>(W_ih, W_hh, d, DP, img);
+  k_tc_gru_pack<<<ceil_div((long long)ncb * 6 * DP * KP, 256), 256, 0, stream>>>(W_ih, W_hh, d, DP, KP, ncb, img);
   MPNN_CHECK_LAUNCH("k_tc_gru_pack");
-  TcGru a = {m, h, mask, img, b_ih, b_hh, h_out, gates, rows, d};
-  const long long tiles = (rows + TILE - 1) / TILE;
+  TcGru a = {m, h, mask, img, b_ih, b_hh, h_out, gates, rows, d, ncb};
+  const long long tiles = ((rows + TILE - 1) / TILE) * ncb;
   const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
-  if (DP == 64) {
-    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<64>, GruCfg<64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
-    k_tc_gru_fwd<64><<<grid, GruCfg<64>::GRU_THREADS, GruCfg<64>::SMEM, stream>>>(a);
+  if (KP == 64) {
+    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<64, 64>, GruCfg<64, 64>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
+    k_tc_gru_fwd<64, 64><<<grid, GruCfg<64, 64>::GRU_THREADS, GruCfg<64, 64>::SMEM, stream>>>(a);
+  } else if (KP == 128) {
+    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<128, 128>, GruCfg<128, 128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
+    k_tc_gru_fwd<128, 128><<<grid, GruCfg<128, 128>::GRU_THREADS, GruCfg<128, 128>::SMEM, stream>>>(a);
   } else {
-    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<128>, GruCfg<128>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
-    k_tc_gru_fwd<128><<<grid, GruCfg<128>::GRU_THREADS, GruCfg<128>::SMEM, stream>>>(a);
+    MPNN_REQUIRE(set_smem(k_tc_gru_fwd<128, 256>, GruCfg<128, 256>::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_fwd: smem attribute");
+    k_tc_gru_fwd<128, 256><<<grid, GruCfg<128, 256>::GRU_THREADS, GruCfg<128, 256>::SMEM, stream>>>(a);
   }
   MPNN_CHECK_LAUNCH("k_tc_gru_fwd");
   return MPNN_OK;

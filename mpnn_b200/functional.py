@@ -65,6 +65,44 @@ class _on_side_stream(object):
         return False
 
 
+# ------------------------------------------------------------------------------------------------
+# launch-bound ops as CUDA graphs
+# ------------------------------------------------------------------------------------------------
+# Set2Vec is 100 strictly sequential attention steps (set2vec.py:123-148): ~700 forward and ~1200 backward launches of
+# microsecond kernels.  When the step as a whole is not being captured (graphs.GraphedStep), the op captures ITS OWN
+# launch sequence once per shape into a CUDA graph over static buffers and replays it (copy in, replay, copy out).
+OP_GRAPHS_ENABLED = os.environ.get("MPNN_B200_OP_GRAPHS", "1") != "0"
+_OP_GRAPHS = {}
+
+
+def _graphed(key, run, ins, make_bufs, n_out):
+    """run(ins, bufs) enqueues the op's kernels reading `ins` and writing `bufs`; the first n_out bufs are returned."""
+    if not OP_GRAPHS_ENABLED or torch.cuda.is_current_stream_capturing():
+        bufs = make_bufs()
+        run(ins, bufs)
+        return bufs[:n_out]
+    ent = _OP_GRAPHS.get(key)
+    if ent is None:                 # first call of this shape: eager (also the warm-up the capture needs)
+        _OP_GRAPHS[key] = "warm"
+        bufs = make_bufs()
+        run(ins, bufs)
+        return bufs[:n_out]
+    if ent == "warm":
+        s_ins = [t.clone() if t is not None else None for t in ins]
+        s_bufs = make_bufs()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run(s_ins, s_bufs)
+        ent = (g, s_ins, s_bufs)
+        _OP_GRAPHS[key] = ent
+    g, s_ins, s_bufs = ent
+    for sbuf, t in zip(s_ins, ins):
+        if sbuf is not None:
+            sbuf.copy_(t)
+    g.replay()
+    return [b.clone() for b in s_bufs[:n_out]]
+
+
 class _inline(object):
     def __enter__(self):
         return self
@@ -553,11 +591,20 @@ class Set2VecFn(torch.autograd.Function):
         Wcat, bcat, Wq, we = f32c(Wcat), f32c(bcat), f32c(Wq), f32c(we)
         B, N, F = X.shape
         dev = X.device
-        out = torch.empty(B, 2 * F, dtype=torch.float32, device=dev)
-        saved = torch.empty(lib.mpnn_set2vec_saved_floats(B, N, F, steps), dtype=torch.float32, device=dev)
-        ws = workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)
-        check(lib.mpnn_set2vec_fwd(ptr(X), ptr(mask_c), ptr(Wcat), ptr(bcat), ptr(Wq), ptr(we), B, N, F, steps, ptr(out),
-                                   ptr(saved), ptr(ws), ws.numel(), stream()), "set2vec_fwd")
+
+        def make_bufs():
+            return [torch.empty(B, 2 * F, dtype=torch.float32, device=dev),
+                    torch.empty(lib.mpnn_set2vec_saved_floats(B, N, F, steps), dtype=torch.float32, device=dev),
+                    workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)]
+
+        def run(ins, bufs):
+            x, mk, wc, bc, wq, w_e = ins
+            out, saved, ws = bufs
+            check(lib.mpnn_set2vec_fwd(ptr(x), ptr(mk), ptr(wc), ptr(bc), ptr(wq), ptr(w_e), B, N, F, steps, ptr(out),
+                                       ptr(saved), ptr(ws), ws.numel(), stream()), "set2vec_fwd")
+
+        out, saved = _graphed(("set2vec_fwd", B, N, F, steps, mask is not None, dev.index), run,
+                              [X, mask_c, Wcat, bcat, Wq, we], make_bufs, 2)
         ctx.save_for_backward(X, mask_c, Wcat, Wq, we, saved)
         ctx.steps = steps
         return out
@@ -570,15 +617,22 @@ class Set2VecFn(torch.autograd.Function):
         B, N, F = X.shape
         dev = X.device
         dout = f32c(dout)
-        dX = torch.empty_like(X)
-        dWcat = torch.empty_like(Wcat)
-        dbcat = torch.empty(4 * F, dtype=torch.float32, device=dev)
-        dWq = torch.empty_like(Wq)
-        dwe = torch.empty_like(we)
-        ws = workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)
-        check(lib.mpnn_set2vec_bwd(ptr(X), ptr(mask), ptr(Wcat), ptr(Wq), ptr(we), ptr(saved), ptr(dout), B, N, F,
-                                   ctx.steps, ptr(dX), ptr(dWcat), ptr(dbcat), ptr(dWq), ptr(dwe), ptr(ws), ws.numel(),
-                                   stream()), "set2vec_bwd")
+        steps = ctx.steps
+
+        def make_bufs():
+            return [torch.empty_like(X), torch.empty_like(Wcat), torch.empty(4 * F, dtype=torch.float32, device=dev),
+                    torch.empty_like(Wq), torch.empty_like(we),
+                    workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)]
+
+        def run(ins, bufs):
+            x, mk, wc, wq, w_e, sv, do = ins
+            dX, dWcat, dbcat, dWq, dwe, ws = bufs
+            check(lib.mpnn_set2vec_bwd(ptr(x), ptr(mk), ptr(wc), ptr(wq), ptr(w_e), ptr(sv), ptr(do), B, N, F, steps,
+                                       ptr(dX), ptr(dWcat), ptr(dbcat), ptr(dWq), ptr(dwe), ptr(ws), ws.numel(),
+                                       stream()), "set2vec_bwd")
+
+        dX, dWcat, dbcat, dWq, dwe = _graphed(("set2vec_bwd", B, N, F, steps, mask is not None, dev.index), run,
+                                              [X, mask, Wcat, Wq, we, saved, dout], make_bufs, 5)
         return dX, None, dWcat, dbcat, dWq, dwe, None
 
 

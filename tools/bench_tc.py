@@ -78,6 +78,22 @@ def main():
                                              ws.numel(), stream()), "grad")
 
             t_gemm, t_seg, t_grad = timed(gemm, flush, args.reps), timed(seg, flush, args.reps), timed(grad, flush, args.reps)
+            # masked GRU forward (fused tcgen05 kernel for d <= 128, dense GEMMs + pointwise above)
+            mask = (torch.rand(n_rows, generator=g) > 0.4).float().to(dev)
+            W_ih = (torch.randn(d, 3 * d, generator=g) / d ** 0.5).to(dev)
+            W_hh = (torch.randn(d, 3 * d, generator=g) / d ** 0.5).to(dev)
+            b3 = torch.zeros(3 * d, device=dev)
+            h_out = torch.empty(n_rows, d, device=dev)
+            gates = torch.empty(n_rows, 4 * d, device=dev)
+            wsg = _lib.workspace(lib.mpnn_gru_workspace_bytes(n_rows, d), dev)
+
+            def gru():
+                check(lib.mpnn_gru_fwd(ptr(M), ptr(H), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(b3), ptr(b3), n_rows, d,
+                                       ptr(h_out), ptr(gates), ptr(wsg), wsg.numel(), stream()), "gru")
+
+            t_gru = timed(gru, flush, args.reps)
+            gru_bytes = 4.0 * n_rows * d * 8 + 4.0 * n_rows     # m, h in; h' and the 4 saved gate planes out
+            gru_flops = 12.0 * n_rows * d * d
             flops = 2.0 * E * d * d
             # algorithmic bytes: every edge reads one sender row and writes one message row (+ 3 index/weight words)
             gemm_bytes = 4.0 * E * d * 2 + 12.0 * E + 4.0 * (ti.U + 1) * d * d
@@ -91,9 +107,15 @@ def main():
                 "segment_sum": {"ms": t_seg, "gbs": seg_bytes / t_seg / 1e6, "frac_hbm": seg_bytes / t_seg / 1e6 / peaks["hbm_gbs"]},
                 "table_grad": {"ms": t_grad, "tflops": flops / t_grad / 1e9, "gbs": grad_bytes / t_grad / 1e6,
                                "frac_hbm": grad_bytes / t_grad / 1e6 / peaks["hbm_gbs"]},
+                "gru_fwd": {"ms": t_gru, "tflops": gru_flops / t_gru / 1e9, "gbs": gru_bytes / t_gru / 1e6,
+                            "frac_hbm": gru_bytes / t_gru / 1e6 / peaks["hbm_gbs"]},
+                # one forward message-passing step = message GEMM + aggregation + GRU update
+                "mp_step_fwd": {"ms": t_gemm + t_seg + t_gru,
+                                "gbs": (gemm_bytes + seg_bytes + gru_bytes) / (t_gemm + t_seg + t_gru) / 1e6,
+                                "frac_hbm": (gemm_bytes + seg_bytes + gru_bytes) / (t_gemm + t_seg + t_gru) / 1e6 / peaks["hbm_gbs"]},
             }
             print(json.dumps(line), flush=True)
-            del H, dM, table, Y, M, dT, ws
+            del H, dM, table, Y, M, dT, ws, gates, h_out, wsg
 
 
 if __name__ == "__main__":
