@@ -29,6 +29,25 @@ def _side_stream(device):
     return k, _SIDE_STREAMS[k]
 
 
+_FWD_SIDE = set()
+
+
+def _note_forward_side_work(device):
+    """forward work was enqueued on the side stream (sibling table prefetch): `join_side_streams()` waits for it"""
+    k = device.index if device.index is not None else torch.cuda.current_device()
+    _FWD_SIDE.add(k)
+
+
+def join_side_streams():
+    """Current stream waits for everything enqueued so far on the side streams.  Needed only by code that must not
+    leave the side stream running: the end of a CUDA-graph capture (graphs.GraphedStep calls it)."""
+    for k in list(_FWD_SIDE):
+        _FWD_SIDE.discard(k)
+        if k in _SIDE_STREAMS:
+            torch.cuda.current_stream(k).wait_stream(_SIDE_STREAMS[k])
+    _join_side_streams()
+
+
 def _join_side_streams():
     for k in list(_SIDE_PENDING):
         ev = _SIDE_PENDING.pop(k)

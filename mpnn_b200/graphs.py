@@ -11,7 +11,7 @@ bond rows U) from DEVICE memory, arrays are sized by capacities fixed at capture
 """
 import torch
 
-from . import graph
+from . import functional, graph
 
 
 class GraphedStep(object):
@@ -46,6 +46,7 @@ class GraphedStep(object):
         with graph.capacities(self.edge_capacity, self.unique_capacity):
             with torch.cuda.graph(self.graph):
                 self.loss = step_fn(self.static)
+                functional.join_side_streams()   # no forked branch may outlive the capture
         self._counts = list(graph._CAPTURED_COUNTS)
         del graph._CAPTURED_COUNTS[:]
         graph.clear_cache()

@@ -209,3 +209,51 @@ def test_skinny_gemm_matches_torch(dev, shape, form):
     check(lib.mpnn_gemm(ptr(A), ptr(W), ptr(C), M, N, K, K, 1, sbk, sbn, N, None, 2, ptr(ws), ws.numel(), stream()), "gemm")
     want = ref + C0.double()
     assert float((C.double() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_sibling_table_prefetch_is_transparent(dev):
+    """Per-step edge networks (normed_basic_model.py:24-27): from the second batch on, the tables of mf_1.. are computed
+    ahead of time on the side stream when mf_0 first sees the batch.  Outputs and every gradient must be bit-identical
+    to the run with the prefetch switched off, and match the CPU oracle."""
+    from mpnn_b200 import graph, modules as M, synthetic
+    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from oracle import mpnn_oracle as O
+    from golden_util import leaf_sd
+    torch.manual_seed(5)
+    mod = MessagePassingModel("normed", 16, 7, 16, 1, 24, message_steps=3)
+    mod.apply(kaiming_init)
+    sd = leaf_sd({k: v.detach().clone() for k, v in mod.state_dict().items()})
+    mod = mod.to(dev).train()
+    batches = [synthetic.make_batch("qm9", B=12, seed_offset=s) for s in (0, 1, 2)]
+
+    def run(b):
+        graph.clear_cache()
+        mod.zero_grad(set_to_none=True)
+        t = {k: torch.from_numpy(b[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+        a = t["afm"].clone().requires_grad_(True)
+        out = mod(a, t["bfm"], t["adj"], t["mask"])
+        out.pow(2).sum().backward()
+        torch.cuda.synchronize()
+        return out.detach().clone(), a.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+
+    assert M.SIBLING_PREFETCH
+    run(batches[0])                      # learns the group mf0 -> (mf1, mf2)
+    assert mod.mfs[0]._table_group is not None and len(mod.mfs[0]._table_group) == 3
+    got = [run(b) for b in batches[1:]]  # prefetched
+    M.SIBLING_PREFETCH = False
+    try:
+        want = [run(b) for b in batches[1:]]
+    finally:
+        M.SIBLING_PREFETCH = True
+    for g_, w_ in zip(got, want):
+        assert torch.equal(g_[0], w_[0]) and torch.equal(g_[1], w_[1])
+        assert g_[2].keys() == w_[2].keys()
+        for k in g_[2]:
+            assert torch.equal(g_[2][k], w_[2][k]), k
+    b = batches[2]
+    t = {k: torch.from_numpy(b[k]) for k in ("afm", "bfm", "adj", "mask")}
+    a0 = t["afm"].clone().requires_grad_(True)
+    ref = O.normed_basic_model(a0, t["bfm"], t["adj"], t["mask"], sd, steps=3)
+    ref.pow(2).sum().backward()
+    assert rel_err(got[1][0].cpu(), ref.detach()) <= 1e-4
+    assert rel_err(got[1][1].cpu(), a0.grad) <= 1e-3
