@@ -46,6 +46,11 @@ constexpr int SCAN_T = 256;
 constexpr int SCAN_PER_T = 8;
 constexpr int SCAN_BLK = SCAN_T * SCAN_PER_T;
 
+__global__ void __launch_bounds__(1024) k_scan_small(const int* __restrict__ a, const int* __restrict__ b, int n,
+                                                     int* __restrict__ outa, int* __restrict__ outb) {
+  small_scan_block(a, b, n, outa, outb);
+}
+
 __global__ void k_scan_blocksum(const int* __restrict__ a, const int* __restrict__ b, int n, int* __restrict__ sa,
                                 int* __restrict__ sb) {
   __shared__ int red[2][SCAN_T / 32];
@@ -285,9 +290,13 @@ int mpnn_compact_count(const float* bfm, const float* adj, int B, int N, int ef,
   k_count<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(bfm, adj, rows, N, ef, words, bitmask, row_cnt,
                                                                    col_cnt);
   MPNN_CHECK_LAUNCH("k_count");
-  k_scan_blocksum<<<nblk, SCAN_T, 0, stream>>>(row_cnt, col_cnt, rows, sa, sb);
-  k_scan_top<<<1, SCAN_T, 0, stream>>>(sa, sb, nblk);
-  k_scan_final<<<nblk, SCAN_T, 0, stream>>>(row_cnt, col_cnt, rows, sa, sb, row_ptr, col_ptr);
+  if (rows <= SMALL_SCAN_MAX) {
+    k_scan_small<<<1, 1024, 0, stream>>>(row_cnt, col_cnt, rows, row_ptr, col_ptr);
+  } else {
+    k_scan_blocksum<<<nblk, SCAN_T, 0, stream>>>(row_cnt, col_cnt, rows, sa, sb);
+    k_scan_top<<<1, SCAN_T, 0, stream>>>(sa, sb, nblk);
+    k_scan_final<<<nblk, SCAN_T, 0, stream>>>(row_cnt, col_cnt, rows, sa, sb, row_ptr, col_ptr);
+  }
   MPNN_CHECK_LAUNCH("k_scan");
   return MPNN_OK;
 }

@@ -123,6 +123,10 @@ __global__ void k_scan1_top(int* __restrict__ sa, int nblk) {
   }
 }
 
+__global__ void __launch_bounds__(1024) k_scan1_small(const int* __restrict__ a, int n, int* __restrict__ out) {
+  small_scan_block(a, nullptr, n, out, nullptr);
+}
+
 __global__ void k_scan1_final(const int* __restrict__ a, int n, const int* __restrict__ sa, int* __restrict__ out) {
   __shared__ int wsum[ST / 32];
   int base = blockIdx.x * SBLK + threadIdx.x * SPT;
@@ -352,9 +356,13 @@ int mpnn_dedup_rows(const float* rows, const int* n_edges_ptr, int edge_capacity
   MPNN_CHECK_LAUNCH("k_dedup_insert");
   k_dedup_flag<<<ceil_div(cap, 256), 256, 0, stream>>>(table, slot_of, n_edges_ptr, edge_capacity, rep, flag);
   MPNN_CHECK_LAUNCH("k_dedup_flag");
-  k_scan1_blocksum<<<nblk, ST, 0, stream>>>(flag, cap, sums);
-  k_scan1_top<<<1, ST, 0, stream>>>(sums, nblk);
-  k_scan1_final<<<nblk, ST, 0, stream>>>(flag, cap, sums, pos);
+  if (cap <= SMALL_SCAN_MAX) {
+    k_scan1_small<<<1, 1024, 0, stream>>>(flag, cap, pos);
+  } else {
+    k_scan1_blocksum<<<nblk, ST, 0, stream>>>(flag, cap, sums);
+    k_scan1_top<<<1, ST, 0, stream>>>(sums, nblk);
+    k_scan1_final<<<nblk, ST, 0, stream>>>(flag, cap, sums, pos);
+  }
   MPNN_CHECK_LAUNCH("k_scan1");
   k_dedup_assign<<<ceil_div(cap, 256), 256, 0, stream>>>(urows_in, n_edges_ptr, edge_capacity, ef, unique_capacity, rep,
                                                          pos, uid, (uint32_t*)urows, counts);
