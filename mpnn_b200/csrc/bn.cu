@@ -100,13 +100,15 @@ __global__ void k_bn_stage(RedArgs a, float* __restrict__ partial) {
       }
     }
   }
-  for (int k = 0; k < a.nq; ++k) {
-    __syncthreads();
-    sm[threadIdx.x] = q[k];
-    __syncthreads();
-    if (rl == 0) {
+  // all nq sums of the block behind ONE barrier pair (sm is [MAXQ][blockDim])
+#pragma unroll
+  for (int k = 0; k < MAXQ; ++k)
+    if (k < a.nq) sm[k * blockDim.x + threadIdx.x] = q[k];
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 0; k < a.nq; ++k) {
       float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += sm[l * C + c];
+      for (int l = 0; l < lanes; ++l) s += sm[k * blockDim.x + l * C + c];
       partial[((size_t)blockIdx.x * a.nq + k) * C + c] = s;
     }
   }
@@ -208,13 +210,15 @@ __global__ void k_bn_stats(StatArgs a, float* __restrict__ partial) {
     }
   }
   float* prt = partial + (size_t)blockIdx.x * 7 * C;
-  for (int k = 0; k < 3; ++k) {
-    __syncthreads();
-    sm[threadIdx.x] = q[k];
-    __syncthreads();
-    if (rl == 0) {
+  float* r3 = sm + blockDim.x + C;   // [3][blockDim]: the three sums of a pass are reduced behind ONE barrier pair
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r3[k * blockDim.x + threadIdx.x] = q[k];
+  __syncthreads();
+  if (rl == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
       float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += sm[l * C + c];
+      for (int l = 0; l < lanes; ++l) s += r3[k * blockDim.x + l * C + c];
       q[k] = s;
       prt[k * C + c] = s;
     }
@@ -238,13 +242,15 @@ __global__ void k_bn_stats(StatArgs a, float* __restrict__ partial) {
       w[2] += m2;
     }
   }
-  for (int k = 0; k < 3; ++k) {
-    __syncthreads();
-    sm[threadIdx.x] = w[k];
-    __syncthreads();
-    if (rl == 0) {
+  __syncthreads();   // the first pass's reads of r3 are done
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r3[k * blockDim.x + threadIdx.x] = w[k];
+  __syncthreads();
+  if (rl == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
       float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += sm[l * C + c];
+      for (int l = 0; l < lanes; ++l) s += r3[k * blockDim.x + l * C + c];
       prt[(4 + k) * C + c] = s;
     }
   }
@@ -412,11 +418,11 @@ int run_stage(RedArgs a, float* partial, cudaStream_t stream) {
   a.rows_per_block = rpb;
   int threads = a.C >= 256 ? a.C : (256 / a.C) * a.C;
   switch (a.mode) {
-    case STATS1: k_bn_stage<STATS1><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
-    case STATS2: k_bn_stage<STATS2><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
-    case BWD_PLAIN: k_bn_stage<BWD_PLAIN><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
-    case BWD_1D_TRAIN: k_bn_stage<BWD_1D_TRAIN><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
-    default: k_bn_stage<BWD_1D_EVAL><<<nblk, threads, threads * sizeof(float), stream>>>(a, partial); break;
+    case STATS1: k_bn_stage<STATS1><<<nblk, threads, MAXQ * threads * sizeof(float), stream>>>(a, partial); break;
+    case STATS2: k_bn_stage<STATS2><<<nblk, threads, MAXQ * threads * sizeof(float), stream>>>(a, partial); break;
+    case BWD_PLAIN: k_bn_stage<BWD_PLAIN><<<nblk, threads, MAXQ * threads * sizeof(float), stream>>>(a, partial); break;
+    case BWD_1D_TRAIN: k_bn_stage<BWD_1D_TRAIN><<<nblk, threads, MAXQ * threads * sizeof(float), stream>>>(a, partial); break;
+    default: k_bn_stage<BWD_1D_EVAL><<<nblk, threads, MAXQ * threads * sizeof(float), stream>>>(a, partial); break;
   }
   MPNN_CHECK_LAUNCH("k_bn_stage");
   return MPNN_OK;
