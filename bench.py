@@ -238,13 +238,26 @@ def run_ours(args):
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     prefetch()   # the first step's inputs; every timed step issues the copy for its successor
     barrier()
+    # every step's loss is copied to pinned host memory inside the step's timed region and READ by the host one step
+    # later (asynchronous logging): the host never stalls the GPU between steps
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    losses, prev = [], None
     for i in range(args.steps):
         flush.fill_(i & 1)
         ev2[i][0].record()
         loss = run_e2e()
-        _ = float(loss.item())
+        loss_host[i & 1].copy_(loss.detach().reshape(()), non_blocking=True)
+        loss_ev[i & 1].record()
+        if prev is not None:
+            loss_ev[prev].synchronize()
+            losses.append(float(loss_host[prev]))
         ev2[i][1].record()
+        prev = i & 1
+    loss_ev[prev].synchronize()
+    losses.append(float(loss_host[prev]))
     barrier()
+    assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: a step's loss was not read back"
     ms2 = sum(a.elapsed_time(b) for a, b in ev2)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
@@ -275,7 +288,8 @@ def run_ours(args):
         "e2e": {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": gb_in,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps,
                 "pipeline": "H2D of the next padded batch on a copy stream (pinned -> staging) overlapped with the current "
-                            "step; D2D staging -> graph inputs; loss.item() every step" if use_graph else "serial"},
+                            "step; D2D staging -> graph inputs; every step's loss copied D2H (pinned) inside the step and read by the host "
+                            "one step later" if use_graph else "serial H2D; loss copied D2H every step, read one step later"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
     }
     if world == 1 and not args.no_cpu_baseline:
