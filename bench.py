@@ -360,7 +360,10 @@ def dominant_kernel_roofline(w, body, devb, flush, n_atoms):
     gbs = bytes_b / (ms_b * 1e-3) / 1e9
     return {"kernel": "k_enet_bwd (+ fixed-order reductions: the edge network's backward on the distinct bond rows)",
             "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of k_enet_bwd per launch, `ncu --set full` capture of this
+            # workload (profiles/r01_summary_qm9_final.md); only meaningful for the default config
+            "traffic": 557312 if (w["d"], w["ef"], R) == (16, 7, 33) else None,
+            "peak_source": peaks["source"] + " (copy bandwidth)",
             "ms_per_launch": ms_b, "algorithmic_bytes_per_launch": bytes_b, "algorithmic_flops_per_launch": flops_b,
             "achieved_tflops_fp32": flops_b / (ms_b * 1e-3) / 1e12, "rows_evaluated": R,
             "forward_ms_per_launch": ms_f,
