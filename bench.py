@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
 def make_workload_batch(config, w, rank):
     from mpnn_b200 import synthetic
     batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=w["B"], seed_offset=rank,
-                                 d=w["d"] if config == "autoenc" else None)
+                                 d=w["d"] if config == "autoenc" else None, return_graphs=True)
     if config != "qm9":
         batch["labels"] = np.random.RandomState(rank).normal(size=(w["B"], w["targets"])).astype(np.float32)
     return batch
@@ -235,35 +235,69 @@ def run_ours(args):
     barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     # ---- e2e: host buffers, H2D + loss D2H inside the timed region ----------------------------
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    prefetch()   # the first step's inputs; every timed step issues the copy for its successor
-    barrier()
-    # every step's loss is copied to pinned host memory inside the step's timed region and READ by the host one step
-    # later (asynchronous logging): the host never stalls the GPU between steps
-    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    losses, prev = [], None
-    for i in range(args.steps):
-        flush.fill_(i & 1)
-        ev2[i][0].record()
-        loss = run_e2e()
-        loss_host[i & 1].copy_(loss.detach().reshape(()), non_blocking=True)
-        loss_ev[i & 1].record()
-        if prev is not None:
-            loss_ev[prev].synchronize()
-            losses.append(float(loss_host[prev]))
-        ev2[i][1].record()
-        prev = i & 1
-    loss_ev[prev].synchronize()
-    losses.append(float(loss_host[prev]))
-    barrier()
-    assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: a step's loss was not read back"
-    ms2 = sum(a.elapsed_time(b) for a, b in ev2)
+    def time_e2e(run_fn, prefetch_fn):
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        prefetch_fn()   # the first step's inputs; every timed step issues the copy for its successor
+        barrier()
+        # every step's loss is copied to pinned host memory inside the step's timed region and READ by the host one
+        # step later (asynchronous logging): the host never stalls the GPU between steps
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        losses, prev = [], None
+        for i in range(args.steps):
+            flush.fill_(i & 1)
+            ev2[i][0].record()
+            loss = run_fn()
+            loss_host[i & 1].copy_(loss.detach().reshape(()), non_blocking=True)
+            loss_ev[i & 1].record()
+            if prev is not None:
+                loss_ev[prev].synchronize()
+                losses.append(float(loss_host[prev]))
+            ev2[i][1].record()
+            prev = i & 1
+        loss_ev[prev].synchronize()
+        losses.append(float(loss_host[prev]))
+        barrier()
+        assert len(losses) == args.steps and all(np.isfinite(losses)), "e2e: a step's loss was not read back"
+        return sum(a.elapsed_time(b) for a, b in ev2)
+
+    ms2 = time_e2e(run_e2e, prefetch)
+    # ---- e2e through the device-side collate (mpnn_b200.loader): the host ships the batch ragged
+    # (real atoms' rows + edge list) and the padded tensors the modules consume are written on the GPU
+    ms3, rb_bytes = None, None
+    if use_graph:
+        from mpnn_b200.loader import RaggedBatch
+        rb_host = RaggedBatch.from_graphs(batch["graphs"], batch["labels"])
+        rb_bytes = rb_host.nbytes()
+        rb_dev = rb_host.to(dev, non_blocking=False)       # device staging buffers of the ragged arrays
+        pad_out = {k: gs.static[k] for k in ("afm", "bfm", "adj", "mask")}
+
+        def prefetch_r():
+            with torch.cuda.stream(copy_stream):
+                for k, v in rb_host.tensors().items():
+                    rb_dev.tensors()[k].copy_(v, non_blocking=True)
+                ev_copy.record(copy_stream)
+
+        def run_e2e_r():
+            main = torch.cuda.current_stream()
+            main.wait_event(ev_copy)
+            rb_dev.scatter_padded(pad_out)                  # memsets + two scatter kernels into the graph's inputs
+            gs.static["labels"].copy_(rb_dev.labels, non_blocking=True)
+            ev_loaded.record(main)
+            copy_stream.wait_event(ev_loaded)
+            prefetch_r()
+            return gs.replay()
+
+        for _ in range(2):
+            prefetch_r()
+            run_e2e_r()
+        ms3 = time_e2e(run_e2e_r, prefetch_r)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, ms2], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms2, ms3 if ms3 is not None else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms2 = float(t[0]), float(t[1])
+    ms3 = float(t[2]) if ms3 is not None else None
 
     # ---- roofline of the dominant kernel, timed alone with CUDA events (L2 flushed before every launch) -------
     roof = None
@@ -292,6 +326,12 @@ def run_ours(args):
                             "one step later" if use_graph else "serial H2D; loss copied D2H every step, read one step later"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
     }
+    if ms3 is not None:
+        line["e2e_device_collate"] = {
+            "value": world * B * args.steps / (ms3 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": rb_bytes,
+            "d2h_bytes_per_step": 4, "ms_per_step": ms3 / args.steps,
+            "note": "same as e2e, but the host ships the batch ragged (mpnn_b200.loader.RaggedBatch) and "
+                    "mpnn_collate_ragged writes the reference's padded tensors on the GPU"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config, budget_s=20.0)
     print(json.dumps(line))

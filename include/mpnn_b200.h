@@ -67,6 +67,14 @@ int mpnn_compact_fill(const float* bfm, const float* adj, int B, int N, int ef, 
 int mpnn_scatter_edge_rows(const float* d_edge_x, const int* edge_dst, const int* edge_src, int E, int N, int ef,
                            float* dense, mpnn_stream_t stream);
 
+/* a0, the step before the path: device-side collate.  The host ships the batch ragged (the real
+ * atoms' feature rows + the edge list, ~6x..12x fewer bytes than the padded tensors) and this call writes the
+ * reference's padded layout (pre_process/data_loader.py:50-70).  atom_row[a] = b*N+i, edge_dst[e] = b*N+i, edge_j[e] = j;
+ * the outputs are zero-filled here. */
+int mpnn_collate_ragged(const int* atom_row, const float* afm_cat, long long n, int Fa, const int* edge_dst,
+                        const int* edge_j, const float* edge_w, const float* edge_x, long long E, int ef, int B, int N,
+                        float* afm, float* bfm, float* adj, float* mask, mpnn_stream_t stream);
+
 /* ---- a0 (cont.): exact de-duplication of the compacted bond rows + stable grouping of edges by distinct row.
  * Bond features are categorical (reference mol_graph/mol_graph.py:74-90), and edge_map is a pure function of the
  * row (edge_network.py:14-21,36-37), so evaluating it once per distinct row is exact.  Rows are compared by bit

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mpnn_compact_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_compact_count": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mpnn_compact_fill": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "mpnn_collate_ragged": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _I, _I, _I, _P, _P, _P, _P, _P]),
     "mpnn_dedup_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_dedup_rows": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
     "mpnn_type_sort_workspace_bytes": (_Z, [_I, _I]),

@@ -245,6 +245,40 @@ __global__ void k_scatter_rows(const float* __restrict__ dx, const int* __restri
   dense[((size_t)edge_dst[e] * N + j) * ef + f] = dx[t];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Device-side collate: the host ships the batch RAGGED -- the real atoms' feature rows and the
+// edge list -- and this kernel writes the reference's padded layout (collate_2d_graphs, data_loader.py:50-70:
+// afm [B,N,Fa], bfm [B,N,N,ef], adj [B,N,N], mask [B,N,1]) into pre-zeroed buffers.  At config-5 size the padded bfm
+// is 757 MB of mostly zeros; the ragged form is ~130 MB.
+//   atom_row[a] = b*N + i (flat padded row of real atom a); edge_dst[e] = b*N + i, edge_j[e] = j.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_collate_atoms(const int* __restrict__ atom_row, const float* __restrict__ afm_cat,
+                                                       long long n, int Fa, float* __restrict__ afm,
+                                                       float* __restrict__ mask) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * Fa) return;
+  const long long a = t / Fa;
+  const int f = (int)(t - a * Fa);
+  const int row = __ldg(atom_row + a);
+  afm[(size_t)row * Fa + f] = afm_cat[t];
+  if (f == 0) mask[row] = 1.0f;
+}
+
+__global__ void __launch_bounds__(256) k_collate_edges(const int* __restrict__ edge_dst, const int* __restrict__ edge_j,
+                                                       const float* __restrict__ edge_w, const float* __restrict__ edge_x,
+                                                       long long E, int ef, int N, float* __restrict__ bfm,
+                                                       float* __restrict__ adj) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= E * (ef + 1)) return;
+  const long long e = t / (ef + 1);
+  const int f = (int)(t - e * (ef + 1));
+  const size_t pair = (size_t)__ldg(edge_dst + e) * N + __ldg(edge_j + e);
+  if (f < ef)
+    bfm[pair * ef + f] = edge_x[e * ef + f];
+  else
+    adj[pair] = edge_w[e];
+}
+
 }  // namespace
 
 extern "C" {
@@ -318,6 +352,29 @@ int mpnn_compact_fill(const float* bfm, const float* adj, int B, int N, int ef, 
     k_fill_csc<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(bitmask, row_ptr, col_ptr, rows, N, words,
                                                                         capacity, csc_eid);
     MPNN_CHECK_LAUNCH("k_fill_csc");
+  }
+  return MPNN_OK;
+}
+
+// Ragged batch -> the reference's padded layout (collate_2d_graphs, data_loader.py:50-70).  All four outputs are
+// zero-filled here and then scattered into; n real atoms, E edges (pairs with adj != 0 or a non-zero bond row).
+int mpnn_collate_ragged(const int* atom_row, const float* afm_cat, long long n, int Fa, const int* edge_dst,
+                        const int* edge_j, const float* edge_w, const float* edge_x, long long E, int ef, int B, int N,
+                        float* afm, float* bfm, float* adj, float* mask, cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && N > 0 && Fa > 0 && ef > 0 && n >= 0 && E >= 0, MPNN_ERR_ARG, "collate_ragged: bad dims");
+  MPNN_REQUIRE(afm && bfm && adj && mask, MPNN_ERR_ARG, "collate_ragged: null output");
+  const size_t rows = (size_t)B * N;
+  MPNN_CUDA(cudaMemsetAsync(afm, 0, rows * Fa * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(mask, 0, rows * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(adj, 0, rows * N * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(bfm, 0, rows * N * ef * sizeof(float), stream));
+  if (n > 0) {
+    k_collate_atoms<<<ceil_div(n * Fa, 256), 256, 0, stream>>>(atom_row, afm_cat, n, Fa, afm, mask);
+    MPNN_CHECK_LAUNCH("k_collate_atoms");
+  }
+  if (E > 0) {
+    k_collate_edges<<<ceil_div(E * (ef + 1), 256), 256, 0, stream>>>(edge_dst, edge_j, edge_w, edge_x, E, ef, N, bfm, adj);
+    MPNN_CHECK_LAUNCH("k_collate_edges");
   }
   return MPNN_OK;
 }

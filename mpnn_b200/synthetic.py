@@ -142,7 +142,7 @@ def collate(graphs, labels=None):
     return out
 
 
-def make_batch(name, B=None, seed_offset=0, d=None):
+def make_batch(name, B=None, seed_offset=0, d=None, return_graphs=False):
     """Padded batch dict for one of the BASELINE.json configs (numpy, float32)."""
     cfg = dict(CONFIGS[name])
     if B is not None:
@@ -156,6 +156,8 @@ def make_batch(name, B=None, seed_offset=0, d=None):
     batch = collate(graphs, labels)
     batch["n_atoms"] = int(batch["mask"].sum())
     batch["n_edges"] = int((batch["adj"] != 0).sum())
+    if return_graphs:
+        batch["graphs"] = graphs
     return batch
 
 

@@ -210,3 +210,29 @@ def test_flat_gradient_allreduce_gloo_world2(tmp_path):
     lin(torch.arange(12.0).view(4, 3)).pow(2).sum().backward()
     for g, p in zip(got, lin.parameters()):
         assert torch.allclose(g, p.grad, rtol=1e-6, atol=1e-6)
+
+
+def test_ragged_batch_matches_host_collate():
+    """loader.RaggedBatch: the ragged form carries exactly the non-zero content of the padded
+    batch that `collate_2d_graphs` (reference data_loader.py:50-70) builds, in row-major (b, i, j) order."""
+    import numpy as np
+    from mpnn_b200 import synthetic
+    from mpnn_b200.loader import RaggedBatch
+    b = synthetic.make_batch("qm9", B=9, return_graphs=True)
+    rb = RaggedBatch.from_graphs(b["graphs"], b["labels"], pin=False)
+    B, N = rb.B, rb.N
+    assert (B, N) == b["afm"].shape[:2] and rb.Fa == b["afm"].shape[2] and rb.ef == b["bfm"].shape[3]
+    afm = np.zeros_like(b["afm"]).reshape(B * N, -1)
+    afm[rb.atom_row.numpy()] = rb.afm_cat.numpy()
+    assert np.array_equal(afm.reshape(b["afm"].shape), b["afm"])
+    mask = np.zeros(B * N, np.float32)
+    mask[rb.atom_row.numpy()] = 1
+    assert np.array_equal(mask.reshape(B, N, 1), b["mask"])
+    keep = (b["bfm"] != 0).any(-1) | (b["adj"] != 0)
+    bb, ii, jj = np.nonzero(keep)
+    assert np.array_equal(rb.edge_dst.numpy(), (bb * N + ii).astype(np.int32))
+    assert np.array_equal(rb.edge_j.numpy(), jj.astype(np.int32))
+    assert np.array_equal(rb.edge_w.numpy(), b["adj"][bb, ii, jj])
+    assert np.array_equal(rb.edge_x.numpy(), b["bfm"][bb, ii, jj])
+    padded = sum(b[k].nbytes for k in ("afm", "bfm", "adj", "mask"))
+    assert rb.nbytes() < padded / 4
