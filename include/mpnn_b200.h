@@ -208,6 +208,14 @@ int mpnn_message_bwd(const int* row_ptr, const int* edge_dst, const int* gidx, c
                      int ldt, float* dG, float* dQ, float* dalpha, float* dW_last, float* dB_last, float* dbeta,
                      void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 
+/* ---- BiLiniearEdgeNetwork (message/bilinear_edge_network.py:25-37): parameter-free,
+ * Y[e, p] = sum_{a,q} H[src_e, a] * X_e.view(nf,nf,nf)[a, p, q] * H[dst_e, q] on the compacted pairs (ef == nf^3). */
+int mpnn_bilinear_fwd(const int* edge_src, const int* edge_dst, const float* X, long long ldx, const float* H,
+                      long long E, int nf, float* Y, mpnn_stream_t stream);
+int mpnn_bilinear_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, const int* edge_src,
+                      const int* edge_dst, const float* X, long long ldx, const float* H, const float* dY, int n_rows,
+                      long long E, int nf, float* dH, float* dX, long long lddx, mpnn_stream_t stream);
+
 /* ---- a4: attention gate of AttEdgeNetwork (att_edge_network.py:18-26) / row softmax -------------------- */
 int mpnn_softmax_mul_fwd(const float* logits, const float* V, long long rows, int n, float* gate, float* out,
                          mpnn_stream_t stream);

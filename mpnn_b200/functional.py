@@ -807,6 +807,40 @@ class TypedMessageFn(torch.autograd.Function):
         return dH, dT, None, dbeta, None, None, None, None, None
 
 
+class BilinearEdgeFn(torch.autograd.Function):
+    """reference bilinear_edge_network.py:25-37 on the compacted pairs: Y[e, p] = h[src_e]^T X_e[:, p, :] h[dst_e] with
+    X_e the bond row viewed [nf, nf, nf].  H [n_rows, nf], X [E(+1), nf^3] -> Y [E, nf]."""
+
+    @staticmethod
+    def forward(ctx, H, X, el):
+        lib = _lib.load()
+        _need_cuda(H, X)
+        H, X = f32c(H), f32c(X)
+        nf = H.shape[1]
+        E = el.E
+        Y = torch.empty(max(E, 1), nf, dtype=torch.float32, device=H.device)
+        check(lib.mpnn_bilinear_fwd(ptr(el.edge_src), ptr(el.edge_dst), ptr(X), X.shape[1], ptr(H), E, nf, ptr(Y),
+                                    stream()), "bilinear_fwd")
+        ctx.save_for_backward(H, X)
+        ctx.el = el
+        return Y[:E]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dY):
+        lib = _lib.load()
+        H, X = ctx.saved_tensors
+        el = ctx.el
+        nf = H.shape[1]
+        dY = f32c(dY)
+        dH = torch.empty_like(H) if ctx.needs_input_grad[0] else None
+        dX = torch.zeros_like(X) if ctx.needs_input_grad[1] else None   # the trailing all-zero row gets no gradient
+        check(lib.mpnn_bilinear_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src),
+                                    ptr(el.edge_dst), ptr(X), X.shape[1], ptr(H), ptr(dY), el.n_rows, el.E, nf, ptr(dH),
+                                    ptr(dX), X.shape[1], stream()), "bilinear_bwd")
+        return dH, dX, None
+
+
 class TypedMessageTCFn(torch.autograd.Function):
     """Tensor-core form of the typed message path for feature widths 33..256 (csrc/tc_message.cu):
     M[i] = sum_{e in E(i)} alpha_e T[uid_e]^T H[src_e] as a grouped TF32 GEMM over the type-sorted edge tiles

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import graph
-from .functional import (DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
+from .functional import (BilinearEdgeFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
                          GraphLevelOutputFn, GRUFn, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, table_dp, tc_dp, typed_dp)
 from . import _lib
@@ -363,15 +363,49 @@ class AttEdgeNetwork(EdgeNetwork):
 
 
 class BiLiniearEdgeNetwork(nn.Module):
-    """reference bilinear_edge_network.py (parameter-free h_j^T E_ij h_i).  Scheduled after the hot path
-    (SURVEY.md 8f rank 3); constructing it works so `from mpnn_functions import *` resolves, forward raises."""
+    """reference bilinear_edge_network.py: parameter-free message h_j^T E_ij h_i with the bond row viewed as an
+    [nf, nf, nf] tensor (edge_features == node_features**3; message width == node_features).  Returns the same lazy
+    handle as EdgeNetwork: an mpnn_b200 aggregator consumes the per-pair messages on the compacted edge list, any
+    other consumer gets the reference's dense [B, N, N, nf] tensor."""
 
     def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
         super(BiLiniearEdgeNetwork, self).__init__()
         self.nf, self.ef, self.mf = node_features, edge_features, message_features
+        self.act_fn = activation_fn if activation_fn is not None else nn.ReLU()   # unused, as in the reference
+
+    def _edge_messages(self, afm, bfm, adj):
+        B, N, nf = afm.shape
+        if bfm.shape[-1] != nf ** 3:
+            raise RuntimeError("BiLiniearEdgeNetwork: edge_features (%d) must equal node_features**3 (%d) "
+                               "(reference bilinear_edge_network.py:31-36)" % (bfm.shape[-1], nf ** 3))
+        el = graph.edge_list_for(bfm, adj)
+        if el.E is None:
+            raise RuntimeError("mpnn_b200.BiLiniearEdgeNetwork is not available in capacity (graph-capture) mode")
+        rows = graph.GatherEdgeRows.apply(bfm, el) if bfm.requires_grad else el.rows
+        return el, BilinearEdgeFn.apply(afm.reshape(-1, nf), rows, el)
+
+    def _aggregated_messages(self, afm, bfm, adj, reuse, alpha_fn, gamma_fn):
+        """sum_j weight[b,i,j] * msg[b,i,j]; pairs without a bond row contribute exactly 0 whatever their weight"""
+        B, N, nf = afm.shape
+        el, Y = self._edge_messages(afm, bfm, adj)
+        alpha = el.edge_w if alpha_fn is None else alpha_fn(el)
+        # backward of the CSR sum: edge e receives the gradient of its receiver row (one-entry transposed lists)
+        one = torch.arange(el.E + 1, dtype=torch.int32, device=afm.device)
+        M = GatherSumFn.apply(Y * alpha.unsqueeze(1), el.row_ptr, None, el.n_rows, one, el.edge_dst)
+        return M.view(B, N, nf)
+
+    def _head_messages(self, afm, bfm, reuse):
+        """the reference's own return value: dense per-pair messages [B, N, N, nf]"""
+        B, N, nf = afm.shape
+        el, Y = self._edge_messages(afm, bfm, None)
+        pair = el.edge_dst.long() * N + (el.edge_src.long() % N)
+        dense = torch.zeros(B * N * N, nf, dtype=torch.float32, device=afm.device)
+        return dense.index_put((pair,), Y).view(B, N, N, nf)
 
     def forward(self, afm, bfm, reuse_graph_tensors=False):
-        raise NotImplementedError("mpnn_b200.BiLiniearEdgeNetwork has no CUDA implementation yet (no fallback)")
+        if not afm.is_cuda:
+            raise RuntimeError("mpnn_b200.BiLiniearEdgeNetwork: CUDA tensors required (there is no CPU fallback)")
+        return LazyMessages(self, afm, bfm, bool(reuse_graph_tensors))
 
 
 class GGNNMsgPass(nn.Module):

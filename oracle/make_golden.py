@@ -86,9 +86,24 @@ def run_case(name, module, fwd, inputs, grad_inputs, meta, seed=0, extra_out=Non
     return ins, sd0, out, cot, gin, gsd
 
 
+def make_bilinear(ref):
+    """BiLiniearEdgeNetwork: ef = nf**3, parameter-free"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from mpnn_b200 import synthetic
+    nf = 3
+    batch = synthetic.small_batch(B=3, n_lo=2, n_hi=6, afm_width=nf, ef=nf ** 3, seed=13, weighted_adj=True)
+    m = ref.BiLiniearEdgeNetwork(nf, nf ** 3, nf)
+    run_case("msg_BiLiniearEdgeNetwork", m, lambda mod, afm, bfm, adj: mod(afm, bfm),
+             dict(afm=batch["afm"], bfm=batch["bfm"], adj=batch["adj"]), ("afm", "bfm"),
+             dict(cls="BiLiniearEdgeNetwork", nf=nf, ef=nf ** 3, mf=nf))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "bilinear":     # only the fixture added after the first freeze
+        make_bilinear(ref)
+        return
     sys.path.insert(0, os.path.dirname(HERE))
     from mpnn_b200 import synthetic  # host-side numpy only
 
@@ -139,6 +154,8 @@ def main():
     save_case("msg_GGNNMsgPass", ins, dict(m.state_dict()), {"y": out}, cot, {"afm": ins["afm"].grad},
               {k: p.grad for k, p in m.named_parameters() if p.grad is not None},
               dict(cls="GGNNMsgPass", nf=nf, ef=nt, mf=mf))
+
+    make_bilinear(ref)
 
     # ---------------- aggregators (stand-alone, dense [B,N,N,mf]) -------------------------------
     rs = np.random.RandomState(4)

@@ -100,6 +100,14 @@ def att_edge_network_pairs(afm, bfm, sd, prefix, mf):
     return emb.matmul(attn_app).squeeze(-1)                                                # :31
 
 
+def bilinear_edge_network(afm, bfm, nf):
+    """BiLiniearEdgeNetwork.forward (bilinear_edge_network.py:25-37): parameter-free, needs ef == nf**3;
+    out[b,i,j,p] = sum_{a,q} afm[b,j,a] * bfm[b,i,j].view(nf,nf,nf)[a,p,q] * afm[b,i,q]   -> [B,N,N,nf]."""
+    ees = bfm.shape[:3] + (nf, -1)
+    return afm.unsqueeze(1).unsqueeze(-2).matmul(bfm.view(ees)).view(ees).matmul(
+        afm.unsqueeze(2).unsqueeze(-1)).squeeze()
+
+
 def ggnn_msg_pass(afm, bfm_int, sd, prefix):
     """GGNNMsgPass.forward (ggnn_msg_pass.py:17-31); bfm_int [B,N,N] int64 bond types, 0 = no bond."""
     B, N, nf = afm.shape

@@ -69,6 +69,8 @@ def oracle_forward(case, ins, sd, buffers=None):
         return O.att_edge_network_pairs(ins["afm"], ins["bfm"], sd, "", m["mf"])
     if cls == "GGNNMsgPass":
         return O.ggnn_msg_pass(ins["afm"], ins["bfm"], sd, "")
+    if cls == "BiLiniearEdgeNetwork":
+        return O.bilinear_edge_network(ins["afm"], ins["bfm"], m["nf"])
     if cls == "AdjMsgAgg":
         return O.adj_msg_agg(ins["messages"], ins["adj"])
     if cls == "WAdjMsgAgg":

@@ -71,7 +71,7 @@ def test_module_state_dict_contract(name):
     case = Case(name)
     m = case.meta
     cls = m["cls"].replace("EdgeNetworkD", "EdgeNetwork")
-    if cls in ("EdgeNetwork", "AttEdgeNetwork", "GGNNMsgPass"):
+    if cls in ("EdgeNetwork", "AttEdgeNetwork", "GGNNMsgPass", "BiLiniearEdgeNetwork"):
         mod = getattr(M, cls)(m["nf"], m["ef"], m["mf"])
     elif cls in ("AdjMsgAgg", "WAdjMsgAgg", "AttMsgAgg"):
         mod = getattr(M, cls)(1)
