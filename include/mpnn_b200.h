@@ -115,11 +115,14 @@ size_t mpnn_tmsg_bwd_workspace_bytes(int edge_capacity, int unique_capacity, int
 int mpnn_tmsg_fwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, const float* H,
                   const float* table, const float* S, const float* beta, int n_rows, int N, int nf, int mf,
                   int zero_type, float* M, mpnn_stream_t stream);
+/* n_src_rows: rows of H (0 = n_rows: node states gathered through edge_src; the edge count when H holds one explicit
+ * sender vector per edge -- the gated states of AttEdgeNetwork, att_edge_network.py:26 -- with identity edge_src /
+ * col_ptr / csc_eid) */
 int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, const int* edge_src, const int* edge_dst,
                   const int* uid, const int* type_ptr, const int* type_eid, const int* counts, const float* alpha,
-                  const float* H, const float* table, const float* tableT, const float* S, int n_rows, int B, int N,
-                  int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dH, float* dT,
-                  void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+                  const float* H, const float* table, const float* tableT, const float* S, int n_rows, int n_src_rows,
+                  int B, int N, int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dH,
+                  float* dT, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 
 /* ---- a1-a3, a5 on the distinct rows, feature widths 33..256: tcgen05 tensor cores (mpnn_b200/csrc/tc_message.cu) ----
  * The type-sorted edge list is cut into single-type tiles of <= 128 edges (the plan, device side, no host read);

@@ -46,7 +46,7 @@ SIGNATURES = {
                            _P]),
     "mpnn_tmsg_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "mpnn_tmsg_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "mpnn_tmsg_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P,
+    "mpnn_tmsg_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P,
                            _P, _P, _P, _Z, _P]),
     "mpnn_tc_dp": (_I, [_I, _I]),
     "mpnn_tc_plan_bytes": (_Z, [_I, _I]),

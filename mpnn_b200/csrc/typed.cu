@@ -41,6 +41,7 @@ struct TMsg {
   const float* S;       // [B, nf] per-graph sums of H (HEAD form) or null
   const float* beta;    // [mf] or null
   int n_rows, N, nf, mf, zero_type;
+  int n_src;            // rows of H (== n_rows when H holds node states; the edge count for per-edge sender vectors)
 };
 
 template <int DP>
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_src(TMsg a, const int* __restr
   const int groups_per_block = 256 / DP;
   const bool head = a.S != nullptr;
   const float* T0 = a.tableT + (size_t)a.zero_type * DP * DP + l;
-  for (int j = blockIdx.x * groups_per_block + threadIdx.x / DP; j < a.n_rows; j += gridDim.x * groups_per_block) {
+  for (int j = blockIdx.x * groups_per_block + threadIdx.x / DP; j < a.n_src; j += gridDim.x * groups_per_block) {
     const int cb = col_ptr[j], ce = col_ptr[j + 1];
     float acc = 0.f;
     for (int c0 = cb; c0 < ce; c0 += DP) {
@@ -841,7 +842,7 @@ int mpnn_tmsg_fwd(const int* row_ptr, const int* edge_src, const int* uid, const
   MPNN_REQUIRE(n_rows > 0 && N > 0 && nf > 0 && mf > 0, MPNN_ERR_ARG, "tmsg_fwd: bad dims");
   int DP = pick_dp(nf, mf);
   MPNN_REQUIRE(DP <= 32, MPNN_ERR_UNSUPPORTED, "tmsg_fwd: feature width > 32 is served by the tensor-core path");
-  TMsg a = {row_ptr, edge_src, nullptr, uid, alpha, H, table, nullptr, S, beta, n_rows, N, nf, mf, zero_type};
+  TMsg a = {row_ptr, edge_src, nullptr, uid, alpha, H, table, nullptr, S, beta, n_rows, N, nf, mf, zero_type, n_rows};
   int grid = msg_grid(n_rows, DP);
   switch (DP) {
     case 8: k_tmsg_fwd<8><<<grid, 256, 0, stream>>>(a, M); break;
@@ -855,16 +856,18 @@ int mpnn_tmsg_fwd(const int* row_ptr, const int* edge_src, const int* uid, const
 // dH [n_rows, nf], dT [(unique_capacity+1)][DP][DP] (both written).  counts = device {E, U, ..} of the edge list.
 int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, const int* edge_src, const int* edge_dst,
                   const int* uid, const int* type_ptr, const int* type_eid, const int* counts, const float* alpha,
-                  const float* H, const float* table, const float* tableT, const float* S, int n_rows, int B, int N,
-                  int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dH, float* dT,
-                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  MPNN_REQUIRE(n_rows > 0 && N > 0 && nf > 0 && mf > 0 && B > 0, MPNN_ERR_ARG, "tmsg_bwd: bad dims");
+                  const float* H, const float* table, const float* tableT, const float* S, int n_rows, int n_src_rows,
+                  int B, int N, int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dH,
+                  float* dT, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(n_rows > 0 && N > 0 && nf > 0 && mf > 0 && B > 0 && n_src_rows >= 0, MPNN_ERR_ARG, "tmsg_bwd: bad dims");
+  const int n_src = n_src_rows > 0 ? n_src_rows : n_rows;
+  MPNN_REQUIRE(!(S && n_src != n_rows), MPNN_ERR_UNSUPPORTED, "tmsg_bwd: the HEAD form needs node-state senders");
   int DP = pick_dp(nf, mf);
   MPNN_REQUIRE(DP <= 32, MPNN_ERR_UNSUPPORTED, "tmsg_bwd: feature width > 32 is served by the tensor-core path");
   MPNN_REQUIRE(workspace_bytes >= mpnn_tmsg_bwd_workspace_bytes(edge_capacity, unique_capacity, nf, mf, B),
                MPNN_ERR_WORKSPACE, "tmsg_bwd: workspace too small");
   const int zero_type = unique_capacity;
-  TMsg a = {row_ptr, edge_src, edge_dst, uid, alpha, H, table, tableT, S, nullptr, n_rows, N, nf, mf, zero_type};
+  TMsg a = {row_ptr, edge_src, edge_dst, uid, alpha, H, table, tableT, S, nullptr, n_rows, N, nf, mf, zero_type, n_src};
   char* wp = (char*)workspace;
   float* Dsum = (float*)wp;
   wp += align_up((size_t)B * mf * sizeof(float), 256);
@@ -873,7 +876,7 @@ int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, co
     int rc = mpnn_graph_sum(dM, B, N, mf, Dsum, stream);
     if (rc) return rc;
   }
-  const int grid = msg_grid(n_rows, DP);
+  const int grid = msg_grid(n_src, DP);
   const int ch = table_chunk(edge_capacity);
   const int chunks = ceil_div(edge_capacity > 0 ? edge_capacity : 1, ch);
   switch (DP) {

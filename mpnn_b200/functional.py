@@ -796,8 +796,8 @@ class TypedMessageFn(torch.autograd.Function):
         ws = workspace(lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, nf, mf, el.B), dev)
         check(lib.mpnn_tmsg_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src), ptr(el.edge_dst),
                                 ptr(ti.uid), ptr(ti.type_ptr), ptr(ti.type_eid), ptr(ti.counts), ptr(alpha), ptr(H),
-                                ptr(table), ptr(tableT), ptr(S), el.n_rows, el.B, el.N, nf, mf, el.Ecap, ti.Ucap,
-                                ptr(dM), ptr(dH), ptr(dT), ptr(ws), ws.numel(), stream()), "tmsg_bwd")
+                                ptr(table), ptr(tableT), ptr(S), el.n_rows, H.shape[0], el.B, el.N, nf, mf, el.Ecap,
+                                ti.Ucap, ptr(dM), ptr(dH), ptr(dT), ptr(ws), ws.numel(), stream()), "tmsg_bwd")
         dbeta = None
         if has_beta:
             dbeta = torch.empty(mf, dtype=torch.float32, device=dev)

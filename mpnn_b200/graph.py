@@ -25,6 +25,7 @@ class EdgeList(object):
         self.edge_src, self.edge_dst, self.edge_w = edge_src, edge_dst, edge_w
         self.rows, self.csc_eid = rows, csc_eid
         self._csc_dst = None
+        self._per_edge = None
         self._typed = None
         self.Ecap = E           # allocated edge slots (== E unless built with explicit capacities)
 
@@ -34,6 +35,15 @@ class EdgeList(object):
             self._typed = dedup_rows(self)
         return self._typed
 
+    def per_edge_view(self):
+        """The same edge list for message functions that bring ONE explicit sender vector per edge (AttEdgeNetwork's
+        gated states, att_edge_network.py:26) instead of gathering node states: sender row of edge e is e."""
+        if self.E is None:
+            raise RuntimeError("mpnn_b200: per-edge sender vectors are not available in capacity (graph-capture) mode")
+        if self._per_edge is None:
+            self._per_edge = PerEdgeView(self)
+        return self._per_edge
+
     @property
     def csc_dst(self):
         """receiver row of every CSC entry (for scatter-free transposed reductions)"""
@@ -42,6 +52,23 @@ class EdgeList(object):
         if self._csc_dst is None:
             self._csc_dst = self.edge_dst[self.csc_eid.long()].contiguous() if self.E else self.edge_dst
         return self._csc_dst
+
+
+class PerEdgeView(object):
+    """EdgeList whose senders are the edges themselves (identity edge_src / col_ptr / csc_eid)."""
+
+    def __init__(self, el):
+        dev = el.row_ptr.device
+        E = el.E
+        self.B, self.N, self.ef, self.E, self.Ecap, self.n_rows = el.B, el.N, el.ef, E, el.Ecap, el.n_rows
+        self.row_ptr, self.edge_dst, self.edge_w, self.rows = el.row_ptr, el.edge_dst, el.edge_w, el.rows
+        self.edge_src = torch.arange(max(E, 1), dtype=torch.int32, device=dev)[:E]
+        self.col_ptr = torch.arange(E + 1, dtype=torch.int32, device=dev)
+        self.csc_eid = self.edge_src
+        self._base = el
+
+    def typed(self):
+        return self._base.typed()
 
 
 # ---- capacity mode (CUDA-graph capture): array sizes come from the caller, nothing is read back ----------

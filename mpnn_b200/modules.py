@@ -299,8 +299,9 @@ class EdgeNetwork(nn.Module):
             if reuse and k in self._msg_cache:
                 return self._msg_cache[k]
             if typed_dp(self.nf, self.mf) >= 0:
-                M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, None, el, el.edge_w, False,
-                                         self.nf, self.mf).view(B, N, self.mf)
+                G, gather = self._sender_vectors(afm, bfm, el)   # node states, or one gated vector per edge
+                M = TypedMessageFn.apply(G, table, tableT, None, el if gather else el.per_edge_view(), el.edge_w,
+                                         False, self.nf, self.mf).view(B, N, self.mf)
             else:
                 M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table, tableT, el, True, self.nf,
                                            self.mf).view(B, N, self.mf)
@@ -329,7 +330,11 @@ class EdgeNetwork(nn.Module):
 
 class AttEdgeNetwork(EdgeNetwork):
     """reference att_edge_network.py: the sender state is gated, per pair, by softmax_features(attn(cat(h_i, bond)))."""
-    _typed_capable = False
+
+    def _typed_ok(self, bfm, el):
+        # the gate brings one sender vector per edge: served by the table kernels of csrc/typed.cu (widths <= 32) when
+        # the edge count is known on the host (not under CUDA-graph capture)
+        return el.E is not None and typed_dp(self.nf, self.mf) >= 0 and super(AttEdgeNetwork, self)._typed_ok(bfm, el)
 
     def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
         super(AttEdgeNetwork, self).__init__(node_features, edge_features, message_features, activation_fn)
