@@ -355,6 +355,86 @@ int skinny_splits(int N, int K) {
 }
 bool skinny_ok(int M, int N, int K, long long sak) { return M <= 64 && sak == 1 && N >= 256 && K >= 128; }
 
+// ---------------------------------------------------------------------------------------------------
+// Small GEMM: problems whose 64 x 64 tiling would leave most SMs idle (Set2Vec's per-step products: 128 x 256 x 128
+// and smaller, set2vec.py:69-72,128, six of them in each of the 100 attention steps).  32 x 32 tiles (one CTA each,
+// 2 x 2 outputs per thread), 32-deep k-slabs whose global loads are issued one slab ahead of the FMAs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SM_T = 32, SM_K = 32;
+
+__global__ void __launch_bounds__(256) k_gemm_small(GemmArgs g) {
+  __shared__ float As[2][SM_K][SM_T + 1];   // [k][m]
+  __shared__ float Bs[2][SM_K][SM_T + 1];   // [k][n]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;   // outputs (m = ty*2 + {0,1}, n = tx*2 + {0,1})
+  const int m0 = blockIdx.y * SM_T, n0 = blockIdx.x * SM_T;
+  const bool a_kfast = (g.sak == 1), b_nfast = (g.sbn == 1);
+  // this thread's 4 + 4 elements of a slab: index i = tid + 256*it over the 32 x 32 tile
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = tid + it * 256;
+      const int ka = a_kfast ? (i & 31) : (i >> 5), ma = a_kfast ? (i >> 5) : (i & 31);
+      const int kb = b_nfast ? (i >> 5) : (i & 31), nb = b_nfast ? (i & 31) : (i >> 5);
+      ra[it] = (m0 + ma < g.M && k0 + ka < g.K) ? __ldg(g.A + (long long)(m0 + ma) * g.sam + (long long)(k0 + ka) * g.sak) : 0.f;
+      rb[it] = (n0 + nb < g.N && k0 + kb < g.K) ? __ldg(g.B + (long long)(k0 + kb) * g.sbk + (long long)(n0 + nb) * g.sbn) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = tid + it * 256;
+      const int ka = a_kfast ? (i & 31) : (i >> 5), ma = a_kfast ? (i >> 5) : (i & 31);
+      const int kb = b_nfast ? (i >> 5) : (i & 31), nb = b_nfast ? (i & 31) : (i >> 5);
+      As[buf][ka][ma] = ra[it];
+      Bs[buf][kb][nb] = rb[it];
+    }
+  };
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < g.K; k0 += SM_K) {
+    const bool more = k0 + SM_K < g.K;
+    if (more) fetch(k0 + SM_K);            // in flight while this slab is multiplied
+#pragma unroll
+    for (int kk = 0; kk < SM_K; ++kk) {
+      const float a0 = As[buf][kk][ty * 2], a1 = As[buf][kk][ty * 2 + 1];
+      const float b0 = Bs[buf][kk][tx * 2], b1 = Bs[buf][kk][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    if (more) {
+      stash(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+      if (m >= g.M || n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n];
+      float* c = g.C + (long long)m * g.ldc + n;
+      if (g.flags & 2) v += *c;
+      if (g.flags & 1) v = fmaxf(v, 0.f);
+      *c = v;
+    }
+}
+bool small_ok(int M, int N, int K) {
+  if (K == 0 || K > 2048) return false;
+  const long long big_tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN);
+  const long long small_tiles = (long long)ceil_div(M, SM_T) * ceil_div(N, SM_T);
+  return big_tiles * 4 <= mpnn_num_sms() && small_tiles <= 4LL * mpnn_num_sms();
+}
+
 int choose_splits(int M, int N, int K) {
   long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, BN);
   int sms = mpnn_num_sms();
@@ -435,6 +515,28 @@ int mpnn_gemm(const float* A, const float* B, float* C, int M, int N, int K, lon
       k_gemm_reduce<<<ceil_div((long long)M * N, 256), 256, 0, stream>>>(g.partial, splits, M, N, C, ldc, bias, flags);
       MPNN_CHECK_LAUNCH("k_gemm_reduce");
     }
+    return MPNN_OK;
+  }
+  if (small_ok(M, N, K)) {
+    GemmArgs g;
+    g.A = A;
+    g.B = B;
+    g.C = C;
+    g.bias = bias;
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.sam = sam;
+    g.sak = sak;
+    g.sbk = sbk;
+    g.sbn = sbn;
+    g.ldc = ldc;
+    g.flags = flags;
+    g.k_per_split = K;
+    g.partial = nullptr;
+    dim3 grid(ceil_div(N, SM_T), ceil_div(M, SM_T), 1);
+    k_gemm_small<<<grid, 256, 0, stream>>>(g);
+    MPNN_CHECK_LAUNCH("k_gemm_small");
     return MPNN_OK;
   }
   int splits = choose_splits(M, N, K);

@@ -257,3 +257,39 @@ def test_sibling_table_prefetch_is_transparent(dev):
     ref.pow(2).sum().backward()
     assert rel_err(got[1][0].cpu(), ref.detach()) <= 1e-4
     assert rel_err(got[1][1].cpu(), a0.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 128), (128, 64, 64), (64, 64, 128), (100, 130, 70), (3, 5, 7)])
+@pytest.mark.parametrize("form", ["nn", "nt", "tn"])
+def test_small_gemm_matches_torch(dev, shape, form):
+    """mpnn_gemm's small-problem kernel (Set2Vec's per-step products, set2vec.py:69-72,128) in the three operand forms
+    the path uses (A row- or column-major, B row- or column-major), with bias and with accumulation."""
+    from mpnn_b200 import _lib
+    from mpnn_b200._lib import check, ptr, stream
+    lib = _lib.load()
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g).to(dev)
+    ref = A.double() @ Bm.double()
+    if form == "tn":     # A stored [K, M]
+        Ad, sam, sak = A.t().contiguous().to(dev), 1, M
+    else:
+        Ad, sam, sak = A.contiguous().to(dev), K, 1
+    if form == "nt":     # B stored [N, K]
+        Bd, sbk, sbn = Bm.t().contiguous().to(dev), 1, K
+    else:
+        Bd, sbk, sbn = Bm.contiguous().to(dev), N, 1
+    ws = _lib.workspace(lib.mpnn_gemm_workspace_bytes(M, N, K), dev)
+    C = torch.empty(M, N, device=dev)
+    check(lib.mpnn_gemm(ptr(Ad), ptr(Bd), ptr(C), M, N, K, sam, sak, sbk, sbn, N, ptr(bias), 0, ptr(ws), ws.numel(),
+                        stream()), "gemm")
+    want = ref + bias.double().cpu()
+    assert float((C.double().cpu() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
+    C0 = torch.randn(M, N, generator=g).to(dev)
+    C = C0.clone()
+    check(lib.mpnn_gemm(ptr(Ad), ptr(Bd), ptr(C), M, N, K, sam, sak, sbk, sbn, N, None, 2, ptr(ws), ws.numel(), stream()),
+          "gemm")
+    want = ref + C0.double().cpu()
+    assert float((C.double().cpu() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
