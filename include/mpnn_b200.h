@@ -269,6 +269,7 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
 /* ---- a13/a14: Set2Vec with its input-less LSTM (readout/set2vec.py:68-75, 93-151) ----------------------- */
 long long mpnn_set2vec_saved_floats(int B, int N, int F, int steps);
 size_t mpnn_set2vec_workspace_bytes(int B, int N, int F);
+size_t mpnn_set2vec_bwd_workspace_bytes(int B, int N, int F, int steps);
 int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
                      const float* we, int B, int N, int F, int steps, float* out, float* saved, void* workspace,
                      size_t workspace_bytes, mpnn_stream_t stream);

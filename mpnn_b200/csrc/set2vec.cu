@@ -163,15 +163,16 @@ __global__ void k_energy_bwd(const float* __restrict__ X, const float* __restric
 }
 // dh [B,F] (already = dq Wq + dm[:, :F]) and dc_next -> dpre [B,4F], dc_prev
 __global__ void k_lstm_bwd(const float* __restrict__ gates, const float* __restrict__ tc,
-                           const float* __restrict__ cprev, const float* __restrict__ dh, float* __restrict__ dc,
-                           int B, int F, float* __restrict__ dpre) {
+                           const float* __restrict__ cprev, const float* __restrict__ dh,
+                           const float* __restrict__ dm, float* __restrict__ dc, int B, int F,
+                           float* __restrict__ dpre) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * F) return;
   int b = t / F, f = t - b * F;
   const float* gs = gates + (size_t)b * 4 * F;
   float i = gs[f], fg = gs[F + f], g = gs[2 * F + f], o = gs[3 * F + f];
   float th = tc[t];
-  float dhv = dh[t];
+  float dhv = dh[t] + dm[(size_t)b * 2 * F + f];   // dh = dq Wq + dm[:, :F]
   float dcn = dhv * o * (1.f - th * th) + dc[t];
   float cp = cprev ? cprev[t] : 0.f;
   float* dp = dpre + (size_t)b * 4 * F;
@@ -181,14 +182,6 @@ __global__ void k_lstm_bwd(const float* __restrict__ gates, const float* __restr
   dp[3 * F + f] = dhv * th * o * (1.f - o);
   dc[t] = dcn * fg;
 }
-__global__ void k_add_cols(float* __restrict__ dst, int ldd, const float* __restrict__ src, int lds, int rows,
-                           int cols) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= rows * cols) return;
-  int r = t / cols, c = t - r * cols;
-  dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
-}
-
 }  // namespace
 
 extern "C" {
@@ -206,6 +199,24 @@ size_t mpnn_set2vec_workspace_bytes(int B, int N, int F) {
   size_t g = mpnn_gemm_workspace_bytes(2 * F, 4 * F, B);
   size_t c = mpnn_colsum_workspace_bytes(B, 4 * F);
   return align_up(fl * sizeof(float), 256) + align_up(g > c ? g : c, 256) + 256;
+}
+
+// The backward keeps every step's dq / pw / dpre and a packed copy of the saved m so that the four parameter gradients
+// are ONE product (or column sum) over steps*B rows each instead of one small accumulate-launch per step.
+size_t mpnn_set2vec_bwd_workspace_bytes(int B, int N, int F, int steps) {
+  size_t rows = (size_t)B * N;
+  size_t sb = (size_t)steps * B;
+  size_t fl = 3 * rows                 // datt / de / spare
+              + (size_t)B * 2 * F * 2  // dm ping-pong
+              + (size_t)B * F * 2      // dc, dh
+              + sb * F * 2             // dq, pw stacks
+              + sb * 4 * F             // dpre stack
+              + sb * 2 * F;            // packed m
+  size_t g = mpnn_gemm_workspace_bytes(2 * F, 4 * F, (int)sb);
+  size_t g2 = mpnn_gemm_workspace_bytes(F, F, (int)sb);
+  size_t c = mpnn_colsum_workspace_bytes((int)sb, 4 * F);
+  size_t m = g > g2 ? g : g2;
+  return align_up(fl * sizeof(float), 256) + align_up(m > c ? m : c, 256) + 256;
 }
 
 int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
@@ -241,61 +252,58 @@ int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const
   return MPNN_OK;
 }
 
-// dWcat [2F,4F], dbcat [4F], dWq [F,F], dwe [F], dX [B,N,F] are written (zero-initialised here).
+// dWcat [2F,4F], dbcat [4F], dWq [F,F], dwe [F], dX [B,N,F] are written.
 int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const float* Wq, const float* we,
                      const float* saved_c, const float* dout, int B, int N, int F, int steps, float* dX, float* dWcat,
                      float* dbcat, float* dWq, float* dwe, void* workspace, size_t workspace_bytes,
                      cudaStream_t stream) {
   MPNN_REQUIRE(B > 0 && N > 0 && F > 0 && steps > 0, MPNN_ERR_ARG, "set2vec_bwd: bad dims");
-  MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_workspace_bytes(B, N, F), MPNN_ERR_WORKSPACE, "set2vec_bwd: workspace");
+  MPNN_REQUIRE((long long)steps * B < (1ll << 31), MPNN_ERR_UNSUPPORTED, "set2vec_bwd: steps*B too large");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_bwd_workspace_bytes(B, N, F, steps), MPNN_ERR_WORKSPACE,
+               "set2vec_bwd: workspace");
   (void)mask;
   float* saved = const_cast<float*>(saved_c);
   const int rows = B * N;
-  float* dpre = (float*)workspace;
-  float* datt = dpre + (size_t)B * 4 * F;
+  const size_t sb = (size_t)steps * B;
+  float* datt = (float*)workspace;
   float* de = datt + rows;
   float* spare = de + rows;
   float* dmA = spare + rows;
   float* dmB = dmA + (size_t)B * 2 * F;
   float* dc = dmB + (size_t)B * 2 * F;
-  float* dq = dc + (size_t)B * F;
-  float* pw = dq + (size_t)B * F;
-  float* dh = pw + (size_t)B * F;
-  char* sub = (char*)workspace + align_up(((size_t)B * 4 * F + 3 * (size_t)rows + (size_t)B * 2 * F * 2 +
-                                           (size_t)B * F * 4) * sizeof(float), 256);
+  float* dh = dc + (size_t)B * F;
+  float* dqS = dh + (size_t)B * F;
+  float* pwS = dqS + sb * F;
+  float* dpreS = pwS + sb * F;
+  float* mS = dpreS + sb * 4 * F;
+  float* fl_end = mS + sb * 2 * F;
+  char* sub = (char*)workspace + align_up((size_t)(fl_end - (float*)workspace) * sizeof(float), 256);
   size_t sub_bytes = workspace_bytes - (size_t)(sub - (char*)workspace);
   MPNN_CUDA(cudaMemsetAsync(dX, 0, (size_t)rows * F * sizeof(float), stream));
-  MPNN_CUDA(cudaMemsetAsync(dWcat, 0, (size_t)2 * F * 4 * F * sizeof(float), stream));
-  MPNN_CUDA(cudaMemsetAsync(dbcat, 0, (size_t)4 * F * sizeof(float), stream));
-  MPNN_CUDA(cudaMemsetAsync(dWq, 0, (size_t)F * F * sizeof(float), stream));
-  MPNN_CUDA(cudaMemsetAsync(dwe, 0, (size_t)F * sizeof(float), stream));
   MPNN_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * F * sizeof(float), stream));
   MPNN_CUDA(cudaMemcpyAsync(dmA, dout, (size_t)B * 2 * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  // packed m: step s at rows [s*B, (s+1)*B)
+  MPNN_CUDA(cudaMemcpy2DAsync(mS, (size_t)B * 2 * F * sizeof(float), saved, step_stride(B, N, F) * sizeof(float),
+                              (size_t)B * 2 * F * sizeof(float), steps, cudaMemcpyDeviceToDevice, stream));
   float* dm = dmA;
   float* dm_prev = dmB;
+  int rc;
   for (int s = steps - 1; s >= 0; --s) {
     StepPtrs cur = step_ptrs(saved, s, B, N, F);
-    int rc;
+    float* dq = dqS + (size_t)s * B * F;
+    float* pw = pwS + (size_t)s * B * F;
+    float* dpre = dpreS + (size_t)s * B * 4 * F;
     k_datt<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(X, dm, rows, N, F, datt);
     k_global_softmax_bwd<<<1, 1024, 0, stream>>>(cur.att, datt, rows, de);
     k_energy_bwd<<<B, 128, 0, stream>>>(X, cur.q, we, cur.att, de, dm, N, F, dq, pw, dX);
     MPNN_CHECK_LAUNCH("set2vec_bwd energy");
-    if ((rc = mpnn_colsum(pw, nullptr, B, F, F, 0, dwe, 1, sub, sub_bytes, stream))) return rc;
-    // dh = dq Wq + dm[:, :F]
+    // dh = dq Wq (+ dm[:, :F], added inside k_lstm_bwd)
     if ((rc = mpnn_gemm(dq, Wq, dh, B, F, F, F, 1, F, 1, F, nullptr, 0, nullptr, 0, stream))) return rc;
-    k_add_cols<<<ceil_div(B * F, 256), 256, 0, stream>>>(dh, F, dm, 2 * F, B, F);
-    // dWq += dq^T h
-    if ((rc = mpnn_gemm(dq, cur.m, dWq, F, F, B, 1, F, 2 * F, 1, F, nullptr, 2, sub, sub_bytes, stream))) return rc;
     const float* cprev = s == 0 ? nullptr : step_ptrs(saved, s - 1, B, N, F).c;
-    k_lstm_bwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(cur.gates, cur.tc, cprev, dh, dc, B, F, dpre);
+    k_lstm_bwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(cur.gates, cur.tc, cprev, dh, dm, dc, B, F, dpre);
     MPNN_CHECK_LAUNCH("set2vec_bwd lstm");
-    if ((rc = mpnn_colsum(dpre, nullptr, B, 4 * F, 4 * F, 0, dbcat, 1, sub, sub_bytes, stream))) return rc;
     if (s > 0) {
-      StepPtrs prev = step_ptrs(saved, s - 1, B, N, F);
-      // dWcat += m_prev^T dpre ; dm_prev = dpre Wcat^T
-      if ((rc = mpnn_gemm(prev.m, dpre, dWcat, 2 * F, 4 * F, B, 1, 2 * F, 4 * F, 1, 4 * F, nullptr, 2, sub, sub_bytes,
-                          stream)))
-        return rc;
+      // dm_prev = dpre Wcat^T
       if ((rc = mpnn_gemm(dpre, Wcat, dm_prev, B, 2 * F, 4 * F, 4 * F, 1, 1, 4 * F, 2 * F, nullptr, 0, nullptr, 0,
                           stream)))
         return rc;
@@ -303,6 +311,19 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
       dm = dm_prev;
       dm_prev = t;
     }
+  }
+  // parameter gradients over all steps at once
+  if ((rc = mpnn_colsum(pwS, nullptr, (int)sb, F, F, 0, dwe, 0, sub, sub_bytes, stream))) return rc;
+  if ((rc = mpnn_colsum(dpreS, nullptr, (int)sb, 4 * F, 4 * F, 0, dbcat, 0, sub, sub_bytes, stream))) return rc;
+  // dWq = sum_s dq_s^T h_s
+  if ((rc = mpnn_gemm(dqS, mS, dWq, F, F, (int)sb, 1, F, 2 * F, 1, F, nullptr, 0, sub, sub_bytes, stream))) return rc;
+  // dWcat = sum_{s>=1} m_{s-1}^T dpre_s  (step 0 has no recurrent input)
+  if (steps > 1) {
+    if ((rc = mpnn_gemm(mS, dpreS + (size_t)B * 4 * F, dWcat, 2 * F, 4 * F, (int)(sb - B), 1, 2 * F, 4 * F, 1, 4 * F,
+                        nullptr, 0, sub, sub_bytes, stream)))
+      return rc;
+  } else {
+    MPNN_CUDA(cudaMemsetAsync(dWcat, 0, (size_t)2 * F * 4 * F * sizeof(float), stream));
   }
   return MPNN_OK;
 }

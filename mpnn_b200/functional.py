@@ -641,7 +641,7 @@ class Set2VecFn(torch.autograd.Function):
         def make_bufs():
             return [torch.empty_like(X), torch.empty_like(Wcat), torch.empty(4 * F, dtype=torch.float32, device=dev),
                     torch.empty_like(Wq), torch.empty_like(we),
-                    workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)]
+                    workspace(lib.mpnn_set2vec_bwd_workspace_bytes(B, N, F, steps), dev)]
 
         def run(ins, bufs):
             x, mk, wc, wq, w_e, sv, do = ins
