@@ -44,7 +44,7 @@ WORKLOADS = {
                  readout_func="Set2Vec", graph=False,
                  desc="att_model (AttEdgeNetwork, AdjMsgAgg, Set2Vec x100), ZINC-shaped, B=128/GPU, d=32, ef=8, P=64, T=3"),
     # configs[3]: normed_encoded_basic_model (atom/bond encoders + masked BN1d everywhere), B=2048 global
-    "affinity": dict(variant="normed_encoded", d=8, ef=2, T=3, out=16, targets=1, B=2048, encoders=True, graph=False,
+    "affinity": dict(variant="normed_encoded", d=8, ef=2, T=3, out=16, targets=1, B=2048, encoders=True,
                      desc="normed_encoded_basic_model (encoders 30->8 / 8->2, MaskBatchNorm1d), B=2048, d=8, ef=2, P=16, T=3"),
 }
 

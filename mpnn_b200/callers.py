@@ -19,7 +19,11 @@ import torch
 
 from .modules import (AdjMsgAgg, EdgeNetwork, GraphLevelOutput, GRUUpdate, MaskBatchNorm, MaskBatchNorm1d)
 
+from .graph import typed_bonds
+import os
+
 _PER_STEP = ("normed", "att", "normed_encoded")
+TYPED_BONDS = os.environ.get("MPNN_B200_TYPED_BONDS", "1") != "0"
 
 
 class MessagePassingModel(nn.Module):
@@ -66,6 +70,10 @@ class MessagePassingModel(nn.Module):
         v = self.variant
         if v == "normed_encoded":
             afm = self.aebn(self.ae(afm), mask)
+            if TYPED_BONDS and torch.is_tensor(bfm) and bfm.is_cuda and not bfm.requires_grad:
+                # encoder + bebn + edge networks on the distinct (bond row, adjacency value) pairs (graph.TypedBonds);
+                # the reference model file gets the same by being handed `typed_bonds(bfm, adj)` in place of `bfm`
+                bfm = typed_bonds(bfm, adj)
             bfm = self.bebn(self.be(bfm), adj)
         node_state = afm
         if v == "basic":

@@ -226,6 +226,8 @@ def _key(t):
 
 
 def edge_list_for(bfm, adj=None):
+    if isinstance(bfm, TypedBonds):
+        return bfm.edge_list(adj)
     k = (_key(bfm), _key(adj))
     hit = _CACHE.get(k)
     if hit is not None:
@@ -240,6 +242,196 @@ def edge_list_for(bfm, adj=None):
 
 def clear_cache():
     _CACHE.clear()
+
+
+# =====================================================================================================================
+# Typed bond tensor: a [B,N,N,F] bond tensor held as its DISTINCT rows  (encoders + input BNs on the
+# compacted form instead of the dense O(B N^2) tensor).
+#
+# The datasets' raw bond rows are categorical, so a batch holds a few dozen distinct (row, adjacency value) pairs.
+# Every row-wise function of the dense tensor -- the bond encoder's Linear/Tanh layers (mpnn_functions/encoders/
+# bond_autoencoder.py:7-11), the adjacency-masked batch norm `bebn` (normed_encoded_basic_model.py:68) -- maps equal
+# rows to equal rows, so it can be evaluated on the distinct rows alone, weighted by how often each one occurs; the
+# edge network then builds its table of matrices from the resulting rows and back-propagates into them, and autograd
+# carries the gradient through the row-space BN and the stock encoder modules.  Nothing of size B N^2 F is touched.
+# The object follows torch's tensor-like protocol (`__torch_function__`), so the UNCHANGED reference model file can be
+# handed one in place of `bfm`; anything that is not row-wise materialises the dense tensor and carries on.
+# =====================================================================================================================
+def _rowwise_table():
+    F = torch.nn.functional
+    unary = [torch.tanh, torch.relu, torch.sigmoid, F.relu, F.tanh, F.sigmoid, F.leaky_relu, F.elu, F.selu, F.celu,
+             F.gelu, F.softplus, F.silu, F.hardtanh, F.relu6, F.softsign, F.tanhshrink, F.logsigmoid, F.mish,
+             torch.nn.functional.hardswish, torch.nn.functional.hardsigmoid, torch.abs, torch.neg, torch.exp]
+    return set(unary)
+
+
+class TypedBonds(object):
+    """rows [R, F] (R = Ucap + 1; row `zero_type` = Ucap stands for every pair that is not in the edge list),
+    mask values a [R] (the adjacency value of the type) and occurrence counts cnt [R] (float; all on the device)."""
+
+    _ROWWISE = None
+
+    def __init__(self, rows, el, a, cnt, adj_key, B, N):
+        self._rows, self._el, self._a, self._cnt, self._adj_key = rows, el, a, cnt, adj_key
+        self._B, self._N = B, N
+        self._dense = None
+
+    # ---- tensor-like surface -------------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return torch.Size((self._B, self._N, self._N, self._rows.shape[1]))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 4
+
+    device = property(lambda self: self._rows.device)
+    dtype = property(lambda self: self._rows.dtype)
+    is_cuda = property(lambda self: self._rows.is_cuda)
+    requires_grad = property(lambda self: self._rows.requires_grad)
+
+    def float(self):
+        return self
+
+    def contiguous(self):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def __len__(self):
+        return self._B
+
+    def __repr__(self):
+        return "TypedBonds(shape=%s, distinct=%d)" % (tuple(self.shape), self._rows.shape[0])
+
+    # ---- row space -----------------------------------------------------------------------------------------------
+    def with_rows(self, rows):
+        """the same pairs with new row values (a row-wise function of this tensor)"""
+        import copy
+        el = copy.copy(self._el)
+        ti = copy.copy(self._el._typed)
+        ti.urows = rows
+        el._typed = ti
+        el.ef = rows.shape[1]
+        el.rows = None
+        el._per_edge = None
+        el.__dict__.pop("_table_users", None)
+        return TypedBonds(rows, el, self._a, self._cnt, self._adj_key, self._B, self._N)
+
+    def edge_list(self, adj=None):
+        if adj is not None and _key(adj) != self._adj_key:
+            raise RuntimeError("mpnn_b200.TypedBonds: used with a different adjacency tensor than it was built from")
+        return self._el
+
+    def dense(self):
+        """[B,N,N,F], differentiable in the rows (any consumer that is not row-wise ends up here)"""
+        if self._dense is None:
+            el = self._el
+            if el.E is None:
+                raise RuntimeError("mpnn_b200.TypedBonds: the dense form is not available in capacity (graph-capture) "
+                                   "mode")
+            ti = el._typed
+            tmap = torch.full((self._B * self._N * self._N,), ti.zero_type, dtype=torch.long, device=self.device)
+            if el.E:
+                pair = el.edge_dst.long() * self._N + el.edge_src.long() % self._N
+                tmap[pair] = ti.uid.long()
+            self._dense = self._rows.index_select(0, tmap).view(self.shape)
+        return self._dense
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.dense(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        F = torch.nn.functional
+        if cls._ROWWISE is None:
+            cls._ROWWISE = _rowwise_table()
+        x = args[0] if args else None
+        if isinstance(x, TypedBonds):
+            rest = list(args[1:]) + list(kwargs.values())
+            plain = not any(isinstance(a, TypedBonds) for a in rest)
+            if func is F.linear and plain:
+                return x.with_rows(func(x._rows, *args[1:], **kwargs))
+            if func in cls._ROWWISE and plain and not kwargs.get("inplace", False):
+                return x.with_rows(func(x._rows, *args[1:], **kwargs))
+            if func in (F.softmax, F.log_softmax, torch.softmax, torch.log_softmax) and plain:
+                dim = kwargs.get("dim", args[1] if len(args) > 1 else None)
+                if dim in (-1, 3) and kwargs.get("dtype") is None:
+                    log = func in (F.log_softmax, torch.log_softmax)
+                    return x.with_rows((torch.log_softmax if log else torch.softmax)(x._rows, -1))
+            if func in (F.dropout, torch.dropout) and plain:
+                training = kwargs.get("training", args[2] if len(args) > 2 else True)
+                p = kwargs.get("p", args[1] if len(args) > 1 else 0.5)
+                if not training or p == 0:
+                    return x
+
+        def unwrap(a):
+            if isinstance(a, TypedBonds):
+                return a.dense()
+            if isinstance(a, (list, tuple)):
+                return type(a)(unwrap(v) for v in a)
+            return a
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in kwargs.items()})
+
+
+def _tb_binop(name):
+    def f(self, other):
+        return getattr(self.dense(), name)(other.dense() if isinstance(other, TypedBonds) else other)
+    return f
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
+           "__matmul__", "__getitem__", "__pow__", "__eq__", "__ne__", "__lt__", "__gt__", "__le__", "__ge__"):
+    setattr(TypedBonds, _n, _tb_binop(_n))
+TypedBonds.__neg__ = lambda self: -self.dense()
+TypedBonds.__hash__ = object.__hash__
+
+
+def typed_bonds(bfm, adj):
+    """(bfm [B,N,N,ef] data tensor, adj [B,N,N]) -> TypedBonds, or `bfm` itself when the batch holds more than
+    TYPED_MAX_UNIQUE distinct (bond row, adjacency value) pairs.  Types are keyed on the row AND the adjacency value,
+    so adjacency-masked statistics are exact for weighted adjacencies too."""
+    import copy
+    if isinstance(bfm, TypedBonds):
+        return bfm
+    if bfm.requires_grad:
+        raise RuntimeError("mpnn_b200.typed_bonds: bfm must be a data tensor (no gradient)")
+    el0 = edge_list_for(bfm, adj)
+    B, N, ef = el0.B, el0.N, el0.ef
+    dev = bfm.device
+    Ecap = el0.Ecap
+    el = copy.copy(el0)
+    w = el0.edge_w if el0.E is None else el0.edge_w[:Ecap]
+    aug = torch.zeros(Ecap + 1, ef + 1, dtype=torch.float32, device=dev)
+    if Ecap:
+        aug[:Ecap, :ef] = el0.rows[:Ecap]
+        aug[:Ecap, ef] = w[:Ecap]
+    el.rows, el.ef, el._typed, el._per_edge = aug, ef + 1, None, None
+    el.__dict__.pop("_table_users", None)
+    if _CAPACITY is not None:
+        ti = dedup_rows(el, unique_capacity=_CAPACITY[1])
+        _CAPTURED_COUNTS.append(ti.counts)
+    else:
+        ti = dedup_rows(el)
+    if ti.type_ptr is None:
+        return bfm
+    el._typed = ti
+    ua = ti.urows                                      # [Ucap+1, ef+1]; rows >= U are zero
+    rows = ua[:, :ef].contiguous()
+    a = ua[:, ef].contiguous()
+    tp = ti.type_ptr
+    cnt = (tp[1:] - tp[:-1]).to(torch.float32)
+    n_edges = el0.row_ptr[el0.n_rows:el0.n_rows + 1].to(torch.float32)
+    zero_cnt = float(B) * N * N - n_edges
+    cnt = torch.cat([cnt, zero_cnt])
+    tb = TypedBonds(rows, el, a, cnt, _key(adj), B, N)
+    return tb.with_rows(rows)
 
 
 class GatherEdgeRows(torch.autograd.Function):

@@ -160,6 +160,8 @@ class EdgeNetwork(nn.Module):
         bfm is not differentiated, the batch holds few distinct bond rows, and the feature widths are <= 32
         (CUDA-core gather kernels, csrc/typed.cu) or 33..256 in multiples of 4 (tcgen05 grouped GEMM,
         csrc/tc_message.cu)."""
+        if isinstance(bfm, graph.TypedBonds):     # distinct rows are differentiable inputs of the table
+            return True
         if not self._typed_capable or bfm.requires_grad or table_dp(self.nf, self.mf) < 0:
             return False
         ti = el.typed()
@@ -325,6 +327,9 @@ class EdgeNetwork(nn.Module):
     def forward(self, afm, bfm, reuse_graph_tensors=False):
         if not afm.is_cuda:
             raise RuntimeError("mpnn_b200.EdgeNetwork: CUDA tensors required (there is no CPU fallback)")
+        if isinstance(bfm, graph.TypedBonds) and not (type(self)._typed_capable and type(self)._typed_ok is
+                                                      EdgeNetwork._typed_ok and table_dp(self.nf, self.mf) >= 0):
+            bfm = bfm.dense()
         return LazyMessages(self, afm, bfm, bool(reuse_graph_tensors))
 
 
@@ -410,6 +415,7 @@ class BiLiniearEdgeNetwork(nn.Module):
     def forward(self, afm, bfm, reuse_graph_tensors=False):
         if not afm.is_cuda:
             raise RuntimeError("mpnn_b200.BiLiniearEdgeNetwork: CUDA tensors required (there is no CPU fallback)")
+        bfm = _as_dense(bfm)
         return LazyMessages(self, afm, bfm, bool(reuse_graph_tensors))
 
 
@@ -445,7 +451,21 @@ class GGNNMsgPass(nn.Module):
 # aggregators
 # =================================================================================================
 def _as_dense(messages):
+    if isinstance(messages, graph.TypedBonds):
+        return messages.dense()
     return messages.materialize() if isinstance(messages, LazyMessages) else messages
+
+
+def _typed_mask_bn(tb, mask, stats_fn):
+    """Adjacency-masked batch norm of a TypedBonds tensor in row space: every sum over the B N^2 rows of the dense
+    tensor is a count-weighted sum over the distinct rows (count c_u, mask value a_u).  `stats_fn(x, a, c, M)` returns
+    the normalised rows; autograd differentiates the few [R, F] torch ops."""
+    if graph._key(mask) != tb._adj_key:
+        return None
+    a = tb._a.unsqueeze(1)
+    c = tb._cnt.unsqueeze(1)
+    M = (tb._cnt * tb._a).sum()
+    return tb.with_rows(stats_fn(tb._rows, a, c, M))
 
 
 class AdjMsgAgg(nn.Module):
@@ -559,13 +579,42 @@ class MaskBatchNorm(nn.Module):
         super(MaskBatchNorm, self).__init__()
 
     def forward(self, tensor, mask, eps=1e-6):
+        if isinstance(tensor, graph.TypedBonds):
+            def stats(x, a, c, M):   # mask_batch_norm.py:11-15 (unmasked sum for the mean)
+                mean = (c * x).sum(0) / M
+                var = (c * ((x - mean) * a) ** 2).sum(0) / M
+                return (x - mean) * a / torch.sqrt(var + eps)
+            out = _typed_mask_bn(tensor, mask, stats)
+            if out is not None:
+                return out
         tensor = _as_dense(tensor)
         y = MaskBNFn.apply(tensor.reshape(-1, tensor.shape[-1]), mask.reshape(-1), eps)
         return y.view(tensor.shape)
 
 
 class MaskBatchNorm1d(nn.BatchNorm1d):
+    def _typed_forward(self, tb, mask):
+        def stats(x, a, c, M):   # mask_batch_norm.py:20-38 on the distinct rows
+            mean = (c * a * x).sum(0) / M
+            var = (c * ((x - mean) * a) ** 2).sum(0) / M
+            if not self.training and self.track_running_stats:
+                y = (x - self.running_mean) / (self.running_var ** .5 + self.eps)
+            else:
+                if self.track_running_stats:
+                    with torch.no_grad():
+                        self.running_mean.mul_(1 - self.momentum).add_(self.momentum * mean)
+                        self.running_var.mul_(1 - self.momentum).add_(self.momentum * var)
+                y = (x - mean) / (var.sqrt() + self.eps)
+            if self.affine:
+                y = self.weight * y + self.bias
+            return y * a
+        return _typed_mask_bn(tb, mask, stats)
+
     def forward(self, tensor, mask):
+        if isinstance(tensor, graph.TypedBonds):
+            out = self._typed_forward(tensor, mask)
+            if out is not None:
+                return out
         tensor = _as_dense(tensor)
         training = self.training or not self.track_running_stats
         rm = self.running_mean if self.track_running_stats else None

@@ -1,0 +1,245 @@
+"""graph.TypedBonds: bond encoder + adjacency-masked batch norm + edge networks evaluated on the
+DISTINCT (bond row, adjacency value) pairs of a batch instead of the dense [B,N,N,ef] tensor.  Every test compares the
+row-space result with the SAME modules run on the dense tensor (the path that is pinned to the reference's golden
+vectors in test_gpu_parity.py)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+TOL_OUT = 1e-4
+TOL_GRAD = 1e-3
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _affinity_batch(B, dev, weighted=False, seed=0):
+    from mpnn_b200 import synthetic
+    batch = synthetic.make_batch("affinity", B=B, seed_offset=seed)
+    t = {k: torch.from_numpy(batch[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+    if weighted:   # bond-order-like adjacency values: types must be keyed on (row, adjacency value)
+        g = torch.Generator().manual_seed(3)
+        w = torch.randint(1, 4, t["adj"].shape, generator=g).float().to(dev)
+        w = torch.maximum(w, w.transpose(1, 2))
+        t["adj"] = t["adj"] * w
+    return t
+
+
+def test_dense_round_trip_bit_exact(dev):
+    from mpnn_b200 import graph
+    for weighted in (False, True):
+        t = _affinity_batch(16, dev, weighted)
+        tb = graph.typed_bonds(t["bfm"], t["adj"])
+        assert isinstance(tb, graph.TypedBonds)
+        assert tuple(tb.shape) == tuple(t["bfm"].shape)
+        assert torch.equal(tb.dense(), t["bfm"])
+        # counts: every pair of the dense tensor is accounted for exactly once
+        B, N = t["adj"].shape[:2]
+        assert float(tb._cnt.sum()) == float(B * N * N)
+        # adjacency value per type reproduces the dense adjacency
+        el = tb.edge_list(t["adj"])
+        ti = el.typed()
+        pair = el.edge_dst.long() * N + el.edge_src.long() % N
+        adj_t = torch.zeros(B * N * N, device=dev)
+        adj_t[pair] = tb._a[ti.uid.long()]
+        assert torch.equal(adj_t.view(B, N, N), t["adj"])
+
+
+def test_stock_modules_stay_in_row_space(dev):
+    from mpnn_b200 import graph
+    t = _affinity_batch(8, dev)
+    tb = graph.typed_bonds(t["bfm"], t["adj"])
+    torch.manual_seed(1)
+    enc = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 3), nn.ReLU(), nn.Softmax(dim=-1),
+                        nn.Dropout(0.0), nn.ELU(), nn.Sigmoid()).to(dev)
+    y = enc(tb)
+    assert isinstance(y, graph.TypedBonds)
+    assert tuple(y.shape) == tuple(t["bfm"].shape[:3]) + (3,)
+    ref = enc(t["bfm"])
+    assert rel_err(y.dense(), ref) <= 1e-6
+    # anything that is not row-wise falls back to the dense tensor and still gives the right answer
+    assert torch.allclose(tb * 2.0, t["bfm"] * 2.0)
+    assert torch.allclose(torch.sum(tb, dim=(1, 2)), t["bfm"].sum(dim=(1, 2)))
+    assert torch.allclose(tb.permute(0, 2, 1, 3), t["bfm"].permute(0, 2, 1, 3))
+
+
+@pytest.mark.parametrize("kind", ["bn1d_train", "bn1d_eval", "bn"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_masked_bn_in_row_space(dev, kind, weighted):
+    from mpnn_b200 import graph
+    from mpnn_b200.modules import MaskBatchNorm, MaskBatchNorm1d
+    t = _affinity_batch(16, dev, weighted)
+    torch.manual_seed(2)
+    enc = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2)).to(dev)
+
+    def build():
+        if kind == "bn":
+            return MaskBatchNorm().to(dev)
+        bn = MaskBatchNorm1d(2).to(dev)
+        with torch.no_grad():
+            bn.weight.copy_(torch.tensor([1.3, 0.7]))
+            bn.bias.copy_(torch.tensor([0.2, -0.4]))
+            bn.running_mean.copy_(torch.tensor([0.1, -0.2]))
+            bn.running_var.copy_(torch.tensor([0.9, 1.4]))
+        return bn.train() if kind == "bn1d_train" else bn.eval()
+
+    outs = []
+    for typed in (True, False):
+        bn = build()
+        enc.zero_grad()
+        x = graph.typed_bonds(t["bfm"], t["adj"]) if typed else t["bfm"]
+        y = bn(enc(x), t["adj"])
+        if typed:
+            assert isinstance(y, graph.TypedBonds)
+            y = y.dense()
+        g = torch.Generator().manual_seed(4)
+        cot = torch.randn(y.shape, generator=g).to(dev)
+        (y * cot).sum().backward()
+        grads = [p.grad.clone() for p in enc.parameters()] + [p.grad.clone() for p in bn.parameters()]
+        bufs = [b.clone() for b in bn.buffers()]
+        outs.append((y.detach(), grads, bufs))
+    (y1, g1, b1), (y0, g0, b0) = outs
+    assert rel_err(y1, y0) <= TOL_OUT
+    # the bias in front of a batch norm has a theoretically zero gradient (both paths return round-off): absolute
+    # floor relative to the largest gradient of the stack
+    gscale = max(float(b.abs().max()) for b in g0)
+    for a, b in zip(g1, g0):
+        diff = float((a.double() - b.double()).abs().max())
+        assert diff <= TOL_GRAD * float(b.abs().max()) + 2e-5 * gscale, (a, b, gscale)
+    for a, b in zip(b1, b0):
+        assert rel_err(a.float(), b.float()) <= TOL_OUT
+
+
+def _encoded_model(dev, steps=3, d=8):
+    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    torch.manual_seed(317)
+    ae = nn.Sequential(nn.Linear(30, 15, bias=False), nn.Tanh(), nn.Linear(15, d))
+    be = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
+    mod = MessagePassingModel("normed_encoded", d, 2, d, 1, 16, message_steps=steps, atom_encoder=ae, bond_encoder=be)
+    mod.apply(kaiming_init)
+    return mod.to(dev).train()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_encoded_model_row_space_equals_dense(dev, weighted, monkeypatch):
+    """config 4's caller loop, TypedBonds on vs off.  Outputs and input gradients must agree tightly.  The parameter
+    gradients of this stack are sums with heavy cancellation (every Linear sits in front of a batch norm), and the two
+    paths add in a different order (per distinct row vs per edge), so both are judged against the fp64 oracle: the
+    row-space path must be within tolerance of it, or at least as close to it as the dense path is."""
+    from mpnn_b200 import callers, graph
+    from oracle import mpnn_oracle as O
+    from golden_util import leaf_sd
+    t = _affinity_batch(32, dev, weighted)
+    res = []
+    for typed in (True, False):
+        monkeypatch.setattr(callers, "TYPED_BONDS", typed)
+        graph.clear_cache()
+        mod = _encoded_model(dev)
+        sd0 = {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
+        afm = t["afm"].clone().requires_grad_(True)
+        out = mod(afm, t["bfm"], t["adj"], t["mask"])
+        cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+        (out * cot).sum().backward()
+        res.append((out.detach(), afm.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters()
+                                                      if p.grad is not None},
+                    {k: b.clone() for k, b in mod.named_buffers()}))
+    (o1, a1, g1, b1), (o0, a0, g0, b0) = res
+    assert rel_err(o1, o0) <= TOL_OUT
+    assert rel_err(a1, a0) <= TOL_GRAD
+    assert set(g1) == set(g0)
+    for k in b0:   # running statistics (means of normalised messages are round-off around zero: absolute floor)
+        assert float((b1[k].double() - b0[k].double()).abs().max()) <= TOL_OUT * float(b0[k].abs().max()) + 1e-6, k
+    # fp64 oracle
+    sd = leaf_sd(sd0, dtype=torch.float64)
+    c = {k: v.detach().cpu().double() for k, v in t.items()}
+    ref = O.normed_encoded_model(c["afm"], c["bfm"], c["adj"], c["mask"], sd, steps=3, buffers={})
+    assert rel_err(o1.cpu(), ref.detach()) <= TOL_OUT
+    (ref * cot.cpu().double()).sum().backward()
+    gscale = max(float(v.grad.abs().max()) for v in sd.values() if getattr(v, "grad", None) is not None)
+    for k in g0:
+        if getattr(sd[k], "grad", None) is None:
+            continue
+        r = sd[k].grad
+        e1 = float((g1[k].cpu().double() - r).abs().max())
+        e0 = float((g0[k].cpu().double() - r).abs().max())
+        # floor: 1e-5 of the stack's largest gradient (7.6e6 here -- the kaiming-initialised 50-layer trunk amplifies;
+        # entries of O(100) are round-off dominated in BOTH fp32 paths: the dense one is 12 % off the oracle there)
+        assert e1 <= max(TOL_GRAD * float(r.abs().max()) + 1e-5 * gscale, 2.0 * e0), (k, e1, e0, float(r.abs().max()))
+
+
+def test_reference_model_file_usage(dev):
+    """the UNCHANGED reference loop (normed_encoded_basic_model.py:67-72) handed a TypedBonds in place of bfm"""
+    from mpnn_b200 import graph
+    t = _affinity_batch(16, dev)
+    mod = _encoded_model(dev)
+
+    def reference_forward(m, afm, bfm, adj, mask):
+        afm = m.aebn(m.ae(afm), mask)
+        bfm = m.bebn(m.be(bfm), adj)
+        node_state = afm
+        for mf, bn, ma_bn in zip(m.mfs, m.bns, m.ma_bns):
+            node_state = bn(m.uf(ma_bn(m.ma(mf(afm, bfm), adj), mask), node_state, mask), mask)
+        return m.of(torch.cat([node_state, afm], dim=-1), mask=mask)
+
+    mod.eval()
+    with torch.no_grad():
+        y_dense = reference_forward(mod, t["afm"], t["bfm"], t["adj"], t["mask"])
+        y_typed = reference_forward(mod, t["afm"], graph.typed_bonds(t["bfm"], t["adj"]), t["adj"], t["mask"])
+    assert rel_err(y_typed, y_dense) <= TOL_OUT
+
+
+def test_wrong_adjacency_is_rejected(dev):
+    from mpnn_b200 import graph
+    from mpnn_b200.modules import EdgeNetwork, AdjMsgAgg
+    t = _affinity_batch(4, dev)
+    tb = graph.typed_bonds(t["bfm"], t["adj"])
+    net = EdgeNetwork(8, 8, 8).to(dev)
+    other = t["adj"].clone()
+    with pytest.raises(RuntimeError):
+        AdjMsgAgg(1)(net(t["afm"][..., :8].contiguous(), tb), other)
+
+
+def test_encoded_step_is_graph_capturable(dev):
+    """with the bond features in row space nothing in config 4 needs the host-side edge count: the whole train step
+    replays as one CUDA graph and matches the eager step"""
+    from mpnn_b200 import graph, graphs
+    t = _affinity_batch(64, dev)
+    labels = torch.randn(64, 1, generator=torch.Generator().manual_seed(1)).to(dev)
+    losses = {}
+    for mode in ("eager", "graph"):
+        graph.clear_cache()
+        mod = _encoded_model(dev)
+        head = nn.Linear(16, 1).to(dev)
+        torch.manual_seed(5)
+        nn.init.normal_(head.weight, std=0.1)
+        params = list(mod.parameters()) + list(head.parameters())
+        opt = torch.optim.Adam(params, lr=1e-3, capturable=(mode == "graph"))
+
+        batch = dict(t, labels=labels)
+
+        def step_fn(b):
+            graph.clear_cache()
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(head(mod(b["afm"], b["bfm"], b["adj"], b["mask"])), b["labels"])
+            loss.backward()
+            opt.step()
+            return loss
+
+        if mode == "eager":
+            ls = [float(step_fn(batch)) for _ in range(6)][3:]
+        else:
+            gs = graphs.GraphedStep(step_fn, batch, warmup=3)
+            ls = [float(gs(batch)) for _ in range(3)]
+            gs.check()
+        losses[mode] = ls
+    assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3, atol=1e-6), losses
