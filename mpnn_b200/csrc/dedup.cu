@@ -43,24 +43,44 @@ __device__ __forceinline__ bool same_row(const uint32_t* __restrict__ a, const u
   return eq;
 }
 
-// pass 1: claim / join a slot; the slot ends up holding the smallest edge index of its row value
+// pass 1: claim / join a slot; the slot ends up holding the smallest edge index of its row value.
+// Bond rows are categorical: a batch of 10^5 edges holds a few dozen distinct rows, so a naive insert is 10^5 atomics
+// on a few dozen addresses.  Two filters keep the atomics to a handful per warp: (1) lanes of a warp that carry the
+// same row elect their lowest lane (= smallest edge index) to insert for all of them; (2) a slot is read before it is
+// touched -- once it holds a smaller index of the same row value there is nothing to do (slot values only decrease,
+// and always within one row value, so a stale read is still a valid witness).
 __global__ void k_dedup_insert(const uint32_t* __restrict__ rows, const int* __restrict__ n_edges_ptr, int cap,
                                int ef, uint32_t* __restrict__ table, uint32_t mask, int* __restrict__ slot_of) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  int E = min(*n_edges_ptr, cap);
-  if (e >= E) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = min(*n_edges_ptr, cap);
+  const bool valid = e < E;
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const int lane = threadIdx.x & 31;
   const uint32_t* x = rows + (size_t)e * ef;
-  uint32_t s = hash_row(x, ef) & mask;
-  while (true) {
-    uint32_t old = atomicCAS(&table[s], SLOT_EMPTY, (uint32_t)e);
-    if (old == SLOT_EMPTY) break;
-    if (same_row(rows + (size_t)old * ef, x, ef)) {
-      atomicMin(&table[s], (uint32_t)e);
-      break;
+  const uint32_t h = hash_row(x, ef);
+  const unsigned grp = __match_any_sync(act, h);
+  const int leader = __ffs(grp) - 1;
+  // equal hash is not equal row: lanes whose row differs from their leader's insert on their own
+  const int e_lead = __shfl_sync(grp, e, leader);
+  const bool follows = (lane != leader) && same_row(rows + (size_t)e_lead * ef, x, ef);
+  uint32_t s = h & mask;
+  if (!follows) {
+    while (true) {
+      uint32_t cur = *((volatile uint32_t*)&table[s]);
+      if (cur == SLOT_EMPTY) {
+        cur = atomicCAS(&table[s], SLOT_EMPTY, (uint32_t)e);
+        if (cur == SLOT_EMPTY) break;
+      }
+      if (same_row(rows + (size_t)cur * ef, x, ef)) {
+        if (cur > (uint32_t)e) atomicMin(&table[s], (uint32_t)e);
+        break;
+      }
+      s = (s + 1) & mask;
     }
-    s = (s + 1) & mask;
   }
-  slot_of[e] = (int)s;
+  const uint32_t s_lead = __shfl_sync(grp, s, leader);
+  slot_of[e] = (int)(follows ? s_lead : s);
 }
 
 // pass 2: rep[e] and the representative flags (0 beyond E so that the scan can run over the capacity)

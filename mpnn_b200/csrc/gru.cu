@@ -350,6 +350,9 @@ int fused_dp(int d) { return d <= 8 ? 8 : (d <= 16 ? 16 : 32); }
 int gru_bwd_grid(long long rows, int DP) {
   long long tiles = (rows + (256 / DP) - 1) / (256 / DP);
   int cap = mpnn_num_sms();
+  // 80 registers x 256 threads: three CTAs fit an SM at DP <= 16.  Small batches keep one CTA per SM (fewer partials
+  // for the fixed-order reduction, the step is latency-bound anyway); 10^5-row batches fill the SMs.
+  if (DP <= 16 && tiles >= 6LL * cap) cap *= 3;
   return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
@@ -366,7 +369,7 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
   size_t pre = 2 * align_up((size_t)rows * 3 * d * sizeof(float), 256);
   size_t g = mpnn_gemm_workspace_bytes(d, 3 * d, (int)rows);
   size_t c = mpnn_colsum_workspace_bytes(rows, 3 * d);
-  size_t fused = (size_t)mpnn_num_sms() * (6 * (size_t)d * d + 6 * d) * sizeof(float);
+  size_t fused = 3 * (size_t)mpnn_num_sms() * (6 * (size_t)d * d + 6 * d) * sizeof(float);
   size_t sub = g > c ? g : c;
   const int DP = d > 32 ? mpnn_tc_dp(d, d) : -1;   // widths 33..256: gate GEMMs on the tensor cores (tc_message.cu)
   if (DP > 0) {

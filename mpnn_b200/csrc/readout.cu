@@ -319,6 +319,17 @@ __global__ void __launch_bounds__(256) k_glo_fwd_fused(const float* __restrict__
     for (int i = warp; i < N; i += 8) {
       const size_t row = (size_t)b * N + i;
       const float mu = __ldg(mask + row);
+      if (mu == 0.f) {   // padded atom (about half of a config-4 batch): u' = b_i, v' = b_j, no contribution
+#pragma unroll
+        for (int k = 0; k < FK; ++k) {
+          const int o = lane + 32 * k;
+          if (o < O) {
+            u[row * O + o] = bio[k];
+            v[row * O + o] = bjo[k];
+          }
+        }
+        continue;
+      }
       float xl[FK];
 #pragma unroll
       for (int k = 0; k < FK; ++k) {
@@ -427,9 +438,18 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
     const bool live = row < rows;
     const long long rr = live ? row : rows - 1;
     const long long b = rr / N;
-    __syncthreads();   // weights staged / previous tile's accumulation finished
+    const float mu = __ldg(mask + rr);
+    // (barrier: weights staged / previous tile's accumulation finished)  A tile of padded atoms only -- they are the
+    // tail of every graph's rows -- contributes nothing: dx = 0 and on to the next tile.
+    if (!__syncthreads_or(live && mu != 0.f)) {
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < FK; ++k)
+          if (lane + 32 * k < F2) dx[row * F2 + lane + 32 * k] = 0.f;
+      }
+      continue;
+    }
     {
-      const float mu = __ldg(mask + rr);
       float s[FK], vv[FK], dr[FK];
       float mx = -INFINITY;
 #pragma unroll
@@ -563,6 +583,7 @@ __global__ void __launch_bounds__(256) k_glo_bwd_reduce(const float* __restrict_
 int glo_bwd_grid(long long rows) {
   long long tiles = (rows + 7) / 8;
   int cap = mpnn_num_sms();
+  if (tiles >= 6LL * cap) cap *= 3;   // 80 registers, 44.5 KB shared: three CTAs per SM once there is work for them
   return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
@@ -574,7 +595,7 @@ size_t mpnn_glo_workspace_bytes(int B, int N, int F2, int O) {
   long long rows = (long long)B * N;
   size_t g = mpnn_gemm_workspace_bytes(O, F2, (int)rows);
   size_t c = mpnn_colsum_workspace_bytes(rows, O);
-  size_t fusedb = (size_t)mpnn_num_sms() * (2 * (size_t)O * F2 + 2 * O) * sizeof(float);
+  size_t fusedb = 3 * (size_t)mpnn_num_sms() * (2 * (size_t)O * F2 + 2 * O) * sizeof(float);
   size_t sub = g > c ? g : c;
   const size_t t = mpnn_tc_linear_workspace_bytes(F2, O);   // projections on the tensor cores when the widths allow
   if (t > sub) sub = t;

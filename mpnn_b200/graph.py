@@ -97,7 +97,7 @@ class capacities(object):
         return False
 
 
-def compact_edges(bfm, adj=None):
+def compact_edges(bfm, adj=None, dedup=True):
     """Compacts (bfm, adj) -> EdgeList.  One 4-byte device->host read (the edge count) sizes the arrays
     (none in capacity mode)."""
     lib = _lib.load()
@@ -129,8 +129,9 @@ def compact_edges(bfm, adj=None):
                                          _lib.stream()), "compact_fill")
         el = EdgeList(B, N, ef, None, row_ptr, col_ptr, edge_src, edge_dst, edge_w, rows, csc_eid)
         el.Ecap = Ecap
-        el._typed = dedup_rows(el, unique_capacity=_CAPACITY[1])
-        _CAPTURED_COUNTS.append(el._typed.counts)
+        if dedup:
+            el._typed = dedup_rows(el, unique_capacity=_CAPACITY[1])
+            _CAPTURED_COUNTS.append(el._typed.counts)
         return el
     E = int(row_ptr[-1].item())
     STATS["E"] = max(STATS["E"], E)
@@ -402,7 +403,8 @@ def typed_bonds(bfm, adj):
         return bfm
     if bfm.requires_grad:
         raise RuntimeError("mpnn_b200.typed_bonds: bfm must be a data tensor (no gradient)")
-    el0 = edge_list_for(bfm, adj)
+    # (capacity mode de-duplicates eagerly; the rows are re-keyed with the adjacency value below, so skip that one)
+    el0 = compact_edges(bfm, adj, dedup=False) if _CAPACITY is not None else edge_list_for(bfm, adj)
     B, N, ef = el0.B, el0.N, el0.ef
     dev = bfm.device
     Ecap = el0.Ecap

@@ -122,7 +122,10 @@ def test_masked_bn_in_row_space(dev, kind, weighted):
 
 def _encoded_model(dev, steps=3, d=8):
     from mpnn_b200.callers import MessagePassingModel, kaiming_init
-    torch.manual_seed(317)
+    # seed 1: a well-conditioned draw.  With kaiming-initialised 50-layer trunks of width 16 some draws (317 is one)
+    # amplify so much that O(100) gradient entries are round-off in BOTH fp32 paths (tools/diag_typed_bonds.py
+    # prints row-space / dense / fp64-oracle errors for several seeds: the row-space path is the closer one on average)
+    torch.manual_seed(1)
     ae = nn.Sequential(nn.Linear(30, 15, bias=False), nn.Tanh(), nn.Linear(15, d))
     be = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
     mod = MessagePassingModel("normed_encoded", d, 2, d, 1, 16, message_steps=steps, atom_encoder=ae, bond_encoder=be)
@@ -172,9 +175,7 @@ def test_encoded_model_row_space_equals_dense(dev, weighted, monkeypatch):
         r = sd[k].grad
         e1 = float((g1[k].cpu().double() - r).abs().max())
         e0 = float((g0[k].cpu().double() - r).abs().max())
-        # floor: 1e-5 of the stack's largest gradient (7.6e6 here -- the kaiming-initialised 50-layer trunk amplifies;
-        # entries of O(100) are round-off dominated in BOTH fp32 paths: the dense one is 12 % off the oracle there)
-        assert e1 <= max(TOL_GRAD * float(r.abs().max()) + 1e-5 * gscale, 2.0 * e0), (k, e1, e0, float(r.abs().max()))
+        assert e1 <= max(TOL_GRAD * float(r.abs().max()) + 1e-6 * gscale, 2.0 * e0), (k, e1, e0, float(r.abs().max()))
 
 
 def test_reference_model_file_usage(dev):
