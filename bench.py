@@ -33,10 +33,12 @@ METRIC = "graphs/sec (fwd+bwd train step)"
 
 WORKLOADS = {
     # name: (synthetic config, caller variant, d, ef, T, readout width, targets)
-    "qm9": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256,
-                desc="normed_basic_model + MaskBatchNorm, QM9-shaped (n<=29), B=256/GPU, d=16, ef=7, P=49, T=3"),
-    "lipo": dict(variant="lipo", d=19, ef=7, T=6, out=38, targets=1, B=32,
-                 desc="lipo_basic_model (HEAD form), Lipophilicity-shaped, B=32, d=19, ef=7, P=49, T=6"),
+    "qm9": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256, head="bn_linear",
+                desc="normed_basic_model + MaskBatchNorm + BatchNorm1d(64) + Linear(64,12), QM9-shaped (n<=29), "
+                     "B=256/GPU, d=16, ef=7, P=49, T=3"),
+    "lipo": dict(variant="lipo", d=19, ef=7, T=6, out=38, targets=1, B=32, head="bn_halving",
+                 desc="lipo_basic_model (HEAD form) + BatchNorm1d(38) + halving dense head, Lipophilicity-shaped, B=32, "
+                      "d=19, ef=7, P=49, T=6"),
     "autoenc": dict(variant="autoencoder", d=64, ef=8, T=3, out=128, targets=128, B=512,
                     desc="basic_graph_autoencoder.encode, ZINC-shaped, B=512/GPU, d=64, ef=8, P=64, T=3"),
     # configs[2]: att_model (AttEdgeNetwork + AdjMsgAgg + MaskBatchNorm + Set2Vec, 100 steps), 128 graphs per GPU
@@ -119,7 +121,20 @@ def build_model(w, dev):
         kw["bond_encoder"] = torch.nn.Sequential(torch.nn.Linear(8, 4, bias=False), torch.nn.Tanh(), torch.nn.Linear(4, 2))
     body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"], **kw)
     body.apply(kaiming_init)
-    head = torch.nn.Linear(w["out"], w["targets"])
+    # prediction heads of the reference drivers (stock torch modules): test_graph_norm.py:86-90
+    # BatchNorm1d(out) + Linear(out, targets); test_lipo.py:103-129 BatchNorm1d(out) + halving dense stack
+    if w.get("head") == "bn_linear":
+        head = torch.nn.Sequential(torch.nn.BatchNorm1d(w["out"]), torch.nn.Linear(w["out"], w["targets"]))
+    elif w.get("head") == "bn_halving":
+        layers, den = [torch.nn.BatchNorm1d(w["out"])], w["out"]
+        while den > 10:
+            nd = int(np.ceil(den / 2))
+            layers += [torch.nn.Linear(den, nd), torch.nn.ReLU()]
+            den = nd
+        layers.append(torch.nn.Linear(den, w["targets"]))
+        head = torch.nn.Sequential(*layers)
+    else:
+        head = torch.nn.Linear(w["out"], w["targets"])
     return body.to(dev), head.to(dev)
 
 
@@ -164,11 +179,21 @@ def run_ours(args):
     # L2 (126 MB) is flushed between timed iterations by writing a 256 MB buffer
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    # the driver's head + criterion (BatchNorm1d -> Linear -> MSELoss) as one launch each way (mpnn_b200/heads.py wraps
+    # the same stock modules; --stock-head keeps them as 14 torch kernels)
+    fused_head = None
+    if w.get("head") == "bn_linear" and not args.stock_head:
+        from mpnn_b200.heads import BNLinearMSE
+        fused_head = BNLinearMSE(head[0], head[1])
+
     def step(b):
         graph.clear_cache()
         opt.zero_grad(set_to_none=True)
-        out = head(body(b["afm"], b["bfm"], b["adj"], b["mask"]))
-        loss = torch.nn.functional.mse_loss(out, b["labels"])
+        feats = body(b["afm"], b["bfm"], b["adj"], b["mask"])
+        if fused_head is not None:
+            loss = fused_head(feats, b["labels"])
+        else:
+            loss = torch.nn.functional.mse_loss(head(feats), b["labels"])
         loss.backward()
         allreduce()
         opt.step()
@@ -525,6 +550,7 @@ def main():
     ap.add_argument("--config", default="qm9", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-head", action="store_true", help="keep the head + loss as stock torch modules")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")
     ap.add_argument("--hidden", type=int, default=0, help="feature width d (autoenc sweep of BASELINE configs[4])")

@@ -278,6 +278,21 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
                      float* dbcat, float* dWq, float* dwe, void* workspace, size_t workspace_bytes,
                      mpnn_stream_t stream);
 
+/* ---- 8f rank 4: prediction head + loss of the drivers (test_graph_norm.py:86-90 nn.BatchNorm1d(out) ->
+ * nn.Linear(out, targets) + nn.MSELoss), one single-CTA launch each way for problems that fit a CTA's shared memory
+ * (mpnn_head_supported).  gamma/beta may be NULL (no affine); running_* / num_batches_tracked may be NULL (training).
+ * fwd writes y [B,T], loss [1], stats [2C]; bwd takes the loss gradient as a DEVICE scalar and writes (not
+ * accumulates) dx [B,C], dgamma/dbeta [C] (may be NULL), dW [T,C], db [T]. */
+int mpnn_head_supported(int B, int C, int T);
+int mpnn_head_bn_linear_mse_fwd(const float* x, const float* target, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, long long* num_batches_tracked,
+                                const float* W, const float* b, int B, int C, int T, int training, float momentum,
+                                float eps, float* y, float* loss, float* stats, mpnn_stream_t stream);
+int mpnn_head_bn_linear_mse_bwd(const float* x, const float* target, const float* gamma, const float* beta,
+                                const float* W, const float* y, const float* stats, const float* gloss, int B, int C,
+                                int T, int training, float* dx, float* dgamma, float* dbeta, float* dW, float* db,
+                                mpnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,9 @@ SIGNATURES = {
     "mpnn_glo_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "mpnn_glo_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_glo_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_head_supported": (_I, [_I, _I, _I]),
+    "mpnn_head_bn_linear_mse_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
+    "mpnn_head_bn_linear_mse_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "mpnn_bilinear_fwd": (_I, [_P, _P, _P, _L, _P, _L, _I, _P, _P]),
     "mpnn_bilinear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _L, _I, _P, _P, _L, _P]),
     "mpnn_softmax_mul_fwd": (_I, [_P, _P, _L, _I, _P, _P, _P]),
