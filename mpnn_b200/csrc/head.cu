@@ -30,7 +30,7 @@ __host__ __device__ inline size_t head_fwd_floats(int B, int C, int T) {
 }
 __host__ __device__ inline size_t head_bwd_floats(int B, int C, int T) {
   const size_t RP = head_rows_per(B);
-  return 2 * RP * (C + 1) + RP * (T + 1) + (size_t)T * (C + 1) + ((size_t)T * C + T) + 6 * (size_t)C + HT;
+  return 2 * RP * (C + 1) + RP * (T + 1) + (size_t)T * (C + 1) + ((size_t)T * C + T) + 8 * (size_t)C + HT;
 }
 
 // global rows of a contiguous [nr, cols] matrix -> shared [nr][ld] through f(value, col).  All loads of a thread are
@@ -125,16 +125,25 @@ __global__ void __launch_bounds__(HT) k_head_fwd(HeadArgs a, float* __restrict__
   float* lp = bs + T;                   // [8]       partial loss             (read by rank 0)
   float* scratch = lp + 8;              // [HT]
   const int tid = threadIdx.x;
+  // every global operand is staged first (independent loads, one latency); the folding of the affine parameters into
+  // the Linear then runs out of shared memory: W' = W gamma, b' = b + W beta
   stage_rows(a.x + (size_t)r0 * C, nr, C, xs, LD, [](float v, int) { return v; });
-  {
-    const float* gamma = a.gamma;
-    stage_rows(a.W, T, C, Ws, LD, [gamma](float v, int c) { return gamma ? v * __ldg(gamma + c) : v; });
+  stage_rows(a.W, T, C, Ws, LD, [](float v, int) { return v; });
+  for (int c = tid; c < C; c += HT) {
+    p0[c] = a.gamma ? __ldg(a.gamma + c) : 1.f;
+    p1[c] = a.beta ? __ldg(a.beta + c) : 0.f;
   }
+  for (int o = tid; o < T; o += HT) bs[o] = a.b ? __ldg(a.b + o) : 0.f;
+  __syncthreads();
   for (int o = tid; o < T; o += HT) {
-    float s = a.b ? a.b[o] : 0.f;
-    if (a.beta)
-      for (int c = 0; c < C; ++c) s = fmaf(a.beta[c], a.W[o * C + c], s);
+    float s = bs[o];
+    for (int c = 0; c < C; ++c) s = fmaf(p1[c], Ws[o * LD + c], s);
     bs[o] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < T * C; i += HT) {
+    const int o = i / C, c = i - o * C;
+    Ws[o * LD + c] *= p0[c];
   }
   __syncthreads();
   if (a.training) {
@@ -237,11 +246,14 @@ __global__ void __launch_bounds__(HT) k_head_bwd(HeadBwd a) {
   float* mean = ps + 2 * C;                // [C]
   float* istd = mean + C;
   float* s12 = istd + C;                   // [2C]      cluster totals of ps
-  float* scratch = s12 + 2 * C;            // [HT]
+  float* gb = s12 + 2 * C;                 // [2C]      gamma, beta
+  float* scratch = gb + 2 * C;             // [HT]
   const int tid = threadIdx.x;
   for (int c = tid; c < C; c += HT) {
-    mean[c] = a.stats[c];
-    istd[c] = a.stats[C + c];
+    mean[c] = __ldg(a.stats + c);
+    istd[c] = __ldg(a.stats + C + c);
+    gb[c] = a.gamma ? __ldg(a.gamma + c) : 1.f;
+    gb[C + c] = a.beta ? __ldg(a.beta + c) : 0.f;
   }
   const float scale = 2.f * __ldg(a.gloss) / ((float)B * T);
   stage_rows(a.W, T, C, Ws, LD, [](float v, int) { return v; });
@@ -312,16 +324,16 @@ __global__ void __launch_bounds__(HT) k_head_bwd(HeadBwd a) {
       float dbo = 0.f;
       if (a.beta) {
         for (int k = 0; k < nc; ++k) dbo += cluster.map_shared_rank(pW, k)[T * C + o];
-        dbo *= a.beta[c];
+        dbo *= gb[C + c];
       }
-      a.dW[e] = fmaf(a.gamma ? a.gamma[c] : 1.f, s, dbo);
+      a.dW[e] = fmaf(gb[c], s, dbo);
     } else {
       a.db[e - T * C] = s;
     }
   }
   for (int i = tid; i < nr * C; i += HT) {
     const int r = i / C, c = i - r * C;
-    const float gm = a.gamma ? a.gamma[c] : 1.f;
+    const float gm = gb[c];
     float g = dz[r * LD + c] * gm;
     if (a.training) g -= gm * (s12[c] + xh[r * LD + c] * s12[C + c]) * (1.f / B);
     a.dx[(size_t)(r0 + r) * C + c] = g * istd[c];
