@@ -240,6 +240,15 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
                  const float* gates, const float* dh_out, long long rows, int d, float* dm, float* dh, float* dW_ih,
                  float* dW_hh, float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes,
                  mpnn_stream_t stream);
+/* Shared-parameter form (one GRUCell applied at every step, basic_model.py:50-58): each step's backward leaves its
+ * per-CTA weight-gradient partials in a caller-provided slab (mpnn_gru_bwd_partial_bytes each; 0 = width not served),
+ * ONE reduction over all slabs gives the four parameter gradients of the whole T-step loop. */
+size_t mpnn_gru_bwd_partial_bytes(long long rows, int d);
+int mpnn_gru_bwd_data(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                      const float* gates, const float* dh_out, long long rows, int d, float* dm, float* dh,
+                      float* partial, mpnn_stream_t stream);
+int mpnn_gru_bwd_params(const float* partial, int slabs, long long rows, int d, float* dW_ih, float* dW_hh,
+                        float* db_ih, float* db_hh, mpnn_stream_t stream);
 
 /* ---- a10/a11: masked batch norms (models/mask_batch_norm.py:9-15, 20-38); stats [2C+1] saved ------------
  * Workspace contract: zero-filled ONCE by the caller; every call leaves it reusable (its completion counter is

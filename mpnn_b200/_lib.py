@@ -81,6 +81,9 @@ SIGNATURES = {
     "mpnn_gru_workspace_bytes": (_Z, [_L, _I]),
     "mpnn_gru_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _Z, _P]),
     "mpnn_gru_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_gru_bwd_partial_bytes": (_Z, [_L, _I]),
+    "mpnn_gru_bwd_data": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),
+    "mpnn_gru_bwd_params": (_I, [_P, _I, _L, _I, _P, _P, _P, _P, _P]),
     "mpnn_bn_workspace_bytes": (_Z, [_L, _I]),
     "mpnn_mask_bn_fwd": (_I, [_P, _P, _L, _I, _F, _P, _P, _P, _Z, _P]),
     "mpnn_mask_bn_bwd": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _Z, _P]),

@@ -430,6 +430,43 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
   return MPNN_OK;
 }
 
+// ---- shared-parameter form: the reference applies ONE GRUCell at every message-passing step (basic_model.py:50-58),
+// so its four parameter gradients are sums over the T steps.  Each step's backward leaves its per-CTA partials in a
+// caller-provided slab; one reduction over all slabs replaces T reductions + 4 (T-1) accumulate kernels of autograd.
+// widths <= 32 (the fused CUDA-core kernels); returns 0 bytes otherwise.
+size_t mpnn_gru_bwd_partial_bytes(long long rows, int d) {
+  if (d > 32 || d <= 0 || rows <= 0) return 0;
+  const int DP = fused_dp(d);
+  return (size_t)gru_bwd_grid(rows, DP) * (6 * (size_t)d * d + 6 * d) * sizeof(float);
+}
+
+int mpnn_gru_bwd_data(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
+                      const float* gates, const float* dh_out, long long rows, int d, float* dm, float* dh,
+                      float* partial, cudaStream_t stream) {
+  MPNN_REQUIRE(rows > 0 && d > 0 && d <= 32 && rows < (1ll << 31), MPNN_ERR_ARG, "gru_bwd_data: bad dims");
+  const int DP = fused_dp(d);
+  const int grid = gru_bwd_grid(rows, DP);
+  const size_t smem = gru_bwd_smem(d, DP);
+  switch (DP) {
+    case 8: k_gru_bwd_fused<8><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
+    case 16: k_gru_bwd_fused<16><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
+    default: k_gru_bwd_fused<32><<<grid, 256, smem, stream>>>(m, h, mask, W_ih, W_hh, gates, dh_out, rows, d, dm, dh, partial); break;
+  }
+  MPNN_CHECK_LAUNCH("k_gru_bwd_fused");
+  return MPNN_OK;
+}
+
+// partial: `slabs` consecutive slabs of mpnn_gru_bwd_partial_bytes(rows, d) each (one per step, any order)
+int mpnn_gru_bwd_params(const float* partial, int slabs, long long rows, int d, float* dW_ih, float* dW_hh,
+                        float* db_ih, float* db_hh, cudaStream_t stream) {
+  MPNN_REQUIRE(rows > 0 && d > 0 && d <= 32 && slabs > 0, MPNN_ERR_ARG, "gru_bwd_params: bad dims");
+  const int grid = gru_bwd_grid(rows, fused_dp(d));
+  k_gru_bwd_reduce<<<ceil_div(6 * d * d + 6 * d, 32), 256, 0, stream>>>(partial, slabs * grid, d, dW_ih, dW_hh, db_ih,
+                                                                        db_hh);
+  MPNN_CHECK_LAUNCH("k_gru_bwd_reduce");
+  return MPNN_OK;
+}
+
 int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
                  const float* gates, const float* dh_out, long long rows, int d, float* dm, float* dh, float* dW_ih,
                  float* dW_hh, float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes,

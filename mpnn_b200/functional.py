@@ -295,11 +295,57 @@ class EdgeMessageFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # GRU update
 # ------------------------------------------------------------------------------------------------
-class GRUFn(torch.autograd.Function):
-    """reference gru_update.py:26-35,66-68 on flat [rows, d] tensors; mask [rows]."""
+class SharedGradSession(object):
+    """One forward pass through a GRU cell that is applied at every message-passing step (basic_model.py:50-58).  The
+    steps' backward calls leave their per-CTA weight-gradient partials in one slab (`GRUFn.backward`); the hub node
+    (`GRUParamHubFn`), which autograd runs after all of them, reduces the slab ONCE.  Replaces T reductions and the
+    4 (T-1) accumulate kernels autograd would launch for the shared parameters."""
+
+    def __init__(self, key):
+        self.key, self.done, self.uses, self.filled = key, False, 0, 0
+        self.slab, self.meta, self.handles = None, None, None
+
+
+class GRUParamHubFn(torch.autograd.Function):
+    """identity on (W_ih, W_hh, b_ih, b_hh); its backward turns the session's slab into the parameter gradients"""
 
     @staticmethod
-    def forward(ctx, m, h, mask, W_ih, W_hh, b_ih, b_hh):
+    def forward(ctx, session, W_ih, W_hh, b_ih, b_hh):
+        ctx.session = session
+        ctx.set_materialize_grads(False)
+        return W_ih.detach(), W_hh.detach(), b_ih.detach(), b_hh.detach()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_ih, g_hh, gb_ih, gb_hh):
+        s = ctx.session
+        s.done = True
+        direct = [g_ih, g_hh, gb_ih, gb_hh]    # from steps that could not use the slab (returned real gradients)
+        if not s.filled:
+            return (None,) + tuple(direct)
+        lib = _lib.load()
+        rows, d, dev = s.meta
+        dW_ih = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
+        dW_hh = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
+        db_ih = torch.empty(3 * d, dtype=torch.float32, device=dev)
+        db_hh = torch.empty(3 * d, dtype=torch.float32, device=dev)
+        check(lib.mpnn_gru_bwd_params(ptr(s.slab), s.filled, rows, d, ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh),
+                                      stream()), "gru_bwd_params")
+        s.filled = 0                            # a second backward through a retained graph refills the slab
+        out = [dW_ih, dW_hh, db_ih, db_hh]
+        out = [o if g is None else o + g for o, g in zip(out, direct)]
+        return (None,) + tuple(out)
+
+
+class GRUFn(torch.autograd.Function):
+    """reference gru_update.py:26-35,66-68 on flat [rows, d] tensors; mask [rows].  `session`: see SharedGradSession
+    (None = parameter gradients are returned by every call)."""
+
+    @staticmethod
+    def forward(ctx, m, h, mask, W_ih, W_hh, b_ih, b_hh, session=None):
+        ctx.session = session
+        if session is not None:
+            session.uses += 1
         lib = _lib.load()
         _need_cuda(m, h, mask, W_ih)
         m, h, mask = f32c(m), f32c(h), f32c(mask)
@@ -322,6 +368,18 @@ class GRUFn(torch.autograd.Function):
         dout = f32c(dout)
         dev = h.device
         dm, dh = torch.empty_like(m), torch.empty_like(h)
+        s = ctx.session
+        if s is not None:
+            pb = lib.mpnn_gru_bwd_partial_bytes(rows, d)
+            if pb and s.slab is None:
+                s.slab = torch.empty(max(s.uses, 1) * pb, dtype=torch.uint8, device=dev)
+                s.meta = (rows, d, dev)
+            if pb and s.meta == (rows, d, dev) and (s.filled + 1) * pb <= s.slab.numel():
+                check(lib.mpnn_gru_bwd_data(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(gates), ptr(dout), rows,
+                                            d, ptr(dm), ptr(dh), s.slab.data_ptr() + s.filled * pb, stream()),
+                      "gru_bwd_data")
+                s.filled += 1
+                return dm, dh, None, None, None, None, None, None
         dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
         db_ih = torch.empty(3 * d, dtype=torch.float32, device=dev)
         db_hh = torch.empty(3 * d, dtype=torch.float32, device=dev)
@@ -329,7 +387,7 @@ class GRUFn(torch.autograd.Function):
         check(lib.mpnn_gru_bwd(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(gates), ptr(dout), rows, d, ptr(dm),
                                ptr(dh), ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh), ptr(ws), ws.numel(), stream()),
               "gru_bwd")
-        return dm, dh, None, dW_ih, dW_hh, db_ih, db_hh
+        return dm, dh, None, dW_ih, dW_hh, db_ih, db_hh, None
 
 
 # ------------------------------------------------------------------------------------------------

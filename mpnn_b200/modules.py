@@ -11,7 +11,7 @@ from torch import nn
 
 from . import graph
 from .functional import (BilinearEdgeFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
-                         GraphLevelOutputFn, GRUFn, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
+                         GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, table_dp, tc_dp, typed_dp)
 from . import _lib
 from .functional import _note_forward_side_work, _side_stream
@@ -19,6 +19,7 @@ import os
 import weakref
 
 SIBLING_PREFETCH = os.environ.get("MPNN_B200_SIBLING_PREFETCH", "1") != "0"
+SHARED_GRAD_HUB = os.environ.get("MPNN_B200_SHARED_GRAD_HUB", "1") != "0"
 
 _N_TIED = 50  # edge_network.py:20
 
@@ -548,9 +549,26 @@ class GRUCell(nn.Module):
         nn.init.constant_(self.bias_ih, 0.0)
         nn.init.constant_(self.bias_hh, 0.0)
 
+    _session = None
+
+    def _shared_parameters(self):
+        """(W_ih, W_hh, b_ih, b_hh, session): while the same parameter values are applied again and again before a
+        backward pass (the T message-passing steps), every call goes through ONE hub node, so the steps' weight-gradient
+        partials are reduced once instead of T times + 4 (T-1) autograd accumulations (functional.SharedGradSession)."""
+        ps = (self.weight_ih, self.weight_hh, self.bias_ih, self.bias_hh)
+        if not (SHARED_GRAD_HUB and torch.is_grad_enabled() and all(p.requires_grad for p in ps)):
+            return ps + (None,)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        s = self._session
+        if s is None or s.done or s.key != key:
+            s = SharedGradSession(key)
+            s.handles = GRUParamHubFn.apply(s, *ps)
+            self._session = s
+        return tuple(s.handles) + (s,)
+
     def forward(self, messages, node_states, mask):
-        return GRUFn.apply(messages, node_states, mask.reshape(-1), self.weight_ih, self.weight_hh, self.bias_ih,
-                           self.bias_hh)
+        W_ih, W_hh, b_ih, b_hh, session = self._shared_parameters()
+        return GRUFn.apply(messages, node_states, mask.reshape(-1), W_ih, W_hh, b_ih, b_hh, session)
 
 
 class GRUUpdate(nn.Module):
