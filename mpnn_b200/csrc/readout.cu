@@ -583,7 +583,9 @@ __global__ void __launch_bounds__(256) k_glo_bwd_reduce(const float* __restrict_
 int glo_bwd_grid(long long rows) {
   long long tiles = (rows + 7) / 8;
   int cap = mpnn_num_sms();
-  if (tiles >= 6LL * cap) cap *= 3;   // 80 registers, 44.5 KB shared: three CTAs per SM once there is work for them
+  // 80 registers, 44.5 KB shared: three CTAs per SM once there is work for them (below that the 3x larger set of
+  // per-CTA partials costs the reduction what the main kernel gains: measured at 928 tiles)
+  if (tiles >= 16LL * cap) cap *= 3;
   return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
