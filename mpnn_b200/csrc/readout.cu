@@ -316,9 +316,22 @@ __global__ void __launch_bounds__(256) k_glo_fwd_fused(const float* __restrict__
   __syncthreads();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     float acc[FK] = {0.f, 0.f};
+    // a warp's rows are loaded one iteration ahead (N / 8 ~ 4 dependent load latencies per graph otherwise)
+    float n_mu = 0.f, n_x[FK];
+    auto prefetch = [&](int i) {
+      const size_t row = (size_t)b * N + min(i, N - 1);
+      n_mu = __ldg(mask + row);
+#pragma unroll
+      for (int k = 0; k < FK; ++k) n_x[k] = __ldg(x + row * F2 + min(lane + 32 * k, F2 - 1));
+    };
+    prefetch(warp);
     for (int i = warp; i < N; i += 8) {
       const size_t row = (size_t)b * N + i;
-      const float mu = __ldg(mask + row);
+      const float mu = n_mu;
+      float xin[FK];
+#pragma unroll
+      for (int k = 0; k < FK; ++k) xin[k] = n_x[k];
+      if (i + 8 < N) prefetch(i + 8);
       if (mu == 0.f) {   // padded atom (about half of a config-4 batch): u' = b_i, v' = b_j, no contribution
 #pragma unroll
         for (int k = 0; k < FK; ++k) {
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(256) k_glo_fwd_fused(const float* __restrict__
 #pragma unroll
       for (int k = 0; k < FK; ++k) {
         const int l = lane + 32 * k;
-        xl[k] = __ldg(x + row * F2 + min(l, F2 - 1)) * mu;
+        xl[k] = xin[k] * mu;
         if (l >= F2) xl[k] = 0.f;
       }
       float ua[FK] = {0.f, 0.f}, va[FK] = {0.f, 0.f};
@@ -433,12 +446,37 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
   const int nkf = (F2 + 31) / 32;
   const long long rows = (long long)B * N;
   const long long ntiles = (rows + 7) / 8;
+  // The inputs of a row (mask, u, v, the graph's dout, x) are loaded ONE TILE AHEAD: with 8 warps per SM nothing else
+  // hides the ~1 us of dependent global-load latency a tile would otherwise start with (6 tiles per CTA at B = 256).
+  float n_mu = 0.f, n_s[FK], n_vv[FK], n_dr[FK], n_x[FK];
+  auto prefetch = [&](long long tile) {
+    const long long row = tile * 8 + warp;
+    const long long rr = row < rows ? row : rows - 1;
+    const long long b = rr / N;
+    n_mu = __ldg(mask + rr);
+#pragma unroll
+    for (int k = 0; k < FK; ++k) {
+      const int o = min(lane + 32 * k, O - 1);
+      n_s[k] = __ldg(u + rr * O + o);
+      n_vv[k] = __ldg(v + rr * O + o);
+      n_dr[k] = __ldg(dout + b * O + o);
+      n_x[k] = __ldg(x + rr * F2 + min(lane + 32 * k, F2 - 1));
+    }
+  };
+  if (blockIdx.x < ntiles) prefetch(blockIdx.x);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row = tile * 8 + warp;
     const bool live = row < rows;
-    const long long rr = live ? row : rows - 1;
-    const long long b = rr / N;
-    const float mu = __ldg(mask + rr);
+    const float mu = n_mu;
+    float s[FK], vv[FK], dr[FK], xin[FK];
+#pragma unroll
+    for (int k = 0; k < FK; ++k) {
+      s[k] = n_s[k];
+      vv[k] = n_vv[k];
+      dr[k] = n_dr[k];
+      xin[k] = n_x[k];
+    }
+    if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);
     // (barrier: weights staged / previous tile's accumulation finished)  A tile of padded atoms only -- they are the
     // tail of every graph's rows -- contributes nothing: dx = 0 and on to the next tile.
     if (!__syncthreads_or(live && mu != 0.f)) {
@@ -450,16 +488,10 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
       continue;
     }
     {
-      float s[FK], vv[FK], dr[FK];
       float mx = -INFINITY;
 #pragma unroll
-      for (int k = 0; k < FK; ++k) {
-        const int o = min(lane + 32 * k, O - 1);
-        s[k] = __ldg(u + rr * O + o);
-        vv[k] = __ldg(v + rr * O + o);
-        dr[k] = __ldg(dout + b * O + o);
+      for (int k = 0; k < FK; ++k)
         if (lane + 32 * k < O) mx = fmaxf(mx, s[k]);
-      }
       mx = warp_max(mx);
       float den = 0.f;
 #pragma unroll
@@ -488,7 +520,7 @@ __global__ void __launch_bounds__(256) k_glo_bwd_fused(const float* __restrict__
         du_s[warp][o] = dup * mu;       // d u_raw (u' = mu * u_raw + b)
         dv_s[warp][o] = dvp * mu;
         const int l = lane + 32 * k;
-        float xv = __ldg(x + rr * F2 + min(l, F2 - 1));
+        float xv = xin[k];
         if (!live || l >= F2) xv = 0.f;
         x_s[warp][l] = xv;
       }
@@ -586,6 +618,7 @@ int glo_bwd_grid(long long rows) {
   // 80 registers, 44.5 KB shared: three CTAs per SM once there is work for them (below that the 3x larger set of
   // per-CTA partials costs the reduction what the main kernel gains: measured at 928 tiles)
   if (tiles >= 16LL * cap) cap *= 3;
+  else if (tiles >= 4LL * cap) cap *= 2;   // two CTAs per SM (122 registers): twice the warps to hide the LDS chains
   return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
