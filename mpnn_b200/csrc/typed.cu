@@ -879,26 +879,23 @@ int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, co
   const int grid = msg_grid(n_src, DP);
   const int ch = table_chunk(edge_capacity);
   const int chunks = ceil_div(edge_capacity > 0 ? edge_capacity : 1, ch);
+  // dH == NULL / dT == NULL skip that half: the sender-state gradient feeds the main backward chain, the table gradient
+  // only the edge network's parameter gradients (the caller may enqueue the two halves on different streams)
+#define MPNN_TMSG_BWD(DPV)                                                                                        \
+  do {                                                                                                            \
+    if (dH) k_tmsg_bwd_src<DPV><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);        \
+    if (dT) {                                                                                                     \
+      k_tmsg_bwd_table<DPV><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);        \
+      k_tmsg_bwd_table_reduce<DPV><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);   \
+      if (S) k_tmsg_bwd_table_zero<DPV><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);                \
+    }                                                                                                             \
+  } while (0)
   switch (DP) {
-    case 8:
-      k_tmsg_bwd_src<8><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
-      k_tmsg_bwd_table<8><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);
-      k_tmsg_bwd_table_reduce<8><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);
-      if (S) k_tmsg_bwd_table_zero<8><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
-      break;
-    case 16:
-      k_tmsg_bwd_src<16><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
-      k_tmsg_bwd_table<16><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);
-      k_tmsg_bwd_table_reduce<16><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);
-      if (S) k_tmsg_bwd_table_zero<16><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
-      break;
-    default:
-      k_tmsg_bwd_src<32><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);
-      k_tmsg_bwd_table<32><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);
-      k_tmsg_bwd_table_reduce<32><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);
-      if (S) k_tmsg_bwd_table_zero<32><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);
-      break;
+    case 8: MPNN_TMSG_BWD(8); break;
+    case 16: MPNN_TMSG_BWD(16); break;
+    default: MPNN_TMSG_BWD(32); break;
   }
+#undef MPNN_TMSG_BWD
   MPNN_CHECK_LAUNCH("k_tmsg_bwd");
   return MPNN_OK;
 }

@@ -22,11 +22,23 @@ _SIDE_PENDING = {}
 SIDE_STREAM_ENABLED = os.environ.get("MPNN_B200_SIDE_STREAM", "1") != "0"
 
 
-def _side_stream(device):
-    k = device.index if device.index is not None else torch.cuda.current_device()
+def _side_stream(device, lane=0):
+    """lane 0: edge-network work (forward table prefetch, backward); lane 1: the table half of the message backward"""
+    d = device.index if device.index is not None else torch.cuda.current_device()
+    k = d if lane == 0 else (d, lane)
     if k not in _SIDE_STREAMS:
         _SIDE_STREAMS[k] = torch.cuda.Stream(device=device)
     return k, _SIDE_STREAMS[k]
+
+
+def _dev_of(k):
+    return k[0] if isinstance(k, tuple) else k
+
+
+# gradient tensors produced on a side stream: data_ptr -> event recorded behind their last kernel.  A consumer that
+# also runs on a side stream waits for THAT event instead of forking from the current position of the main stream
+# (autograd runs the edge networks' backward nodes last, long after their inputs were ready).
+_READY_EVENTS = {}
 
 
 _FWD_SIDE = set()
@@ -51,30 +63,37 @@ def join_side_streams():
 def _join_side_streams():
     for k in list(_SIDE_PENDING):
         ev = _SIDE_PENDING.pop(k)
-        torch.cuda.current_stream(k).wait_event(ev)
+        torch.cuda.current_stream(_dev_of(k)).wait_event(ev)
+    _READY_EVENTS.clear()
 
 
 class _on_side_stream(object):
     """`with _on_side_stream(device, tensors_read): ...` runs the body's launches on the side stream, after
     everything enqueued so far on the current stream; the join is deferred to the end of the backward pass."""
 
-    def __init__(self, device, tensors):
+    def __init__(self, device, tensors, lane=0, after=None):
         self.device, self.tensors = device, [t for t in tensors if t is not None]
+        self.lane, self.after = lane, after
+        self.done = None
 
     def __enter__(self):
-        self.key, self.side = _side_stream(self.device)
-        main = torch.cuda.current_stream(self.device)
-        ev = torch.cuda.Event()
-        ev.record(main)
-        self.side.wait_event(ev)
+        self.key, self.side = _side_stream(self.device, self.lane)
+        if self.after is not None:       # inputs were produced on another side stream: depend on exactly that
+            self.side.wait_event(self.after)
+        else:
+            main = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
         return self
 
     def __exit__(self, *exc):
-        first = self.key not in _SIDE_PENDING
+        first = not _SIDE_PENDING
         ev = torch.cuda.Event()
         ev.record(self.side)
+        self.done = ev
         _SIDE_PENDING[self.key] = ev
         self.ctx.__exit__(*exc)
         for t in self.tensors:
@@ -732,6 +751,10 @@ def table_dp(nf, mf):
     return d if d >= 0 else tc_dp(nf, mf)
 
 
+_ENET_LANES = (0, 2, 3)
+_ENET_LANE = 0
+
+
 class EdgeNetTableFn(torch.autograd.Function):
     """Fused growth layers + 50 tied layers + last Linear on the distinct rows (P <= 64):
     urows [R, ef] -> table T[u][l][k], tableT T[u][k][l]  ([R, DP, DP] each; reference edge_network.py:14-21,37)."""
@@ -778,7 +801,16 @@ class EdgeNetTableFn(torch.autograd.Function):
         # them before the join); if it has to accumulate into an existing .grad the work stays on the main stream
         side = (SIDE_STREAM_ENABLED and d_rows is None
                 and all(getattr(t, "grad", None) is None for t in [w_tied, W_last] + gw))
-        with (_on_side_stream(dev, [dT, urows, w_tied, W_last, saved] + gw) if side else _inline()):
+        # the edge networks of a model are independent of each other: their backward chains (57 CTAs each) go to
+        # different lanes round-robin, so the last one does not queue behind the others
+        global _ENET_LANE
+        _ENET_LANE = (_ENET_LANE + 1) % len(_ENET_LANES)
+        lane = _ENET_LANES[_ENET_LANE]
+        ready = _READY_EVENTS.pop(dT.data_ptr(), None)
+        if not side and ready is not None:
+            torch.cuda.current_stream(dev).wait_event(ready)   # dT was produced on a side stream
+        with (_on_side_stream(dev, [dT, urows, w_tied, W_last, saved] + gw, lane=lane, after=ready) if side
+              else _inline()):
             ws = workspace(lib.mpnn_enet_workspace_bytes(R, ef, G, P), dev)
             check(lib.mpnn_enet_bwd(ptr(urows), R, ef, G, ptr_array(gw), ptr(w_tied), P, n_tied, ptr(W_last), nf, mf,
                                     ptr(saved), ptr(dT), ptr_array(d_gw), ptr_array(d_gb), ptr(d_w_tied),
@@ -815,15 +847,27 @@ class TableLayoutFn(torch.autograd.Function):
         return dflat, None, None
 
 
+class TableHolder(object):
+    """Rides on a table tensor produced by EdgeNetTableFn: how many message functions consume it in this forward pass.
+    With exactly one consumer its gradient dT goes straight from TypedMessageFn.backward into EdgeNetTableFn.backward
+    (no autograd accumulation in between), so the table half of the message backward can run on the side stream too."""
+
+    def __init__(self):
+        self.uses = 0
+
+
 class TypedMessageFn(torch.autograd.Function):
     """M[i] = sum_{e in E(i)} alpha_e T[uid_e]^T H[src_e]  (+ HEAD terms: zero-row matrix on all non-bonded pairs,
     + beta).  H [n_rows, nf]; table/tableT from EdgeNetTableFn / TableLayoutFn; alpha [E] or None (not
     differentiated: the adjacency value); head selects edge_network.py:50-51 over edge_network.py:52."""
 
     @staticmethod
-    def forward(ctx, H, table, tableT, beta, el, alpha, head, nf, mf):
+    def forward(ctx, H, table, tableT, beta, el, alpha, head, nf, mf, holder=None):
         lib = _lib.load()
         _need_cuda(H, table)
+        ctx.holder = holder
+        if holder is not None:
+            holder.uses += 1
         H, table, tableT = f32c(H), f32c(table), f32c(tableT)
         beta_c = f32c(beta) if beta is not None else None
         alpha_c = f32c(alpha) if alpha is not None else None
@@ -849,20 +893,42 @@ class TypedMessageFn(torch.autograd.Function):
         ti = el.typed()
         dev = H.device
         dM = f32c(dM)
-        dH = torch.empty_like(H)
-        dT = torch.empty_like(table)
-        ws = workspace(lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, nf, mf, el.B), dev)
-        check(lib.mpnn_tmsg_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src), ptr(el.edge_dst),
-                                ptr(ti.uid), ptr(ti.type_ptr), ptr(ti.type_eid), ptr(ti.counts), ptr(alpha), ptr(H),
-                                ptr(table), ptr(tableT), ptr(S), el.n_rows, H.shape[0], el.B, el.N, nf, mf, el.Ecap,
-                                ti.Ucap, ptr(dM), ptr(dH), ptr(dT), ptr(ws), ws.numel(), stream()), "tmsg_bwd")
+        need_dH, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+
+        def run(dH, dT):
+            ws = workspace(lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, nf, mf, el.B), dev)
+            check(lib.mpnn_tmsg_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src),
+                                    ptr(el.edge_dst), ptr(ti.uid), ptr(ti.type_ptr), ptr(ti.type_eid), ptr(ti.counts),
+                                    ptr(alpha), ptr(H), ptr(table), ptr(tableT), ptr(S), el.n_rows, H.shape[0], el.B,
+                                    el.N, nf, mf, el.Ecap, ti.Ucap, ptr(dM), ptr(dH), ptr(dT), ptr(ws), ws.numel(),
+                                    stream()), "tmsg_bwd")
+
+        # The sender-state gradient continues the main backward chain (and is skipped when the senders are data: the
+        # reference's loops pass the INPUT features to every message function, normed_basic_model.py:58).  The table
+        # gradient only feeds the edge network's parameter gradients: with a single consumer of the table it runs on the
+        # side stream, where EdgeNetTableFn.backward picks it up in stream order.
+        dH = dT = None
+        h = ctx.holder
+        side = SIDE_STREAM_ENABLED and need_dT and h is not None and h.uses == 1
+        if need_dH:
+            dH = torch.empty_like(H)
+            if not side and need_dT:
+                dT = torch.empty_like(table)
+            run(dH, dT)
+        if need_dT and dT is None:
+            cm = _on_side_stream(dev, [dM, H, table, tableT, S, alpha], lane=1) if side else _inline()
+            with cm:
+                dT = torch.empty_like(table)
+                run(None, dT)
+            if side:
+                _READY_EVENTS[dT.data_ptr()] = cm.done
         dbeta = None
         if has_beta:
             dbeta = torch.empty(mf, dtype=torch.float32, device=dev)
             ws2 = workspace(lib.mpnn_colsum_workspace_bytes(el.n_rows, mf), dev)
             check(lib.mpnn_colsum(ptr(dM), None, el.n_rows, mf, mf, 0, ptr(dbeta), 0, ptr(ws2), ws2.numel(), stream()),
                   "colsum")
-        return dH, dT, None, dbeta, None, None, None, None, None
+        return dH, dT, None, dbeta, None, None, None, None, None, None
 
 
 class BilinearEdgeFn(torch.autograd.Function):

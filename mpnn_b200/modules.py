@@ -11,7 +11,7 @@ from torch import nn
 
 from . import graph
 from .functional import (BilinearEdgeFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
-                         GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
+                         GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, TableHolder, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, table_dp, tc_dp, typed_dp)
 from . import _lib
 from .functional import _note_forward_side_work, _side_stream
@@ -232,6 +232,7 @@ class EdgeNetwork(nn.Module):
         lib = _lib.load()
         if table_dp(self.nf, self.mf) <= lib.mpnn_enet_max_dp() and lib.mpnn_enet_supported(self.ef, len(gw), self.P):
             table, tableT = EdgeNetTableFn.apply(ti.urows, w_tied, _N_TIED, W, Bv, self.nf, self.mf, *(gw + gb))
+            table._mpnn_holder = TableHolder()
         else:   # wide trunks (P = 256, 625, 4096): generic trunk + last Linear on the distinct rows
             X = EdgeTrunkFn.apply(ti.urows, w_tied, _N_TIED, *(gw + gb))
             flat = LinearFn.apply(X[:, :self.P].contiguous(), W, Bv)
@@ -273,7 +274,7 @@ class EdgeNetwork(nn.Module):
                 return self._msg_cache[k]
             if typed_dp(self.nf, self.mf) >= 0:
                 M = TypedMessageFn.apply(afm.reshape(-1, nf), table, tableT, self.message_bias, el, None, True,
-                                         self.nf, self.mf).view(B, N, self.mf)
+                                         self.nf, self.mf, getattr(table, "_mpnn_holder", None)).view(B, N, self.mf)
             else:
                 M = self._head_messages_tc(afm, table, el)
             self._msg_cache[k] = M
@@ -304,7 +305,8 @@ class EdgeNetwork(nn.Module):
             if typed_dp(self.nf, self.mf) >= 0:
                 G, gather = self._sender_vectors(afm, bfm, el)   # node states, or one gated vector per edge
                 M = TypedMessageFn.apply(G, table, tableT, None, el if gather else el.per_edge_view(), el.edge_w,
-                                         False, self.nf, self.mf).view(B, N, self.mf)
+                                         False, self.nf, self.mf, getattr(table, "_mpnn_holder", None)
+                                         ).view(B, N, self.mf)
             else:
                 M = TypedMessageTCFn.apply(afm.reshape(-1, nf), table, tableT, el, True, self.nf,
                                            self.mf).view(B, N, self.mf)
