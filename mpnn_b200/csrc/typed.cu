@@ -657,6 +657,70 @@ __global__ void k_enet_last_bwd(const float* __restrict__ acts_x /*[R][PW]*/, co
     dB[f] = s;
 }
 
+// Everything that follows k_enet_bwd, as ONE launch: blocks [0, nb_red) reduce the per-CTA partials (fixed order) and
+// write each sum straight to its destination -- the tied weight's [P][P] gradient out of the padded [PW][PW] block, the
+// growth layers' weight / bias gradients -- and blocks [nb_red, ...) compute the last Linear's gradient, which does not
+// depend on the trunk backward at all.  (Was reduce + unpack + two copies per growth layer + last-layer kernel: five
+// dependent launches at the tail of the backward pass' critical path.)
+struct ENetDst {
+  float* tied;
+  float* gw[MAXG];
+  float* gb[MAXG];
+  int off[MAXG], wn[MAXG], bn[MAXG];   // region of growth layer g inside the reduced vector: [off, off+wn) | [.., +bn)
+  int G, P;
+};
+
+__global__ void k_enet_finish(const float* __restrict__ partial, int nparts, int stride, ENetDst d, int nb_red,
+                              const float* __restrict__ acts_x, const float* __restrict__ dT, int R, int nf, int mf,
+                              int DP, float* __restrict__ dW, float* __restrict__ dB) {
+  if ((int)blockIdx.x < nb_red) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= stride) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * stride + idx];
+    if (idx < PW * PW) {
+      const int o = idx / PW, i = idx - o * PW;
+      if (o < d.P && i < d.P) d.tied[o * d.P + i] = s;
+      return;
+    }
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) {
+      if (g < d.G) {
+        const int r = idx - d.off[g];
+        if (r >= 0 && r < d.wn[g]) d.gw[g][r] = s;
+        else if (r >= d.wn[g] && r < d.wn[g] + d.bn[g]) d.gb[g][r - d.wn[g]] = s;
+      }
+    }
+    return;
+  }
+  const int P = d.P;
+  const int idx = (blockIdx.x - nb_red) * blockDim.x + threadIdx.x;  // over (f, p), p fastest, p in [0, P]
+  const int total = mf * nf * (P + 1);
+  if (idx >= total) return;
+  const int p = idx % (P + 1), f = idx / (P + 1);
+  const int l = f % nf, k = f / nf;
+  float s = 0.f;
+  const float* dcol = dT + (size_t)l * DP + k;
+  const float* xcol = acts_x + min(p, P - 1);
+  for (int u0 = 0; u0 < R; u0 += 8) {
+    float dv[8], xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 16 independent clamped loads
+      const int u = min(u0 + j, R - 1);
+      dv[j] = __ldg(dcol + (size_t)u * DP * DP);
+      xv[j] = __ldg(xcol + (size_t)u * PW);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (u0 + j < R) s = fmaf(dv[j], p < P ? xv[j] : 1.f, s);
+  }
+  if (p < P)
+    dW[(size_t)f * P + p] = s;
+  else
+    dB[f] = s;
+}
+
 int pick_dp(int nf, int mf) {
   int d = nf > mf ? nf : mf;
   return pow2_at_least(d, 8);
@@ -808,22 +872,27 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
   k_enet_bwd<<<nparts, 256, act_smem, stream>>>(n, saved, dT, partial, stride, d_rows);
   MPNN_CHECK_LAUNCH("k_enet_bwd");
-  k_enet_reduce<<<ceil_div(stride, 256), 256, 0, stream>>>(partial, nparts, stride, stride, red);
-  MPNN_CHECK_LAUNCH("k_enet_reduce");
-  k_enet_unpack_tied<<<ceil_div(P * P, 256), 256, 0, stream>>>(red, P, d_w_tied);
-  MPNN_CHECK_LAUNCH("k_enet_unpack_tied");
+  ENetDst dst;
+  memset(&dst, 0, sizeof(dst));
+  dst.tied = d_w_tied;
+  dst.G = n_growth;
+  dst.P = P;
   size_t off = (size_t)PW * PW;
-  for (int g = n_growth - 1; g >= 0; --g) {
-    size_t wn = (size_t)n.gout[g] * n.gin[g];
-    MPNN_CUDA(cudaMemcpyAsync(d_growth_w[g], red + off, wn * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    MPNN_CUDA(cudaMemcpyAsync(d_growth_b[g], red + off + wn, (size_t)n.gout[g] * sizeof(float),
-                              cudaMemcpyDeviceToDevice, stream));
-    off += wn + n.gout[g];
+  for (int g = n_growth - 1; g >= 0; --g) {   // order of the partial vector: last growth layer first
+    dst.gw[g] = d_growth_w[g];
+    dst.gb[g] = d_growth_b[g];
+    dst.off[g] = (int)off;
+    dst.wn[g] = n.gout[g] * n.gin[g];
+    dst.bn[g] = n.gout[g];
+    off += (size_t)dst.wn[g] + dst.bn[g];
   }
   const float* x = saved + (size_t)(n_growth + n_tied) * R * PW;
-  k_enet_last_bwd<<<ceil_div((long long)mf * nf * (P + 1), 256), 256, 0, stream>>>(x, dT, R, nf, mf, P, n.DP, d_w_last,
-                                                                                  d_b_last);
-  MPNN_CHECK_LAUNCH("k_enet_last_bwd");
+  const int nb_red = ceil_div(stride, 256);
+  const int nb_last = ceil_div((long long)mf * nf * (P + 1), 256);
+  (void)red;
+  k_enet_finish<<<nb_red + nb_last, 256, 0, stream>>>(partial, nparts, stride, dst, nb_red, x, dT, R, nf, mf, n.DP,
+                                                      d_w_last, d_b_last);
+  MPNN_CHECK_LAUNCH("k_enet_finish");
   return MPNN_OK;
 }
 

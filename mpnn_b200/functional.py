@@ -41,6 +41,29 @@ def _dev_of(k):
 _READY_EVENTS = {}
 
 
+def _ready_put(t, ev):
+    import weakref
+    _READY_EVENTS[t.data_ptr()] = (weakref.ref(t), ev)
+
+
+def _note_produced(t):
+    """record an event behind the kernels enqueued so far on the current stream as the producer of `t`"""
+    if SIDE_STREAM_ENABLED:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        _ready_put(t, ev)
+
+
+def _ready_get(t):
+    """event behind the producer of `t` -- only while the tensor object it was registered for is still alive (so the
+    address cannot have been recycled for something else) and `t` starts at the same address (itself or a view)"""
+    ent = _READY_EVENTS.pop(t.data_ptr(), None)
+    if ent is None:
+        return None
+    src = ent[0]()
+    return ent[1] if (src is not None and src.data_ptr() == t.data_ptr()) else None
+
+
 _FWD_SIDE = set()
 
 
@@ -331,6 +354,7 @@ class GRUParamHubFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, session, W_ih, W_hh, b_ih, b_hh):
         ctx.session = session
+        ctx.params = (W_ih, W_hh, b_ih, b_hh)
         ctx.set_materialize_grads(False)
         return W_ih.detach(), W_hh.detach(), b_ih.detach(), b_hh.detach()
 
@@ -344,12 +368,16 @@ class GRUParamHubFn(torch.autograd.Function):
             return (None,) + tuple(direct)
         lib = _lib.load()
         rows, d, dev = s.meta
-        dW_ih = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
-        dW_hh = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
-        db_ih = torch.empty(3 * d, dtype=torch.float32, device=dev)
-        db_hh = torch.empty(3 * d, dtype=torch.float32, device=dev)
-        check(lib.mpnn_gru_bwd_params(ptr(s.slab), s.filled, rows, d, ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh),
-                                      stream()), "gru_bwd_params")
+        # parameter gradients only: off the main stream when autograd will ASSIGN them (see EdgeNetTableFn.backward)
+        side = (SIDE_STREAM_ENABLED and all(g is None for g in direct)
+                and all(getattr(p, "grad", None) is None for p in ctx.params))
+        with (_on_side_stream(dev, [s.slab], lane=4) if side else _inline()):
+            dW_ih = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
+            dW_hh = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
+            db_ih = torch.empty(3 * d, dtype=torch.float32, device=dev)
+            db_hh = torch.empty(3 * d, dtype=torch.float32, device=dev)
+            check(lib.mpnn_gru_bwd_params(ptr(s.slab), s.filled, rows, d, ptr(dW_ih), ptr(dW_hh), ptr(db_ih),
+                                          ptr(db_hh), stream()), "gru_bwd_params")
         s.filled = 0                            # a second backward through a retained graph refills the slab
         out = [dW_ih, dW_hh, db_ih, db_hh]
         out = [o if g is None else o + g for o, g in zip(out, direct)]
@@ -398,6 +426,7 @@ class GRUFn(torch.autograd.Function):
                                             d, ptr(dm), ptr(dh), s.slab.data_ptr() + s.filled * pb, stream()),
                       "gru_bwd_data")
                 s.filled += 1
+                _note_produced(dm)
                 return dm, dh, None, None, None, None, None, None
         dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
         db_ih = torch.empty(3 * d, dtype=torch.float32, device=dev)
@@ -406,6 +435,7 @@ class GRUFn(torch.autograd.Function):
         check(lib.mpnn_gru_bwd(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(gates), ptr(dout), rows, d, ptr(dm),
                                ptr(dh), ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh), ptr(ws), ws.numel(), stream()),
               "gru_bwd")
+        _note_produced(dm)
         return dm, dh, None, dW_ih, dW_hh, db_ih, db_hh, None
 
 
@@ -806,7 +836,7 @@ class EdgeNetTableFn(torch.autograd.Function):
         global _ENET_LANE
         _ENET_LANE = (_ENET_LANE + 1) % len(_ENET_LANES)
         lane = _ENET_LANES[_ENET_LANE]
-        ready = _READY_EVENTS.pop(dT.data_ptr(), None)
+        ready = _ready_get(dT)
         if not side and ready is not None:
             torch.cuda.current_stream(dev).wait_event(ready)   # dT was produced on a side stream
         with (_on_side_stream(dev, [dT, urows, w_tied, W_last, saved] + gw, lane=lane, after=ready) if side
@@ -916,12 +946,15 @@ class TypedMessageFn(torch.autograd.Function):
                 dT = torch.empty_like(table)
             run(dH, dT)
         if need_dT and dT is None:
-            cm = _on_side_stream(dev, [dM, H, table, tableT, S, alpha], lane=1) if side else _inline()
+            # fork behind the kernel that produced dM (the GRU backward registers it), not behind whatever the main
+            # stream has been given since
+            cm = (_on_side_stream(dev, [dM, H, table, tableT, S, alpha], lane=1, after=_ready_get(dM)) if side
+                  else _inline())
             with cm:
                 dT = torch.empty_like(table)
                 run(None, dT)
             if side:
-                _READY_EVENTS[dT.data_ptr()] = cm.done
+                _ready_put(dT, cm.done)
         dbeta = None
         if has_beta:
             dbeta = torch.empty(mf, dtype=torch.float32, device=dev)
