@@ -174,7 +174,11 @@ def run_ours(args):
     # the attention gate (per-pair sender vectors) and differentiable bond features run on the per-edge contraction
     # kernels, whose array sizes come from a host read of the edge count: eager launches for those workloads
     use_graph = not args.no_graph and w.get("graph", True)
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=use_graph, fused=use_graph or None)
+    if args.stock_adam:
+        opt = torch.optim.Adam(params, lr=1e-3, capturable=use_graph, fused=use_graph or None)
+    else:   # same update rule as torch.optim.Adam, one launch over all parameter tensors (mpnn_b200/optim.py)
+        from mpnn_b200.optim import FusedAdam
+        opt = FusedAdam(params, lr=1e-3)
     allreduce = D.FlatGradAllReduce(params)
     # L2 (126 MB) is flushed between timed iterations by writing a 256 MB buffer
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -550,6 +554,7 @@ def main():
     ap.add_argument("--config", default="qm9", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stock-adam", action="store_true", help="torch.optim.Adam(fused) instead of mpnn_b200.optim.FusedAdam")
     ap.add_argument("--stock-head", action="store_true", help="keep the head + loss as stock torch modules")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")

@@ -302,6 +302,13 @@ int mpnn_head_bn_linear_mse_bwd(const float* x, const float* target, const float
                                 int T, int training, float* dx, float* dgamma, float* dbeta, float* dW, float* db,
                                 mpnn_stream_t stream);
 
+/* ---- 8f rank 4: the drivers' optimizer (torch.optim.Adam, test_lipo.py:138-139) over a list of small tensors as one
+ * launch.  Host arrays of n device pointers / element counts; `step` = device float (steps taken so far, incremented
+ * by the call: CUDA-graph replayable); `ticket` = device uint32, zero before the first call. */
+int mpnn_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const long long* numel, float* step, unsigned int* ticket, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, mpnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

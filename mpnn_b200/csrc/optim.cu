@@ -1,0 +1,110 @@
+// Adam over a list of small parameter tensors as ONE launch ("fused multi-tensor Adam").
+// The reference drivers train with torch.optim.Adam (test_lipo.py:138-139); its fused multi-tensor kernel gives one
+// CTA a whole 64 K chunk of a tensor, so the ~100 K parameters of an edge-network model take 17 us on 27 CTAs.  Here
+// the tensors are laid end to end in an index space cut into 1 K-element blocks: ~100 CTAs, 4 us.
+// Arithmetic = torch.optim.Adam (amsgrad off, maximize off, L2-style weight decay):
+//   g += wd p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// The step count lives on the device (CUDA-graph replay): every CTA reads it on entry, the last CTA to finish writes
+// t+1 back (ticket counter, self-resetting) -- no separate increment launch.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ADAM_MAXT = 40;        // tensors per launch (pointer table travels as a kernel argument)
+constexpr int ADAM_BLOCK = 1024;     // elements per CTA (256 threads x 4)
+
+struct AdamPack {
+  float* p[ADAM_MAXT];
+  const float* g[ADAM_MAXT];
+  float* m[ADAM_MAXT];
+  float* v[ADAM_MAXT];
+  int first_block[ADAM_MAXT + 1];    // CTA range of tensor i
+  int numel[ADAM_MAXT];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) k_adam(AdamPack pk, float* __restrict__ step, unsigned int* __restrict__ ticket,
+                                              int bump, float lr, float b1, float b2, float eps, float wd) {
+  const float t = step[0] + 1.f;
+  int i = 0;
+  while (i + 1 < pk.n && (int)blockIdx.x >= pk.first_block[i + 1]) ++i;
+  const int base = ((int)blockIdx.x - pk.first_block[i]) * ADAM_BLOCK;
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2s = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  float* __restrict__ P = pk.p[i];
+  const float* __restrict__ G = pk.g[i];
+  float* __restrict__ M = pk.m[i];
+  float* __restrict__ V = pk.v[i];
+  const int n = pk.numel[i];
+  float pv[4], gv[4], mv[4], vv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = base + k * 256 + threadIdx.x;
+    const bool in = e < n;
+    pv[k] = in ? P[e] : 0.f;
+    gv[k] = in ? G[e] : 0.f;
+    mv[k] = in ? M[e] : 0.f;
+    vv[k] = in ? V[e] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = base + k * 256 + threadIdx.x;
+    if (e < n) {
+      const float g = wd != 0.f ? fmaf(wd, pv[k], gv[k]) : gv[k];
+      const float m = b1 * mv[k] + (1.f - b1) * g;
+      const float v = b2 * vv[k] + (1.f - b2) * g * g;
+      const float denom = sqrtf(v) / bc2s + eps;
+      M[e] = m;
+      V[e] = v;
+      P[e] = pv[k] - step_size * (m / denom);
+    }
+  }
+  if (!bump) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {   // every CTA has read step[0] before it took a ticket
+      step[0] = t;
+      *ticket = 0u;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// n tensors: params[i], grads[i], exp_avg[i], exp_avg_sq[i] (device pointers, numel[i] floats each; host arrays).
+// step: device float (number of steps taken so far; incremented by this call); ticket: device uint32, zero on first use.
+int mpnn_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const long long* numel, float* step, unsigned int* ticket, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, cudaStream_t stream) {
+  MPNN_REQUIRE(n >= 0 && step && ticket, MPNN_ERR_ARG, "adam_step: bad arguments");
+  int done = 0;
+  while (done < n) {
+    AdamPack pk;
+    memset(&pk, 0, sizeof(pk));
+    int blocks = 0, k = 0;
+    while (done + k < n && k < ADAM_MAXT) {
+      const long long ne = numel[done + k];
+      MPNN_REQUIRE(ne > 0 && ne < (1ll << 31), MPNN_ERR_ARG, "adam_step: tensor %d has %lld elements", done + k, ne);
+      pk.p[k] = params[done + k];
+      pk.g[k] = grads[done + k];
+      pk.m[k] = exp_avg[done + k];
+      pk.v[k] = exp_avg_sq[done + k];
+      pk.numel[k] = (int)ne;
+      pk.first_block[k] = blocks;
+      blocks += ceil_div(ne, ADAM_BLOCK);
+      ++k;
+    }
+    pk.first_block[k] = blocks;
+    pk.n = k;
+    done += k;
+    k_adam<<<blocks, 256, 0, stream>>>(pk, step, ticket, done == n ? 1 : 0, lr, beta1, beta2, eps, weight_decay);
+    MPNN_CHECK_LAUNCH("k_adam");
+  }
+  return MPNN_OK;
+}
+
+}  // extern "C"
