@@ -67,10 +67,10 @@ def _ready_get(t):
 _FWD_SIDE = set()
 
 
-def _note_forward_side_work(device):
-    """forward work was enqueued on the side stream (sibling table prefetch): `join_side_streams()` waits for it"""
-    k = device.index if device.index is not None else torch.cuda.current_device()
-    _FWD_SIDE.add(k)
+def _note_forward_side_work(device, lane=0):
+    """forward work was enqueued on a side stream (sibling table prefetch, type sort): `join_side_streams()` waits for it"""
+    d = device.index if device.index is not None else torch.cuda.current_device()
+    _FWD_SIDE.add(d if lane == 0 else (d, lane))
 
 
 def join_side_streams():
@@ -79,7 +79,7 @@ def join_side_streams():
     for k in list(_FWD_SIDE):
         _FWD_SIDE.discard(k)
         if k in _SIDE_STREAMS:
-            torch.cuda.current_stream(k).wait_stream(_SIDE_STREAMS[k])
+            torch.cuda.current_stream(_dev_of(k)).wait_stream(_SIDE_STREAMS[k])
     _join_side_streams()
 
 
@@ -926,6 +926,8 @@ class TypedMessageFn(torch.autograd.Function):
         need_dH, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
 
         def run(dH, dT):
+            if dT is not None:
+                ti.wait_sorted()
             ws = workspace(lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, nf, mf, el.B), dev)
             check(lib.mpnn_tmsg_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src),
                                     ptr(el.edge_dst), ptr(ti.uid), ptr(ti.type_ptr), ptr(ti.type_eid), ptr(ti.counts),

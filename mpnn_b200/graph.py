@@ -4,6 +4,7 @@ Layout contract: the reference's padded tensors (collate_2d_graphs, pre_process/
 bfm [B,N,N,ef], adj [B,N,N].  The compacted form is what every message kernel consumes.
 """
 import collections
+import os
 
 import torch
 
@@ -157,9 +158,16 @@ class TypedInfo(object):
         self.U, self.Ucap = U, Ucap
         self.zero_type = Ucap
         self._tc_plan = None
+        self.sort_event = None    # set when the type sort was enqueued on a side stream (capacity mode)
+
+    def wait_sorted(self):
+        """type_ptr / type_eid / type_pos are about to be read on the current stream"""
+        if self.sort_event is not None:
+            torch.cuda.current_stream(self.uid.device).wait_event(self.sort_event)
 
     def tc_plan(self, el):
         """single-type tiles of <= 128 type-sorted edges for the tcgen05 kernels (csrc/tc_message.cu), built once"""
+        self.wait_sorted()
         if self._tc_plan is None:
             lib = _lib.load()
             if self.type_ptr is None:
@@ -172,6 +180,7 @@ class TypedInfo(object):
         return self._tc_plan
 
 
+SORT_ON_SIDE_STREAM = os.environ.get("MPNN_B200_SORT_SIDE_STREAM", "1") != "0"
 TYPED_MAX_UNIQUE = 1024   # beyond this many distinct bond rows the per-edge contraction (csrc/message.cu) is used
 
 
@@ -210,10 +219,36 @@ def dedup_rows(el, unique_capacity=None):
     urows = torch.zeros(Ucap + 1, ef, dtype=torch.float32, device=dev)
     type_ptr = torch.empty(Ucap + 1, dtype=torch.int32, device=dev)
     ws = _lib.workspace(lib.mpnn_dedup_workspace_bytes(Ecap, Ucap), dev)
+    if not SORT_ON_SIDE_STREAM:
+        _lib.check(lib.mpnn_dedup_rows(_lib.ptr(el.rows), _lib.ptr(n_edges_ptr), Ecap, ef, Ucap, _lib.ptr(uid),
+                                       _lib.ptr(urows), _lib.ptr(counts), 1, _lib.ptr(type_ptr), _lib.ptr(type_eid),
+                                       _lib.ptr(type_pos), _lib.ptr(ws), ws.numel(), _lib.stream()), "dedup_rows")
+        return TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], None, Ucap)
+    # The forward pass needs the distinct rows and the per-edge type ids only; the edges grouped by type are read by
+    # the table-gradient kernels of the backward pass (and the tensor-core plan).  The grouping (histogram, scan, fill:
+    # three dependent launches) therefore runs on a side stream, a parallel branch of the captured step.
+    from . import functional
     _lib.check(lib.mpnn_dedup_rows(_lib.ptr(el.rows), _lib.ptr(n_edges_ptr), Ecap, ef, Ucap, _lib.ptr(uid),
-                                   _lib.ptr(urows), _lib.ptr(counts), 1, _lib.ptr(type_ptr), _lib.ptr(type_eid),
-                                   _lib.ptr(type_pos), _lib.ptr(ws), ws.numel(), _lib.stream()), "dedup_rows")
-    return TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], None, Ucap)
+                                   _lib.ptr(urows), _lib.ptr(counts), 0, None, None, None, _lib.ptr(ws), ws.numel(),
+                                   _lib.stream()), "dedup_rows")
+    main = torch.cuda.current_stream(dev)
+    _, side = functional._side_stream(dev, lane=5)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        ws2 = _lib.workspace(lib.mpnn_type_sort_workspace_bytes(Ecap, Ucap), dev)
+        _lib.check(lib.mpnn_type_sort(_lib.ptr(uid), _lib.ptr(counts), Ecap, Ucap, _lib.ptr(type_ptr),
+                                      _lib.ptr(type_eid), _lib.ptr(type_pos), _lib.ptr(ws2), ws2.numel(),
+                                      _lib.stream()), "type_sort")
+        done = torch.cuda.Event()
+        done.record(side)
+    for t in (uid, counts, type_ptr, type_eid, type_pos):
+        t.record_stream(side)
+    functional._note_forward_side_work(dev, lane=5)
+    ti = TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], None, Ucap)
+    ti.sort_event = done
+    return ti
 
 
 # ---- small identity cache: the same (bfm, adj) pair is compacted once per batch, whatever number of
@@ -424,6 +459,7 @@ def typed_bonds(bfm, adj):
     if ti.type_ptr is None:
         return bfm
     el._typed = ti
+    ti.wait_sorted()                                   # the occurrence counts come from the grouping by type
     ua = ti.urows                                      # [Ucap+1, ef+1]; rows >= U are zero
     rows = ua[:, :ef].contiguous()
     a = ua[:, ef].contiguous()
