@@ -319,7 +319,6 @@ __global__ void k_table_to_flat(const float* __restrict__ dT, int R, int nf, int
 // layer).  The tied weight stays in shared memory for all layers.
 // ===================================================================================================
 constexpr int PW = 64;    // max padded trunk width handled here
-constexpr int WS_ = 68;   // shared-memory row stride of the tied weight (== 4 mod 32: conflict-free 4-lane split)
 constexpr int MAXG = 4;
 
 struct ENet {
@@ -609,54 +608,6 @@ __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restric
         make_float4(accW[a][0], accW[a][1], accW[a][2], accW[a][3]);
 }
 
-// fixed-order reduction of the per-CTA partials: out[idx] = sum_c partial[c][idx]
-__global__ void k_enet_reduce(const float* __restrict__ partial, int nparts, int partial_stride, int count,
-                              float* __restrict__ out) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count) return;
-  float s = 0.f;
-#pragma unroll 8
-  for (int c = 0; c < nparts; ++c) s += partial[(size_t)c * partial_stride + idx];
-  out[idx] = s;
-}
-
-// unpack the reduced tied gradient [PW][PW] -> [P][P]
-__global__ void k_enet_unpack_tied(const float* __restrict__ red, int P, float* __restrict__ dW) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P * P) return;
-  int o = idx / P, i = idx - o * P;
-  dW[idx] = red[o * PW + i];
-}
-
-// dW_last[k*nf+l, p] = sum_u dT[u][l][k] x_u[p];  dB_last[k*nf+l] = sum_u dT[u][l][k]
-__global__ void k_enet_last_bwd(const float* __restrict__ acts_x /*[R][PW]*/, const float* __restrict__ dT, int R,
-                                int nf, int mf, int P, int DP, float* __restrict__ dW, float* __restrict__ dB) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over (f, p), p fastest, p in [0, P]
-  int total = mf * nf * (P + 1);
-  if (idx >= total) return;
-  int p = idx % (P + 1), f = idx / (P + 1);
-  int l = f % nf, k = f / nf;
-  float s = 0.f;
-  const float* dcol = dT + (size_t)l * DP + k;
-  const float* xcol = acts_x + min(p, P - 1);
-  for (int u0 = 0; u0 < R; u0 += 8) {
-    float dv[8], xv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {  // 16 independent clamped loads
-      const int u = min(u0 + j, R - 1);
-      dv[j] = __ldg(dcol + (size_t)u * DP * DP);
-      xv[j] = __ldg(xcol + (size_t)u * PW);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (u0 + j < R) s = fmaf(dv[j], p < P ? xv[j] : 1.f, s);
-  }
-  if (p < P)
-    dW[(size_t)f * P + p] = s;
-  else
-    dB[f] = s;
-}
-
 // Everything that follows k_enet_bwd, as ONE launch: blocks [0, nb_red) reduce the per-CTA partials (fixed order) and
 // write each sum straight to its destination -- the tied weight's [P][P] gradient out of the padded [PW][PW] block, the
 // growth layers' weight / bias gradients -- and blocks [nb_red, ...) compute the last Linear's gradient, which does not
@@ -866,7 +817,6 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   const int stride = enet_partial_stride(n);
   const int nparts = enet_grid(R);
   float* partial = (float*)workspace;
-  float* red = partial + (size_t)nparts * stride;
   const size_t act_smem = (size_t)(n_growth + n_tied + 1) * PW * sizeof(float);
   MPNN_REQUIRE(act_smem <= 160 * 1024, MPNN_ERR_UNSUPPORTED, "enet_bwd: too many layers for the shared-memory stage");
   MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
@@ -889,7 +839,6 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   const float* x = saved + (size_t)(n_growth + n_tied) * R * PW;
   const int nb_red = ceil_div(stride, 256);
   const int nb_last = ceil_div((long long)mf * nf * (P + 1), 256);
-  (void)red;
   k_enet_finish<<<nb_red + nb_last, 256, 0, stream>>>(partial, nparts, stride, dst, nb_red, x, dT, R, nf, mf, n.DP,
                                                       d_w_last, d_b_last);
   MPNN_CHECK_LAUNCH("k_enet_finish");
