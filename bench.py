@@ -108,7 +108,8 @@ def make_workload_batch(config, w, rank):
 
 
 def build_model(w, dev):
-    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    # the UNMODIFIED reference model files (tests/ref_models/models/*.py, byte-identical) over this package's modules
+    from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
     from mpnn_b200 import modules as M
     torch.manual_seed(317)
     kw = {}
@@ -117,8 +118,8 @@ def build_model(w, dev):
     if w.get("readout_func"):
         kw["readout_func"] = getattr(M, w["readout_func"])
     if w.get("encoders"):   # AtomAutoEncoder / BondAutoEncoder .encoder halves (encoders/*_autoencoder.py:7-11)
-        kw["atom_encoder"] = torch.nn.Sequential(torch.nn.Linear(30, 15, bias=False), torch.nn.Tanh(), torch.nn.Linear(15, 8))
-        kw["bond_encoder"] = torch.nn.Sequential(torch.nn.Linear(8, 4, bias=False), torch.nn.Tanh(), torch.nn.Linear(4, 2))
+        kw["atom_encoder"] = M.AtomAutoEncoder().encoder
+        kw["bond_encoder"] = M.BondAutoEncoder().encoder
     body = MessagePassingModel(w["variant"], w["d"], w["ef"], w["d"], 1, w["out"], message_steps=w["T"], **kw)
     body.apply(kaiming_init)
     # prediction heads of the reference drivers (stock torch modules): test_graph_norm.py:86-90
@@ -460,7 +461,6 @@ def count_launches(fn):
 # ---------------------------------------------------------------------------------------------------
 def _oracle_step_fn(config, B):
     from mpnn_b200 import synthetic
-    from mpnn_b200.callers import kaiming_init, MessagePassingModel
     from oracle import mpnn_oracle as O
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from golden_util import leaf_sd

@@ -279,13 +279,21 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
 long long mpnn_set2vec_saved_floats(int B, int N, int F, int steps);
 size_t mpnn_set2vec_workspace_bytes(int B, int N, int F);
 size_t mpnn_set2vec_bwd_workspace_bytes(int B, int N, int F, int steps);
+/* m0 [B,2F] / c0 [B,F]: caller-supplied initial LSTM state (set2vec.py:111-117: m0 = cat(mprev, 0)); NULL = zeros.
+ * bwd writes dm0 [B,2F] / dc0 [B,F] when non-NULL. */
 int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
-                     const float* we, int B, int N, int F, int steps, float* out, float* saved, void* workspace,
-                     size_t workspace_bytes, mpnn_stream_t stream);
+                     const float* we, const float* m0, const float* c0, int B, int N, int F, int steps, float* out,
+                     float* saved, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const float* Wq, const float* we,
-                     const float* saved, const float* dout, int B, int N, int F, int steps, float* dX, float* dWcat,
-                     float* dbcat, float* dWq, float* dwe, void* workspace, size_t workspace_bytes,
-                     mpnn_stream_t stream);
+                     const float* m0, const float* c0, const float* saved, const float* dout, int B, int N, int F,
+                     int steps, float* dX, float* dWcat, float* dbcat, float* dWq, float* dwe, float* dm0, float* dc0,
+                     void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* LSTMCellHidden.forward alone (set2vec.py:68-75) on pre [B,4F] = hprev [w_hi|w_hf|w_hg|w_ho] + [b_*] (the caller's
+ * mpnn_gemm): activated gates [B,4F], c' [B,F], tanh(c') [B,F], h' [B,F]; bwd: dh, dc' -> dpre [B,4F], dc_prev. */
+int mpnn_lstm_hidden_fwd(const float* pre, const float* cprev, int B, int F, float* gates, float* c, float* tc,
+                         float* h, mpnn_stream_t stream);
+int mpnn_lstm_hidden_bwd(const float* gates, const float* tc, const float* cprev, const float* dh, const float* dc_next,
+                         int B, int F, float* dpre, float* dc_prev, mpnn_stream_t stream);
 
 /* ---- 8f rank 4: prediction head + loss of the drivers (test_graph_norm.py:86-90 nn.BatchNorm1d(out) ->
  * nn.Linear(out, targets) + nn.MSELoss), one single-CTA launch each way for problems that fit a CTA's shared memory

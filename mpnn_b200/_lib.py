@@ -105,8 +105,11 @@ SIGNATURES = {
     "mpnn_set2vec_saved_floats": (_L, [_I, _I, _I, _I]),
     "mpnn_set2vec_workspace_bytes": (_Z, [_I, _I, _I]),
     "mpnn_set2vec_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),
-    "mpnn_set2vec_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
-    "mpnn_set2vec_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_set2vec_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "mpnn_set2vec_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _Z,
+                              _P]),
+    "mpnn_lstm_hidden_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "mpnn_lstm_hidden_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
 }
 
 _lib = None

@@ -39,10 +39,10 @@ inline StepPtrs step_ptrs(float* saved, int s, int B, int N, int F) {
   return r;
 }
 
-// pre [B,4F] -> activated gates, c', h' (written to m[:, :F])
+// pre [B,4F] -> activated gates, c', h' (written to m[:, :F], row stride ldm)
 __global__ void k_lstm_fwd(const float* __restrict__ pre, const float* __restrict__ cprev, int B, int F,
                            float* __restrict__ gates, float* __restrict__ c, float* __restrict__ tc,
-                           float* __restrict__ m) {
+                           float* __restrict__ m, int ldm) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= B * F) return;
   int b = t / F, f = t - b * F;
@@ -61,7 +61,7 @@ __global__ void k_lstm_fwd(const float* __restrict__ pre, const float* __restric
   gs[3 * F + f] = o;
   c[t] = cn;
   tc[t] = th;
-  m[(size_t)b * 2 * F + f] = o * th;
+  m[(size_t)b * ldm + f] = o * th;
 }
 
 // e[r] = sum_f we[f] * tanh(q[b,f] + X[r,f]) + (1-mask[r]) * BIG_NEGATIVE.   One warp per row.
@@ -172,7 +172,7 @@ __global__ void k_lstm_bwd(const float* __restrict__ gates, const float* __restr
   const float* gs = gates + (size_t)b * 4 * F;
   float i = gs[f], fg = gs[F + f], g = gs[2 * F + f], o = gs[3 * F + f];
   float th = tc[t];
-  float dhv = dh[t] + dm[(size_t)b * 2 * F + f];   // dh = dq Wq + dm[:, :F]
+  float dhv = dh[t] + (dm ? dm[(size_t)b * 2 * F + f] : 0.f);   // dh = dq Wq + dm[:, :F]
   float dcn = dhv * o * (1.f - th * th) + dc[t];
   float cp = cprev ? cprev[t] : 0.f;
   float* dp = dpre + (size_t)b * 4 * F;
@@ -220,8 +220,8 @@ size_t mpnn_set2vec_bwd_workspace_bytes(int B, int N, int F, int steps) {
 }
 
 int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
-                     const float* we, int B, int N, int F, int steps, float* out, float* saved, void* workspace,
-                     size_t workspace_bytes, cudaStream_t stream) {
+                     const float* we, const float* m0, const float* c0, int B, int N, int F, int steps, float* out,
+                     float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(B > 0 && N > 0 && F > 0 && steps > 0, MPNN_ERR_ARG, "set2vec_fwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_workspace_bytes(B, N, F), MPNN_ERR_WORKSPACE, "set2vec_fwd: workspace");
   const int rows = B * N;
@@ -230,16 +230,19 @@ int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const
   for (int s = 0; s < steps; ++s) {
     StepPtrs cur = step_ptrs(saved, s, B, N, F);
     int rc;
-    if (s == 0) {
+    if (s == 0 && !m0) {
       // m_prev = 0: pre-activations are just the biases
       rc = mpnn_gemm(nullptr, nullptr, pre, B, 4 * F, 0, 0, 0, 0, 0, 4 * F, bcat, 0, nullptr, 0, stream);
+    } else if (s == 0) {
+      // caller-supplied initial state (set2vec.py:111-117): m0 = cat(mprev, 0) [B, 2F]
+      rc = mpnn_gemm(m0, Wcat, pre, B, 4 * F, 2 * F, 2 * F, 1, 4 * F, 1, 4 * F, bcat, 0, nullptr, 0, stream);
     } else {
       StepPtrs prev = step_ptrs(saved, s - 1, B, N, F);
       rc = mpnn_gemm(prev.m, Wcat, pre, B, 4 * F, 2 * F, 2 * F, 1, 4 * F, 1, 4 * F, bcat, 0, nullptr, 0, stream);
     }
     if (rc) return rc;
-    const float* cprev = s == 0 ? nullptr : step_ptrs(saved, s - 1, B, N, F).c;
-    k_lstm_fwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(pre, cprev, B, F, cur.gates, cur.c, cur.tc, cur.m);
+    const float* cprev = s == 0 ? c0 : step_ptrs(saved, s - 1, B, N, F).c;
+    k_lstm_fwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(pre, cprev, B, F, cur.gates, cur.c, cur.tc, cur.m, 2 * F);
     // q = h Wq^T  (h = m[:, :F], row stride 2F; Wq is nn.Linear weight [F_out, F_in])
     if ((rc = mpnn_gemm(cur.m, Wq, cur.q, B, F, F, 2 * F, 1, 1, F, F, nullptr, 0, nullptr, 0, stream))) return rc;
     k_energy<<<ceil_div((long long)rows * 32, 256), 256, 0, stream>>>(X, cur.q, we, mask, rows, N, F, e);
@@ -252,11 +255,12 @@ int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const
   return MPNN_OK;
 }
 
-// dWcat [2F,4F], dbcat [4F], dWq [F,F], dwe [F], dX [B,N,F] are written.
+// dWcat [2F,4F], dbcat [4F], dWq [F,F], dwe [F], dX [B,N,F] are written; dm0 [B,2F] / dc0 [B,F] when non-NULL
+// (gradients of the caller-supplied initial state m0 / c0, NULL = the reference's zero initial state).
 int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const float* Wq, const float* we,
-                     const float* saved_c, const float* dout, int B, int N, int F, int steps, float* dX, float* dWcat,
-                     float* dbcat, float* dWq, float* dwe, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+                     const float* m0, const float* c0, const float* saved_c, const float* dout, int B, int N, int F,
+                     int steps, float* dX, float* dWcat, float* dbcat, float* dWq, float* dwe, float* dm0, float* dc0,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(B > 0 && N > 0 && F > 0 && steps > 0, MPNN_ERR_ARG, "set2vec_bwd: bad dims");
   MPNN_REQUIRE((long long)steps * B < (1ll << 31), MPNN_ERR_UNSUPPORTED, "set2vec_bwd: steps*B too large");
   MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_bwd_workspace_bytes(B, N, F, steps), MPNN_ERR_WORKSPACE,
@@ -299,7 +303,7 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
     MPNN_CHECK_LAUNCH("set2vec_bwd energy");
     // dh = dq Wq (+ dm[:, :F], added inside k_lstm_bwd)
     if ((rc = mpnn_gemm(dq, Wq, dh, B, F, F, F, 1, F, 1, F, nullptr, 0, nullptr, 0, stream))) return rc;
-    const float* cprev = s == 0 ? nullptr : step_ptrs(saved, s - 1, B, N, F).c;
+    const float* cprev = s == 0 ? c0 : step_ptrs(saved, s - 1, B, N, F).c;
     k_lstm_bwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(cur.gates, cur.tc, cprev, dh, dm, dc, B, F, dpre);
     MPNN_CHECK_LAUNCH("set2vec_bwd lstm");
     if (s > 0) {
@@ -310,8 +314,12 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
       float* t = dm;
       dm = dm_prev;
       dm_prev = t;
+    } else if (m0 && dm0) {
+      if ((rc = mpnn_gemm(dpre, Wcat, dm0, B, 2 * F, 4 * F, 4 * F, 1, 1, 4 * F, 2 * F, nullptr, 0, nullptr, 0, stream)))
+        return rc;
     }
   }
+  if (dc0) MPNN_CUDA(cudaMemcpyAsync(dc0, dc, (size_t)B * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   // parameter gradients over all steps at once
   if ((rc = mpnn_colsum(pwS, nullptr, (int)sb, F, F, 0, dwe, 0, sub, sub_bytes, stream))) return rc;
   if ((rc = mpnn_colsum(dpreS, nullptr, (int)sb, 4 * F, 4 * F, 0, dbcat, 0, sub, sub_bytes, stream))) return rc;
@@ -325,6 +333,31 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
   } else {
     MPNN_CUDA(cudaMemsetAsync(dWcat, 0, (size_t)2 * F * 4 * F * sizeof(float), stream));
   }
+  if (m0) {  // step 0 read the caller's initial state: dWcat += m0^T dpre_0
+    if ((rc = mpnn_gemm(m0, dpreS, dWcat, 2 * F, 4 * F, B, 1, 2 * F, 4 * F, 1, 4 * F, nullptr, 2, sub, sub_bytes,
+                        stream)))
+      return rc;
+  }
+  return MPNN_OK;
+}
+
+// ---- the input-less LSTM cell alone (set2vec.py:68-75): pre [B,4F] = hprev Wcat + bcat is the caller's GEMM --------
+// gates [B,4F] (activated i,f,g,o), c [B,F], tc [B,F] = tanh(c), h [B,F] are written.
+int mpnn_lstm_hidden_fwd(const float* pre, const float* cprev, int B, int F, float* gates, float* c, float* tc,
+                         float* h, cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && F > 0, MPNN_ERR_ARG, "lstm_hidden_fwd: bad dims");
+  k_lstm_fwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(pre, cprev, B, F, gates, c, tc, h, F);
+  MPNN_CHECK_LAUNCH("lstm_hidden_fwd");
+  return MPNN_OK;
+}
+
+// dh, dc_next [B,F] -> dpre [B,4F], dc_prev [B,F]
+int mpnn_lstm_hidden_bwd(const float* gates, const float* tc, const float* cprev, const float* dh, const float* dc_next,
+                         int B, int F, float* dpre, float* dc_prev, cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && F > 0, MPNN_ERR_ARG, "lstm_hidden_bwd: bad dims");
+  MPNN_CUDA(cudaMemcpyAsync(dc_prev, dc_next, (size_t)B * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  k_lstm_bwd<<<ceil_div(B * F, 256), 256, 0, stream>>>(gates, tc, cprev, dh, nullptr, dc_prev, B, F, dpre);
+  MPNN_CHECK_LAUNCH("lstm_hidden_bwd");
   return MPNN_OK;
 }
 

@@ -706,15 +706,18 @@ class DenseAggFn(torch.autograd.Function):
 # Set2Vec readout
 # ------------------------------------------------------------------------------------------------
 class Set2VecFn(torch.autograd.Function):
-    """reference set2vec.py:93-151 ("default" inner product).  Wcat [2F,4F] = [w_hi|w_hf|w_hg|w_ho], bcat [4F]."""
+    """reference set2vec.py:93-151 ("default" inner product).  Wcat [2F,4F] = [w_hi|w_hf|w_hg|w_ho], bcat [4F];
+    m0 [B,2F] / c0 [B,F]: caller-supplied initial state (set2vec.py:111-117), None = zeros."""
 
     @staticmethod
-    def forward(ctx, X, mask, Wcat, bcat, Wq, we, steps):
+    def forward(ctx, X, mask, Wcat, bcat, Wq, we, steps, m0=None, c0=None):
         lib = _lib.load()
         _need_cuda(X, Wcat)
         X = f32c(X)
         mask_c = f32c(mask) if mask is not None else None
         Wcat, bcat, Wq, we = f32c(Wcat), f32c(bcat), f32c(Wq), f32c(we)
+        m0_c = f32c(m0) if m0 is not None else None
+        c0_c = f32c(c0) if c0 is not None else None
         B, N, F = X.shape
         dev = X.device
 
@@ -724,14 +727,14 @@ class Set2VecFn(torch.autograd.Function):
                     workspace(lib.mpnn_set2vec_workspace_bytes(B, N, F), dev)]
 
         def run(ins, bufs):
-            x, mk, wc, bc, wq, w_e = ins
+            x, mk, wc, bc, wq, w_e, m_0, c_0 = ins
             out, saved, ws = bufs
-            check(lib.mpnn_set2vec_fwd(ptr(x), ptr(mk), ptr(wc), ptr(bc), ptr(wq), ptr(w_e), B, N, F, steps, ptr(out),
-                                       ptr(saved), ptr(ws), ws.numel(), stream()), "set2vec_fwd")
+            check(lib.mpnn_set2vec_fwd(ptr(x), ptr(mk), ptr(wc), ptr(bc), ptr(wq), ptr(w_e), ptr(m_0), ptr(c_0), B, N, F,
+                                       steps, ptr(out), ptr(saved), ptr(ws), ws.numel(), stream()), "set2vec_fwd")
 
-        out, saved = _graphed(("set2vec_fwd", B, N, F, steps, mask is not None, dev.index), run,
-                              [X, mask_c, Wcat, bcat, Wq, we], make_bufs, 2)
-        ctx.save_for_backward(X, mask_c, Wcat, Wq, we, saved)
+        out, saved = _graphed(("set2vec_fwd", B, N, F, steps, mask is not None, m0 is not None, c0 is not None,
+                               dev.index), run, [X, mask_c, Wcat, bcat, Wq, we, m0_c, c0_c], make_bufs, 2)
+        ctx.save_for_backward(X, mask_c, Wcat, Wq, we, saved, m0_c, c0_c)
         ctx.steps = steps
         return out
 
@@ -739,7 +742,7 @@ class Set2VecFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, dout):
         lib = _lib.load()
-        X, mask, Wcat, Wq, we, saved = ctx.saved_tensors
+        X, mask, Wcat, Wq, we, saved, m0, c0 = ctx.saved_tensors
         B, N, F = X.shape
         dev = X.device
         dout = f32c(dout)
@@ -748,18 +751,76 @@ class Set2VecFn(torch.autograd.Function):
         def make_bufs():
             return [torch.empty_like(X), torch.empty_like(Wcat), torch.empty(4 * F, dtype=torch.float32, device=dev),
                     torch.empty_like(Wq), torch.empty_like(we),
+                    torch.empty(B, 2 * F, dtype=torch.float32, device=dev) if m0 is not None else None,
+                    torch.empty(B, F, dtype=torch.float32, device=dev) if c0 is not None else None,
                     workspace(lib.mpnn_set2vec_bwd_workspace_bytes(B, N, F, steps), dev)]
 
         def run(ins, bufs):
-            x, mk, wc, wq, w_e, sv, do = ins
-            dX, dWcat, dbcat, dWq, dwe, ws = bufs
-            check(lib.mpnn_set2vec_bwd(ptr(x), ptr(mk), ptr(wc), ptr(wq), ptr(w_e), ptr(sv), ptr(do), B, N, F, steps,
-                                       ptr(dX), ptr(dWcat), ptr(dbcat), ptr(dWq), ptr(dwe), ptr(ws), ws.numel(),
-                                       stream()), "set2vec_bwd")
+            x, mk, wc, wq, w_e, m_0, c_0, sv, do = ins
+            dX, dWcat, dbcat, dWq, dwe, dm0, dc0, ws = bufs
+            check(lib.mpnn_set2vec_bwd(ptr(x), ptr(mk), ptr(wc), ptr(wq), ptr(w_e), ptr(m_0), ptr(c_0), ptr(sv), ptr(do),
+                                       B, N, F, steps, ptr(dX), ptr(dWcat), ptr(dbcat), ptr(dWq), ptr(dwe), ptr(dm0),
+                                       ptr(dc0), ptr(ws), ws.numel(), stream()), "set2vec_bwd")
 
-        dX, dWcat, dbcat, dWq, dwe = _graphed(("set2vec_bwd", B, N, F, steps, mask is not None, dev.index), run,
-                                              [X, mask, Wcat, Wq, we, saved, dout], make_bufs, 5)
-        return dX, None, dWcat, dbcat, dWq, dwe, None
+        if m0 is None and c0 is None:
+            dX, dWcat, dbcat, dWq, dwe, dm0, dc0 = _graphed(
+                ("set2vec_bwd", B, N, F, steps, mask is not None, dev.index), run,
+                [X, mask, Wcat, Wq, we, None, None, saved, dout], make_bufs, 7)
+        else:
+            bufs = make_bufs()
+            run([X, mask, Wcat, Wq, we, m0, c0, saved, dout], bufs)
+            dX, dWcat, dbcat, dWq, dwe, dm0, dc0 = bufs[:7]
+        return dX, None, dWcat, dbcat, dWq, dwe, None, dm0, dc0
+
+
+class LSTMCellHiddenFn(torch.autograd.Function):
+    """reference set2vec.py:68-75 (the input-less LSTM cell on its own): (hprev [B,2F], cprev [B,F], Wcat, bcat) ->
+    (h' [B,F], c' [B,F])."""
+
+    @staticmethod
+    def forward(ctx, hprev, cprev, Wcat, bcat):
+        lib = _lib.load()
+        _need_cuda(hprev, cprev, Wcat)
+        hprev, cprev, Wcat, bcat = f32c(hprev), f32c(cprev), f32c(Wcat), f32c(bcat)
+        B, K = hprev.shape
+        F = Wcat.shape[1] // 4
+        dev = hprev.device
+        pre = torch.empty(B, 4 * F, dtype=torch.float32, device=dev)
+        check(lib.mpnn_gemm(ptr(hprev), ptr(Wcat), ptr(pre), B, 4 * F, K, K, 1, 4 * F, 1, 4 * F, ptr(bcat), 0, None, 0,
+                            stream()), "gemm")
+        gates = torch.empty(B, 4 * F, dtype=torch.float32, device=dev)
+        c = torch.empty(B, F, dtype=torch.float32, device=dev)
+        tc = torch.empty(B, F, dtype=torch.float32, device=dev)
+        h = torch.empty(B, F, dtype=torch.float32, device=dev)
+        check(lib.mpnn_lstm_hidden_fwd(ptr(pre), ptr(cprev), B, F, ptr(gates), ptr(c), ptr(tc), ptr(h), stream()),
+              "lstm_hidden_fwd")
+        ctx.save_for_backward(hprev, cprev, Wcat, gates, tc)
+        return h, c
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dh, dc):
+        lib = _lib.load()
+        hprev, cprev, Wcat, gates, tc = ctx.saved_tensors
+        B, K = hprev.shape
+        F = Wcat.shape[1] // 4
+        dev = hprev.device
+        dh = f32c(dh) if dh is not None else torch.zeros(B, F, dtype=torch.float32, device=dev)
+        dc = f32c(dc) if dc is not None else torch.zeros(B, F, dtype=torch.float32, device=dev)
+        dpre = torch.empty(B, 4 * F, dtype=torch.float32, device=dev)
+        dcprev = torch.empty(B, F, dtype=torch.float32, device=dev)
+        check(lib.mpnn_lstm_hidden_bwd(ptr(gates), ptr(tc), ptr(cprev), ptr(dh), ptr(dc), B, F, ptr(dpre), ptr(dcprev),
+                                       stream()), "lstm_hidden_bwd")
+        dhprev = torch.empty_like(hprev)
+        check(lib.mpnn_gemm(ptr(dpre), ptr(Wcat), ptr(dhprev), B, K, 4 * F, 4 * F, 1, 1, 4 * F, K, None, 0, None, 0,
+                            stream()), "gemm")
+        dW = torch.empty_like(Wcat)
+        ws = workspace(lib.mpnn_gemm_workspace_bytes(K, 4 * F, B) + lib.mpnn_colsum_workspace_bytes(B, 4 * F), dev)
+        check(lib.mpnn_gemm(ptr(hprev), ptr(dpre), ptr(dW), K, 4 * F, B, 1, K, 4 * F, 1, 4 * F, None, 0, ptr(ws),
+                            ws.numel(), stream()), "gemm")
+        db = torch.empty(4 * F, dtype=torch.float32, device=dev)
+        check(lib.mpnn_colsum(ptr(dpre), None, B, 4 * F, 4 * F, 0, ptr(db), 0, ptr(ws), ws.numel(), stream()), "colsum")
+        return dhprev, dcprev, dW, db
 
 
 # ------------------------------------------------------------------------------------------------

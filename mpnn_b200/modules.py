@@ -11,7 +11,8 @@ from torch import nn
 
 from . import graph
 from .functional import (BilinearEdgeFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
-                         GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, TableHolder, LinearFn, MaskBN1dFn, MaskBNFn, Set2VecFn, SoftmaxMulFn,
+                         GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, TableHolder, LinearFn, LSTMCellHiddenFn, MaskBN1dFn, MaskBNFn,
+                         Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, table_dp, tc_dp, typed_dp)
 from . import _lib
 from .functional import _note_forward_side_work, _side_stream
@@ -330,6 +331,8 @@ class EdgeNetwork(nn.Module):
     def forward(self, afm, bfm, reuse_graph_tensors=False):
         if not afm.is_cuda:
             raise RuntimeError("mpnn_b200.EdgeNetwork: CUDA tensors required (there is no CPU fallback)")
+        if isinstance(bfm, DeferredRows):
+            bfm = bfm.materialize()
         if isinstance(bfm, graph.TypedBonds) and not (type(self)._typed_capable and type(self)._typed_ok is
                                                       EdgeNetwork._typed_ok and table_dp(self.nf, self.mf) >= 0):
             bfm = bfm.dense()
@@ -451,11 +454,127 @@ class GGNNMsgPass(nn.Module):
 
 
 # =================================================================================================
+# encoders on categorical bond tensors (reference mpnn_functions/encoders/*.py)
+# =================================================================================================
+class DeferredRows(object):
+    """What a `RowwiseSequential` returns for a dense 4-D CUDA data tensor: "module(x)", not yet evaluated.
+
+    The unchanged reference models run `bfm = self.bebn(self.be(bfm), adj)` (normed_encoded_basic_model.py:68): the
+    encoder sees the bond tensor before the adjacency is known.  The masked batch norm that receives this handle
+    resolves it: it de-duplicates the RAW bond rows keyed with the adjacency value (`graph.typed_bonds`), pushes the few
+    distinct rows through the encoder and normalises them in row space (`graph.TypedBonds`); nothing of size B N^2 F is
+    read after compaction.  Any other consumer gets the dense result of the stock layers."""
+
+    def __init__(self, module, x):
+        self._module, self._x = module, x
+        self._value = None
+
+    def materialize(self):
+        if self._value is None:
+            self._value = nn.Sequential.forward(self._module, self._x)
+        return self._value
+
+    def resolve(self, adj):
+        """-> TypedBonds holding module(distinct rows), or the dense tensor when the batch is not categorical"""
+        x = self._x
+        if (self._value is None and torch.is_tensor(adj) and adj.is_cuda and adj.dim() == 3
+                and tuple(adj.shape) == tuple(x.shape[:3])):
+            tb = graph.typed_bonds(x, adj)
+            if isinstance(tb, graph.TypedBonds):
+                return nn.Sequential.forward(self._module, tb)
+        return self.materialize()
+
+    @property
+    def shape(self):
+        return torch.Size(tuple(self._x.shape[:-1]) + (self._module.out_features(self._x.shape[-1]),))
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def unwrap(a):
+            if isinstance(a, DeferredRows):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(unwrap(v) for v in a)
+            return a
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
+           "__matmul__", "__getitem__", "__pow__", "__eq__", "__ne__", "__lt__", "__gt__", "__le__", "__ge__"):
+    setattr(DeferredRows, _n, _binop(_n))
+DeferredRows.__neg__ = lambda self: -self.materialize()
+DeferredRows.__hash__ = object.__hash__
+
+
+class RowwiseSequential(nn.Sequential):
+    """nn.Sequential of row-wise layers (Linear / activations).  On a dense [B,N,N,F] CUDA data tensor it returns a
+    `DeferredRows` handle (see there); on anything else it is the stock nn.Sequential."""
+
+    def out_features(self, f):
+        for m in self:
+            if isinstance(m, nn.Linear):
+                f = m.out_features
+        return f
+
+    def forward(self, x):
+        if (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and not x.requires_grad and x.dtype == torch.float32
+                and x.shape[1] == x.shape[2]):
+            return DeferredRows(self, x)
+        return super(RowwiseSequential, self).forward(x)
+
+
+class Autoencoder(nn.Module):
+    """reference mpnn_functions/encoders/auto_encoder.py (same layers and state_dict keys)"""
+
+    def __init__(self, in_dim=784, mid_dim=400, e_dim=20):
+        super(Autoencoder, self).__init__()
+        self.encoder = RowwiseSequential(nn.Linear(in_dim, mid_dim, bias=False), nn.Sigmoid(),
+                                         nn.Linear(mid_dim, e_dim, bias=False), nn.Sigmoid())
+        self.decoder = nn.Sequential(nn.Linear(e_dim, mid_dim, bias=False), nn.Sigmoid(),
+                                     nn.Linear(mid_dim, in_dim, bias=False), nn.Sigmoid())
+
+    def forward(self, x):
+        return self.decoder(self.encoder(x))
+
+
+class _TanhAutoEncoder(nn.Module):
+    def __init__(self, in_f, mid_f, out_f):
+        super(_TanhAutoEncoder, self).__init__()
+        self.encoder = RowwiseSequential(nn.Linear(in_f, mid_f, bias=False), nn.Tanh(), nn.Linear(mid_f, out_f))
+        self.decoder = nn.Sequential(nn.BatchNorm1d(out_f), nn.Linear(out_f, mid_f), nn.Tanh(),
+                                     nn.Linear(mid_f, in_f), nn.Sigmoid())
+
+    def forward(self, x):
+        return self.decoder(self.encoder(x))
+
+
+class AtomAutoEncoder(_TanhAutoEncoder):
+    """reference mpnn_functions/encoders/atom_autoencoder.py: 30 -> 15 -> 8"""
+
+    def __init__(self):
+        super(AtomAutoEncoder, self).__init__(30, 15, 8)
+
+
+class BondAutoEncoder(_TanhAutoEncoder):
+    """reference mpnn_functions/encoders/bond_autoencoder.py: 8 -> 4 -> 2"""
+
+    def __init__(self):
+        super(BondAutoEncoder, self).__init__(8, 4, 2)
+
+
+# =================================================================================================
 # aggregators
 # =================================================================================================
 def _as_dense(messages):
     if isinstance(messages, graph.TypedBonds):
         return messages.dense()
+    if isinstance(messages, DeferredRows):
+        return messages.materialize()
     return messages.materialize() if isinstance(messages, LazyMessages) else messages
 
 
@@ -493,15 +612,24 @@ class WAdjMsgAgg(nn.Module):
     def forward(self, messages, adj):
         if isinstance(messages, LazyMessages):
             def parts(el):
-                ew = torch.exp(el.edge_w)
+                # softmax over ALL N columns of the row (non-neighbours and padded atoms carry adj = 0): subtract the
+                # row maximum max(0, max_e w_e) like torch.softmax does, so large weighted adjacencies cannot overflow
+                w = el.edge_w
+                dst = el.edge_dst.long()
+                with torch.no_grad():
+                    mx = torch.zeros(el.n_rows, dtype=torch.float32, device=w.device)
+                    if w.numel():
+                        mx.scatter_reduce_(0, dst, w.detach(), "amax", include_self=True)
+                ew = torch.exp(w - mx[dst])
+                e0 = torch.exp(-mx)                       # weight of a zero entry of the row
                 deg = (el.row_ptr[1:] - el.row_ptr[:-1]).float()
                 Z = GatherSumFn.apply(ew.unsqueeze(1), el.row_ptr, None, el.n_rows, None, None).squeeze(1) \
-                    + (el.N - deg)
-                return ew, Z
+                    + (el.N - deg) * e0
+                return ew, Z, e0
             return messages.aggregate(
                 adj,
-                alpha_fn=lambda el: (lambda ew, Z: ew / Z[el.edge_dst.long()])(*parts(el)),
-                gamma_fn=lambda el: (1.0 / parts(el)[1]).unsqueeze(1))
+                alpha_fn=lambda el: (lambda ew, Z, e0: ew / Z[el.edge_dst.long()])(*parts(el)),
+                gamma_fn=lambda el: (lambda ew, Z, e0: (e0 / Z).unsqueeze(1))(*parts(el)))
         B, N, _ = adj.shape
         w = SoftmaxMulFn.apply(adj.reshape(B * N, N), None).view(B, N, N)
         return DenseAggFn.apply(messages, w)
@@ -599,6 +727,8 @@ class MaskBatchNorm(nn.Module):
         super(MaskBatchNorm, self).__init__()
 
     def forward(self, tensor, mask, eps=1e-6):
+        if isinstance(tensor, DeferredRows):
+            tensor = tensor.resolve(mask)
         if isinstance(tensor, graph.TypedBonds):
             def stats(x, a, c, M):   # mask_batch_norm.py:11-15 (unmasked sum for the mean)
                 mean = (c * x).sum(0) / M
@@ -631,6 +761,8 @@ class MaskBatchNorm1d(nn.BatchNorm1d):
         return _typed_mask_bn(tb, mask, stats)
 
     def forward(self, tensor, mask):
+        if isinstance(tensor, DeferredRows):
+            tensor = tensor.resolve(mask)
         if isinstance(tensor, graph.TypedBonds):
             out = self._typed_forward(tensor, mask)
             if out is not None:
@@ -668,6 +800,27 @@ class GraphLevelOutput(nn.Module):
                                         self.j[0].bias)
 
 
+class GraphLevelOutputAtoms(GraphLevelOutput):
+    """GraphLevelOutput with the reference's commented `return gated_activations` (graph_level_output.py:46) in place
+    of the sum over atoms (:47): the per-atom readout [B, N, O] that normed_encoded_basic_model_ecfp.py:70-71
+    (`self.obn(output, mask)`) and its driver (test_graph_encode_norm_ecfp.py:137) were written against.
+    Same parameters and state_dict keys; pass it as `readout_func=` to the unchanged ecfp model file."""
+
+    def forward(self, input_set, mask=None, mprev=None, cprev=None):
+        input_set = _as_dense(input_set)
+        if mask is None:
+            raise RuntimeError("mpnn_b200.GraphLevelOutputAtoms: the per-atom readout is defined with a mask "
+                               "(graph_level_output.py:33-36)")
+        if not input_set.is_cuda:
+            raise RuntimeError("mpnn_b200.GraphLevelOutputAtoms: CUDA tensors required (there is no CPU fallback)")
+        B, N, F2 = input_set.shape
+        m = mask.reshape(B * N, 1)
+        xm = input_set.reshape(B * N, F2) * m
+        u = LinearFn.apply(xm, self.i[0].weight, self.i[0].bias)
+        v = LinearFn.apply(xm, self.j[0].weight, self.j[0].bias)
+        return (SoftmaxMulFn.apply(u, v) * m).view(B, N, self.out_dim)
+
+
 class LSTMCellHidden(nn.Module):
     """Parameter holder of the input-less LSTM (reference set2vec.py:13-66): w_h{i,f,g,o} [hd, cd], b_h* [1, cd]."""
 
@@ -688,7 +841,10 @@ class LSTMCellHidden(nn.Module):
         return W, b
 
     def forward(self, hprev, cprev):
-        raise NotImplementedError("mpnn_b200.LSTMCellHidden is evaluated inside the fused Set2Vec kernels")
+        """set2vec.py:68-75: (hprev [B, hd], cprev [B, cd]) -> (h', c').  Inside Set2Vec the cell is evaluated by the
+        fused kernels; this is the stand-alone call of the exported class."""
+        W, b = self.cat_params()
+        return LSTMCellHiddenFn.apply(hprev, cprev, W, b)
 
 
 class Set2Vec(nn.Module):
@@ -711,7 +867,9 @@ class Set2Vec(nn.Module):
 
     def forward(self, input_set, mask=None, mprev=None, cprev=None):
         input_set = _as_dense(input_set)
-        if mprev is not None or cprev is not None:
-            raise NotImplementedError("mpnn_b200.Set2Vec: explicit mprev/cprev are not supported (no fallback)")
         W, b = self.lstmcell.cat_params()
-        return Set2VecFn.apply(input_set, mask, W, b, self.q_attn.weight, self.e_attn.weight.reshape(-1), self.steps)
+        m0 = None
+        if mprev is not None:   # set2vec.py:113-114: the caller's [B, F] state is padded with a zero read vector
+            m0 = torch.cat([mprev, torch.zeros_like(mprev)], dim=1)
+        return Set2VecFn.apply(input_set, mask, W, b, self.q_attn.weight, self.e_attn.weight.reshape(-1), self.steps,
+                               m0, cprev)

@@ -1,3 +1,3 @@
-from ...modules import GraphLevelOutput, LSTMCellHidden, Set2Vec  # noqa: F401
+from ...modules import GraphLevelOutput, GraphLevelOutputAtoms, LSTMCellHidden, Set2Vec  # noqa: F401
 
 __all__ = ["GraphLevelOutput", "LSTMCellHidden", "Set2Vec"]

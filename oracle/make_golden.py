@@ -47,12 +47,23 @@ def _perturb_biases(module, seed):
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
 
 
-def save_case(name, inputs, module_sd, outputs, cot, gin, gsd, meta):
+def save_case(name, inputs, module_sd, outputs, cot, gin, gsd, meta, dedup_aliases=False):
     arrs = {}
     for k, v in inputs.items():
         arrs["in." + k] = v.detach().numpy()
+    first = {}
+    aliases = {}
     for k, v in module_sd.items():
+        if dedup_aliases and ".0.weight" in k and "edge_map" in k:
+            # the 50 tied layers are ONE tensor under 50 keys (edge_network.py:20): store it once, list the aliases
+            key = (k.split("edge_map")[0], tuple(v.shape), v.detach().numpy().tobytes())
+            if key in first:
+                aliases[k] = first[key]
+                continue
+            first[key] = k
         arrs["sd." + k] = v.detach().numpy()
+    if aliases:
+        meta = dict(meta, sd_aliases=aliases)
     for k, v in outputs.items():
         arrs["out." + k] = v.detach().numpy()
     if cot is not None:
@@ -66,7 +77,7 @@ def save_case(name, inputs, module_sd, outputs, cot, gin, gsd, meta):
     print("wrote %-28s %6.1f KB" % (name, os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1024))
 
 
-def run_case(name, module, fwd, inputs, grad_inputs, meta, seed=0, extra_out=None):
+def run_case(name, module, fwd, inputs, grad_inputs, meta, seed=0, extra_out=None, dedup_aliases=False):
     """fwd(module, **inputs) -> tensor; records grads of `grad_inputs` and all trainable params."""
     ins = {k: _t(v, k in grad_inputs) for k, v in inputs.items()}
     sd0 = {k: v.clone() for k, v in module.state_dict().items()}
@@ -82,7 +93,16 @@ def run_case(name, module, fwd, inputs, grad_inputs, meta, seed=0, extra_out=Non
     outs = {"y": out}
     if extra_out:
         outs.update(extra_out(module))
-    save_case(name, ins, sd0, outs, cot, gin, gsd, meta)
+    if dedup_aliases:   # gradients of the aliased keys are one tensor too
+        seen, keep = {}, {}
+        for k, v in gsd.items():
+            key = (tuple(v.shape), v.numpy().tobytes()) if (".0.weight" in k and "edge_map" in k) else k
+            if key in seen:
+                continue
+            seen[key] = k
+            keep[k] = v
+        gsd = keep
+    save_case(name, ins, sd0, outs, cot, gin, gsd, meta, dedup_aliases=dedup_aliases)
     return ins, sd0, out, cot, gin, gsd
 
 
@@ -98,11 +118,87 @@ def make_bilinear(ref):
              dict(cls="BiLiniearEdgeNetwork", nf=nf, ef=nf ** 3, mf=nf))
 
 
+def make_round2(ref):
+    """Fixtures added in round 2 (the round-1 files are left untouched): the exported LSTM cell, Set2Vec with a
+    caller-supplied initial state, the per-atom readout + BASELINE config 4's ecfp model, and compositions at widths the
+    tensor-core kernels serve (d = 64 / 40) plus config 3's shape (d = 32, Set2Vec x 100)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from mpnn_b200 import synthetic
+    torch.set_num_threads(4)
+    # LSTMCellHidden.forward (set2vec.py:68-75)
+    rs = np.random.RandomState(41)
+    torch.manual_seed(317)
+    m = ref.LSTMCellHidden(12, 6)
+    _perturb_biases(m, 15)
+    run_case("readout_LSTMCellHidden", m, lambda mod, hprev, cprev: torch.cat(mod(hprev, cprev), dim=1),
+             dict(hprev=rs.normal(size=(5, 12)).astype(np.float32), cprev=rs.normal(size=(5, 6)).astype(np.float32)),
+             ("hprev", "cprev"), dict(cls="LSTMCellHidden", hd=12, cd=6))
+    # Set2Vec with explicit mprev / cprev (set2vec.py:110-116)
+    batch = synthetic.small_batch(B=4, n_lo=1, n_hi=7, afm_width=6, ef=3, seed=24)
+    torch.manual_seed(317)
+    m = ref.Set2Vec(3, 99, time_steps=5)
+    _perturb_biases(m, 10)
+    run_case("readout_Set2Vec_init", m,
+             lambda mod, input_set, mask, mprev, cprev: mod(input_set, mask=mask, mprev=mprev, cprev=cprev),
+             dict(input_set=batch["afm"] * batch["mask"], mask=batch["mask"],
+                  mprev=rs.normal(size=(4, 6)).astype(np.float32), cprev=rs.normal(size=(4, 6)).astype(np.float32)),
+             ("input_set", "mprev", "cprev"), dict(cls="Set2Vec", nf=3, steps=5))
+    # per-atom readout (graph_level_output.py:46)
+    batch = synthetic.small_batch(B=4, n_lo=1, n_hi=7, afm_width=10, ef=3, seed=23)
+    torch.manual_seed(317)
+    m = ref.GraphLevelOutputD(5, 7)
+    _perturb_biases(m, 9)
+    run_case("readout_GraphLevelOutputAtoms", m, lambda mod, input_set, mask: mod(input_set, mask=mask),
+             dict(input_set=batch["afm"], mask=batch["mask"]), ("input_set",),
+             dict(cls="GraphLevelOutputAtoms", nf=5, out=7))
+    # BASELINE config 4: normed_encoded_basic_model_ecfp (no ma_bn, obn on the per-atom readout)
+    rawb = synthetic.small_batch(B=4, n_lo=1, n_hi=7, afm_width=30, ef=8, seed=32)
+    torch.manual_seed(317)
+    mod = ref.normed_encoded_basic_model_ecfp.BasicModel(
+        8, 2, 8, 1, 5, message_func=ref.EdgeNetworkD, message_opts={}, agg_opts={}, update_opts={},
+        readout_func=ref.GraphLevelOutputD, readout_opts={}, message_steps=2,
+        atom_encoder=ref.AtomAutoEncoder().encoder, bond_encoder=ref.BondAutoEncoder().encoder)
+    mod.apply(_kaiming)
+    _perturb_biases(mod, 14)
+    mod.train()
+    run_case("model_normed_encoded_ecfp", mod, lambda mm, afm, bfm, adj, mask: mm(afm, bfm, adj, mask),
+             dict(afm=rawb["afm"], bfm=rawb["bfm"], adj=rawb["adj"], mask=rawb["mask"]), ("afm",),
+             dict(cls="normed_encoded_basic_model_ecfp.BasicModel", d=8, ef=2, out=5, steps=2),
+             extra_out=lambda mm: {"obn.running_mean": mm.obn.running_mean.clone(),
+                                   "obn.running_var": mm.obn.running_var.clone(),
+                                   "bebn.running_mean": mm.bebn.running_mean.clone(),
+                                   "bebn.running_var": mm.bebn.running_var.clone()})
+
+    # ---- tensor-core widths (d > 32) and config 3's shape --------------------------------------------------------
+    def tier_d(name, ctor, d, ef, out, fwd_name="forward", seed=33, B=3, n_hi=7, **kw):
+        batch = synthetic.small_batch(B=B, n_lo=2, n_hi=n_hi, afm_width=d, ef=ef, seed=seed)
+        torch.manual_seed(317)
+        mod = ctor(d, ef, d, 1, out, message_opts={}, agg_opts={}, update_opts={}, **kw)
+        mod.apply(_kaiming)
+        _perturb_biases(mod, 12)
+        mod.train()
+        meta = dict(cls=name.split("_d")[0], d=d, ef=ef, out=out)
+        meta.update({k: (v if isinstance(v, (int, float, dict)) else str(v)) for k, v in kw.items()})
+        run_case(name, mod, lambda mm, afm, bfm, adj, mask: getattr(mm, fwd_name)(afm, bfm, adj, mask),
+                 dict(afm=batch["afm"], bfm=batch["bfm"], adj=batch["adj"], mask=batch["mask"]), ("afm",), meta,
+                 dedup_aliases=True)
+
+    tier_d("model_autoencoder_encode_d64", ref.basic_graph_autoencoder.Encoder, 64, 8, 128, fwd_name="encode",
+           message_func=ref.EdgeNetworkD, message_steps=3, readout_opts={})
+    tier_d("model_basic_d40", ref.basic_model.BasicModel, 40, 7, 24, message_func=ref.EdgeNetworkD, message_steps=3,
+           readout_opts={})
+    tier_d("model_att_d32", ref.att_model.BasicModel, 32, 8, 9, message_func=ref.AttEdgeNetworkD,
+           message_agg_func=ref.AdjMsgAgg, message_steps=3, readout_opts={"time_steps": 100})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
     if len(sys.argv) > 1 and sys.argv[1] == "bilinear":     # only the fixture added after the first freeze
         make_bilinear(ref)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":       # fixtures added in round 2 (see make_round2)
+        make_round2(ref)
         return
     sys.path.insert(0, os.path.dirname(HERE))
     from mpnn_b200 import synthetic  # host-side numpy only
@@ -299,6 +395,7 @@ def main():
                         **{k: coll[k].numpy() for k in ("afm", "nafm", "bfm", "adj", "mask")},
                         sizes=np.array([g["afm"].shape[0] for g in graphs]))
     print("collate_2d_graphs == synthetic.collate : OK")
+    make_round2(ref)
 
 
 if __name__ == "__main__":

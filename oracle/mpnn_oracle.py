@@ -209,6 +209,16 @@ def graph_level_output(x, mask, sd, prefix):
     return g.sum(dim=1)                                                                    # :47
 
 
+def graph_level_output_atoms(x, mask, sd, prefix):
+    """GraphLevelOutput with the commented `return gated_activations` (graph_level_output.py:46) instead of :47: the
+    per-atom readout [B,N,O] that normed_encoded_basic_model_ecfp.py:70-71 and its driver
+    (test_graph_encode_norm_ecfp.py:137) were written against."""
+    lin = torch.nn.functional.linear
+    xm = x * mask
+    return (torch.softmax(lin(xm, sd[prefix + "i.0.weight"], sd[prefix + "i.0.bias"]), dim=-1)
+            * lin(xm, sd[prefix + "j.0.weight"], sd[prefix + "j.0.bias"]) * mask)           # :36, :46
+
+
 def lstm_cell_hidden(hprev, cprev, sd, prefix):
     """LSTMCellHidden.forward (set2vec.py:68-75)."""
     i = torch.sigmoid(hprev.matmul(sd[prefix + "w_hi"]) + sd[prefix + "b_hi"])
@@ -219,11 +229,14 @@ def lstm_cell_hidden(hprev, cprev, sd, prefix):
     return o * torch.tanh(cprime), cprime
 
 
-def set2vec(x, mask, sd, prefix, steps=100):
+def set2vec(x, mask, sd, prefix, steps=100, mprev=None, cprev=None):
     """Set2Vec.forward, inner_prod="default" (set2vec.py:93-151); softmax over ALL B*N rows (:139)."""
     B, N, F = x.shape
-    mprev = torch.zeros(B, 2 * F, dtype=x.dtype)                                          # :110-113
-    cprev = torch.zeros(B, F, dtype=x.dtype)                                              # :114-116
+    if mprev is None:
+        mprev = torch.zeros(B, F, dtype=x.dtype)                                          # :110-111
+    mprev = torch.cat([mprev, torch.zeros(B, F, dtype=x.dtype)], dim=1)                   # :113
+    if cprev is None:
+        cprev = torch.zeros(B, F, dtype=x.dtype)                                          # :114-116
     neg = (1 - mask) * _BIG_NEGATIVE if mask is not None else None                        # :120-121
     m = mprev
     for _ in range(steps):
@@ -299,7 +312,16 @@ def _encoder(x, sd, prefix):
     return torch.nn.functional.linear(h, sd[prefix + "2.weight"], sd[prefix + "2.bias"])
 
 
-def normed_encoded_model(afm, bfm, adj, mask, sd, prefix="", steps=3, buffers=None, training=True, ma_bn=True):
+def normed_encoded_ecfp_model(afm, bfm, adj, mask, sd, prefix="", steps=3, buffers=None, training=True):
+    """normed_encoded_basic_model_ecfp.BasicModel.forward (:65-71) with the per-atom readout its `obn(output, mask)`
+    call needs (graph_level_output.py:46): BASELINE config 4."""
+    y = normed_encoded_model(afm, bfm, adj, mask, sd, prefix, steps, buffers, training, ma_bn=False,
+                             readout=graph_level_output_atoms)
+    return mask_batch_norm_1d(y, mask, sd, prefix + "obn.", training, buffers=buffers)    # :71
+
+
+def normed_encoded_model(afm, bfm, adj, mask, sd, prefix="", steps=3, buffers=None, training=True, ma_bn=True,
+                         readout=None):
     """normed_encoded_basic_model.BasicModel.forward (:67-72; ma_bn=True) and the message-passing part of
     normed_encoded_basic_model_ecfp.BasicModel.forward (:65-70; ma_bn=False -- its trailing `obn` call on the
     [B,O] output, :71, is shape-inconsistent at HEAD, SURVEY §2.3, and is left to the caller)."""
@@ -314,7 +336,7 @@ def normed_encoded_model(afm, bfm, adj, mask, sd, prefix="", steps=3, buffers=No
             agg = mask_batch_norm_1d(agg, mask, sd, prefix + "ma_bn%d." % t, training, buffers=buffers)
         node_state = mask_batch_norm_1d(gru_update(agg, node_state, mask, sd, prefix + "uf."), mask, sd,
                                         prefix + "bn%d." % t, training, buffers=buffers)
-    return graph_level_output(torch.cat([node_state, afm], dim=-1), mask, sd, prefix + "of.")
+    return (readout or graph_level_output)(torch.cat([node_state, afm], dim=-1), mask, sd, prefix + "of.")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -346,7 +368,3 @@ def count_params(sd):
             seen.add(v.data_ptr())
             total += v.numel()
     return total
-
-
-def _unused():  # keep math imported for downstream users of this module
-    return math.pi

@@ -110,6 +110,17 @@ def load():
         def _precompute_edge_embed(self, bfm):
             self.edge_embed = self.edge_map(bfm).view(bfm.shape[:3] + (self.mf, self.nf))
 
+    GraphLevelOutput = names["GraphLevelOutput"]
+
+    class GraphLevelOutputD(GraphLevelOutput):
+        """graph_level_output.py:36 followed by the commented `return gated_activations` (:46) instead of the sum
+        (:47): the per-atom readout normed_encoded_basic_model_ecfp.py:70-71 needs for `obn(output, mask)`."""
+
+        def forward(self, input_set, mask=None, mprev=None, cprev=None):
+            import torch
+            return torch.nn.Softmax(dim=-1)(self.i(input_set * mask)) * self.j(input_set * mask) * mask
+
+    names["GraphLevelOutputD"] = GraphLevelOutputD
     names["EdgeNetworkD"] = EdgeNetworkD
     names["AttEdgeNetworkD"] = AttEdgeNetworkD
     _loaded.update(names)

@@ -32,6 +32,8 @@ class Case(object):
             elif head == "gsd":
                 self.gsd[rest] = torch.from_numpy(z[k])
         self.cot = torch.from_numpy(z["cot"]) if "cot" in z.files else None
+        for alias, first in self.meta.get("sd_aliases", {}).items():   # the 50 tied layers, stored once
+            self.sd[alias] = self.sd[first]
 
 
 def all_cases(prefix=""):
@@ -86,17 +88,26 @@ def oracle_forward(case, ins, sd, buffers=None):
                                     buffers=buffers)
     if cls == "GraphLevelOutput":
         return O.graph_level_output(ins["input_set"], ins.get("mask"), sd, "")
+    if cls == "GraphLevelOutputAtoms":
+        return O.graph_level_output_atoms(ins["input_set"], ins["mask"], sd, "")
+    if cls == "LSTMCellHidden":
+        return torch.cat(O.lstm_cell_hidden(ins["hprev"], ins["cprev"], sd, ""), dim=1)
     if cls == "Set2Vec":
-        return O.set2vec(ins["input_set"], ins["mask"], sd, "", steps=m["steps"])
+        return O.set2vec(ins["input_set"], ins["mask"], sd, "", steps=m["steps"], mprev=ins.get("mprev"),
+                         cprev=ins.get("cprev"))
     a = (ins["afm"], ins["bfm"], ins["adj"], ins["mask"])
     if cls == "lipo_basic_model.BasicModel":
         return O.lipo_model(*a, sd=sd, steps=m["steps"], buffers=buffers)
     if cls == "model_basic":
-        return O.basic_model(*a, sd=sd, steps=3)
+        return O.basic_model(*a, sd=sd, steps=int(m.get("message_steps", 3)))
     if cls == "model_normed_basic":
         return O.normed_basic_model(*a, sd=sd, steps=2)
     if cls == "model_autoencoder_encode":
-        return O.basic_model(*a, sd=sd, steps=2, chain_state=False)
+        return O.basic_model(*a, sd=sd, steps=int(m.get("message_steps", 2)), chain_state=False)
+    if cls == "model_att":
+        return O.att_model(*a, sd=sd, steps=int(m["message_steps"]), s2v_steps=m["readout_opts"]["time_steps"], agg="adj")
+    if cls == "normed_encoded_basic_model_ecfp.BasicModel":
+        return O.normed_encoded_ecfp_model(*a, sd=sd, steps=m["steps"], buffers=buffers)
     if cls == "att_model.BasicModel":
         return O.att_model(*a, sd=sd, steps=m["steps"], s2v_steps=m["s2v_steps"],
                            agg="adj" if m["agg"] == "AdjMsgAgg" else "att")

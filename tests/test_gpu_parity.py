@@ -36,7 +36,8 @@ def _cuda_inputs(case, dev, grad_keys):
     return ins
 
 
-def _check_grads(module, case, ins, grad_keys, skip_params=()):
+def _check_grads(module, case, ins, grad_keys, skip_params=(), tol=None):
+    TOL_GRAD = tol if tol is not None else globals()["TOL_GRAD"]
     for k in grad_keys:
         assert rel_err(ins[k].grad.cpu(), case.gin[k]) <= TOL_GRAD, "grad of input %s" % k
     params = dict(module.named_parameters())
@@ -115,6 +116,10 @@ def _build(case, dev):
         mod = M.MaskBatchNorm1d(case.inputs["tensor"].shape[-1])
     elif cls == "GraphLevelOutput":
         mod = M.GraphLevelOutput(m["nf"], m["out"])
+    elif cls == "GraphLevelOutputAtoms":
+        mod = M.GraphLevelOutputAtoms(m["nf"], m["out"])
+    elif cls == "LSTMCellHidden":
+        mod = M.LSTMCellHidden(m["hd"], m["cd"])
     elif cls == "Set2Vec":
         mod = M.Set2Vec(m["nf"], 99, time_steps=m["steps"])
     else:
@@ -149,10 +154,12 @@ def test_module_matches_reference_golden(dev, name):
         out = mod(ins["messages"], ins["node_states"], ins["mask"])
     elif cls in ("MaskBatchNorm", "MaskBatchNorm1d"):
         out = mod(ins["tensor"], ins["mask"])
-    elif cls == "GraphLevelOutput":
+    elif cls in ("GraphLevelOutput", "GraphLevelOutputAtoms"):
         out = mod(ins["input_set"], mask=ins.get("mask"))
+    elif cls == "LSTMCellHidden":
+        out = torch.cat(mod(ins["hprev"], ins["cprev"]), dim=1)
     elif cls == "Set2Vec":
-        out = mod(ins["input_set"], mask=ins["mask"])
+        out = mod(ins["input_set"], mask=ins["mask"], mprev=ins.get("mprev"), cprev=ins.get("cprev"))
     assert out.shape == case.out["y"].shape
     assert rel_err(out.detach().cpu(), case.out["y"]) <= TOL_OUT
     (out * case.cot.to(dev)).sum().backward()
@@ -227,26 +234,35 @@ def test_fused_message_aggregation(dev, name, agg):
 # ------------------------------------------------------------------------------------------------
 def _model_for(case, dev):
     from mpnn_b200 import modules as M
-    from mpnn_b200.callers import MessagePassingModel
+    from mpnn_b200.dropin import reference_model as MessagePassingModel
     m = case.meta
     cls = m["cls"]
     if cls == "lipo_basic_model.BasicModel":
         mod = MessagePassingModel("lipo", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=m["steps"])
     elif cls == "model_basic":
-        mod = MessagePassingModel("basic", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=3)
+        mod = MessagePassingModel("basic", m["d"], m["ef"], m["d"], 1, m["out"],
+                                  message_steps=int(m.get("message_steps", 3)))
     elif cls == "model_normed_basic":
         mod = MessagePassingModel("normed", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=2)
     elif cls == "model_autoencoder_encode":
-        mod = MessagePassingModel("autoencoder", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=2)
+        mod = MessagePassingModel("autoencoder", m["d"], m["ef"], m["d"], 1, m["out"],
+                                  message_steps=int(m.get("message_steps", 2)))
+    elif cls == "model_att":
+        mod = MessagePassingModel("att", m["d"], m["ef"], m["d"], 1, m["out"], message_func=M.AttEdgeNetwork,
+                                  message_agg_func=M.AdjMsgAgg, message_steps=int(m["message_steps"]),
+                                  readout_func=M.Set2Vec, readout_opts=dict(m["readout_opts"]))
+    elif cls == "normed_encoded_basic_model_ecfp.BasicModel":
+        # BASELINE config 4: the unchanged ecfp model file + the drop-in encoders + the per-atom readout its obn needs
+        mod = MessagePassingModel("normed_encoded_ecfp", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=m["steps"],
+                                  readout_func=M.GraphLevelOutputAtoms, atom_encoder=M.AtomAutoEncoder().encoder,
+                                  bond_encoder=M.BondAutoEncoder().encoder)
     elif cls == "att_model.BasicModel":
         mod = MessagePassingModel("att", m["d"], m["ef"], m["d"], 1, 9, message_func=M.AttEdgeNetwork,
                                   message_agg_func=getattr(M, m["agg"]), message_steps=m["steps"],
                                   readout_func=M.Set2Vec, readout_opts={"time_steps": m["s2v_steps"]})
     elif cls == "normed_encoded_basic_model.BasicModel":
-        ae = nn.Sequential(nn.Linear(30, 15, bias=False), nn.Tanh(), nn.Linear(15, 8))
-        be = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
         mod = MessagePassingModel("normed_encoded", m["d"], m["ef"], m["d"], 1, m["out"], message_steps=m["steps"],
-                                  atom_encoder=ae, bond_encoder=be)
+                                  atom_encoder=M.AtomAutoEncoder().encoder, bond_encoder=M.BondAutoEncoder().encoder)
     else:
         raise KeyError(cls)
     missing = mod.load_state_dict(case.sd, strict=True)
@@ -254,21 +270,32 @@ def _model_for(case, dev):
     return mod.to(dev)
 
 
+# widths > 32 run on the tcgen05 kernels: TF32 operands (fp32 accumulate) in the message / GRU / readout GEMMs and
+# tanh.approx gates; SURVEY 8c allows 2e-2 for tensor-core inputs, the tests hold 3e-3 (forward) / 1e-2 (gradients)
+TOL_OUT_TC = 3e-3
+TOL_GRAD_TC = 1e-2
+
+
 @pytest.mark.parametrize("name", all_cases("model_"))
 def test_model_matches_reference_golden(dev, name):
+    """The UNMODIFIED reference model files (tests/ref_models/models/*.py, loaded through mpnn_b200.dropin) executing
+    forward + backward on the CUDA modules, against outputs / gradients / running statistics frozen from the reference
+    itself (oracle/make_golden.py)."""
     case = Case(name)
     mod = _model_for(case, dev)
     mod.train()
+    wide = case.meta["d"] > 32
+    tol_out, tol_grad = (TOL_OUT_TC, TOL_GRAD_TC) if wide else (TOL_OUT, TOL_GRAD)
     ins = _cuda_inputs(case, dev, ["afm"])
     out = mod(ins["afm"], ins["bfm"], ins["adj"], ins["mask"])
     assert out.shape == case.out["y"].shape
-    assert rel_err(out.detach().cpu(), case.out["y"]) <= TOL_OUT
+    assert rel_err(out.detach().cpu(), case.out["y"]) <= tol_out
     (out * case.cot.to(dev)).sum().backward()
-    _check_grads(mod, case, ins, ["afm"])
+    _check_grads(mod, case, ins, ["afm"], tol=tol_grad)
     sd_now = mod.state_dict()
     for k, v in case.out.items():
         if k.endswith("running_mean") or k.endswith("running_var"):
-            assert rel_err(sd_now[k].cpu(), v) <= TOL_OUT, k
+            assert rel_err(sd_now[k].cpu(), v) <= tol_out, k
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,7 +309,7 @@ def _oracle_sd(mod):
 @pytest.mark.parametrize("cfg", ["lipo", "qm9"])
 def test_config_shaped_against_oracle(dev, cfg):
     from mpnn_b200 import synthetic
-    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
     from oracle import mpnn_oracle as O
     torch.manual_seed(317)
     if cfg == "lipo":
@@ -321,7 +348,7 @@ def test_full_size_properties(dev):
     """BASELINE config 2 at full size (B=256): run-to-run bit-identical, masked rows exactly zero, graphs
     independent (BN-free variant): permuting the batch permutes the outputs."""
     from mpnn_b200 import synthetic, graph
-    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
     torch.manual_seed(317)
     batch = synthetic.make_batch("qm9")
     t = {k: torch.from_numpy(batch[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
@@ -406,3 +433,29 @@ def test_bilinear_fused_with_aggregators(dev, agg):
     assert rel_err(a1.grad.cpu(), a0.grad) <= TOL_GRAD
     on_edges = (bfm != 0).any(-1, keepdim=True).float()      # WAdjMsgAgg also weights the all-zero rows: see above
     assert rel_err(b1.grad.cpu() * on_edges, b0.grad * on_edges) <= TOL_GRAD
+
+
+def test_wadj_large_weights_do_not_overflow(dev):
+    """WAdjMsgAgg on lazy messages subtracts the row maximum like the reference's softmax
+    (weighted_adjacent_message_agg.py:20): adjacency values of ~150 (exp overflows fp32 at 88.7) stay finite and equal
+    to the oracle."""
+    from mpnn_b200 import modules as M, synthetic
+    from oracle import mpnn_oracle as O
+    case = Case("msg_EdgeNetworkD_g1")
+    m = case.meta
+    batch = synthetic.small_batch(B=3, n_lo=1, n_hi=6, afm_width=m["nf"], ef=m["ef"], seed=11, weighted_adj=True)
+    adj = torch.from_numpy(batch["adj"]) * 100.0
+    net = M.EdgeNetwork(m["nf"], m["ef"], m["mf"])
+    net.load_state_dict(case.sd, strict=True)
+    net = net.to(dev)
+    afm = case.inputs["afm"].clone().to(dev).requires_grad_(True)
+    out = M.WAdjMsgAgg(1)(net(afm, case.inputs["bfm"].to(dev)), adj.to(dev))
+    assert bool(torch.isfinite(out).all())
+    sd = leaf_sd(case.sd)
+    a = case.inputs["afm"].clone().requires_grad_(True)
+    ref = O.wadj_msg_agg(O.edge_network_pairs(a, case.inputs["bfm"], sd, "", m["mf"]), adj)
+    assert rel_err(out.detach().cpu(), ref.detach()) <= TOL_OUT
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    (out * cot.to(dev)).sum().backward()
+    (ref * cot).sum().backward()
+    assert rel_err(afm.grad.cpu(), a.grad) <= TOL_GRAD

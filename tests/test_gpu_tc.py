@@ -225,7 +225,7 @@ def test_config5_full_size_properties(dev, cfg):
     size-independent properties.  Run-to-run bit-identical (no atomics anywhere), graphs independent (permuting the
     batch permutes the outputs, within the TF32 summation-order noise), padded atoms contribute nothing to the readout."""
     from mpnn_b200 import synthetic, graph
-    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
     B, d = cfg
     torch.manual_seed(317)
     batch = synthetic.make_batch("autoenc", B=B, d=d)

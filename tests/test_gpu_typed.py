@@ -78,7 +78,7 @@ def test_dedup_continuous_rows_and_capacity_mode(dev):
 
 def _net(nf, ef, mf, dev, seed):
     from mpnn_b200 import modules as M
-    from mpnn_b200.callers import kaiming_init
+    from mpnn_b200.dropin import kaiming_init
     torch.manual_seed(seed)
     net = M.EdgeNetwork(nf, ef, mf)
     net.apply(kaiming_init)
@@ -216,7 +216,7 @@ def test_sibling_table_prefetch_is_transparent(dev):
     ahead of time on the side stream when mf_0 first sees the batch.  Outputs and every gradient must be bit-identical
     to the run with the prefetch switched off, and match the CPU oracle."""
     from mpnn_b200 import graph, modules as M, synthetic
-    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+    from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
     from oracle import mpnn_oracle as O
     from golden_util import leaf_sd
     torch.manual_seed(5)

@@ -120,14 +120,17 @@ def test_masked_bn_in_row_space(dev, kind, weighted):
         assert rel_err(a.float(), b.float()) <= TOL_OUT
 
 
-def _encoded_model(dev, steps=3, d=8):
-    from mpnn_b200.callers import MessagePassingModel, kaiming_init
+def _encoded_model(dev, steps=3, d=8, typed=True):
+    """the UNCHANGED reference model file (tests/ref_models/models/normed_encoded_basic_model.py) with the drop-in bond
+    encoder (`typed`: mpnn_b200's RowwiseSequential, as `BondAutoEncoder().encoder`) or a stock nn.Sequential"""
+    from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
+    from mpnn_b200.modules import RowwiseSequential
     # seed 1: a well-conditioned draw.  With kaiming-initialised 50-layer trunks of width 16 some draws (317 is one)
     # amplify so much that O(100) gradient entries are round-off in BOTH fp32 paths (tools/diag_typed_bonds.py
     # prints row-space / dense / fp64-oracle errors for several seeds: the row-space path is the closer one on average)
     torch.manual_seed(1)
     ae = nn.Sequential(nn.Linear(30, 15, bias=False), nn.Tanh(), nn.Linear(15, d))
-    be = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
+    be = (RowwiseSequential if typed else nn.Sequential)(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
     mod = MessagePassingModel("normed_encoded", d, 2, d, 1, 16, message_steps=steps, atom_encoder=ae, bond_encoder=be)
     mod.apply(kaiming_init)
     return mod.to(dev).train()
@@ -139,15 +142,14 @@ def test_encoded_model_row_space_equals_dense(dev, weighted, monkeypatch):
     gradients of this stack are sums with heavy cancellation (every Linear sits in front of a batch norm), and the two
     paths add in a different order (per distinct row vs per edge), so both are judged against the fp64 oracle: the
     row-space path must be within tolerance of it, or at least as close to it as the dense path is."""
-    from mpnn_b200 import callers, graph
+    from mpnn_b200 import graph
     from oracle import mpnn_oracle as O
     from golden_util import leaf_sd
     t = _affinity_batch(32, dev, weighted)
     res = []
     for typed in (True, False):
-        monkeypatch.setattr(callers, "TYPED_BONDS", typed)
         graph.clear_cache()
-        mod = _encoded_model(dev)
+        mod = _encoded_model(dev, typed=typed)
         sd0 = {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
         afm = t["afm"].clone().requires_grad_(True)
         out = mod(afm, t["bfm"], t["adj"], t["mask"])
@@ -179,24 +181,33 @@ def test_encoded_model_row_space_equals_dense(dev, weighted, monkeypatch):
 
 
 def test_reference_model_file_usage(dev):
-    """the UNCHANGED reference loop (normed_encoded_basic_model.py:67-72) handed a TypedBonds in place of bfm"""
+    """the UNCHANGED reference model file (normed_encoded_basic_model.py:67-72): (a) with the drop-in encoder the bond
+    tensor is resolved to row space inside `bebn` without the caller doing anything; (b) a stock encoder handed a
+    TypedBonds in place of bfm; both equal the dense evaluation"""
     from mpnn_b200 import graph
+    from mpnn_b200 import modules as M
     t = _affinity_batch(16, dev)
-    mod = _encoded_model(dev)
+    mod = _encoded_model(dev, typed=False).eval()
+    auto = _encoded_model(dev, typed=True).eval()
+    auto.load_state_dict(mod.state_dict())
+    seen = []
+    orig = M.MaskBatchNorm1d._typed_forward
 
-    def reference_forward(m, afm, bfm, adj, mask):
-        afm = m.aebn(m.ae(afm), mask)
-        bfm = m.bebn(m.be(bfm), adj)
-        node_state = afm
-        for mf, bn, ma_bn in zip(m.mfs, m.bns, m.ma_bns):
-            node_state = bn(m.uf(ma_bn(m.ma(mf(afm, bfm), adj), mask), node_state, mask), mask)
-        return m.of(torch.cat([node_state, afm], dim=-1), mask=mask)
+    def spy(self, tb, mask):
+        seen.append(type(tb).__name__)
+        return orig(self, tb, mask)
 
-    mod.eval()
     with torch.no_grad():
-        y_dense = reference_forward(mod, t["afm"], t["bfm"], t["adj"], t["mask"])
-        y_typed = reference_forward(mod, t["afm"], graph.typed_bonds(t["bfm"], t["adj"]), t["adj"], t["mask"])
+        y_dense = mod(t["afm"], t["bfm"], t["adj"], t["mask"])
+        y_typed = mod(t["afm"], graph.typed_bonds(t["bfm"], t["adj"]), t["adj"], t["mask"])
+        M.MaskBatchNorm1d._typed_forward = spy
+        try:
+            y_auto = auto(t["afm"], t["bfm"], t["adj"], t["mask"])
+        finally:
+            M.MaskBatchNorm1d._typed_forward = orig
     assert rel_err(y_typed, y_dense) <= TOL_OUT
+    assert rel_err(y_auto, y_dense) <= TOL_OUT
+    assert seen == ["TypedBonds"], "the drop-in encoder did not hand the bond rows to bebn in row space"
 
 
 def test_wrong_adjacency_is_rejected(dev):

@@ -149,7 +149,7 @@ print("ok")
 
 
 def test_model_state_dict_contract():
-    from mpnn_b200.callers import MessagePassingModel
+    from mpnn_b200.dropin import reference_model as MessagePassingModel
     case = Case("model_lipo")
     mod = MessagePassingModel("lipo", case.meta["d"], case.meta["ef"], case.meta["d"], 1, case.meta["out"],
                               message_steps=3)
@@ -236,3 +236,69 @@ def test_ragged_batch_matches_host_collate():
     assert np.array_equal(rb.edge_x.numpy(), b["bfm"][bb, ii, jj])
     padded = sum(b[k].nbytes for k in ("afm", "bfm", "adj", "mask"))
     assert rb.nbytes() < padded / 4
+
+
+def test_vendored_model_files_are_the_unmodified_reference():
+    """tests/ref_models/models/*.py are byte-identical copies of the reference's model files (clients of the boundary,
+    test fixtures only): checked against the committed SHA256SUMS always, and against /root/reference when present."""
+    import hashlib
+    d = os.path.join(ROOT, "tests", "ref_models")
+    sums = dict(reversed(line.split()) for line in open(os.path.join(d, "SHA256SUMS")) if line.strip())
+    files = sorted(f for f in os.listdir(os.path.join(d, "models")) if f.endswith(".py"))
+    assert files == sorted(sums), (files, sorted(sums))
+    for f in files:
+        data = open(os.path.join(d, "models", f), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == sums[f], f
+        ref = os.path.join("/root/reference/models", f)
+        if os.path.exists(ref):
+            assert open(ref, "rb").read() == data, "%s differs from the reference" % f
+
+
+def test_dropin_loads_every_model_file():
+    """dropin.reference_models(): every vendored model file imports against this package and constructs (CPU)"""
+    from mpnn_b200 import dropin, modules
+    ns = dropin.reference_models()
+    for variant, (fname, cls, _) in dropin.MODEL_FILES.items():
+        assert hasattr(ns, fname), fname
+        kw = {}
+        if variant.startswith("normed_encoded"):
+            kw = dict(atom_encoder=modules.AtomAutoEncoder().encoder, bond_encoder=modules.BondAutoEncoder().encoder)
+        d, ef = (8, 2) if kw else (16, 7)
+        m = dropin.reference_model(variant, d, ef, d, 1, 12, **kw)
+        assert any(isinstance(c, modules.EdgeNetwork) for c in m.modules()), variant
+        assert isinstance(m.uf, modules.GRUUpdate)
+    w = ns.graph_model_wrapper.GraphWrapper(dropin.reference_model("basic", 16, 7, 16, 1, 12))
+    assert "graph_model.mf.message_bias" in w.state_dict()
+    assert isinstance(ns.graph_norm_wrapper.GraphWrapper(torch.nn.Identity(), 3).bn, modules.MaskBatchNorm1d)
+
+
+def test_dropin_encoders_state_dict_contract():
+    """mpnn_functions.encoders drop-in: same layers / state_dict keys as the reference's encoder classes
+    (mpnn_functions/encoders/{atom,bond}_autoencoder.py:7-20, auto_encoder.py:7-19)"""
+    from mpnn_b200 import dropin
+    dropin.install()
+    from mpnn_functions.encoders.atom_autoencoder import AtomAutoEncoder
+    from mpnn_functions.encoders.bond_autoencoder import BondAutoEncoder
+    from mpnn_functions.encoders.auto_encoder import Autoencoder
+    a, b, c = AtomAutoEncoder(), BondAutoEncoder(), Autoencoder(12, 6, 3)
+    assert {k: tuple(v.shape) for k, v in a.encoder.state_dict().items()} == {
+        "0.weight": (15, 30), "2.weight": (8, 15), "2.bias": (8,)}
+    assert {k: tuple(v.shape) for k, v in b.encoder.state_dict().items()} == {
+        "0.weight": (4, 8), "2.weight": (2, 4), "2.bias": (2,)}
+    assert sorted(a.state_dict()) == sorted(
+        ["encoder.0.weight", "encoder.2.weight", "encoder.2.bias", "decoder.0.weight", "decoder.0.bias",
+         "decoder.0.running_mean", "decoder.0.running_var", "decoder.0.num_batches_tracked", "decoder.1.weight",
+         "decoder.1.bias", "decoder.3.weight", "decoder.3.bias"])
+    assert sorted(c.state_dict()) == ["decoder.0.weight", "decoder.2.weight", "encoder.0.weight", "encoder.2.weight"]
+    x = torch.randn(5, 8)
+    assert b.encoder(x).shape == (5, 2) and b(x).shape == (5, 8)      # CPU tensors: the stock layers
+    ref = "/root/reference/mpnn_functions/encoders"
+    if os.path.isdir(ref):
+        import importlib.util
+        for name, ours in (("atom_autoencoder", a), ("bond_autoencoder", b)):
+            spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(ref, name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            theirs = [v for k, v in vars(mod).items() if k.endswith("AutoEncoder")][0]()
+            assert {k: tuple(v.shape) for k, v in theirs.state_dict().items()} == \
+                {k: tuple(v.shape) for k, v in ours.state_dict().items()}

@@ -4,17 +4,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from torch import nn
-from mpnn_b200 import callers, graph, synthetic
-from mpnn_b200.callers import MessagePassingModel, kaiming_init
+from mpnn_b200 import graph, synthetic
+from mpnn_b200.modules import RowwiseSequential
+from mpnn_b200.dropin import reference_model as MessagePassingModel, kaiming_init
 from oracle import mpnn_oracle as O
 from golden_util import leaf_sd
 
 dev = torch.device("cuda:0")
 
-def model(seed, tame):
+def model(seed, tame, typed=True):
     torch.manual_seed(seed)
     ae = nn.Sequential(nn.Linear(30, 15, bias=False), nn.Tanh(), nn.Linear(15, 8))
-    be = nn.Sequential(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
+    be = (RowwiseSequential if typed else nn.Sequential)(nn.Linear(8, 4, bias=False), nn.Tanh(), nn.Linear(4, 2))
     mod = MessagePassingModel("normed_encoded", 8, 2, 8, 1, 16, message_steps=3, atom_encoder=ae, bond_encoder=be)
     mod.apply(kaiming_init)
     if tame:
@@ -34,9 +35,8 @@ for weighted in (False, True):
                 t["adj"] = t["adj"] * torch.maximum(w, w.transpose(1, 2))
             res = []
             for typed in (True, False):
-                callers.TYPED_BONDS = typed
                 graph.clear_cache()
-                mod = model(seed, tame)
+                mod = model(seed, tame, typed)
                 sd0 = {k: v.detach().cpu().clone() for k, v in mod.state_dict().items()}
                 out = mod(t["afm"], t["bfm"], t["adj"], t["mask"])
                 cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(9)).to(dev)
