@@ -81,8 +81,10 @@ def test_module_state_dict_contract(name):
         mod = M.MaskBatchNorm()
     elif cls == "MaskBatchNorm1d":
         mod = M.MaskBatchNorm1d(5)
-    elif cls == "GraphLevelOutput":
-        mod = M.GraphLevelOutput(m["nf"], m["out"])
+    elif cls in ("GraphLevelOutput", "GraphLevelOutputAtoms"):
+        mod = getattr(M, cls)(m["nf"], m["out"])
+    elif cls == "LSTMCellHidden":
+        mod = M.LSTMCellHidden(m["hd"], m["cd"])
     else:
         mod = M.Set2Vec(m["nf"], 99, time_steps=m["steps"])
     sd = mod.state_dict()
