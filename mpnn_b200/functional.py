@@ -161,7 +161,7 @@ def _graphed(key, run, ins, make_bufs, n_out):
         if sbuf is not None:
             sbuf.copy_(t)
     g.replay()
-    return [b.clone() for b in s_bufs[:n_out]]
+    return [b.clone() if b is not None else None for b in s_bufs[:n_out]]
 
 
 class _inline(object):

@@ -271,9 +271,11 @@ def _model_for(case, dev):
 
 
 # widths > 32 run on the tcgen05 kernels: TF32 operands (fp32 accumulate) in the message / GRU / readout GEMMs and
-# tanh.approx gates; SURVEY 8c allows 2e-2 for tensor-core inputs, the tests hold 3e-3 (forward) / 1e-2 (gradients)
-TOL_OUT_TC = 3e-3
-TOL_GRAD_TC = 1e-2
+# tanh.approx gates.  SURVEY 8c: <= 2e-2 relative for tensor-core inputs, checked after the following GRU / readout.
+# Measured end to end on the reference's goldens: 1.1e-2 (d=64: message GEMM -> GRU -> feature softmax of the readout,
+# three TF32 products chained), 1e-3 (d=40).
+TOL_OUT_TC = 2e-2
+TOL_GRAD_TC = 2e-2
 
 
 @pytest.mark.parametrize("name", all_cases("model_"))
