@@ -275,6 +275,33 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
                  const float* UV, const float* dout, int B, int N, int F2, int O, float* dx, float* dWi, float* dbi,
                  float* dWj, float* dbj, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 
+/* ---- x1: the whole T-step message-passing loop as one persistent kernel each way (feature widths <= 32) ---------
+ * h <- bn_t(GRU(sum_{e in E(i)} alpha_e T_t[uid_e]^T H0[src_e], h) * mask) for t = 0..T-1: the loops of
+ * models/normed_basic_model.py:56-59, basic_model.py:50-58, normed_encoded_basic_model_ecfp.py:67-69 on the typed
+ * edge list (csrc/chain.cu).  bn_kind[t]: 0 none, 1 MaskBatchNorm (mask_batch_norm.py:9-15), 2 MaskBatchNorm1d (:20-38);
+ * bn_kind / bn_training / bn_eps / bn_momentum are HOST arrays [T]; bn_ptrs is a HOST array [4T] of device pointers
+ * (gamma, beta, running_mean, running_var per step, NULL allowed), tables a HOST array [T] of device pointers to the
+ * per-type matrices T[u][l][k] of each step (equal pointers = shared edge network).  The first 256 bytes of the workspace
+ * must be zero on entry and are zero again on exit.  saved: mpnn_chain_saved_floats floats, read by the backward.
+ * bwd writes dM [T][rows][d], dh_init [rows][d] (or NULL), the GRU cell's gradients and bn_grads[2t], [2t+1]
+ * (d gamma, d beta of step t's MaskBatchNorm1d; HOST array of device pointers, NULL allowed). */
+int mpnn_chain_supported(int d, int T);
+long long mpnn_chain_saved_floats(long long rows, int d, int T);
+size_t mpnn_chain_workspace_bytes(long long rows, int d, int T);
+int mpnn_chain_fwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, int ecap, int zero_type,
+                   const float* H0, const float* h_init, const float* mask, const float* const* tables, int T,
+                   const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const int* bn_kind,
+                   const int* bn_training, const float* bn_eps, const float* bn_momentum, float* const* bn_ptrs,
+                   long long rows, int d, float* saved, float* out, void* workspace, size_t workspace_bytes,
+                   mpnn_stream_t stream);
+int mpnn_chain_bwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, int ecap, int zero_type,
+                   const float* H0, const float* h_init, const float* mask, const float* const* tables, int T,
+                   const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const int* bn_kind,
+                   const int* bn_training, const float* bn_eps, const float* bn_momentum, float* const* bn_ptrs,
+                   long long rows, int d, float* saved, const float* dout, float* dM, float* dh_init, float* dW_ih,
+                   float* dW_hh, float* db_ih, float* db_hh, float* const* bn_grads, void* workspace,
+                   size_t workspace_bytes, mpnn_stream_t stream);
+
 /* ---- a13/a14: Set2Vec with its input-less LSTM (readout/set2vec.py:68-75, 93-151) ----------------------- */
 long long mpnn_set2vec_saved_floats(int B, int N, int F, int steps);
 size_t mpnn_set2vec_workspace_bytes(int B, int N, int F);

@@ -1027,6 +1027,144 @@ class TypedMessageFn(torch.autograd.Function):
         return dH, dT, None, dbeta, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# the whole T-step loop as one persistent kernel each way (csrc/chain.cu)
+# ------------------------------------------------------------------------------------------------
+CHAIN_ENABLED = os.environ.get("MPNN_B200_FUSED_CHAIN", "1") != "0"
+
+
+def chain_supported(d, T):
+    return bool(CHAIN_ENABLED and _lib.load().mpnn_chain_supported(int(d), int(T)))
+
+
+class ChainFn(torch.autograd.Function):
+    """h_T of  h <- bn_t(GRU(sum_e alpha_e T_t[uid_e]^T H0[src_e], h) * mask), t = 0..T-1  (see csrc/chain.cu).
+
+    args: H0 [rows,d], h_init [rows,d], mask [rows], el, bn (list of T dicts: kind 0/1/2, module, training, eps,
+    momentum), W_ih, W_hh, b_ih, b_hh, then T tables, T transposed tables, then (gamma, beta) of every kind-2 step that
+    has an affine transform."""
+
+    @staticmethod
+    def forward(ctx, H0, h_init, mask, el, bn, W_ih, W_hh, b_ih, b_hh, *rest):
+        lib = _lib.load()
+        _need_cuda(H0, h_init, mask, W_ih)
+        T = len(bn)
+        tables = [f32c(t) for t in rest[:T]]
+        tablesT = [f32c(t) for t in rest[T:2 * T]]
+        affine = list(rest[2 * T:])
+        H0, h_init, mask = f32c(H0), f32c(h_init), f32c(mask)
+        W_ih, W_hh, b_ih, b_hh = f32c(W_ih), f32c(W_hh), f32c(b_ih), f32c(b_hh)
+        rows, d = h_init.shape
+        dev = h_init.device
+        ti = el.typed()
+        kinds = (ctypes.c_int * T)(*[b["kind"] for b in bn])
+        training = (ctypes.c_int * T)(*[int(b["training"]) for b in bn])
+        eps = (ctypes.c_float * T)(*[float(b["eps"]) for b in bn])
+        mom = (ctypes.c_float * T)(*[float(b["momentum"] or 0.0) for b in bn])
+        ptrs, ai, aff_idx = [], 0, []
+        for b in bn:
+            g = be = None
+            if b["kind"] == 2 and b["affine"]:
+                g, be = f32c(affine[ai]), f32c(affine[ai + 1])
+                aff_idx.append(ai)
+                ai += 2
+            else:
+                aff_idx.append(-1)
+            ptrs += [g, be, b.get("running_mean"), b.get("running_var")]
+        keep = [p for p in ptrs if p is not None]
+        bn_ptrs = ptr_array(ptrs)
+        out = torch.empty_like(h_init)
+        saved = torch.empty(lib.mpnn_chain_saved_floats(rows, d, T), dtype=torch.float32, device=dev)
+        ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev)
+        alpha = f32c(el.edge_w) if el.edge_w is not None else None
+        args = (ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0), ptr(h_init),
+                ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), kinds, training, eps, mom,
+                bn_ptrs, rows, d, ptr(saved))
+        check(lib.mpnn_chain_fwd(*(args + (ptr(out), ptr(ws), ws.numel(), stream()))), "chain_fwd")
+        ctx.save_for_backward(H0, h_init, mask, W_ih, W_hh, b_ih, b_hh, saved, alpha, *(tables + tablesT + affine))
+        ctx.meta = (el, bn, T, rows, d, aff_idx, keep)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        el, bn, T, rows, d, aff_idx, keep = ctx.meta
+        H0, h_init, mask, W_ih, W_hh, b_ih, b_hh, saved, alpha = ctx.saved_tensors[:9]
+        rest = ctx.saved_tensors[9:]
+        tables, tablesT, affine = list(rest[:T]), list(rest[T:2 * T]), list(rest[2 * T:])
+        dev = h_init.device
+        ti = el.typed()
+        dout = f32c(dout)
+        need_H0, need_h = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        kinds = (ctypes.c_int * T)(*[b["kind"] for b in bn])
+        training = (ctypes.c_int * T)(*[int(b["training"]) for b in bn])
+        eps = (ctypes.c_float * T)(*[float(b["eps"]) for b in bn])
+        mom = (ctypes.c_float * T)(*[float(b["momentum"] or 0.0) for b in bn])
+        ptrs = []
+        for t, b in enumerate(bn):
+            g = be = None
+            if aff_idx[t] >= 0:
+                g, be = affine[aff_idx[t]], affine[aff_idx[t] + 1]
+            ptrs += [g, be, b.get("running_mean"), b.get("running_var")]
+        dM = torch.empty(T, rows, d, dtype=torch.float32, device=dev)
+        dh = torch.empty_like(h_init) if need_h else None
+        dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
+        db_ih, db_hh = torch.empty_like(b_ih), torch.empty_like(b_hh)
+        d_aff = [torch.empty_like(a) for a in affine]
+        gptrs = []
+        for t in range(T):
+            gptrs += ([d_aff[aff_idx[t]], d_aff[aff_idx[t] + 1]] if aff_idx[t] >= 0 else [None, None])
+        ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev)
+        check(lib.mpnn_chain_bwd(ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0),
+                                 ptr(h_init), ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh),
+                                 kinds, training, eps, mom, ptr_array(ptrs), rows, d, ptr(saved), ptr(dout), ptr(dM),
+                                 ptr(dh), ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh), ptr_array(gptrs), ptr(ws),
+                                 ws.numel(), stream()), "chain_bwd")
+        # ---- message gradients -> table gradients (parameter-only: side lane) and sender gradients -------------------
+        # steps that share a table (basic_model.py:57: one EdgeNetwork, reuse_graph_tensors) share H0 too, so their
+        # message gradients add up before the (linear) table / sender gradient kernels
+        groups = {}
+        for t in range(T):
+            groups.setdefault(tables[t].data_ptr(), []).append(t)
+        need_T = [ctx.needs_input_grad[9 + t] for t in range(T)]
+        dTs = [None] * T
+        dH0 = None
+        produced = torch.cuda.Event() if SIDE_STREAM_ENABLED else None
+        if produced is not None:
+            produced.record(torch.cuda.current_stream(dev))
+
+        def run(dMsum, t0, dH, dT):
+            if dT is not None:
+                ti.wait_sorted()
+            wsb = workspace(lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, d, d, el.B), dev)
+            check(lib.mpnn_tmsg_bwd(ptr(el.row_ptr), ptr(el.col_ptr), ptr(el.csc_eid), ptr(el.edge_src),
+                                    ptr(el.edge_dst), ptr(ti.uid), ptr(ti.type_ptr), ptr(ti.type_eid), ptr(ti.counts),
+                                    ptr(alpha), ptr(H0), ptr(tables[t0]), ptr(tablesT[t0]), None, el.n_rows, H0.shape[0],
+                                    el.B, el.N, d, d, el.Ecap, ti.Ucap, ptr(dMsum), ptr(dH), ptr(dT), ptr(wsb),
+                                    wsb.numel(), stream()), "tmsg_bwd")
+
+        for ts in groups.values():
+            t0 = ts[0]
+            dMsum = dM[t0] if len(ts) == 1 else dM[ts].sum(0)
+            want_T = any(need_T[t] for t in ts)
+            if need_H0:
+                dHt = torch.empty_like(H0)
+                run(dMsum, t0, dHt, None)
+                dH0 = dHt if dH0 is None else dH0 + dHt
+            if want_T:
+                side = SIDE_STREAM_ENABLED and len(ts) == 1
+                cm = _on_side_stream(dev, [dM, H0, tables[t0], tablesT[t0], alpha], lane=1, after=produced) if side \
+                    else _inline()
+                with cm:
+                    dT = torch.empty_like(tables[t0])
+                    run(dMsum, t0, None, dT)
+                if side:
+                    _ready_put(dT, cm.done)
+                dTs[t0] = dT     # the other steps of the group point at the same table: autograd sums, they get None
+        return (dH0, dh, None, None, None, dW_ih, dW_hh, db_ih, db_hh) + tuple(dTs) + (None,) * T + tuple(d_aff)
+
+
 class BilinearEdgeFn(torch.autograd.Function):
     """reference bilinear_edge_network.py:25-37 on the compacted pairs: Y[e, p] = h[src_e]^T X_e[:, p, :] h[dst_e] with
     X_e the bond row viewed [nf, nf, nf].  H [n_rows, nf], X [E(+1), nf^3] -> Y [E, nf]."""

@@ -10,10 +10,10 @@ import torch
 from torch import nn
 
 from . import graph
-from .functional import (BilinearEdgeFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
+from .functional import (BilinearEdgeFn, ChainFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
                          GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, TableHolder, LinearFn, LSTMCellHiddenFn, MaskBN1dFn, MaskBNFn,
                          Set2VecFn, SoftmaxMulFn,
-                         TableLayoutFn, TypedMessageFn, TypedMessageTCFn, table_dp, tc_dp, typed_dp)
+                         TableLayoutFn, TypedMessageFn, TypedMessageTCFn, chain_supported, table_dp, tc_dp, typed_dp)
 from . import _lib
 from .functional import _note_forward_side_work, _side_stream
 import os
@@ -21,6 +21,7 @@ import weakref
 
 SIBLING_PREFETCH = os.environ.get("MPNN_B200_SIBLING_PREFETCH", "1") != "0"
 SHARED_GRAD_HUB = os.environ.get("MPNN_B200_SHARED_GRAD_HUB", "1") != "0"
+LAZY_CHAIN = os.environ.get("MPNN_B200_LAZY_CHAIN", "1") != "0"   # module calls build a lazy chain (fused T-step kernel)
 
 _N_TIED = 50  # edge_network.py:20
 
@@ -32,7 +33,50 @@ def _key(t):
 # =================================================================================================
 # message functions
 # =================================================================================================
-class LazyMessages(object):
+class _LazyTensor(object):
+    """Tensor-like handle whose value is computed on first use (`materialize()`): attribute access, operators and torch
+    functions (the `__torch_function__` protocol) all evaluate it first, so arbitrary code can consume it."""
+
+    _value = None
+
+    def materialize(self):
+        raise NotImplementedError
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        def unwrap(a):
+            if isinstance(a, _LazyTensor):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(unwrap(x) for x in a)
+            return a
+        kwargs = {k: unwrap(v) for k, v in (kwargs or {}).items()}
+        return func(*[unwrap(a) for a in args], **kwargs)
+
+    __hash__ = object.__hash__
+
+
+def _binop(name):
+    def f(self, other):
+        if isinstance(other, _LazyTensor):
+            other = other.materialize()
+        return getattr(self.materialize(), name)(other)
+    return f
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
+           "__matmul__", "__getitem__", "__pow__", "__eq__", "__ne__", "__lt__", "__gt__", "__le__", "__ge__"):
+    setattr(_LazyTensor, _n, _binop(_n))
+_LazyTensor.__neg__ = lambda self: -self.materialize()
+_LazyTensor.__hash__ = object.__hash__
+
+
+class LazyMessages(_LazyTensor):
     """What EdgeNetwork.forward returns: the messages of one (afm, bfm) pair, not yet evaluated.
 
     The reference HEAD is internally inconsistent: EdgeNetwork.forward returns already-summed
@@ -58,40 +102,11 @@ class LazyMessages(object):
     def aggregate(self, adj, alpha_fn=None, gamma_fn=None):
         return self._net._aggregated_messages(self._afm, self._bfm, adj, self._reuse, alpha_fn, gamma_fn)
 
-    def __getattr__(self, name):
-        if name.startswith("_"):
-            raise AttributeError(name)
-        return getattr(self.materialize(), name)
-
-    @classmethod
-    def __torch_function__(cls, func, types, args=(), kwargs=None):
-        def unwrap(a):
-            if isinstance(a, LazyMessages):
-                return a.materialize()
-            if isinstance(a, (list, tuple)):
-                return type(a)(unwrap(x) for x in a)
-            return a
-        kwargs = {k: unwrap(v) for k, v in (kwargs or {}).items()}
-        return func(*[unwrap(a) for a in args], **kwargs)
-
     def __len__(self):
         return self._afm.shape[0]
 
     def __repr__(self):
         return "LazyMessages(%s, afm=%s)" % (type(self._net).__name__, tuple(self._afm.shape))
-
-
-def _binop(name):
-    def f(self, other):
-        return getattr(self.materialize(), name)(other)
-    return f
-
-
-for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
-           "__matmul__", "__getitem__", "__pow__", "__eq__", "__ne__", "__lt__", "__gt__", "__le__", "__ge__"):
-    setattr(LazyMessages, _n, _binop(_n))
-LazyMessages.__neg__ = lambda self: -self.materialize()
-LazyMessages.__hash__ = object.__hash__
 
 
 class EdgeNetwork(nn.Module):
@@ -456,7 +471,7 @@ class GGNNMsgPass(nn.Module):
 # =================================================================================================
 # encoders on categorical bond tensors (reference mpnn_functions/encoders/*.py)
 # =================================================================================================
-class DeferredRows(object):
+class DeferredRows(_LazyTensor):
     """What a `RowwiseSequential` returns for a dense 4-D CUDA data tensor: "module(x)", not yet evaluated.
 
     The unchanged reference models run `bfm = self.bebn(self.be(bfm), adj)` (normed_encoded_basic_model.py:68): the
@@ -487,28 +502,6 @@ class DeferredRows(object):
     @property
     def shape(self):
         return torch.Size(tuple(self._x.shape[:-1]) + (self._module.out_features(self._x.shape[-1]),))
-
-    def __getattr__(self, name):
-        if name.startswith("_"):
-            raise AttributeError(name)
-        return getattr(self.materialize(), name)
-
-    @classmethod
-    def __torch_function__(cls, func, types, args=(), kwargs=None):
-        def unwrap(a):
-            if isinstance(a, DeferredRows):
-                return a.materialize()
-            if isinstance(a, (list, tuple)):
-                return type(a)(unwrap(v) for v in a)
-            return a
-        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in (kwargs or {}).items()})
-
-
-for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__",
-           "__matmul__", "__getitem__", "__pow__", "__eq__", "__ne__", "__lt__", "__gt__", "__le__", "__ge__"):
-    setattr(DeferredRows, _n, _binop(_n))
-DeferredRows.__neg__ = lambda self: -self.materialize()
-DeferredRows.__hash__ = object.__hash__
 
 
 class RowwiseSequential(nn.Sequential):
@@ -573,9 +566,7 @@ class BondAutoEncoder(_TanhAutoEncoder):
 def _as_dense(messages):
     if isinstance(messages, graph.TypedBonds):
         return messages.dense()
-    if isinstance(messages, DeferredRows):
-        return messages.materialize()
-    return messages.materialize() if isinstance(messages, LazyMessages) else messages
+    return messages.materialize() if isinstance(messages, _LazyTensor) else messages
 
 
 def _typed_mask_bn(tb, mask, stats_fn):
@@ -590,6 +581,108 @@ def _typed_mask_bn(tb, mask, stats_fn):
     return tb.with_rows(stats_fn(tb._rows, a, c, M))
 
 
+class LazyAgg(_LazyTensor):
+    """`AdjMsgAgg()(mf(afm, bfm), adj)`, not yet evaluated: consumed by GRUUpdate it becomes part of a fused step
+    (csrc/chain.cu); anything else gets the aggregated messages [B, N, mf] (the fused message + aggregation kernel)."""
+
+    def __init__(self, messages, adj):
+        self._messages, self._adj = messages, adj
+
+    def materialize(self):
+        if self._value is None:
+            self._value = self._messages.aggregate(self._adj)
+        return self._value
+
+
+class LazyState(_LazyTensor):
+    """Node state after `uf(ma(mf(afm, bfm), adj), prev, mask)` (kind "gru") or after a masked batch norm of such a
+    state (kind "bn"), not yet evaluated.  The reference's loops (normed_basic_model.py:56-59, basic_model.py:50-58,
+    normed_encoded_basic_model_ecfp.py:67-69) build a chain of these, one link per module call; the first real consumer
+    (`torch.cat([node_state, afm])` in front of the readout) evaluates the WHOLE chain as one persistent kernel
+    (`functional.ChainFn`).  Chains the fused kernel does not serve are evaluated link by link by the per-module
+    kernels, with identical results."""
+
+    def __init__(self, kind, src, prev, mask, module, eps=None):
+        self._kind, self._src, self._prev, self._mask, self._module, self._eps = kind, src, prev, mask, module, eps
+
+    # ---- link-by-link evaluation (what the module call would have done) ----
+    def _evaluate_link(self):
+        if self._kind == "gru":
+            prev = _as_dense(self._prev)
+            return self._module._run(self._src.materialize(), prev, self._mask)
+        return self._module._run(self._src.materialize(), self._mask, *([] if self._eps is None else [self._eps]))
+
+    def materialize(self):
+        if self._value is None:
+            v = _fused_chain(self)
+            self._value = v if v is not None else self._evaluate_link()
+        return self._value
+
+
+def _fused_chain(head):
+    """Evaluates the chain ending in `head` with the persistent step kernel when every link fits it; None otherwise."""
+    steps, node = [], head
+    while isinstance(node, LazyState) and node._value is None:
+        bn = None
+        if node._kind == "bn":
+            bn, node = node, node._src
+            if not (isinstance(node, LazyState) and node._kind == "gru" and node._value is None):
+                return None
+        if not isinstance(node._src, LazyAgg) or node._src._value is not None:
+            return None
+        steps.append((node, bn))
+        node = node._prev
+    if not steps:
+        return None
+    steps.reverse()
+    base = _as_dense(node)
+    g0 = steps[0][0]
+    msg0 = g0._src._messages
+    afm, bfm, adj, mask, uf = msg0._afm, msg0._bfm, g0._src._adj, g0._mask, g0._module
+    if not (torch.is_tensor(afm) and afm.is_cuda and torch.is_tensor(base) and base.is_cuda and afm.dim() == 3
+            and base.shape == afm.shape and afm.dtype == torch.float32 and base.dtype == torch.float32):
+        return None
+    d = afm.shape[-1]
+    if uf.nf != d or uf.mf != d or not chain_supported(d, len(steps)):
+        return None
+    for gru, bn in steps:
+        m = gru._src._messages
+        net = m._net
+        if (gru._module is not uf or gru._mask is not mask or m._afm is not afm or m._bfm is not bfm
+                or gru._src._adj is not adj or type(net)._aggregated_messages is not EdgeNetwork._aggregated_messages
+                or not net._typed_capable or net.nf != d or net.mf != d):
+            return None
+        if bn is not None and (bn._mask is not mask or (isinstance(bn._module, MaskBatchNorm1d)
+                                                        and bn._module.momentum is None)):
+            return None
+    el = graph.edge_list_for(bfm, adj)
+    if not all(gru._src._messages._net._typed_ok(bfm, el) for gru, _ in steps):
+        return None
+    tables, tablesT, bnspec, affine = [], [], [], []
+    for gru, bn in steps:
+        m = gru._src._messages
+        table, tableT = m._net._table(el, m._reuse)
+        tables.append(table)
+        tablesT.append(tableT)
+        if bn is None:
+            bnspec.append(dict(kind=0, training=0, eps=0.0, momentum=0.0, affine=False))
+        elif isinstance(bn._module, MaskBatchNorm1d):
+            mod = bn._module
+            tracked = mod.track_running_stats
+            bnspec.append(dict(kind=2, training=mod.training or not tracked, eps=mod.eps, momentum=mod.momentum,
+                               affine=mod.affine, running_mean=mod.running_mean if tracked else None,
+                               running_var=mod.running_var if tracked else None))
+            if mod.affine:
+                affine += [mod.weight, mod.bias]
+        else:
+            bnspec.append(dict(kind=1, training=1, eps=1e-6 if bn._eps is None else bn._eps, momentum=0.0, affine=False))
+    W_ih, W_hh, b_ih, b_hh = uf.gru_cell.weight_ih, uf.gru_cell.weight_hh, uf.gru_cell.bias_ih, uf.gru_cell.bias_hh
+    B, N, _ = afm.shape
+    out = ChainFn.apply(afm.reshape(-1, d), base.reshape(-1, d), mask.reshape(-1), el, bnspec, W_ih, W_hh, b_ih, b_hh,
+                        *(tables + tablesT + affine))
+    return out.view(B, N, d)
+
+
 class AdjMsgAgg(nn.Module):
     """reference adjacent_message_agg.py: out[b,i] = sum_j adj[b,i,j] * messages[b,i,j]."""
 
@@ -598,8 +691,10 @@ class AdjMsgAgg(nn.Module):
 
     def forward(self, messages, adj):
         if isinstance(messages, LazyMessages):
+            if LAZY_CHAIN and type(messages._net) is EdgeNetwork and torch.is_tensor(adj) and adj.is_cuda:
+                return LazyAgg(messages, adj)      # may become part of a fused step (LazyState)
             return messages.aggregate(adj)
-        return DenseAggFn.apply(messages, adj)
+        return DenseAggFn.apply(_as_dense(messages), adj)
 
 
 class WAdjMsgAgg(nn.Module):
@@ -712,9 +807,13 @@ class GRUUpdate(nn.Module):
         self.gru_cell = GRUCell(self.mf, self.nf)
 
     def forward(self, messages, node_states, mask):
-        messages = _as_dense(messages)
         if self.nf != self.mf:
             raise RuntimeError("GRUUpdate requires node_features == message_features (reference gru_update.py:53)")
+        if isinstance(messages, LazyAgg) and (torch.is_tensor(node_states) or isinstance(node_states, LazyState)):
+            return LazyState("gru", messages, node_states, mask, self)
+        return self._run(_as_dense(messages), _as_dense(node_states), mask)
+
+    def _run(self, messages, node_states, mask):
         h = self.gru_cell(messages.reshape(-1, self.mf), node_states.reshape(-1, self.nf), mask)
         return h.view(node_states.shape)
 
@@ -727,6 +826,11 @@ class MaskBatchNorm(nn.Module):
         super(MaskBatchNorm, self).__init__()
 
     def forward(self, tensor, mask, eps=1e-6):
+        if isinstance(tensor, LazyState) and tensor._kind == "gru" and tensor._value is None and tensor._mask is mask:
+            return LazyState("bn", tensor, None, mask, self, eps)
+        return self._run(tensor, mask, eps)
+
+    def _run(self, tensor, mask, eps=1e-6):
         if isinstance(tensor, DeferredRows):
             tensor = tensor.resolve(mask)
         if isinstance(tensor, graph.TypedBonds):
@@ -761,6 +865,11 @@ class MaskBatchNorm1d(nn.BatchNorm1d):
         return _typed_mask_bn(tb, mask, stats)
 
     def forward(self, tensor, mask):
+        if isinstance(tensor, LazyState) and tensor._kind == "gru" and tensor._value is None and tensor._mask is mask:
+            return LazyState("bn", tensor, None, mask, self)
+        return self._run(tensor, mask)
+
+    def _run(self, tensor, mask):
         if isinstance(tensor, DeferredRows):
             tensor = tensor.resolve(mask)
         if isinstance(tensor, graph.TypedBonds):
