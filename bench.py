@@ -336,6 +336,8 @@ def run_ours(args):
         roof = dominant_kernel_roofline(w, body, devb, flush, n)
     # every rank replays the step here (it contains the gradient all-reduce when N > 1); rank 0 keeps the count
     launches = count_launches(run_resident)
+    if args.timeline and rank == 0:
+        dump_timeline(run_resident, args.timeline)
     if gs is not None:
         gs.check()
 
@@ -440,6 +442,26 @@ def dominant_kernel_roofline(w, body, devb, flush, n_atoms):
             "note": "latency-bound by construction: 52 dependent layers on R = #distinct bond rows + 1 rows (the "
                     "reference evaluates them on B*N*N rows); HBM-bound kernels of the same path at config-5 size reach "
                     "0.75-0.84 of the measured copy bandwidth (profiles/, tools/bench_tc.py)"}
+
+
+def dump_timeline(fn, path):
+    """warm per-kernel timeline of one step (CUPTI through torch.profiler): start offset, duration, stream, name"""
+    from torch.profiler import profile, ProfilerActivity
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start
+    with open(path, "w") as fh:
+        fh.write("# start_us dur_us end_us stream name\n")
+        for e in evs:
+            a, b = e.time_range.start - t0, e.time_range.end - t0
+            fh.write("%8.1f %7.1f %8.1f %4s %s\n" % (a, b - a, b, getattr(e, "device_resource_id", "?"),
+                                                     e.name.replace("(anonymous namespace)::", "")[:90]))
 
 
 def count_launches(fn):
@@ -558,6 +580,7 @@ def main():
     ap.add_argument("--stock-head", action="store_true", help="keep the head + loss as stock torch modules")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")
+    ap.add_argument("--timeline", default="", help="write a warm per-kernel timeline of one step to this file")
     ap.add_argument("--hidden", type=int, default=0, help="feature width d (autoenc sweep of BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -282,25 +282,33 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
  * bn_kind / bn_training / bn_eps / bn_momentum are HOST arrays [T]; bn_ptrs is a HOST array [4T] of device pointers
  * (gamma, beta, running_mean, running_var per step, NULL allowed), tables a HOST array [T] of device pointers to the
  * per-type matrices T[u][l][k] of each step (equal pointers = shared edge network).  The first 256 bytes of the workspace
- * must be zero on entry and are zero again on exit.  saved: mpnn_chain_saved_floats floats, read by the backward.
+ * (barrier words) and the 2048 bytes behind them (mailboxes) must be zero on entry and are zero again on exit.
+ * saved: mpnn_chain_saved_floats floats, read by the backward.
  * bwd writes dM [T][rows][d], dh_init [rows][d] (or NULL), the GRU cell's gradients and bn_grads[2t], [2t+1]
  * (d gamma, d beta of step t's MaskBatchNorm1d; HOST array of device pointers, NULL allowed). */
 int mpnn_chain_supported(int d, int T);
+int mpnn_chain_debug(long long* out64);   /* profiling aid: phase timestamps of the last forward (MPNN_B200_CHAIN_DEBUG=1) */
 long long mpnn_chain_saved_floats(long long rows, int d, int T);
 size_t mpnn_chain_workspace_bytes(long long rows, int d, int T);
 int mpnn_chain_fwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, int ecap, int zero_type,
                    const float* H0, const float* h_init, const float* mask, const float* const* tables, int T,
                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const int* bn_kind,
                    const int* bn_training, const float* bn_eps, const float* bn_momentum, float* const* bn_ptrs,
-                   long long rows, int d, float* saved, float* out, void* workspace, size_t workspace_bytes,
-                   mpnn_stream_t stream);
+                   long long rows, int d, const int* real_list, float* saved, float* out, void* workspace,
+                   size_t workspace_bytes, mpnn_stream_t stream);
 int mpnn_chain_bwd(const int* row_ptr, const int* edge_src, const int* uid, const float* alpha, int ecap, int zero_type,
                    const float* H0, const float* h_init, const float* mask, const float* const* tables, int T,
                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const int* bn_kind,
                    const int* bn_training, const float* bn_eps, const float* bn_momentum, float* const* bn_ptrs,
-                   long long rows, int d, float* saved, const float* dout, float* dM, float* dh_init, float* dW_ih,
-                   float* dW_hh, float* db_ih, float* db_hh, float* const* bn_grads, void* workspace,
-                   size_t workspace_bytes, mpnn_stream_t stream);
+                   long long rows, int d, const int* real_list, float* saved, const float* dout, float* dM,
+                   float* dh_init, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh, float* const* bn_grads,
+                   void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* real_list (optional, NULL allowed): [rows + 1] ints from mpnn_real_rows = the rows with mask != 0 in increasing order
+ * and, in the last slot, their number; lets every CTA of the step kernels own the same number of real rows.  `out`,
+ * `dM` and `dh_init` must be zero-filled by the caller: rows with mask == 0 are skipped (their values are exact zeros). */
+int mpnn_real_rows_max(void);
+int mpnn_real_rows(const float* mask, long long rows, int* list, void* workspace, size_t workspace_bytes,
+                   mpnn_stream_t stream);
 
 /* ---- a13/a14: Set2Vec with its input-less LSTM (readout/set2vec.py:68-75, 93-151) ----------------------- */
 long long mpnn_set2vec_saved_floats(int B, int N, int F, int steps);

@@ -103,12 +103,15 @@ SIGNATURES = {
     "mpnn_dense_agg_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "mpnn_dense_agg_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P]),
     "mpnn_chain_supported": (_I, [_I, _I]),
+    "mpnn_chain_debug": (_I, [_P]),
     "mpnn_chain_saved_floats": (_L, [_L, _I, _I]),
     "mpnn_chain_workspace_bytes": (_Z, [_L, _I, _I]),
     "mpnn_chain_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _PP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _PP, _L, _I, _P,
-                            _P, _P, _Z, _P]),
+                            _P, _P, _P, _Z, _P]),
     "mpnn_chain_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _PP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _PP, _L, _I, _P,
-                            _P, _P, _P, _P, _P, _P, _P, _PP, _P, _Z, _P]),
+                            _P, _P, _P, _P, _P, _P, _P, _P, _PP, _P, _Z, _P]),
+    "mpnn_real_rows_max": (_I, []),
+    "mpnn_real_rows": (_I, [_P, _L, _P, _P, _Z, _P]),
     "mpnn_set2vec_saved_floats": (_L, [_I, _I, _I, _I]),
     "mpnn_set2vec_workspace_bytes": (_Z, [_I, _I, _I]),
     "mpnn_set2vec_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -1037,6 +1037,48 @@ def chain_supported(d, T):
     return bool(CHAIN_ENABLED and _lib.load().mpnn_chain_supported(int(d), int(T)))
 
 
+_REAL_ROWS = {}     # (mask identity) -> (mask, list, event): the rows with mask != 0, computed once per batch
+
+
+def real_rows(mask, side=False):
+    """(list [rows+1] int32 or None, event or None) for the step kernels: the rows of `mask` that are real, so every CTA
+    owns the same number of them.  With side=True the (tiny, single-block) kernel is enqueued on a side stream, forked
+    from the current position of the main stream: `modules._fused_chain` calls it before the compaction and the edge
+    networks, which it then overlaps.  Batches beyond mpnn_real_rows_max() rows use the kernels' round-robin deal."""
+    lib = _lib.load()
+    m = mask.reshape(-1)
+    rows = m.shape[0]
+    if rows > lib.mpnn_real_rows_max() or not m.is_cuda:
+        return None, None
+    key = (m.data_ptr(), m._version, rows, m.device.index)
+    hit = _REAL_ROWS.get(key)
+    if hit is not None:
+        return hit[1], hit[2]
+    m = f32c(m)
+    dev = m.device
+    lst = torch.empty(rows + 1, dtype=torch.int32, device=dev)
+    ws = torch.empty(2 * (rows + 1), dtype=torch.int32, device=dev)
+    ev = None
+    if side and SIDE_STREAM_ENABLED:
+        main = torch.cuda.current_stream(dev)
+        _, s_ = _side_stream(dev, lane=6)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        s_.wait_event(fork)
+        with torch.cuda.stream(s_):
+            check(lib.mpnn_real_rows(ptr(m), rows, ptr(lst), ptr(ws), ws.numel() * 4, stream()), "real_rows")
+            ev = torch.cuda.Event()
+            ev.record(s_)
+        for t_ in (m, lst, ws):
+            t_.record_stream(s_)
+        _note_forward_side_work(dev, lane=6)
+    else:
+        check(lib.mpnn_real_rows(ptr(m), rows, ptr(lst), ptr(ws), ws.numel() * 4, stream()), "real_rows")
+    _REAL_ROWS.clear()
+    _REAL_ROWS[key] = (mask, lst, ev)
+    return lst, ev
+
+
 class ChainFn(torch.autograd.Function):
     """h_T of  h <- bn_t(GRU(sum_e alpha_e T_t[uid_e]^T H0[src_e], h) * mask), t = 0..T-1  (see csrc/chain.cu).
 
@@ -1048,6 +1090,7 @@ class ChainFn(torch.autograd.Function):
     def forward(ctx, H0, h_init, mask, el, bn, W_ih, W_hh, b_ih, b_hh, *rest):
         lib = _lib.load()
         _need_cuda(H0, h_init, mask, W_ih)
+        real = real_rows(mask)      # (list tensor or None, event or None): enqueued early by modules._fused_chain
         T = len(bn)
         tables = [f32c(t) for t in rest[:T]]
         tablesT = [f32c(t) for t in rest[T:2 * T]]
@@ -1073,23 +1116,25 @@ class ChainFn(torch.autograd.Function):
             ptrs += [g, be, b.get("running_mean"), b.get("running_var")]
         keep = [p for p in ptrs if p is not None]
         bn_ptrs = ptr_array(ptrs)
-        out = torch.empty_like(h_init)
+        out = torch.zeros_like(h_init)      # rows with mask == 0 are skipped by the kernel: exact zeros
         saved = torch.empty(lib.mpnn_chain_saved_floats(rows, d, T), dtype=torch.float32, device=dev)
+        if real[1] is not None:
+            torch.cuda.current_stream(dev).wait_event(real[1])
         ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev)
         alpha = f32c(el.edge_w) if el.edge_w is not None else None
         args = (ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0), ptr(h_init),
                 ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), kinds, training, eps, mom,
-                bn_ptrs, rows, d, ptr(saved))
+                bn_ptrs, rows, d, ptr(real[0]), ptr(saved))
         check(lib.mpnn_chain_fwd(*(args + (ptr(out), ptr(ws), ws.numel(), stream()))), "chain_fwd")
         ctx.save_for_backward(H0, h_init, mask, W_ih, W_hh, b_ih, b_hh, saved, alpha, *(tables + tablesT + affine))
-        ctx.meta = (el, bn, T, rows, d, aff_idx, keep)
+        ctx.meta = (el, bn, T, rows, d, aff_idx, keep, real[0])
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         lib = _lib.load()
-        el, bn, T, rows, d, aff_idx, keep = ctx.meta
+        el, bn, T, rows, d, aff_idx, keep, real_list = ctx.meta
         H0, h_init, mask, W_ih, W_hh, b_ih, b_hh, saved, alpha = ctx.saved_tensors[:9]
         rest = ctx.saved_tensors[9:]
         tables, tablesT, affine = list(rest[:T]), list(rest[T:2 * T]), list(rest[2 * T:])
@@ -1107,8 +1152,9 @@ class ChainFn(torch.autograd.Function):
             if aff_idx[t] >= 0:
                 g, be = affine[aff_idx[t]], affine[aff_idx[t] + 1]
             ptrs += [g, be, b.get("running_mean"), b.get("running_var")]
-        dM = torch.empty(T, rows, d, dtype=torch.float32, device=dev)
-        dh = torch.empty_like(h_init) if need_h else None
+        # padded rows (mask == 0) are skipped by the kernel: their gradients are exact zeros
+        dM = torch.zeros(T, rows, d, dtype=torch.float32, device=dev)
+        dh = torch.zeros_like(h_init) if need_h else None
         dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
         db_ih, db_hh = torch.empty_like(b_ih), torch.empty_like(b_hh)
         d_aff = [torch.empty_like(a) for a in affine]
@@ -1118,7 +1164,8 @@ class ChainFn(torch.autograd.Function):
         ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev)
         check(lib.mpnn_chain_bwd(ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0),
                                  ptr(h_init), ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh),
-                                 kinds, training, eps, mom, ptr_array(ptrs), rows, d, ptr(saved), ptr(dout), ptr(dM),
+                                 kinds, training, eps, mom, ptr_array(ptrs), rows, d, ptr(real_list), ptr(saved),
+                                 ptr(dout), ptr(dM),
                                  ptr(dh), ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh), ptr_array(gptrs), ptr(ws),
                                  ws.numel(), stream()), "chain_bwd")
         # ---- message gradients -> table gradients (parameter-only: side lane) and sender gradients -------------------

@@ -278,6 +278,8 @@ def edge_list_for(bfm, adj=None):
 
 def clear_cache():
     _CACHE.clear()
+    from . import functional
+    functional._REAL_ROWS.clear()
 
 
 # =====================================================================================================================

@@ -15,7 +15,7 @@ from .functional import (BilinearEdgeFn, ChainFn, DenseAggFn, EdgeMessageFn, Edg
                          Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, chain_supported, table_dp, tc_dp, typed_dp)
 from . import _lib
-from .functional import _note_forward_side_work, _side_stream
+from .functional import _note_forward_side_work, _side_stream, real_rows
 import os
 import weakref
 
@@ -655,6 +655,7 @@ def _fused_chain(head):
         if bn is not None and (bn._mask is not mask or (isinstance(bn._module, MaskBatchNorm1d)
                                                         and bn._module.momentum is None)):
             return None
+    real_rows(mask, side=True)     # tiny kernel on a side lane, overlapped with the compaction / edge networks below
     el = graph.edge_list_for(bfm, adj)
     if not all(gru._src._messages._net._typed_ok(bfm, el) for gru, _ in steps):
         return None
