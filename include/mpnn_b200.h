@@ -275,6 +275,27 @@ int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float
                  const float* UV, const float* dout, int B, int N, int F2, int O, float* dx, float* dWi, float* dbi,
                  float* dWj, float* dbj, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 
+/* K sibling edge networks (one per message-passing step, normed_basic_model.py:24-27: same layer plan, same distinct
+ * rows, different weights) in ONE launch each way.  Per-network arguments are HOST arrays of device pointers:
+ * growth_w / growth_b / d_growth_* [K * n_growth] (network-major), the others [K]. */
+int mpnn_enet_max_nets(void);
+int mpnn_enet_fwd_multi(int K, const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
+                        const float* const* growth_b, const float* const* w_tied, int P, int n_tied,
+                        const float* const* w_last, const float* const* b_last, int nf, int mf, float* const* saved,
+                        float* const* table, float* const* tableT, mpnn_stream_t stream);
+int mpnn_enet_bwd_multi(int K, const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
+                        const float* const* w_tied, int P, int n_tied, const float* const* w_last, int nf, int mf,
+                        const float* const* saved, const float* const* dT, float* const* d_growth_w,
+                        float* const* d_growth_b, float* const* d_w_tied, float* const* d_w_last,
+                        float* const* d_b_last, float* const* d_rows, void* workspace, size_t workspace_bytes,
+                        mpnn_stream_t stream);
+/* table gradients of K steps that share the edge list and the sender states: dM [K][n_rows][mf] ->
+ * dT [K][unique_capacity+1][DP][DP]; workspace K x mpnn_tmsg_bwd_workspace_bytes(.., B = 1) */
+int mpnn_tmsg_bwd_table_multi(int K, const int* edge_src, const int* edge_dst, const int* uid, const int* type_ptr,
+                              const int* type_eid, const int* counts, const float* alpha, const float* H, int n_rows,
+                              int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dT,
+                              void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
 /* ---- x1: the whole T-step message-passing loop as one persistent kernel each way (feature widths <= 32) ---------
  * h <- bn_t(GRU(sum_{e in E(i)} alpha_e T_t[uid_e]^T H0[src_e], h) * mask) for t = 0..T-1: the loops of
  * models/normed_basic_model.py:56-59, basic_model.py:50-58, normed_encoded_basic_model_ecfp.py:67-69 on the typed

@@ -44,6 +44,11 @@ SIGNATURES = {
     "mpnn_enet_fwd": (_I, [_P, _I, _I, _I, _PP, _PP, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P]),
     "mpnn_enet_bwd": (_I, [_P, _I, _I, _I, _PP, _P, _I, _I, _P, _I, _I, _P, _P, _PP, _PP, _P, _P, _P, _P, _P, _Z,
                            _P]),
+    "mpnn_enet_max_nets": (_I, []),
+    "mpnn_enet_fwd_multi": (_I, [_I, _P, _I, _I, _I, _PP, _PP, _PP, _I, _I, _PP, _PP, _I, _I, _PP, _PP, _PP, _P]),
+    "mpnn_enet_bwd_multi": (_I, [_I, _P, _I, _I, _I, _PP, _PP, _I, _I, _PP, _I, _I, _PP, _PP, _PP, _PP, _PP, _PP, _PP,
+                                 _PP, _P, _Z, _P]),
+    "mpnn_tmsg_bwd_table_multi": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "mpnn_tmsg_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "mpnn_tmsg_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "mpnn_tmsg_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P,

@@ -192,8 +192,11 @@ constexpr int SB = 64;   // edges staged per round (chunk sizes are multiples of
 template <int DP>
 __global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __restrict__ counts, int cap, int ch,
                                                         const int* __restrict__ type_eid, const float* __restrict__ dM,
-                                                        float* __restrict__ part) {
+                                                        float* __restrict__ part, long long dm_stride,
+                                                        long long part_stride) {
   constexpr int OPT = (DP * DP + 255) / 256;  // outputs per thread (DP=32: 4, else 1)
+  dM += (size_t)blockIdx.y * dm_stride;       // blockIdx.y: message-passing step (several gradients, one launch)
+  part += (size_t)blockIdx.y * part_stride;
   __shared__ float g[SB][DP + 1];
   __shared__ float m[SB][DP + 1];
   __shared__ int ty[SB];
@@ -253,8 +256,11 @@ __global__ void __launch_bounds__(256) k_tmsg_bwd_table(TMsg a, const int* __res
 template <int DP>
 __global__ void __launch_bounds__(256) k_tmsg_bwd_table_reduce(const int* __restrict__ type_ptr,
                                                                const float* __restrict__ part, int zero_type, int ch,
-                                                               float* __restrict__ dT) {
+                                                               float* __restrict__ dT, long long part_stride,
+                                                               long long dt_stride) {
   const int u = blockIdx.x;
+  part += (size_t)blockIdx.y * part_stride;
+  dT += (size_t)blockIdx.y * dt_stride;
   float* out = dT + (size_t)u * DP * DP;
   int b = 0, e = 0;
   if (u < zero_type) {
@@ -340,8 +346,8 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // saved layout (floats): acts[(G + L + 1)][R][PW] : slot 0 = input rows (zero padded), 1..G growth outputs,
 // G+1..G+L tied outputs (slot G+L = x)
-__global__ void __launch_bounds__(256) k_enet_fwd(ENet n, int fch, float* __restrict__ acts,
-                                                  float* __restrict__ table, float* __restrict__ tableT) {
+__device__ __forceinline__ void enet_fwd_body(const ENet& n, int fch, float* __restrict__ acts,
+                                              float* __restrict__ table, float* __restrict__ tableT) {
   extern __shared__ __align__(16) float Wl[];   // [fch][P | 1] staged rows of the last Linear
   __shared__ __align__(16) float A[2][PW];
   int staged_f0 = -1;
@@ -466,9 +472,9 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, int fch, float* __rest
 // registers: thread owns a 4 x 4 micro-tile of the 64 x 64 gradient, accumulated over the CTA's rows), the growth
 // layers; partials per CTA.
 // partial layout per CTA (floats): [PW*PW tied] then for g = G-1 .. 0: [gout*gin weights][gout bias]
-__global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restrict__ acts, const float* __restrict__ dT,
-                                                  float* __restrict__ partial, int partial_stride,
-                                                  float* __restrict__ d_rows /*[R, ef] or null*/) {
+__device__ __forceinline__ void enet_bwd_body(const ENet& n, const float* __restrict__ acts,
+                                              const float* __restrict__ dT, float* __restrict__ partial,
+                                              int partial_stride, float* __restrict__ d_rows /*[R, ef] or null*/) {
   __shared__ __align__(16) float D[2][PW];       // delta of the current layer
   __shared__ __align__(16) float Ap[2][PW];      // input activation of the current layer
   __shared__ __align__(16) float dAs[PW];        // un-masked gradient w.r.t. the tied input
@@ -621,9 +627,10 @@ struct ENetDst {
   int G, P;
 };
 
-__global__ void k_enet_finish(const float* __restrict__ partial, int nparts, int stride, ENetDst d, int nb_red,
-                              const float* __restrict__ acts_x, const float* __restrict__ dT, int R, int nf, int mf,
-                              int DP, float* __restrict__ dW, float* __restrict__ dB) {
+__device__ __forceinline__ void enet_finish_body(const float* __restrict__ partial, int nparts, int stride,
+                                                 const ENetDst& d, int nb_red, const float* __restrict__ acts_x,
+                                                 const float* __restrict__ dT, int R, int nf, int mf, int DP,
+                                                 float* __restrict__ dW, float* __restrict__ dB) {
   if ((int)blockIdx.x < nb_red) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= stride) return;
@@ -670,6 +677,62 @@ __global__ void k_enet_finish(const float* __restrict__ partial, int nparts, int
     dW[(size_t)f * P + p] = s;
   else
     dB[f] = s;
+}
+
+// ---- kernels: one edge network per launch, or K sibling networks (one EdgeNetwork per message-passing step,
+// normed_basic_model.py:24-27: same layer plan and the same distinct bond rows, different weights) as ONE launch with
+// the network index in blockIdx.y -- their 52-layer chains are independent and latency-bound, so K of them cost one.
+constexpr int MAXNET = 8;
+
+__global__ void __launch_bounds__(256) k_enet_fwd(ENet n, int fch, float* __restrict__ acts,
+                                                  float* __restrict__ table, float* __restrict__ tableT) {
+  enet_fwd_body(n, fch, acts, table, tableT);
+}
+__global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restrict__ acts, const float* __restrict__ dT,
+                                                  float* __restrict__ partial, int partial_stride,
+                                                  float* __restrict__ d_rows) {
+  enet_bwd_body(n, acts, dT, partial, partial_stride, d_rows);
+}
+__global__ void k_enet_finish(const float* __restrict__ partial, int nparts, int stride, ENetDst d, int nb_red,
+                              const float* __restrict__ acts_x, const float* __restrict__ dT, int R, int nf, int mf,
+                              int DP, float* __restrict__ dW, float* __restrict__ dB) {
+  enet_finish_body(partial, nparts, stride, d, nb_red, acts_x, dT, R, nf, mf, DP, dW, dB);
+}
+
+struct ENetFwdMulti {
+  ENet n[MAXNET];
+  float* acts[MAXNET];
+  float* table[MAXNET];
+  float* tableT[MAXNET];
+};
+struct ENetBwdMulti {
+  ENet n[MAXNET];
+  const float* acts[MAXNET];
+  const float* dT[MAXNET];
+  float* partial[MAXNET];
+  float* d_rows[MAXNET];
+};
+struct ENetFinMulti {
+  ENetDst d[MAXNET];
+  const float* partial[MAXNET];
+  const float* acts_x[MAXNET];
+  const float* dT[MAXNET];
+  float* dW[MAXNET];
+  float* dB[MAXNET];
+};
+
+__global__ void __launch_bounds__(256) k_enet_fwd_multi(const __grid_constant__ ENetFwdMulti m, int fch) {
+  const int y = blockIdx.y;
+  enet_fwd_body(m.n[y], fch, m.acts[y], m.table[y], m.tableT[y]);
+}
+__global__ void __launch_bounds__(256) k_enet_bwd_multi(const __grid_constant__ ENetBwdMulti m, int partial_stride) {
+  const int y = blockIdx.y;
+  enet_bwd_body(m.n[y], m.acts[y], m.dT[y], m.partial[y], partial_stride, m.d_rows[y]);
+}
+__global__ void k_enet_finish_multi(const __grid_constant__ ENetFinMulti m, int nparts, int stride, int nb_red, int R,
+                                    int nf, int mf, int DP) {
+  const int y = blockIdx.y;
+  enet_finish_body(m.partial[y], nparts, stride, m.d[y], nb_red, m.acts_x[y], m.dT[y], R, nf, mf, DP, m.dW[y], m.dB[y]);
 }
 
 int pick_dp(int nf, int mf) {
@@ -845,6 +908,90 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   return MPNN_OK;
 }
 
+// ---- K sibling edge networks in one launch each way ---------------------------------------------------------------
+// All K networks share the layer plan (ef, n_growth, P, n_tied, nf, mf) and the distinct rows; per-network arrays are
+// HOST arrays of device pointers: growth_w / growth_b [K * n_growth] (network-major), the rest [K].
+int mpnn_enet_max_nets(void) { return MAXNET; }
+
+int mpnn_enet_fwd_multi(int K, const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
+                        const float* const* growth_b, const float* const* w_tied, int P, int n_tied,
+                        const float* const* w_last, const float* const* b_last, int nf, int mf, float* const* saved,
+                        float* const* table, float* const* tableT, cudaStream_t stream) {
+  MPNN_REQUIRE(K >= 1 && K <= MAXNET && R > 0 && n_tied >= 1 && nf > 0 && mf > 0, MPNN_ERR_ARG, "enet_fwd_multi: bad dims");
+  ENetFwdMulti m;
+  memset(&m, 0, sizeof(m));
+  for (int k = 0; k < K; ++k) {
+    MPNN_REQUIRE(fill_enet(&m.n[k], rows, R, ef, n_growth, growth_w + (size_t)k * n_growth,
+                           growth_b + (size_t)k * n_growth, w_tied[k], P, n_tied, w_last[k], b_last[k], nf, mf),
+                 MPNN_ERR_UNSUPPORTED, "enet_fwd_multi: layer plan ef=%d growth=%d P=%d not supported", ef, n_growth, P);
+    m.acts[k] = saved[k];
+    m.table[k] = table[k];
+    m.tableT[k] = tableT[k];
+  }
+  MPNN_REQUIRE(m.n[0].DP <= 64, MPNN_ERR_UNSUPPORTED, "enet_fwd_multi: feature width > 64");
+  int fch = nf * mf < 512 ? nf * mf : 512;
+  size_t smem = (size_t)fch * (P | 1) * sizeof(float);
+  MPNN_CUDA(cudaFuncSetAttribute(k_enet_fwd_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_enet_fwd_multi<<<dim3(enet_grid(R), K), 256, smem, stream>>>(m, fch);
+  MPNN_CHECK_LAUNCH("k_enet_fwd_multi");
+  return MPNN_OK;
+}
+
+// workspace: K x mpnn_enet_workspace_bytes.  d_rows [K] entries may be NULL (no gradient w.r.t. the distinct rows).
+int mpnn_enet_bwd_multi(int K, const float* rows, int R, int ef, int n_growth, const float* const* growth_w,
+                        const float* const* w_tied, int P, int n_tied, const float* const* w_last, int nf, int mf,
+                        const float* const* saved, const float* const* dT, float* const* d_growth_w,
+                        float* const* d_growth_b, float* const* d_w_tied, float* const* d_w_last,
+                        float* const* d_b_last, float* const* d_rows, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
+  MPNN_REQUIRE(K >= 1 && K <= MAXNET && R > 0 && n_tied >= 1 && nf > 0 && mf > 0, MPNN_ERR_ARG, "enet_bwd_multi: bad dims");
+  const size_t ws1 = mpnn_enet_workspace_bytes(R, ef, n_growth, P);
+  MPNN_REQUIRE(workspace_bytes >= (size_t)K * ws1, MPNN_ERR_WORKSPACE, "enet_bwd_multi: workspace too small");
+  ENetBwdMulti m;
+  ENetFinMulti f;
+  memset(&m, 0, sizeof(m));
+  memset(&f, 0, sizeof(f));
+  const size_t act_smem = (size_t)(n_growth + n_tied + 1) * PW * sizeof(float);
+  MPNN_REQUIRE(act_smem <= 160 * 1024, MPNN_ERR_UNSUPPORTED, "enet_bwd_multi: too many layers for the shared-memory stage");
+  for (int k = 0; k < K; ++k) {
+    MPNN_REQUIRE(fill_enet(&m.n[k], rows, R, ef, n_growth, growth_w + (size_t)k * n_growth, nullptr, w_tied[k], P, n_tied,
+                           w_last[k], nullptr, nf, mf),
+                 MPNN_ERR_UNSUPPORTED, "enet_bwd_multi: layer plan not supported by the fused kernel");
+    m.acts[k] = saved[k];
+    m.dT[k] = dT[k];
+    m.partial[k] = (float*)((char*)workspace + (size_t)k * ws1);
+    m.d_rows[k] = d_rows ? d_rows[k] : nullptr;
+    ENetDst& dst = f.d[k];
+    dst.tied = d_w_tied[k];
+    dst.G = n_growth;
+    dst.P = P;
+    size_t off = (size_t)PW * PW;
+    for (int g = n_growth - 1; g >= 0; --g) {
+      dst.gw[g] = d_growth_w[(size_t)k * n_growth + g];
+      dst.gb[g] = d_growth_b[(size_t)k * n_growth + g];
+      dst.off[g] = (int)off;
+      dst.wn[g] = m.n[k].gout[g] * m.n[k].gin[g];
+      dst.bn[g] = m.n[k].gout[g];
+      off += (size_t)dst.wn[g] + dst.bn[g];
+    }
+    f.partial[k] = m.partial[k];
+    f.acts_x[k] = saved[k] + (size_t)(n_growth + n_tied) * R * PW;
+    f.dT[k] = dT[k];
+    f.dW[k] = d_w_last[k];
+    f.dB[k] = d_b_last[k];
+  }
+  const int stride = enet_partial_stride(m.n[0]);
+  const int nparts = enet_grid(R);
+  MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
+  k_enet_bwd_multi<<<dim3(nparts, K), 256, act_smem, stream>>>(m, stride);
+  MPNN_CHECK_LAUNCH("k_enet_bwd_multi");
+  const int nb_red = ceil_div(stride, 256);
+  const int nb_last = ceil_div((long long)mf * nf * (P + 1), 256);
+  k_enet_finish_multi<<<dim3(nb_red + nb_last, K), 256, 0, stream>>>(f, nparts, stride, nb_red, R, nf, mf, m.n[0].DP);
+  MPNN_CHECK_LAUNCH("k_enet_finish_multi");
+  return MPNN_OK;
+}
+
 // ---- typed message + aggregation ------------------------------------------------------------------------
 size_t mpnn_tmsg_bwd_workspace_bytes(int edge_capacity, int unique_capacity, int nf, int mf, int B) {
   int DP = pick_dp(nf, mf);
@@ -903,8 +1050,9 @@ int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, co
   do {                                                                                                            \
     if (dH) k_tmsg_bwd_src<DPV><<<grid, 256, 0, stream>>>(a, col_ptr, csc_eid, dM, S ? Dsum : nullptr, dH);        \
     if (dT) {                                                                                                     \
-      k_tmsg_bwd_table<DPV><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part);        \
-      k_tmsg_bwd_table_reduce<DPV><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT);   \
+      k_tmsg_bwd_table<DPV><<<chunks, 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part, 0, 0);  \
+      k_tmsg_bwd_table_reduce<DPV><<<unique_capacity + 1, 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT, 0, \
+                                                                            0);                                  \
       if (S) k_tmsg_bwd_table_zero<DPV><<<1, 256, 0, stream>>>(S, Dsum, B, nf, mf, zero_type, dT);                \
     }                                                                                                             \
   } while (0)
@@ -915,6 +1063,43 @@ int mpnn_tmsg_bwd(const int* row_ptr, const int* col_ptr, const int* csc_eid, co
   }
 #undef MPNN_TMSG_BWD
   MPNN_CHECK_LAUNCH("k_tmsg_bwd");
+  return MPNN_OK;
+}
+
+// table gradients of K message-passing steps that share the edge list and the sender states (documented per-pair form,
+// no HEAD terms) as one launch pair: dM [K][n_rows][mf] -> dT [K][(unique_capacity+1)][DP][DP].
+// workspace: K x mpnn_tmsg_bwd_workspace_bytes.
+int mpnn_tmsg_bwd_table_multi(int K, const int* edge_src, const int* edge_dst, const int* uid, const int* type_ptr,
+                              const int* type_eid, const int* counts, const float* alpha, const float* H, int n_rows,
+                              int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dT,
+                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(K >= 1 && n_rows > 0 && nf > 0 && mf > 0, MPNN_ERR_ARG, "tmsg_bwd_table_multi: bad dims");
+  int DP = pick_dp(nf, mf);
+  MPNN_REQUIRE(DP <= 32, MPNN_ERR_UNSUPPORTED, "tmsg_bwd_table_multi: feature width > 32");
+  const size_t ws1 = mpnn_tmsg_bwd_workspace_bytes(edge_capacity, unique_capacity, nf, mf, 1);
+  MPNN_REQUIRE(workspace_bytes >= (size_t)K * ws1, MPNN_ERR_WORKSPACE, "tmsg_bwd_table_multi: workspace too small");
+  const int zero_type = unique_capacity;
+  TMsg a = {nullptr, edge_src, edge_dst, uid, alpha, H, nullptr, nullptr, nullptr, nullptr, n_rows, 1, nf, mf, zero_type,
+            n_rows};
+  float* part = (float*)workspace;
+  const long long part_stride = (long long)(ws1 / sizeof(float));
+  const int ch = table_chunk(edge_capacity);
+  const int chunks = ceil_div(edge_capacity > 0 ? edge_capacity : 1, ch);
+  const long long dm_stride = (long long)n_rows * mf, dt_stride = (long long)(unique_capacity + 1) * DP * DP;
+#define MPNN_TMSG_TM(DPV)                                                                                            \
+  do {                                                                                                               \
+    k_tmsg_bwd_table<DPV><<<dim3(chunks, K), 256, 0, stream>>>(a, counts, edge_capacity, ch, type_eid, dM, part,      \
+                                                                dm_stride, part_stride);                             \
+    k_tmsg_bwd_table_reduce<DPV><<<dim3(unique_capacity + 1, K), 256, 0, stream>>>(type_ptr, part, zero_type, ch, dT, \
+                                                                                   part_stride, dt_stride);          \
+  } while (0)
+  switch (DP) {
+    case 8: MPNN_TMSG_TM(8); break;
+    case 16: MPNN_TMSG_TM(16); break;
+    default: MPNN_TMSG_TM(32); break;
+  }
+#undef MPNN_TMSG_TM
+  MPNN_CHECK_LAUNCH("k_tmsg_bwd_table_multi");
   return MPNN_OK;
 }
 

@@ -938,6 +938,90 @@ class TableLayoutFn(torch.autograd.Function):
         return dflat, None, None
 
 
+class MultiEdgeNetTableFn(torch.autograd.Function):
+    """EdgeNetTableFn for K sibling networks (one EdgeNetwork per message-passing step, normed_basic_model.py:24-27: same
+    layer plan, same distinct rows, different weights) as ONE launch each way (csrc/typed.cu k_enet_*_multi).
+    params: per network [w_tied, W_last, B_last, growth weights (G), growth biases (G)].
+    Returns (table_0, tableT_0, table_1, tableT_1, ...)."""
+
+    @staticmethod
+    def forward(ctx, urows, n_tied, nf, mf, K, G, *params):
+        lib = _lib.load()
+        per = 3 + 2 * G
+        assert len(params) == K * per
+        urows = f32c(urows)
+        _need_cuda(urows)
+        nets = [[f32c(t) for t in params[k * per:(k + 1) * per]] for k in range(K)]
+        R, ef = urows.shape
+        P = nets[0][0].shape[0]
+        DP = table_dp(nf, mf)
+        dev = urows.device
+        nsaved = lib.mpnn_enet_saved_floats(R, G, n_tied)
+        saved = [torch.empty(nsaved, dtype=torch.float32, device=dev) for _ in range(K)]
+        tables = [torch.empty(R, DP, DP, dtype=torch.float32, device=dev) for _ in range(K)]
+        tablesT = [torch.empty(R, DP, DP, dtype=torch.float32, device=dev) for _ in range(K)]
+        gw = [w for n in nets for w in n[3:3 + G]]
+        gb = [b for n in nets for b in n[3 + G:3 + 2 * G]]
+        check(lib.mpnn_enet_fwd_multi(K, ptr(urows), R, ef, G, ptr_array(gw), ptr_array(gb),
+                                      ptr_array([n[0] for n in nets]), P, n_tied, ptr_array([n[1] for n in nets]),
+                                      ptr_array([n[2] for n in nets]), nf, mf, ptr_array(saved), ptr_array(tables),
+                                      ptr_array(tablesT), stream()), "enet_fwd_multi")
+        ctx.save_for_backward(urows, *([t for n in nets for t in n] + saved))
+        ctx.dims = (R, ef, G, P, n_tied, nf, mf, K)
+        out = []
+        for k in range(K):
+            out += [tables[k], tablesT[k]]
+        ctx.mark_non_differentiable(*tablesT)
+        return tuple(out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        R, ef, G, P, n_tied, nf, mf, K = ctx.dims
+        per = 3 + 2 * G
+        urows = ctx.saved_tensors[0]
+        flat = ctx.saved_tensors[1:1 + K * per]
+        saved = list(ctx.saved_tensors[1 + K * per:])
+        nets = [list(flat[k * per:(k + 1) * per]) for k in range(K)]
+        dev = urows.device
+        DP = table_dp(nf, mf)
+        dTs, ready = [], None
+        for k in range(K):
+            g = grads[2 * k]
+            if g is None:
+                g = torch.zeros(R, DP, DP, dtype=torch.float32, device=dev)
+            else:
+                ev = _ready_get(g)
+                ready = ev if ev is not None else ready
+                g = f32c(g)
+            dTs.append(g)
+        d_nets = [[torch.empty_like(t) for t in n] for n in nets]
+        need_rows = ctx.needs_input_grad[0]
+        d_rows = [torch.empty_like(urows) for _ in range(K)] if need_rows else None
+        side = (SIDE_STREAM_ENABLED and not need_rows
+                and all(getattr(t, "grad", None) is None for n in nets for t in n))
+        if not side and ready is not None:
+            torch.cuda.current_stream(dev).wait_event(ready)
+        with (_on_side_stream(dev, dTs + [urows] + list(flat) + saved, lane=0, after=ready) if side else _inline()):
+            ws = workspace(K * lib.mpnn_enet_workspace_bytes(R, ef, G, P), dev)
+            gw = [w for n in nets for w in n[3:3 + G]]
+            d_gw = [w for n in d_nets for w in n[3:3 + G]]
+            d_gb = [b for n in d_nets for b in n[3 + G:3 + 2 * G]]
+            check(lib.mpnn_enet_bwd_multi(K, ptr(urows), R, ef, G, ptr_array(gw), ptr_array([n[0] for n in nets]), P,
+                                          n_tied, ptr_array([n[1] for n in nets]), nf, mf, ptr_array(saved),
+                                          ptr_array(dTs), ptr_array(d_gw), ptr_array(d_gb),
+                                          ptr_array([n[0] for n in d_nets]), ptr_array([n[1] for n in d_nets]),
+                                          ptr_array([n[2] for n in d_nets]), ptr_array(d_rows) if d_rows else None,
+                                          ptr(ws), ws.numel(), stream()), "enet_bwd_multi")
+        d_urows = None
+        if need_rows:
+            d_urows = d_rows[0]
+            for k in range(1, K):
+                d_urows = d_urows + d_rows[k]
+        return (d_urows, None, None, None, None, None) + tuple(t for n in d_nets for t in n)
+
+
 class TableHolder(object):
     """Rides on a table tensor produced by EdgeNetTableFn: how many message functions consume it in this forward pass.
     With exactly one consumer its gradient dT goes straight from TypedMessageFn.backward into EdgeNetTableFn.backward
@@ -1191,24 +1275,41 @@ class ChainFn(torch.autograd.Function):
                                     el.B, el.N, d, d, el.Ecap, ti.Ucap, ptr(dMsum), ptr(dH), ptr(dT), ptr(wsb),
                                     wsb.numel(), stream()), "tmsg_bwd")
 
-        for ts in groups.values():
-            t0 = ts[0]
-            dMsum = dM[t0] if len(ts) == 1 else dM[ts].sum(0)
-            want_T = any(need_T[t] for t in ts)
-            if need_H0:
+        glist = list(groups.values())
+        if need_H0:
+            for ts in glist:
+                t0 = ts[0]
+                dMsum = dM[t0] if len(ts) == 1 else dM[ts].sum(0)
                 dHt = torch.empty_like(H0)
                 run(dMsum, t0, dHt, None)
                 dH0 = dHt if dH0 is None else dH0 + dHt
-            if want_T:
-                side = SIDE_STREAM_ENABLED and len(ts) == 1
-                cm = _on_side_stream(dev, [dM, H0, tables[t0], tablesT[t0], alpha], lane=1, after=produced) if side \
-                    else _inline()
-                with cm:
-                    dT = torch.empty_like(tables[t0])
-                    run(dMsum, t0, None, dT)
+        want = [ts for ts in glist if any(need_T[t] for t in ts)]
+        if want:
+            # the table gradients of all steps as ONE launch pair; they only feed the edge networks' parameter
+            # gradients: side lane, behind the step kernel
+            K = len(want)
+            single = all(len(ts) == 1 for ts in want)
+            if single and [ts[0] for ts in want] == list(range(T)):
+                dMs = dM
+            else:
+                dMs = torch.stack([dM[ts[0]] if len(ts) == 1 else dM[ts].sum(0) for ts in want])
+            side = SIDE_STREAM_ENABLED
+            DPt = tables[0].shape[-1]
+            cm = _on_side_stream(dev, [dMs, H0, alpha], lane=1, after=produced if dMs is dM else None) if side \
+                else _inline()
+            with cm:
+                ti.wait_sorted()
+                dTall = torch.empty(K, ti.Ucap + 1, DPt, DPt, dtype=torch.float32, device=dev)
+                wsb = workspace(K * lib.mpnn_tmsg_bwd_workspace_bytes(el.Ecap, ti.Ucap, d, d, 1), dev)
+                check(lib.mpnn_tmsg_bwd_table_multi(K, ptr(el.edge_src), ptr(el.edge_dst), ptr(ti.uid), ptr(ti.type_ptr),
+                                                    ptr(ti.type_eid), ptr(ti.counts), ptr(alpha), ptr(H0), el.n_rows, d,
+                                                    d, el.Ecap, ti.Ucap, ptr(dMs), ptr(dTall), ptr(wsb), wsb.numel(),
+                                                    stream()), "tmsg_bwd_table_multi")
+            for k, ts in enumerate(want):
+                dT = dTall[k]
                 if side:
                     _ready_put(dT, cm.done)
-                dTs[t0] = dT     # the other steps of the group point at the same table: autograd sums, they get None
+                dTs[ts[0]] = dT   # the other steps of the group point at the same table: autograd sums, they get None
         return (dH0, dh, None, None, None, dW_ih, dW_hh, db_ih, db_hh) + tuple(dTs) + (None,) * T + tuple(d_aff)
 
 

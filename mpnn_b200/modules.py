@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import graph
-from .functional import (BilinearEdgeFn, ChainFn, DenseAggFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
+from .functional import (BilinearEdgeFn, ChainFn, DenseAggFn, MultiEdgeNetTableFn, EdgeMessageFn, EdgeNetTableFn, EdgeTrunkFn, GatherRowsFn, GatherSumFn,
                          GraphLevelOutputFn, GRUFn, GRUParamHubFn, SharedGradSession, TableHolder, LinearFn, LSTMCellHiddenFn, MaskBN1dFn, MaskBNFn,
                          Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, chain_supported, table_dp, tc_dp, typed_dp)
@@ -619,6 +619,47 @@ class LazyState(_LazyTensor):
         return self._value
 
 
+def _tables_for_steps(msgs, el):
+    """Per-type matrices of every step's edge network for one edge list.  Networks whose cached table cannot be reused
+    are evaluated together: K sibling networks with the same layer plan (normed_basic_model.py:24-27) are ONE launch
+    each way (`MultiEdgeNetTableFn`); anything else goes through the per-network path."""
+    todo, seen = [], set()
+    for m in msgs:
+        net = m._net
+        c = net._table_cache
+        if id(net) in seen:
+            continue
+        if m._reuse and c is not None and c[0] is el:
+            continue
+        seen.add(id(net))
+        todo.append(net)
+    lib = _lib.load()
+    ti = el.typed()
+    plan = lambda n: (n.nf, n.ef, n.mf, n.P, len(n._growth_idx))
+    fusable = (len(todo) >= 2 and len(todo) <= lib.mpnn_enet_max_nets() and len({plan(n) for n in todo}) == 1
+               and table_dp(todo[0].nf, todo[0].mf) <= lib.mpnn_enet_max_dp()
+               and lib.mpnn_enet_supported(todo[0].ef, len(todo[0]._growth_idx), todo[0].P))
+    if not fusable:
+        for n in todo:
+            n._table_prefetch = None
+            table, tableT = n._compute_table(el)
+            n._table_cache = (el, table, tableT)
+            n._msg_cache = {}
+        return
+    n0 = todo[0]
+    G = len(n0._growth_idx)
+    params = []
+    for n in todo:
+        W, Bv = n._last()
+        params += [n.edge_map[n._tied_idx][0].weight, W, Bv]
+        params += [n.edge_map[i].weight for i in n._growth_idx] + [n.edge_map[i].bias for i in n._growth_idx]
+    outs = MultiEdgeNetTableFn.apply(ti.urows, _N_TIED, n0.nf, n0.mf, len(todo), G, *params)
+    for k, n in enumerate(todo):
+        n._table_prefetch = None
+        n._table_cache = (el, outs[2 * k], outs[2 * k + 1])
+        n._msg_cache = {}
+
+
 def _fused_chain(head):
     """Evaluates the chain ending in `head` with the persistent step kernel when every link fits it; None otherwise."""
     steps, node = [], head
@@ -660,9 +701,10 @@ def _fused_chain(head):
     if not all(gru._src._messages._net._typed_ok(bfm, el) for gru, _ in steps):
         return None
     tables, tablesT, bnspec, affine = [], [], [], []
+    _tables_for_steps([gru._src._messages for gru, _ in steps], el)
     for gru, bn in steps:
         m = gru._src._messages
-        table, tableT = m._net._table(el, m._reuse)
+        table, tableT = m._net._table(el, True)      # cached by _tables_for_steps
         tables.append(table)
         tablesT.append(tableT)
         if bn is None:
