@@ -34,6 +34,11 @@ typedef struct CUstream_st* mpnn_stream_t; /* == cudaStream_t */
 #define MPNN_ERR_WORKSPACE -4
 
 int mpnn_version(void);            /* major*10000 + minor*100 + patch */
+/* Precision of the widths 33..256: 1 (default) = tcgen05 kernels with TF32 operands and fp32 accumulation (SURVEY 8c:
+ * <= 2e-2 relative after the GRU / readout); 0 = the fp32 kernels everywhere (fp32 accuracy, a fraction of the speed).
+ * Process-wide; returns the previous setting. */
+int mpnn_set_tensor_cores(int enabled);
+int mpnn_tensor_cores_enabled(void);
 const char* mpnn_last_error(void); /* thread-local, valid until the next failing call on this thread */
 
 /* ---- generic building blocks ------------------------------------------------------------------------ */

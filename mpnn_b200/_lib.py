@@ -20,6 +20,8 @@ _PP = ctypes.POINTER(ctypes.c_void_p)
 SIGNATURES = {
     "mpnn_version": (_I, []),
     "mpnn_last_error": (ctypes.c_char_p, []),
+    "mpnn_set_tensor_cores": (_I, [_I]),
+    "mpnn_tensor_cores_enabled": (_I, []),
     "mpnn_segment_sum": (_I, [_P, _P, _P, _I, _I, _L, _P, _L, _I, _F, _P]),
     "mpnn_colsum_workspace_bytes": (_Z, [_L, _I]),
     "mpnn_colsum": (_I, [_P, _P, _L, _I, _L, _L, _P, _I, _P, _Z, _P]),

@@ -1102,9 +1102,13 @@ __global__ void __launch_bounds__(256) k_tc_pack_image(const float* __restrict__
   }
 }
 
+// Process-wide precision switch (mpnn_set_tensor_cores): with the tensor cores off every width is served by the fp32
+// kernels (per-edge contraction, tile GEMMs), at fp32 accuracy and a fraction of the speed.
+int g_tc_enabled = 1;
+
 int tc_dp(int nf, int mf) {
   int d = nf > mf ? nf : mf;
-  if (d <= 32 || d > 256 || (nf & 3) || (mf & 3)) return -1;
+  if (!g_tc_enabled || d <= 32 || d > 256 || (nf & 3) || (mf & 3)) return -1;
   return pow2_at_least(d, 64);
 }
 int tc_grid() { return mpnn_num_sms(); }
@@ -1155,6 +1159,15 @@ extern "C" {
 
 // padded feature width served by the tensor-core typed path (64, 128 or 256); -1 = not served
 int mpnn_tc_dp(int nf, int mf) { return tc_dp(nf, mf); }
+
+// 1 (default): widths 33..256 run on the tcgen05 kernels with TF32 operands; 0: fp32 kernels everywhere.  Returns the
+// previous setting.
+int mpnn_set_tensor_cores(int enabled) {
+  const int prev = g_tc_enabled;
+  g_tc_enabled = enabled ? 1 : 0;
+  return prev;
+}
+int mpnn_tensor_cores_enabled(void) { return g_tc_enabled; }
 
 // plan buffer: the type-sorted edge list cut into single-type tiles; built once per edge list
 size_t mpnn_tc_plan_bytes(int edge_capacity, int unique_capacity) {
@@ -1434,7 +1447,7 @@ static bool tc_split(int W, int* parts, int* width) {
   return false;
 }
 static int tc_linear_plan(int K, int N, int* kseg, int* Ks, int* G, int* Nb) {
-  if ((K <= 32 && N <= 32) || !tc_split(K, kseg, Ks) || !tc_split(N, G, Nb)) return -1;
+  if (!g_tc_enabled || (K <= 32 && N <= 32) || !tc_split(K, kseg, Ks) || !tc_split(N, G, Nb)) return -1;
   const int m = *Ks > *Nb ? *Ks : *Nb;
   return pow2_at_least(m, 64);
 }
@@ -1491,7 +1504,7 @@ int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, c
 }
 
 // ---- fused masked GRU forward on the tensor cores (widths 33..256, multiples of 4) -------------------------------
-int mpnn_tc_gru_supported(int d) { return (d > 32 && d <= 256 && (d & 3) == 0) ? 1 : 0; }
+int mpnn_tc_gru_supported(int d) { return (g_tc_enabled && d > 32 && d <= 256 && (d & 3) == 0) ? 1 : 0; }
 
 static void tc_gru_dims(int d, int* DP, int* KP, int* ncb) {
   *KP = pow2_at_least(d, 64);

@@ -26,6 +26,8 @@ extern "C" int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, in
                                      int G, int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
                                      size_t workspace_bytes, cudaStream_t stream);
 
+extern "C" int mpnn_tensor_cores_enabled(void);
+
 namespace {
 
 constexpr int TR = 64;        // rows per tile
@@ -320,7 +322,7 @@ constexpr int MAX_TIED = 64;   // tied layers the wide-trunk backward can stack 
 constexpr int WIDE_STACK_ROWS = 256;   // the delta stack is kept only for few rows (typed path: distinct bond rows)
 // widths whose tied-weight gradient runs as ONE stacked X^T D GEMM on the tensor cores (TF32 operands)
 inline int wide_block(int P) { return P % 256 == 0 ? 256 : (P % 128 == 0 ? 128 : 64); }
-inline bool wide_dw_on_tc(int P) { return P % 64 == 0 && P >= 256; }
+inline bool wide_dw_on_tc(int P) { return mpnn_tensor_cores_enabled() && P % 64 == 0 && P >= 256; }
 
 }  // namespace
 

@@ -69,6 +69,8 @@ _FWD_SIDE = set()
 
 def _note_forward_side_work(device, lane=0):
     """forward work was enqueued on a side stream (sibling table prefetch, type sort): `join_side_streams()` waits for it"""
+    if not torch.cuda.is_current_stream_capturing():
+        return      # eager mode: consumers wait for the work's own event; only a capture must re-join its forked branches
     d = device.index if device.index is not None else torch.cuda.current_device()
     _FWD_SIDE.add(d if lane == 0 else (d, lane))
 

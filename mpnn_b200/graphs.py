@@ -43,6 +43,7 @@ class GraphedStep(object):
         self.graph = torch.cuda.CUDAGraph()
         graph.clear_cache()
         del graph._CAPTURED_COUNTS[:]
+        functional._FWD_SIDE.clear()
         with graph.capacities(self.edge_capacity, self.unique_capacity):
             with torch.cuda.graph(self.graph):
                 self.loss = step_fn(self.static)

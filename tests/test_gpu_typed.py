@@ -211,8 +211,9 @@ def test_skinny_gemm_matches_torch(dev, shape, form):
     assert float((C.double() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
 
 
-def test_sibling_table_prefetch_is_transparent(dev):
-    """Per-step edge networks (normed_basic_model.py:24-27): from the second batch on, the tables of mf_1.. are computed
+def test_sibling_table_prefetch_is_transparent(dev, monkeypatch):
+    """(Module-by-module evaluation, i.e. the lazy step chain switched off: with it, sibling networks are ONE launch.)
+    Per-step edge networks (normed_basic_model.py:24-27): from the second batch on, the tables of mf_1.. are computed
     ahead of time on the side stream when mf_0 first sees the batch.  Outputs and every gradient must be bit-identical
     to the run with the prefetch switched off, and match the CPU oracle."""
     from mpnn_b200 import graph, modules as M, synthetic
@@ -237,6 +238,7 @@ def test_sibling_table_prefetch_is_transparent(dev):
         return out.detach().clone(), a.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
 
     assert M.SIBLING_PREFETCH
+    monkeypatch.setattr(M, "LAZY_CHAIN", False)
     run(batches[0])                      # learns the group mf0 -> (mf1, mf2)
     assert mod.mfs[0]._table_group is not None and len(mod.mfs[0]._table_group) == 3
     got = [run(b) for b in batches[1:]]  # prefetched

@@ -218,7 +218,7 @@ def test_wrong_adjacency_is_rejected(dev):
     net = EdgeNetwork(8, 8, 8).to(dev)
     other = t["adj"].clone()
     with pytest.raises(RuntimeError):
-        AdjMsgAgg(1)(net(t["afm"][..., :8].contiguous(), tb), other)
+        AdjMsgAgg(1)(net(t["afm"][..., :8].contiguous(), tb), other) + 0.0    # (lazy: evaluated by the first consumer)
 
 
 def test_encoded_step_is_graph_capturable(dev):
