@@ -301,6 +301,17 @@ int mpnn_tmsg_bwd_table_multi(int K, const int* edge_src, const int* edge_dst, c
                               int nf, int mf, int edge_capacity, int unique_capacity, const float* dM, float* dT,
                               void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 
+/* ---- a0 (small batches): compaction + exact de-duplication as ONE cooperative launch (csrc/prep.cu) ------------------
+ * Same outputs as mpnn_compact_count/_fill + mpnn_dedup_rows in capacity mode: CSR/CSC of the edge set (row-major =
+ * torch.nonzero order), edge_w = adj value, uid = distinct-row id by first occurrence (clamped to the zero type
+ * `unique_capacity` on overflow), urows [unique_capacity+1, ef], counts = {E, U, overflow, 0} (the overflow flag is only
+ * ever SET: sticky across replays).  The workspace must be zero on first use and is left zero. */
+int mpnn_prep_supported(int B, int N, int ef, int unique_capacity);
+size_t mpnn_prep_workspace_bytes(int B, int unique_capacity);
+int mpnn_prep_edges(const float* bfm, const float* adj, int B, int N, int ef, int edge_capacity, int unique_capacity,
+                    int* row_ptr, int* col_ptr, int* edge_src, int* edge_dst, float* edge_w, int* csc_eid, int* uid,
+                    float* urows, int* counts, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+
 /* ---- x1: the whole T-step message-passing loop as one persistent kernel each way (feature widths <= 32) ---------
  * h <- bn_t(GRU(sum_{e in E(i)} alpha_e T_t[uid_e]^T H0[src_e], h) * mask) for t = 0..T-1: the loops of
  * models/normed_basic_model.py:56-59, basic_model.py:50-58, normed_encoded_basic_model_ecfp.py:67-69 on the typed

@@ -109,6 +109,9 @@ SIGNATURES = {
     "mpnn_softmax_mul_bwd": (_I, [_P, _P, _P, _L, _I, _P, _P, _P]),
     "mpnn_dense_agg_fwd": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "mpnn_dense_agg_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P]),
+    "mpnn_prep_supported": (_I, [_I, _I, _I, _I]),
+    "mpnn_prep_workspace_bytes": (_Z, [_I, _I]),
+    "mpnn_prep_edges": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_chain_supported": (_I, [_I, _I]),
     "mpnn_chain_debug": (_I, [_P]),
     "mpnn_chain_saved_floats": (_L, [_L, _I, _I]),

@@ -98,6 +98,66 @@ class capacities(object):
         return False
 
 
+FUSED_PREP = os.environ.get("MPNN_B200_FUSED_PREP", "1") != "0"
+
+
+def _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev):
+    """type_ptr / type_eid / type_pos (edges grouped by distinct row, stable): only the backward's table-gradient kernels
+    and the tensor-core plan read them, so the three dependent launches run on a side stream (a parallel branch of the
+    captured step).  Returns (type_ptr, type_eid, type_pos, done event)."""
+    from . import functional
+    lib = _lib.load()
+    type_ptr = torch.empty(Ucap + 1, dtype=torch.int32, device=dev)
+    type_eid = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    type_pos = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    main = torch.cuda.current_stream(dev)
+    _, side = functional._side_stream(dev, lane=5)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        ws2 = _lib.workspace(lib.mpnn_type_sort_workspace_bytes(Ecap, Ucap), dev)
+        _lib.check(lib.mpnn_type_sort(_lib.ptr(uid), _lib.ptr(counts), Ecap, Ucap, _lib.ptr(type_ptr),
+                                      _lib.ptr(type_eid), _lib.ptr(type_pos), _lib.ptr(ws2), ws2.numel(),
+                                      _lib.stream()), "type_sort")
+        done = torch.cuda.Event()
+        done.record(side)
+    for t in (uid, counts, type_ptr, type_eid, type_pos):
+        t.record_stream(side)
+    functional._note_forward_side_work(dev, lane=5)
+    return type_ptr, type_eid, type_pos, done
+
+
+def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap):
+    """capacity mode, small batches: compaction + de-duplication as ONE cooperative launch (csrc/prep.cu)"""
+    lib = _lib.load()
+    dev = bfm_c.device
+    n_rows = B * N
+    i32 = dict(dtype=torch.int32, device=dev)
+    row_ptr = torch.empty(n_rows + 1, **i32)
+    col_ptr = torch.empty(n_rows + 1, **i32)
+    edge_src = torch.empty(Ecap, **i32)
+    edge_dst = torch.empty(Ecap, **i32)
+    csc_eid = torch.empty(Ecap, **i32)
+    uid = torch.empty(max(Ecap, 1), **i32)
+    edge_w = torch.empty(Ecap, dtype=torch.float32, device=dev)
+    urows = torch.empty(Ucap + 1, ef, dtype=torch.float32, device=dev)
+    counts = torch.zeros(4, **i32)
+    ws = _lib.clean_workspace(lib.mpnn_prep_workspace_bytes(B, Ucap), dev)
+    _lib.check(lib.mpnn_prep_edges(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, Ecap, Ucap, _lib.ptr(row_ptr),
+                                   _lib.ptr(col_ptr), _lib.ptr(edge_src), _lib.ptr(edge_dst), _lib.ptr(edge_w),
+                                   _lib.ptr(csc_eid), _lib.ptr(uid), _lib.ptr(urows), _lib.ptr(counts), _lib.ptr(ws),
+                                   ws.numel(), _lib.stream()), "prep_edges")
+    el = EdgeList(B, N, ef, None, row_ptr, col_ptr, edge_src, edge_dst, edge_w, None, csc_eid)
+    el.Ecap = Ecap
+    type_ptr, type_eid, type_pos, done = _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev)
+    ti = TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], None, Ucap)
+    ti.sort_event = done
+    el._typed = ti
+    _CAPTURED_COUNTS.append(counts)
+    return el
+
+
 def compact_edges(bfm, adj=None, dedup=True):
     """Compacts (bfm, adj) -> EdgeList.  One 4-byte device->host read (the edge count) sizes the arrays
     (none in capacity mode)."""
@@ -112,6 +172,8 @@ def compact_edges(bfm, adj=None, dedup=True):
         assert tuple(adj_c.shape) == (B, N, N), "adj must be [B,N,N]"
     dev = bfm_c.device
     n_rows = B * N
+    if _CAPACITY is not None and dedup and FUSED_PREP and lib.mpnn_prep_supported(B, N, ef, _CAPACITY[1]):
+        return _prep_edges(bfm_c, adj_c, B, N, ef, _CAPACITY[0], _CAPACITY[1])
     row_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
     col_ptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
     ws = _lib.workspace(lib.mpnn_compact_workspace_bytes(B, N), dev)

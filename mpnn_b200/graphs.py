@@ -66,10 +66,13 @@ class GraphedStep(object):
         return self.replay()
 
     def check(self):
-        """One small D2H read: did any replayed batch exceed the captured edge / distinct-row capacities?"""
+        """One small D2H read: did any batch replayed since the last check exceed the captured edge / distinct-row
+        capacities?  (Kernels clamp their reads to the capacities, so an overflowing batch computes on a truncated edge
+        list; the step's result must be discarded by the caller.)"""
         for c in self._counts:
             e, u, flag, _ = c.cpu().tolist()
             if flag:
+                c[2] = 0     # the flag is sticky on the device (set by any replay since the last check): clear it here
                 raise RuntimeError("mpnn_b200.GraphedStep: batch with %d edges / %d distinct bond rows exceeds the "
                                    "captured capacities (%d / %d); re-capture with larger capacities"
                                    % (e, u, self.edge_capacity, self.unique_capacity))

@@ -295,3 +295,56 @@ def test_small_gemm_matches_torch(dev, shape, form):
           "gemm")
     want = ref + C0.double().cpu()
     assert float((C.double().cpu() - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("case", ["qm9", "lipo", "weighted", "empty", "tiny", "overflow_e", "overflow_u"])
+def test_fused_prep_is_bit_identical_to_the_multi_launch_path(dev, case, monkeypatch):
+    """csrc/prep.cu (compaction + de-duplication as one cooperative launch, capacity mode) against csrc/compact.cu +
+    csrc/dedup.cu: every array bit-identical (CSR, CSC, adjacency values, type ids by first occurrence, distinct rows,
+    counts), incl. adjacency-only / bond-only edges, an empty batch, single-atom graphs and both overflows."""
+    from mpnn_b200 import graph, synthetic
+    if case in ("qm9", "lipo"):
+        b = synthetic.make_batch(case, B=37)
+        bfm, adj = torch.from_numpy(b["bfm"]), torch.from_numpy(b["adj"])
+    elif case == "empty":
+        bfm, adj = torch.zeros(3, 5, 5, 4), torch.zeros(3, 5, 5)
+    else:
+        b = synthetic.small_batch(B=9 if case != "tiny" else 2, n_lo=1, n_hi=11 if case != "tiny" else 2, afm_width=3,
+                                  ef=5, seed=4, weighted_adj=True)
+        bfm, adj = torch.from_numpy(b["bfm"]).clone(), torch.from_numpy(b["adj"]).clone()
+        if bfm.shape[1] > 1:
+            bfm[0, 0, 1] = 0       # adjacency-only edge (all-zero bond row that IS an edge)
+            adj[-1, 0, 1] = 0      # bond-only edge
+    bfm, adj = bfm.to(dev), adj.to(dev)
+    E = int(((bfm != 0).any(-1) | (adj != 0)).sum())
+    ecap, ucap = E + 17, (64 if case in ("qm9", "lipo", "empty") else 256)   # (random bond rows: all distinct)
+    if case == "overflow_e":
+        ecap = max(E - 5, 1)
+    if case == "overflow_u":
+        ucap = 3
+    res = []
+    for fused in (True, False):
+        monkeypatch.setattr(graph, "FUSED_PREP", fused)
+        with graph.capacities(ecap, ucap):
+            el = graph.compact_edges(bfm, adj)
+        ti = el.typed()
+        ti.wait_sorted()
+        torch.cuda.synchronize()
+        res.append((el, ti))
+    (e1, t1), (e0, t0) = res
+    assert e1.rows is None and e0.rows is not None, "the fused path was not taken"
+    n = min(E, ecap)
+    assert torch.equal(e1.row_ptr, e0.row_ptr) and torch.equal(e1.col_ptr, e0.col_ptr)
+    for k in ("edge_src", "edge_dst", "edge_w", "csc_eid"):
+        assert torch.equal(getattr(e1, k)[:n], getattr(e0, k)[:n]), k
+    c1, c0 = t1.counts.cpu().tolist(), t0.counts.cpu().tolist()
+    assert (c1[0], c1[2]) == (c0[0], c0[2]) and (case == "overflow_e" or c1[1] == c0[1]), (c1, c0)
+    assert c1[2] == (1 if case.startswith("overflow") else 0)
+    U = min(c0[1], ucap)
+    if case != "overflow_e":    # (the old path de-duplicates the truncated edge list: the two see different rows then)
+        assert torch.equal(t1.urows[:U], t0.urows[:U])
+        assert float(t1.urows[U:].abs().max()) == 0.0
+        assert torch.equal(t1.uid[:n].clamp(max=ucap), t0.uid[:n].clamp(max=ucap))
+        if case != "overflow_u":
+            assert torch.equal(t1.type_ptr, t0.type_ptr) and torch.equal(t1.type_eid[:n], t0.type_eid[:n])
+    assert int(t1.uid[:n].max() if n else 0) <= ucap
