@@ -68,6 +68,9 @@ int mpnn_compact_count(const float* bfm, const float* adj, int B, int N, int ef,
 int mpnn_compact_fill(const float* bfm, const float* adj, int B, int N, int ef, const int* row_ptr, const int* col_ptr,
                       int capacity, int* edge_src, int* edge_dst, float* edge_w, float* edge_x, int* csc_eid,
                       const void* workspace, mpnn_stream_t stream);
+/* capacity mode: clamp row_ptr / col_ptr [n_rows+1] to the allocated edge slots in place (consumers walk these ranges);
+ * e_true [2 ints]: e_true[0] receives the true edge count */
+int mpnn_compact_clamp(int* row_ptr, int* col_ptr, int n_rows, int capacity, int* e_true, mpnn_stream_t stream);
 /* backward of the bond-row gather: dense[b,i,j,:] = d_edge_x[e,:] (dense is pre-zeroed by the caller) */
 int mpnn_scatter_edge_rows(const float* d_edge_x, const int* edge_dst, const int* edge_src, int E, int N, int ef,
                            float* dense, mpnn_stream_t stream);
@@ -387,7 +390,8 @@ int mpnn_head_bn_linear_mse_bwd(const float* x, const float* target, const float
  * by the call: CUDA-graph replayable); `ticket` = device uint32, zero before the first call. */
 int mpnn_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
                    float* const* exp_avg_sq, const long long* numel, float* step, unsigned int* ticket, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, mpnn_stream_t stream);
+                   float beta1, float beta2, float eps, float weight_decay, const int* const* guards, int n_guards,
+                   mpnn_stream_t stream);
 
 #ifdef __cplusplus
 }

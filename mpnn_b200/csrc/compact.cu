@@ -279,6 +279,19 @@ __global__ void __launch_bounds__(256) k_collate_edges(const int* __restrict__ e
     adj[pair] = edge_w[e];
 }
 
+// capacity mode: consumers walk row_ptr / col_ptr ranges, so the pointers themselves are clamped to the allocated edge
+// slots (an overflowing batch then computes on a truncated edge list instead of reading out of bounds); the true edge
+// count is kept for the overflow flag
+__global__ void k_clamp_ptrs(int* __restrict__ row_ptr, int* __restrict__ col_ptr, int n, int cap, int* __restrict__ e_true) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) e_true[0] = row_ptr[n];
+  if (i <= n) {
+    const int a = row_ptr[i], b = col_ptr[i];
+    if (a > cap) row_ptr[i] = cap;
+    if (b > cap) col_ptr[i] = cap;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -376,6 +389,17 @@ int mpnn_collate_ragged(const int* atom_row, const float* afm_cat, long long n, 
     k_collate_edges<<<ceil_div(E * (ef + 1), 256), 256, 0, stream>>>(edge_dst, edge_j, edge_w, edge_x, E, ef, N, bfm, adj);
     MPNN_CHECK_LAUNCH("k_collate_edges");
   }
+  return MPNN_OK;
+}
+
+// clamps row_ptr / col_ptr [n_rows + 1] to `capacity` in place and stores the true edge count in e_true[0]
+int mpnn_compact_clamp(int* row_ptr, int* col_ptr, int n_rows, int capacity, int* e_true, cudaStream_t stream) {
+  MPNN_REQUIRE(n_rows >= 0 && capacity >= 0, MPNN_ERR_ARG, "compact_clamp: bad dims");
+  // (single pass: entry n is read by thread 0 of block 0 before any block can clamp it only if it is in block 0's range;
+  //  read it first in its own launch to keep the order explicit)
+  k_clamp_ptrs<<<1, 32, 0, stream>>>(row_ptr + n_rows, col_ptr + n_rows, 0, 0x7fffffff, e_true);
+  k_clamp_ptrs<<<ceil_div(n_rows + 1, 256), 256, 0, stream>>>(row_ptr, col_ptr, n_rows, capacity, e_true + 1);
+  MPNN_CHECK_LAUNCH("k_clamp_ptrs");
   return MPNN_OK;
 }
 

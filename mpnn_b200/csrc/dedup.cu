@@ -189,7 +189,7 @@ __global__ void k_dedup_assign(const uint32_t* __restrict__ rows, const int* __r
   if (e == 0) {
     counts[0] = Eraw;
     counts[1] = U;
-    counts[2] = (Eraw > cap || U > ucap) ? 1 : 0;
+    if (Eraw > cap || U > ucap) counts[2] = 1;   // sticky: cleared only by the host (GraphedStep.check)
     counts[3] = 0;
   }
   if (e >= E) return;

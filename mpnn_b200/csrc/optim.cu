@@ -21,10 +21,14 @@ struct AdamPack {
   int first_block[ADAM_MAXT + 1];    // CTA range of tensor i
   int numel[ADAM_MAXT];
   int n;
+  const int* guard[8];               // overflow flags of the step's edge lists (counts[2] of each): any set -> no update
+  int n_guard;
 };
 
 __global__ void __launch_bounds__(256) k_adam(AdamPack pk, float* __restrict__ step, unsigned int* __restrict__ ticket,
                                               int bump, float lr, float b1, float b2, float eps, float wd) {
+  for (int q = 0; q < pk.n_guard; ++q)
+    if (pk.guard[q][2] != 0) return;   // a batch overflowed the captured capacities: its gradients are not applied
   const float t = step[0] + 1.f;
   int i = 0;
   while (i + 1 < pk.n && (int)blockIdx.x >= pk.first_block[i + 1]) ++i;
@@ -77,10 +81,13 @@ extern "C" {
 
 // n tensors: params[i], grads[i], exp_avg[i], exp_avg_sq[i] (device pointers, numel[i] floats each; host arrays).
 // step: device float (number of steps taken so far; incremented by this call); ticket: device uint32, zero on first use.
+// guards: HOST array of n_guards (<= 8) device pointers to `counts` arrays of the step's edge lists: when any counts[2]
+// (capacity overflow of a captured step) is set, the whole update is skipped on the device.
 int mpnn_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
                    float* const* exp_avg_sq, const long long* numel, float* step, unsigned int* ticket, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, cudaStream_t stream) {
-  MPNN_REQUIRE(n >= 0 && step && ticket, MPNN_ERR_ARG, "adam_step: bad arguments");
+                   float beta1, float beta2, float eps, float weight_decay, const int* const* guards, int n_guards,
+                   cudaStream_t stream) {
+  MPNN_REQUIRE(n >= 0 && step && ticket && n_guards >= 0 && n_guards <= 8, MPNN_ERR_ARG, "adam_step: bad arguments");
   int done = 0;
   while (done < n) {
     AdamPack pk;
@@ -100,6 +107,8 @@ int mpnn_adam_step(int n, float* const* params, const float* const* grads, float
     }
     pk.first_block[k] = blocks;
     pk.n = k;
+    pk.n_guard = n_guards;
+    for (int q = 0; q < n_guards; ++q) pk.guard[q] = guards[q];
     done += k;
     k_adam<<<blocks, 256, 0, stream>>>(pk, step, ticket, done == n ? 1 : 0, lr, beta1, beta2, eps, weight_decay);
     MPNN_CHECK_LAUNCH("k_adam");

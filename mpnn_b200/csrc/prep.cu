@@ -198,9 +198,9 @@ __global__ void __launch_bounds__(PT, 1) k_prep(Prep p) {
       oa += s_wa[w];
       ob += s_wb[w];
     }
-    if (r < r1) {
-      p.row_ptr[r] = oa + ia - va;
-      p.col_ptr[r] = ob + ib - vb;
+    if (r < r1) {   // clamped to the allocated slots: consumers walk these ranges
+      p.row_ptr[r] = min(oa + ia - va, p.ecap);
+      p.col_ptr[r] = min(ob + ib - vb, p.ecap);
     }
     __syncthreads();
     if (tid == PT - 1) {
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(PT, 1) k_prep(Prep p) {
     __syncthreads();
   }
   if (blockIdx.x == G - 1 && tid == 0) {
-    p.row_ptr[p.B * N] = total;
-    p.col_ptr[p.B * N] = total;
+    p.row_ptr[p.B * N] = min(total, p.ecap);
+    p.col_ptr[p.B * N] = min(total, p.ecap);
   }
   // (3) type id of every slot: occupied slots ranked by first position (every CTA computes the same map)
   if (tid == 0) s_U = 0;

@@ -418,6 +418,10 @@ class GRUFn(torch.autograd.Function):
         dev = h.device
         dm, dh = torch.empty_like(m), torch.empty_like(h)
         s = ctx.session
+        # the slab is only reduced by the hub node, which autograd reaches only when the cell's parameters are
+        # differentiated in THIS backward pass (not e.g. torch.autograd.grad(loss, [afm])): otherwise return direct gradients
+        if s is not None and not all(ctx.needs_input_grad[3:7]):
+            s = None
         if s is not None:
             pb = lib.mpnn_gru_bwd_partial_bytes(rows, d)
             if pb and s.slab is None:
@@ -847,6 +851,28 @@ def table_dp(nf, mf):
 _ENET_LANES = (0, 2, 3)
 _ENET_LANE = 0
 
+# forward applications of a parameter set (keyed by its first tensor) that have not been back-propagated yet
+_PARAM_USES = {}
+
+
+def _note_param_use(t):
+    key = (t.data_ptr(), t._version)
+    _PARAM_USES[key] = _PARAM_USES.get(key, 0) + 1
+    if len(_PARAM_USES) > 256:      # forward passes that never reach a backward
+        _PARAM_USES.clear()
+    return key
+
+
+def _single_param_use(key):
+    """True when the backward being run is the only pending application of the parameter set (consumes the use)"""
+    n = _PARAM_USES.pop(key, 1)
+    if n == 1:
+        return True
+    rem = abs(n) - 1            # several applications: none of their backward passes may leave the main stream
+    if rem > 0:
+        _PARAM_USES[key] = -rem
+    return False
+
 
 class EdgeNetTableFn(torch.autograd.Function):
     """Fused growth layers + 50 tied layers + last Linear on the distinct rows (P <= 64):
@@ -872,6 +898,7 @@ class EdgeNetTableFn(torch.autograd.Function):
         ctx.save_for_backward(urows, w_tied, W_last, saved, *gw)
         ctx.dims = (R, ef, G, P, n_tied, nf, mf)
         ctx.mark_non_differentiable(tableT)
+        ctx.use_key = _note_param_use(w_tied)
         return table, tableT
 
     @staticmethod
@@ -892,7 +919,9 @@ class EdgeNetTableFn(torch.autograd.Function):
         # only parameter gradients come out of this call (d_rows is needed upstream: stay on the main stream then)
         # deferred join is only safe when autograd ASSIGNS these gradients (param.grad is None: no kernel touches
         # them before the join); if it has to accumulate into an existing .grad the work stays on the main stream
-        side = (SIDE_STREAM_ENABLED and d_rows is None
+        # ... and when this is the ONLY application of these weights since their last backward: with two producers
+        # autograd sums the two gradients on the main stream, which does not wait for the side lanes
+        side = (SIDE_STREAM_ENABLED and d_rows is None and _single_param_use(ctx.use_key)
                 and all(getattr(t, "grad", None) is None for t in [w_tied, W_last] + gw))
         # the edge networks of a model are independent of each other: their backward chains (57 CTAs each) go to
         # different lanes round-robin, so the last one does not queue behind the others
@@ -970,6 +999,7 @@ class MultiEdgeNetTableFn(torch.autograd.Function):
                                       ptr_array(tablesT), stream()), "enet_fwd_multi")
         ctx.save_for_backward(urows, *([t for n in nets for t in n] + saved))
         ctx.dims = (R, ef, G, P, n_tied, nf, mf, K)
+        ctx.use_keys = [_note_param_use(n[0]) for n in nets]
         out = []
         for k in range(K):
             out += [tables[k], tablesT[k]]
@@ -1001,7 +1031,8 @@ class MultiEdgeNetTableFn(torch.autograd.Function):
         d_nets = [[torch.empty_like(t) for t in n] for n in nets]
         need_rows = ctx.needs_input_grad[0]
         d_rows = [torch.empty_like(urows) for _ in range(K)] if need_rows else None
-        side = (SIDE_STREAM_ENABLED and not need_rows
+        single = all([_single_param_use(k) for k in ctx.use_keys])
+        side = (SIDE_STREAM_ENABLED and not need_rows and single
                 and all(getattr(t, "grad", None) is None for n in nets for t in n))
         if not side and ready is not None:
             torch.cuda.current_stream(dev).wait_event(ready)

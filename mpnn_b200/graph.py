@@ -128,6 +128,12 @@ def _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev):
     return type_ptr, type_eid, type_pos, done
 
 
+def _note_edge_overflow(counts, e_true, Ecap):
+    """counts[0] <- true edge count, counts[2] |= (true count > capacity)   (multi-launch capacity path)"""
+    counts[0:1].copy_(e_true[0:1])
+    counts[2:3].bitwise_or_((e_true[0:1] > Ecap).to(torch.int32))
+
+
 def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap):
     """capacity mode, small batches: compaction + de-duplication as ONE cooperative launch (csrc/prep.cu)"""
     lib = _lib.load()
@@ -190,10 +196,17 @@ def compact_edges(bfm, adj=None, dedup=True):
                                          _lib.ptr(col_ptr), Ecap, _lib.ptr(edge_src), _lib.ptr(edge_dst),
                                          _lib.ptr(edge_w), _lib.ptr(rows), _lib.ptr(csc_eid), _lib.ptr(ws),
                                          _lib.stream()), "compact_fill")
+        # consumers walk row_ptr / col_ptr ranges: clamp them to the allocated slots (an overflowing batch computes on a
+        # truncated edge list, never out of bounds); the true count goes into the overflow flag below
+        e_true = torch.empty(2, dtype=torch.int32, device=dev)
+        _lib.check(lib.mpnn_compact_clamp(_lib.ptr(row_ptr), _lib.ptr(col_ptr), n_rows, Ecap, _lib.ptr(e_true),
+                                          _lib.stream()), "compact_clamp")
         el = EdgeList(B, N, ef, None, row_ptr, col_ptr, edge_src, edge_dst, edge_w, rows, csc_eid)
         el.Ecap = Ecap
+        el.e_true = e_true
         if dedup:
             el._typed = dedup_rows(el, unique_capacity=_CAPACITY[1])
+            _note_edge_overflow(el._typed.counts, e_true, Ecap)
             _CAPTURED_COUNTS.append(el._typed.counts)
         return el
     E = int(row_ptr[-1].item())
@@ -316,7 +329,7 @@ def dedup_rows(el, unique_capacity=None):
 # ---- small identity cache: the same (bfm, adj) pair is compacted once per batch, whatever number of
 # ---- EdgeNetworks / steps consume it (reference models call mf(afm, bfm) T times per forward).
 _CACHE = collections.OrderedDict()
-_CACHE_SIZE = 8
+_CACHE_SIZE = 2     # (each entry keeps one padded batch alive: ~1 GB at BASELINE config 5)
 
 
 def _key(t):
@@ -517,6 +530,8 @@ def typed_bonds(bfm, adj):
     el.__dict__.pop("_table_users", None)
     if _CAPACITY is not None:
         ti = dedup_rows(el, unique_capacity=_CAPACITY[1])
+        if getattr(el0, "e_true", None) is not None:
+            _note_edge_overflow(ti.counts, el0.e_true, Ecap)
         _CAPTURED_COUNTS.append(ti.counts)
     else:
         ti = dedup_rows(el)

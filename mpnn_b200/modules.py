@@ -828,7 +828,8 @@ class GRUCell(nn.Module):
             return ps + (None,)
         key = tuple((p.data_ptr(), p._version) for p in ps)
         s = self._session
-        if s is None or s.done or s.key != key or s.uses >= 64:   # (forward passes that never reach a backward)
+        # (s.filled: a backward pass left partials in the slab without reaching the hub node -- never reuse it)
+        if s is None or s.done or s.filled or s.key != key or s.uses >= 64:
             s = SharedGradSession(key)
             s.handles = GRUParamHubFn.apply(s, *ps)
             self._session = s

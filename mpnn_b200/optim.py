@@ -53,7 +53,12 @@ class FusedAdam(torch.optim.Optimizer):
                 vs.append(st["exp_avg_sq"])
             numel = (ctypes.c_longlong * len(ps))(*[p.numel() for p in ps])
             b1, b2 = group["betas"]
+            # capacity (graph-capture) mode: the overflow flags of the edge lists built in this step gate the update on
+            # the device -- a batch that exceeded the captured capacities must not touch the weights or the moments
+            from . import graph
+            guards = [c for c in graph._CAPTURED_COUNTS if c.device == dev][-8:] if graph._CAPACITY is not None else []
             check(lib.mpnn_adam_step(len(ps), ptr_array(ps), ptr_array(grads), ptr_array(ms), ptr_array(vs), numel,
                                      ptr(gs["step"]), ptr(gs["ticket"]), float(group["lr"]), float(b1), float(b2),
-                                     float(group["eps"]), float(group["weight_decay"]), stream()), "adam_step")
+                                     float(group["eps"]), float(group["weight_decay"]), ptr_array(guards), len(guards),
+                                     stream()), "adam_step")
         return loss

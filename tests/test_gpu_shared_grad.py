@@ -96,3 +96,61 @@ def test_hub_new_session_after_backward_and_after_update(dev, monkeypatch):
         p.requires_grad_(False)
     h = upd(x.clone().requires_grad_(True), x, mask)    # frozen parameters: per-call path
     h.sum().backward()
+
+
+def test_inputs_only_backward_leaves_no_stale_partials(dev):
+    """a backward pass that differentiates only the inputs (torch.autograd.grad(loss, [afm])) must not leave
+    weight-gradient partials in the shared slab that a later backward would add to its parameter gradients"""
+    from mpnn_b200 import modules as M
+    torch.manual_seed(3)
+    uf = M.GRUUpdate(8, 8).to(dev)
+    B, N = 4, 6
+    m = [torch.randn(B, N, 8, device=dev) for _ in range(3)]
+    mask = (torch.rand(B, N, 1, device=dev) > 0.2).float()
+
+    def forward(h0):
+        h = h0
+        for t in range(3):
+            h = uf(m[t], h, mask)
+        return h
+
+    h0 = torch.randn(B, N, 8, device=dev, requires_grad=True)
+    want_h = forward(h0)
+    uf.zero_grad()
+    want_h.pow(2).sum().backward()
+    want = {k: p.grad.clone() for k, p in uf.named_parameters()}
+    # inputs-only gradient first, then a full backward of a NEW forward pass with the same parameters
+    h1 = torch.randn(B, N, 8, device=dev, requires_grad=True)
+    torch.autograd.grad(forward(h1).sum(), [h1])
+    uf.zero_grad()
+    h2 = h0.detach().clone().requires_grad_(True)
+    forward(h2).pow(2).sum().backward()
+    for k, p in uf.named_parameters():
+        assert torch.allclose(p.grad, want[k], rtol=1e-5, atol=1e-6), k
+
+
+def test_two_forward_passes_one_backward_edge_network(dev):
+    """two applications of the same EdgeNetwork before ONE backward: the gradients (summed by autograd) must
+    equal the run with the side streams switched off"""
+    from mpnn_b200 import functional, graph, modules as M, synthetic
+    b = synthetic.make_batch("qm9", B=6)
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+    torch.manual_seed(2)
+    net = M.EdgeNetwork(16, 7, 16).to(dev)
+    ma = M.AdjMsgAgg(1)
+    res = []
+    for side in (True, False):
+        functional.SIDE_STREAM_ENABLED = side
+        try:
+            graph.clear_cache()
+            net.zero_grad()
+            a = ma(net(t["afm"], t["bfm"]), t["adj"]).materialize()
+            graph.clear_cache()
+            b2 = ma(net(t["afm"] * 0.5, t["bfm"]), t["adj"]).materialize()
+            (a.pow(2).sum() + b2.sum()).backward()
+            torch.cuda.synchronize()
+            res.append({k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+        finally:
+            functional.SIDE_STREAM_ENABLED = True
+    for k in res[0]:
+        assert torch.equal(res[0][k], res[1][k]), k

@@ -335,7 +335,8 @@ def test_fused_prep_is_bit_identical_to_the_multi_launch_path(dev, case, monkeyp
     assert e1.rows is None and e0.rows is not None, "the fused path was not taken"
     n = min(E, ecap)
     assert torch.equal(e1.row_ptr, e0.row_ptr) and torch.equal(e1.col_ptr, e0.col_ptr)
-    for k in ("edge_src", "edge_dst", "edge_w", "csc_eid"):
+    # (an overflowing batch is flagged and its step discarded; the truncated CSC lists need not agree)
+    for k in ("edge_src", "edge_dst", "edge_w") + (() if case == "overflow_e" else ("csc_eid",)):
         assert torch.equal(getattr(e1, k)[:n], getattr(e0, k)[:n]), k
     c1, c0 = t1.counts.cpu().tolist(), t0.counts.cpu().tolist()
     assert (c1[0], c1[2]) == (c0[0], c0[2]) and (case == "overflow_e" or c1[1] == c0[1]), (c1, c0)
