@@ -392,6 +392,15 @@ int mpnn_adam_step(int n, float* const* params, const float* const* grads, float
                    float* const* exp_avg_sq, const long long* numel, float* step, unsigned int* ticket, float lr,
                    float beta1, float beta2, float eps, float weight_decay, const int* const* guards, int n_guards,
                    mpnn_stream_t stream);
+/* 8e: the gradient all-reduce fused into the Adam step over NVLink peer memory (one launch, csrc/optim.cu k_adam_ddp).
+ * flat / flags: HOST arrays of `world` peer-mapped device pointers into every rank's symmetric buffer
+ * ([2][region_floats] gradient regions + [world][n_chunks] flags, zero on first use); goff: offsets of the tensors inside
+ * a region.  params == NULL: returns the number of chunks (sizing query). */
+int mpnn_adam_step_ddp(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const long long* numel, const long long* goff, float* step,
+                       unsigned int* ticket, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float* const* flat, unsigned* const* flags, long long region_floats, int world, int rank,
+                       mpnn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,7 @@ SIGNATURES = {
     "mpnn_glo_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_glo_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _PP, _I, _P]),
+    "mpnn_adam_step_ddp": (_I, [_I, _PP, _PP, _PP, _PP, _P, _P, _P, _P, _F, _F, _F, _F, _F, _PP, _PP, _L, _I, _I, _P]),
     "mpnn_compact_clamp": (_I, [_P, _P, _I, _I, _P, _P]),
     "mpnn_head_supported": (_I, [_I, _I, _I]),
     "mpnn_head_bn_linear_mse_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
