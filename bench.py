@@ -171,6 +171,10 @@ def run_ours(args):
         from mpnn_b200.optim import FusedAdam
         opt = FusedAdam(params, lr=1e-3)
     allreduce = D.FlatGradAllReduce(params)
+    fused_ddp = False
+    if world > 1 and not args.stock_adam and not args.nccl_allreduce:
+        # the gradient all-reduce runs INSIDE the Adam launch over NVLink peer memory (mpnn_b200/optim.py enable_ddp)
+        fused_ddp = opt.enable_ddp()
     # L2 (126 MB) is flushed between timed iterations by writing a 256 MB buffer
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
@@ -190,7 +194,8 @@ def run_ours(args):
         else:
             loss = torch.nn.functional.mse_loss(head(feats), b["labels"])
         loss.backward()
-        allreduce()
+        if not fused_ddp:
+            allreduce()
         opt.step()
         return loss
 
@@ -347,7 +352,9 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "graphs_per_gpu": B, "atoms_per_gpu": n, "directed_edges_per_gpu": e,
                    "optimizer": "Adam", "loss": "MSE", "cuda_graph": bool(use_graph), "l2_flush": "256 MB write between timed iterations",
-                   "parallelism": "dp%d" % world},
+                   "parallelism": "dp%d" % world,
+                   "grad_allreduce": ("fused into the Adam launch over NVLink peer memory (k_adam_ddp)" if fused_ddp else
+                                      ("NCCL, one flat bucket" if world > 1 else "none (1 GPU)"))},
         "e2e": {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": gb_in,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps,
                 "pipeline": "H2D of the next padded batch on a copy stream (pinned -> staging) overlapped with the current "
@@ -657,6 +664,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stock-adam", action="store_true", help="torch.optim.Adam(fused) instead of mpnn_b200.optim.FusedAdam")
     ap.add_argument("--stock-head", action="store_true", help="keep the head + loss as stock torch modules")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + Adam instead of the fused kernel")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")
     ap.add_argument("--timeline", default="", help="write a warm per-kernel timeline of one step to this file")

@@ -23,12 +23,19 @@ class FusedAdam(torch.optim.Optimizer):
         pack + ncclAllReduce + scale + unpack + Adam (5 launches, a latency-bound collective) by ONE launch.
         Call it on every rank, after the parameters are on their device and before the first step."""
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return False
+        self._ddp_on = True
         if len(self.param_groups) != 1:
             raise RuntimeError("mpnn_b200.FusedAdam.enable_ddp: one parameter group only")
-        ps = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        self._ddp_group = group
+        self._ddp = None      # buffers are built at the first step, from the parameters that receive gradients
+        return True
+
+    def _build_ddp(self, ps):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self._ddp_group
         lib = _lib.load()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > 8 or len(ps) > 40:
@@ -53,7 +60,6 @@ class FusedAdam(torch.optim.Optimizer):
                          goff=(ctypes.c_longlong * len(ps))(*goff),
                          flat_ptrs=(ctypes.c_void_p * world)(*bufs),
                          flag_ptrs=(ctypes.c_void_p * world)(*[b + 2 * region * 4 for b in bufs]))
-        return True
 
     def _group_state(self, group, dev):
         st = group.get("_mpnn_state")
@@ -93,8 +99,10 @@ class FusedAdam(torch.optim.Optimizer):
                 vs.append(st["exp_avg_sq"])
             numel = (ctypes.c_longlong * len(ps))(*[p.numel() for p in ps])
             b1, b2 = group["betas"]
-            dd = getattr(self, "_ddp", None)
-            if dd is not None:
+            if getattr(self, "_ddp_on", False):
+                if self._ddp is None:
+                    self._build_ddp(ps)     # collective: every rank reaches its first step
+                dd = self._ddp
                 if [id(p) for p in ps] != [id(p) for p in dd["params"]]:
                     raise RuntimeError("mpnn_b200.FusedAdam (ddp): every parameter needs a gradient on every rank, every step")
                 check(lib.mpnn_adam_step_ddp(len(ps), ptr_array(ps), ptr_array(grads), ptr_array(ms), ptr_array(vs), numel,
