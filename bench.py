@@ -461,9 +461,13 @@ def mp_step_roofline(tag, body, devb, flush, n, e, T, P, n_bn):
         else:
             kernels = "k_tc_edge_gemm + k_segment_sum + k_tc_gru_fwd | k_tc_* backward GEMMs, table gradient"
 
+            # as modules._wide_chain runs it: on the real rows only (the gather / scatter of the node tensors happens
+            # once per forward pass, outside the step)
+            elc, _real, hc, mc = M.compact_nodes(afm, mask, el)
+
             def fwd():
-                Mm = Fn.TypedMessageTCFn.apply(h0, tables[0], tablesT[0], el, True, d, d)
-                return Fn.GRUFn.apply(Mm, h0, m1, ws[0], ws[1], ws[2], ws[3], None)
+                Mm = Fn.TypedMessageTCFn.apply(hc, tables[0], tablesT[0], elc, True, d, d)
+                return Fn.GRUFn.apply(Mm, hc, mc, ws[0], ws[1], ws[2], ws[3], None)
         s_ = torch.cuda.Stream()
         s_.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s_):

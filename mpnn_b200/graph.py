@@ -75,7 +75,7 @@ class PerEdgeView(object):
 # ---- capacity mode (CUDA-graph capture): array sizes come from the caller, nothing is read back ----------
 _CAPACITY = None          # (edge_capacity, unique_capacity) or None
 _CAPTURED_COUNTS = []     # counts tensors of the edge lists built in capacity mode (overflow flags)
-STATS = {"E": 0, "U": 0}  # largest edge / distinct-row counts seen by the eager path (sizes the capacities)
+STATS = {"E": 0, "U": 0, "n_real": 0}  # largest edge / distinct-row counts seen by the eager path (sizes the capacities)
 
 
 class capacities(object):

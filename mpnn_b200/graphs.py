@@ -26,7 +26,7 @@ class GraphedStep(object):
     def __init__(self, step_fn, example_inputs, warmup=3, headroom=1.25, edge_capacity=None, unique_capacity=None):
         self.static = {k: v.clone() for k, v in example_inputs.items()}
         self.step_fn = step_fn
-        graph.STATS["E"] = graph.STATS["U"] = 0
+        graph.STATS["E"] = graph.STATS["U"] = graph.STATS["n_real"] = 0
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -660,6 +660,94 @@ def _tables_for_steps(msgs, el):
         n._msg_cache = {}
 
 
+WIDE_COMPACT = os.environ.get("MPNN_B200_WIDE_COMPACT", "1") != "0"
+
+
+class _CompactEdges(object):
+    """The edge list of a batch re-indexed over its REAL rows (mask != 0): what the tensor-core kernels see in
+    `_wide_chain`.  Padded rows have no edges, so the CSR / CSC pointers of the real rows are a gather of the padded
+    ones; sender / receiver ids go through the inverse of the row list; edge ids (CSC lists, type grouping) are unchanged."""
+
+    def __init__(self, el, real, cap):
+        rows = el.n_rows
+        dev = real.device
+        self.B, self.N, self.ef, self.E, self.Ecap = el.B, el.N, el.ef, el.E, el.Ecap
+        self.n_rows = cap
+        self.edge_w, self.csc_eid, self.rows = el.edge_w, el.csc_eid, None
+        rl = real.long()
+        inv = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
+        inv[rl] = torch.arange(cap, dtype=torch.int32, device=dev)
+        self.row_ptr = torch.cat([el.row_ptr.index_select(0, rl), el.row_ptr[-1:]]).contiguous()
+        self.col_ptr = torch.cat([el.col_ptr.index_select(0, rl), el.col_ptr[-1:]]).contiguous()
+        # (capacity mode: slots behind the edge count hold arbitrary bits -- clamp before they are used as indices)
+        self.edge_src = inv[el.edge_src.clamp(0, rows).long()].contiguous()
+        self.edge_dst = inv[el.edge_dst.clamp(0, rows).long()].contiguous()
+        import copy
+        self._typed = copy.copy(el.typed())
+        self._typed._tc_plan = None        # the plan bakes sender / receiver rows in: rebuilt over the compact ids
+
+    def typed(self):
+        return self._typed
+
+
+_NODE_FLAGS = {}     # device -> persistent {0, 0, overflow, 0} of the compact node lists built in capacity mode
+
+
+def compact_nodes(afm, mask, el):
+    """(compact edge list, real-row list [cap], afm on the real rows [cap, d], mask on them [cap]).  Eager: cap = number
+    of real rows (one small device->host read, like the edge count).  Capacity mode (graph capture): cap comes from the
+    eager warm-up with 10 % headroom, nothing is read back, an overflow sets the sticky flag `GraphedStep.check` reads."""
+    B, N, d = afm.shape
+    rows = B * N
+    dev = afm.device
+    m1 = mask.reshape(-1)
+    if graph._CAPACITY is None:
+        n_real = int((m1 != 0).sum().item())
+        graph.STATS["n_real"] = max(graph.STATS.get("n_real", 0), n_real)
+        cap = max(n_real, 1)
+        if dev not in _NODE_FLAGS:
+            _NODE_FLAGS[dev] = torch.zeros(4, dtype=torch.int32, device=dev)
+    else:
+        seen = graph.STATS.get("n_real", 0)
+        cap = min(rows, int(seen * 1.1) + 64) if seen else rows
+        flags = _NODE_FLAGS.get(dev)
+        if flags is not None and cap < rows:
+            flags[2:3].bitwise_or_(((m1 != 0).sum() > cap).to(torch.int32).reshape(1))
+            graph._CAPTURED_COUNTS.append(flags)
+        elif cap < rows:
+            cap = rows      # no persistent flag to report an overflow with: do not truncate
+    real = torch.nonzero_static(m1 != 0, size=cap, fill_value=rows).reshape(-1)     # fill: the appended zero row
+    elc = _CompactEdges(el, real, cap)
+    afm_c = torch.cat([afm.reshape(-1, d), afm.new_zeros(1, d)]).index_select(0, real)
+    mask_c = torch.cat([m1, m1.new_zeros(1)]).index_select(0, real)
+    return elc, real, afm_c, mask_c
+
+
+def _wide_chain(steps, base, afm, mask, el, uf, d):
+    """The step chain at tensor-core widths (33..256) on the REAL rows only.  The reference pads every graph to the
+    largest one of the batch (data_loader.py:52-59): 40 % of the rows of a ZINC-shaped batch are padding, and every
+    node-tensor pass of the message / GRU / batch-norm kernels pays for them.  Here the node tensors are gathered to
+    [n_real, d] once, all steps run on the compact tensors (the per-module kernels, unchanged), and the result is
+    scattered back into the padded layout once.  Exact: padded rows carry no edges and their states are zero."""
+    B, N, _ = afm.shape
+    rows = B * N
+    dev = afm.device
+    elc, real, afm_c, mask_c = compact_nodes(afm, mask, el)
+    h = afm_c if base is afm else torch.cat([base.reshape(-1, d), afm.new_zeros(1, d)]).index_select(0, real)
+    for gru, bn in steps:
+        msg = gru._src._messages
+        table, tableT = msg._net._table(el, True)
+        M = TypedMessageTCFn.apply(afm_c, table, tableT, elc, True, d, d)
+        h = uf.gru_cell(M, h, mask_c)
+        if bn is not None:
+            if isinstance(bn._module, MaskBatchNorm1d):
+                h = bn._module._run(h, mask_c)
+            else:
+                h = bn._module._run(h, mask_c, 1e-6 if bn._eps is None else bn._eps)
+    out = torch.zeros(rows + 1, d, dtype=torch.float32, device=dev).index_copy(0, real, h)
+    return out[:rows].view(B, N, d)
+
+
 def _fused_chain(head):
     """Evaluates the chain ending in `head` with the persistent step kernel when every link fits it; None otherwise."""
     steps, node = [], head
@@ -684,8 +772,13 @@ def _fused_chain(head):
             and base.shape == afm.shape and afm.dtype == torch.float32 and base.dtype == torch.float32):
         return None
     d = afm.shape[-1]
-    if uf.nf != d or uf.mf != d or not chain_supported(d, len(steps)):
+    wide = False
+    if uf.nf != d or uf.mf != d:
         return None
+    if not chain_supported(d, len(steps)):
+        wide = WIDE_COMPACT and d > 32 and tc_dp(d, d) >= 0     # tensor-core widths: real rows only (see _wide_chain)
+        if not wide:
+            return None
     for gru, bn in steps:
         m = gru._src._messages
         net = m._net
@@ -696,12 +789,15 @@ def _fused_chain(head):
         if bn is not None and (bn._mask is not mask or (isinstance(bn._module, MaskBatchNorm1d)
                                                         and bn._module.momentum is None)):
             return None
-    real_rows(mask, side=True)     # tiny kernel on a side lane, overlapped with the compaction / edge networks below
+    if not wide:
+        real_rows(mask, side=True)     # tiny kernel on a side lane, overlapped with the compaction / edge networks below
     el = graph.edge_list_for(bfm, adj)
     if not all(gru._src._messages._net._typed_ok(bfm, el) for gru, _ in steps):
         return None
     tables, tablesT, bnspec, affine = [], [], [], []
     _tables_for_steps([gru._src._messages for gru, _ in steps], el)
+    if wide:
+        return _wide_chain(steps, base, afm, mask, el, uf, d)
     for gru, bn in steps:
         m = gru._src._messages
         table, tableT = m._net._table(el, True)      # cached by _tables_for_steps

@@ -258,3 +258,39 @@ def test_config5_full_size_properties(dev, cfg):
     # padded atoms: no gradient reaches their (zero) input features through the masked update and readout
     pad = (1 - t["mask"]).bool().expand_as(g1)
     assert float(g1[pad].abs().max()) <= 1e-6 * float(g1.abs().max())
+
+
+@pytest.mark.parametrize("variant,d,T", [("autoencoder", 64, 3), ("basic", 40, 3), ("normed", 64, 2)])
+def test_wide_chain_on_real_rows_equals_padded_evaluation(dev, variant, d, T, monkeypatch):
+    """modules._wide_chain (tensor-core widths: the step loop on the REAL rows only, node tensors gathered once and
+    scattered back once) == the same modules evaluated link by link on the padded rows: outputs, input gradients and every
+    parameter gradient (same kernels, same TF32 products per row; only the batch-norm reductions see the rows in another
+    tiling)"""
+    from mpnn_b200 import graph, modules as M, synthetic
+    from mpnn_b200.dropin import reference_model, kaiming_init
+    b = synthetic.make_batch("zinc", B=24, d=d)
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+    torch.manual_seed(11)
+    mod = reference_model(variant, d, 8, d, 1, 2 * d, message_steps=T)
+    mod.apply(kaiming_init)
+    with torch.no_grad():       # tame the 50-layer trunk: messages of O(1), so TF32 round-off does not dominate the check
+        for net in ([mod.mf] if hasattr(mod, "mf") else mod.mfs):
+            net.edge_map[net._last_idx].weight.mul_(0.05)
+    mod = mod.to(dev).train()
+    res = []
+    for compact in (True, False):
+        monkeypatch.setattr(M, "WIDE_COMPACT", compact)
+        graph.clear_cache()
+        mod.zero_grad()
+        a = t["afm"].clone().requires_grad_(True)
+        out = mod(a, t["bfm"], t["adj"], t["mask"])
+        cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        (out * cot).sum().backward()
+        res.append((out.detach(), a.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}))
+    (o1, a1, g1), (o0, a0, g0) = res
+    assert rel_err(o1.cpu(), o0.cpu()) <= 2e-5
+    assert rel_err(a1.cpu(), a0.cpu()) <= 2e-4
+    assert float((a1 * (1 - t["mask"])).abs().max()) == 0.0 or variant != "autoencoder"
+    scale = max(float(v.abs().max()) for v in g0.values())
+    for k in g0:
+        assert float((g1[k] - g0[k]).abs().max()) <= 2e-4 * float(g0[k].abs().max()) + 1e-6 * scale, k
