@@ -92,7 +92,14 @@ __global__ void k_colsum_final(const float* __restrict__ partial, int nblk, int 
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= width) return;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * width + c];
+  for (int b0 = 0; b0 < nblk; b0 += 8) {   // eight loads in flight, added in block order (a load-add loop is one L2 round
+    float v[8];                             // trip per block: 35 us for 1 184 partials)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = b0 + k < nblk ? partial[(size_t)(b0 + k) * width + c] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (b0 + k < nblk) s += v[k];
+  }
   out[c] = accumulate ? out[c] + s : s;
 }
 
