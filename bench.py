@@ -331,10 +331,10 @@ def run_ours(args):
     roof = None
     roof_large = None
     launches = None
-    if rank == 0 and w["variant"] in ("normed", "basic", "autoencoder"):
+    if rank == 0 and w["variant"] in ("normed", "basic", "autoencoder") and not args.no_roofline:
         net0 = body.mfs[0] if hasattr(body, "mfs") else body.mf
         roof = mp_step_roofline(args.config, body, devb, flush, n, e, w["T"], net0.P, 1 if w["variant"] == "normed" else 0)
-    if rank == 0 and world == 1 and not args.no_large:
+    if rank == 0 and world == 1 and not args.no_large and not args.no_roofline:
         roof_large = roofline_large(dev, flush)
     # every rank replays the step here (it contains the gradient all-reduce when N > 1); rank 0 keeps the count
     launches = count_launches(run_resident)
@@ -661,6 +661,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--no-roofline", action="store_true", help="skip the roofline measurements (profiling runs)")
     ap.add_argument("--no-large", action="store_true", help="skip the roofline_large points (autoenc B=16384, d=64/256)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="qm9", choices=sorted(WORKLOADS))
