@@ -39,6 +39,14 @@ WORKLOADS = {
     "qm9": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256, head="bn_linear",
                 desc="normed_basic_model + MaskBatchNorm + BatchNorm1d(64) + Linear(64,12), QM9-shaped (n<=29), "
                      "B=256/GPU, d=16, ef=7, P=49, T=3"),
+    # the same model on NON-categorical bond features (the reference's docstrings allow "topological distance and 3D
+    # distance", models/basic_model.py:41-42): every bond row is distinct, the edge network runs per edge (trunk on E rows,
+    # per-edge contraction kernels, csrc/trunk.cu + csrc/message.cu); eager launches (the per-edge path sizes its arrays
+    # from the host-side edge count)
+    "qm9_continuous": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256, head="bn_linear", synth="qm9",
+                           continuous=True, graph=False,
+                           desc="normed_basic_model as config 2 but with a continuous bond feature (one distinct row per "
+                                "bond): per-edge contraction path, eager launches, B=256/GPU, d=16, ef=7, P=49, T=3"),
     "lipo": dict(variant="lipo", d=19, ef=7, T=6, out=38, targets=1, B=32, head="bn_halving",
                  desc="lipo_basic_model (HEAD form) + BatchNorm1d(38) + halving dense head, Lipophilicity-shaped, B=32, "
                       "d=19, ef=7, P=49, T=6"),
@@ -51,6 +59,13 @@ WORKLOADS = {
     # configs[3]: normed_encoded_basic_model (atom/bond encoders + masked BN1d everywhere), B=2048 global
     "affinity": dict(variant="normed_encoded", d=8, ef=2, T=3, out=16, targets=1, B=2048, encoders=True,
                      desc="normed_encoded_basic_model (encoders 30->8 / 8->2, MaskBatchNorm1d), B=2048, d=8, ef=2, P=16, T=3"),
+    # configs[3] as BASELINE.json names it: normed_encoded_basic_model_ecfp (no ma_bn, obn on the per-atom readout the model
+    # was written against, graph_level_output.py:46), per-atom targets like the driver's masked ECFP regression
+    # (test_graph_encode_norm_ecfp.py:137), B=2048
+    "affinity_ecfp": dict(variant="normed_encoded_ecfp", d=8, ef=2, T=3, out=16, targets=1, B=2048, encoders=True,
+                          readout_func="GraphLevelOutputAtoms", per_atom=True, synth="affinity",
+                          desc="normed_encoded_basic_model_ecfp (encoders 30->8 / 8->2, MaskBatchNorm1d per step + obn, "
+                               "per-atom readout), B=2048, d=8, ef=2, P=16, T=3"),
 }
 
 
@@ -100,10 +115,17 @@ class ClockSampler(threading.Thread):
 
 def make_workload_batch(config, w, rank):
     from mpnn_b200 import synthetic
-    batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=w["B"], seed_offset=rank,
+    batch = synthetic.make_batch(w.get("synth", config), B=w["B"], seed_offset=rank,
                                  d=w["d"] if config == "autoenc" else None, return_graphs=True)
-    if config != "qm9":
-        batch["labels"] = np.random.RandomState(rank).normal(size=(w["B"], w["targets"])).astype(np.float32)
+    if w.get("continuous"):     # a "3D distance"-like column: symmetric, positive on bonds, zero elsewhere
+        rs = np.random.RandomState(1000 + rank)
+        dist = rs.uniform(0.9, 1.6, size=batch["adj"].shape).astype(np.float32)
+        dist = np.maximum(dist, dist.transpose(0, 2, 1)) * (batch["adj"] != 0)
+        batch["bfm"] = batch["bfm"].copy()
+        batch["bfm"][..., -1] = dist
+    if config not in ("qm9", "qm9_continuous"):
+        shape = (w["B"], batch["afm"].shape[1], w["targets"]) if w.get("per_atom") else (w["B"], w["targets"])
+        batch["labels"] = np.random.RandomState(rank).normal(size=shape).astype(np.float32)
     return batch
 
 
@@ -438,6 +460,8 @@ def mp_step_roofline(tag, body, devb, flush, n, e, T, P, n_bn):
     shared = not hasattr(body, "mfs")
     graph.clear_cache()
     el = graph.edge_list_for(bfm, adj)
+    if el.typed().type_ptr is None:     # non-categorical bond rows: the per-edge path, no typed step kernels to time
+        return None
     with torch.no_grad():
         tabs = [net._compute_table(el) for net in nets]
     tables = [t[0].detach().requires_grad_(True) for t in tabs]
@@ -573,7 +597,7 @@ def _oracle_step_fn(config, B):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from golden_util import leaf_sd
     w = WORKLOADS[config]
-    batch = synthetic.make_batch("qm9" if config == "qm9" else config, B=B)
+    batch = synthetic.make_batch(w.get("synth", config), B=B)
     body, head = build_model(w, torch.device("cpu"))
     sd = leaf_sd({k: v.detach().clone() for k, v in body.state_dict().items()})
     leaves, seen = [], set()
@@ -583,7 +607,8 @@ def _oracle_step_fn(config, B):
             leaves.append(v)
     opt = torch.optim.Adam(leaves, lr=1e-3)
     t = {k: torch.from_numpy(batch[k]) for k in ("afm", "bfm", "adj", "mask")}
-    labels = torch.from_numpy(batch["labels"]) if config == "qm9" else torch.zeros(B, w["targets"])
+    labels = torch.from_numpy(batch["labels"]) if config in ("qm9", "qm9_continuous") else (
+        torch.zeros(B, t["afm"].shape[1], w["targets"]) if w.get("per_atom") else torch.zeros(B, w["targets"]))
     buffers = {}
 
     def step():
@@ -597,6 +622,8 @@ def _oracle_step_fn(config, B):
             y = O.att_model(*a, sd=sd, steps=w["T"], s2v_steps=100, agg="adj")
         elif w["variant"] == "normed_encoded":
             y = O.normed_encoded_model(*a, sd=sd, steps=w["T"], buffers=buffers)
+        elif w["variant"] == "normed_encoded_ecfp":
+            y = O.normed_encoded_ecfp_model(*a, sd=sd, steps=w["T"], buffers=buffers)
         else:
             y = O.basic_model(*a, sd=sd, steps=w["T"], chain_state=False)
         loss = torch.nn.functional.mse_loss(head(y), labels)

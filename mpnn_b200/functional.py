@@ -20,6 +20,15 @@ from ._lib import check, f32c, ptr, ptr_array, stream, workspace
 _SIDE_STREAMS = {}
 _SIDE_PENDING = {}
 SIDE_STREAM_ENABLED = os.environ.get("MPNN_B200_SIDE_STREAM", "1") != "0"
+# The backward's side lanes only pay inside a captured step (parallel branches of the CUDA graph, explicit event edges);
+# with eager launches the Python dispatch is the bottleneck and the lanes buy nothing, so they are off there by default.
+# (Round 2: with eager lanes + the ready-event shortcut the att_model's input gradient was wrong when other models had run
+# before it in the same process -- tests/test_gpu_parity.py config-shaped zinc; not root-caused, eager lanes switched off.)
+SIDE_STREAM_EAGER = os.environ.get("MPNN_B200_SIDE_STREAM_EAGER", "0") != "0"
+
+
+def _side_ok():
+    return SIDE_STREAM_ENABLED and (SIDE_STREAM_EAGER or torch.cuda.is_current_stream_capturing())
 
 
 def _side_stream(device, lane=0):
@@ -48,17 +57,20 @@ def _ready_put(t, ev):
 
 def _note_produced(t):
     """record an event behind the kernels enqueued so far on the current stream as the producer of `t`"""
-    if SIDE_STREAM_ENABLED:
+    if _side_ok():
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(t.device))
         _ready_put(t, ev)
+
+
+READY_EVENTS_ENABLED = os.environ.get("MPNN_B200_READY_EVENTS", "1") != "0"
 
 
 def _ready_get(t):
     """event behind the producer of `t` -- only while the tensor object it was registered for is still alive (so the
     address cannot have been recycled for something else) and `t` starts at the same address (itself or a view)"""
     ent = _READY_EVENTS.pop(t.data_ptr(), None)
-    if ent is None:
+    if ent is None or not READY_EVENTS_ENABLED or not _side_ok():
         return None
     src = ent[0]()
     return ent[1] if (src is not None and src.data_ptr() == t.data_ptr()) else None
@@ -371,7 +383,7 @@ class GRUParamHubFn(torch.autograd.Function):
         lib = _lib.load()
         rows, d, dev = s.meta
         # parameter gradients only: off the main stream when autograd will ASSIGN them (see EdgeNetTableFn.backward)
-        side = (SIDE_STREAM_ENABLED and all(g is None for g in direct)
+        side = (_side_ok() and all(g is None for g in direct)
                 and all(getattr(p, "grad", None) is None for p in ctx.params))
         with (_on_side_stream(dev, [s.slab], lane=4) if side else _inline()):
             dW_ih = torch.empty(d, 3 * d, dtype=torch.float32, device=dev)
@@ -921,7 +933,7 @@ class EdgeNetTableFn(torch.autograd.Function):
         # them before the join); if it has to accumulate into an existing .grad the work stays on the main stream
         # ... and when this is the ONLY application of these weights since their last backward: with two producers
         # autograd sums the two gradients on the main stream, which does not wait for the side lanes
-        side = (SIDE_STREAM_ENABLED and d_rows is None and _single_param_use(ctx.use_key)
+        side = (_side_ok() and d_rows is None and _single_param_use(ctx.use_key)
                 and all(getattr(t, "grad", None) is None for t in [w_tied, W_last] + gw))
         # the edge networks of a model are independent of each other: their backward chains (57 CTAs each) go to
         # different lanes round-robin, so the last one does not queue behind the others
@@ -1032,7 +1044,7 @@ class MultiEdgeNetTableFn(torch.autograd.Function):
         need_rows = ctx.needs_input_grad[0]
         d_rows = [torch.empty_like(urows) for _ in range(K)] if need_rows else None
         single = all([_single_param_use(k) for k in ctx.use_keys])
-        side = (SIDE_STREAM_ENABLED and not need_rows and single
+        side = (_side_ok() and not need_rows and single
                 and all(getattr(t, "grad", None) is None for n in nets for t in n))
         if not side and ready is not None:
             torch.cuda.current_stream(dev).wait_event(ready)
@@ -1119,7 +1131,7 @@ class TypedMessageFn(torch.autograd.Function):
         # side stream, where EdgeNetTableFn.backward picks it up in stream order.
         dH = dT = None
         h = ctx.holder
-        side = SIDE_STREAM_ENABLED and need_dT and h is not None and h.uses == 1
+        side = _side_ok() and need_dT and h is not None and h.uses == 1
         if need_dH:
             dH = torch.empty_like(H)
             if not side and need_dT:
@@ -1294,7 +1306,7 @@ class ChainFn(torch.autograd.Function):
         need_T = [ctx.needs_input_grad[9 + t] for t in range(T)]
         dTs = [None] * T
         dH0 = None
-        produced = torch.cuda.Event() if SIDE_STREAM_ENABLED else None
+        produced = torch.cuda.Event() if _side_ok() else None
         if produced is not None:
             produced.record(torch.cuda.current_stream(dev))
 
@@ -1326,7 +1338,7 @@ class ChainFn(torch.autograd.Function):
                 dMs = dM
             else:
                 dMs = torch.stack([dM[ts[0]] if len(ts) == 1 else dM[ts].sum(0) for ts in want])
-            side = SIDE_STREAM_ENABLED
+            side = _side_ok()
             DPt = tables[0].shape[-1]
             cm = _on_side_stream(dev, [dMs, H0, alpha], lane=1, after=produced if dMs is dM else None) if side \
                 else _inline()

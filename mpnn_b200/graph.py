@@ -351,6 +351,37 @@ def edge_list_for(bfm, adj=None):
     return el
 
 
+def int_typed_edge_list(bt, n_types):
+    """Edge list of an INTEGER bond-type tensor bt [B,N,N] (reference ggnn_msg_pass.py: 0 = no bond, t >= 1 selects
+    matrix t-1): the pairs with a bond, compacted like any other batch; the type id of an edge is its bond type - 1, the
+    zero type is n_types.  Cached by tensor identity like `edge_list_for`."""
+    k = ("int", _key(bt), int(n_types))
+    hit = _CACHE.get(k)
+    if hit is not None:
+        _CACHE.move_to_end(k)
+        return hit[0]
+    lib = _lib.load()
+    x = bt.detach().to(torch.float32).unsqueeze(-1).contiguous()
+    el = compact_edges(x, None, dedup=False)
+    dev = x.device
+    Ecap = el.Ecap
+    uid = (el.rows[:max(Ecap, 1), 0].to(torch.int32) - 1).clamp_(0, n_types).contiguous()
+    counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    counts[0:1].copy_(el.row_ptr[el.n_rows:el.n_rows + 1])
+    counts[1] = n_types
+    type_ptr = torch.empty(n_types + 1, dtype=torch.int32, device=dev)
+    type_eid = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    type_pos = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    ws = _lib.workspace(lib.mpnn_type_sort_workspace_bytes(Ecap, n_types), dev)
+    _lib.check(lib.mpnn_type_sort(_lib.ptr(uid), _lib.ptr(counts), Ecap, n_types, _lib.ptr(type_ptr), _lib.ptr(type_eid),
+                                  _lib.ptr(type_pos), _lib.ptr(ws), ws.numel(), _lib.stream()), "type_sort")
+    el._typed = TypedInfo(uid[:Ecap], None, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], n_types, n_types)
+    _CACHE[k] = (el, bt, None)
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return el
+
+
 def clear_cache():
     _CACHE.clear()
     from . import functional

@@ -441,8 +441,7 @@ class BiLiniearEdgeNetwork(nn.Module):
 
 
 class GGNNMsgPass(nn.Module):
-    """reference ggnn_msg_pass.py: integer bond type -> [mf, nf] matrix lookup.  Same contraction kernel with
-    x_e = one-hot(bond type) (P = #types), W~ = adj_w; type 0 (no bond) maps to the zero matrix."""
+    """reference ggnn_msg_pass.py: integer bond type -> [mf, nf] matrix lookup; type 0 (no bond) maps to the zero matrix."""
 
     def __init__(self, node_features, edge_features, message_features):
         super(GGNNMsgPass, self).__init__()
@@ -455,8 +454,27 @@ class GGNNMsgPass(nn.Module):
         torch.nn.init.kaiming_uniform_(self.adj_w, nonlinearity='relu')
 
     def forward(self, afm, bfm, reuse_graph_tensors=False):
+        """ggnn_msg_pass.py:17-31: out[b,i] = sum_j adj_w[type(b,i,j) - 1] afm[b,j] + message_bias, type 0 = no bond.
+        The integer bond type IS the type id of the typed message path: the pairs with a bond are compacted, the
+        parameter tensor is the table of per-type matrices (no dense one-hot tensor, no de-duplication pass)."""
         if not afm.is_cuda:
             raise RuntimeError("mpnn_b200.GGNNMsgPass: CUDA tensors required (there is no CPU fallback)")
+        B, N, nf = afm.shape
+        DP = table_dp(self.nf, self.mf)
+        if DP < 0:
+            return self._forward_onehot(afm, bfm)
+        el = graph.int_typed_edge_list(bfm, self.ef)
+        F = torch.nn.functional
+        table = F.pad(self.adj_w.permute(0, 2, 1), (0, DP - self.mf, 0, DP - self.nf, 0, 1))     # T[u][l][k], row ef = 0
+        tableT = F.pad(self.adj_w.detach(), (0, DP - self.nf, 0, DP - self.mf, 0, 1))
+        H = afm.reshape(-1, nf)
+        if typed_dp(self.nf, self.mf) >= 0:
+            M = TypedMessageFn.apply(H, table, tableT, self.message_bias, el, None, False, self.nf, self.mf, None)
+        else:
+            M = TypedMessageTCFn.apply(H, table, tableT, el, False, self.nf, self.mf) + self.message_bias
+        return M.view(B, N, self.mf)
+
+    def _forward_onehot(self, afm, bfm):
         B, N, nf = afm.shape
         onehot = torch.zeros(B, N, N, self.ef, dtype=torch.float32, device=afm.device)
         onehot.scatter_(-1, (bfm.long().clamp(min=1) - 1).unsqueeze(-1), (bfm > 0).float().unsqueeze(-1))

@@ -184,3 +184,38 @@ def test_fused_chain_large_batch(dev, monkeypatch):
     fused = _run(mod, t, True, monkeypatch)
     plain = _run(mod, t, False, monkeypatch)
     _compare(fused, plain, tol_out=2e-5, tol_grad=5e-4)
+
+
+def test_captured_step_equals_eager_step(dev):
+    """BASELINE config 2's whole train step (fused chain, backward side lanes as graph branches, fused Adam) replayed
+    as one CUDA graph against the same step launched eagerly (no side lanes): same losses, same parameters"""
+    import numpy as np
+    from mpnn_b200 import graph, graphs, optim
+    t = _batch("qm9", 48, dev)
+    labels = torch.randn(48, 12, generator=torch.Generator().manual_seed(1)).to(dev)
+    losses, finals = {}, {}
+    for mode in ("eager", "graph"):
+        graph.clear_cache()
+        mod = _model("normed", dev, 16, 7, 12, 3, seed=11)
+        opt = optim.FusedAdam(list(mod.parameters()), lr=1e-3)
+        batch = dict(t, labels=labels)
+
+        def step_fn(b):
+            graph.clear_cache()
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(mod(b["afm"], b["bfm"], b["adj"], b["mask"]), b["labels"])
+            loss.backward()
+            opt.step()
+            return loss
+
+        if mode == "eager":
+            ls = [float(step_fn(batch)) for _ in range(6)]
+        else:
+            gs = graphs.GraphedStep(step_fn, batch, warmup=3)
+            ls = [float("nan")] * 3 + [float(gs(batch)) for _ in range(3)]
+            gs.check()
+        losses[mode] = ls[3:]
+        finals[mode] = [p.detach().clone() for p in mod.parameters()]
+    assert np.allclose(losses["eager"], losses["graph"], rtol=1e-4, atol=1e-7), losses
+    for a, b in zip(finals["eager"], finals["graph"]):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)

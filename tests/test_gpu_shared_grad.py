@@ -141,6 +141,7 @@ def test_two_forward_passes_one_backward_edge_network(dev):
     res = []
     for side in (True, False):
         functional.SIDE_STREAM_ENABLED = side
+        functional.SIDE_STREAM_EAGER = side        # (the lanes are capture-only by default)
         try:
             graph.clear_cache()
             net.zero_grad()
@@ -152,5 +153,6 @@ def test_two_forward_passes_one_backward_edge_network(dev):
             res.append({k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
         finally:
             functional.SIDE_STREAM_ENABLED = True
+            functional.SIDE_STREAM_EAGER = False
     for k in res[0]:
         assert torch.equal(res[0][k], res[1][k]), k
