@@ -363,6 +363,13 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
                      const float* m0, const float* c0, const float* saved, const float* dout, int B, int N, int F,
                      int steps, float* dX, float* dWcat, float* dbcat, float* dWq, float* dwe, float* dm0, float* dc0,
                      void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* The loop of `steps` iterations runs in two persistent cooperative kernels (csrc/s2v_persist.cu: one CTA per group of
+ * graphs, the batch-wide softmax statistics exchanged through tagged slots in L2) when F <= 64 and the batch fits;
+ * other shapes, or after mpnn_set2vec_set_persistent(0), run six launches per iteration.  Returns the previous setting. */
+int mpnn_set2vec_set_persistent(int enabled);
+/* Profiling aid: CTA 0 of the persistent kernels writes %globaltimer stamps of the phases of its first four iterations
+ * into buf (448 x uint64 of DEVICE memory: forward [0,64), backward [64,128), 16 per iteration; [128,448): post / gather-done time of every CTA in forward iteration 2); NULL = off. */
+void mpnn_set2vec_debug(unsigned long long* buf);
 /* LSTMCellHidden.forward alone (set2vec.py:68-75) on pre [B,4F] = hprev [w_hi|w_hf|w_hg|w_ho] + [b_*] (the caller's
  * mpnn_gemm): activated gates [B,4F], c' [B,F], tanh(c') [B,F], h' [B,F]; bwd: dh, dc' -> dpre [B,4F], dc_prev. */
 int mpnn_lstm_hidden_fwd(const float* pre, const float* cprev, int B, int F, float* gates, float* c, float* tc,

@@ -124,6 +124,8 @@ SIGNATURES = {
                             _P, _P, _P, _P, _P, _P, _P, _P, _PP, _P, _Z, _P]),
     "mpnn_real_rows_max": (_I, []),
     "mpnn_real_rows": (_I, [_P, _L, _P, _P, _Z, _P]),
+    "mpnn_set2vec_set_persistent": (_I, [_I]),
+    "mpnn_set2vec_debug": (None, [_P]),
     "mpnn_set2vec_saved_floats": (_L, [_I, _I, _I, _I]),
     "mpnn_set2vec_workspace_bytes": (_Z, [_I, _I, _I]),
     "mpnn_set2vec_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -17,6 +17,15 @@ extern "C" int mpnn_colsum(const float* X, const float* Y, long long rows, int w
                            float* out, int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_colsum_workspace_bytes(long long rows, int width);
 
+// the persistent kernels (s2v_persist.cu): return 1 if they served the call (*rc = status), 0 if the shape is not theirs
+size_t s2v_persist_slot_bytes();
+int s2v_persist_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
+                    const float* we, const float* m0, const float* c0, int B, int N, int F, int steps, float* out,
+                    float* saved, void* slots, cudaStream_t stream, int* rc);
+int s2v_persist_bwd(const float* X, const float* Wcat, const float* Wq, const float* we, const float* c0,
+                    const float* saved, const float* dout, int B, int N, int F, int steps, float* dX, float* dqS,
+                    float* pwS, float* dpreS, float* dm0, float* dc0, void* slots, cudaStream_t stream, int* rc);
+
 namespace {
 
 constexpr float BIG_NEGATIVE = -1e8f;  // set2vec.py:10
@@ -198,7 +207,7 @@ size_t mpnn_set2vec_workspace_bytes(int B, int N, int F) {
               + (size_t)B * F * 4;   // dc, dq, pw, dh
   size_t g = mpnn_gemm_workspace_bytes(2 * F, 4 * F, B);
   size_t c = mpnn_colsum_workspace_bytes(B, 4 * F);
-  return align_up(fl * sizeof(float), 256) + align_up(g > c ? g : c, 256) + 256;
+  return s2v_persist_slot_bytes() + align_up(fl * sizeof(float), 256) + align_up(g > c ? g : c, 256) + 256;
 }
 
 // The backward keeps every step's dq / pw / dpre and a packed copy of the saved m so that the four parameter gradients
@@ -216,7 +225,7 @@ size_t mpnn_set2vec_bwd_workspace_bytes(int B, int N, int F, int steps) {
   size_t g2 = mpnn_gemm_workspace_bytes(F, F, (int)sb);
   size_t c = mpnn_colsum_workspace_bytes((int)sb, 4 * F);
   size_t m = g > g2 ? g : g2;
-  return align_up(fl * sizeof(float), 256) + align_up(m > c ? m : c, 256) + 256;
+  return s2v_persist_slot_bytes() + align_up(fl * sizeof(float), 256) + align_up(m > c ? m : c, 256) + 256;
 }
 
 int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const float* bcat, const float* Wq,
@@ -225,7 +234,12 @@ int mpnn_set2vec_fwd(const float* X, const float* mask, const float* Wcat, const
   MPNN_REQUIRE(B > 0 && N > 0 && F > 0 && steps > 0, MPNN_ERR_ARG, "set2vec_fwd: bad dims");
   MPNN_REQUIRE(workspace_bytes >= mpnn_set2vec_workspace_bytes(B, N, F), MPNN_ERR_WORKSPACE, "set2vec_fwd: workspace");
   const int rows = B * N;
-  float* pre = (float*)workspace;
+  {
+    int rc = MPNN_OK;
+    if (s2v_persist_fwd(X, mask, Wcat, bcat, Wq, we, m0, c0, B, N, F, steps, out, saved, workspace, stream, &rc))
+      return rc;
+  }
+  float* pre = (float*)((char*)workspace + s2v_persist_slot_bytes());
   float* e = pre + (size_t)B * 4 * F;
   for (int s = 0; s < steps; ++s) {
     StepPtrs cur = step_ptrs(saved, s, B, N, F);
@@ -269,7 +283,7 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
   float* saved = const_cast<float*>(saved_c);
   const int rows = B * N;
   const size_t sb = (size_t)steps * B;
-  float* datt = (float*)workspace;
+  float* datt = (float*)((char*)workspace + s2v_persist_slot_bytes());
   float* de = datt + rows;
   float* spare = de + rows;
   float* dmA = spare + rows;
@@ -281,17 +295,22 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
   float* dpreS = pwS + sb * F;
   float* mS = dpreS + sb * 4 * F;
   float* fl_end = mS + sb * 2 * F;
-  char* sub = (char*)workspace + align_up((size_t)(fl_end - (float*)workspace) * sizeof(float), 256);
+  char* sub = (char*)datt + align_up((size_t)(fl_end - datt) * sizeof(float), 256);
   size_t sub_bytes = workspace_bytes - (size_t)(sub - (char*)workspace);
-  MPNN_CUDA(cudaMemsetAsync(dX, 0, (size_t)rows * F * sizeof(float), stream));
-  MPNN_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * F * sizeof(float), stream));
-  MPNN_CUDA(cudaMemcpyAsync(dmA, dout, (size_t)B * 2 * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   // packed m: step s at rows [s*B, (s+1)*B)
   MPNN_CUDA(cudaMemcpy2DAsync(mS, (size_t)B * 2 * F * sizeof(float), saved, step_stride(B, N, F) * sizeof(float),
                               (size_t)B * 2 * F * sizeof(float), steps, cudaMemcpyDeviceToDevice, stream));
+  int rc;
+  int prc = MPNN_OK;
+  const bool persistent = s2v_persist_bwd(X, Wcat, Wq, we, c0, saved, dout, B, N, F, steps, dX, dqS, pwS, dpreS,
+                                          m0 ? dm0 : nullptr, dc0, workspace, stream, &prc) != 0;
+  if (persistent && prc) return prc;
+  if (!persistent) {
+  MPNN_CUDA(cudaMemsetAsync(dX, 0, (size_t)rows * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * F * sizeof(float), stream));
+  MPNN_CUDA(cudaMemcpyAsync(dmA, dout, (size_t)B * 2 * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   float* dm = dmA;
   float* dm_prev = dmB;
-  int rc;
   for (int s = steps - 1; s >= 0; --s) {
     StepPtrs cur = step_ptrs(saved, s, B, N, F);
     float* dq = dqS + (size_t)s * B * F;
@@ -320,6 +339,7 @@ int mpnn_set2vec_bwd(const float* X, const float* mask, const float* Wcat, const
     }
   }
   if (dc0) MPNN_CUDA(cudaMemcpyAsync(dc0, dc, (size_t)B * F * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  }
   // parameter gradients over all steps at once
   if ((rc = mpnn_colsum(pwS, nullptr, (int)sb, F, F, 0, dwe, 0, sub, sub_bytes, stream))) return rc;
   if ((rc = mpnn_colsum(dpreS, nullptr, (int)sb, 4 * F, 4 * F, 0, dbcat, 0, sub, sub_bytes, stream))) return rc;

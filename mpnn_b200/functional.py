@@ -723,6 +723,18 @@ class DenseAggFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # Set2Vec readout
 # ------------------------------------------------------------------------------------------------
+_S2V_PERSISTENT = [True]
+
+
+def set2vec_persistent(enabled):
+    """Set2Vec's loop in the persistent kernels (csrc/s2v_persist.cu; default) or as per-iteration launches; returns the
+    previous setting.  (Part of the op-graph keys: a captured per-shape graph holds one of the two forms.)"""
+    prev = _S2V_PERSISTENT[0]
+    _lib.load().mpnn_set2vec_set_persistent(1 if enabled else 0)
+    _S2V_PERSISTENT[0] = bool(enabled)
+    return prev
+
+
 class Set2VecFn(torch.autograd.Function):
     """reference set2vec.py:93-151 ("default" inner product).  Wcat [2F,4F] = [w_hi|w_hf|w_hg|w_ho], bcat [4F];
     m0 [B,2F] / c0 [B,F]: caller-supplied initial state (set2vec.py:111-117), None = zeros."""
@@ -751,7 +763,7 @@ class Set2VecFn(torch.autograd.Function):
                                        steps, ptr(out), ptr(saved), ptr(ws), ws.numel(), stream()), "set2vec_fwd")
 
         out, saved = _graphed(("set2vec_fwd", B, N, F, steps, mask is not None, m0 is not None, c0 is not None,
-                               dev.index), run, [X, mask_c, Wcat, bcat, Wq, we, m0_c, c0_c], make_bufs, 2)
+                               dev.index, _S2V_PERSISTENT[0]), run, [X, mask_c, Wcat, bcat, Wq, we, m0_c, c0_c], make_bufs, 2)
         ctx.save_for_backward(X, mask_c, Wcat, Wq, we, saved, m0_c, c0_c)
         ctx.steps = steps
         return out
@@ -782,7 +794,7 @@ class Set2VecFn(torch.autograd.Function):
 
         if m0 is None and c0 is None:
             dX, dWcat, dbcat, dWq, dwe, dm0, dc0 = _graphed(
-                ("set2vec_bwd", B, N, F, steps, mask is not None, dev.index), run,
+                ("set2vec_bwd", B, N, F, steps, mask is not None, dev.index, _S2V_PERSISTENT[0]), run,
                 [X, mask, Wcat, Wq, we, None, None, saved, dout], make_bufs, 7)
         else:
             bufs = make_bufs()
