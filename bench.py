@@ -54,7 +54,7 @@ WORKLOADS = {
                     desc="basic_graph_autoencoder.encode, ZINC-shaped, B=512/GPU, d=64, ef=8, P=64, T=3"),
     # configs[2]: att_model (AttEdgeNetwork + AdjMsgAgg + MaskBatchNorm + Set2Vec, 100 steps), 128 graphs per GPU
     "zinc": dict(variant="att", d=32, ef=8, T=3, out=128, targets=1, B=128, message_func="AttEdgeNetwork",
-                 readout_func="Set2Vec", graph=False,
+                 readout_func="Set2Vec",
                  desc="att_model (AttEdgeNetwork, AdjMsgAgg, Set2Vec x100), ZINC-shaped, B=128/GPU, d=32, ef=8, P=64, T=3"),
     # configs[3]: normed_encoded_basic_model (atom/bond encoders + masked BN1d everywhere), B=2048 global
     "affinity": dict(variant="normed_encoded", d=8, ef=2, T=3, out=16, targets=1, B=2048, encoders=True,

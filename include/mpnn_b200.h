@@ -34,6 +34,8 @@ typedef struct CUstream_st* mpnn_stream_t; /* == cudaStream_t */
 #define MPNN_ERR_WORKSPACE -4
 
 int mpnn_version(void);            /* major*10000 + minor*100 + patch */
+/* p[0:bytes] <- 0 on `stream` (cudaMemsetAsync: a memset node under graph capture, not a kernel) */
+int mpnn_zero_bytes(void* p, size_t bytes, cudaStream_t stream);
 /* Precision of the widths 33..256: 1 (default) = tcgen05 kernels with TF32 operands and fp32 accumulation (SURVEY 8c:
  * <= 2e-2 relative after the GRU / readout); 0 = the fp32 kernels everywhere (fp32 accuracy, a fraction of the speed).
  * Process-wide; returns the previous setting. */
@@ -166,6 +168,17 @@ int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg,
                        long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
                        float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
                        mpnn_stream_t stream);
+/* mpnn_tc_dense_gemm with a 64-bit offset (floats, multiple of 4) between the G output blocks: they may be different
+ * buffers (the GRU backward writes dm and dh = its two blocks) */
+int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                          long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
+                          float* Y, int ldy, long long ycol, int accumulate, int DP, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+/* GRU weight gradients for widths <= 64 in ONE pass over the gate gradients (gru_update.py:27-28 backward):
+ * dW_ih [d,3d] = m^T (dar|daz|dan), dW_hh [d,3d] = h^T (dar|daz|dnh); dg [rows, ldg] holds the blocks dar|daz|dan|dnh. */
+size_t mpnn_tc_gru_param_workspace_bytes(void);
+int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
+                           float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
 int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol, int G,
                           int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,

@@ -19,6 +19,7 @@ _PP = ctypes.POINTER(ctypes.c_void_p)
 # name -> (restype, argtypes); must match include/mpnn_b200.h (tests/test_abi.py checks the symbol list)
 SIGNATURES = {
     "mpnn_version": (_I, []),
+    "mpnn_zero_bytes": (_I, [_P, _Z, _P]),
     "mpnn_last_error": (ctypes.c_char_p, []),
     "mpnn_set_tensor_cores": (_I, [_I]),
     "mpnn_tensor_cores_enabled": (_I, []),
@@ -72,6 +73,9 @@ SIGNATURES = {
     "mpnn_tc_linear_fwd": (_I, [_P, _L, _I, _I, _P, _I, _P, _P, _I, _I, _P, _Z, _P]),
     "mpnn_tc_linear_bwd_data": (_I, [_P, _L, _I, _I, _P, _I, _P, _I, _I, _P, _Z, _P]),
     "mpnn_tc_linear_bwd_weight": (_I, [_P, _L, _I, _I, _P, _I, _I, _P, _P, _Z, _P]),
+    "mpnn_tc_dense_gemm_ll": (_I, [_P, _L, _I, _I, _I, _I, _P, _L, _L, _L, _L, _I, _I, _P, _P, _I, _L, _I, _I, _P, _Z, _P]),
+    "mpnn_tc_gru_param_workspace_bytes": (_Z, []),
+    "mpnn_tc_gru_param_grad": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P, _Z, _P]),
     "mpnn_tc_dense_grad_workspace_bytes": (_Z, [_I, _I]),
     "mpnn_tc_dense_gemm_tn": (_I, [_P, _L, _I, _I, _P, _I, _I, _I, _I, _I, _P, _L, _L, _P, _Z, _P]),
     "mpnn_scatter_edge_rows": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),

@@ -200,6 +200,14 @@ extern "C" {
 
 int mpnn_version(void) { return 100; }  // 0.1.0
 
+// bytes of device memory <- 0 on `stream` (a memset node under CUDA-graph capture): the one clear of a captured step's
+// arena of zero-initialised buffers (mpnn_b200/functional.py zeros)
+int mpnn_zero_bytes(void* p, size_t bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(p || bytes == 0, MPNN_ERR_ARG, "zero_bytes: null pointer");
+  if (bytes) MPNN_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+  return MPNN_OK;
+}
+
 const char* mpnn_last_error(void) { return g_err; }
 
 int mpnn_segment_sum(const float* src, const int* ptr, const int* idx, int rows, int width, long long lds, float* out,

@@ -29,6 +29,15 @@ extern "C" int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, in
                                      int G, int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
                                      size_t workspace_bytes, cudaStream_t stream);
 
+extern "C" int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                                     long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N,
+                                     const float* bias, float* Y, int ldy, long long ycol, int accumulate, int DP,
+                                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+extern "C" size_t mpnn_tc_gru_param_workspace_bytes(void);
+extern "C" int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
+                                      float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes,
+                                      cudaStream_t stream);
+
 namespace {
 
 __global__ void k_gru_point_fwd(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h,
@@ -86,6 +95,127 @@ __global__ void k_gru_point_bwd(const float* __restrict__ gates, const float* __
   dh[t] = go * z;
 }
 
+
+// Gate gradients of the wide path (d > 32), ONE array dg [rows, 6d] = dar | daz | dan | dnh | hi(go z) | lo(go z).  The
+// last two blocks are the direct term of dh, which the data product adds through identity blocks instead of a
+// read-modify-write epilogue; it is split into a part that is exact in TF32 (13 low mantissa bits cleared) and the
+// remainder, so that the tensor core's operand truncation costs the dominant term of dh 2^-22 instead of 2^-11,
+// and their column sums (the bias gradients) as per-CTA partials: a thread owns 4 columns and walks the rows, so the
+// sums stay in registers; no second pass over the gate gradients.
+__global__ void __launch_bounds__(256) k_gru_point_bwd5(const float* __restrict__ gates, const float* __restrict__ h,
+                                                        const float* __restrict__ mask,
+                                                        const float* __restrict__ dhout, long long rows, int d,
+                                                        float* __restrict__ dg, float* __restrict__ bias_part) {
+  __shared__ float4 red[256];
+  const int cg = d >> 2;                      // column groups per row
+  const int rpb = 256 / cg;                   // rows per block and iteration
+  const int ty = threadIdx.x / cg, c = (threadIdx.x - ty * cg) * 4;
+  const bool active = ty < rpb;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+  if (active) {
+    for (long long row = (long long)blockIdx.x * rpb + ty; row < rows; row += (long long)gridDim.x * rpb) {
+      const float mu = __ldg(mask + row);
+      const float* g = gates + row * 4 * d + c;
+      const float4 sr = __ldg(reinterpret_cast<const float4*>(g));
+      const float4 sz = __ldg(reinterpret_cast<const float4*>(g + d));
+      const float4 tn = __ldg(reinterpret_cast<const float4*>(g + 2 * d));
+      const float4 nh = __ldg(reinterpret_cast<const float4*>(g + 3 * d));
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + row * d + c));
+      const float4 dv = __ldg(reinterpret_cast<const float4*>(dhout + row * d + c));
+      float4 o0, o1, o2, o3, o4, o5;
+#define MPNN_GRU_POINT(X)                                  \
+  {                                                        \
+    const float r_ = sr.X * mu, z_ = sz.X * mu, n_ = tn.X * mu; \
+    const float go = dv.X * mu;                            \
+    const float dn = go * (1.f - z_);                      \
+    const float dz = go * (hv.X - n_);                     \
+    const float dan = dn * mu * (1.f - tn.X * tn.X);       \
+    const float dr = dan * nh.X;                           \
+    o0.X = dr * mu * sr.X * (1.f - sr.X);                  \
+    o1.X = dz * mu * sz.X * (1.f - sz.X);                  \
+    o2.X = dan;                                            \
+    o3.X = dan * r_;                                       \
+    const float gz = go * z_;                              \
+    o4.X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u); \
+    o5.X = gz - o4.X;                                      \
+  }
+      MPNN_GRU_POINT(x) MPNN_GRU_POINT(y) MPNN_GRU_POINT(z) MPNN_GRU_POINT(w)
+#undef MPNN_GRU_POINT
+      float* o = dg + row * 6 * d + c;
+      *reinterpret_cast<float4*>(o) = o0;
+      *reinterpret_cast<float4*>(o + d) = o1;
+      *reinterpret_cast<float4*>(o + 2 * d) = o2;
+      *reinterpret_cast<float4*>(o + 3 * d) = o3;
+      *reinterpret_cast<float4*>(o + 4 * d) = o4;
+      *reinterpret_cast<float4*>(o + 5 * d) = o5;
+      s0.x += o0.x; s0.y += o0.y; s0.z += o0.z; s0.w += o0.w;
+      s1.x += o1.x; s1.y += o1.y; s1.z += o1.z; s1.w += o1.w;
+      s2.x += o2.x; s2.y += o2.y; s2.z += o2.z; s2.w += o2.w;
+      s3.x += o3.x; s3.y += o3.y; s3.z += o3.z; s3.w += o3.w;
+    }
+  }
+  // fixed-order sum over the block's row slots, one gate block at a time
+  float* out = bias_part + (size_t)blockIdx.x * 4 * d;
+#pragma unroll 1
+  for (int b = 0; b < 4; ++b) {
+    red[threadIdx.x] = b == 0 ? s0 : b == 1 ? s1 : b == 2 ? s2 : s3;
+    __syncthreads();
+    if (threadIdx.x < cg) {
+      float4 t = red[threadIdx.x];
+      for (int y = 1; y < rpb; ++y) {
+        const float4 v = red[y * cg + threadIdx.x];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      *reinterpret_cast<float4*>(out + b * d + threadIdx.x * 4) = t;
+    }
+    __syncthreads();
+  }
+}
+
+// db_ih = (sum dar | sum daz | sum dan), db_hh = (sum dar | sum daz | sum dnh) over the per-CTA partials, fixed order
+__global__ void __launch_bounds__(256) k_gru_bias_final(const float* __restrict__ part, int n_part, int d,
+                                                        float* __restrict__ db_ih, float* __restrict__ db_hh) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= 4 * d) return;
+  float s = 0.f;
+  int i = 0;
+  for (; i + 4 <= n_part; i += 4) {
+    const float v0 = part[(size_t)i * 4 * d + j], v1 = part[(size_t)(i + 1) * 4 * d + j],
+                v2 = part[(size_t)(i + 2) * 4 * d + j], v3 = part[(size_t)(i + 3) * 4 * d + j];
+    s += v0;
+    s += v1;
+    s += v2;
+    s += v3;
+  }
+  for (; i < n_part; ++i) s += part[(size_t)i * 4 * d + j];
+  const int b = j / d, c = j - b * d;
+  if (b < 2) {
+    db_ih[j] = s;
+    db_hh[j] = s;
+  } else if (b == 2) {
+    db_ih[j] = s;
+  } else {
+    db_hh[2 * d + c] = s;
+  }
+}
+
+// Wc[g][s][n][k] (g: 0 = dm, 1 = dh; s: the six blocks of dg): the B matrices of the data product
+//   dm = dar Wr_ih^T + daz Wz_ih^T + dan Wn_ih^T,   dh = dar Wr_hh^T + daz Wz_hh^T + dnh Wn_hh^T + (hi + lo) I
+__global__ void __launch_bounds__(256) k_gru_bwd_wcomb(const float* __restrict__ W_ih, const float* __restrict__ W_hh,
+                                                       int d, float* __restrict__ Wc) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= 12 * d * d) return;
+  const int k = i % d, n = (i / d) % d, s = (i / (d * d)) % 6, g = i / (6 * d * d);
+  float v = 0.f;
+  if (g == 0) {
+    if (s < 3) v = W_ih[(size_t)n * 3 * d + s * d + k];
+  } else {
+    if (s < 2) v = W_hh[(size_t)n * 3 * d + s * d + k];
+    else if (s == 3) v = W_hh[(size_t)n * 3 * d + 2 * d + k];
+    else if (s >= 4) v = n == k ? 1.f : 0.f;
+  }
+  Wc[i] = v;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Fused GRU for feature widths <= 32: one kernel forward, one kernel (+ a fixed-order reduction of the
@@ -374,8 +504,11 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
   size_t sub = g > c ? g : c;
   const int DP = d > 32 ? mpnn_tc_dp(d, d) : -1;   // widths 33..256: gate GEMMs on the tensor cores (tc_message.cu)
   if (DP > 0) {
-    size_t t = align_up(mpnn_tc_dense_workspace_bytes(3, DP), 256) + mpnn_tc_dense_grad_workspace_bytes(3, DP);
+    size_t t = align_up(mpnn_tc_dense_workspace_bytes(12, DP), 256) + mpnn_tc_dense_grad_workspace_bytes(3, DP);
     if (t > sub) sub = t;
+    if (mpnn_tc_gru_param_workspace_bytes() > sub) sub = mpnn_tc_gru_param_workspace_bytes();
+    // dg [rows, 6d] (= the two [rows, 3d] arrays of the fp32 path) + bias partials + the combined weights
+    pre += align_up((size_t)4 * mpnn_num_sms() * 4 * d * sizeof(float), 256) + align_up((size_t)12 * d * d * sizeof(float), 256);
   }
   size_t need = pre + align_up(sub, 256);
   const size_t tg = mpnn_tc_gru_workspace_bytes(d);
@@ -489,6 +622,37 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
     MPNN_CHECK_LAUNCH("k_gru_bwd_reduce");
     return MPNN_OK;
   }
+  const int DP = mpnn_tc_dp(d, d);
+  if (DP > 0 && ((dh - dm) & 3) == 0) {
+    // ---- tensor-core path: three passes over ONE gate-gradient array ----
+    //   1. k_gru_point_bwd5: dg [rows, 6d] = dar | daz | dan | dnh | hi(go z) | lo(go z), and the bias gradients
+    //   2. one grouped product for both data gradients: (dm | dh) = dg Wc (block g of the output is buffer g)
+    //   3. the weight gradients: widths <= 64 in one pass (m and h stacked into one M = 128 operand), else per product
+    char* wp = (char*)workspace;
+    float* dg = (float*)wp;
+    wp += align_up((size_t)rows * 6 * d * sizeof(float), 256);
+    const int nblk = 4 * mpnn_num_sms();
+    float* bias_part = (float*)wp;
+    wp += align_up((size_t)nblk * 4 * d * sizeof(float), 256);
+    float* Wc = (float*)wp;
+    wp += align_up((size_t)12 * d * d * sizeof(float), 256);
+    void* sub = wp;
+    size_t sub_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
+    k_gru_point_bwd5<<<nblk, 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dg, bias_part);
+    MPNN_CHECK_LAUNCH("k_gru_point_bwd5");
+    k_gru_bias_final<<<ceil_div(4 * d, 256), 256, 0, stream>>>(bias_part, nblk, d, db_ih, db_hh);
+    MPNN_CHECK_LAUNCH("k_gru_bias_final");
+    k_gru_bwd_wcomb<<<ceil_div(12 * d * d, 256), 256, 0, stream>>>(W_ih, W_hh, d, Wc);
+    MPNN_CHECK_LAUNCH("k_gru_bwd_wcomb");
+    int rc;
+    if ((rc = mpnn_tc_dense_gemm_ll(dg, rows, 6 * d, d, 6, d, Wc, d, 1, (long long)6 * d * d, (long long)d * d, 2, d, nullptr,
+                                    dm, d, (long long)(dh - dm), 0, DP, sub, sub_bytes, stream)))
+      return rc;
+    if (d <= 64) return mpnn_tc_gru_param_grad(m, h, dg, 6 * d, rows, d, dW_ih, dW_hh, sub, sub_bytes, stream);
+    if ((rc = mpnn_tc_dense_gemm_tn(m, rows, d, d, dg, 6 * d, d, 3, d, DP, dW_ih, d, 3 * d, sub, sub_bytes, stream))) return rc;
+    if ((rc = mpnn_tc_dense_gemm_tn(h, rows, d, d, dg, 6 * d, d, 2, d, DP, dW_hh, d, 3 * d, sub, sub_bytes, stream))) return rc;
+    return mpnn_tc_dense_gemm_tn(h, rows, d, d, dg + 3 * d, 6 * d, d, 1, d, DP, dW_hh + 2 * d, d, 3 * d, sub, sub_bytes, stream);
+  }
   char* wp = (char*)workspace;
   float* dgi = (float*)wp;
   wp += align_up((size_t)rows * 3 * d * sizeof(float), 256);
@@ -500,28 +664,6 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
   k_gru_point_bwd<<<ceil_div(rows * d, 256), 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dgi, dgh, dh);
   MPNN_CHECK_LAUNCH("k_gru_point_bwd");
   int rc;
-  const int DP = mpnn_tc_dp(d, d);
-  if (DP > 0) {
-    // tensor-core path: dm = sum_g dgi_g W_ih,g^T (three K segments), dW = X^T dG (K = rows, per-CTA partials)
-    char* ip = (char*)sub;
-    size_t img_bytes = align_up(mpnn_tc_dense_workspace_bytes(3, DP), 256);
-    void* gsub = ip + img_bytes;
-    size_t gsub_bytes = sub_bytes - img_bytes;
-    if ((rc = mpnn_tc_dense_gemm(dgi, rows, 3 * d, d, 3, d, W_ih, 3 * d, 1, 0, d, 1, d, nullptr, dm, d, 0, 0, DP, sub, sub_bytes,
-                                 stream)))
-      return rc;
-    if ((rc = mpnn_tc_dense_gemm(dgh, rows, 3 * d, d, 3, d, W_hh, 3 * d, 1, 0, d, 1, d, nullptr, dh, d, 0, 1, DP, sub, sub_bytes,
-                                 stream)))
-      return rc;
-    if ((rc = mpnn_tc_dense_gemm_tn(m, rows, d, d, dgi, 3 * d, d, 3, d, DP, dW_ih, d, 3 * d, gsub, gsub_bytes, stream))) return rc;
-    if ((rc = mpnn_tc_dense_gemm_tn(h, rows, d, d, dgh, 3 * d, d, 3, d, DP, dW_hh, d, 3 * d, gsub, gsub_bytes, stream))) return rc;
-    // dgh = (dar | daz | dnh) shares its first two gate blocks with dgi = (dar | daz | dan): one full column sum, one over
-    // the last block only, and a 2d-float copy (the second full pass over [rows, 3d] was 94 us at B = 16 384, d = 64)
-    if ((rc = mpnn_colsum(dgi, nullptr, rows, 3 * d, 3 * d, 0, db_ih, 0, gsub, gsub_bytes, stream))) return rc;
-    if ((rc = mpnn_colsum(dgh + 2 * d, nullptr, rows, d, 3 * d, 0, db_hh + 2 * d, 0, gsub, gsub_bytes, stream))) return rc;
-    MPNN_CUDA(cudaMemcpyAsync(db_hh, db_ih, (size_t)2 * d * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    return MPNN_OK;
-  }
   // dm = dgi W_ih^T ; dh += dgh W_hh^T
   if ((rc = mpnn_gemm(dgi, W_ih, dm, R, d, 3 * d, 3 * d, 1, 1, 3 * d, d, nullptr, 0, nullptr, 0, stream))) return rc;
   if ((rc = mpnn_gemm(dgh, W_hh, dh, R, d, 3 * d, 3 * d, 1, 1, 3 * d, d, nullptr, 2, nullptr, 0, stream))) return rc;

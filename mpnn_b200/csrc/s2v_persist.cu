@@ -23,7 +23,6 @@ namespace {
 
 constexpr float BIG_NEGATIVE = -1e8f;  // set2vec.py:10
 constexpr int NT = 512;
-constexpr int NW = NT / 32;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct S2VFwd {

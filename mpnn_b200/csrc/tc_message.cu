@@ -268,7 +268,7 @@ struct TcGemm {
   long long rows;
   int kseg;             // K segments accumulated per tile: segment s reads A columns s*acol.. and B matrix u*kseg+s
   int acol;
-  int ycol;             // output column offset between N-blocks
+  long long ycol;       // output offset (floats) between N-blocks
   int accumulate;       // Y += result
   const float* bias;    // [G*N] or null
 };
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
       gemm_tile(a, t, u, pos, cnt);
       const int e = r < cnt ? (a.dense ? pos + r : __ldg(a.type_eid + pos + r)) : -1;
       const float al = (e >= 0 && a.use_alpha) ? __ldg(a.plan.palpha + pos + r) : 1.f;
-      const int ybase = a.dense ? u * a.ycol : 0;
+      const long long ybase = a.dense ? (long long)u * a.ycol : 0;
       const float* bias = a.bias ? a.bias + (size_t)u * a.N : nullptr;
       int erow[8];
 #pragma unroll
@@ -1051,6 +1051,186 @@ __global__ void __launch_bounds__(GruCfg<DP, KP>::GRU_THREADS, 1) k_tc_gru_fwd(T
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// GRU weight gradients for widths <= 64 in ONE pass over the gate gradients (gru_update.py:27-28 backward):
+//     dW_ih [d, 3d] = m^T (dar | daz | dan),     dW_hh [d, 3d] = h^T (dar | daz | dnh)
+// Both products contract over the rows, so every operand is MN-major (the table-gradient machinery above).  m and h
+// are stacked into one M = 128 operand ([m row | h row], 64 columns each) and the four gate-gradient blocks into one
+// N = 256 operand: one tcgen05.mma per 8 rows gives D[128][256] = [m^T; h^T] (dar|daz|dan|dnh), of which the reduction
+// keeps m^T (dar|daz|dan) and h^T (dar|daz|dnh).  Every CTA accumulates its rows in TMEM and writes ONE partial.
+// (The per-product kernels read m / h three times and the gate gradients twice: 1.04 GB instead of 0.58 GB at
+// B = 16 384, d = 64.)
+// ---------------------------------------------------------------------------------------------------
+struct TcGruParam {
+  const float* m;     // [rows, d]
+  const float* h;     // [rows, d]
+  const float* dg;    // [rows, ldg]: blocks dar | daz | dan | dnh, d columns each
+  float* partial;     // [grid][128][256]
+  long long rows;
+  int d, ldg;
+};
+struct GpCfg {
+  static constexpr int KST = 32;                 // rows per stage
+  static constexpr int EPT = KST / 16;
+  static constexpr int A_BYTES = KST * 128 * 4;
+  static constexpr int B_BYTES = KST * 256 * 4;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = 4;
+  static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+  static constexpr int TCOLS = 256;
+  static constexpr uint32_t SBO = 512;
+  static constexpr uint32_t LBO = (KST / 4) * 512;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_grad(TcGruParam a) {
+  using C = GpCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 2);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSTAGE + s); };
+  const uint32_t accfull_bar = bar_base + 8u * (2 * C::NSTAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) {
+      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_chunks = (a.rows + C::KST - 1) / C::KST;
+  const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const long long c0 = (long long)blockIdx.x * per;
+  const long long c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+  const int d = a.d;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int sub = tid >> 3, chunk = tid & 7;
+    int stage = 0, phase = 0;
+    for (long long c = c0; c < c1; ++c) {
+      const long long pos = c * C::KST;
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      const uint32_t As = smem_base + stage * C::STAGE;
+      const uint32_t Bs = As + C::A_BYTES;
+#pragma unroll
+      for (int hh = 0; hh < C::EPT; ++hh) {
+        const int r = sub + 16 * hh;
+        const long long row = pos + r;
+        const bool rok = row < a.rows;
+        const uint32_t roff = (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk);
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          const int col = (mb & 1) * 32 + chunk * 4;
+          const float* base = mb < 2 ? a.m : a.h;
+          const bool ok = rok && col < d;
+          cp_async16(As + (uint32_t)mb * C::LBO + roff, ok ? base + (size_t)row * d + col : base, ok ? 16u : 0u);
+        }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const int col = (nb & 1) * 32 + chunk * 4;
+          const bool ok = rok && col < d;
+          cp_async16(Bs + (uint32_t)nb * C::LBO + roff,
+                     ok ? a.dg + (size_t)row * a.ldg + (size_t)(nb >> 1) * d + col : a.dg, ok ? 16u : 0u);
+        }
+      }
+      cp_async_arrive_noinc(full_bar(stage));
+      if (++stage == C::NSTAGE) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && c0 < c1) {
+      constexpr uint32_t idesc = make_idesc(128, 256, 1, 1);
+      int stage = 0, phase = 0;
+      bool fresh = true;
+      for (long long c = c0; c < c1; ++c) {
+        mbar_wait(full_bar(stage), phase);
+        fence_proxy_async();
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE;
+#pragma unroll
+        for (int j = 0; j < C::KST / 8; ++j) {
+          const uint64_t ad = make_sdesc(sa + j * 1024, C::LBO, C::SBO, 1u);
+          const uint64_t bd = make_sdesc(sa + C::A_BYTES + j * 1024, C::LBO, C::SBO, 1u);
+          umma_tf32(tmem_base, ad, bd, idesc, fresh ? 0u : 1u);
+          fresh = false;
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == C::NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(accfull_bar);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int l = q * 32 + lane;
+    float* out = a.partial + (size_t)blockIdx.x * 128 * 256 + (size_t)l * 256;
+    if (c0 < c1) {
+      mbar_wait(accfull_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 256; cc += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(out + cc + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    } else {
+      for (int cc = 0; cc < 256; cc += 4) *reinterpret_cast<float4*>(out + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+// dW_ih[k][g*d + c] = sum_cta partial[cta][k][g*64 + c];  dW_hh[k][g*d + c] = sum_cta partial[cta][64 + k][blk(g)*64 + c],
+// blk = (0, 1, 3): fixed order over the CTAs
+__global__ void __launch_bounds__(256) k_tc_gru_param_reduce(const float* __restrict__ partial, int n_cta, int d,
+                                                             float* __restrict__ dW_ih, float* __restrict__ dW_hh) {
+  const int per = 3 * d * d;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= 2 * per) return;
+  const int which = e / per, rem = e - which * per;
+  const int k = rem / (3 * d), j = rem - k * 3 * d;
+  const int g = j / d, c = j - g * d;
+  const int blk = (which == 1 && g == 2) ? 3 : g;
+  const float* p = partial + (size_t)(which * 64 + k) * 256 + blk * 64 + c;
+  float s = 0.f;
+  int i = 0;
+  for (; i + 4 <= n_cta; i += 4) {
+    const float v0 = p[(size_t)i * 32768], v1 = p[(size_t)(i + 1) * 32768], v2 = p[(size_t)(i + 2) * 32768],
+                v3 = p[(size_t)(i + 3) * 32768];
+    s += v0;
+    s += v1;
+    s += v2;
+    s += v3;
+  }
+  for (; i < n_cta; ++i) s += p[(size_t)i * 32768];
+  (which ? dW_hh : dW_ih)[rem] = s;
+}
+
 // out[u*su + l*sl + k] (l < M, k < N) = sum over the CTAs whose tile range touches type u of partial[cta + u][l][k]
 // (fixed order).  Plan mode: the tile range of a type comes from tile_off; dense mode: type u owns tiles [u*RT, (u+1)*RT).
 __global__ void __launch_bounds__(256) k_tc_table_reduce(TcPlan plan, int dense, int RT, int grid_ctas, int ntypes,
@@ -1321,12 +1501,26 @@ int mpnn_tc_table_grad(const void* plan, int edge_capacity, int unique_capacity,
 // [rows, K] x [K, N] products on contiguous rows: the grouped-GEMM kernel with an identity plan.
 size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP) { return (size_t)n_blocks * DP * DP * sizeof(float); }
 
+int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                          long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
+                          float* Y, int ldy, long long ycol, int accumulate, int DP, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream);
+
 // Y[r, g*ycol + n] (+)= sum_{s < kseg} sum_{k < K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + g*w_sg + s*w_ss] + bias[g*N + n]
 // for g < G, n < N.  K, N <= DP in {64, 128, 256}; widths, strides of A / Y multiples of 4 floats.
 int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
                        long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
                        float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
+  return mpnn_tc_dense_gemm_ll(A, rows, lda, K, kseg, acol, W, w_sn, w_sk, w_sg, w_ss, G, N, bias, Y, ldy, (long long)ycol,
+                          accumulate, DP, workspace, workspace_bytes, stream);
+}
+
+// the same with a 64-bit offset between the G output blocks (they may be different buffers: mpnn_gru_bwd's dm / dh)
+int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
+                     long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
+                     float* Y, int ldy, long long ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
   MPNN_REQUIRE(A && W && Y && workspace && rows > 0 && G > 0 && kseg > 0, MPNN_ERR_ARG, "tc_dense_gemm: bad argument");
   MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm: DP must be 64, 128 or 256");
   MPNN_REQUIRE((K & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldy & 3) == 0 && (acol & 3) == 0 && (ycol & 3) == 0 &&
@@ -1500,6 +1694,27 @@ int mpnn_tc_linear_bwd_weight(const float* dY, long long rows, int ldd, int N, c
                                    dW + (size_t)mb * Nb * K, Ks, K, workspace, workspace_bytes, stream);
     if (rc) return rc;
   }
+  return MPNN_OK;
+}
+
+// ---- GRU weight gradients for widths <= 64 in one pass (k_tc_gru_param_grad) --------------------------------------
+size_t mpnn_tc_gru_param_workspace_bytes(void) { return (size_t)tc_grid() * 128 * 256 * sizeof(float); }
+
+// dg [rows, ldg]: the gate-gradient blocks dar | daz | dan | dnh (d columns each, as mpnn_gru_bwd lays them out)
+int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
+                           float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(m && h && dg && dW_ih && dW_hh && workspace && rows > 0, MPNN_ERR_ARG, "tc_gru_param_grad: bad argument");
+  MPNN_REQUIRE(d > 0 && d <= 64 && (d & 3) == 0 && (ldg & 3) == 0 && ldg >= 4 * d, MPNN_ERR_UNSUPPORTED,
+               "tc_gru_param_grad: width %d not served", d);
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_param_workspace_bytes(), MPNN_ERR_WORKSPACE,
+               "tc_gru_param_grad: workspace too small");
+  TcGruParam a = {m, h, dg, (float*)workspace, rows, d, ldg};
+  const int grid = tc_grid();
+  MPNN_REQUIRE(set_smem(k_tc_gru_param_grad, GpCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_param_grad: smem attribute");
+  k_tc_gru_param_grad<<<grid, THREADS, GpCfg::SMEM, stream>>>(a);
+  MPNN_CHECK_LAUNCH("k_tc_gru_param_grad");
+  k_tc_gru_param_reduce<<<ceil_div(6 * d * d, 256), 256, 0, stream>>>(a.partial, grid, d, dW_ih, dW_hh);
+  MPNN_CHECK_LAUNCH("k_tc_gru_param_reduce");
   return MPNN_OK;
 }
 

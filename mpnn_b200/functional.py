@@ -186,6 +186,48 @@ class _inline(object):
         return False
 
 
+# ------------------------------------------------------------------------------------------------
+# Zero-initialised buffers of a captured step.  Accumulators and "rows the kernel skips are zero" outputs each cost a
+# fill launch per step; inside a captured step (graphs.GraphedStep) they are carved from ONE arena that a single
+# memset node clears at the head of the graph.  GraphedStep sizes the arena with an eager dry run of the step.
+# ------------------------------------------------------------------------------------------------
+_ARENA = {"mode": None, "need": 0, "buf": None, "off": 0}
+
+
+def arena_measure():
+    _ARENA.update(mode="measure", need=0, buf=None, off=0)
+
+
+def arena_begin(buf):
+    """buf: uint8 tensor the caller has cleared (on the capturing stream, inside the graph)"""
+    _ARENA.update(mode="carve", buf=buf, off=0)
+
+
+def arena_end():
+    need = _ARENA["need"]
+    _ARENA.update(mode=None, buf=None, off=0, need=0)
+    return need
+
+
+def zeros(shape, dtype, device):
+    """torch.zeros(shape), or a slice of the captured step's cleared arena"""
+    mode = _ARENA["mode"]
+    if mode is None:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    n = 1
+    for v in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+        n *= int(v)
+    nbytes = (n * torch.empty(0, dtype=dtype).element_size() + 255) // 256 * 256
+    if mode == "measure":
+        _ARENA["need"] += nbytes
+        return torch.zeros(shape, dtype=dtype, device=device)
+    buf, off = _ARENA["buf"], _ARENA["off"]
+    if buf is None or buf.device != torch.device(device) or off + nbytes > buf.numel():
+        return torch.zeros(shape, dtype=dtype, device=device)     # (a shape the dry run did not see)
+    _ARENA["off"] = off + nbytes
+    return buf[off:off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(shape)
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -618,6 +660,38 @@ class GatherRowsFn(torch.autograd.Function):
         return dsrc, None, None, None
 
 
+class TypeGatherFn(torch.autograd.Function):
+    """out[e,:] = per_type[uid[e],:] for every edge slot; backward: the fixed-order sum over each type's edge list
+    (type_ptr / type_eid of graph.TypedInfo; the rows behind the last type, e.g. the zero row, get zero)."""
+
+    @staticmethod
+    def forward(ctx, per_type, ti):
+        lib = _lib.load()
+        _need_cuda(per_type)
+        per_type = f32c(per_type)
+        T, width = ti.uid.shape[0], per_type.shape[1]
+        out = torch.empty(T, width, dtype=torch.float32, device=per_type.device)
+        if T:
+            unit = torch.arange(T + 1, dtype=torch.int32, device=per_type.device)
+            check(lib.mpnn_segment_sum(ptr(per_type), ptr(unit), ptr(ti.uid), T, width, width, ptr(out), width, 0, 1.0,
+                                       stream()), "segment_sum")
+        ctx.t = (ti, per_type.shape[0], width)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        ti, n_src, width = ctx.t
+        dout = f32c(dout)
+        ti.wait_sorted()
+        d = zeros((n_src, width), torch.float32, dout.device)
+        n_types = min(n_src, ti.type_ptr.shape[0] - 1)
+        check(lib.mpnn_segment_sum(ptr(dout), ptr(ti.type_ptr), ptr(ti.type_eid), n_types, width, width, ptr(d), width,
+                                   0, 1.0, stream()), "segment_sum")
+        return d, None
+
+
 # ------------------------------------------------------------------------------------------------
 # linear layer on flat rows (plumbing GEMM of the library; y = x W^T + b, W is an nn.Linear weight)
 # ------------------------------------------------------------------------------------------------
@@ -932,8 +1006,8 @@ class EdgeNetTableFn(torch.autograd.Function):
         urows, w_tied, W_last, saved = ctx.saved_tensors[:4]
         gw = list(ctx.saved_tensors[4:])
         R, ef, G, P, n_tied, nf, mf = ctx.dims
-        dT = f32c(dT)
         dev = urows.device
+        dT = f32c(dT) if dT is not None else zeros((R, table_dp(nf, mf), table_dp(nf, mf)), torch.float32, dev)
         d_w_tied = torch.empty_like(w_tied)
         d_W_last = torch.empty_like(W_last)
         d_B_last = torch.empty(W_last.shape[0], dtype=torch.float32, device=dev)
@@ -980,6 +1054,7 @@ class TableLayoutFn(torch.autograd.Function):
         check(lib.mpnn_table_from_flat(ptr(flat), R, nf, mf, ptr(table), ptr(tableT), stream()), "table_from_flat")
         ctx.dims = (R, nf, mf)
         ctx.mark_non_differentiable(tableT)
+        ctx.set_materialize_grads(False)
         return table, tableT
 
     @staticmethod
@@ -987,6 +1062,8 @@ class TableLayoutFn(torch.autograd.Function):
     def backward(ctx, dT, _dTt):
         lib = _lib.load()
         R, nf, mf = ctx.dims
+        if dT is None:
+            return None, None, None
         dT = f32c(dT)
         dflat = torch.empty(R, mf * nf, dtype=torch.float32, device=dT.device)
         check(lib.mpnn_table_to_flat(ptr(dT), R, nf, mf, ptr(dflat), stream()), "table_to_flat")
@@ -1028,6 +1105,7 @@ class MultiEdgeNetTableFn(torch.autograd.Function):
         for k in range(K):
             out += [tables[k], tablesT[k]]
         ctx.mark_non_differentiable(*tablesT)
+        ctx.set_materialize_grads(False)     # (else autograd fills a zero tensor per transposed table, every step)
         return tuple(out)
 
     @staticmethod
@@ -1046,7 +1124,7 @@ class MultiEdgeNetTableFn(torch.autograd.Function):
         for k in range(K):
             g = grads[2 * k]
             if g is None:
-                g = torch.zeros(R, DP, DP, dtype=torch.float32, device=dev)
+                g = zeros((R, DP, DP), torch.float32, dev)
             else:
                 ev = _ready_get(g)
                 ready = ev if ev is not None else ready
@@ -1257,7 +1335,7 @@ class ChainFn(torch.autograd.Function):
             ptrs += [g, be, b.get("running_mean"), b.get("running_var")]
         keep = [p for p in ptrs if p is not None]
         bn_ptrs = ptr_array(ptrs)
-        out = torch.zeros_like(h_init)      # rows with mask == 0 are skipped by the kernel: exact zeros
+        out = zeros(h_init.shape, torch.float32, h_init.device)   # rows with mask == 0 are skipped by the kernel: exact zeros
         saved = torch.empty(lib.mpnn_chain_saved_floats(rows, d, T), dtype=torch.float32, device=dev)
         if real[1] is not None:
             torch.cuda.current_stream(dev).wait_event(real[1])
@@ -1294,8 +1372,8 @@ class ChainFn(torch.autograd.Function):
                 g, be = affine[aff_idx[t]], affine[aff_idx[t] + 1]
             ptrs += [g, be, b.get("running_mean"), b.get("running_var")]
         # padded rows (mask == 0) are skipped by the kernel: their gradients are exact zeros
-        dM = torch.zeros(T, rows, d, dtype=torch.float32, device=dev)
-        dh = torch.zeros_like(h_init) if need_h else None
+        dM = zeros((T, rows, d), torch.float32, dev)
+        dh = zeros(h_init.shape, torch.float32, dev) if need_h else None
         dW_ih, dW_hh = torch.empty_like(W_ih), torch.empty_like(W_hh)
         db_ih, db_hh = torch.empty_like(b_ih), torch.empty_like(b_hh)
         d_aff = [torch.empty_like(a) for a in affine]

@@ -39,11 +39,21 @@ class EdgeList(object):
     def per_edge_view(self):
         """The same edge list for message functions that bring ONE explicit sender vector per edge (AttEdgeNetwork's
         gated states, att_edge_network.py:26) instead of gathering node states: sender row of edge e is e."""
-        if self.E is None:
-            raise RuntimeError("mpnn_b200: per-edge sender vectors are not available in capacity (graph-capture) mode")
         if self._per_edge is None:
             self._per_edge = PerEdgeView(self)
         return self._per_edge
+
+    def neutralise_tail(self):
+        """capacity mode: edge slots behind the last real edge -> sender / receiver / bond type 0, weight 0 (in place;
+        the CSR / CSC / type lists never reach them, only per-slot kernels do)"""
+        if self.E is not None or getattr(self, "_tail_done", False):
+            return
+        self._tail_done = True
+        tail = torch.arange(self.Ecap, device=self.row_ptr.device) >= self.row_ptr[-1]
+        self.edge_w.masked_fill_(tail, 0.0)
+        self.edge_src.masked_fill_(tail, 0)
+        self.edge_dst.masked_fill_(tail, 0)
+        self.typed().uid.masked_fill_(tail, 0)
 
     @property
     def csc_dst(self):
@@ -61,7 +71,12 @@ class PerEdgeView(object):
     def __init__(self, el):
         dev = el.row_ptr.device
         E = el.E
-        self.B, self.N, self.ef, self.E, self.Ecap, self.n_rows = el.B, el.N, el.ef, E, el.Ecap, el.n_rows
+        if E is None:
+            # capacity mode: one sender vector per edge SLOT.  The slots behind the batch's last edge get valid indices
+            # and weight 0, so that whatever is computed for them is finite and their gradients are exactly zero.
+            E = el.Ecap
+            el.neutralise_tail()
+        self.B, self.N, self.ef, self.E, self.Ecap, self.n_rows = el.B, el.N, el.ef, el.E, el.Ecap, el.n_rows
         self.row_ptr, self.edge_dst, self.edge_w, self.rows = el.row_ptr, el.edge_dst, el.edge_w, el.rows
         self.edge_src = torch.arange(max(E, 1), dtype=torch.int32, device=dev)[:E]
         self.col_ptr = torch.arange(E + 1, dtype=torch.int32, device=dev)
@@ -148,7 +163,8 @@ def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap):
     uid = torch.empty(max(Ecap, 1), **i32)
     edge_w = torch.empty(Ecap, dtype=torch.float32, device=dev)
     urows = torch.empty(Ucap + 1, ef, dtype=torch.float32, device=dev)
-    counts = torch.zeros(4, **i32)
+    from . import functional
+    counts = functional.zeros((4,), torch.int32, dev)
     ws = _lib.clean_workspace(lib.mpnn_prep_workspace_bytes(B, Ucap), dev)
     _lib.check(lib.mpnn_prep_edges(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, Ecap, Ucap, _lib.ptr(row_ptr),
                                    _lib.ptr(col_ptr), _lib.ptr(edge_src), _lib.ptr(edge_dst), _lib.ptr(edge_w),

@@ -11,7 +11,7 @@ bond rows U) from DEVICE memory, arrays are sized by capacities fixed at capture
 """
 import torch
 
-from . import functional, graph
+from . import _lib, functional, graph
 
 
 class GraphedStep(object):
@@ -26,6 +26,7 @@ class GraphedStep(object):
     def __init__(self, step_fn, example_inputs, warmup=3, headroom=1.25, edge_capacity=None, unique_capacity=None):
         self.static = {k: v.clone() for k, v in example_inputs.items()}
         self.step_fn = step_fn
+        self.eager_steps = warmup + 1    # executions of step_fn before the capture (warm-up + the arena dry run)
         graph.STATS["E"] = graph.STATS["U"] = graph.STATS["n_real"] = 0
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -40,13 +41,31 @@ class GraphedStep(object):
         self.unique_capacity = int(unique_capacity or min(max(int(graph.STATS["U"] * 1.5) + 8, 16),
                                                            graph.TYPED_MAX_UNIQUE))
         del n_rows
+        # dry run with the captured array sizes: how many bytes of zero-initialised buffers does one step ask for?
+        graph.clear_cache()
+        functional.arena_measure()
+        try:
+            with graph.capacities(self.edge_capacity, self.unique_capacity):
+                with torch.cuda.stream(side):
+                    step_fn(self.static)
+        finally:
+            need = functional.arena_end()
+        torch.cuda.synchronize()
+        del graph._CAPTURED_COUNTS[:]
+        self.arena = torch.empty(max(need, 256), dtype=torch.uint8, device=next(iter(self.static.values())).device)
         self.graph = torch.cuda.CUDAGraph()
         graph.clear_cache()
-        del graph._CAPTURED_COUNTS[:]
         functional._FWD_SIDE.clear()
+        lib = _lib.load()
         with graph.capacities(self.edge_capacity, self.unique_capacity):
             with torch.cuda.graph(self.graph):
-                self.loss = step_fn(self.static)
+                # every zero-initialised buffer of the step is a slice of this arena: one memset node, no fill launches
+                _lib.check(lib.mpnn_zero_bytes(_lib.ptr(self.arena), self.arena.numel(), _lib.stream()), "zero_bytes")
+                functional.arena_begin(self.arena)
+                try:
+                    self.loss = step_fn(self.static)
+                finally:
+                    functional.arena_end()
                 functional.join_side_streams()   # no forked branch may outlive the capture
         self._counts = list(graph._CAPTURED_COUNTS)
         del graph._CAPTURED_COUNTS[:]

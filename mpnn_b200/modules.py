@@ -15,7 +15,7 @@ from .functional import (BilinearEdgeFn, ChainFn, DenseAggFn, MultiEdgeNetTableF
                          Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, chain_supported, table_dp, tc_dp, typed_dp)
 from . import _lib
-from .functional import _note_forward_side_work, _side_stream, real_rows
+from .functional import _note_forward_side_work, _side_stream, real_rows, TypeGatherFn
 import os
 import weakref
 
@@ -358,9 +358,8 @@ class AttEdgeNetwork(EdgeNetwork):
     """reference att_edge_network.py: the sender state is gated, per pair, by softmax_features(attn(cat(h_i, bond)))."""
 
     def _typed_ok(self, bfm, el):
-        # the gate brings one sender vector per edge: served by the table kernels of csrc/typed.cu (widths <= 32) when
-        # the edge count is known on the host (not under CUDA-graph capture)
-        return el.E is not None and typed_dp(self.nf, self.mf) >= 0 and super(AttEdgeNetwork, self)._typed_ok(bfm, el)
+        # the gate brings one sender vector per edge: served by the table kernels of csrc/typed.cu (widths <= 32)
+        return typed_dp(self.nf, self.mf) >= 0 and super(AttEdgeNetwork, self)._typed_ok(bfm, el)
 
     def __init__(self, node_features, edge_features, message_features, activation_fn=None, attn_act=None):
         super(AttEdgeNetwork, self).__init__(node_features, edge_features, message_features, activation_fn)
@@ -378,8 +377,17 @@ class AttEdgeNetwork(EdgeNetwork):
 
     def _sender_vectors(self, afm, bfm, el):
         H = afm.reshape(-1, self.nf)
+        el.neutralise_tail()     # (capacity mode: the slots behind the last edge get valid indices, weight 0)
         Hr = GatherRowsFn.apply(H, el.edge_dst, el.row_ptr, None)          # receiver state per edge
         Hs = GatherRowsFn.apply(H, el.edge_src, el.col_ptr, el.csc_eid)    # sender state per edge
+        if el.E is None:
+            # capacity (graph-capture) mode: one vector per edge SLOT (graph.PerEdgeView); the bond part of the gate is
+            # evaluated on the distinct bond rows and handed out by type, its gradient summed over the type lists
+            ti = el.typed()
+            Wa, ba = self.attn.weight, self.attn.bias
+            LU = LinearFn.apply(ti.urows, Wa[:, self.nf:].contiguous(), None)
+            logits = LinearFn.apply(Hr, Wa[:, :self.nf].contiguous(), ba) + TypeGatherFn.apply(LU, ti)
+            return SoftmaxMulFn.apply(logits, Hs), False
         rows = graph.GatherEdgeRows.apply(bfm, el) if bfm.requires_grad else el.rows
         return SoftmaxMulFn.apply(self._gate_logits(Hr, rows[:el.E]), Hs), False
 

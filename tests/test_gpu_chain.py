@@ -209,13 +209,52 @@ def test_captured_step_equals_eager_step(dev):
             return loss
 
         if mode == "eager":
-            ls = [float(step_fn(batch)) for _ in range(6)]
+            ls = [float(step_fn(batch)) for _ in range(7)]
         else:
             gs = graphs.GraphedStep(step_fn, batch, warmup=3)
-            ls = [float("nan")] * 3 + [float(gs(batch)) for _ in range(3)]
+            assert gs.eager_steps == 4
+            ls = [float("nan")] * 4 + [float(gs(batch)) for _ in range(3)]
             gs.check()
-        losses[mode] = ls[3:]
+        losses[mode] = ls[4:]
         finals[mode] = [p.detach().clone() for p in mod.parameters()]
     assert np.allclose(losses["eager"], losses["graph"], rtol=1e-4, atol=1e-7), losses
     for a, b in zip(finals["eager"], finals["graph"]):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
+
+
+def test_captured_att_step_equals_eager_step(dev):
+    """BASELINE config 3's train step (att_model: AttEdgeNetwork's per-edge gate on edge SLOTS in capacity mode, Set2Vec's
+    persistent kernels, fused Adam) replayed as one CUDA graph against the eager step"""
+    import numpy as np
+    from mpnn_b200 import graph, graphs, modules as M, optim, synthetic
+    b = synthetic.make_batch("zinc", B=24)
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+    d, ef = t["afm"].shape[-1], t["bfm"].shape[-1]
+    labels = torch.randn(24, 4 * d, generator=torch.Generator().manual_seed(1)).to(dev)
+    losses, finals = {}, {}
+    for mode in ("eager", "graph"):
+        graph.clear_cache()
+        mod = _model("att", dev, d, ef, 4 * d, 3, seed=5, message_func=M.AttEdgeNetwork, readout_func=M.Set2Vec,
+                     readout_opts={"time_steps": 10})
+        opt = optim.FusedAdam(list(mod.parameters()), lr=1e-3)
+        batch = dict(t, labels=labels)
+
+        def step_fn(bb):
+            graph.clear_cache()
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(mod(bb["afm"], bb["bfm"], bb["adj"], bb["mask"]), bb["labels"])
+            loss.backward()
+            opt.step()
+            return loss
+
+        if mode == "eager":
+            ls = [float(step_fn(batch)) for _ in range(7)][4:]
+        else:
+            gs = graphs.GraphedStep(step_fn, batch, warmup=3)
+            ls = [float(gs(batch)) for _ in range(3)]
+            gs.check()
+        losses[mode] = ls
+        finals[mode] = [p.detach().clone() for p in mod.parameters()]
+    assert np.allclose(losses["eager"], losses["graph"], rtol=1e-4, atol=1e-7), losses
+    for a, c in zip(finals["eager"], finals["graph"]):
+        assert torch.allclose(a, c, rtol=2e-3, atol=2e-5)

@@ -248,7 +248,7 @@ def test_encoded_step_is_graph_capturable(dev):
             return loss
 
         if mode == "eager":
-            ls = [float(step_fn(batch)) for _ in range(6)][3:]
+            ls = [float(step_fn(batch)) for _ in range(7)][4:]    # GraphedStep: 3 warm-up steps + 1 dry run before capture
         else:
             gs = graphs.GraphedStep(step_fn, batch, warmup=3)
             ls = [float(gs(batch)) for _ in range(3)]
