@@ -356,8 +356,11 @@ def run_ours(args):
     if rank == 0 and w["variant"] in ("normed", "basic", "autoencoder") and not args.no_roofline:
         net0 = body.mfs[0] if hasattr(body, "mfs") else body.mf
         roof = mp_step_roofline(args.config, body, devb, flush, n, e, w["T"], net0.P, 1 if w["variant"] == "normed" else 0)
+    others = None
     if rank == 0 and world == 1 and not args.no_large and not args.no_roofline:
         roof_large = roofline_large(dev, flush)
+        if args.config == "qm9":
+            others = other_config_points(dev, flush)
     # every rank replays the step here (it contains the gradient all-reduce when N > 1); rank 0 keeps the count
     launches = count_launches(run_resident)
     if args.timeline and rank == 0:
@@ -387,6 +390,8 @@ def run_ours(args):
     }
     if roof_large is not None:
         line["roofline_large"] = roof_large
+    if others is not None:
+        line["other_configs"] = others
     if ms3 is not None:
         line["e2e_device_collate"] = {
             "value": world * B * args.steps / (ms3 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": rb_bytes,
@@ -551,6 +556,57 @@ def roofline_large(dev, flush, points=((16384, 64), (16384, 256))):
             torch.cuda.empty_cache()
         except Exception as ex:   # a point that does not fit is reported, not hidden
             out.append({"what": "autoenc_B%d_d%d" % (Bn, h), "error": repr(ex)[:300]})
+    return out
+
+
+def other_config_points(dev, flush, names=("zinc", "affinity_ecfp", "lipo"), steps=20):
+    """the train step of BASELINE.json's other single-GPU configs (configs[0], [2], [3]) on this box, same method as the
+    headline (captured step, L2 flushed between iterations, CUDA events, median): parity-tested workloads, not the
+    metric line -- reported so that every config of the baseline has a driver-run number"""
+    from mpnn_b200 import graph
+    from mpnn_b200.graphs import GraphedStep
+    from mpnn_b200.optim import FusedAdam
+    out = []
+    for name in names:
+        try:
+            w = dict(WORKLOADS[name])
+            batch = make_workload_batch(name, w, 0)
+            devb = {k: torch.from_numpy(batch[k]).to(dev) for k in ("afm", "bfm", "adj", "mask", "labels")}
+            body, head = build_model(w, dev)
+            opt = FusedAdam(list(body.parameters()) + list(head.parameters()), lr=1e-3)
+
+            def step(b):
+                graph.clear_cache()
+                opt.zero_grad(set_to_none=True)
+                loss = torch.nn.functional.mse_loss(head(body(b["afm"], b["bfm"], b["adj"], b["mask"])), b["labels"])
+                loss.backward()
+                opt.step()
+                return loss
+
+            use_graph = w.get("graph", True)
+            gs = GraphedStep(step, devb, warmup=3) if use_graph else None
+            run = gs.replay if gs is not None else (lambda: step(devb))
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for i in range(steps):
+                flush.fill_(i & 1)
+                ev[i][0].record()
+                run()
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            if gs is not None:
+                gs.check()
+            t = float(np.median([a.elapsed_time(b) for a, b in ev]))
+            out.append({"workload": w["desc"], "config": name, "graphs": w["B"], "median_ms_per_step": t,
+                        "graphs_per_s": w["B"] / (t * 1e-3), "cuda_graph": bool(use_graph), "steps": steps,
+                        "launches": count_launches(run)})
+            del gs, body, head, opt, devb
+            graph.clear_cache()
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out.append({"config": name, "error": repr(ex)[:300]})
     return out
 
 

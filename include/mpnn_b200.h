@@ -168,11 +168,11 @@ int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg,
                        long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
                        float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
                        mpnn_stream_t stream);
-/* mpnn_tc_dense_gemm with a 64-bit offset (floats, multiple of 4) between the G output blocks: they may be different
- * buffers (the GRU backward writes dm and dh = its two blocks) */
+/* mpnn_tc_dense_gemm with a 64-bit offset (floats, multiple of 4) between output blocks that may be different buffers
+ * (the GRU backward writes dm and dh): the G blocks, or -- nsplit > 0, G = 1 -- every nsplit columns of one product */
 int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
                           long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
-                          float* Y, int ldy, long long ycol, int accumulate, int DP, void* workspace,
+                          float* Y, int ldy, long long ycol, int nsplit, int accumulate, int DP, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream);
 /* GRU weight gradients for widths <= 64 in ONE pass over the gate gradients (gru_update.py:27-28 backward):
  * dW_ih [d,3d] = m^T (dar|daz|dan), dW_hh [d,3d] = h^T (dar|daz|dnh); dg [rows, ldg] holds the blocks dar|daz|dan|dnh. */

@@ -31,8 +31,8 @@ extern "C" int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, in
 
 extern "C" int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
                                      long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N,
-                                     const float* bias, float* Y, int ldy, long long ycol, int accumulate, int DP,
-                                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                                     const float* bias, float* Y, int ldy, long long ycol, int nsplit, int accumulate,
+                                     int DP, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_tc_gru_param_workspace_bytes(void);
 extern "C" int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
                                       float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes,
@@ -172,40 +172,52 @@ __global__ void __launch_bounds__(256) k_gru_point_bwd5(const float* __restrict_
   }
 }
 
-// db_ih = (sum dar | sum daz | sum dan), db_hh = (sum dar | sum daz | sum dnh) over the per-CTA partials, fixed order
+// db_ih = (sum dar | sum daz | sum dan), db_hh = (sum dar | sum daz | sum dnh) over the per-CTA partials, fixed order:
+// a block is 32 columns x 8 slices of the partials (slice sums in registers, then a fixed-order sum of the 8 slices)
 __global__ void __launch_bounds__(256) k_gru_bias_final(const float* __restrict__ part, int n_part, int d,
                                                         float* __restrict__ db_ih, float* __restrict__ db_hh) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= 4 * d) return;
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
   float s = 0.f;
-  int i = 0;
-  for (; i + 4 <= n_part; i += 4) {
-    const float v0 = part[(size_t)i * 4 * d + j], v1 = part[(size_t)(i + 1) * 4 * d + j],
-                v2 = part[(size_t)(i + 2) * 4 * d + j], v3 = part[(size_t)(i + 3) * 4 * d + j];
-    s += v0;
-    s += v1;
-    s += v2;
-    s += v3;
+  if (j < 4 * d) {
+    int i = sl;
+    for (; i + 24 < n_part; i += 32) {
+      const float v0 = part[(size_t)i * 4 * d + j], v1 = part[(size_t)(i + 8) * 4 * d + j],
+                  v2 = part[(size_t)(i + 16) * 4 * d + j], v3 = part[(size_t)(i + 24) * 4 * d + j];
+      s += v0;
+      s += v1;
+      s += v2;
+      s += v3;
+    }
+    for (; i < n_part; i += 8) s += part[(size_t)i * 4 * d + j];
   }
-  for (; i < n_part; ++i) s += part[(size_t)i * 4 * d + j];
-  const int b = j / d, c = j - b * d;
-  if (b < 2) {
-    db_ih[j] = s;
-    db_hh[j] = s;
-  } else if (b == 2) {
-    db_ih[j] = s;
-  } else {
-    db_hh[2 * d + c] = s;
+  red[sl][cx] = s;
+  __syncthreads();
+  if (sl == 0 && j < 4 * d) {
+    float t = red[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][cx];
+    const int b = j / d, c = j - b * d;
+    if (b < 2) {
+      db_ih[j] = t;
+      db_hh[j] = t;
+    } else if (b == 2) {
+      db_ih[j] = t;
+    } else {
+      db_hh[2 * d + c] = t;
+    }
   }
 }
 
-// Wc[g][s][n][k] (g: 0 = dm, 1 = dh; s: the six blocks of dg): the B matrices of the data product
+// Wc[s][g*d + n][k] (g: 0 = dm, 1 = dh; s: the six blocks of dg): the B matrix of the data product, N = 2d
 //   dm = dar Wr_ih^T + daz Wz_ih^T + dan Wn_ih^T,   dh = dar Wr_hh^T + daz Wz_hh^T + dnh Wn_hh^T + (hi + lo) I
 __global__ void __launch_bounds__(256) k_gru_bwd_wcomb(const float* __restrict__ W_ih, const float* __restrict__ W_hh,
                                                        int d, float* __restrict__ Wc) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= 12 * d * d) return;
-  const int k = i % d, n = (i / d) % d, s = (i / (d * d)) % 6, g = i / (6 * d * d);
+  const int k = i % d, nn = (i / d) % (2 * d), s = i / (2 * d * d);   // [s][n of (dm | dh)][k]
+  const int g = nn / d, n = nn - g * d;
   float v = 0.f;
   if (g == 0) {
     if (s < 3) v = W_ih[(size_t)n * 3 * d + s * d + k];
@@ -504,7 +516,7 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
   size_t sub = g > c ? g : c;
   const int DP = d > 32 ? mpnn_tc_dp(d, d) : -1;   // widths 33..256: gate GEMMs on the tensor cores (tc_message.cu)
   if (DP > 0) {
-    size_t t = align_up(mpnn_tc_dense_workspace_bytes(12, DP), 256) + mpnn_tc_dense_grad_workspace_bytes(3, DP);
+    size_t t = align_up(mpnn_tc_dense_workspace_bytes(24, DP), 256) + mpnn_tc_dense_grad_workspace_bytes(3, DP);
     if (t > sub) sub = t;
     if (mpnn_tc_gru_param_workspace_bytes() > sub) sub = mpnn_tc_gru_param_workspace_bytes();
     // dg [rows, 6d] (= the two [rows, 3d] arrays of the fp32 path) + bias partials + the combined weights
@@ -640,14 +652,20 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
     size_t sub_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
     k_gru_point_bwd5<<<nblk, 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dg, bias_part);
     MPNN_CHECK_LAUNCH("k_gru_point_bwd5");
-    k_gru_bias_final<<<ceil_div(4 * d, 256), 256, 0, stream>>>(bias_part, nblk, d, db_ih, db_hh);
+    k_gru_bias_final<<<ceil_div(4 * d, 32), 256, 0, stream>>>(bias_part, nblk, d, db_ih, db_hh);
     MPNN_CHECK_LAUNCH("k_gru_bias_final");
     k_gru_bwd_wcomb<<<ceil_div(12 * d * d, 256), 256, 0, stream>>>(W_ih, W_hh, d, Wc);
     MPNN_CHECK_LAUNCH("k_gru_bwd_wcomb");
     int rc;
-    if ((rc = mpnn_tc_dense_gemm_ll(dg, rows, 6 * d, d, 6, d, Wc, d, 1, (long long)6 * d * d, (long long)d * d, 2, d, nullptr,
-                                    dm, d, (long long)(dh - dm), 0, DP, sub, sub_bytes, stream)))
-      return rc;
+    if (2 * d <= 256) {   // one N = 2d product, columns [0, d) -> dm, [d, 2d) -> dh: the gate gradients are read once
+      const int DP2 = 2 * d <= 64 ? 64 : 2 * d <= 128 ? 128 : 256;
+      rc = mpnn_tc_dense_gemm_ll(dg, rows, 6 * d, d, 6, d, Wc, d, 1, 0, (long long)2 * d * d, 1, 2 * d, nullptr, dm, d,
+                                 (long long)(dh - dm), d, 0, DP2, sub, sub_bytes, stream);
+    } else {              // two output groups
+      rc = mpnn_tc_dense_gemm_ll(dg, rows, 6 * d, d, 6, d, Wc, d, 1, (long long)d * d, (long long)2 * d * d, 2, d, nullptr,
+                                 dm, d, (long long)(dh - dm), 0, 0, DP, sub, sub_bytes, stream);
+    }
+    if (rc) return rc;
     if (d <= 64) return mpnn_tc_gru_param_grad(m, h, dg, 6 * d, rows, d, dW_ih, dW_hh, sub, sub_bytes, stream);
     if ((rc = mpnn_tc_dense_gemm_tn(m, rows, d, d, dg, 6 * d, d, 3, d, DP, dW_ih, d, 3 * d, sub, sub_bytes, stream))) return rc;
     if ((rc = mpnn_tc_dense_gemm_tn(h, rows, d, d, dg, 6 * d, d, 2, d, DP, dW_hh, d, 3 * d, sub, sub_bytes, stream))) return rc;

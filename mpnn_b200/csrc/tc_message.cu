@@ -270,6 +270,7 @@ struct TcGemm {
   int acol;
   long long ycol;       // output offset (floats) between N-blocks
   int accumulate;       // Y += result
+  int nsplit;           // > 0: output columns [j*nsplit, (j+1)*nsplit) go to buffer j (Y + j*ycol), G must be 1
   const float* bias;    // [G*N] or null
 };
 
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
   constexpr int NKB = DP / KB;
+  const int nkbu = (a.K + KB - 1) / KB;   // K-blocks that hold data (K < DP: the all-zero ones are skipped)
 
   if (warp < 4) {
     // ===================== producers =====================
@@ -365,8 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) rows[i] = rows_next[i];
       load_rows(t + 1, rows_next);
-      for (int sk = 0; sk < a.kseg * NKB; ++sk) {
-        const int seg = sk / NKB, kb = sk - seg * NKB;
+      for (int sk = 0, seg = 0, kb = 0; sk < a.kseg * nkbu; ++sk, kb = (kb + 1 == nkbu ? 0 : kb + 1), seg += (kb == 0)) {
         const float* bimg = a.Bimg + (size_t)(u * a.kseg + seg) * NKB * (DP * KB);
         const int kk = kb * KB + chunk * 4;
         const int acol = seg * a.acol + kk;
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
         mbar_wait(accempty_bar(acc), (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(acc * DP);
-        for (int kb = 0; kb < a.kseg * NKB; ++kb) {
+        for (int kb = 0; kb < a.kseg * nkbu; ++kb) {
           mbar_wait(full_bar(stage), phase);
           fence_proxy_async();   // cp.async wrote through the generic proxy; the MMA reads through the async proxy
           tc_fence_after();
@@ -455,7 +456,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_edge_gemm(TcGemm a) {
           for (int it = 0; it < 8; ++it) {
             const float* p = tb + (it * 4 + orow) * 33 + ocol;
             if (erow[it] >= 0) {
-              float4* y = reinterpret_cast<float4*>(a.Y + (size_t)erow[it] * a.ldy + ybase + c0 + ocol);
+              const int cc = c0 + ocol;
+              const long long yoff = a.nsplit > 0 ? (long long)(cc / a.nsplit) * a.ycol + (cc % a.nsplit) : ybase + cc;
+              float4* y = reinterpret_cast<float4*>(a.Y + (size_t)erow[it] * a.ldy + yoff);
               float4 o = make_float4(p[0] + bv.x, p[1] + bv.y, p[2] + bv.z, p[3] + bv.w);
               if (a.accumulate) {
                 const float4 old = *y;
@@ -1424,6 +1427,7 @@ int mpnn_tc_edge_gemm(const void* plan, int edge_capacity, int unique_capacity, 
   a.acol = 0;
   a.ycol = 0;
   a.accumulate = 0;
+  a.nsplit = 0;
   a.bias = nullptr;
   const int grid = tc_grid();
   switch (DP) {
@@ -1503,7 +1507,7 @@ size_t mpnn_tc_dense_workspace_bytes(int n_blocks, int DP) { return (size_t)n_bl
 
 int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
                           long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
-                          float* Y, int ldy, long long ycol, int accumulate, int DP, void* workspace,
+                          float* Y, int ldy, long long ycol, int nsplit, int accumulate, int DP, void* workspace,
                           size_t workspace_bytes, cudaStream_t stream);
 
 // Y[r, g*ycol + n] (+)= sum_{s < kseg} sum_{k < K} A[r, s*acol + k] * W[n*w_sn + k*w_sk + g*w_sg + s*w_ss] + bias[g*N + n]
@@ -1513,14 +1517,16 @@ int mpnn_tc_dense_gemm(const float* A, long long rows, int lda, int K, int kseg,
                        float* Y, int ldy, int ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
                        cudaStream_t stream) {
   return mpnn_tc_dense_gemm_ll(A, rows, lda, K, kseg, acol, W, w_sn, w_sk, w_sg, w_ss, G, N, bias, Y, ldy, (long long)ycol,
-                          accumulate, DP, workspace, workspace_bytes, stream);
+                               0, accumulate, DP, workspace, workspace_bytes, stream);
 }
 
-// the same with a 64-bit offset between the G output blocks (they may be different buffers: mpnn_gru_bwd's dm / dh)
+// the same with a 64-bit offset between output blocks that may be different buffers (mpnn_gru_bwd's dm / dh): either
+// the G blocks, or -- nsplit > 0, G = 1 -- every nsplit columns of the one N-wide product
 int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int kseg, int acol, const float* W,
-                     long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
-                     float* Y, int ldy, long long ycol, int accumulate, int DP, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+                          long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N, const float* bias,
+                          float* Y, int ldy, long long ycol, int nsplit, int accumulate, int DP, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(nsplit == 0 || (G == 1 && nsplit > 0 && (nsplit & 3) == 0), MPNN_ERR_ARG, "tc_dense_gemm: bad nsplit");
   MPNN_REQUIRE(A && W && Y && workspace && rows > 0 && G > 0 && kseg > 0, MPNN_ERR_ARG, "tc_dense_gemm: bad argument");
   MPNN_REQUIRE(DP == 64 || DP == 128 || DP == 256, MPNN_ERR_UNSUPPORTED, "tc_dense_gemm: DP must be 64, 128 or 256");
   MPNN_REQUIRE((K & 3) == 0 && (N & 3) == 0 && (lda & 3) == 0 && (ldy & 3) == 0 && (acol & 3) == 0 && (ycol & 3) == 0 &&
@@ -1553,6 +1559,7 @@ int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int ks
   a.acol = acol;
   a.ycol = ycol;
   a.accumulate = accumulate;
+  a.nsplit = nsplit;
   a.bias = bias;
   const long long tiles = ((rows + TILE - 1) / TILE) * G;
   const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
