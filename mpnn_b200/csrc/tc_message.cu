@@ -577,6 +577,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
     // ===================== producers =====================
     const int sub = tid >> 3, chunk = tid & 7;   // sub: 0..15 -> edges sub, sub+16, ... of the stage
     int stage = 0, phase = 0;
+    if (unit_alpha) {
+      // 32-column blocks of the A operand that lie entirely behind nf (a 64-wide table in the M = 128 operand) are never
+      // written again: clear them in every stage once instead of zero-filling them with cp.async per stage
+      for (int st = 0; st < C::NSTAGE; ++st)
+        for (int mb = 0; mb < C::MP / 32; ++mb)
+          if (mb * 32 >= a.nf)
+            for (int i = tid; i < C::KST * 8; i += PRODUCERS)
+              sts4(smem + st * C::STAGE, (uint32_t)mb * C::LBO + (uint32_t)i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+      fence_proxy_async();
+    }
     for (int t = t0; t < t1; ++t) {
       int u_, pos, cnt;
       grad_tile(a, t, u_, pos, cnt);
@@ -602,7 +612,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
         const uint32_t Bs = As + C::A_BYTES;
         if (unit_alpha) {
 #pragma unroll
-          for (int mb = 0; mb < C::MP / 32; ++mb)
+          for (int mb = 0; mb < C::MP / 32; ++mb) {
+            if (mb * 32 >= a.nf) continue;   // padding columns of the M = 128 operand: zeroed once, below
 #pragma unroll
             for (int h = 0; h < C::EPT; ++h) {
               const int r = sub + 16 * h, col = mb * 32 + chunk * 4;
@@ -610,6 +621,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_table_grad(TcGrad a) {
               cp_async16(As + (uint32_t)mb * C::LBO + (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk),
                          ok ? hrow[h] + col : a.H, ok ? 16u : 0u);
             }
+          }
 #pragma unroll
           for (int nb = 0; nb < DP / 32; ++nb)
 #pragma unroll
