@@ -66,19 +66,30 @@ class FlatGradAllReduce(object):
     def __call__(self, average=True):
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return
-        ps = [p for p in self.params if p.grad is not None]
+        # the bucket layout is the list of parameters that REQUIRE a gradient -- the same on every rank whatever
+        # happened to receive one in this step; a parameter without a gradient contributes zeros (and keeps None if no
+        # rank had one: its slice of the sum is then zero and is not written back)
+        ps = self.params
         if not ps:
             return
-        n = sum(p.grad.numel() for p in ps)
-        if self._flat is None or self._flat.numel() != n or self._flat.device != ps[0].grad.device:
-            self._flat = torch.empty(n, dtype=torch.float32, device=ps[0].grad.device)
+        dev = ps[0].device
+        n = sum(p.numel() for p in ps)
+        if self._flat is None or self._flat.numel() != n or self._flat.device != dev:
+            self._flat = torch.empty(n, dtype=torch.float32, device=dev)
         views, o = [], 0
         for p in ps:
-            v = self._flat[o:o + p.grad.numel()].view_as(p.grad)
-            views.append(v)
-            o += p.grad.numel()
-        torch._foreach_copy_(views, [p.grad for p in ps])
+            views.append(self._flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+        have = [i for i, p in enumerate(ps) if p.grad is not None]
+        if len(have) != len(ps):
+            self._flat.zero_()
+        if have:
+            torch._foreach_copy_([views[i] for i in have], [ps[i].grad for i in have])
         dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
         if average:
             self._flat.div_(dist.get_world_size())
-        torch._foreach_copy_([p.grad for p in ps], views)
+        if have:
+            torch._foreach_copy_([ps[i].grad for i in have], [views[i] for i in have])
+        for i, p in enumerate(ps):
+            if p.grad is None and len(have) != len(ps):
+                p.grad = views[i].clone()    # another rank may have produced this gradient: take the averaged sum

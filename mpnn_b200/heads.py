@@ -5,7 +5,7 @@
 
 `BNLinearMSE(bn, linear)` wraps the driver's OWN stock modules (same parameters, buffers and state_dict entries) and
 returns `mse_loss(linear(bn(x)), target)`; the predictions of the last call are kept in `.prediction`.  Problems that
-do not fit one CTA's shared memory (`mpnn_head_supported`) run the stock modules.
+do not fit one CTA's shared memory (`mpnn_head_supported`) raise: the caller keeps its stock modules for those.
 """
 import torch
 from torch import nn
@@ -74,9 +74,10 @@ class BNLinearMSE(nn.Module):
         lib = _lib.load()
         if (not lib.mpnn_head_supported(B, C, T) or bn.momentum is None or target.shape != (B, T)
                 or (training and B < 2)):
-            y = lin(bn(x))                      # stock modules: larger than one CTA (or cumulative-average momentum)
-            self.prediction = y.detach()
-            return torch.nn.functional.mse_loss(y, target)
+            # no silent dispatch to another implementation: the caller keeps its stock modules for such a head
+            raise RuntimeError("mpnn_b200.heads.BNLinearMSE: B=%d, C=%d, T=%d%s is not served by the fused head kernel "
+                               "(mpnn_head_supported); use the stock BatchNorm1d / Linear / mse_loss modules for it"
+                               % (B, C, T, ", momentum=None" if bn.momentum is None else ""))
         tracked = bn.track_running_stats
         loss, y = _BNLinearMSEFn.apply(x, target, bn.weight if bn.affine else None, bn.bias if bn.affine else None,
                                        lin.weight, lin.bias, bn.running_mean if tracked else None,

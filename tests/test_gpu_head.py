@@ -59,7 +59,7 @@ def test_fused_head_matches_stock_modules(dev, B, C, T, mode):
         assert rel_err(q.float(), p.float()) <= 1e-5, k
 
 
-def test_fused_head_reproducible_and_falls_back_to_stock(dev):
+def test_fused_head_reproducible_and_refuses_unserved_shapes(dev):
     from mpnn_b200.heads import BNLinearMSE
     torch.manual_seed(0)
     bn, lin = nn.BatchNorm1d(64).to(dev), nn.Linear(64, 12).to(dev)
@@ -72,9 +72,9 @@ def test_fused_head_reproducible_and_falls_back_to_stock(dev):
         fused(xi, t).backward()
         outs.append((xi.grad.clone(), lin.weight.grad.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    # larger than one CTA's shared memory: the stock modules run (same modules, same result contract)
+    # larger than the kernel serves: an error, never a silent switch to another implementation
     xb, tb = torch.randn(8192, 64, device=dev), torch.randn(8192, 12, device=dev)
-    ref = torch.nn.functional.mse_loss(lin(bn(xb)), tb)
-    assert rel_err(fused(xb, tb), ref) <= 1e-4
+    with pytest.raises(RuntimeError):
+        fused(xb, tb)
     with pytest.raises(RuntimeError):
         fused(x.cpu(), t.cpu())

@@ -214,6 +214,36 @@ def test_flat_gradient_allreduce_gloo_world2(tmp_path):
         assert torch.allclose(g, p.grad, rtol=1e-6, atol=1e-6)
 
 
+def _dp_uneven_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from mpnn_b200.dist import FlatGradAllReduce
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(3, 2), torch.nn.Linear(3, 2)
+    x = torch.arange(12.0).view(4, 3)[rank * 2:(rank + 1) * 2]
+    # rank 1 never touches `b`: its gradients are None there, the bucket layout must not depend on that
+    (a(x).pow(2).sum() + (b(x).sum() if rank == 0 else 0.0)).backward()
+    FlatGradAllReduce(list(a.parameters()) + list(b.parameters()))(average=False)
+    torch.save([p.grad.clone() for p in list(a.parameters()) + list(b.parameters())], out + str(rank))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_uneven_none_pattern(tmp_path):
+    """ranks with different `grad is None` patterns reduce the same layout"""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_dp_uneven_worker, args=(2, 29811 + os.getpid() % 200, out), nprocs=2, join=True)
+    g0, g1 = torch.load(out + "0"), torch.load(out + "1")
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(3, 2), torch.nn.Linear(3, 2)
+    x = torch.arange(12.0).view(4, 3)
+    (a(x).pow(2).sum() + b(x[:2]).sum()).backward()
+    want = [p.grad for p in list(a.parameters()) + list(b.parameters())]
+    for u, v, w in zip(g0, g1, want):
+        assert torch.allclose(u, w, rtol=1e-6, atol=1e-6) and torch.allclose(v, w, rtol=1e-6, atol=1e-6)
+
+
 def test_ragged_batch_matches_host_collate():
     """loader.RaggedBatch: the ragged form carries exactly the non-zero content of the padded
     batch that `collate_2d_graphs` (reference data_loader.py:50-70) builds, in row-major (b, i, j) order."""
