@@ -191,6 +191,10 @@ size_t mpnn_tc_gru_workspace_bytes(int d);
 int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
                     const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
                     void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+int mpnn_tc_gru_fwd_agg(const float* Y, const int* row_ptr, const float* m, const float* h, const float* mask,
+                        const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, long long rows,
+                        int d, float* m_out, float* h_out, float* gates, void* workspace, size_t workspace_bytes,
+                        mpnn_stream_t stream);
 
 /* nn.Linear-shaped wrappers (W [N, K] row-major; K, N multiples of 4 up to 1024, cut into blocks of <= 256) */
 int mpnn_tc_linear_supported(int K, int N);
@@ -257,6 +261,13 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d);
 int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
                  const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
                  void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* GRU forward with the aggregation (adjacent_message_agg.py:18) folded into the kernel's operand producer, tensor-core
+ * widths only: message row i = sum of Y[row_ptr[i] : row_ptr[i+1], :] (per-edge messages in CSR order, summed in edge
+ * order); the sums are also written to m_out [rows, d], which mpnn_gru_bwd reads as `m`. */
+int mpnn_gru_agg_supported(int d);
+int mpnn_gru_fwd_agg(const float* Y, const int* row_ptr, const float* h, const float* mask, const float* W_ih,
+                     const float* W_hh, const float* b_ih, const float* b_hh, long long rows, int d, float* m_out,
+                     float* h_out, float* gates, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
                  const float* gates, const float* dh_out, long long rows, int d, float* dm, float* dh, float* dW_ih,
                  float* dW_hh, float* db_ih, float* db_hh, void* workspace, size_t workspace_bytes,

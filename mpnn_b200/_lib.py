@@ -91,6 +91,9 @@ SIGNATURES = {
                               _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_gru_workspace_bytes": (_Z, [_L, _I]),
     "mpnn_gru_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _Z, _P]),
+    "mpnn_gru_agg_supported": (_I, [_I]),
+    "mpnn_gru_fwd_agg": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_tc_gru_fwd_agg": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "mpnn_gru_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     "mpnn_gru_bwd_partial_bytes": (_Z, [_L, _I]),
     "mpnn_gru_bwd_data": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P]),

@@ -33,6 +33,10 @@ extern "C" int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, in
                                      long long w_sn, long long w_sk, long long w_sg, long long w_ss, int G, int N,
                                      const float* bias, float* Y, int ldy, long long ycol, int nsplit, int accumulate,
                                      int DP, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+extern "C" int mpnn_tc_gru_fwd_agg(const float* Y, const int* row_ptr, const float* m, const float* h, const float* mask,
+                                   const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
+                                   long long rows, int d, float* m_out, float* h_out, float* gates, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_tc_gru_param_workspace_bytes(void);
 extern "C" int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
                                       float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes,
@@ -574,6 +578,20 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
   k_gru_point_fwd<<<ceil_div(rows * d, 256), 256, 0, stream>>>(gi, gh, h, mask, rows, d, h_out, gates);
   MPNN_CHECK_LAUNCH("k_gru_point_fwd");
   return MPNN_OK;
+}
+
+// GRU forward with the message aggregation folded in (tensor-core widths only, mpnn_gru_agg_supported): the messages
+// are sum_{e in [row_ptr[i], row_ptr[i+1])} Y[e, :]; they are written to m_out [rows, d] as well (saved for backward).
+int mpnn_gru_agg_supported(int d) { return mpnn_tc_gru_supported(d); }
+
+int mpnn_gru_fwd_agg(const float* Y, const int* row_ptr, const float* h, const float* mask, const float* W_ih,
+                     const float* W_hh, const float* b_ih, const float* b_hh, long long rows, int d, float* m_out,
+                     float* h_out, float* gates, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(rows > 0 && d > 0 && rows < (1ll << 31), MPNN_ERR_ARG, "gru_fwd_agg: bad dims");
+  MPNN_REQUIRE(mpnn_tc_gru_supported(d), MPNN_ERR_UNSUPPORTED, "gru_fwd_agg: width %d not served", d);
+  MPNN_REQUIRE(workspace_bytes >= mpnn_gru_workspace_bytes(rows, d), MPNN_ERR_WORKSPACE, "gru_fwd_agg: workspace");
+  return mpnn_tc_gru_fwd_agg(Y, row_ptr, nullptr, h, mask, W_ih, W_hh, b_ih, b_hh, rows, d, m_out, h_out, gates,
+                             workspace, workspace_bytes, stream);
 }
 
 // ---- shared-parameter form: the reference applies ONE GRUCell at every message-passing step (basic_model.py:50-58),

@@ -802,6 +802,12 @@ struct TcGru {
   long long rows;
   int d;
   int ncb;             // output-column blocks of DP (d = 256: two blocks of 128, the A tiles are read once per block)
+  // aggregation folded into the A-tile producer (adjacent_message_agg.py:18): when Y is given, row i of the message
+  // operand is sum_{e in [row_ptr[i], row_ptr[i+1])} Y[e, :] (the per-edge messages of the grouped GEMM, CSR order),
+  // summed in edge order while staging; m is ignored and m_out (if given) receives the sums for the backward
+  const float* Y;      // [E, d]
+  const int* row_ptr;  // [rows + 1]
+  float* m_out;        // [rows, d]
 };
 
 // MUFU.TANH (max relative error 2^-11, the same order as the TF32 operands feeding it): the gate arithmetic of the
@@ -901,12 +907,72 @@ __global__ void __launch_bounds__(GruCfg<DP, KP>::GRU_THREADS, 1) k_tc_gru_fwd(T
         const int seg = sk / NKB, kb = sk - seg * NKB;
         const float* A = seg == 0 ? a.m : a.h;
         const int kk = kb * KB + chunk * 4;
+        // the CSR ranges of this thread's eight rows: loaded before the wait for the stage (two dependent round trips)
+        int e0[8], e1[8];
+        const bool agg = seg == 0 && a.Y != nullptr;
+        if (agg) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long row = pos + i * 16 + sub;
+            const bool ok = row < a.rows && kk < d;
+            e0[i] = ok ? __ldg(a.row_ptr + row) : 0;
+            e1[i] = ok ? __ldg(a.row_ptr + row + 1) : 0;
+          }
+        }
         mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t As = smem_base + stage * C::STAGE;
         if (tid == 0) {
           mbar_arrive_expect_tx(full_bar(stage), C::B_BYTES);
           bulk_copy(As + C::A_BYTES, a.Bimg + (size_t)((cb * 2 + seg) * NKB + kb) * 3 * (DP * KB), C::B_BYTES,
                     full_bar(stage));
+        }
+        if (agg) {
+          uint8_t* Ag = smem + stage * C::STAGE;
+          // four rows at a time, the first four edges of each with all 16 loads in flight (molecular graphs: degree <= 4;
+          // a sequential loop per row costs one DRAM latency per ROW); absent edges add +0, the order stays e ascending
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 y[4][4];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+              const int i = half * 4 + ii;
+              const float* yb = a.Y + (size_t)e0[i] * d + kk;
+              const int ne = e1[i] - e0[i];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                y[ii][j] = j < ne ? ldg4(yb + j * d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+              const int i = half * 4 + ii;
+              const long long row = pos + i * 16 + sub;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc.x += y[ii][j].x;
+                acc.y += y[ii][j].y;
+                acc.z += y[ii][j].z;
+                acc.w += y[ii][j].w;
+              }
+              for (int e = e0[i] + 4; e < e1[i]; ++e) {
+                const float4 z = ldg4(a.Y + (size_t)e * d + kk);
+                acc.x += z.x;
+                acc.y += z.y;
+                acc.z += z.z;
+                acc.w += z.w;
+              }
+              sts4(Ag, swz(i * 16 + sub, chunk), acc);
+              if (a.m_out && cb == 0 && row < a.rows && kk < d)
+                *reinterpret_cast<float4*>(a.m_out + (size_t)row * d + kk) = acc;
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(full_bar(stage));
+          if (++stage == C::NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -1770,10 +1836,27 @@ size_t mpnn_tc_gru_workspace_bytes(int d) {
   return (size_t)ncb * 2 * 3 * DP * KP * sizeof(float);
 }
 
+int mpnn_tc_gru_fwd_agg(const float* Y, const int* row_ptr, const float* m, const float* h, const float* mask,
+                        const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, long long rows,
+                        int d, float* m_out, float* h_out, float* gates, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream);
+
 // h_out [rows, d], gates [rows, 4d] (sigmoid r | sigmoid z | tanh n | nh: what mpnn_gru_bwd reads)
 int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
                     const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return mpnn_tc_gru_fwd_agg(nullptr, nullptr, m, h, mask, W_ih, W_hh, b_ih, b_hh, rows, d, nullptr, h_out, gates,
+                             workspace, workspace_bytes, stream);
+}
+
+// The same with the aggregation folded in (Y, row_ptr non-NULL): message row i = sum of Y[row_ptr[i] : row_ptr[i+1]]
+// in edge order (the fixed-order CSR sum of mpnn_segment_sum), computed by the A-tile producer while staging; the sums
+// are also written to m_out [rows, d] (what the backward reads as `m`).
+int mpnn_tc_gru_fwd_agg(const float* Y, const int* row_ptr, const float* m, const float* h, const float* mask,
+                        const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, long long rows,
+                        int d, float* m_out, float* h_out, float* gates, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
+  MPNN_REQUIRE((Y != nullptr) == (row_ptr != nullptr) && (Y || m), MPNN_ERR_ARG, "tc_gru_fwd: message operand missing");
   MPNN_REQUIRE(mpnn_tc_gru_supported(d), MPNN_ERR_UNSUPPORTED, "tc_gru_fwd: width %d not served", d);
   MPNN_REQUIRE(rows > 0 && rows < (1ll << 30), MPNN_ERR_ARG, "tc_gru_fwd: bad row count");
   MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_workspace_bytes(d), MPNN_ERR_WORKSPACE, "tc_gru_fwd: workspace too small");
@@ -1782,7 +1865,7 @@ int mpnn_tc_gru_fwd(const float* m, const float* h, const float* mask, const flo
   float* img = (float*)workspace;
   k_tc_gru_pack<<<ceil_div((long long)ncb * 6 * DP * KP, 256), 256, 0, stream>>>(W_ih, W_hh, d, DP, KP, ncb, img);
   MPNN_CHECK_LAUNCH("k_tc_gru_pack");
-  TcGru a = {m, h, mask, img, b_ih, b_hh, h_out, gates, rows, d, ncb};
+  TcGru a = {m, h, mask, img, b_ih, b_hh, h_out, gates, rows, d, ncb, Y, row_ptr, m_out};
   const long long tiles = ((rows + TILE - 1) / TILE) * ncb;
   const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
   if (KP == 64) {

@@ -457,8 +457,18 @@ class GRUFn(torch.autograd.Function):
         out = torch.empty_like(h)
         gates = torch.empty(rows, 4 * d, dtype=torch.float32, device=h.device)
         ws = workspace(lib.mpnn_gru_workspace_bytes(rows, d), h.device)
-        check(lib.mpnn_gru_fwd(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), rows, d, ptr(out),
-                               ptr(gates), ptr(ws), ws.numel(), stream()), "gru_fwd")
+        pend = getattr(m, "_mpnn_pending_sum", None)
+        if pend is not None:
+            # TypedMessageTCFn left the aggregation to this kernel: its operand producer sums the per-edge messages of
+            # every row while staging and writes the sums into m (saved for the backward below)
+            del m._mpnn_pending_sum
+            Y, row_ptr = pend
+            check(lib.mpnn_gru_fwd_agg(ptr(Y), ptr(row_ptr), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(b_ih),
+                                       ptr(b_hh), rows, d, ptr(m), ptr(out), ptr(gates), ptr(ws), ws.numel(), stream()),
+                  "gru_fwd_agg")
+        else:
+            check(lib.mpnn_gru_fwd(ptr(m), ptr(h), ptr(mask), ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), rows, d,
+                                   ptr(out), ptr(gates), ptr(ws), ws.numel(), stream()), "gru_fwd")
         ctx.save_for_backward(m, h, mask, W_ih, W_hh, gates)
         return out
 
@@ -1491,7 +1501,9 @@ class TypedMessageTCFn(torch.autograd.Function):
     The HEAD-form extras (edge_network.py:50-51) are composed around this op in modules.EdgeNetwork."""
 
     @staticmethod
-    def forward(ctx, H, table, tableT, el, weighted, nf, mf):
+    def forward(ctx, H, table, tableT, el, weighted, nf, mf, defer_sum=False):
+        """defer_sum: the caller hands M straight to GRUFn (modules._wide_chain), whose tensor-core kernel does the CSR sum
+        in its operand producer and fills M; M is NOT valid before that call."""
         lib = _lib.load()
         _need_cuda(H, table)
         H, table, tableT = f32c(H), f32c(table), f32c(tableT)
@@ -1504,8 +1516,11 @@ class TypedMessageTCFn(torch.autograd.Function):
         check(lib.mpnn_tc_edge_gemm(ptr(plan), el.Ecap, ti.Ucap, ptr(ti.type_eid), 0, ptr(H), nf, nf, ptr(tableT), DP,
                                     1 if weighted else 0, ptr(Y), mf, mf, ptr(ws), ws.numel(), stream()), "tc_edge_gemm")
         M = torch.empty(el.n_rows, mf, dtype=torch.float32, device=dev)
-        check(lib.mpnn_segment_sum(ptr(Y), ptr(el.row_ptr), None, el.n_rows, mf, mf, ptr(M), mf, 0, 1.0, stream()),
-              "segment_sum")
+        if defer_sum and lib.mpnn_gru_agg_supported(mf):
+            M._mpnn_pending_sum = (Y, el.row_ptr)
+        else:
+            check(lib.mpnn_segment_sum(ptr(Y), ptr(el.row_ptr), None, el.n_rows, mf, mf, ptr(M), mf, 0, 1.0, stream()),
+                  "segment_sum")
         ctx.save_for_backward(H, table)
         ctx.meta = (el, nf, mf, DP, bool(weighted))
         return M
@@ -1535,4 +1550,4 @@ class TypedMessageTCFn(torch.autograd.Function):
             ws = workspace(lib.mpnn_tc_table_grad_workspace_bytes(ti.Ucap, DP), dev)
             check(lib.mpnn_tc_table_grad(ptr(plan), el.Ecap, ti.Ucap, ptr(H), nf, ptr(dM), mf, DP, 1 if weighted else 0,
                                          ptr(dT), ptr(ws), ws.numel(), stream()), "tc_table_grad")
-        return dH, dT, None, None, None, None, None
+        return dH, dT, None, None, None, None, None, None

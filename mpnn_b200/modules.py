@@ -686,6 +686,7 @@ def _tables_for_steps(msgs, el):
         n._msg_cache = {}
 
 
+AGG_IN_GRU = os.environ.get("MPNN_B200_AGG_IN_GRU", "1") != "0"
 WIDE_COMPACT = os.environ.get("MPNN_B200_WIDE_COMPACT", "1") != "0"
 
 
@@ -763,7 +764,8 @@ def _wide_chain(steps, base, afm, mask, el, uf, d):
     for gru, bn in steps:
         msg = gru._src._messages
         table, tableT = msg._net._table(el, True)
-        M = TypedMessageTCFn.apply(afm_c, table, tableT, elc, True, d, d)
+        # (the CSR sum of the per-edge messages is left to the GRU kernel's operand producer: M is filled there)
+        M = TypedMessageTCFn.apply(afm_c, table, tableT, elc, True, d, d, AGG_IN_GRU)
         h = uf.gru_cell(M, h, mask_c)
         if bn is not None:
             if isinstance(bn._module, MaskBatchNorm1d):

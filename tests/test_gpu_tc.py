@@ -294,3 +294,35 @@ def test_wide_chain_on_real_rows_equals_padded_evaluation(dev, variant, d, T, mo
     scale = max(float(v.abs().max()) for v in g0.values())
     for k in g0:
         assert float((g1[k] - g0[k]).abs().max()) <= 2e-4 * float(g0[k].abs().max()) + 1e-6 * scale, k
+
+
+@pytest.mark.parametrize("d,B", [(64, 40), (40, 12), (128, 16), (256, 6)])
+def test_aggregation_inside_gru_kernel_is_bit_identical(dev, d, B, monkeypatch):
+    """north star: aggregation fused with the GRU gates.  The CSR sum of the per-edge messages done by the fused GRU
+    kernel's operand producer (mpnn_gru_fwd_agg) == mpnn_segment_sum followed by the same kernel: same summation order,
+    so outputs, messages saved for the backward and every gradient are bit-identical"""
+    from mpnn_b200 import graph, modules as M, synthetic
+    from mpnn_b200.dropin import reference_model, kaiming_init
+    b = synthetic.make_batch("zinc", B=B, d=d)
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
+    torch.manual_seed(5)
+    mod = reference_model("normed", d, 8, d, 1, 2 * d, message_steps=2)
+    mod.apply(kaiming_init)
+    with torch.no_grad():
+        for net in mod.mfs:
+            net.edge_map[net._last_idx].weight.mul_(0.05)
+    mod = mod.to(dev).train()
+    res = []
+    for fused in (True, False):
+        monkeypatch.setattr(M, "AGG_IN_GRU", fused)
+        graph.clear_cache()
+        mod.zero_grad()
+        a = t["afm"].clone().requires_grad_(True)
+        out = mod(a, t["bfm"], t["adj"], t["mask"])
+        cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        (out * cot).sum().backward()
+        res.append((out.detach(), a.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}))
+    (o1, a1, g1), (o0, a0, g0) = res
+    assert torch.equal(o1, o0) and torch.equal(a1, a0)
+    for k in g0:
+        assert torch.equal(g1[k], g0[k]), k

@@ -24,7 +24,7 @@ Fn.SIDE_STREAM_ENABLED = False
 
 
 def step():
-    Mm = Fn.TypedMessageTCFn.apply(hc, tab, tabT, elc, True, h, h)
+    Mm = Fn.TypedMessageTCFn.apply(hc, tab, tabT, elc, True, h, h, os.environ.get("MPNN_B200_AGG_IN_GRU", "1") != "0")
     out = Fn.GRUFn.apply(Mm, hc, mc, ws[0], ws[1], ws[2], ws[3], None)
     torch.autograd.grad(out, ws + [tab], torch.ones_like(out))
 
