@@ -198,10 +198,11 @@ def workspace(nbytes, device):
 _CLEAN_WS = {}
 
 
-def clean_workspace(nbytes, device):
-    """Persistent zero-initialised workspace per (device, stream, size) for ops whose kernels leave their scratch
-    counters zero on exit (masked batch norms): no memset per call."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
+def clean_workspace(nbytes, device, family="bn"):
+    """Persistent zero-initialised workspace per (op family, device, stream, size) for ops whose kernels leave their
+    scratch counters / flags zero on exit (masked batch norms, the step kernels, the fused compaction): no memset per
+    call.  Families never share a buffer: their flag words live at different offsets."""
+    key = (family, device.index, torch.cuda.current_stream(device).cuda_stream, int(nbytes))
     ws = _CLEAN_WS.get(key)
     if ws is None:
         ws = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)

@@ -452,15 +452,18 @@ size_t mpnn_bn_workspace_bytes(long long rows, int C) {
          256;
 }
 
+// The counter sits at offset 0 for EVERY (rows, C): a workspace that is reused across shapes of the same byte size must
+// never present one shape's partial sums as another shape's counter (round 2: a batch norm on [rows, C] after one on a
+// different [rows', C'] of equal workspace size started with a non-zero counter and normalised with garbage).
 static void carve(void* workspace, long long rows, int C, float** partial, float** red, unsigned int** counter) {
   int rpb;
   int nblk = red_blocks(rows, &rpb);
   char* wp = (char*)workspace;
+  *counter = (unsigned int*)wp;
+  wp += 256;
   *partial = (float*)wp;
   wp += align_up((size_t)nblk * MAXQ * C * sizeof(float), 256);
   *red = (float*)wp;
-  wp += align_up((size_t)(MAXQ + 2) * C * sizeof(float), 256);
-  *counter = (unsigned int*)wp;
 }
 
 // stats: [2*C + 1] floats (mean, sqrt(var+eps), M) saved for backward

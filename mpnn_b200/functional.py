@@ -1349,7 +1349,7 @@ class ChainFn(torch.autograd.Function):
         saved = torch.empty(lib.mpnn_chain_saved_floats(rows, d, T), dtype=torch.float32, device=dev)
         if real[1] is not None:
             torch.cuda.current_stream(dev).wait_event(real[1])
-        ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev)
+        ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev, "chain")
         alpha = f32c(el.edge_w) if el.edge_w is not None else None
         args = (ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0), ptr(h_init),
                 ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), kinds, training, eps, mom,
@@ -1390,7 +1390,7 @@ class ChainFn(torch.autograd.Function):
         gptrs = []
         for t in range(T):
             gptrs += ([d_aff[aff_idx[t]], d_aff[aff_idx[t] + 1]] if aff_idx[t] >= 0 else [None, None])
-        ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev)
+        ws = _lib.clean_workspace(lib.mpnn_chain_workspace_bytes(rows, d, T), dev, "chain")
         check(lib.mpnn_chain_bwd(ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0),
                                  ptr(h_init), ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh),
                                  kinds, training, eps, mom, ptr_array(ptrs), rows, d, ptr(real_list), ptr(saved),

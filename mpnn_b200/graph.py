@@ -165,7 +165,7 @@ def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap):
     urows = torch.empty(Ucap + 1, ef, dtype=torch.float32, device=dev)
     from . import functional
     counts = functional.zeros((4,), torch.int32, dev)
-    ws = _lib.clean_workspace(lib.mpnn_prep_workspace_bytes(B, Ucap), dev)
+    ws = _lib.clean_workspace(lib.mpnn_prep_workspace_bytes(B, Ucap), dev, "prep")
     _lib.check(lib.mpnn_prep_edges(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, Ecap, Ucap, _lib.ptr(row_ptr),
                                    _lib.ptr(col_ptr), _lib.ptr(edge_src), _lib.ptr(edge_dst), _lib.ptr(edge_w),
                                    _lib.ptr(csc_eid), _lib.ptr(uid), _lib.ptr(urows), _lib.ptr(counts), _lib.ptr(ws),

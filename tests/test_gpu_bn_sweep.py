@@ -49,3 +49,31 @@ def test_mask_bn_shape_sweep(B, N, C, weighted):
     out2 = MaskBatchNorm()(xg2, mask.to(dev))
     (out2 * cot.to(dev)).sum().backward()
     assert torch.equal(out, out2) and torch.equal(xg.grad, xg2.grad)
+
+
+def test_workspace_reuse_across_shapes_of_equal_size():
+    """The batch norms reuse one persistent zeroed workspace per byte size.  Two shapes whose workspaces have the same
+    size but a different internal layout must not disturb each other (round 2: the completion counter of one layout lay
+    inside the partial sums of the other; the second batch norm then started from a non-zero counter and normalised with
+    garbage).  Every pair of shapes with equal workspace size is run back to back, both orders."""
+    from mpnn_b200 import _lib
+    from mpnn_b200.modules import MaskBatchNorm
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    shapes = [(r, c) for r in (96, 128, 250, 256, 300, 512, 1000, 1024, 2048) for c in (8, 16, 24, 32, 40, 48, 64, 80, 128)]
+    by_size = {}
+    for r, c in shapes:
+        by_size.setdefault(int(lib.mpnn_bn_workspace_bytes(r, c)), []).append((r, c))
+    pairs = [(a, b) for v in by_size.values() for a in v for b in v if a != b]
+    assert pairs, "no two shapes share a workspace size: widen the sweep"
+    g = torch.Generator().manual_seed(0)
+
+    def run(rows, C):
+        mask = (torch.rand(1, rows, 1, generator=g) > 0.3).float()
+        x = (torch.randn(1, rows, C, generator=g) * 3 + 1) * mask
+        out = MaskBatchNorm()(x.to(dev), mask.to(dev))
+        assert rel_err(out.cpu(), reference(x.double(), mask.double())) <= 2e-5, (rows, C)
+
+    for a, b in pairs[:40]:
+        run(*a)
+        run(*b)
