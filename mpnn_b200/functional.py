@@ -22,8 +22,9 @@ _SIDE_PENDING = {}
 SIDE_STREAM_ENABLED = os.environ.get("MPNN_B200_SIDE_STREAM", "1") != "0"
 # The backward's side lanes only pay inside a captured step (parallel branches of the CUDA graph, explicit event edges);
 # with eager launches the Python dispatch is the bottleneck and the lanes buy nothing, so they are off there by default.
-# (Round 2: with eager lanes + the ready-event shortcut the att_model's input gradient was wrong when other models had run
-# before it in the same process -- tests/test_gpu_parity.py config-shaped zinc; not root-caused, eager lanes switched off.)
+# (Round 2: an in-suite failure of the att_model's input gradient first blamed on the eager lanes was the batch-norm
+# workspace bug fixed in csrc/bn.cu `carve`; with MPNN_B200_SIDE_STREAM_EAGER=1 the eager att_model step still differs
+# from its captured replay in tests/test_gpu_chain.py, so the eager lanes stay off.)
 SIDE_STREAM_EAGER = os.environ.get("MPNN_B200_SIDE_STREAM_EAGER", "0") != "0"
 
 
