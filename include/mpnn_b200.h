@@ -179,6 +179,13 @@ int mpnn_tc_dense_gemm_ll(const float* A, long long rows, int lda, int K, int ks
 size_t mpnn_tc_gru_param_workspace_bytes(void);
 int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
                            float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* The same with the pointwise GRU backward folded in: reads the saved gates [rows, 4d], m, h, dh', mask once; writes
+ * dg [rows, 6d] (dar | daz | dan | dnh | hi(go z) | lo(go z), the operand of the data product), the bias partials
+ * [mpnn_tc_gru_param_bias_parts()][4d] and dW_ih, dW_hh. */
+int mpnn_tc_gru_param_bias_parts(void);
+int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, const float* gates, const float* dh_out,
+                            long long rows, int d, float* dg, float* bias_part, float* dW_ih, float* dW_hh,
+                            void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 size_t mpnn_tc_dense_grad_workspace_bytes(int G, int DP);
 int mpnn_tc_dense_gemm_tn(const float* X, long long rows, int ldx, int M, const float* D, int ldd, int dcol, int G,
                           int N, int DP, float* out, long long o_sg, long long o_sl, void* workspace,
@@ -261,6 +268,9 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d);
 int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float* W_ih, const float* W_hh,
                  const float* b_ih, const float* b_hh, long long rows, int d, float* h_out, float* gates,
                  void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* 1 (default): at widths 33..64 mpnn_gru_bwd runs the pointwise pass inside the weight-gradient kernel's producers
+ * (mpnn_tc_gru_param_point); 0: as a separate launch, like the wider tensor-core widths.  Returns the previous setting. */
+int mpnn_gru_bwd_one_pass(int enabled);
 /* GRU forward with the aggregation (adjacent_message_agg.py:18) folded into the kernel's operand producer, tensor-core
  * widths only: message row i = sum of Y[row_ptr[i] : row_ptr[i+1], :] (per-edge messages in CSR order, summed in edge
  * order); the sums are also written to m_out [rows, d], which mpnn_gru_bwd reads as `m`. */

@@ -38,11 +38,18 @@ extern "C" int mpnn_tc_gru_fwd_agg(const float* Y, const int* row_ptr, const flo
                                    long long rows, int d, float* m_out, float* h_out, float* gates, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_tc_gru_param_workspace_bytes(void);
+extern "C" int mpnn_tc_gru_param_bias_parts(void);
+extern "C" int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, const float* gates,
+                                       const float* dh_out, long long rows, int d, float* dg, float* bias_part,
+                                       float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes,
+                                       cudaStream_t stream);
 extern "C" int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
                                       float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes,
                                       cudaStream_t stream);
 
 namespace {
+int g_point_in_param = 1;   // mpnn_gru_bwd_one_pass: pointwise pass inside the weight-gradient kernel (widths <= 64)
+
 
 __global__ void k_gru_point_fwd(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ h,
                                 const float* __restrict__ mask, long long rows, int d, float* __restrict__ hout,
@@ -524,7 +531,7 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
     if (t > sub) sub = t;
     if (mpnn_tc_gru_param_workspace_bytes() > sub) sub = mpnn_tc_gru_param_workspace_bytes();
     // dg [rows, 6d] (= the two [rows, 3d] arrays of the fp32 path) + bias partials + the combined weights
-    pre += align_up((size_t)4 * mpnn_num_sms() * 4 * d * sizeof(float), 256) + align_up((size_t)12 * d * d * sizeof(float), 256);
+    pre += align_up((size_t)16 * mpnn_num_sms() * 4 * d * sizeof(float), 256) + align_up((size_t)12 * d * d * sizeof(float), 256);
   }
   size_t need = pre + align_up(sub, 256);
   const size_t tg = mpnn_tc_gru_workspace_bytes(d);
@@ -578,6 +585,14 @@ int mpnn_gru_fwd(const float* m, const float* h, const float* mask, const float*
   k_gru_point_fwd<<<ceil_div(rows * d, 256), 256, 0, stream>>>(gi, gh, h, mask, rows, d, h_out, gates);
   MPNN_CHECK_LAUNCH("k_gru_point_fwd");
   return MPNN_OK;
+}
+
+// 1 (default): at widths 33..64 the pointwise GRU backward runs inside the weight-gradient kernel's producers; 0: as a
+// separate launch (the form every other tensor-core width uses).  Returns the previous setting.
+int mpnn_gru_bwd_one_pass(int enabled) {
+  const int prev = g_point_in_param;
+  g_point_in_param = enabled ? 1 : 0;
+  return prev;
 }
 
 // GRU forward with the message aggregation folded in (tensor-core widths only, mpnn_gru_agg_supported): the messages
@@ -663,18 +678,29 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
     wp += align_up((size_t)rows * 6 * d * sizeof(float), 256);
     const int nblk = 4 * mpnn_num_sms();
     float* bias_part = (float*)wp;
-    wp += align_up((size_t)nblk * 4 * d * sizeof(float), 256);
+    wp += align_up((size_t)16 * mpnn_num_sms() * 4 * d * sizeof(float), 256);
     float* Wc = (float*)wp;
     wp += align_up((size_t)12 * d * d * sizeof(float), 256);
     void* sub = wp;
     size_t sub_bytes = workspace_bytes - (size_t)(wp - (char*)workspace);
-    k_gru_point_bwd5<<<nblk, 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dg, bias_part);
-    MPNN_CHECK_LAUNCH("k_gru_point_bwd5");
-    k_gru_bias_final<<<ceil_div(4 * d, 32), 256, 0, stream>>>(bias_part, nblk, d, db_ih, db_hh);
-    MPNN_CHECK_LAUNCH("k_gru_bias_final");
+    int rc;
+    const bool one_pass = d <= 64 && g_point_in_param;
+    if (one_pass) {
+      // widths <= 64: the pointwise pass lives in the producers of the weight-gradient kernel (reads gates / h / dh' / m
+      // once, writes dg for the data product): no separate launch that writes and re-reads the gate gradients
+      if ((rc = mpnn_tc_gru_param_point(m, h, mask, gates, dh_out, rows, d, dg, bias_part, dW_ih, dW_hh, sub, sub_bytes,
+                                        stream)))
+        return rc;
+      k_gru_bias_final<<<ceil_div(4 * d, 32), 256, 0, stream>>>(bias_part, mpnn_tc_gru_param_bias_parts(), d, db_ih, db_hh);
+      MPNN_CHECK_LAUNCH("k_gru_bias_final");
+    } else {
+      k_gru_point_bwd5<<<nblk, 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dg, bias_part);
+      MPNN_CHECK_LAUNCH("k_gru_point_bwd5");
+      k_gru_bias_final<<<ceil_div(4 * d, 32), 256, 0, stream>>>(bias_part, nblk, d, db_ih, db_hh);
+      MPNN_CHECK_LAUNCH("k_gru_bias_final");
+    }
     k_gru_bwd_wcomb<<<ceil_div(12 * d * d, 256), 256, 0, stream>>>(W_ih, W_hh, d, Wc);
     MPNN_CHECK_LAUNCH("k_gru_bwd_wcomb");
-    int rc;
     if (2 * d <= 256) {   // one N = 2d product, columns [0, d) -> dm, [d, 2d) -> dh: the gate gradients are read once
       const int DP2 = 2 * d <= 64 ? 64 : 2 * d <= 128 ? 128 : 256;
       rc = mpnn_tc_dense_gemm_ll(dg, rows, 6 * d, d, 6, d, Wc, d, 1, 0, (long long)2 * d * d, 1, 2 * d, nullptr, dm, d,
@@ -684,6 +710,7 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
                                  dm, d, (long long)(dh - dm), 0, 0, DP, sub, sub_bytes, stream);
     }
     if (rc) return rc;
+    if (one_pass) return MPNN_OK;
     if (d <= 64) return mpnn_tc_gru_param_grad(m, h, dg, 6 * d, rows, d, dW_ih, dW_hh, sub, sub_bytes, stream);
     if ((rc = mpnn_tc_dense_gemm_tn(m, rows, d, d, dg, 6 * d, d, 3, d, DP, dW_ih, d, 3 * d, sub, sub_bytes, stream))) return rc;
     if ((rc = mpnn_tc_dense_gemm_tn(h, rows, d, d, dg, 6 * d, d, 2, d, DP, dW_hh, d, 3 * d, sub, sub_bytes, stream))) return rc;

@@ -1166,6 +1166,13 @@ struct TcGruParam {
   float* partial;     // [grid][128][256]
   long long rows;
   int d, ldg;
+  // k_tc_gru_param_point only: the saved gates [rows, 4d], dh' [rows, d], mask [rows]; outputs dg [rows, 6d] and the
+  // bias partials [grid * 16][4d]
+  const float* gates;
+  const float* dh_out;
+  const float* mask;
+  float* dg_out;
+  float* bias_part;
 };
 struct GpCfg {
   static constexpr int KST = 32;                 // rows per stage
@@ -1247,6 +1254,208 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_grad(TcGruParam a) 
       if (++stage == C::NSTAGE) {
         stage = 0;
         phase ^= 1;
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && c0 < c1) {
+      constexpr uint32_t idesc = make_idesc(128, 256, 1, 1);
+      int stage = 0, phase = 0;
+      bool fresh = true;
+      for (long long c = c0; c < c1; ++c) {
+        mbar_wait(full_bar(stage), phase);
+        fence_proxy_async();
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE;
+#pragma unroll
+        for (int j = 0; j < C::KST / 8; ++j) {
+          const uint64_t ad = make_sdesc(sa + j * 1024, C::LBO, C::SBO, 1u);
+          const uint64_t bd = make_sdesc(sa + C::A_BYTES + j * 1024, C::LBO, C::SBO, 1u);
+          umma_tf32(tmem_base, ad, bd, idesc, fresh ? 0u : 1u);
+          fresh = false;
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == C::NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(accfull_bar);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int l = q * 32 + lane;
+    float* out = a.partial + (size_t)blockIdx.x * 128 * 256 + (size_t)l * 256;
+    if (c0 < c1) {
+      mbar_wait(accfull_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 256; cc += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(out + cc + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    } else {
+      for (int cc = 0; cc < 256; cc += 4) *reinterpret_cast<float4*>(out + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+// The same with the pointwise GRU backward folded into the producers (no separate pass that writes the gate gradients and no
+// re-read of them here): reads gates / h / dh' / m once, writes dg [rows, 6d] for the data product and the bias partials.
+__global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a) {
+  using C = GpCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 2);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSTAGE + s); };
+  const uint32_t accfull_bar = bar_base + 8u * (2 * C::NSTAGE);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) {
+      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_chunks = (a.rows + C::KST - 1) / C::KST;
+  const long long per = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const long long c0 = (long long)blockIdx.x * per;
+  const long long c1 = c0 + per < n_chunks ? c0 + per : n_chunks;
+  const int d = a.d;
+
+  if (warp < 4) {
+    // ===================== producers: pointwise GRU backward + operand staging =====================
+    // A thread owns the 4-column groups (half hb, chunk) of rows sub and sub + 16 of every stage: it reads the saved
+    // gates, h and dh' of those elements, computes the six gate-gradient values, stores the first four into the
+    // MN-major B image AND all six to dg (the data product reads them), and keeps the bias column sums in registers.
+    const int sub = tid >> 3, chunk = tid & 7;
+    int stage = 0, phase = 0;
+    float4 bsum[2][4];
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) bsum[hb][q4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long c = c0; c < c1; ++c) {
+      const long long pos = c * C::KST;
+      // the global operands of this stage's elements: all loads in flight before the stage is waited for
+      float4 sr[2][2], sz[2][2], tn[2][2], nh[2][2], hv[2][2], dv[2][2];
+      float mu[2];
+#pragma unroll
+      for (int hh = 0; hh < C::EPT; ++hh) {
+        const long long row = pos + sub + 16 * hh;
+        const bool rok = row < a.rows;
+        mu[hh] = rok ? __ldg(a.mask + row) : 0.f;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const int col = hb * 32 + chunk * 4;
+          const bool ok = rok && col < d;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* g = a.gates + (size_t)(ok ? row : 0) * 4 * d + (ok ? col : 0);
+          sr[hh][hb] = ok ? ldg4(g) : z4;
+          sz[hh][hb] = ok ? ldg4(g + d) : z4;
+          tn[hh][hb] = ok ? ldg4(g + 2 * d) : z4;
+          nh[hh][hb] = ok ? ldg4(g + 3 * d) : z4;
+          hv[hh][hb] = ok ? ldg4(a.h + (size_t)row * d + col) : z4;
+          dv[hh][hb] = ok ? ldg4(a.dh_out + (size_t)row * d + col) : z4;
+        }
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      const uint32_t As = smem_base + stage * C::STAGE;
+      uint8_t* Bg = smem + stage * C::STAGE + C::A_BYTES;
+#pragma unroll
+      for (int hh = 0; hh < C::EPT; ++hh) {
+        const int r = sub + 16 * hh;
+        const long long row = pos + r;
+        const bool rok = row < a.rows;
+        const uint32_t roff = (uint32_t)(r >> 2) * C::SBO + swz32(r & 3, chunk);
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          const int col = (mb & 1) * 32 + chunk * 4;
+          const float* base = mb < 2 ? a.m : a.h;
+          const bool ok = rok && col < d;
+          cp_async16(As + (uint32_t)mb * C::LBO + roff, ok ? base + (size_t)row * d + col : base, ok ? 16u : 0u);
+        }
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          const int col = hb * 32 + chunk * 4;
+          const bool ok = rok && col < d;
+          float4 o[6];
+          const float m_ = mu[hh];
+#define MPNN_GP(X)                                                              \
+  {                                                                             \
+    const float r_ = sr[hh][hb].X * m_, z_ = sz[hh][hb].X * m_, n_ = tn[hh][hb].X * m_; \
+    const float go = dv[hh][hb].X * m_;                                         \
+    const float dn = go * (1.f - z_);                                           \
+    const float dz = go * (hv[hh][hb].X - n_);                                  \
+    const float dan = dn * m_ * (1.f - tn[hh][hb].X * tn[hh][hb].X);            \
+    const float dr = dan * nh[hh][hb].X;                                        \
+    o[0].X = dr * m_ * sr[hh][hb].X * (1.f - sr[hh][hb].X);                     \
+    o[1].X = dz * m_ * sz[hh][hb].X * (1.f - sz[hh][hb].X);                     \
+    o[2].X = dan;                                                               \
+    o[3].X = dan * r_;                                                          \
+    const float gz = go * z_;                                                   \
+    o[4].X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u);                \
+    o[5].X = gz - o[4].X;                                                       \
+  }
+          MPNN_GP(x) MPNN_GP(y) MPNN_GP(z) MPNN_GP(w)
+#undef MPNN_GP
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            sts4(Bg, (uint32_t)(2 * q4 + hb) * C::LBO + roff, ok ? o[q4] : make_float4(0.f, 0.f, 0.f, 0.f));
+            if (ok) {
+              bsum[hb][q4].x += o[q4].x;
+              bsum[hb][q4].y += o[q4].y;
+              bsum[hb][q4].z += o[q4].z;
+              bsum[hb][q4].w += o[q4].w;
+            }
+          }
+          if (ok) {
+            float* og = a.dg_out + (size_t)row * 6 * d + col;
+#pragma unroll
+            for (int q6 = 0; q6 < 6; ++q6) *reinterpret_cast<float4*>(og + q6 * d) = o[q6];
+          }
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_proxy_async();
+      mbar_arrive(full_bar(stage));
+      if (++stage == C::NSTAGE) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // bias column sums of this (CTA, sub): one [4d] row of the partial array (k_gru_bias_final sums the rows in order)
+    {
+      float* bp = a.bias_part + ((size_t)blockIdx.x * 16 + sub) * 4 * d;
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+        const int col = hb * 32 + chunk * 4;
+        if (col < d) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<float4*>(bp + q4 * d + col) = bsum[hb][q4];
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -1810,11 +2019,34 @@ int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int 
                "tc_gru_param_grad: width %d not served", d);
   MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_param_workspace_bytes(), MPNN_ERR_WORKSPACE,
                "tc_gru_param_grad: workspace too small");
-  TcGruParam a = {m, h, dg, (float*)workspace, rows, d, ldg};
+  TcGruParam a = {m, h, dg, (float*)workspace, rows, d, ldg, nullptr, nullptr, nullptr, nullptr, nullptr};
   const int grid = tc_grid();
   MPNN_REQUIRE(set_smem(k_tc_gru_param_grad, GpCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_param_grad: smem attribute");
   k_tc_gru_param_grad<<<grid, THREADS, GpCfg::SMEM, stream>>>(a);
   MPNN_CHECK_LAUNCH("k_tc_gru_param_grad");
+  k_tc_gru_param_reduce<<<ceil_div(6 * d * d, 256), 256, 0, stream>>>(a.partial, grid, d, dW_ih, dW_hh);
+  MPNN_CHECK_LAUNCH("k_tc_gru_param_reduce");
+  return MPNN_OK;
+}
+
+// Pointwise GRU backward + weight gradients in one pass (widths <= 64): reads the saved gates [rows, 4d], m, h, dh', mask;
+// writes dg [rows, 6d] (dar | daz | dan | dnh | hi(go z) | lo(go z): the operand of the data product), bias partials
+// [mpnn_tc_gru_param_bias_parts()][4d] (sum them in order for db_ih / db_hh) and dW_ih, dW_hh [d, 3d].
+int mpnn_tc_gru_param_bias_parts(void) { return tc_grid() * 16; }
+
+int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, const float* gates, const float* dh_out,
+                            long long rows, int d, float* dg, float* bias_part, float* dW_ih, float* dW_hh,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MPNN_REQUIRE(m && h && mask && gates && dh_out && dg && bias_part && dW_ih && dW_hh && workspace && rows > 0,
+               MPNN_ERR_ARG, "tc_gru_param_point: bad argument");
+  MPNN_REQUIRE(d > 0 && d <= 64 && (d & 3) == 0, MPNN_ERR_UNSUPPORTED, "tc_gru_param_point: width %d not served", d);
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_param_workspace_bytes(), MPNN_ERR_WORKSPACE,
+               "tc_gru_param_point: workspace too small");
+  TcGruParam a = {m, h, nullptr, (float*)workspace, rows, d, 6 * d, gates, dh_out, mask, dg, bias_part};
+  const int grid = tc_grid();
+  MPNN_REQUIRE(set_smem(k_tc_gru_param_point, GpCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_param_point: smem attribute");
+  k_tc_gru_param_point<<<grid, THREADS, GpCfg::SMEM, stream>>>(a);
+  MPNN_CHECK_LAUNCH("k_tc_gru_param_point");
   k_tc_gru_param_reduce<<<ceil_div(6 * d * d, 256), 256, 0, stream>>>(a.partial, grid, d, dW_ih, dW_hh);
   MPNN_CHECK_LAUNCH("k_tc_gru_param_reduce");
   return MPNN_OK;

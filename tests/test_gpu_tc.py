@@ -326,3 +326,35 @@ def test_aggregation_inside_gru_kernel_is_bit_identical(dev, d, B, monkeypatch):
     assert torch.equal(o1, o0) and torch.equal(a1, a0)
     for k in g0:
         assert torch.equal(g1[k], g0[k]), k
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 64), (333, 40), (5000, 64), (77, 36)])
+def test_gru_backward_one_pass_equals_separate_pointwise(dev, rows, d):
+    """widths 33..64: the pointwise GRU backward inside the weight-gradient kernel's producers (mpnn_tc_gru_param_point)
+    against the separate pointwise launch: same gate gradients, so dm / dh / dW are bit-identical; the bias gradients
+    are summed over another partition of the rows"""
+    from mpnn_b200 import _lib, functional as Fn
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(rows + d)
+    m = torch.randn(rows, d, generator=g).to(dev)
+    h = torch.randn(rows, d, generator=g).to(dev)
+    mask = (torch.rand(rows, generator=g) > 0.25).float().to(dev)
+    W = [(torch.randn(d, 3 * d, generator=g) * 0.2).to(dev).requires_grad_(True) for _ in range(2)]
+    bb = [(torch.randn(3 * d, generator=g) * 0.1).to(dev).requires_grad_(True) for _ in range(2)]
+    cot = torch.randn(rows, d, generator=g).to(dev)
+    res = []
+    for one in (1, 0):
+        prev = lib.mpnn_gru_bwd_one_pass(one)
+        try:
+            mm, hh = m.clone().requires_grad_(True), h.clone().requires_grad_(True)
+            out = Fn.GRUFn.apply(mm, hh, mask, W[0], W[1], bb[0], bb[1], None)
+            grads = torch.autograd.grad(out, [mm, hh] + W + bb, cot)
+            torch.cuda.synchronize()
+            res.append([t.clone() for t in grads])
+        finally:
+            lib.mpnn_gru_bwd_one_pass(prev)
+    a, b = res
+    for i in range(4):
+        assert torch.equal(a[i], b[i]), i
+    for i in (4, 5):
+        assert rel_err(a[i], b[i]) <= 1e-5, i
