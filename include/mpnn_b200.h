@@ -180,8 +180,14 @@ size_t mpnn_tc_gru_param_workspace_bytes(void);
 int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int ldg, long long rows, int d,
                            float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* The same with the pointwise GRU backward folded in: reads the saved gates [rows, 4d], m, h, dh', mask once; writes
- * dg [rows, 6d] (dar | daz | dan | dnh | hi(go z) | lo(go z), the operand of the data product), the bias partials
+ * dg [rows, 6d] when non-NULL (dar | daz | dan | dnh | hi(go z) | lo(go z)), the bias partials
  * [mpnn_tc_gru_param_bias_parts()][4d] and dW_ih, dW_hh. */
+/* GRU data gradients for widths <= 64 straight from the saved gates (no gate-gradient array in HBM):
+ * (dm | dh) = (dar|daz|dan|dnh|hi(go z)|lo(go z)) x Wc, Wc = combined weights [6][2d][d] (device). */
+size_t mpnn_tc_gru_data_workspace_bytes(void);
+int mpnn_tc_gru_data_grad(const float* gates, const float* h, const float* dh_out, const float* mask, const float* Wc,
+                          long long rows, int d, float* dm, float* dh, void* workspace, size_t workspace_bytes,
+                          mpnn_stream_t stream);
 int mpnn_tc_gru_param_bias_parts(void);
 int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, const float* gates, const float* dh_out,
                             long long rows, int d, float* dg, float* bias_part, float* dW_ih, float* dW_hh,

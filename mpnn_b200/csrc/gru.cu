@@ -39,6 +39,10 @@ extern "C" int mpnn_tc_gru_fwd_agg(const float* Y, const int* row_ptr, const flo
                                    size_t workspace_bytes, cudaStream_t stream);
 extern "C" size_t mpnn_tc_gru_param_workspace_bytes(void);
 extern "C" int mpnn_tc_gru_param_bias_parts(void);
+extern "C" size_t mpnn_tc_gru_data_workspace_bytes(void);
+extern "C" int mpnn_tc_gru_data_grad(const float* gates, const float* h, const float* dh_out, const float* mask,
+                                     const float* Wc, long long rows, int d, float* dm, float* dh, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream);
 extern "C" int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, const float* gates,
                                        const float* dh_out, long long rows, int d, float* dg, float* bias_part,
                                        float* dW_ih, float* dW_hh, void* workspace, size_t workspace_bytes,
@@ -530,6 +534,7 @@ size_t mpnn_gru_workspace_bytes(long long rows, int d) {
     size_t t = align_up(mpnn_tc_dense_workspace_bytes(24, DP), 256) + mpnn_tc_dense_grad_workspace_bytes(3, DP);
     if (t > sub) sub = t;
     if (mpnn_tc_gru_param_workspace_bytes() > sub) sub = mpnn_tc_gru_param_workspace_bytes();
+    if (mpnn_tc_gru_data_workspace_bytes() > sub) sub = mpnn_tc_gru_data_workspace_bytes();
     // dg [rows, 6d] (= the two [rows, 3d] arrays of the fp32 path) + bias partials + the combined weights
     pre += align_up((size_t)16 * mpnn_num_sms() * 4 * d * sizeof(float), 256) + align_up((size_t)12 * d * d * sizeof(float), 256);
   }
@@ -686,13 +691,17 @@ int mpnn_gru_bwd(const float* m, const float* h, const float* mask, const float*
     int rc;
     const bool one_pass = d <= 64 && g_point_in_param;
     if (one_pass) {
-      // widths <= 64: the pointwise pass lives in the producers of the weight-gradient kernel (reads gates / h / dh' / m
-      // once, writes dg for the data product): no separate launch that writes and re-reads the gate gradients
-      if ((rc = mpnn_tc_gru_param_point(m, h, mask, gates, dh_out, rows, d, dg, bias_part, dW_ih, dW_hh, sub, sub_bytes,
-                                        stream)))
+      // widths <= 64: the gate gradients never reach HBM.  The pointwise pass lives in the producers of BOTH tensor-core
+      // kernels: the weight-gradient kernel (MN-major operand, + bias column sums) and the data-gradient kernel (K-major
+      // operand, six stages = the six gate-gradient blocks); each reads the saved gates / h / dh' once.
+      if ((rc = mpnn_tc_gru_param_point(m, h, mask, gates, dh_out, rows, d, nullptr, bias_part, dW_ih, dW_hh, sub,
+                                        sub_bytes, stream)))
         return rc;
       k_gru_bias_final<<<ceil_div(4 * d, 32), 256, 0, stream>>>(bias_part, mpnn_tc_gru_param_bias_parts(), d, db_ih, db_hh);
       MPNN_CHECK_LAUNCH("k_gru_bias_final");
+      k_gru_bwd_wcomb<<<ceil_div(12 * d * d, 256), 256, 0, stream>>>(W_ih, W_hh, d, Wc);
+      MPNN_CHECK_LAUNCH("k_gru_bwd_wcomb");
+      return mpnn_tc_gru_data_grad(gates, h, dh_out, mask, Wc, rows, d, dm, dh, sub, sub_bytes, stream);
     } else {
       k_gru_point_bwd5<<<nblk, 256, 0, stream>>>(gates, h, mask, dh_out, rows, d, dg, bias_part);
       MPNN_CHECK_LAUNCH("k_gru_point_bwd5");

@@ -1431,7 +1431,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a)
               bsum[hb][q4].w += o[q4].w;
             }
           }
-          if (ok) {
+          if (ok && a.dg_out) {
             float* og = a.dg_out + (size_t)row * 6 * d + col;
 #pragma unroll
             for (int q6 = 0; q6 < 6; ++q6) *reinterpret_cast<float4*>(og + q6 * d) = o[q6];
@@ -1502,6 +1502,218 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a)
       }
     } else {
       for (int cc = 0; cc < 256; cc += 4) *reinterpret_cast<float4*>(out + cc) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GRU data gradients for widths <= 64 WITHOUT a gate-gradient array in HBM (gru_update.py:27-34 backward):
+//     (dm | dh) [rows, 2d] = (dar | daz | dan | dnh | hi(go z) | lo(go z)) [rows, 6d]  x  Wc [6d, 2d]
+// The producers read the saved gates, h and dh' of a 128-row x 32-column block ONCE, compute the six gate-gradient
+// blocks and store each into its own stage as the K-major A operand (six stages = the six K segments of one
+// (row tile, 32-column block) group; the B operand of a stage is the matching 32 x 2d slice of Wc, one bulk copy).
+// The MMA warp walks the six stages in order; the accumulator (N = 128 columns: dm | dh) is double-buffered in TMEM;
+// the epilogue sends columns [0, d) to dm and [d, 2d) to dh.  With mpnn_tc_gru_param_point the gate gradients of
+// the wide GRU backward never reach HBM.
+// ---------------------------------------------------------------------------------------------------
+struct TcGruData {
+  const float *gates, *h, *dh_out, *mask;
+  const float* Bimg;   // [6][DP / 32][DP][32] swizzled (k_tc_pack_image, DP = 128)
+  float *dm, *dh;
+  long long rows;
+  int d;
+};
+struct GdCfg {
+  static constexpr int DP = 128;
+  static constexpr int NSEG = 6;
+  static constexpr int A_BYTES = TILE * 128;
+  static constexpr int B_BYTES = DP * 128;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
+  static constexpr int SMEM = NSEG * STAGE + EPI_BYTES + 1024 + 256;
+  static constexpr int TCOLS = 2 * DP;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
+  using C = GdCfg;
+  constexpr int DP = C::DP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi = reinterpret_cast<float*>(smem + C::NSEG * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSEG * C::STAGE + C::EPI_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSEG + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSEG + s); };
+  auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * C::NSEG + s); };
+  auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * C::NSEG + 2 + s); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < C::NSEG; ++s) {
+      mbar_init(full_bar(s), PRODUCERS + 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(accfull_bar(s), 1);
+      mbar_init(accempty_bar(s), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int d = a.d;
+  const int nkb = (d + KB - 1) / KB;
+  constexpr int NKB = DP / KB;
+  const int n_tiles = (int)((a.rows + TILE - 1) / TILE);
+  const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t0 = blockIdx.x * per;
+  const int t1 = min(t0 + per, n_tiles);
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    const int sub = tid >> 3, chunk = tid & 7;
+    int phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      const long long pos = (long long)t * TILE;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int col = kb * KB + chunk * 4;
+        const bool cok = col < d;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float4 sr[4], sz[4], tn[4], nh[4], hv[4], dv[4];
+          float mu[4];
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const long long row = pos + (half * 4 + ii) * 16 + sub;
+            const bool ok = cok && row < a.rows;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            mu[ii] = ok ? __ldg(a.mask + row) : 0.f;
+            const float* g = a.gates + (size_t)(ok ? row : 0) * 4 * d + (ok ? col : 0);
+            sr[ii] = ok ? ldg4(g) : z4;
+            sz[ii] = ok ? ldg4(g + d) : z4;
+            tn[ii] = ok ? ldg4(g + 2 * d) : z4;
+            nh[ii] = ok ? ldg4(g + 3 * d) : z4;
+            hv[ii] = ok ? ldg4(a.h + (size_t)row * d + col) : z4;
+            dv[ii] = ok ? ldg4(a.dh_out + (size_t)row * d + col) : z4;
+          }
+          if (half == 0) {
+            // the six stages of this group: wait until the MMAs of the previous group have drained them, start their B copies
+#pragma unroll 1
+            for (int sg = 0; sg < C::NSEG; ++sg) {
+              mbar_wait(empty_bar(sg), phase ^ 1);
+              if (tid == 0) {
+                mbar_arrive_expect_tx(full_bar(sg), C::B_BYTES);
+                bulk_copy(smem_base + sg * C::STAGE + C::A_BYTES, a.Bimg + (size_t)(sg * NKB + kb) * (DP * KB), C::B_BYTES,
+                          full_bar(sg));
+              }
+            }
+          }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int r = (half * 4 + ii) * 16 + sub;
+            float4 o[6];
+            const float m_ = mu[ii];
+#define MPNN_GD(X)                                                      \
+  {                                                                     \
+    const float r_ = sr[ii].X * m_, z_ = sz[ii].X * m_, n_ = tn[ii].X * m_; \
+    const float go = dv[ii].X * m_;                                     \
+    const float dn = go * (1.f - z_);                                   \
+    const float dz = go * (hv[ii].X - n_);                              \
+    const float dan = dn * m_ * (1.f - tn[ii].X * tn[ii].X);            \
+    const float dr = dan * nh[ii].X;                                    \
+    o[0].X = dr * m_ * sr[ii].X * (1.f - sr[ii].X);                     \
+    o[1].X = dz * m_ * sz[ii].X * (1.f - sz[ii].X);                     \
+    o[2].X = dan;                                                       \
+    o[3].X = dan * r_;                                                  \
+    const float gz = go * z_;                                           \
+    o[4].X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u);        \
+    o[5].X = gz - o[4].X;                                               \
+  }
+            MPNN_GD(x) MPNN_GD(y) MPNN_GD(z) MPNN_GD(w)
+#undef MPNN_GD
+#pragma unroll
+            for (int sg = 0; sg < C::NSEG; ++sg) sts4(smem + sg * C::STAGE, swz(r, chunk), o[sg]);
+          }
+        }
+        fence_proxy_async();
+#pragma unroll 1
+        for (int sg = 0; sg < C::NSEG; ++sg) mbar_arrive(full_bar(sg));
+        phase ^= 1;
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE, DP, 0, 0);
+      int phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int i = t - t0, acc = i & 1, use = i >> 1;
+        mbar_wait(accempty_bar(acc), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dtm = tmem_base + (uint32_t)(acc * DP);
+        for (int kb = 0; kb < nkb; ++kb) {
+          for (int sg = 0; sg < C::NSEG; ++sg) {
+            mbar_wait(full_bar(sg), phase);
+            fence_proxy_async();
+            tc_fence_after();
+            const uint32_t sa = smem_base + sg * C::STAGE;
+            const uint64_t ad = make_sdesc(sa, 16, 1024);
+            const uint64_t bd = make_sdesc(sa + C::A_BYTES, 16, 1024);
+#pragma unroll
+            for (int j = 0; j < KB / 8; ++j) umma_tf32(dtm, ad + 2u * j, bd + 2u * j, idesc, (kb | sg | j) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(sg));
+          }
+          phase ^= 1;
+        }
+        umma_commit(accfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    float* tb = epi + q * (32 * 33);
+    const int orow = lane >> 3, ocol = (lane & 7) * 4;
+    for (int t = t0; t < t1; ++t) {
+      const int i = t - t0, acc = i & 1, use = i >> 1;
+      const long long pos = (long long)t * TILE + q * 32;
+      mbar_wait(accfull_bar(acc), use & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        if (c0 >= 2 * d) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DP + c0), v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tb[lane * 33 + c] = v[c];
+        __syncwarp();
+        const int cc = c0 + ocol;
+        if (cc < 2 * d) {
+          float* out = cc < d ? a.dm + cc : a.dh + (cc - d);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const long long row = pos + it * 4 + orow;
+            if (row < a.rows) {
+              const float* p = tb + (it * 4 + orow) * 33 + ocol;
+              *reinterpret_cast<float4*>(out + (size_t)row * d) = make_float4(p[0], p[1], p[2], p[3]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(accempty_bar(acc));
     }
   }
   tc_fence_before();
@@ -2037,7 +2249,7 @@ int mpnn_tc_gru_param_bias_parts(void) { return tc_grid() * 16; }
 int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, const float* gates, const float* dh_out,
                             long long rows, int d, float* dg, float* bias_part, float* dW_ih, float* dW_hh,
                             void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  MPNN_REQUIRE(m && h && mask && gates && dh_out && dg && bias_part && dW_ih && dW_hh && workspace && rows > 0,
+  MPNN_REQUIRE(m && h && mask && gates && dh_out && bias_part && dW_ih && dW_hh && workspace && rows > 0,
                MPNN_ERR_ARG, "tc_gru_param_point: bad argument");
   MPNN_REQUIRE(d > 0 && d <= 64 && (d & 3) == 0, MPNN_ERR_UNSUPPORTED, "tc_gru_param_point: width %d not served", d);
   MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_param_workspace_bytes(), MPNN_ERR_WORKSPACE,
@@ -2049,6 +2261,32 @@ int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, c
   MPNN_CHECK_LAUNCH("k_tc_gru_param_point");
   k_tc_gru_param_reduce<<<ceil_div(6 * d * d, 256), 256, 0, stream>>>(a.partial, grid, d, dW_ih, dW_hh);
   MPNN_CHECK_LAUNCH("k_tc_gru_param_reduce");
+  return MPNN_OK;
+}
+
+// GRU data gradients for widths <= 64 straight from the saved gates (k_tc_gru_data_grad): dm, dh [rows, d].
+// Wc: the combined weights [6][2d][d] (rows [0,d) of a block -> dm, [d,2d) -> dh; blocks = dar | daz | dan | dnh | I | I).
+size_t mpnn_tc_gru_data_workspace_bytes(void) { return (size_t)6 * 128 * 128 * sizeof(float); }
+
+int mpnn_tc_gru_data_grad(const float* gates, const float* h, const float* dh_out, const float* mask, const float* Wc,
+                          long long rows, int d, float* dm, float* dh, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
+  MPNN_REQUIRE(gates && h && dh_out && mask && Wc && dm && dh && workspace && rows > 0, MPNN_ERR_ARG,
+               "tc_gru_data_grad: bad argument");
+  MPNN_REQUIRE(d > 0 && d <= 64 && (d & 3) == 0, MPNN_ERR_UNSUPPORTED, "tc_gru_data_grad: width %d not served", d);
+  MPNN_REQUIRE(rows < (1ll << 31) - TILE, MPNN_ERR_UNSUPPORTED, "tc_gru_data_grad: too many rows");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_tc_gru_data_workspace_bytes(), MPNN_ERR_WORKSPACE,
+               "tc_gru_data_grad: workspace too small");
+  float* img = (float*)workspace;
+  k_tc_pack_image<<<ceil_div(6LL * 128 * 128, 256), 256, 0, stream>>>(Wc, d, 1, 0, (long long)2 * d * d, 6, 6, 2 * d, d, 128,
+                                                                     img);
+  MPNN_CHECK_LAUNCH("k_tc_pack_image");
+  TcGruData a = {gates, h, dh_out, mask, img, dm, dh, rows, d};
+  const long long tiles = (rows + TILE - 1) / TILE;
+  const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
+  MPNN_REQUIRE(set_smem(k_tc_gru_data_grad, GdCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_data_grad: smem attribute");
+  k_tc_gru_data_grad<<<grid, THREADS, GdCfg::SMEM, stream>>>(a);
+  MPNN_CHECK_LAUNCH("k_tc_gru_data_grad");
   return MPNN_OK;
 }
 
