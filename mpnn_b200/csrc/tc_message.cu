@@ -1311,14 +1311,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_grad(TcGruParam a) 
 }
 
 // The same with the pointwise GRU backward folded into the producers (no separate pass that writes the gate gradients and no
-// re-read of them here): reads gates / h / dh' / m once, writes dg [rows, 6d] for the data product and the bias partials.
+// re-read of them here): reads gates / h / dh' / m once, writes the bias partials and -- when asked -- dg [rows, 6d].
+// The raw operands (four gate planes, h, dh', mask of a 32-row stage) travel through a two-deep cp.async ring in shared
+// memory, so the loads of stages c+1 and c+2 are in flight while stage c is converted into the MMA operand (a first
+// version loaded them into registers: 49 KB in flight per SM with a bubble per stage, 47 % of the DRAM peak).  A thread
+// converts exactly the elements it copied, so no barrier is needed between the copy and the conversion.
+struct GppCfg {
+  static constexpr int KST = 32;
+  static constexpr int EPT = 2;
+  static constexpr int A_BYTES = KST * 128 * 4;
+  static constexpr int B_BYTES = KST * 256 * 4;
+  static constexpr int STAGE = A_BYTES + B_BYTES;       // operand stage
+  static constexpr int NSTAGE = 2;
+  static constexpr int RAW_ITEMS = 24;                  // float4 per thread and stage: (row 2) x (column half 2) x (plane 6)
+  static constexpr int RAW_BYTES = RAW_ITEMS * PRODUCERS * 16 + 2 * PRODUCERS * 4;   // + the rows' mask values
+  static constexpr int RAW_STAGE = (RAW_BYTES + 1023) / 1024 * 1024;
+  static constexpr int NRAW = 2;
+  static constexpr int SMEM = NSTAGE * STAGE + NRAW * RAW_STAGE + 1024 + 256;
+  static constexpr int TCOLS = 256;
+  static constexpr uint32_t SBO = 512;
+  static constexpr uint32_t LBO = (KST / 4) * 512;
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a) {
-  using C = GpCfg;
+  using C = GppCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE);
+  uint8_t* rawbuf = smem + C::NSTAGE * C::STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rawbuf + C::NRAW * C::RAW_STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSTAGE + 2);
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t raw_base = smem_u32(rawbuf);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSTAGE + s); };
@@ -1327,7 +1354,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < C::NSTAGE; ++s) {
-      mbar_init(full_bar(s), PRODUCERS);
+      mbar_init(full_bar(s), 2 * PRODUCERS);   // per producer: one arrival for its stores, one for its async copies
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accfull_bar, 1);
@@ -1347,40 +1374,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a)
 
   if (warp < 4) {
     // ===================== producers: pointwise GRU backward + operand staging =====================
-    // A thread owns the 4-column groups (half hb, chunk) of rows sub and sub + 16 of every stage: it reads the saved
-    // gates, h and dh' of those elements, computes the six gate-gradient values, stores the first four into the
-    // MN-major B image AND all six to dg (the data product reads them), and keeps the bias column sums in registers.
+    // A thread owns the 4-column groups (half hb, chunk) of rows sub and sub + 16 of every stage.
     const int sub = tid >> 3, chunk = tid & 7;
-    int stage = 0, phase = 0;
     float4 bsum[2][4];
 #pragma unroll
     for (int hb = 0; hb < 2; ++hb)
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) bsum[hb][q4] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long c = c0; c < c1; ++c) {
-      const long long pos = c * C::KST;
-      // the global operands of this stage's elements: all loads in flight before the stage is waited for
-      float4 sr[2][2], sz[2][2], tn[2][2], nh[2][2], hv[2][2], dv[2][2];
-      float mu[2];
+    // raw item k = (hh * 2 + hb) * 6 + plane lives at raw[(k * PRODUCERS + tid) * 16]: conflict-free both ways
+    auto issue_raw = [&](long long c) {
+      if (c < c1) {
+        const long long pos = c * C::KST;
+        const uint32_t rb = raw_base + (uint32_t)((c - c0) & 1) * C::RAW_STAGE;
 #pragma unroll
-      for (int hh = 0; hh < C::EPT; ++hh) {
-        const long long row = pos + sub + 16 * hh;
-        const bool rok = row < a.rows;
-        mu[hh] = rok ? __ldg(a.mask + row) : 0.f;
+        for (int hh = 0; hh < C::EPT; ++hh) {
+          const long long row = pos + sub + 16 * hh;
+          const bool rok = row < a.rows;
+          cp_async4(rb + C::RAW_ITEMS * PRODUCERS * 16 + (uint32_t)(hh * PRODUCERS + tid) * 4, rok ? a.mask + row : a.mask,
+                    rok ? 4u : 0u);
 #pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          const int col = hb * 32 + chunk * 4;
-          const bool ok = rok && col < d;
-          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float* g = a.gates + (size_t)(ok ? row : 0) * 4 * d + (ok ? col : 0);
-          sr[hh][hb] = ok ? ldg4(g) : z4;
-          sz[hh][hb] = ok ? ldg4(g + d) : z4;
-          tn[hh][hb] = ok ? ldg4(g + 2 * d) : z4;
-          nh[hh][hb] = ok ? ldg4(g + 3 * d) : z4;
-          hv[hh][hb] = ok ? ldg4(a.h + (size_t)row * d + col) : z4;
-          dv[hh][hb] = ok ? ldg4(a.dh_out + (size_t)row * d + col) : z4;
+          for (int hb = 0; hb < 2; ++hb) {
+            const int col = hb * 32 + chunk * 4;
+            const bool ok = rok && col < d;
+            const uint32_t n = ok ? 16u : 0u;
+            const float* g = a.gates + (ok ? (size_t)row * 4 * d + col : 0);
+            const uint32_t k0 = (uint32_t)((hh * 2 + hb) * 6);
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) cp_async16(rb + ((k0 + pl) * PRODUCERS + tid) * 16, ok ? g + pl * d : a.gates, n);
+            cp_async16(rb + ((k0 + 4) * PRODUCERS + tid) * 16, ok ? a.h + (size_t)row * d + col : a.h, n);
+            cp_async16(rb + ((k0 + 5) * PRODUCERS + tid) * 16, ok ? a.dh_out + (size_t)row * d + col : a.dh_out, n);
+          }
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_raw(c0);
+    issue_raw(c0 + 1);
+    int stage = 0, phase = 0;
+    for (long long c = c0; c < c1; ++c) {
+      const long long pos = c * C::KST;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");     // this thread's copies of stage c have landed
+      const uint8_t* rw = rawbuf + ((c - c0) & 1) * C::RAW_STAGE;
       mbar_wait(empty_bar(stage), phase ^ 1);
       const uint32_t As = smem_base + stage * C::STAGE;
       uint8_t* Bg = smem + stage * C::STAGE + C::A_BYTES;
@@ -1397,39 +1431,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a)
           const bool ok = rok && col < d;
           cp_async16(As + (uint32_t)mb * C::LBO + roff, ok ? base + (size_t)row * d + col : base, ok ? 16u : 0u);
         }
+        const float m_ = *reinterpret_cast<const float*>(rw + C::RAW_ITEMS * PRODUCERS * 16 + (hh * PRODUCERS + tid) * 4);
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
           const int col = hb * 32 + chunk * 4;
           const bool ok = rok && col < d;
+          const int k0 = (hh * 2 + hb) * 6;
+          const float4 sr = *reinterpret_cast<const float4*>(rw + ((k0 + 0) * PRODUCERS + tid) * 16);
+          const float4 sz = *reinterpret_cast<const float4*>(rw + ((k0 + 1) * PRODUCERS + tid) * 16);
+          const float4 tn = *reinterpret_cast<const float4*>(rw + ((k0 + 2) * PRODUCERS + tid) * 16);
+          const float4 nh = *reinterpret_cast<const float4*>(rw + ((k0 + 3) * PRODUCERS + tid) * 16);
+          const float4 hv = *reinterpret_cast<const float4*>(rw + ((k0 + 4) * PRODUCERS + tid) * 16);
+          const float4 dv = *reinterpret_cast<const float4*>(rw + ((k0 + 5) * PRODUCERS + tid) * 16);
           float4 o[6];
-          const float m_ = mu[hh];
-#define MPNN_GP(X)                                                              \
-  {                                                                             \
-    const float r_ = sr[hh][hb].X * m_, z_ = sz[hh][hb].X * m_, n_ = tn[hh][hb].X * m_; \
-    const float go = dv[hh][hb].X * m_;                                         \
-    const float dn = go * (1.f - z_);                                           \
-    const float dz = go * (hv[hh][hb].X - n_);                                  \
-    const float dan = dn * m_ * (1.f - tn[hh][hb].X * tn[hh][hb].X);            \
-    const float dr = dan * nh[hh][hb].X;                                        \
-    o[0].X = dr * m_ * sr[hh][hb].X * (1.f - sr[hh][hb].X);                     \
-    o[1].X = dz * m_ * sz[hh][hb].X * (1.f - sz[hh][hb].X);                     \
-    o[2].X = dan;                                                               \
-    o[3].X = dan * r_;                                                          \
-    const float gz = go * z_;                                                   \
-    o[4].X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u);                \
-    o[5].X = gz - o[4].X;                                                       \
+#define MPNN_GP(X)                                              \
+  {                                                             \
+    const float r_ = sr.X * m_, z_ = sz.X * m_, n_ = tn.X * m_; \
+    const float go = dv.X * m_;                                 \
+    const float dn = go * (1.f - z_);                           \
+    const float dz = go * (hv.X - n_);                          \
+    const float dan = dn * m_ * (1.f - tn.X * tn.X);            \
+    const float dr = dan * nh.X;                                \
+    o[0].X = dr * m_ * sr.X * (1.f - sr.X);                     \
+    o[1].X = dz * m_ * sz.X * (1.f - sz.X);                     \
+    o[2].X = dan;                                               \
+    o[3].X = dan * r_;                                          \
+    const float gz = go * z_;                                   \
+    o[4].X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u); \
+    o[5].X = gz - o[4].X;                                       \
   }
           MPNN_GP(x) MPNN_GP(y) MPNN_GP(z) MPNN_GP(w)
 #undef MPNN_GP
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            sts4(Bg, (uint32_t)(2 * q4 + hb) * C::LBO + roff, ok ? o[q4] : make_float4(0.f, 0.f, 0.f, 0.f));
-            if (ok) {
-              bsum[hb][q4].x += o[q4].x;
-              bsum[hb][q4].y += o[q4].y;
-              bsum[hb][q4].z += o[q4].z;
-              bsum[hb][q4].w += o[q4].w;
-            }
+            sts4(Bg, (uint32_t)(2 * q4 + hb) * C::LBO + roff, o[q4]);   // (zero where the raw copy was zero-filled)
+            bsum[hb][q4].x += o[q4].x;
+            bsum[hb][q4].y += o[q4].y;
+            bsum[hb][q4].z += o[q4].z;
+            bsum[hb][q4].w += o[q4].w;
           }
           if (ok && a.dg_out) {
             float* og = a.dg_out + (size_t)row * 6 * d + col;
@@ -1438,14 +1477,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_param_point(TcGruParam a)
           }
         }
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
       fence_proxy_async();
-      mbar_arrive(full_bar(stage));
+      mbar_arrive(full_bar(stage));              // the B image (generic stores)
+      cp_async_arrive_noinc(full_bar(stage));    // the A image (and every older copy of this thread)
+      issue_raw(c + 2);                          // refill the raw stage just consumed
       if (++stage == C::NSTAGE) {
         stage = 0;
         phase ^= 1;
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     // bias column sums of this (CTA, sub): one [4d] row of the partial array (k_gru_bias_final sums the rows in order)
     {
       float* bp = a.bias_part + ((size_t)blockIdx.x * 16 + sub) * 4 * d;
@@ -2256,8 +2297,8 @@ int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, c
                "tc_gru_param_point: workspace too small");
   TcGruParam a = {m, h, nullptr, (float*)workspace, rows, d, 6 * d, gates, dh_out, mask, dg, bias_part};
   const int grid = tc_grid();
-  MPNN_REQUIRE(set_smem(k_tc_gru_param_point, GpCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_param_point: smem attribute");
-  k_tc_gru_param_point<<<grid, THREADS, GpCfg::SMEM, stream>>>(a);
+  MPNN_REQUIRE(set_smem(k_tc_gru_param_point, GppCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_param_point: smem attribute");
+  k_tc_gru_param_point<<<grid, THREADS, GppCfg::SMEM, stream>>>(a);
   MPNN_CHECK_LAUNCH("k_tc_gru_param_point");
   k_tc_gru_param_reduce<<<ceil_div(6 * d * d, 256), 256, 0, stream>>>(a.partial, grid, d, dW_ih, dW_hh);
   MPNN_CHECK_LAUNCH("k_tc_gru_param_reduce");
