@@ -1573,32 +1573,43 @@ struct TcGruData {
 struct GdCfg {
   static constexpr int DP = 128;
   static constexpr int NSEG = 6;
+  static constexpr int NST = 3;                          // operand stages: three gate-gradient blocks per pass, two passes
   static constexpr int A_BYTES = TILE * 128;
   static constexpr int B_BYTES = DP * 128;
   static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int RAW_ITEMS = 24;                   // float4 per thread and half tile: (row 4) x (plane 6)
+  static constexpr int RAW_HALF = (RAW_ITEMS * PRODUCERS * 16 + 4 * PRODUCERS * 4 + 1023) / 1024 * 1024;
   static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
-  static constexpr int SMEM = NSEG * STAGE + EPI_BYTES + 1024 + 256;
+  static constexpr int SMEM = NST * STAGE + 2 * RAW_HALF + EPI_BYTES + 1024 + 256;
   static constexpr int TCOLS = 2 * DP;
 };
 
+// Producer schedule per (row tile, 32-column block) group: the raw operands of its two half tiles (64 rows each) arrive
+// through two cp.async buffers.  Pass 0 converts both halves: blocks dar, daz, dan go to the three operand stages, the
+// other three (dnh, hi, lo) overwrite the raw slots they were computed from.  Pass 1 moves those into the same stages
+// once the MMAs of pass 0 have drained them, and refills each raw buffer with the NEXT group's half as soon as it has been
+// read: up to 96 KB of loads are in flight per SM while a group is converted (a first version loaded 24 float4 per
+// thread into registers, converted, loaded the next 24: 40 % of the DRAM peak).
 __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
   using C = GdCfg;
   constexpr int DP = C::DP;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* epi = reinterpret_cast<float*>(smem + C::NSEG * C::STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSEG * C::STAGE + C::EPI_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NSEG + 4);
+  uint8_t* rawbuf = smem + C::NST * C::STAGE;
+  float* epi = reinterpret_cast<float*>(rawbuf + 2 * C::RAW_HALF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rawbuf + 2 * C::RAW_HALF + C::EPI_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::NST + 4);
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t raw_base = smem_u32(rawbuf);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NSEG + s); };
-  auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * C::NSEG + s); };
-  auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * C::NSEG + 2 + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::NST + s); };
+  auto accfull_bar = [&](int s) { return bar_base + 8u * (2 * C::NST + s); };
+  auto accempty_bar = [&](int s) { return bar_base + 8u * (2 * C::NST + 2 + s); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < C::NSEG; ++s) {
+    for (int s = 0; s < C::NST; ++s) {
       mbar_init(full_bar(s), PRODUCERS + 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -1621,79 +1632,118 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
   const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int t0 = blockIdx.x * per;
   const int t1 = min(t0 + per, n_tiles);
+  const int n_groups = (t1 - t0) * nkb;   // group g -> tile t0 + g / nkb, column block g % nkb
 
   if (warp < 4) {
     // ===================== producers =====================
     const int sub = tid >> 3, chunk = tid & 7;
+    // raw item k = ii * 6 + plane of half tile hf lives at raw[hf][(k * PRODUCERS + tid) * 16]
+    auto issue_raw = [&](int g, int hf) {
+      if (g < n_groups) {
+        const long long pos = (long long)(t0 + g / nkb) * TILE;
+        const int col = (g % nkb) * KB + chunk * 4;
+        const uint32_t rb = raw_base + (uint32_t)hf * C::RAW_HALF;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const long long row = pos + (hf * 4 + ii) * 16 + sub;
+          const bool ok = col < d && row < a.rows;
+          const uint32_t n = ok ? 16u : 0u;
+          cp_async4(rb + C::RAW_ITEMS * PRODUCERS * 16 + (uint32_t)(ii * PRODUCERS + tid) * 4, ok ? a.mask + row : a.mask,
+                    ok ? 4u : 0u);
+          const float* gp = a.gates + (ok ? (size_t)row * 4 * d + col : 0);
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl) cp_async16(rb + ((ii * 6 + pl) * PRODUCERS + tid) * 16, ok ? gp + pl * d : a.gates, n);
+          cp_async16(rb + ((ii * 6 + 4) * PRODUCERS + tid) * 16, ok ? a.h + (size_t)row * d + col : a.h, n);
+          cp_async16(rb + ((ii * 6 + 5) * PRODUCERS + tid) * 16, ok ? a.dh_out + (size_t)row * d + col : a.dh_out, n);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_raw(0, 0);
+    issue_raw(0, 1);
     int phase = 0;
-    for (int t = t0; t < t1; ++t) {
-      const long long pos = (long long)t * TILE;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int col = kb * KB + chunk * 4;
-        const bool cok = col < d;
+    for (int g = 0; g < n_groups; ++g) {
+      const int kb = g % nkb;
+      // ---- pass 0: dar, daz, dan -> stages 0..2; dnh, hi, lo -> back into the raw slots ----
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          float4 sr[4], sz[4], tn[4], nh[4], hv[4], dv[4];
-          float mu[4];
-#pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            const long long row = pos + (half * 4 + ii) * 16 + sub;
-            const bool ok = cok && row < a.rows;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            mu[ii] = ok ? __ldg(a.mask + row) : 0.f;
-            const float* g = a.gates + (size_t)(ok ? row : 0) * 4 * d + (ok ? col : 0);
-            sr[ii] = ok ? ldg4(g) : z4;
-            sz[ii] = ok ? ldg4(g + d) : z4;
-            tn[ii] = ok ? ldg4(g + 2 * d) : z4;
-            nh[ii] = ok ? ldg4(g + 3 * d) : z4;
-            hv[ii] = ok ? ldg4(a.h + (size_t)row * d + col) : z4;
-            dv[ii] = ok ? ldg4(a.dh_out + (size_t)row * d + col) : z4;
-          }
-          if (half == 0) {
-            // the six stages of this group: wait until the MMAs of the previous group have drained them, start their B copies
+      for (int sg = 0; sg < C::NST; ++sg) {
+        mbar_wait(empty_bar(sg), phase ^ 1);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(full_bar(sg), C::B_BYTES);
+          bulk_copy(smem_base + sg * C::STAGE + C::A_BYTES, a.Bimg + (size_t)(sg * NKB + kb) * (DP * KB), C::B_BYTES,
+                    full_bar(sg));
+        }
+      }
 #pragma unroll 1
-            for (int sg = 0; sg < C::NSEG; ++sg) {
-              mbar_wait(empty_bar(sg), phase ^ 1);
-              if (tid == 0) {
-                mbar_arrive_expect_tx(full_bar(sg), C::B_BYTES);
-                bulk_copy(smem_base + sg * C::STAGE + C::A_BYTES, a.Bimg + (size_t)(sg * NKB + kb) * (DP * KB), C::B_BYTES,
-                          full_bar(sg));
-              }
-            }
-          }
+      for (int hf = 0; hf < 2; ++hf) {
+        if (hf == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        uint8_t* rw = rawbuf + hf * C::RAW_HALF;
 #pragma unroll
-          for (int ii = 0; ii < 4; ++ii) {
-            const int r = (half * 4 + ii) * 16 + sub;
-            float4 o[6];
-            const float m_ = mu[ii];
-#define MPNN_GD(X)                                                      \
-  {                                                                     \
-    const float r_ = sr[ii].X * m_, z_ = sz[ii].X * m_, n_ = tn[ii].X * m_; \
-    const float go = dv[ii].X * m_;                                     \
-    const float dn = go * (1.f - z_);                                   \
-    const float dz = go * (hv[ii].X - n_);                              \
-    const float dan = dn * m_ * (1.f - tn[ii].X * tn[ii].X);            \
-    const float dr = dan * nh[ii].X;                                    \
-    o[0].X = dr * m_ * sr[ii].X * (1.f - sr[ii].X);                     \
-    o[1].X = dz * m_ * sz[ii].X * (1.f - sz[ii].X);                     \
-    o[2].X = dan;                                                       \
-    o[3].X = dan * r_;                                                  \
-    const float gz = go * z_;                                           \
-    o[4].X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u);        \
-    o[5].X = gz - o[4].X;                                               \
+        for (int ii = 0; ii < 4; ++ii) {
+          const int r = (hf * 4 + ii) * 16 + sub;
+          float4* slot = reinterpret_cast<float4*>(rw + ((ii * 6) * PRODUCERS + tid) * 16);
+          const float4 sr = slot[0 * PRODUCERS], sz = slot[1 * PRODUCERS], tn = slot[2 * PRODUCERS], nh = slot[3 * PRODUCERS],
+                       hv = slot[4 * PRODUCERS], dv = slot[5 * PRODUCERS];
+          const float m_ = *reinterpret_cast<const float*>(rw + C::RAW_ITEMS * PRODUCERS * 16 + (ii * PRODUCERS + tid) * 4);
+          float4 o[6];
+#define MPNN_GD(X)                                              \
+  {                                                             \
+    const float r_ = sr.X * m_, z_ = sz.X * m_, n_ = tn.X * m_; \
+    const float go = dv.X * m_;                                 \
+    const float dn = go * (1.f - z_);                           \
+    const float dz = go * (hv.X - n_);                          \
+    const float dan = dn * m_ * (1.f - tn.X * tn.X);            \
+    const float dr = dan * nh.X;                                \
+    o[0].X = dr * m_ * sr.X * (1.f - sr.X);                     \
+    o[1].X = dz * m_ * sz.X * (1.f - sz.X);                     \
+    o[2].X = dan;                                               \
+    o[3].X = dan * r_;                                          \
+    const float gz = go * z_;                                   \
+    o[4].X = __uint_as_float(__float_as_uint(gz) & 0xffffe000u); \
+    o[5].X = gz - o[4].X;                                       \
   }
-            MPNN_GD(x) MPNN_GD(y) MPNN_GD(z) MPNN_GD(w)
+          MPNN_GD(x) MPNN_GD(y) MPNN_GD(z) MPNN_GD(w)
 #undef MPNN_GD
 #pragma unroll
-            for (int sg = 0; sg < C::NSEG; ++sg) sts4(smem + sg * C::STAGE, swz(r, chunk), o[sg]);
+          for (int sg = 0; sg < C::NST; ++sg) {
+            sts4(smem + sg * C::STAGE, swz(r, chunk), o[sg]);
+            slot[sg * PRODUCERS] = o[3 + sg];
           }
         }
-        fence_proxy_async();
-#pragma unroll 1
-        for (int sg = 0; sg < C::NSEG; ++sg) mbar_arrive(full_bar(sg));
-        phase ^= 1;
       }
+      fence_proxy_async();
+#pragma unroll 1
+      for (int sg = 0; sg < C::NST; ++sg) mbar_arrive(full_bar(sg));
+      phase ^= 1;
+      // ---- pass 1: dnh, hi, lo -> stages 0..2; each raw buffer is refilled with the next group's half once read ----
+#pragma unroll 1
+      for (int sg = 0; sg < C::NST; ++sg) {
+        mbar_wait(empty_bar(sg), phase ^ 1);
+        if (tid == 0) {
+          mbar_arrive_expect_tx(full_bar(sg), C::B_BYTES);
+          bulk_copy(smem_base + sg * C::STAGE + C::A_BYTES, a.Bimg + (size_t)((3 + sg) * NKB + kb) * (DP * KB), C::B_BYTES,
+                    full_bar(sg));
+        }
+      }
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        uint8_t* rw = rawbuf + hf * C::RAW_HALF;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int r = (hf * 4 + ii) * 16 + sub;
+          const float4* slot = reinterpret_cast<const float4*>(rw + ((ii * 6) * PRODUCERS + tid) * 16);
+#pragma unroll
+          for (int sg = 0; sg < C::NST; ++sg) sts4(smem + sg * C::STAGE, swz(r, chunk), slot[sg * PRODUCERS]);
+        }
+        issue_raw(g + 1, hf);
+      }
+      fence_proxy_async();
+#pragma unroll 1
+      for (int sg = 0; sg < C::NST; ++sg) mbar_arrive(full_bar(sg));
+      phase ^= 1;
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -1704,8 +1754,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
         mbar_wait(accempty_bar(acc), (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t dtm = tmem_base + (uint32_t)(acc * DP);
-        for (int kb = 0; kb < nkb; ++kb) {
-          for (int sg = 0; sg < C::NSEG; ++sg) {
+        for (int kp = 0; kp < 2 * nkb; ++kp) {      // (column block, pass)
+          for (int sg = 0; sg < C::NST; ++sg) {
             mbar_wait(full_bar(sg), phase);
             fence_proxy_async();
             tc_fence_after();
@@ -1713,7 +1763,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
             const uint64_t ad = make_sdesc(sa, 16, 1024);
             const uint64_t bd = make_sdesc(sa + C::A_BYTES, 16, 1024);
 #pragma unroll
-            for (int j = 0; j < KB / 8; ++j) umma_tf32(dtm, ad + 2u * j, bd + 2u * j, idesc, (kb | sg | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < KB / 8; ++j) umma_tf32(dtm, ad + 2u * j, bd + 2u * j, idesc, (kp | sg | j) != 0 ? 1u : 0u);
             umma_commit(empty_bar(sg));
           }
           phase ^= 1;
