@@ -328,7 +328,7 @@ def test_aggregation_inside_gru_kernel_is_bit_identical(dev, d, B, monkeypatch):
         assert torch.equal(g1[k], g0[k]), k
 
 
-@pytest.mark.parametrize("rows,d", [(1000, 64), (333, 40), (5000, 64), (77, 36)])
+@pytest.mark.parametrize("rows,d", [(1000, 64), (333, 40), (5000, 64), (77, 36), (5, 64), (130, 44), (40000, 48)])
 def test_gru_backward_one_pass_equals_separate_pointwise(dev, rows, d):
     """widths 33..64: the pointwise GRU backward inside the weight-gradient kernel's producers (mpnn_tc_gru_param_point)
     and of the data-gradient kernel (mpnn_tc_gru_data_grad) against the separate pointwise launch + grouped product:
