@@ -10,7 +10,7 @@
 
 namespace {
 
-constexpr int ADAM_MAXT = 40;        // tensors per launch (pointer table travels as a kernel argument)
+constexpr int ADAM_MAXT = 72;        // tensors per launch (pointer table travels as a kernel argument)
 constexpr int ADAM_BLOCK = 1024;     // elements per CTA (256 threads x 4)
 
 struct AdamPack {
@@ -231,7 +231,7 @@ int mpnn_adam_step(int n, float* const* params, const float* const* grads, float
 // Data-parallel Adam: gradient sum over `world` ranks fused into the step (see k_adam_ddp).  flat / flags: HOST arrays of
 // `world` peer-mapped device pointers (this rank's own buffer at index `rank`); every rank's buffer holds
 // [2][region_floats] floats followed by its flag array [world][n_chunks] (zero on first use); goff[i] = offset of tensor i
-// inside a region (the same on every rank).  All n tensors must fit one launch (n <= 40).  Returns the number of chunks
+// inside a region (the same on every rank).  All n tensors must fit one launch (n <= 72).  Returns the number of chunks
 // (CTAs) when called with params == NULL (sizing query).
 int mpnn_adam_step_ddp(int n, float* const* params, const float* const* grads, float* const* exp_avg,
                        float* const* exp_avg_sq, const long long* numel, const long long* goff, float* step,

@@ -38,8 +38,8 @@ class FusedAdam(torch.optim.Optimizer):
         group = self._ddp_group
         lib = _lib.load()
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        if world > 8 or len(ps) > 40:
-            raise RuntimeError("mpnn_b200.FusedAdam.enable_ddp: at most 8 ranks (one NVSwitch domain) and 40 tensors")
+        if world > 8 or len(ps) > 72:
+            raise RuntimeError("mpnn_b200.FusedAdam.enable_ddp: at most 8 ranks (one NVSwitch domain) and 72 tensors")
         dev = ps[0].device
         goff, o = [], 0
         for p in ps:
