@@ -81,6 +81,53 @@ __global__ void __launch_bounds__(256) k_softmax_mul_bwd(const float* __restrict
   }
 }
 
+// Rows of at most 32 values (the attention gate at nf <= 32, the per-atom readout of config 4 at 16): LANES lanes per
+// row (8, 16 or 32), so a warp handles 32 / LANES rows and nothing is predicated over the 32-slice general form above
+// (102 400 rows of 16 took 137 + 58 us there, one half-empty warp per row walking 32 predicated slices).
+template <int LANES>
+__global__ void __launch_bounds__(256) k_softmax_mul_fwd_small(const float* __restrict__ logits, const float* __restrict__ V,
+                                                               long long rows, int n, float* __restrict__ gate,
+                                                               float* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = t / LANES;
+  const int o = (int)(t % LANES);
+  const bool ok = row < rows && o < n;
+  float v = ok ? logits[row * n + o] : -INFINITY;
+  float mx = v;
+#pragma unroll
+  for (int w = LANES / 2; w > 0; w >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, w));
+  const float e = ok ? expf(v - mx) : 0.f;
+  float den = e;
+#pragma unroll
+  for (int w = LANES / 2; w > 0; w >>= 1) den += __shfl_xor_sync(0xffffffffu, den, w);
+  if (ok) {
+    const float g = e / den;
+    if (gate) gate[row * n + o] = g;
+    out[row * n + o] = V ? g * V[row * n + o] : g;
+  }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(256) k_softmax_mul_bwd_small(const float* __restrict__ gate, const float* __restrict__ V,
+                                                               const float* __restrict__ dout, long long rows, int n,
+                                                               float* __restrict__ dlogits, float* __restrict__ dV) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = t / LANES;
+  const int o = (int)(t % LANES);
+  const bool ok = row < rows && o < n;
+  float g = 0.f, dg = 0.f;
+  if (ok) {
+    g = gate[row * n + o];
+    const float d = dout[row * n + o];
+    dg = V ? d * V[row * n + o] : d;
+    if (dV) dV[row * n + o] = d * g;
+  }
+  float dot = dg * g;
+#pragma unroll
+  for (int w = LANES / 2; w > 0; w >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, w);
+  if (ok) dlogits[row * n + o] = g * (dg - dot);
+}
+
 // out[r,k] = sum_j w[r,j] * m[r,j,k]
 __global__ void k_dense_agg_fwd(const float* __restrict__ m, const float* __restrict__ w, long long R, int N, int mf,
                                 float* __restrict__ out) {
@@ -125,7 +172,10 @@ int mpnn_softmax_mul_fwd(const float* logits, const float* V, long long rows, in
                          cudaStream_t stream) {
   MPNN_REQUIRE(rows >= 0 && n > 0 && n <= 32 * KMAX, MPNN_ERR_ARG, "softmax_mul_fwd: bad dims rows=%lld n=%d", rows, n);
   if (rows == 0) return MPNN_OK;
-  k_softmax_mul_fwd<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(logits, V, rows, n, gate, out);
+  if (n <= 8) k_softmax_mul_fwd_small<8><<<ceil_div(rows * 8, 256), 256, 0, stream>>>(logits, V, rows, n, gate, out);
+  else if (n <= 16) k_softmax_mul_fwd_small<16><<<ceil_div(rows * 16, 256), 256, 0, stream>>>(logits, V, rows, n, gate, out);
+  else if (n <= 32) k_softmax_mul_fwd_small<32><<<ceil_div(rows * 32, 256), 256, 0, stream>>>(logits, V, rows, n, gate, out);
+  else k_softmax_mul_fwd<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(logits, V, rows, n, gate, out);
   MPNN_CHECK_LAUNCH("k_softmax_mul_fwd");
   return MPNN_OK;
 }
@@ -134,7 +184,10 @@ int mpnn_softmax_mul_bwd(const float* gate, const float* V, const float* dout, l
                          float* dV, cudaStream_t stream) {
   MPNN_REQUIRE(rows >= 0 && n > 0 && n <= 32 * KMAX, MPNN_ERR_ARG, "softmax_mul_bwd: bad dims");
   if (rows == 0) return MPNN_OK;
-  k_softmax_mul_bwd<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(gate, V, dout, rows, n, dlogits, dV);
+  if (n <= 8) k_softmax_mul_bwd_small<8><<<ceil_div(rows * 8, 256), 256, 0, stream>>>(gate, V, dout, rows, n, dlogits, dV);
+  else if (n <= 16) k_softmax_mul_bwd_small<16><<<ceil_div(rows * 16, 256), 256, 0, stream>>>(gate, V, dout, rows, n, dlogits, dV);
+  else if (n <= 32) k_softmax_mul_bwd_small<32><<<ceil_div(rows * 32, 256), 256, 0, stream>>>(gate, V, dout, rows, n, dlogits, dV);
+  else k_softmax_mul_bwd<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(gate, V, dout, rows, n, dlogits, dV);
   MPNN_CHECK_LAUNCH("k_softmax_mul_bwd");
   return MPNN_OK;
 }

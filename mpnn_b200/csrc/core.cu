@@ -87,20 +87,35 @@ __global__ void k_colsum_partial(const float* __restrict__ X, const float* __res
     partial[(size_t)blockIdx.x * width + c] = s;
   }
 }
-__global__ void k_colsum_final(const float* __restrict__ partial, int nblk, int width, float* __restrict__ out,
-                               int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= width) return;
+// A block is 32 columns x 8 slices of the partials: slice sl sums blocks sl, sl + 8, ... with four loads in flight, the
+// eight slice sums are added in slice order (fixed order: bit-reproducible).  (One thread per column walking all the
+// partials took 41 us for the 16 columns of config 4's per-atom tensors: 16 threads, thousands of dependent round trips.)
+__global__ void __launch_bounds__(256) k_colsum_final(const float* __restrict__ partial, int nblk, int width,
+                                                      float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int b0 = 0; b0 < nblk; b0 += 8) {   // eight loads in flight, added in block order (a load-add loop is one L2 round
-    float v[8];                             // trip per block: 35 us for 1 184 partials)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = b0 + k < nblk ? partial[(size_t)(b0 + k) * width + c] : 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (b0 + k < nblk) s += v[k];
+  if (c < width) {
+    int b = sl;
+    for (; b + 24 < nblk; b += 32) {
+      const float v0 = partial[(size_t)b * width + c], v1 = partial[(size_t)(b + 8) * width + c],
+                  v2 = partial[(size_t)(b + 16) * width + c], v3 = partial[(size_t)(b + 24) * width + c];
+      s += v0;
+      s += v1;
+      s += v2;
+      s += v3;
+    }
+    for (; b < nblk; b += 8) s += partial[(size_t)b * width + c];
   }
-  out[c] = accumulate ? out[c] + s : s;
+  red[sl][cx] = s;
+  __syncthreads();
+  if (sl == 0 && c < width) {
+    float t = red[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][cx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // float4 form (width, lds, ldo multiples of 4, 16-byte aligned bases): one thread per (row, 4 columns); four
@@ -252,7 +267,7 @@ int mpnn_colsum(const float* X, const float* Y, long long rows, int width, long 
                                                                         (float*)workspace);
     MPNN_CHECK_LAUNCH("k_colsum_partial");
   }
-  k_colsum_final<<<ceil_div(width, 128), 128, 0, stream>>>((const float*)workspace, nblk, width, out, accumulate);
+  k_colsum_final<<<ceil_div(width, 32), 256, 0, stream>>>((const float*)workspace, nblk, width, out, accumulate);
   MPNN_CHECK_LAUNCH("k_colsum_final");
   return MPNN_OK;
 }
