@@ -8,8 +8,9 @@ import bench
 from mpnn_b200 import _lib, graph
 
 dev = torch.device("cuda:0")
-w = dict(bench.WORKLOADS["qm9"])
-batch = bench.make_workload_batch("qm9", w, 0)
+cfg = sys.argv[1] if len(sys.argv) > 1 else "qm9"
+w = dict(bench.WORKLOADS[cfg])
+batch = bench.make_workload_batch(cfg, w, 0)
 t = {k: torch.from_numpy(batch[k]).to(dev) for k in ("afm", "bfm", "adj", "mask")}
 body, head = bench.build_model(w, dev)
 lib = _lib.load()
