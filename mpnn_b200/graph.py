@@ -272,7 +272,7 @@ class TypedInfo(object):
 
 
 SORT_ON_SIDE_STREAM = os.environ.get("MPNN_B200_SORT_SIDE_STREAM", "1") != "0"
-TYPED_MAX_UNIQUE = 1024   # beyond this many distinct bond rows the per-edge contraction (csrc/message.cu) is used
+TYPED_MAX_UNIQUE = int(os.environ.get("MPNN_B200_TYPED_MAX_UNIQUE", "1024"))   # beyond this many distinct bond rows the per-edge contraction (csrc/message.cu) is used
 
 
 def dedup_rows(el, unique_capacity=None):
