@@ -9,7 +9,7 @@
 // This is the same contraction as csrc/message.cu (edge-embedding (x) neighbour-state against the shared weight),
 // with the contraction over p hoisted out of the per-edge work: exact, because x depends on the bond row only.
 // Per-edge d x d matrices are never formed; the table has one matrix per distinct bond row (a few dozen).
-// Feature widths up to 32 run here on CUDA cores (HBM/L1-bound gather); wider states use csrc/typed_mma.cu.
+// Feature widths up to 32 run here on CUDA cores (HBM/L1-bound gather); wider states use csrc/tc_message.cu (tcgen05).
 //
 // All reductions have a fixed order (CSC lists, type-sorted chunks): results are bit-reproducible.
 #include "common.cuh"
