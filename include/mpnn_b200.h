@@ -184,6 +184,8 @@ int mpnn_tc_gru_param_grad(const float* m, const float* h, const float* dg, int 
  * [mpnn_tc_gru_param_bias_parts()][4d] and dW_ih, dW_hh. */
 /* GRU data gradients for widths <= 64 straight from the saved gates (no gate-gradient array in HBM):
  * (dm | dh) = (dar|daz|dan|dnh|hi(go z)|lo(go z)) x Wc, Wc = combined weights [6][2d][d] (device). */
+/* profiling aid: DEVICE buffer of 64 x uint64 receiving %globaltimer stamps of k_tc_gru_data_grad's producer; NULL = off */
+void mpnn_tc_debug(unsigned long long* buf);
 size_t mpnn_tc_gru_data_workspace_bytes(void);
 int mpnn_tc_gru_data_grad(const float* gates, const float* h, const float* dh_out, const float* mask, const float* Wc,
                           long long rows, int d, float* dm, float* dh, void* workspace, size_t workspace_bytes,

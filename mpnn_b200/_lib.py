@@ -76,6 +76,7 @@ SIGNATURES = {
     "mpnn_tc_dense_gemm_ll": (_I, [_P, _L, _I, _I, _I, _I, _P, _L, _L, _L, _L, _I, _I, _P, _P, _I, _L, _I, _I, _I, _P, _Z, _P]),
     "mpnn_tc_gru_param_workspace_bytes": (_Z, []),
     "mpnn_tc_gru_param_bias_parts": (_I, []),
+    "mpnn_tc_debug": (None, [_P]),
     "mpnn_tc_gru_data_workspace_bytes": (_Z, []),
     "mpnn_tc_gru_data_grad": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _Z, _P]),
     "mpnn_tc_gru_param_point": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _Z, _P]),

@@ -1569,6 +1569,7 @@ struct TcGruData {
   float *dm, *dh;
   long long rows;
   int d;
+  unsigned long long* dbg;   // profiling aid (mpnn_tc_debug): %globaltimer stamps of CTA 0's producer thread 0
 };
 struct GdCfg {
   static constexpr int DP = 128;
@@ -1662,8 +1663,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
     issue_raw(0, 0);
     issue_raw(0, 1);
     int phase = 0;
+    int ds = 0;
+    auto stamp = [&]() {
+      if (a.dbg && blockIdx.x == 0 && tid == 0 && ds < 64) {
+        unsigned long long tt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        a.dbg[ds] = tt;
+      }
+      ++ds;
+    };
     for (int g = 0; g < n_groups; ++g) {
       const int kb = g % nkb;
+      stamp();
       // ---- pass 0: dar, daz, dan -> stages 0..2; dnh, hi, lo -> back into the raw slots ----
 #pragma unroll 1
       for (int sg = 0; sg < C::NST; ++sg) {
@@ -1674,10 +1685,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
                     full_bar(sg));
         }
       }
+      stamp();
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         if (hf == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        stamp();
         uint8_t* rw = rawbuf + hf * C::RAW_HALF;
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
@@ -1712,6 +1725,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
           }
         }
       }
+      stamp();
       fence_proxy_async();
 #pragma unroll 1
       for (int sg = 0; sg < C::NST; ++sg) mbar_arrive(full_bar(sg));
@@ -1726,6 +1740,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_gru_data_grad(TcGruData a) {
                     full_bar(sg));
         }
       }
+      stamp();
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         uint8_t* rw = rawbuf + hf * C::RAW_HALF;
@@ -1895,6 +1910,7 @@ __global__ void __launch_bounds__(256) k_tc_pack_image(const float* __restrict__
 // Process-wide precision switch (mpnn_set_tensor_cores): with the tensor cores off every width is served by the fp32
 // kernels (per-edge contraction, tile GEMMs), at fp32 accuracy and a fraction of the speed.
 int g_tc_enabled = 1;
+unsigned long long* g_tc_dbg = nullptr;
 
 int tc_dp(int nf, int mf) {
   int d = nf > mf ? nf : mf;
@@ -2355,6 +2371,10 @@ int mpnn_tc_gru_param_point(const float* m, const float* h, const float* mask, c
   return MPNN_OK;
 }
 
+// profiling aid: DEVICE buffer of 64 x uint64 that receives %globaltimer stamps of k_tc_gru_data_grad's producer (CTA 0,
+// thread 0; seven per group: start, stages free, half 0 landed, half 1 landed, converted, pass-1 stages free, ...); NULL = off
+void mpnn_tc_debug(unsigned long long* buf) { g_tc_dbg = buf; }
+
 // GRU data gradients for widths <= 64 straight from the saved gates (k_tc_gru_data_grad): dm, dh [rows, d].
 // Wc: the combined weights [6][2d][d] (rows [0,d) of a block -> dm, [d,2d) -> dh; blocks = dar | daz | dan | dnh | I | I).
 size_t mpnn_tc_gru_data_workspace_bytes(void) { return (size_t)6 * 128 * 128 * sizeof(float); }
@@ -2372,7 +2392,7 @@ int mpnn_tc_gru_data_grad(const float* gates, const float* h, const float* dh_ou
   k_tc_pack_image<<<ceil_div(6LL * 128 * 128, 256), 256, 0, stream>>>(Wc, d, 1, 0, (long long)2 * d * d, 6, 6, 2 * d, d, 128,
                                                                      img);
   MPNN_CHECK_LAUNCH("k_tc_pack_image");
-  TcGruData a = {gates, h, dh_out, mask, img, dm, dh, rows, d};
+  TcGruData a = {gates, h, dh_out, mask, img, dm, dh, rows, d, g_tc_dbg};
   const long long tiles = (rows + TILE - 1) / TILE;
   const int grid = (int)(tiles < tc_grid() ? tiles : tc_grid());
   MPNN_REQUIRE(set_smem(k_tc_gru_data_grad, GdCfg::SMEM) == 0, MPNN_ERR_CUDA, "tc_gru_data_grad: smem attribute");
