@@ -321,6 +321,14 @@ size_t mpnn_glo_workspace_bytes(int B, int N, int F2, int O);
 int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float* bi, const float* Wj, const float* bj,
                  int B, int N, int F2, int O, float* out, float* u, float* v, float* UV, void* workspace,
                  size_t workspace_bytes, mpnn_stream_t stream);
+/* The fused masked backward (O <= 64, F2 <= 64) as two calls: the data half writes dx and per-CTA partials into the
+ * workspace, the parameter half reduces them (fixed order); the caller may enqueue the second on another stream. */
+int mpnn_glo_bwd_split_supported(int has_mask, int F2, int O);
+int mpnn_glo_bwd_data(const float* x, const float* mask, const float* Wi, const float* Wj, const float* u, const float* v,
+                      const float* dout, int B, int N, int F2, int O, float* dx, void* workspace, size_t workspace_bytes,
+                      mpnn_stream_t stream);
+int mpnn_glo_bwd_params(const void* workspace, int B, int N, int F2, int O, float* dWi, float* dbi, float* dWj, float* dbj,
+                        mpnn_stream_t stream);
 int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float* Wj, const float* u, const float* v,
                  const float* UV, const float* dout, int B, int N, int F2, int O, float* dx, float* dWi, float* dbi,
                  float* dWj, float* dbj, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);

@@ -677,6 +677,34 @@ int mpnn_glo_fwd(const float* x, const float* mask, const float* Wi, const float
   return MPNN_OK;
 }
 
+// The fused masked backward (O <= 64, F2 <= 64) in two calls, so that the caller can put the parameter half on another
+// stream: `mpnn_glo_bwd_data` writes dx and the per-CTA partials into the workspace, `mpnn_glo_bwd_params` reduces them in
+// fixed order into dWi / dbi / dWj / dbj (only parameter gradients: nothing downstream of the readout waits for it).
+int mpnn_glo_bwd_split_supported(int has_mask, int F2, int O) { return (has_mask && O <= FO && F2 <= FO) ? 1 : 0; }
+
+int mpnn_glo_bwd_data(const float* x, const float* mask, const float* Wi, const float* Wj, const float* u, const float* v,
+                      const float* dout, int B, int N, int F2, int O, float* dx, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && N > 0 && mpnn_glo_bwd_split_supported(mask != nullptr, F2, O), MPNN_ERR_UNSUPPORTED,
+               "glo_bwd_data: shape not served by the fused kernel");
+  MPNN_REQUIRE(workspace_bytes >= mpnn_glo_workspace_bytes(B, N, F2, O), MPNN_ERR_WORKSPACE, "glo_bwd_data: workspace");
+  const long long rows = (long long)B * N;
+  const int grid = glo_bwd_grid(rows);
+  k_glo_bwd_fused<<<grid, 256, 0, stream>>>(x, mask, Wi, Wj, u, v, dout, B, N, F2, O, dx, (float*)workspace);
+  MPNN_CHECK_LAUNCH("k_glo_bwd_fused");
+  return MPNN_OK;
+}
+
+int mpnn_glo_bwd_params(const void* workspace, int B, int N, int F2, int O, float* dWi, float* dbi, float* dWj, float* dbj,
+                        cudaStream_t stream) {
+  MPNN_REQUIRE(B > 0 && N > 0 && mpnn_glo_bwd_split_supported(1, F2, O), MPNN_ERR_UNSUPPORTED, "glo_bwd_params: shape");
+  const int grid = glo_bwd_grid((long long)B * N);
+  k_glo_bwd_reduce<<<ceil_div(2 * O * F2 + 2 * O, 32), 256, 0, stream>>>((const float*)workspace, grid, F2, O, dWi, dWj, dbi,
+                                                                        dbj);
+  MPNN_CHECK_LAUNCH("k_glo_bwd_reduce");
+  return MPNN_OK;
+}
+
 int mpnn_glo_bwd(const float* x, const float* mask, const float* Wi, const float* Wj, const float* u, const float* v,
                  const float* UV, const float* dout, int B, int N, int F2, int O, float* dx, float* dWi, float* dbi,
                  float* dWj, float* dbj, void* workspace, size_t workspace_bytes, cudaStream_t stream) {

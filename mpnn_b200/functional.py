@@ -603,6 +603,7 @@ class GraphLevelOutputFn(torch.autograd.Function):
     def forward(ctx, x, mask, Wi, bi, Wj, bj):
         lib = _lib.load()
         _need_cuda(x, Wi)
+        params = (Wi, bi, Wj, bj)
         x = f32c(x)
         mask_c = f32c(mask) if mask is not None else None
         Wi, bi, Wj, bj = f32c(Wi), f32c(bi), f32c(Wj), f32c(bj)
@@ -617,6 +618,7 @@ class GraphLevelOutputFn(torch.autograd.Function):
         check(lib.mpnn_glo_fwd(ptr(x), ptr(mask_c), ptr(Wi), ptr(bi), ptr(Wj), ptr(bj), B, N, F2, O, ptr(out), ptr(u),
                                ptr(v), ptr(UV), ptr(ws), ws.numel(), stream()), "glo_fwd")
         ctx.save_for_backward(x, mask_c, Wi, Wj, u, v, UV)
+        ctx.params = params
         return out
 
     @staticmethod
@@ -633,6 +635,18 @@ class GraphLevelOutputFn(torch.autograd.Function):
         dbi = torch.empty(O, dtype=torch.float32, device=dev)
         dbj = torch.empty(O, dtype=torch.float32, device=dev)
         ws = workspace(lib.mpnn_glo_workspace_bytes(B, N, F2, O), dev)
+        if lib.mpnn_glo_bwd_split_supported(int(mask is not None), F2, O):
+            # dx continues the main backward chain; the reduction of the weight-gradient partials feeds parameter gradients
+            # only: inside a captured step it is a side branch (when autograd will ASSIGN those gradients, see
+            # EdgeNetTableFn.backward)
+            check(lib.mpnn_glo_bwd_data(ptr(x), ptr(mask), ptr(Wi), ptr(Wj), ptr(u), ptr(v), ptr(dout), B, N, F2, O, ptr(dx),
+                                        ptr(ws), ws.numel(), stream()), "glo_bwd_data")
+            side = (_side_ok() and all(ctx.needs_input_grad[2:6])
+                    and all(getattr(t, "grad", None) is None for t in ctx.params))
+            with (_on_side_stream(dev, [ws], lane=7) if side else _inline()):
+                check(lib.mpnn_glo_bwd_params(ptr(ws), B, N, F2, O, ptr(dWi), ptr(dbi), ptr(dWj), ptr(dbj), stream()),
+                      "glo_bwd_params")
+            return dx, None, dWi, dbi, dWj, dbj
         check(lib.mpnn_glo_bwd(ptr(x), ptr(mask), ptr(Wi), ptr(Wj), ptr(u), ptr(v), ptr(UV), ptr(dout), B, N, F2, O,
                                ptr(dx), ptr(dWi), ptr(dbi), ptr(dWj), ptr(dbj), ptr(ws), ws.numel(), stream()),
               "glo_bwd")
