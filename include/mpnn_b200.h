@@ -308,6 +308,16 @@ int mpnn_mask_bn_fwd(const float* x, const float* mask, long long rows, int C, f
                      void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
 int mpnn_mask_bn_bwd(const float* x, const float* mask, const float* dy, const float* stats, long long rows, int C,
                      float* dx, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* Masked batch norms of a categorical bond tensor in row space (graph.TypedBonds): x [R,F] distinct rows, a [R] their mask
+ * (adjacency) values, cnt [R] their multiplicities.  masked_mean 1 / eps_inside 0 = MaskBatchNorm1d (mask_batch_norm.py:20-38),
+ * masked_mean 0 / eps_inside 1 = MaskBatchNorm (:9-15).  stats [3F+1] is saved for the backward; gamma, beta, running_*,
+ * dx, dgamma, dbeta may be NULL. */
+int mpnn_row_bn_fwd(const float* x, const float* a, const float* cnt, int R, int F, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, int masked_mean, int eps_inside, int training,
+                    float momentum, float eps, float* y, float* stats, mpnn_stream_t stream);
+int mpnn_row_bn_bwd(const float* x, const float* a, const float* cnt, int R, int F, const float* gamma, const float* stats,
+                    const float* dy, int masked_mean, int eps_inside, int training, float* dx, float* dgamma,
+                    float* dbeta, mpnn_stream_t stream);
 int mpnn_mask_bn1d_fwd(const float* x, const float* mask, const float* weight, const float* bias, float* running_mean,
                        float* running_var, long long rows, int C, int training, float momentum, float eps, float* y,
                        float* stats, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);

@@ -111,6 +111,8 @@ SIGNATURES = {
     "mpnn_mask_bn1d_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "mpnn_glo_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "mpnn_glo_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "mpnn_row_bn_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P, _P]),
+    "mpnn_row_bn_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "mpnn_glo_bwd_split_supported": (_I, [_I, _I, _I]),
     "mpnn_glo_bwd_data": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "mpnn_glo_bwd_params": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

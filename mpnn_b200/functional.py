@@ -544,6 +544,46 @@ class MaskBNFn(torch.autograd.Function):
         return dx, None, None
 
 
+class TypedRowBNFn(torch.autograd.Function):
+    """Masked batch norm of a categorical bond tensor in row space (csrc/bn.cu k_row_bn_*): rows [R, F] distinct rows,
+    a [R] their mask (adjacency) values, cnt [R] their multiplicities (data, not differentiated).  `bn1d` selects
+    MaskBatchNorm1d's arithmetic (masked mean, eps outside the root, affine, running statistics: mask_batch_norm.py:20-38),
+    else MaskBatchNorm's (:9-15)."""
+
+    @staticmethod
+    def forward(ctx, rows, a, cnt, gamma, beta, running_mean, running_var, bn1d, training, momentum, eps):
+        lib = _lib.load()
+        _need_cuda(rows, a, cnt)
+        rows, a, cnt = f32c(rows), f32c(a), f32c(cnt)
+        gamma_c = f32c(gamma) if gamma is not None else None
+        beta_c = f32c(beta) if beta is not None else None
+        R, F = rows.shape
+        y = torch.empty_like(rows)
+        stats = torch.empty(3 * F + 1, dtype=torch.float32, device=rows.device)
+        check(lib.mpnn_row_bn_fwd(ptr(rows), ptr(a), ptr(cnt), R, F, ptr(gamma_c), ptr(beta_c), ptr(running_mean),
+                                  ptr(running_var), int(bn1d), int(not bn1d), int(training), float(momentum or 0.0),
+                                  float(eps), ptr(y), ptr(stats), stream()), "row_bn_fwd")
+        ctx.save_for_backward(rows, a, cnt, gamma_c, stats)
+        ctx.cfg = (int(bn1d), int(training), beta is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        rows, a, cnt, gamma, stats = ctx.saved_tensors
+        bn1d, training, has_beta = ctx.cfg
+        R, F = rows.shape
+        dy = f32c(dy)
+        dev = rows.device
+        dx = torch.empty_like(rows) if ctx.needs_input_grad[0] else None
+        dgamma = torch.empty(F, dtype=torch.float32, device=dev) if gamma is not None else None
+        dbeta = torch.empty(F, dtype=torch.float32, device=dev) if has_beta else None
+        check(lib.mpnn_row_bn_bwd(ptr(rows), ptr(a), ptr(cnt), R, F, ptr(gamma), ptr(stats), ptr(dy), bn1d, int(not bn1d),
+                                  training, ptr(dx), ptr(dgamma), ptr(dbeta), stream()), "row_bn_bwd")
+        return dx, None, None, dgamma, dbeta, None, None, None, None, None, None
+
+
 class MaskBN1dFn(torch.autograd.Function):
     """reference mask_batch_norm.py:20-38; running buffers are updated in place when training."""
 

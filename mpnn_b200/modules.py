@@ -15,7 +15,7 @@ from .functional import (BilinearEdgeFn, ChainFn, DenseAggFn, MultiEdgeNetTableF
                          Set2VecFn, SoftmaxMulFn,
                          TableLayoutFn, TypedMessageFn, TypedMessageTCFn, chain_supported, table_dp, tc_dp, typed_dp)
 from . import _lib
-from .functional import _note_forward_side_work, _side_stream, real_rows, TypeGatherFn
+from .functional import _note_forward_side_work, _side_stream, real_rows, TypeGatherFn, TypedRowBNFn
 import os
 import weakref
 
@@ -595,16 +595,25 @@ def _as_dense(messages):
     return messages.materialize() if isinstance(messages, _LazyTensor) else messages
 
 
-def _typed_mask_bn(tb, mask, stats_fn):
+def _typed_mask_bn(tb, mask, bn1d, module=None, eps=1e-6):
     """Adjacency-masked batch norm of a TypedBonds tensor in row space: every sum over the B N^2 rows of the dense
-    tensor is a count-weighted sum over the distinct rows (count c_u, mask value a_u).  `stats_fn(x, a, c, M)` returns
-    the normalised rows; autograd differentiates the few [R, F] torch ops."""
+    tensor is a count-weighted sum over the distinct rows (count c_u, mask value a_u) -- one launch each way
+    (`functional.TypedRowBNFn`, csrc/bn.cu k_row_bn_*).  bn1d: MaskBatchNorm1d `module` (mask_batch_norm.py:20-38), else
+    MaskBatchNorm (:9-15) with `eps`.  None when the mask is not the adjacency the rows were typed with."""
     if graph._key(mask) != tb._adj_key:
         return None
-    a = tb._a.unsqueeze(1)
-    c = tb._cnt.unsqueeze(1)
-    M = (tb._cnt * tb._a).sum()
-    return tb.with_rows(stats_fn(tb._rows, a, c, M))
+    if not bn1d:
+        y = TypedRowBNFn.apply(tb._rows, tb._a, tb._cnt, None, None, None, None, False, True, 0.0, eps)
+        return tb.with_rows(y)
+    m = module
+    training = m.training or not m.track_running_stats
+    if m.momentum is None and training and m.track_running_stats:
+        return None          # cumulative moving average: not served in row space (dense kernels)
+    track = m.track_running_stats
+    y = TypedRowBNFn.apply(tb._rows, tb._a, tb._cnt, m.weight if m.affine else None, m.bias if m.affine else None,
+                           m.running_mean if track else None, m.running_var if track else None, True, training,
+                           m.momentum, m.eps)
+    return tb.with_rows(y)
 
 
 class LazyAgg(_LazyTensor):
@@ -1002,11 +1011,7 @@ class MaskBatchNorm(nn.Module):
         if isinstance(tensor, DeferredRows):
             tensor = tensor.resolve(mask)
         if isinstance(tensor, graph.TypedBonds):
-            def stats(x, a, c, M):   # mask_batch_norm.py:11-15 (unmasked sum for the mean)
-                mean = (c * x).sum(0) / M
-                var = (c * ((x - mean) * a) ** 2).sum(0) / M
-                return (x - mean) * a / torch.sqrt(var + eps)
-            out = _typed_mask_bn(tensor, mask, stats)
+            out = _typed_mask_bn(tensor, mask, False, eps=eps)    # mask_batch_norm.py:11-15 on the distinct rows
             if out is not None:
                 return out
         tensor = _as_dense(tensor)
@@ -1016,21 +1021,7 @@ class MaskBatchNorm(nn.Module):
 
 class MaskBatchNorm1d(nn.BatchNorm1d):
     def _typed_forward(self, tb, mask):
-        def stats(x, a, c, M):   # mask_batch_norm.py:20-38 on the distinct rows
-            mean = (c * a * x).sum(0) / M
-            var = (c * ((x - mean) * a) ** 2).sum(0) / M
-            if not self.training and self.track_running_stats:
-                y = (x - self.running_mean) / (self.running_var ** .5 + self.eps)
-            else:
-                if self.track_running_stats:
-                    with torch.no_grad():
-                        self.running_mean.mul_(1 - self.momentum).add_(self.momentum * mean)
-                        self.running_var.mul_(1 - self.momentum).add_(self.momentum * var)
-                y = (x - mean) / (var.sqrt() + self.eps)
-            if self.affine:
-                y = self.weight * y + self.bias
-            return y * a
-        return _typed_mask_bn(tb, mask, stats)
+        return _typed_mask_bn(tb, mask, True, module=self)    # mask_batch_norm.py:20-38 on the distinct rows
 
     def forward(self, tensor, mask):
         if isinstance(tensor, LazyState) and tensor._kind == "gru" and tensor._value is None and tensor._mask is mask:

@@ -255,3 +255,52 @@ def test_encoded_step_is_graph_capturable(dev):
             gs.check()
         losses[mode] = ls
     assert np.allclose(losses["eager"], losses["graph"], rtol=2e-3, atol=1e-6), losses
+
+
+@pytest.mark.parametrize("bn1d,training", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("R,F", [(7, 2), (33, 8), (300, 5)])
+def test_row_space_batch_norm_kernel(dev, bn1d, training, R, F):
+    """functional.TypedRowBNFn (csrc/bn.cu k_row_bn_*: the masked batch norms of mask_batch_norm.py on R distinct rows with
+    multiplicities) against the same formulas evaluated by torch autograd in fp64"""
+    from mpnn_b200.functional import TypedRowBNFn
+    g = torch.Generator().manual_seed(R * 7 + F)
+    x = torch.randn(R, F, generator=g) * 2 + 0.5
+    a = (torch.rand(R, generator=g) > 0.2).float() * (1 + torch.rand(R, generator=g))
+    a[0] = 1.0
+    cnt = torch.randint(1, 50, (R,), generator=g).float()
+    gamma, beta = torch.rand(F, generator=g) + 0.5, torch.randn(F, generator=g) * 0.1
+    rm, rv = torch.randn(F, generator=g) * 0.1, torch.rand(F, generator=g) + 0.5
+    cot = torch.randn(R, F, generator=g)
+    eps, mom = (1e-5, 0.1) if bn1d else (1e-6, 0.0)
+
+    xd, gd, bd = x.double().requires_grad_(True), gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ad, cd = a.double().unsqueeze(1), cnt.double().unsqueeze(1)
+    Mtot = (cd * ad).sum()
+    if bn1d:
+        if training:
+            mean = (cd * ad * xd).sum(0) / Mtot
+            var = (cd * ((xd - mean) * ad) ** 2).sum(0) / Mtot
+            yr = (xd - mean) / (var.sqrt() + eps)
+        else:
+            mean, var = rm.double(), rv.double()
+            yr = (xd - mean) / (var ** .5 + eps)
+        yr = (gd * yr + bd) * ad
+    else:
+        mean = (cd * xd).sum(0) / Mtot
+        var = (cd * ((xd - mean) * ad) ** 2).sum(0) / Mtot
+        yr = (xd - mean) * ad / torch.sqrt(var + eps)
+    (yr * cot.double()).sum().backward()
+
+    xg = x.to(dev).requires_grad_(True)
+    gg, bg = gamma.to(dev).requires_grad_(True), beta.to(dev).requires_grad_(True)
+    rm_d, rv_d = rm.clone().to(dev), rv.clone().to(dev)
+    y = TypedRowBNFn.apply(xg, a.to(dev), cnt.to(dev), gg if bn1d else None, bg if bn1d else None,
+                           rm_d if bn1d else None, rv_d if bn1d else None, bn1d, training, mom, eps)
+    (y * cot.to(dev)).sum().backward()
+    assert rel_err(y.cpu(), yr.detach()) <= 1e-5
+    assert rel_err(xg.grad.cpu(), xd.grad) <= 2e-4
+    if bn1d:
+        assert rel_err(gg.grad.cpu(), gd.grad) <= 1e-4 and rel_err(bg.grad.cpu(), bd.grad) <= 1e-4
+        if training:
+            assert rel_err(rm_d.cpu(), (0.9 * rm.double() + 0.1 * mean.detach())) <= 1e-5
+            assert rel_err(rv_d.cpu(), (0.9 * rv.double() + 0.1 * var.detach())) <= 1e-5
