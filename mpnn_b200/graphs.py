@@ -18,7 +18,9 @@ class GraphedStep(object):
     """Captures `step_fn(inputs) -> loss` (which does zero_grad / backward / optimizer.step itself) into a CUDA
     graph over static copies of `example_inputs` (dict of CUDA tensors; all later batches must have these shapes).
 
-        gs = GraphedStep(step_fn, batch)        # 3 eager warm-up steps on a side stream, then capture
+        gs = GraphedStep(step_fn, batch)        # 3 eager warm-up steps on a side stream + 1 eager dry run with the
+                                                # captured array sizes (it sizes the zero-buffer arena), then capture:
+                                                # step_fn has run `gs.eager_steps` times when the constructor returns
         loss = gs(batch)                        # copies the batch into the static buffers, replays
         gs.check()                              # raises if a batch overflowed the captured capacities
     """
