@@ -107,3 +107,27 @@ def test_persistent_against_oracle(dev):
     assert rel_err(dX.cpu(), x.grad) <= 1e-3
     for k, g in grads.items():
         assert rel_err(g.cpu(), sd[k].grad) <= 2e-3, k
+
+
+def test_persistent_without_mask(dev):
+    """Set2Vec.forward(input_set) with mask=None (set2vec.py:120: no -1e8 term): persistent == per-iteration"""
+    from mpnn_b200 import functional, modules as M
+    torch.manual_seed(4)
+    mod = M.Set2Vec(8, 99, time_steps=9).to(dev)
+    X = torch.randn(20, 11, 16, generator=torch.Generator().manual_seed(1)).to(dev)
+    res = []
+    for persistent in (True, False):
+        prev = functional.set2vec_persistent(persistent)
+        try:
+            mod.zero_grad()
+            x = X.clone().requires_grad_(True)
+            out = mod(x)
+            out.pow(2).sum().backward()
+            torch.cuda.synchronize()
+            res.append((out.detach(), x.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters()}))
+        finally:
+            functional.set2vec_persistent(prev)
+    a, b = res
+    assert rel_err(a[0], b[0]) <= 2e-5 and rel_err(a[1], b[1]) <= 2e-4
+    for k in b[2]:
+        assert rel_err(a[2][k], b[2][k]) <= 5e-4, k
