@@ -488,7 +488,8 @@ def mp_step_roofline(tag, body, devb, flush, n, e, T, P, n_bn):
             def fwd():
                 return Fn.ChainFn.apply(h0, h0, m1, el, bn, *(ws + tl + tlT))
         else:
-            kernels = "k_tc_edge_gemm + k_segment_sum + k_tc_gru_fwd | k_tc_* backward GEMMs, table gradient"
+            kernels = ("k_tc_edge_gemm -> k_tc_gru_fwd (aggregation + GRU) | k_tc_gru_param_point + k_tc_gru_data_grad (d <= 64; "
+                       "k_gru_point_bwd5 + grouped products above), k_tc_table_grad")
 
             # as modules._wide_chain runs it: on the real rows only (the gather / scatter of the node tensors happens
             # once per forward pass, outside the step)
@@ -522,7 +523,12 @@ def mp_step_roofline(tag, body, devb, flush, n, e, T, P, n_bn):
     t_tc = 3.0 * F / (peaks["bf16_tflops"] * 1e12)
     frac = t_hbm / t_step
     ours_bytes = (12.0 * e + 4.0 * n + 12.0 * n * d + 16.0 * n * d * n_bn) * 2.5   # typed formulation: uid instead of x_e rows
-    return {"what": "one message-passing step, forward + backward (SURVEY 8d), " + tag, "kernels": kernels,
+    extra = {}
+    if frac > 1.0:
+        extra["frac_exceeds_one"] = ("SURVEY 8d's Q_step counts 4eP bytes of per-edge trunk rows (P = %d here); with the bond rows "
+                                     "de-duplicated this implementation never moves them, so the step finishes faster than that "
+                                     "traffic could be streamed: read frac_hbm_typed_formulation for the bytes it does move" % P)
+    return {**extra, "what": "one message-passing step, forward + backward (SURVEY 8d), " + tag, "kernels": kernels,
             "bound": "hbm", "achieved": 2.5 * Q / t_step / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": frac,
             "traffic": _ncu_traffic(tag), "peak_source": peaks["source"] + " (copy bandwidth)",
             "ms_per_step_fwd": ms_f / steps, "ms_per_step_bwd": ms_b / steps, "steps_per_launch": steps,
@@ -536,7 +542,7 @@ def mp_step_roofline(tag, body, devb, flush, n, e, T, P, n_bn):
                     "and does 2ed^2 FLOPs instead, `typed_formulation_*`)"}
 
 
-def roofline_large(dev, flush, points=((16384, 64), (16384, 256))):
+def roofline_large(dev, flush, points=((16384, 64), (16384, 128), (16384, 256))):
     """the same per-step figure where HBM is the limit: basic_graph_autoencoder (BASELINE configs[4]) at B = 16 384"""
     from mpnn_b200 import graph, synthetic
     out = []
