@@ -36,7 +36,7 @@ METRIC = "graphs/sec (fwd+bwd train step)"
 
 WORKLOADS = {
     # name: (synthetic config, caller variant, d, ef, T, readout width, targets)
-    "qm9": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256, head="bn_linear",
+    "qm9": dict(variant="normed", d=16, ef=7, T=3, out=64, targets=12, B=256, head="bn_linear", pipeline_prep=True,
                 desc="normed_basic_model + MaskBatchNorm + BatchNorm1d(64) + Linear(64,12), QM9-shaped (n<=29), "
                      "B=256/GPU, d=16, ef=7, P=49, T=3"),
     # the same model on NON-categorical bond features (the reference's docstrings allow "topological distance and 3D
@@ -215,11 +215,13 @@ def run_ours(args):
             loss = fused_head(feats, b["labels"])
         else:
             loss = torch.nn.functional.mse_loss(head(feats), b["labels"])
-        loss.backward()
+        loss.backward(gradient=one)     # (a persistent 1.0: no fill launch for the seed of the backward pass)
         if not fused_ddp:
             allreduce()
         opt.step()
         return loss
+
+    one = torch.ones((), dtype=torch.float32, device=dev)
 
     def barrier():
         if world > 1:
@@ -230,7 +232,17 @@ def run_ours(args):
     if use_graph:
         # the whole step (compaction .. optimizer) as ONE CUDA graph over static input buffers
         from mpnn_b200.graphs import GraphedStep
-        gs = GraphedStep(step, devb, warmup=3)
+        # input preprocessing (compaction, de-duplication, type sort: functions of bfm / adj only) software-pipelined one
+        # step ahead, as a branch of the previous step's graph, where the one-launch compaction serves the batch shape
+        pipe = (not args.no_pipeline_prep and w.get("pipeline_prep", False)
+                and bool(_lib.load().mpnn_prep_supported(devb["bfm"].shape[0], devb["bfm"].shape[1],
+                                                         devb["bfm"].shape[3], 64)))
+        gs = GraphedStep(step, devb, warmup=3, pipeline_prep=pipe)
+        # pipelined prep: a prefetched batch's bfm / adj are consumed one replay before its afm / mask / labels, which wait
+        # in one of two small staging sets (alternating by step)
+        rest_keys = [k for k in keys if k not in ("bfm", "adj")]
+        small = [{k: devb[k].clone() for k in rest_keys} for _ in range(2)] if pipe else None
+        cnt = {"pre": 0, "run": 0, "pre_r": 0, "run_r": 0}
 
         def run_resident():
             return gs.replay()
@@ -244,14 +256,25 @@ def run_ours(args):
 
         def prefetch():
             with torch.cuda.stream(copy_stream):
+                j = cnt["pre"]
+                cnt["pre"] = j + 1
                 for k in keys:
-                    staging[k].copy_(host[k], non_blocking=True)
+                    dst = small[j & 1][k] if (pipe and k in rest_keys) else staging[k]
+                    dst.copy_(host[k], non_blocking=True)
                 ev_copy.record(copy_stream)
 
         def run_e2e():
             main = torch.cuda.current_stream()
             main.wait_event(ev_copy)           # this step's inputs have landed in the staging buffer
-            gs.load(staging, non_blocking=True)
+            if pipe:
+                # the batch that has just landed is the one AFTER the batch this replay trains on: its bfm / adj are
+                # prepared during this replay; the current batch's afm / mask / labels arrived one step earlier
+                k_ = cnt["run"]
+                cnt["run"] = k_ + 1
+                gs.load(small[(k_ - 1) & 1], non_blocking=True)
+                gs.load_next(staging, non_blocking=True)
+            else:
+                gs.load(staging, non_blocking=True)
             ev_loaded.record(main)
             copy_stream.wait_event(ev_loaded)  # the staging buffer may be overwritten from here on
             prefetch()                         # next step's H2D overlaps this step's kernels
@@ -330,8 +353,19 @@ def run_ours(args):
         def run_e2e_r():
             main = torch.cuda.current_stream()
             main.wait_event(ev_copy)
-            rb_dev.scatter_padded(pad_out)                  # memsets + two scatter kernels into the graph's inputs
-            gs.static["labels"].copy_(rb_dev.labels, non_blocking=True)
+            if pipe:
+                # the ragged batch that has landed is the NEXT one: bfm / adj straight into the graph's inputs, afm / mask
+                # / labels into the small set the next step loads from
+                k_ = cnt["run_r"]
+                cnt["run_r"] = k_ + 1
+                gs.load(small[(k_ - 1) & 1], non_blocking=True)
+                nxt = small[k_ & 1]
+                rb_dev.scatter_padded({"afm": nxt["afm"], "bfm": gs.static["bfm"], "adj": gs.static["adj"],
+                                       "mask": nxt["mask"]})
+                nxt["labels"].copy_(rb_dev.labels, non_blocking=True)
+            else:
+                rb_dev.scatter_padded(pad_out)              # memsets + two scatter kernels into the graph's inputs
+                gs.static["labels"].copy_(rb_dev.labels, non_blocking=True)
             ev_loaded.record(main)
             copy_stream.wait_event(ev_loaded)
             prefetch_r()
@@ -378,6 +412,9 @@ def run_ours(args):
         "config": {"workload": w["desc"], "graphs_per_gpu": B, "atoms_per_gpu": n, "directed_edges_per_gpu": e,
                    "optimizer": "Adam", "loss": "MSE", "cuda_graph": bool(use_graph), "l2_flush": "256 MB write between timed iterations",
                    "parallelism": "dp%d" % world,
+                   "input_prep": ("compaction + de-duplication + type sort of batch k+1 run as a parallel branch of batch "
+                                  "k's captured step (GraphedStep(pipeline_prep=True)): one prep and one train step per "
+                                  "replay" if (gs is not None and gs.pipeline_prep) else "at the head of every step"),
                    "grad_allreduce": ("fused into the Adam launch over NVLink peer memory (k_adam_ddp)" if fused_ddp else
                                       ("NCCL, one flat bucket" if world > 1 else "none (1 GPU)"))},
         "e2e": {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": gb_in,
@@ -760,6 +797,8 @@ def main():
     ap.add_argument("--stock-head", action="store_true", help="keep the head + loss as stock torch modules")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + Adam instead of the fused kernel")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
+    ap.add_argument("--no-pipeline-prep", action="store_true",
+                    help="compaction / de-duplication at the head of each step instead of one step ahead")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")
     ap.add_argument("--timeline", default="", help="write a warm per-kernel timeline of one step to this file")
     ap.add_argument("--hidden", type=int, default=0, help="feature width d (autoenc sweep of BASELINE configs[4])")

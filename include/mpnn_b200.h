@@ -400,9 +400,12 @@ int mpnn_chain_bwd(const int* row_ptr, const int* edge_src, const int* uid, cons
                    const float* H0, const float* h_init, const float* mask, const float* const* tables, int T,
                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const int* bn_kind,
                    const int* bn_training, const float* bn_eps, const float* bn_momentum, float* const* bn_ptrs,
-                   long long rows, int d, const int* real_list, float* saved, const float* dout, float* dM,
-                   float* dh_init, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh, float* const* bn_grads,
-                   void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+                   long long rows, int d, const int* real_list, float* saved, const float* dout, long long dout_ld,
+                   float* dM, float* dh_init, float* dW_ih, float* dW_hh, float* db_ih, float* db_hh,
+                   float* const* bn_grads, void* workspace, size_t workspace_bytes, mpnn_stream_t stream);
+/* dout: gradient w.r.t. the last step's output, [rows, d] with a row stride of dout_ld >= d floats (the reference models
+ * concatenate the final state with afm before the readout, normed_basic_model.py:59: the gradient arrives as a column
+ * slice of a [rows, 2d] array and is read in place). */
 /* real_list (optional, NULL allowed): [rows + 1] ints from mpnn_real_rows = the rows with mask != 0 in increasing order
  * and, in the last slot, their number; lets every CTA of the step kernels own the same number of real rows.  `out`,
  * `dM` and `dh_init` must be zero-filled by the caller: rows with mask == 0 are skipped (their values are exact zeros). */

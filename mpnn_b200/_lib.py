@@ -139,7 +139,7 @@ SIGNATURES = {
     "mpnn_chain_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _PP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _PP, _L, _I, _P,
                             _P, _P, _P, _Z, _P]),
     "mpnn_chain_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _PP, _I, _P, _P, _P, _P, _P, _P, _P, _P, _PP, _L, _I, _P,
-                            _P, _P, _P, _P, _P, _P, _P, _P, _PP, _P, _Z, _P]),
+                            _P, _P, _L, _P, _P, _P, _P, _P, _P, _PP, _P, _Z, _P]),
     "mpnn_real_rows_max": (_I, []),
     "mpnn_real_rows": (_I, [_P, _L, _P, _P, _Z, _P]),
     "mpnn_set2vec_set_persistent": (_I, [_I]),

@@ -78,7 +78,8 @@ struct Chain {
 
 struct ChainB {
   Chain f;
-  const float* dout;   // [rows, d]
+  const float* dout;   // [rows, d], row stride dout_ld floats (a column slice of the caller's wider gradient is fine)
+  long long dout_ld;
   float* dM;           // [T][rows][d]
   float* dh_init;      // [rows][d] or null
   float* dY;           // [rows][d] scratch
@@ -742,8 +743,8 @@ struct BwdOps {   // operands of one row of one backward step (lane c)
 };
 
 template <int DP>
-__device__ __forceinline__ void load_ops(const Chain& a, int t, const float* dyin, const int* rowlist, int idx, int nreal,
-                                         bool on, int c, BwdOps& o, int* row_out) {
+__device__ __forceinline__ void load_ops(const Chain& a, int t, const float* dyin, size_t dy_ld, const int* rowlist,
+                                         int idx, int nreal, bool on, int c, BwdOps& o, int* row_out) {
   const bool live = idx < nreal && on;
   const int row = idx < nreal ? rowlist[idx] : 0;
   *row_out = row;
@@ -752,7 +753,7 @@ __device__ __forceinline__ void load_ops(const Chain& a, int t, const float* dyi
   const int d = a.d;
   const size_t rows = a.rows;
   o.mu = __ldg(a.mask + row);
-  o.dy = __ldcg(dyin + (size_t)row * d + c);
+  o.dy = __ldcg(dyin + (size_t)row * dy_ld + c);
   if (a.bn[t].kind) o.g = __ldcg(a.G + ((size_t)t * rows + row) * d + c);
   const float* g = a.gates + ((size_t)t * rows + row) * 4 * d;
   o.sr = __ldcg(g + c);
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(ChainB b) {
         const float mu = __ldg(a.mask + row);
         float xh;
         bn_out<DP>(a.bn[T1].kind, __ldcg(Gl + (size_t)row * d + c), mu, bnc, c, &xh);
-        const float dy = __ldg(b.dout + (size_t)row * d + c);
+        const float dy = __ldg(b.dout + (size_t)row * (size_t)b.dout_ld + c);
         s12[0] = fmaf(dy, xh, s12[0]);
         s12[1] = fmaf(dy, mu, s12[1]);
       }
@@ -838,10 +839,11 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(ChainB b) {
     const BNDesc bn = a.bn[t];
     const int pkind = t > 0 ? a.bn[t - 1].kind : 0;
     const float* dyin = t == T1 ? b.dout : b.dY;
+    const size_t dy_ld = t == T1 ? (size_t)b.dout_ld : (size_t)d;
     // operands of the first tile and the statistics of the previous batch norm are loaded while the sums are in flight
     BwdOps nx;
     int nrow;
-    load_ops<DP>(a, t, dyin, rowlist, grp, nreal, on, c, nx, &nrow);
+    load_ops<DP>(a, t, dyin, dy_ld, rowlist, grp, nreal, on, c, nx, &nrow);
     load_bnv<DP>(a, t - 1, bnv);   // the batch norm that produced h_t
     float Mn = 1.f;
     if (bn.kind) {
@@ -855,7 +857,7 @@ __global__ void __launch_bounds__(NT, 1) k_chain_bwd(ChainB b) {
       const int row = nrow;
       const bool live = base + grp < nreal;
       const BwdOps o = nx;
-      load_ops<DP>(a, t, dyin, rowlist, base + TR + grp, nreal, on, c, nx, &nrow);
+      load_ops<DP>(a, t, dyin, dy_ld, rowlist, base + TR + grp, nreal, on, c, nx, &nrow);
       __syncthreads();   // previous tile's accumulation is done with the staging buffers
       float dar = 0.f, daz = 0.f, dan = 0.f, dnh = 0.f, dhd = 0.f, mv = 0.f, hv = 0.f, xhp = 0.f;
       const float mu = o.mu;
@@ -1161,8 +1163,8 @@ int mpnn_chain_bwd(const int* row_ptr, const int* edge_src, const int* uid, cons
                    const float* H0, const float* h_init, const float* mask, const float* const* tables, int T,
                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh, const int* bn_kind,
                    const int* bn_training, const float* bn_eps, const float* bn_momentum, float* const* bn_ptrs,
-                   long long rows, int d, const int* real_list, float* saved, const float* dout, float* dM,
-                   float* dh_init, float* dW_ih,
+                   long long rows, int d, const int* real_list, float* saved, const float* dout, long long dout_ld,
+                   float* dM, float* dh_init, float* dW_ih,
                    float* dW_hh, float* db_ih, float* db_hh, float* const* bn_grads, void* workspace,
                    size_t workspace_bytes, cudaStream_t stream) {
   MPNN_REQUIRE(rows > 0 && rows < (1ll << 31) && mpnn_chain_supported(d, T), MPNN_ERR_UNSUPPORTED,
@@ -1175,7 +1177,9 @@ int mpnn_chain_bwd(const int* row_ptr, const int* edge_src, const int* uid, cons
                           b_ih, b_hh, bn_kind, bn_training, bn_eps, bn_momentum, bn_ptrs, rows, d, saved, nullptr,
                           workspace, grid, DP, real_list),
                MPNN_ERR_ARG, "chain_bwd: bad step description");
+  MPNN_REQUIRE(dout_ld >= d, MPNN_ERR_ARG, "chain_bwd: dout row stride smaller than d");
   b.dout = dout;
+  b.dout_ld = dout_ld;
   b.dM = dM;
   b.dh_init = dh_init;
   const size_t part = align_up((size_t)T * grid * (2 * DP + 4) * sizeof(float), 256);

@@ -1321,6 +1321,9 @@ def chain_supported(d, T):
     return bool(CHAIN_ENABLED and _lib.load().mpnn_chain_supported(int(d), int(T)))
 
 
+AFTER_CHAIN_FWD = []   # one-shot callbacks run right behind the launch of the fused step kernel's forward
+
+
 _REAL_ROWS = {}     # (mask identity) -> (mask, list, event): the rows with mask != 0, computed once per batch
 
 
@@ -1410,6 +1413,8 @@ class ChainFn(torch.autograd.Function):
                 ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh), kinds, training, eps, mom,
                 bn_ptrs, rows, d, ptr(real[0]), ptr(saved))
         check(lib.mpnn_chain_fwd(*(args + (ptr(out), ptr(ws), ws.numel(), stream()))), "chain_fwd")
+        while AFTER_CHAIN_FWD:      # one-shot callbacks (graphs.GraphedStep: fork the next batch's preprocessing here)
+            AFTER_CHAIN_FWD.pop(0)()
         ctx.save_for_backward(H0, h_init, mask, W_ih, W_hh, b_ih, b_hh, saved, alpha, *(tables + tablesT + affine))
         ctx.meta = (el, bn, T, rows, d, aff_idx, keep, real[0])
         return out
@@ -1424,7 +1429,14 @@ class ChainFn(torch.autograd.Function):
         tables, tablesT, affine = list(rest[:T]), list(rest[T:2 * T]), list(rest[2 * T:])
         dev = h_init.device
         ti = el.typed()
-        dout = f32c(dout)
+        # the reference models concatenate the final state with afm (normed_basic_model.py:59): the gradient arrives as a
+        # column slice of a wider array and the kernel reads it in place through its row stride
+        if (dout.dtype == torch.float32 and dout.dim() == 2 and dout.shape[0] > 1 and dout.stride(1) == 1
+                and dout.stride(0) >= d):
+            dout_ld = int(dout.stride(0))
+        else:
+            dout = f32c(dout)
+            dout_ld = d
         need_H0, need_h = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         kinds = (ctypes.c_int * T)(*[b["kind"] for b in bn])
         training = (ctypes.c_int * T)(*[int(b["training"]) for b in bn])
@@ -1449,7 +1461,7 @@ class ChainFn(torch.autograd.Function):
         check(lib.mpnn_chain_bwd(ptr(el.row_ptr), ptr(el.edge_src), ptr(ti.uid), ptr(alpha), el.Ecap, ti.zero_type, ptr(H0),
                                  ptr(h_init), ptr(mask), ptr_array(tables), T, ptr(W_ih), ptr(W_hh), ptr(b_ih), ptr(b_hh),
                                  kinds, training, eps, mom, ptr_array(ptrs), rows, d, ptr(real_list), ptr(saved),
-                                 ptr(dout), ptr(dM),
+                                 ctypes.c_void_p(dout.data_ptr()), dout_ld, ptr(dM),   # (row-strided: see above)
                                  ptr(dh), ptr(dW_ih), ptr(dW_hh), ptr(db_ih), ptr(db_hh), ptr_array(gptrs), ptr(ws),
                                  ws.numel(), stream()), "chain_bwd")
         # ---- message gradients -> table gradients (parameter-only: side lane) and sender gradients -------------------

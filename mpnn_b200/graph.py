@@ -116,15 +116,18 @@ class capacities(object):
 FUSED_PREP = os.environ.get("MPNN_B200_FUSED_PREP", "1") != "0"
 
 
-def _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev):
+def _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev, out=None):
     """type_ptr / type_eid / type_pos (edges grouped by distinct row, stable): only the backward's table-gradient kernels
     and the tensor-core plan read them, so the three dependent launches run on a side stream (a parallel branch of the
     captured step).  Returns (type_ptr, type_eid, type_pos, done event)."""
     from . import functional
     lib = _lib.load()
-    type_ptr = torch.empty(Ucap + 1, dtype=torch.int32, device=dev)
-    type_eid = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
-    type_pos = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+    if out is not None:
+        type_ptr, type_eid, type_pos = out
+    else:
+        type_ptr = torch.empty(Ucap + 1, dtype=torch.int32, device=dev)
+        type_eid = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
+        type_pos = torch.empty(max(Ecap, 1), dtype=torch.int32, device=dev)
     main = torch.cuda.current_stream(dev)
     _, side = functional._side_stream(dev, lane=5)
     ev = torch.cuda.Event()
@@ -149,22 +152,46 @@ def _note_edge_overflow(counts, e_true, Ecap):
     counts[2:3].bitwise_or_((e_true[0:1] > Ecap).to(torch.int32))
 
 
-def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap):
-    """capacity mode, small batches: compaction + de-duplication as ONE cooperative launch (csrc/prep.cu)"""
+def _slab_views(slab, sizes):
+    """consecutive 256-byte aligned int32 views of `slab`"""
+    out, off = [], 0
+    for n in sizes:
+        out.append(slab[off:off + n])
+        off += (n + 63) // 64 * 64
+    return out
+
+
+def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap, slab=False):
+    """capacity mode, small batches: compaction + de-duplication as ONE cooperative launch (csrc/prep.cu).
+    slab=True: every output array (incl. the type-sorted lists and the counts) is a view of ONE int32 allocation
+    (`el.slab`), so a whole edge list can be handed over with one device copy (graphs.GraphedStep(pipeline_prep=True))."""
     lib = _lib.load()
     dev = bfm_c.device
     n_rows = B * N
     i32 = dict(dtype=torch.int32, device=dev)
-    row_ptr = torch.empty(n_rows + 1, **i32)
-    col_ptr = torch.empty(n_rows + 1, **i32)
-    edge_src = torch.empty(Ecap, **i32)
-    edge_dst = torch.empty(Ecap, **i32)
-    csc_eid = torch.empty(Ecap, **i32)
-    uid = torch.empty(max(Ecap, 1), **i32)
-    edge_w = torch.empty(Ecap, dtype=torch.float32, device=dev)
-    urows = torch.empty(Ucap + 1, ef, dtype=torch.float32, device=dev)
     from . import functional
-    counts = functional.zeros((4,), torch.int32, dev)
+    sort_out, slab_t = None, None
+    if slab:
+        e1 = max(Ecap, 1)
+        sizes = [n_rows + 1, n_rows + 1, e1, e1, e1, e1, e1, (Ucap + 1) * ef, 4, Ucap + 1, e1, e1]
+        slab_t = torch.empty(sum((n + 63) // 64 * 64 for n in sizes), **i32)
+        (row_ptr, col_ptr, edge_src, edge_dst, csc_eid, uid, edge_w, urows, counts, type_ptr, type_eid,
+         type_pos) = _slab_views(slab_t, sizes)
+        edge_src, edge_dst, csc_eid = edge_src[:Ecap], edge_dst[:Ecap], csc_eid[:Ecap]
+        edge_w = edge_w.view(torch.float32)[:Ecap]
+        urows = urows.view(torch.float32).view(Ucap + 1, ef)
+        counts.zero_()
+        sort_out = (type_ptr, type_eid, type_pos)
+    else:
+        row_ptr = torch.empty(n_rows + 1, **i32)
+        col_ptr = torch.empty(n_rows + 1, **i32)
+        edge_src = torch.empty(Ecap, **i32)
+        edge_dst = torch.empty(Ecap, **i32)
+        csc_eid = torch.empty(Ecap, **i32)
+        uid = torch.empty(max(Ecap, 1), **i32)
+        edge_w = torch.empty(Ecap, dtype=torch.float32, device=dev)
+        urows = torch.empty(Ucap + 1, ef, dtype=torch.float32, device=dev)
+        counts = functional.zeros((4,), torch.int32, dev)
     ws = _lib.clean_workspace(lib.mpnn_prep_workspace_bytes(B, Ucap), dev, "prep")
     _lib.check(lib.mpnn_prep_edges(_lib.ptr(bfm_c), _lib.ptr(adj_c), B, N, ef, Ecap, Ucap, _lib.ptr(row_ptr),
                                    _lib.ptr(col_ptr), _lib.ptr(edge_src), _lib.ptr(edge_dst), _lib.ptr(edge_w),
@@ -172,12 +199,28 @@ def _prep_edges(bfm_c, adj_c, B, N, ef, Ecap, Ucap):
                                    ws.numel(), _lib.stream()), "prep_edges")
     el = EdgeList(B, N, ef, None, row_ptr, col_ptr, edge_src, edge_dst, edge_w, None, csc_eid)
     el.Ecap = Ecap
-    type_ptr, type_eid, type_pos, done = _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev)
+    el.slab = slab_t
+    type_ptr, type_eid, type_pos, done = _type_sort_on_side_lane(uid, counts, Ecap, Ucap, dev, out=sort_out)
     ti = TypedInfo(uid[:Ecap], urows, counts, type_ptr, type_eid[:Ecap], type_pos[:Ecap], None, Ucap)
     ti.sort_event = done
     el._typed = ti
     _CAPTURED_COUNTS.append(counts)
     return el
+
+
+def prep_edges_slab(bfm, adj):
+    """Capacity-mode edge list of (bfm, adj) with all arrays in one allocation (`el.slab`); raises where the one-launch
+    compaction does not serve the shape."""
+    lib = _lib.load()
+    if _CAPACITY is None:
+        raise RuntimeError("mpnn_b200.prep_edges_slab: only inside `with graph.capacities(...)`")
+    if not (bfm.is_cuda and bfm.dtype == torch.float32 and bfm.is_contiguous()
+            and adj is not None and adj.dtype == torch.float32 and adj.is_contiguous()):
+        raise RuntimeError("mpnn_b200.prep_edges_slab: contiguous float32 CUDA bfm / adj required")
+    B, N, _, ef = bfm.shape
+    if not (FUSED_PREP and lib.mpnn_prep_supported(B, N, ef, _CAPACITY[1])):
+        raise RuntimeError("mpnn_b200.prep_edges_slab: batch shape not served by the one-launch compaction")
+    return _prep_edges(bfm.detach(), adj.detach(), B, N, ef, _CAPACITY[0], _CAPACITY[1], slab=True)
 
 
 def compact_edges(bfm, adj=None, dedup=True):
@@ -352,9 +395,29 @@ def _key(t):
     return None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.device.index)
 
 
+_PINNED = {}     # (bfm address, adj address) -> [EdgeList, uses]: edge lists prepared AHEAD of the step that consumes them
+
+
+def pin(bfm, adj, el):
+    """`edge_list_for(bfm, adj)` returns `el` (whatever the tensors' versions, across `clear_cache()`) until `unpin()`:
+    graphs.GraphedStep(pipeline_prep=True) prepares a batch's edge list one step ahead."""
+    _PINNED[(bfm.data_ptr(), adj.data_ptr())] = [el, 0]
+
+
+def unpin():
+    uses = sum(v[1] for v in _PINNED.values())
+    _PINNED.clear()
+    return uses
+
+
 def edge_list_for(bfm, adj=None):
     if isinstance(bfm, TypedBonds):
         return bfm.edge_list(adj)
+    if _PINNED and adj is not None:
+        hit = _PINNED.get((bfm.data_ptr(), adj.data_ptr()))
+        if hit is not None:
+            hit[1] += 1
+            return hit[0]
     k = (_key(bfm), _key(adj))
     hit = _CACHE.get(k)
     if hit is not None:

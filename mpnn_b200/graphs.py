@@ -23,11 +23,27 @@ class GraphedStep(object):
                                                 # step_fn has run `gs.eager_steps` times when the constructor returns
         loss = gs(batch)                        # copies the batch into the static buffers, replays
         gs.check()                              # raises if a batch overflowed the captured capacities
+
+    pipeline_prep=True software-pipelines the input preprocessing: compaction + de-duplication + type sort of a batch
+    (csrc/prep.cu; they depend on `bfm` / `adj` only, not on the weights) run one replay AHEAD, as a parallel branch of the
+    previous batch's train step (forked behind the fused step kernel's forward: the one-CTA-per-SM step kernels and the
+    cooperative compaction kernel cannot share an SM, the readout / head kernels in between leave room), instead of at
+    the head of the step's critical path.  Every replay still does one preprocessing and one train step.  In this mode
+    the static `bfm` / `adj` buffers hold the batch AFTER the one being trained on; the step may use them only through
+    the message-passing modules (which receive the edge list prepared one replay earlier), not read them densely:
+
+        gs = GraphedStep(step_fn, batch0, pipeline_prep=True)    # batch0's edge list is prepared eagerly
+        gs.load_next(batch1)                    # bfm / adj of the batch AFTER the one about to be trained on
+        loss0 = gs.replay()                     # trains on batch0, prepares batch1's edge list
+        gs.load(batch1); gs.load_next(batch2)   # batch1's afm / mask / labels ...; batch2's bfm / adj
+        loss1 = gs.replay()                     # ...
     """
 
-    def __init__(self, step_fn, example_inputs, warmup=3, headroom=1.25, edge_capacity=None, unique_capacity=None):
+    def __init__(self, step_fn, example_inputs, warmup=3, headroom=1.25, edge_capacity=None, unique_capacity=None,
+                 pipeline_prep=False):
         self.static = {k: v.clone() for k, v in example_inputs.items()}
         self.step_fn = step_fn
+        self.pipeline_prep = bool(pipeline_prep)
         self.eager_steps = warmup + 1    # executions of step_fn before the capture (warm-up + the arena dry run)
         graph.STATS["E"] = graph.STATS["U"] = graph.STATS["n_real"] = 0
         side = torch.cuda.Stream()
@@ -59,23 +75,75 @@ class GraphedStep(object):
         graph.clear_cache()
         functional._FWD_SIDE.clear()
         lib = _lib.load()
+        dev = next(iter(self.static.values())).device
+        self._sticky = None
         with graph.capacities(self.edge_capacity, self.unique_capacity):
-            with torch.cuda.graph(self.graph):
+            if self.pipeline_prep:
+                # the edge list the FIRST replay trains on, built eagerly; every replay hands the next one over
+                self.next = {k: self.static[k] for k in ("bfm", "adj")}
+                self._el_cur = graph.prep_edges_slab(self.static["bfm"], self.static["adj"])
+                torch.cuda.synchronize()
+                del graph._CAPTURED_COUNTS[:]
+                self._el_cur._typed.sort_event = None       # (recorded outside the capture; the work is finished)
+                self._sticky = torch.zeros(1, dtype=torch.int32, device=dev)
+            # captured on the stream the warm-up steps ran on: the per-stream persistent workspaces (_lib.clean_workspace) of
+            # the warm-up are the capture's, so no zero-fill of a fresh workspace lands in the graph
+            with torch.cuda.graph(self.graph, stream=side):
                 # every zero-initialised buffer of the step is a slice of this arena: one memset node, no fill launches
                 _lib.check(lib.mpnn_zero_bytes(_lib.ptr(self.arena), self.arena.numel(), _lib.stream()), "zero_bytes")
                 functional.arena_begin(self.arena)
                 try:
+                    if self.pipeline_prep:
+                        self._el_nxt = None
+                        graph.pin(self.static["bfm"], self.static["adj"], self._el_cur)
+                        graph._CAPTURED_COUNTS.append(self._el_cur._typed.counts)   # the optimizer's overflow guard
+                        functional.AFTER_CHAIN_FWD.append(lambda: self._capture_prep_branch(dev))
                     self.loss = step_fn(self.static)
+                    if self.pipeline_prep and self._el_nxt is None:
+                        del functional.AFTER_CHAIN_FWD[:]
+                        self._capture_prep_branch(dev)      # (no fused step kernel in this step: no overlap, same result)
                 finally:
                     functional.arena_end()
+                    uses = graph.unpin()
+                    del functional.AFTER_CHAIN_FWD[:]
                 functional.join_side_streams()   # no forked branch may outlive the capture
+                if self.pipeline_prep:
+                    if not uses:
+                        raise RuntimeError("mpnn_b200.GraphedStep(pipeline_prep=True): the step never asked for the "
+                                           "edge list of (inputs['bfm'], inputs['adj'])")
+                    # every consumer of the current edge list has finished, the next one is complete: hand it over
+                    self._el_cur.slab.copy_(self._el_nxt.slab)
         self._counts = list(graph._CAPTURED_COUNTS)
         del graph._CAPTURED_COUNTS[:]
         graph.clear_cache()
 
+    def _capture_prep_branch(self, dev):
+        """(inside the capture) the NEXT batch's compaction / de-duplication / type sort on a side lane forked from the
+        current position of the capturing stream"""
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        key, lane = functional._side_stream(dev, lane=7)
+        lane.wait_event(fork)
+        with torch.cuda.stream(lane):
+            self._sticky.bitwise_or_(self._el_cur._typed.counts[2:3])    # overflow flag of the batch being trained on
+            self._el_nxt = graph.prep_edges_slab(self.next["bfm"], self.next["adj"])
+        functional._FWD_SIDE.add(key)
+        # the optimizer's overflow guard is the CURRENT batch's flag, not the next one's
+        nxt = self._el_nxt._typed.counts
+        graph._CAPTURED_COUNTS[:] = [c for c in graph._CAPTURED_COUNTS if c is not nxt]
+
     def load(self, inputs, non_blocking=True):
+        """copies a batch into the static buffers (pipeline_prep: everything but bfm / adj, see load_next)"""
         for k, v in inputs.items():
+            if self.pipeline_prep and k in ("bfm", "adj"):
+                continue
             self.static[k].copy_(v, non_blocking=non_blocking)
+
+    def load_next(self, inputs, non_blocking=True):
+        """pipeline_prep: bfm / adj of the batch that FOLLOWS the one the next replay trains on"""
+        for k in ("bfm", "adj"):
+            self.static[k].copy_(inputs[k], non_blocking=non_blocking)
 
     def replay(self):
         self.graph.replay()
@@ -83,6 +151,8 @@ class GraphedStep(object):
 
     def __call__(self, inputs=None):
         if inputs is not None:
+            if self.pipeline_prep:
+                raise RuntimeError("mpnn_b200.GraphedStep(pipeline_prep=True): use load() / load_next() + replay()")
             self.load(inputs)
         return self.replay()
 
@@ -90,6 +160,11 @@ class GraphedStep(object):
         """One small D2H read: did any batch replayed since the last check exceed the captured edge / distinct-row
         capacities?  (Kernels clamp their reads to the capacities, so an overflowing batch computes on a truncated edge
         list; the step's result must be discarded by the caller.)"""
+        if self._sticky is not None and int(self._sticky.item()):
+            self._sticky.zero_()
+            raise RuntimeError("mpnn_b200.GraphedStep: a replayed batch exceeded the captured capacities (%d edges / "
+                               "%d distinct bond rows); re-capture with larger capacities"
+                               % (self.edge_capacity, self.unique_capacity))
         for c in self._counts:
             e, u, flag, _ = c.cpu().tolist()
             if flag:

@@ -35,6 +35,7 @@ class _BNLinearMSEFn(torch.autograd.Function):
         ctx.save_for_backward(x, target, gamma, beta, W, y, stats)
         ctx.dims = (B, C, T, int(training), b is not None)
         ctx.mark_non_differentiable(y)
+        ctx.set_materialize_grads(False)     # no zero-filled gradient for the non-differentiable predictions
         return loss, y
 
     @staticmethod
@@ -44,6 +45,8 @@ class _BNLinearMSEFn(torch.autograd.Function):
         x, target, gamma, beta, W, y, stats = ctx.saved_tensors
         B, C, T, training, has_b = ctx.dims
         dev = x.device
+        if gloss is None:
+            return (None,) * 12
         gloss = f32c(gloss.reshape(1))
         dx = torch.empty_like(x)
         dgamma = torch.empty_like(gamma) if gamma is not None else None

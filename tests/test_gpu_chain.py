@@ -222,6 +222,110 @@ def test_captured_step_equals_eager_step(dev):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
 
 
+def _padded_batches(dev, n, B, out):
+    """n different qm9-shaped batches zero-padded to one common N (a captured step has fixed shapes)"""
+    import numpy as np
+    from mpnn_b200 import synthetic
+    raw = [synthetic.make_batch("qm9", B=B, seed_offset=s) for s in range(n)]
+    N = max(b["afm"].shape[1] for b in raw)
+    res = []
+    for s, b in enumerate(raw):
+        n0 = b["afm"].shape[1]
+        pad = N - n0
+        t = {"afm": np.pad(b["afm"], ((0, 0), (0, pad), (0, 0))),
+             "bfm": np.pad(b["bfm"], ((0, 0), (0, pad), (0, pad), (0, 0))),
+             "adj": np.pad(b["adj"], ((0, 0), (0, pad), (0, pad))),
+             "mask": np.pad(b["mask"], ((0, 0), (0, pad)) + ((0, 0),) * (b["mask"].ndim - 2))}
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in t.items()}
+        t["labels"] = torch.randn(B, out, generator=torch.Generator().manual_seed(100 + s)).to(dev)
+        res.append(t)
+    return res
+
+
+def test_pipelined_prep_equals_plain_captured_step(dev):
+    """GraphedStep(pipeline_prep=True): a batch's compaction / de-duplication / type sort run one replay AHEAD, beside
+    the previous batch's train step.  Over a sequence of DIFFERENT batches the losses and the parameters are
+    bit-identical to the plain captured step (same kernels on the same edge lists, only scheduled earlier)."""
+    from mpnn_b200 import graph, graphs, optim
+    seq = _padded_batches(dev, 5, 40, 12)
+    order = [0, 1, 2, 3, 4, 2, 0]
+    losses, finals = {}, {}
+    for mode in ("plain", "pipelined"):
+        graph.clear_cache()
+        mod = _model("normed", dev, 16, 7, 12, 3, seed=11)
+        opt = optim.FusedAdam(list(mod.parameters()), lr=1e-3)
+
+        def step_fn(b):
+            graph.clear_cache()
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(mod(b["afm"], b["bfm"], b["adj"], b["mask"]), b["labels"])
+            loss.backward()
+            opt.step()
+            return loss
+
+        gs = graphs.GraphedStep(step_fn, seq[0], warmup=3, edge_capacity=4096, unique_capacity=64,
+                                pipeline_prep=(mode == "pipelined"))
+        ls = []
+        if mode == "plain":
+            for i in order:
+                ls.append(float(gs(seq[i])))
+        else:
+            # the constructor prepared seq[0] (the example batch); every following batch's bfm / adj are announced one
+            # replay before its afm / mask / labels are loaded
+            for k in range(len(order)):
+                gs.load(seq[order[k]])
+                gs.load_next(seq[order[min(k + 1, len(order) - 1)]])
+                ls.append(float(gs.replay()))
+        gs.check()
+        losses[mode] = ls
+        finals[mode] = [p.detach().clone() for p in mod.parameters()]
+    assert losses["plain"] == losses["pipelined"], losses
+    for a, b in zip(finals["plain"], finals["pipelined"]):
+        assert torch.equal(a, b)
+    assert len(set(losses["plain"][:5])) == 5      # the batches really differ
+
+
+def test_pipelined_prep_overflow_flag_is_sticky(dev):
+    """an overflowing batch anywhere in the replayed sequence is reported by check(), and its update is skipped"""
+    from mpnn_b200 import graph, graphs, optim
+    seq = _padded_batches(dev, 2, 40, 12)
+    graph.clear_cache()
+    mod = _model("normed", dev, 16, 7, 12, 3, seed=11)
+    opt = optim.FusedAdam(list(mod.parameters()), lr=1e-3)
+
+    def step_fn(b):
+        graph.clear_cache()
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(mod(b["afm"], b["bfm"], b["adj"], b["mask"]), b["labels"])
+        loss.backward()
+        opt.step()
+        return loss
+
+    small = {k: v.clone() for k, v in seq[0].items()}
+    small["bfm"][20:] = 0
+    small["adj"][20:] = 0        # half of the graphs lose their bonds: far fewer edges than seq[1]
+    e_small = int(((small["bfm"] != 0).any(-1) | (small["adj"] != 0)).sum())
+    e_big = int(((seq[1]["bfm"] != 0).any(-1) | (seq[1]["adj"] != 0)).sum())
+    assert e_big > e_small + 80
+    gs = graphs.GraphedStep(step_fn, small, warmup=3, edge_capacity=e_small + 64, unique_capacity=64,
+                            pipeline_prep=True)
+    gs.load(small)
+    gs.load_next(seq[1])
+    gs.replay()                      # trains on `small`, prepares seq[1] (overflows)
+    before = [p.detach().clone() for p in mod.parameters()]
+    gs.load(seq[1])
+    gs.load_next(small)
+    gs.replay()                      # trains on the truncated seq[1]: the update is gated off
+    after = [p.detach().clone() for p in mod.parameters()]
+    for a, b in zip(before, after):
+        assert torch.equal(a, b)
+    gs.load(small)
+    gs.replay()                      # a fitting batch again
+    with pytest.raises(RuntimeError, match="capacit"):
+        gs.check()
+    gs.check()                       # cleared by the first check
+
+
 def test_captured_att_step_equals_eager_step(dev):
     """BASELINE config 3's train step (att_model: AttEdgeNetwork's per-edge gate on edge SLOTS in capacity mode, Set2Vec's
     persistent kernels, fused Adam) replayed as one CUDA graph against the eager step"""
