@@ -41,7 +41,22 @@ class GraphedStep(object):
 
     def __init__(self, step_fn, example_inputs, warmup=3, headroom=1.25, edge_capacity=None, unique_capacity=None,
                  pipeline_prep=False):
-        self.static = {k: v.clone() for k, v in example_inputs.items()}
+        # static inputs as views of two flat allocations ("bonds": bfm / adj, "rest": everything else), so a batch can be
+        # loaded with two device copies whatever its number of tensors (`flat`, `mirror()`)
+        dev0 = next(iter(example_inputs.values())).device
+        self.layout, self.flat, self.static = {}, {}, {}
+        for group, ks in (("bonds", [k for k in example_inputs if k in ("bfm", "adj")]),
+                          ("rest", [k for k in example_inputs if k not in ("bfm", "adj")])):
+            self.layout[group], off = [], 0
+            for k in ks:
+                v = example_inputs[k]
+                self.layout[group].append((k, off, tuple(v.shape), v.dtype))
+                off += (v.numel() * v.element_size() + 255) // 256 * 256
+            self.layout[group] = (self.layout[group], off)
+            self.flat[group], views = self.mirror(group, device=dev0)
+            for k in ks:
+                views[k].copy_(example_inputs[k])
+            self.static.update(views)
         self.step_fn = step_fn
         self.pipeline_prep = bool(pipeline_prep)
         self.eager_steps = warmup + 1    # executions of step_fn before the capture (warm-up + the arena dry run)
@@ -116,6 +131,20 @@ class GraphedStep(object):
         self._counts = list(graph._CAPTURED_COUNTS)
         del graph._CAPTURED_COUNTS[:]
         graph.clear_cache()
+
+    def mirror(self, group, device=None, pin_memory=False):
+        """(flat uint8 buffer, {name: tensor view}) with the layout of the static input group "bonds" (bfm, adj) or "rest":
+        a host (pinned) or device staging copy of a batch that moves with ONE copy into `self.flat[group]`"""
+        entries, total = self.layout[group]
+        flat = torch.empty(max(total, 256), dtype=torch.uint8, device=device, pin_memory=pin_memory)
+        views = {}
+        for k, off, shape, dtype in entries:
+            n = 1
+            for d_ in shape:
+                n *= d_
+            nb = n * torch.empty(0, dtype=dtype).element_size()
+            views[k] = flat[off:off + nb].view(dtype).view(shape)
+        return flat, views
 
     def _capture_prep_branch(self, dev):
         """(inside the capture) the NEXT batch's compaction / de-duplication / type sort on a side lane forked from the
