@@ -1327,7 +1327,7 @@ AFTER_CHAIN_FWD = []   # one-shot callbacks run right behind the launch of the f
 _REAL_ROWS = {}     # (mask identity) -> (mask, list, event): the rows with mask != 0, computed once per batch
 
 
-def real_rows(mask, side=False):
+def real_rows(mask, side=False, fork=None):
     """(list [rows+1] int32 or None, event or None) for the step kernels: the rows of `mask` that are real, so every CTA
     owns the same number of them.  With side=True the (tiny, single-block) kernel is enqueued on a side stream, forked
     from the current position of the main stream: `modules._fused_chain` calls it before the compaction and the edge
@@ -1349,8 +1349,9 @@ def real_rows(mask, side=False):
     if side and SIDE_STREAM_ENABLED:
         main = torch.cuda.current_stream(dev)
         _, s_ = _side_stream(dev, lane=6)
-        fork = torch.cuda.Event()
-        fork.record(main)
+        if fork is None:       # (else: an event the caller recorded earlier on the main stream)
+            fork = torch.cuda.Event()
+            fork.record(main)
         s_.wait_event(fork)
         with torch.cuda.stream(s_):
             check(lib.mpnn_real_rows(ptr(m), rows, ptr(lst), ptr(ws), ws.numel() * 4, stream()), "real_rows")

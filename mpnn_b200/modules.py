@@ -696,6 +696,7 @@ def _tables_for_steps(msgs, el):
 
 
 AGG_IN_GRU = os.environ.get("MPNN_B200_AGG_IN_GRU", "1") != "0"
+REAL_ROWS_LATE = os.environ.get("MPNN_B200_REAL_ROWS_LATE", "1") != "0"
 WIDE_COMPACT = os.environ.get("MPNN_B200_WIDE_COMPACT", "1") != "0"
 
 
@@ -826,13 +827,22 @@ def _fused_chain(head):
         if bn is not None and (bn._mask is not mask or (isinstance(bn._module, MaskBatchNorm1d)
                                                         and bn._module.momentum is None)):
             return None
-    if not wide:
+    fork = None
+    if not wide and REAL_ROWS_LATE and mask.is_cuda:
+        # the list of real rows (tiny kernel, side lane) depends on the mask only: forked from HERE, but enqueued behind the
+        # compaction / edge networks, so that in a captured step the critical chain (edge networks -> step kernel) is the
+        # first branch created behind the graph's root and the side lane the second
+        fork = torch.cuda.Event()
+        fork.record(torch.cuda.current_stream(mask.device))
+    elif not wide:
         real_rows(mask, side=True)     # tiny kernel on a side lane, overlapped with the compaction / edge networks below
     el = graph.edge_list_for(bfm, adj)
     if not all(gru._src._messages._net._typed_ok(bfm, el) for gru, _ in steps):
         return None
     tables, tablesT, bnspec, affine = [], [], [], []
     _tables_for_steps([gru._src._messages for gru, _ in steps], el)
+    if fork is not None:
+        real_rows(mask, side=True, fork=fork)
     if wide:
         return _wide_chain(steps, base, afm, mask, el, uf, d)
     for gru, bn in steps:
