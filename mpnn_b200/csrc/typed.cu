@@ -354,6 +354,27 @@ __device__ __forceinline__ void enet_fwd_body(const ENet& n, int fch, float* __r
   const int tid = threadIdx.x;
   const int o = tid >> 2, q = tid & 3;
   const int P = n.P;
+  // A table that fits one chunk: the last Linear's weight goes to shared memory with one wave of async copies issued
+  // HERE, so its L2 / HBM latency hides behind the serial chain of tied layers instead of following it.
+  bool pre_staged = false;
+  if (n.mf * n.nf <= fch && blockIdx.x < n.R) {
+    const int tot = n.mf * n.nf * P, LPp = P | 1;
+    if (LPp == P && (tot & 3) == 0 && (reinterpret_cast<size_t>(n.w_last) & 15) == 0) {
+      for (int i4 = tid; i4 < tot / 4; i4 += 256) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(Wl + i4 * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(n.w_last + i4 * 4) : "memory");
+      }
+    } else {
+      for (int i = tid; i < tot; i += 256) {
+        const int f = i / P, pp = i - f * P;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(Wl + f * LPp + pp);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(n.w_last + i) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pre_staged = true;
+    staged_f0 = 0;
+  }
   // this thread's slice of row o of the tied weight, kept in REGISTERS for all layers and rows:
   // wreg[4j + t] = W[o][16j + 4q + t]   (the 16-byte chunk q of every 64-byte group: conflict-free LDS.128)
   float wreg[16];
@@ -416,6 +437,11 @@ __device__ __forceinline__ void enet_fwd_body(const ENet& n, int fch, float* __r
     const int warp = tid >> 5, lane = tid & 31;
     const int nout = n.mf * n.nf;
     const int LP = P | 1;
+    if (pre_staged) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      pre_staged = false;
+    }
     for (int f0 = 0; f0 < nout; f0 += fch) {
       const int cnt = min(fch, nout - f0);
       if (f0 != staged_f0) {     // single-chunk tables are staged once per CTA
@@ -474,7 +500,8 @@ __device__ __forceinline__ void enet_fwd_body(const ENet& n, int fch, float* __r
 // partial layout per CTA (floats): [PW*PW tied] then for g = G-1 .. 0: [gout*gin weights][gout bias]
 __device__ __forceinline__ void enet_bwd_body(const ENet& n, const float* __restrict__ acts,
                                               const float* __restrict__ dT, float* __restrict__ partial,
-                                              int partial_stride, float* __restrict__ d_rows /*[R, ef] or null*/) {
+                                              int partial_stride, float* __restrict__ d_rows /*[R, ef] or null*/,
+                                              int stage_wl /*1: W_last + the row's dT staged in shared memory*/) {
   __shared__ __align__(16) float D[2][PW];       // delta of the current layer
   __shared__ __align__(16) float Ap[2][PW];      // input activation of the current layer
   __shared__ __align__(16) float dAs[PW];        // un-masked gradient w.r.t. the tied input
@@ -500,10 +527,31 @@ __device__ __forceinline__ void enet_bwd_body(const ENet& n, const float* __rest
 #pragma unroll
     for (int b = 0; b < 4; ++b) accW[a][b] = 0.f;
   float* part = partial + (size_t)blockIdx.x * partial_stride;
-  // growth partials accumulate over the CTA's rows in global memory (own slice): zero them first
-  for (int e = PW * PW + tid; e < partial_stride; e += 256) part[e] = 0.f;
+  // growth partials accumulate over the CTA's rows in global memory (own slice): the first row writes them, a CTA
+  // without rows zeroes them
+  if ((int)blockIdx.x >= n.R)
+    for (int e = PW * PW + tid; e < partial_stride; e += 256) part[e] = 0.f;
   const int nslots = n.G + n.L + 1;
+  // W_last [mf*nf, P] -> shared memory behind the saved activations with one wave of async copies (the dx pre-pass below
+  // would otherwise walk it in eight dependent batches of L2 loads per row)
+  float* Wls = As + (size_t)nslots * PW;
+  float* dTs = Wls + (((size_t)n.mf * n.nf * P + 3) & ~(size_t)3);
+  if (stage_wl && (int)blockIdx.x < n.R) {
+    const int tot = n.mf * n.nf * P;
+    if ((tot & 3) == 0 && (reinterpret_cast<size_t>(n.w_last) & 15) == 0) {
+      for (int i4 = tid; i4 < tot / 4; i4 += 256) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(Wls + i4 * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(n.w_last + i4 * 4) : "memory");
+      }
+    } else {
+      for (int i = tid; i < tot; i += 256) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(Wls + i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(n.w_last + i) : "memory");
+      }
+    }
+  }
   for (int row = blockIdx.x; row < n.R; row += gridDim.x) {
+    const bool first_row = row == (int)blockIdx.x;
     __syncthreads();
     // all saved activations of the row -> shared memory with one wave of 16-byte async copies (the per-layer
     // loads of the 52-layer chain would otherwise pay one L2/HBM latency each); overlapped with the dx pre-pass
@@ -513,9 +561,53 @@ __device__ __forceinline__ void enet_bwd_body(const ENet& n, const float* __rest
       const float* src = acts + ((size_t)slot * n.R + row) * PW + c4 * 4;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
+    if (stage_wl)
+      for (int i4 = tid; i4 < DP * DP / 4; i4 += 256) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(dTs + i4 * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(dT + (size_t)row * DP * DP + i4 * 4)
+                     : "memory");
+      }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // dx[p] = sum_f dT[row][l][k] W_last[f, p]   (f = k*nf + l), f split over the 4 warp pairs
-    {
+    if (stage_wl) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const int p = tid & 63, part_f = tid >> 6;
+      float acc0 = 0.f, acc1 = 0.f;
+      if (p < P) {
+        const int nout = n.mf * n.nf;
+        int k = part_f / n.nf, l = part_f - k * n.nf;
+        int f = part_f;
+#pragma unroll 4
+        for (; f + 4 < nout; f += 8) {
+          const float t0 = dTs[l * DP + k];
+          const float w0 = Wls[(size_t)f * P + p];
+          l += 4;
+          while (l >= n.nf) {
+            l -= n.nf;
+            ++k;
+          }
+          const float t1 = dTs[l * DP + k];
+          const float w1 = Wls[(size_t)(f + 4) * P + p];
+          l += 4;
+          while (l >= n.nf) {
+            l -= n.nf;
+            ++k;
+          }
+          acc0 = fmaf(t0, w0, acc0);
+          acc1 = fmaf(t1, w1, acc1);
+        }
+        for (; f < nout; f += 4) {
+          acc0 = fmaf(dTs[l * DP + k], Wls[(size_t)f * P + p], acc0);
+          l += 4;
+          while (l >= n.nf) {
+            l -= n.nf;
+            ++k;
+          }
+        }
+      }
+      red4[part_f][p] = acc0 + acc1;
+    } else {
       const int p = tid & 63, part_f = tid >> 6;
       float acc = 0.f;
       if (p < P) {
@@ -593,9 +685,13 @@ __device__ __forceinline__ void enet_bwd_body(const ENet& n, const float* __rest
       __syncthreads();
       for (int e = tid; e < gout * gin; e += 256) {
         const int oo = e / gin, ii = e - oo * gin;
-        part[poff + e] += D[0][oo] * Ap[0][ii];
+        const float v = D[0][oo] * Ap[0][ii];
+        part[poff + e] = first_row ? v : part[poff + e] + v;
       }
-      for (int e = tid; e < gout; e += 256) part[poff + (size_t)gout * gin + e] += D[0][e];
+      for (int e = tid; e < gout; e += 256) {
+        const size_t at = poff + (size_t)gout * gin + e;
+        part[at] = first_row ? D[0][e] : part[at] + D[0][e];
+      }
       poff += (size_t)gout * gin + gout;
       float acc = 0.f;
       if (tid < gin) {
@@ -690,8 +786,8 @@ __global__ void __launch_bounds__(256) k_enet_fwd(ENet n, int fch, float* __rest
 }
 __global__ void __launch_bounds__(256) k_enet_bwd(ENet n, const float* __restrict__ acts, const float* __restrict__ dT,
                                                   float* __restrict__ partial, int partial_stride,
-                                                  float* __restrict__ d_rows) {
-  enet_bwd_body(n, acts, dT, partial, partial_stride, d_rows);
+                                                  float* __restrict__ d_rows, int stage_wl) {
+  enet_bwd_body(n, acts, dT, partial, partial_stride, d_rows, stage_wl);
 }
 __global__ void k_enet_finish(const float* __restrict__ partial, int nparts, int stride, ENetDst d, int nb_red,
                               const float* __restrict__ acts_x, const float* __restrict__ dT, int R, int nf, int mf,
@@ -725,9 +821,10 @@ __global__ void __launch_bounds__(256) k_enet_fwd_multi(const __grid_constant__ 
   const int y = blockIdx.y;
   enet_fwd_body(m.n[y], fch, m.acts[y], m.table[y], m.tableT[y]);
 }
-__global__ void __launch_bounds__(256) k_enet_bwd_multi(const __grid_constant__ ENetBwdMulti m, int partial_stride) {
+__global__ void __launch_bounds__(256) k_enet_bwd_multi(const __grid_constant__ ENetBwdMulti m, int partial_stride,
+                                                        int stage_wl) {
   const int y = blockIdx.y;
-  enet_bwd_body(m.n[y], m.acts[y], m.dT[y], m.partial[y], partial_stride, m.d_rows[y]);
+  enet_bwd_body(m.n[y], m.acts[y], m.dT[y], m.partial[y], partial_stride, m.d_rows[y], stage_wl);
 }
 __global__ void k_enet_finish_multi(const __grid_constant__ ENetFinMulti m, int nparts, int stride, int nb_red, int R,
                                     int nf, int mf, int DP) {
@@ -882,8 +979,12 @@ int mpnn_enet_bwd(const float* rows, int R, int ef, int n_growth, const float* c
   float* partial = (float*)workspace;
   const size_t act_smem = (size_t)(n_growth + n_tied + 1) * PW * sizeof(float);
   MPNN_REQUIRE(act_smem <= 160 * 1024, MPNN_ERR_UNSUPPORTED, "enet_bwd: too many layers for the shared-memory stage");
-  MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
-  k_enet_bwd<<<nparts, 256, act_smem, stream>>>(n, saved, dT, partial, stride, d_rows);
+  // the last Linear's weight and the row's table gradient ride behind the activations when they fit
+  const size_t wl_smem = ((((size_t)nf * mf * P + 3) & ~(size_t)3) + (size_t)n.DP * n.DP) * sizeof(float);
+  const int stage_wl = act_smem + wl_smem <= 160 * 1024 ? 1 : 0;
+  const size_t bwd_smem_bytes = act_smem + (stage_wl ? wl_smem : 0);
+  MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes));
+  k_enet_bwd<<<nparts, 256, bwd_smem_bytes, stream>>>(n, saved, dT, partial, stride, d_rows, stage_wl);
   MPNN_CHECK_LAUNCH("k_enet_bwd");
   ENetDst dst;
   memset(&dst, 0, sizeof(dst));
@@ -982,8 +1083,11 @@ int mpnn_enet_bwd_multi(int K, const float* rows, int R, int ef, int n_growth, c
   }
   const int stride = enet_partial_stride(m.n[0]);
   const int nparts = enet_grid(R);
-  MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_smem));
-  k_enet_bwd_multi<<<dim3(nparts, K), 256, act_smem, stream>>>(m, stride);
+  const size_t wl_smem = ((((size_t)nf * mf * P + 3) & ~(size_t)3) + (size_t)m.n[0].DP * m.n[0].DP) * sizeof(float);
+  const int stage_wl = act_smem + wl_smem <= 160 * 1024 ? 1 : 0;
+  const size_t bwd_smem_bytes = act_smem + (stage_wl ? wl_smem : 0);
+  MPNN_CUDA(cudaFuncSetAttribute(k_enet_bwd_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem_bytes));
+  k_enet_bwd_multi<<<dim3(nparts, K), 256, bwd_smem_bytes, stream>>>(m, stride, stage_wl);
   MPNN_CHECK_LAUNCH("k_enet_bwd_multi");
   const int nb_red = ceil_div(stride, 256);
   const int nb_last = ceil_div((long long)mf * nf * (P + 1), 256);
