@@ -228,7 +228,7 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    gs = None
+    gs = gs_io = None
     if use_graph:
         # the whole step (compaction .. optimizer) as ONE CUDA graph over static input buffers
         from mpnn_b200.graphs import GraphedStep
@@ -290,6 +290,20 @@ def run_ours(args):
             copy_stream.wait_event(ev_loaded)  # the staging buffer may be overwritten from here on
             prefetch()                         # next step's H2D overlaps this step's kernels
             return gs.replay()
+
+        gs_io = None
+        if not args.no_host_io:
+            # the same pipeline as ONE graph per step: device copy staging -> static inputs at the head, the step, and the
+            # H2D of the host's pinned buffers into the staging area as a parallel branch (GraphedStep(host_io=True));
+            # the host launches one graph and reads the previous step's loss
+            gs_io = GraphedStep(step, devb, warmup=1, pipeline_prep=pipe, host_io=True)
+            run_e2e_staged, prefetch_staged = run_e2e, prefetch
+
+            def run_e2e():
+                return gs_io.replay()
+
+            def prefetch():
+                pass
     else:
         def run_resident():
             return step(devb)
@@ -412,6 +426,8 @@ def run_ours(args):
         dump_timeline(run_resident, args.timeline)
     if gs is not None:
         gs.check()
+        if gs_io is not None:
+            gs_io.check()
 
     if rank != 0:
         return
@@ -431,9 +447,13 @@ def run_ours(args):
                                       ("NCCL, one flat bucket" if world > 1 else "none (1 GPU)"))},
         "e2e": {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "graphs/s", "h2d_bytes_per_step": gb_in,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps,
-                "pipeline": "H2D of the next padded batch on a copy stream (pinned -> staging) overlapped with the current "
-                            "step; D2D staging -> graph inputs; every step's loss copied D2H (pinned) inside the step and read by the host "
-                            "one step later" if use_graph else "serial H2D; loss copied D2H every step, read one step later"},
+                "pipeline": ("one CUDA graph per step (GraphedStep(host_io=True)): device copy staging -> graph inputs, the step, "
+                             "and the H2D of the host's pinned batch into the staging area as a parallel branch of the same "
+                             "graph; every step's loss copied D2H (pinned) inside the timed region and read by the host one step "
+                             "later" if (use_graph and gs_io is not None) else
+                             "H2D of the next padded batch on a copy stream (pinned -> staging) overlapped with the current "
+                             "step; D2D staging -> graph inputs; every step's loss copied D2H (pinned) inside the step and read by the host "
+                             "one step later") if use_graph else "serial H2D; loss copied D2H every step, read one step later"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
         "median_ms_per_step": med_ms, "median_value": world * B / (med_ms * 1e-3),
     }
@@ -809,6 +829,8 @@ def main():
     ap.add_argument("--stock-head", action="store_true", help="keep the head + loss as stock torch modules")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: NCCL all-reduce + Adam instead of the fused kernel")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one captured CUDA graph")
+    ap.add_argument("--no-host-io", action="store_true",
+                    help="e2e: separate H2D / D2D launches around the step's graph instead of transfers inside the graph")
     ap.add_argument("--no-pipeline-prep", action="store_true",
                     help="compaction / de-duplication at the head of each step instead of one step ahead")
     ap.add_argument("--batch", type=int, default=0, help="graphs per GPU (default: the workload's BASELINE.json batch)")

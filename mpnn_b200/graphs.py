@@ -37,10 +37,17 @@ class GraphedStep(object):
         loss0 = gs.replay()                     # trains on batch0, prepares batch1's edge list
         gs.load(batch1); gs.load_next(batch2)   # batch1's afm / mask / labels ...; batch2's bfm / adj
         loss1 = gs.replay()                     # ...
+
+    host_io=True puts the input transfers INTO the graph: `gs.host[group][1]` are pinned host tensors (views of one flat
+    pinned allocation per input group) the data loader fills; every replay first moves the staged copy of the inputs
+    into the static buffers (device copy), then runs the step while a parallel branch of the same graph copies the host
+    buffers into the staging area for the next replay (H2D from pinned memory, overlapped with the step's kernels).
+    A train step is then ONE graph launch for the host, transfers included.  The host buffers must hold, when replay k
+    is launched, what replay k + 1 consumes (with pipeline_prep: bfm / adj of batch k + 2, the rest of batch k + 1).
     """
 
     def __init__(self, step_fn, example_inputs, warmup=3, headroom=1.25, edge_capacity=None, unique_capacity=None,
-                 pipeline_prep=False):
+                 pipeline_prep=False, host_io=False):
         # static inputs as views of two flat allocations ("bonds": bfm / adj, "rest": everything else), so a batch can be
         # loaded with two device copies whatever its number of tensors (`flat`, `mirror()`)
         dev0 = next(iter(example_inputs.values())).device
@@ -59,6 +66,14 @@ class GraphedStep(object):
             self.static.update(views)
         self.step_fn = step_fn
         self.pipeline_prep = bool(pipeline_prep)
+        self.host_io = bool(host_io)
+        self.host, self.stage = {}, {}
+        if self.host_io:
+            for group in ("bonds", "rest"):
+                self.host[group] = self.mirror(group, device="cpu", pin_memory=True)
+                self.stage[group] = self.mirror(group, device=dev0)
+                self.host[group][0].copy_(self.flat[group])
+                self.stage[group][0].copy_(self.flat[group])
         self.eager_steps = warmup + 1    # executions of step_fn before the capture (warm-up + the arena dry run)
         graph.STATS["E"] = graph.STATS["U"] = graph.STATS["n_real"] = 0
         side = torch.cuda.Stream()
@@ -108,6 +123,8 @@ class GraphedStep(object):
                 _lib.check(lib.mpnn_zero_bytes(_lib.ptr(self.arena), self.arena.numel(), _lib.stream()), "zero_bytes")
                 functional.arena_begin(self.arena)
                 try:
+                    if self.host_io:
+                        self._capture_host_io(dev)
                     if self.pipeline_prep:
                         self._el_nxt = None
                         graph.pin(self.static["bfm"], self.static["adj"], self._el_cur)
@@ -145,6 +162,36 @@ class GraphedStep(object):
             nb = n * torch.empty(0, dtype=dtype).element_size()
             views[k] = flat[off:off + nb].view(dtype).view(shape)
         return flat, views
+
+    def _capture_host_io(self, dev):
+        """(inside the capture, at the head of the step) staged inputs -> static inputs, then, as a parallel branch, the
+        host's pinned buffers -> staging area for the next replay.  With pipeline_prep only the preprocessing branch reads
+        bfm / adj, so their (large) device copy runs on that branch and the step's own chain waits for the small one."""
+        main = torch.cuda.current_stream(dev)
+        root = torch.cuda.Event()
+        root.record(main)
+        self.flat["rest"].copy_(self.stage["rest"][0], non_blocking=True)
+        bonds_done = None
+        if self.pipeline_prep:
+            key7, lane7 = functional._side_stream(dev, lane=7)
+            lane7.wait_event(root)
+            with torch.cuda.stream(lane7):
+                self.flat["bonds"].copy_(self.stage["bonds"][0], non_blocking=True)
+                bonds_done = torch.cuda.Event()
+                bonds_done.record(lane7)
+            functional._FWD_SIDE.add(key7)
+        else:
+            self.flat["bonds"].copy_(self.stage["bonds"][0], non_blocking=True)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        key, lane = functional._side_stream(dev, lane=8)
+        lane.wait_event(fork)
+        if bonds_done is not None:
+            lane.wait_event(bonds_done)
+        with torch.cuda.stream(lane):
+            for group in ("bonds", "rest"):
+                self.stage[group][0].copy_(self.host[group][0], non_blocking=True)
+        functional._FWD_SIDE.add(key)
 
     def _capture_prep_branch(self, dev):
         """(inside the capture) the NEXT batch's compaction / de-duplication / type sort on a side lane forked from the

@@ -285,6 +285,56 @@ def test_pipelined_prep_equals_plain_captured_step(dev):
     assert len(set(losses["plain"][:5])) == 5      # the batches really differ
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_host_io_graph_equals_plain_captured_step(dev, pipelined):
+    """GraphedStep(host_io=True): the H2D of the host's pinned buffers and the device copy into the static inputs are
+    nodes of the step's graph.  Over a sequence of different batches fed through the pinned buffers the losses and the
+    parameters equal the plain captured step's (with and without the pipelined preprocessing)."""
+    from mpnn_b200 import graph, graphs, optim
+    seq = _padded_batches(dev, 4, 40, 12)
+    order = [0, 1, 2, 3, 1, 0]
+    losses, finals = {}, {}
+    for mode in ("plain", "host_io"):
+        graph.clear_cache()
+        mod = _model("normed", dev, 16, 7, 12, 3, seed=11)
+        opt = optim.FusedAdam(list(mod.parameters()), lr=1e-3)
+
+        def step_fn(b):
+            graph.clear_cache()
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(mod(b["afm"], b["bfm"], b["adj"], b["mask"]), b["labels"])
+            loss.backward()
+            opt.step()
+            return loss
+
+        if mode == "plain":
+            gs = graphs.GraphedStep(step_fn, seq[0], warmup=3, edge_capacity=4096, unique_capacity=64)
+            ls = [float(gs(seq[i])) for i in order]
+        else:
+            gs = graphs.GraphedStep(step_fn, seq[0], warmup=3, edge_capacity=4096, unique_capacity=64,
+                                    pipeline_prep=pipelined, host_io=True)
+            at = lambda k: seq[order[min(k, len(order) - 1)]]
+
+            def fill(views, batch, keys):
+                for k_ in keys:
+                    views[k_].copy_(batch[k_])
+
+            if pipelined:   # the staged bfm / adj are one batch ahead of the staged afm / mask / labels
+                fill(gs.stage["bonds"][1], at(1), ("bfm", "adj"))
+            ls = []
+            for k in range(len(order)):
+                torch.cuda.synchronize()        # the previous replay has read the pinned buffers
+                fill(gs.host["bonds"][1], at(k + 2) if pipelined else at(k + 1), ("bfm", "adj"))
+                fill(gs.host["rest"][1], at(k + 1), ("afm", "mask", "labels"))
+                ls.append(float(gs.replay()))
+        gs.check()
+        losses[mode] = ls
+        finals[mode] = [p.detach().clone() for p in mod.parameters()]
+    assert losses["plain"] == losses["host_io"], losses
+    for a, b in zip(finals["plain"], finals["host_io"]):
+        assert torch.equal(a, b)
+
+
 def test_pipelined_prep_overflow_flag_is_sticky(dev):
     """an overflowing batch anywhere in the replayed sequence is reported by check(), and its update is skipped"""
     from mpnn_b200 import graph, graphs, optim

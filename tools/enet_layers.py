@@ -7,7 +7,7 @@ import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mpnn_b200 import _lib
-from mpnn_b200.functional import EdgeNetTableFn
+from mpnn_b200.functional import EdgeNetTableFn, MultiEdgeNetTableFn
 
 
 def main():
@@ -23,12 +23,19 @@ def main():
     gw = (torch.randn(P, ef, device=dev) * 0.3).requires_grad_(True)
     gb = torch.zeros(P, device=dev, requires_grad=True)
     params = [w_tied, W_last, B_last, gw, gb]
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    multi = []
+    for k in range(K):
+        multi += [(p_.detach().clone() + 0.01 * k).requires_grad_(True) for p_ in params]
 
     def fwd(L):
+        if K > 1:    # K sibling networks in one launch each way (one EdgeNetwork per message-passing step)
+            outs = MultiEdgeNetTableFn.apply(urows, L, nf, nf, K, 1, *multi)
+            return torch.stack([outs[2 * k] for k in range(K)]).sum(0)
         return EdgeNetTableFn.apply(urows, w_tied, L, W_last, B_last, nf, nf, gw, gb)[0]
 
     def both(L):
-        for p_ in params:
+        for p_ in params + multi:
             p_.grad = None
         t = fwd(L)
         t.backward(gones)
