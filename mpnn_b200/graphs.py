@@ -106,7 +106,9 @@ class GraphedStep(object):
         functional._FWD_SIDE.clear()
         lib = _lib.load()
         dev = next(iter(self.static.values())).device
-        self._sticky = None
+        # overflow flags of every replay since the last check(), OR-ed on the device (the per-step counts are cleared or
+        # overwritten by the next replay)
+        self._sticky = torch.zeros(1, dtype=torch.int32, device=dev)
         with graph.capacities(self.edge_capacity, self.unique_capacity):
             if self.pipeline_prep:
                 # the edge list the FIRST replay trains on, built eagerly; every replay hands the next one over
@@ -115,7 +117,6 @@ class GraphedStep(object):
                 torch.cuda.synchronize()
                 del graph._CAPTURED_COUNTS[:]
                 self._el_cur._typed.sort_event = None       # (recorded outside the capture; the work is finished)
-                self._sticky = torch.zeros(1, dtype=torch.int32, device=dev)
             # captured on the stream the warm-up steps ran on: the per-stream persistent workspaces (_lib.clean_workspace) of
             # the warm-up are the capture's, so no zero-fill of a fresh workspace lands in the graph
             with torch.cuda.graph(self.graph, stream=side):
@@ -139,6 +140,9 @@ class GraphedStep(object):
                     uses = graph.unpin()
                     del functional.AFTER_CHAIN_FWD[:]
                 functional.join_side_streams()   # no forked branch may outlive the capture
+                if not self.pipeline_prep:
+                    for c in graph._CAPTURED_COUNTS:
+                        self._sticky.bitwise_or_(c[2:3])
                 if self.pipeline_prep:
                     if not uses:
                         raise RuntimeError("mpnn_b200.GraphedStep(pipeline_prep=True): the step never asked for the "
@@ -236,15 +240,11 @@ class GraphedStep(object):
         """One small D2H read: did any batch replayed since the last check exceed the captured edge / distinct-row
         capacities?  (Kernels clamp their reads to the capacities, so an overflowing batch computes on a truncated edge
         list; the step's result must be discarded by the caller.)"""
-        if self._sticky is not None and int(self._sticky.item()):
+        if int(self._sticky.item()):
             self._sticky.zero_()
-            raise RuntimeError("mpnn_b200.GraphedStep: a replayed batch exceeded the captured capacities (%d edges / "
-                               "%d distinct bond rows); re-capture with larger capacities"
-                               % (self.edge_capacity, self.unique_capacity))
-        for c in self._counts:
-            e, u, flag, _ = c.cpu().tolist()
-            if flag:
-                c[2] = 0     # the flag is sticky on the device (set by any replay since the last check): clear it here
-                raise RuntimeError("mpnn_b200.GraphedStep: batch with %d edges / %d distinct bond rows exceeds the "
-                                   "captured capacities (%d / %d); re-capture with larger capacities"
-                                   % (e, u, self.edge_capacity, self.unique_capacity))
+            last = [c.cpu().tolist() for c in self._counts]
+            raise RuntimeError("mpnn_b200.GraphedStep: a batch replayed since the last check exceeded the captured "
+                               "capacities (%d edges / %d distinct bond rows; the most recent edge lists hold %s); "
+                               "re-capture with larger capacities"
+                               % (self.edge_capacity, self.unique_capacity,
+                                  ", ".join("%d / %d" % (c[0], c[1]) for c in last) or "-"))

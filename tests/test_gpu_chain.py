@@ -285,6 +285,41 @@ def test_pipelined_prep_equals_plain_captured_step(dev):
     assert len(set(losses["plain"][:5])) == 5      # the batches really differ
 
 
+def test_overflow_flag_survives_later_replays(dev):
+    """plain captured step: an overflowing batch in the MIDDLE of a replayed sequence skips its update on the device and
+    is still reported by the next check(), although later replays rewrite the per-step counts"""
+    from mpnn_b200 import graph, graphs, optim
+    seq = _padded_batches(dev, 2, 40, 12)
+    graph.clear_cache()
+    mod = _model("normed", dev, 16, 7, 12, 3, seed=11)
+    opt = optim.FusedAdam(list(mod.parameters()), lr=1e-3)
+
+    def step_fn(b):
+        graph.clear_cache()
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(mod(b["afm"], b["bfm"], b["adj"], b["mask"]), b["labels"])
+        loss.backward()
+        opt.step()
+        return loss
+
+    small = {k: v.clone() for k, v in seq[0].items()}
+    small["bfm"][20:] = 0
+    small["adj"][20:] = 0
+    e_small = int(((small["bfm"] != 0).any(-1) | (small["adj"] != 0)).sum())
+    gs = graphs.GraphedStep(step_fn, small, warmup=3, edge_capacity=e_small + 64, unique_capacity=64)
+    gs(small)
+    gs.check()
+    before = [p.detach().clone() for p in mod.parameters()]
+    gs(seq[1])                       # overflows: the update is gated off
+    for a, b in zip(before, [p.detach().clone() for p in mod.parameters()]):
+        assert torch.equal(a, b)
+    gs(small)
+    gs(small)
+    with pytest.raises(RuntimeError, match="capacit"):
+        gs.check()
+    gs.check()
+
+
 @pytest.mark.parametrize("pipelined", [False, True])
 def test_host_io_graph_equals_plain_captured_step(dev, pipelined):
     """GraphedStep(host_io=True): the H2D of the host's pinned buffers and the device copy into the static inputs are
