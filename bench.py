@@ -424,6 +424,8 @@ def run_ours(args):
     launches = count_launches(run_resident)
     if args.timeline and rank == 0:
         dump_timeline(run_resident, args.timeline)
+        if gs_io is not None:       # the e2e step (transfers inside the graph)
+            dump_timeline(gs_io.replay, args.timeline + ".e2e")
     if gs is not None:
         gs.check()
         if gs_io is not None:
