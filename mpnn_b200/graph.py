@@ -105,6 +105,10 @@ class capacities(object):
         global _CAPACITY
         self.prev = _CAPACITY
         _CAPACITY = self.cap
+        if self.prev is None:
+            # a new capacity session: the overflow guards the optimizer consults (optim.FusedAdam.step) are those of the
+            # edge lists built INSIDE it, never the flags an earlier session left behind
+            del _CAPTURED_COUNTS[:]
         return self
 
     def __exit__(self, *exc):
