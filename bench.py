@@ -422,7 +422,10 @@ def run_ours(args):
             others = other_config_points(dev, flush)
     # every rank replays the step here (it contains the gradient all-reduce when N > 1); rank 0 keeps the count
     launches = count_launches(run_resident)
-    if args.timeline and rank == 0:
+    if args.timeline and world > 1 and rank == 0:
+        # (the replayed step holds the fused all-reduce: one rank replaying alone would wait for its peers for ever)
+        sys.stderr.write("bench.py: --timeline is a single-GPU option, skipped at %d GPUs\n" % world)
+    if args.timeline and rank == 0 and world == 1:
         dump_timeline(run_resident, args.timeline)
         if gs_io is not None:       # the e2e step (transfers inside the graph)
             dump_timeline(gs_io.replay, args.timeline + ".e2e")
