@@ -334,3 +334,23 @@ def test_dropin_encoders_state_dict_contract():
             theirs = [v for k, v in vars(mod).items() if k.endswith("AutoEncoder")][0]()
             assert {k: tuple(v.shape) for k, v in theirs.state_dict().items()} == \
                 {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+
+
+def test_edge_list_slab_views_are_aligned_and_disjoint():
+    """graph._slab_views (the one-allocation edge list of the pipelined preprocessing): consecutive views, each starting
+    on a 256-byte boundary, none overlapping, every requested length honoured"""
+    import torch
+    from mpnn_b200 import graph
+    sizes = [7425, 7425, 10794, 10794, 10794, 10794, 10794, 65 * 7, 4, 65, 10794, 10794, 1, 63, 64, 65]
+    slab = torch.zeros(sum((n + 63) // 64 * 64 for n in sizes), dtype=torch.int32)
+    views = graph._slab_views(slab, sizes)
+    assert [v.numel() for v in views] == sizes
+    end = 0
+    for i, v in enumerate(views):
+        off = v.storage_offset()
+        assert off % 64 == 0 and off >= end, (i, off, end)       # 64 int32 = 256 bytes
+        end = off + v.numel()
+        v.fill_(i + 1)
+    assert end <= slab.numel()
+    for i, v in enumerate(views):
+        assert bool((v == i + 1).all())
